@@ -1,0 +1,947 @@
+// ygl_api.cpp — the C ABI of include/ygl_b200.h: device arenas, the wavefront driver loop,
+// batch intersection, and the multi-GPU tile gather. Host C++ only; all device work goes through
+// the launch_* entry points of ygl_kernels.cu. There is no CPU fallback anywhere in this file:
+// without a usable CUDA device every rendering call fails with YGL_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ygl_b200.h"
+#include "ygl_build.h"
+#include "ygl_kernels.cuh"
+
+using namespace ygl;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t err__ = (expr);                                                                     \
+    if (err__ != cudaSuccess)                                                                       \
+      return fail(YGL_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorName(err__) + " (" +      \
+                                    cudaGetErrorString(err__) + ") at " #expr);                     \
+  } while (0)
+
+// A host-built byte arena uploaded with one cudaMemcpy; sub-allocations are 256-B aligned so every
+// float4 / packet array starts on a sector boundary.
+struct Arena {
+  std::vector<uint8_t> host;
+  uint8_t*             dev = nullptr;
+  size_t add(const void* data, size_t bytes) {
+    size_t off = (host.size() + 255) & ~size_t(255);
+    host.resize(off + bytes);
+    if (bytes && data) memcpy(host.data() + off, data, bytes);
+    return off;
+  }
+  template <typename T>
+  const T* ptr(size_t off) const {
+    return (const T*)(dev + off);
+  }
+  cudaError_t upload() {
+    if (host.empty()) host.resize(256);
+    cudaError_t e = cudaMalloc((void**)&dev, host.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice);
+  }
+  void release() {
+    if (dev) cudaFree(dev);
+    dev = nullptr;
+  }
+};
+
+}  // namespace
+
+struct ygl_context {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  int          num_sms = 0;
+  // scratch queues sized for the largest state seen
+  int       queue_lanes = 0;
+  int*      queue_mem   = nullptr;
+  Counters* counters    = nullptr;
+  int*      h_done      = nullptr;  // pinned
+  cudaEvent_t ev[2]     = {nullptr, nullptr};
+  uint64_t  stats[8]    = {0};
+  // binding cache: DShape table for a (scene, bvh, lights) triple
+  const ygl_scene*  bound_scene  = nullptr;
+  const ygl_bvh*    bound_bvh    = nullptr;
+  const ygl_lights* bound_lights = nullptr;
+  uint64_t          bound_epoch  = 0;
+  DShape*           d_shapes     = nullptr;
+  DLight*           d_lights     = nullptr;
+  DScene            dscene       = {};
+  // nccl
+  void* nccl_lib  = nullptr;
+  void* nccl_comm = nullptr;
+  int   rank = 0, nranks = 1;
+};
+
+struct ygl_scene {
+  Arena arena;
+  int   device = 0;
+  // offsets
+  size_t off_cameras = 0, off_instances = 0, off_materials = 0, off_environments = 0, off_textures = 0;
+  int    num_cameras = 0, num_instances = 0, num_materials = 0, num_environments = 0, num_textures = 0,
+      num_shapes = 0;
+  struct ShapeOff {
+    size_t points, lines, triangles, quads, positions, normals, texcoords, colors, radius;
+    int    np, nl, nt, nq, nnormals, ntexcoords, ncolors, nradius;
+  };
+  std::vector<ShapeOff> shapes;
+  uint64_t              epoch = 0;
+};
+
+struct ygl_bvh {
+  HostBvh host;
+  // device copy (made on first use)
+  mutable Arena arena;
+  mutable bool  uploaded = false;
+  mutable std::vector<size_t> off_nodes, off_packets, off_prims;
+  mutable size_t off_top_nodes = 0, off_top_packets = 0, off_top_prims = 0, off_inst_packets = 0;
+};
+
+struct ygl_lights {
+  std::vector<HostLight> host;
+  mutable Arena          arena;
+  mutable bool           uploaded = false;
+  mutable std::vector<size_t> off_cdf;
+};
+
+struct ygl_state {
+  ygl_context* ctx   = nullptr;
+  int          width = 0, height = 0, samples = 0;
+  int          row_begin = 0, row_end = 0;
+  PathState    st    = {};
+  uint8_t*     mem   = nullptr;
+};
+
+static uint64_t g_epoch = 1;
+
+extern "C" {
+
+const char* ygl_last_error(void) { return g_error.c_str(); }
+const char* ygl_version(void) { return "ygl_b200 0.1 (sm_100a wavefront path tracer)"; }
+
+void ygl_trace_params_default(ygl_trace_params* p) {
+  *p            = ygl_trace_params{};
+  p->camera     = 0;
+  p->resolution = 1280;
+  p->sampler    = YGL_SAMPLER_PATH;
+  p->falsecolor = YGL_FALSECOLOR_COLOR;
+  p->samples    = 512;
+  p->bounces    = 8;
+  p->clamp      = 10;
+  p->seed       = YGL_DEFAULT_SEED;
+  p->pratio     = 8;
+  p->batch      = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+int ygl_context_create(int device, ygl_context** out) {
+  if (!out) return fail(YGL_ERR_INVALID, "null output");
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(YGL_ERR_CUDA, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  auto ctx    = std::make_unique<ygl_context>();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc((void**)&ctx->counters, sizeof(Counters)));
+  CUDA_TRY(cudaMemset(ctx->counters, 0, sizeof(Counters)));
+  CUDA_TRY(cudaHostAlloc((void**)&ctx->h_done, 2 * sizeof(int), cudaHostAllocDefault));
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));
+  *out = ctx.release();
+  return YGL_OK;
+}
+
+void ygl_comm_destroy(ygl_context* ctx);
+
+void ygl_context_destroy(ygl_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  ygl_comm_destroy(ctx);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->queue_mem) cudaFree(ctx->queue_mem);
+  if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->h_done) cudaFreeHost(ctx->h_done);
+  if (ctx->d_shapes) cudaFree(ctx->d_shapes);
+  if (ctx->d_lights) cudaFree(ctx->d_lights);
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int ygl_context_synchronize(ygl_context* ctx) {
+  if (!ctx) return fail(YGL_ERR_INVALID, "null context");
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return YGL_OK;
+}
+void* ygl_context_stream(ygl_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+static int check_desc(const ygl_scene_desc* d) {
+  if (!d) return fail(YGL_ERR_INVALID, "null scene description");
+  for (int i = 0; i < d->num_instances; i++) {
+    if (d->instances[i].shape < 0 || d->instances[i].shape >= d->num_shapes)
+      return fail(YGL_ERR_INVALID, "instance shape id out of range");
+    if (d->instances[i].material < 0 || d->instances[i].material >= d->num_materials)
+      return fail(YGL_ERR_INVALID, "instance material id out of range");
+  }
+  auto texok = [&](int t) { return t == YGL_INVALID_ID || (t >= 0 && t < d->num_textures); };
+  for (int i = 0; i < d->num_materials; i++) {
+    auto& m = d->materials[i];
+    if (!texok(m.emission_tex) || !texok(m.color_tex) || !texok(m.roughness_tex) || !texok(m.scattering_tex) ||
+        !texok(m.normal_tex))
+      return fail(YGL_ERR_INVALID, "material texture id out of range");
+  }
+  for (int i = 0; i < d->num_environments; i++)
+    if (!texok(d->environments[i].emission_tex)) return fail(YGL_ERR_INVALID, "environment texture id out of range");
+  return YGL_OK;
+}
+
+static DCamera to_dcamera(const ygl_camera& c) {
+  DCamera d;
+  memcpy(&d.frame, &c.frame, sizeof(frame3));
+  d.orthographic = c.orthographic;
+  d.lens = c.lens, d.film = c.film, d.aspect = c.aspect, d.focus = c.focus, d.aperture = c.aperture;
+  return d;
+}
+
+int ygl_scene_create(ygl_context* ctx, const ygl_scene_desc* desc, ygl_scene** out) {
+  if (!ctx || !out) return fail(YGL_ERR_INVALID, "null argument");
+  if (int rc = check_desc(desc)) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto scene    = std::make_unique<ygl_scene>();
+  scene->device = ctx->device;
+  scene->epoch  = g_epoch++;
+  Arena& A      = scene->arena;
+
+  std::vector<DCamera> cams(desc->num_cameras);
+  for (int i = 0; i < desc->num_cameras; i++) cams[i] = to_dcamera(desc->cameras[i]);
+  scene->off_cameras = A.add(cams.data(), cams.size() * sizeof(DCamera));
+  scene->num_cameras = desc->num_cameras;
+
+  std::vector<DInstance> insts(desc->num_instances);
+  for (int i = 0; i < desc->num_instances; i++) {
+    memcpy(&insts[i].frame, &desc->instances[i].frame, sizeof(frame3));
+    insts[i].shape = desc->instances[i].shape, insts[i].material = desc->instances[i].material;
+    insts[i].pad0 = insts[i].pad1 = 0;
+  }
+  scene->off_instances = A.add(insts.data(), insts.size() * sizeof(DInstance));
+  scene->num_instances = desc->num_instances;
+
+  static_assert(sizeof(DMaterial) == sizeof(ygl_material), "material layout");
+  scene->off_materials = A.add(desc->materials, (size_t)desc->num_materials * sizeof(DMaterial));
+  scene->num_materials = desc->num_materials;
+
+  std::vector<DEnvironment> envs(desc->num_environments);
+  for (int i = 0; i < desc->num_environments; i++) {
+    auto& e = desc->environments[i];
+    memcpy(&envs[i].frame, &e.frame, sizeof(frame3));
+    envs[i].inv_frame    = frame_inverse(envs[i].frame, false);  // inverse(environment.frame), yocto_scene.cpp:598
+    envs[i].emission     = {e.emission[0], e.emission[1], e.emission[2]};
+    envs[i].emission_tex = e.emission_tex;
+  }
+  scene->off_environments = A.add(envs.data(), envs.size() * sizeof(DEnvironment));
+  scene->num_environments = desc->num_environments;
+
+  // textures: pixel arrays first, table patched after upload
+  std::vector<size_t> tex_off(desc->num_textures);
+  for (int i = 0; i < desc->num_textures; i++) {
+    auto&  t = desc->textures[i];
+    size_t n = (size_t)t.width * t.height;
+    if (t.pixelsf)
+      tex_off[i] = A.add(t.pixelsf, n * 16);
+    else if (t.pixelsb)
+      tex_off[i] = A.add(t.pixelsb, n * 4);
+    else if (n)
+      return fail(YGL_ERR_INVALID, "texture without pixels");
+  }
+  scene->off_textures = A.add(nullptr, (size_t)desc->num_textures * sizeof(DTexture));
+  scene->num_textures = desc->num_textures;
+
+  scene->num_shapes = desc->num_shapes;
+  scene->shapes.resize(desc->num_shapes);
+  for (int i = 0; i < desc->num_shapes; i++) {
+    auto& s = desc->shapes[i];
+    auto& o = scene->shapes[i];
+    o.np = s.num_points, o.nl = s.num_lines, o.nt = s.num_triangles, o.nq = s.num_quads;
+    o.nnormals = s.num_normals, o.ntexcoords = s.num_texcoords, o.ncolors = s.num_colors, o.nradius = s.num_radius;
+    o.points    = A.add(s.points, (size_t)s.num_points * 4);
+    o.lines     = A.add(s.lines, (size_t)s.num_lines * 8);
+    o.triangles = A.add(s.triangles, (size_t)s.num_triangles * 12);
+    o.quads     = A.add(s.quads, (size_t)s.num_quads * 16);
+    o.positions = A.add(s.positions, (size_t)s.num_positions * 12);
+    o.normals   = A.add(s.normals, (size_t)s.num_normals * 12);
+    o.texcoords = A.add(s.texcoords, (size_t)s.num_texcoords * 8);
+    o.colors    = A.add(s.colors, (size_t)s.num_colors * 16);
+    o.radius    = A.add(s.radius, (size_t)s.num_radius * 4);
+  }
+  // patch the texture table with device pointers: allocate first to learn the base address
+  if (A.host.empty()) A.host.resize(256);
+  CUDA_TRY(cudaMalloc((void**)&A.dev, A.host.size()));
+  for (int i = 0; i < desc->num_textures; i++) {
+    auto&    t = desc->textures[i];
+    DTexture d = {t.width, t.height, t.linear, t.nearest, t.clamp, 0, nullptr, nullptr};
+    if (t.pixelsf) d.pixelsf = A.ptr<float4>(tex_off[i]);
+    else if (t.pixelsb) d.pixelsb = A.ptr<uchar4>(tex_off[i]);
+    memcpy(A.host.data() + scene->off_textures + i * sizeof(DTexture), &d, sizeof(DTexture));
+  }
+  CUDA_TRY(cudaMemcpy(A.dev, A.host.data(), A.host.size(), cudaMemcpyHostToDevice));
+  A.host.clear();
+  A.host.shrink_to_fit();
+  *out = scene.release();
+  return YGL_OK;
+}
+
+int ygl_scene_update_cameras(ygl_scene* scene, const ygl_camera* cameras, int num_cameras) {
+  if (!scene || !cameras) return fail(YGL_ERR_INVALID, "null argument");
+  if (num_cameras != scene->num_cameras) return fail(YGL_ERR_INVALID, "camera count mismatch");
+  CUDA_TRY(cudaSetDevice(scene->device));
+  std::vector<DCamera> cams(num_cameras);
+  for (int i = 0; i < num_cameras; i++) cams[i] = to_dcamera(cameras[i]);
+  CUDA_TRY(cudaMemcpy(scene->arena.dev + scene->off_cameras, cams.data(), cams.size() * sizeof(DCamera),
+      cudaMemcpyHostToDevice));
+  return YGL_OK;
+}
+
+void ygl_scene_destroy(ygl_scene* scene) {
+  if (!scene) return;
+  cudaSetDevice(scene->device);
+  scene->arena.release();
+  delete scene;
+}
+
+// ------------------------------------------------------------------------------------------
+int ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
+  if (!out) return fail(YGL_ERR_INVALID, "null output");
+  if (int rc = check_desc(desc)) return rc;
+  auto        bvh = std::make_unique<ygl_bvh>();
+  std::string error;
+  if (!build_scene_bvh(*desc, highquality != 0, bvh->host, error)) return fail(YGL_ERR_INVALID, error);
+  *out = bvh.release();
+  return YGL_OK;
+}
+static const HostTree* pick_tree(const ygl_bvh* bvh, int shape) {
+  if (shape < 0) return &bvh->host.top;
+  if (shape >= (int)bvh->host.shapes.size()) return nullptr;
+  return &bvh->host.shapes[shape];
+}
+int ygl_bvh_tree_size(const ygl_bvh* bvh, int shape, int* num_nodes, int* num_primitives) {
+  if (!bvh) return fail(YGL_ERR_INVALID, "null bvh");
+  auto tree = pick_tree(bvh, shape);
+  if (!tree) return fail(YGL_ERR_INVALID, "shape id out of range");
+  if (num_nodes) *num_nodes = (int)tree->nodes.size();
+  if (num_primitives) *num_primitives = (int)tree->prims.size();
+  return YGL_OK;
+}
+int ygl_bvh_tree_get(const ygl_bvh* bvh, int shape, ygl_bvh_node* nodes, int32_t* primitives) {
+  if (!bvh) return fail(YGL_ERR_INVALID, "null bvh");
+  auto tree = pick_tree(bvh, shape);
+  if (!tree) return fail(YGL_ERR_INVALID, "shape id out of range");
+  if (nodes) memcpy(nodes, tree->nodes.data(), tree->nodes.size() * sizeof(ygl_bvh_node));
+  if (primitives) memcpy(primitives, tree->prims.data(), tree->prims.size() * sizeof(int32_t));
+  return YGL_OK;
+}
+void ygl_bvh_destroy(ygl_bvh* bvh) {
+  if (!bvh) return;
+  bvh->arena.release();
+  delete bvh;
+}
+
+static int bvh_upload(const ygl_bvh* bvh) {
+  if (bvh->uploaded) return YGL_OK;
+  Arena& A  = bvh->arena;
+  auto&  H  = bvh->host;
+  size_t ns = H.shapes.size();
+  bvh->off_nodes.resize(ns), bvh->off_packets.resize(ns), bvh->off_prims.resize(ns);
+  for (size_t i = 0; i < ns; i++) {
+    bvh->off_nodes[i]   = A.add(H.shape_nodes[i].data(), H.shape_nodes[i].size() * 16);
+    bvh->off_packets[i] = A.add(H.shape_packets[i].data(), H.shape_packets[i].size() * 16);
+    bvh->off_prims[i]   = A.add(H.shapes[i].prims.data(), H.shapes[i].prims.size() * 4);
+  }
+  bvh->off_top_nodes    = A.add(H.top_nodes.data(), H.top_nodes.size() * 16);
+  bvh->off_top_packets  = A.add(H.top_packets.data(), H.top_packets.size() * 16);
+  bvh->off_top_prims    = A.add(H.top.prims.data(), H.top.prims.size() * 4);
+  bvh->off_inst_packets = A.add(H.inst_packets.data(), H.inst_packets.size() * 16);
+  CUDA_TRY(A.upload());
+  A.host.clear();
+  A.host.shrink_to_fit();
+  bvh->uploaded = true;
+  return YGL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int ygl_lights_create(const ygl_scene_desc* desc, ygl_lights** out) {
+  if (!out) return fail(YGL_ERR_INVALID, "null output");
+  if (int rc = check_desc(desc)) return rc;
+  auto lights = std::make_unique<ygl_lights>();
+  build_lights(*desc, lights->host);
+  *out = lights.release();
+  return YGL_OK;
+}
+int ygl_lights_count(const ygl_lights* lights) { return lights ? (int)lights->host.size() : 0; }
+int ygl_lights_get(const ygl_lights* lights, int i, int* instance, int* environment, int* cdf_size, float* cdf) {
+  if (!lights || i < 0 || i >= (int)lights->host.size()) return fail(YGL_ERR_INVALID, "light id out of range");
+  auto& l = lights->host[i];
+  if (instance) *instance = l.instance;
+  if (environment) *environment = l.environment;
+  if (cdf_size) *cdf_size = (int)l.cdf.size();
+  if (cdf) memcpy(cdf, l.cdf.data(), l.cdf.size() * sizeof(float));
+  return YGL_OK;
+}
+void ygl_lights_destroy(ygl_lights* lights) {
+  if (!lights) return;
+  lights->arena.release();
+  delete lights;
+}
+static int lights_upload(const ygl_lights* lights) {
+  if (lights->uploaded) return YGL_OK;
+  Arena& A = lights->arena;
+  lights->off_cdf.resize(lights->host.size());
+  for (size_t i = 0; i < lights->host.size(); i++)
+    lights->off_cdf[i] = A.add(lights->host[i].cdf.data(), lights->host[i].cdf.size() * 4);
+  CUDA_TRY(A.upload());
+  A.host.clear();
+  A.host.shrink_to_fit();
+  lights->uploaded = true;
+  return YGL_OK;
+}
+
+// Assemble the DScene for a (scene, bvh, lights) triple; cached on the context.
+static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_lights* lights) {
+  if (!scene || !bvh) return fail(YGL_ERR_INVALID, "null scene or bvh");
+  if (scene->device != ctx->device) return fail(YGL_ERR_INVALID, "scene lives on another device");
+  if ((int)bvh->host.shapes.size() != scene->num_shapes ||
+      (int)(bvh->host.inst_packets.size() / 4) != scene->num_instances)
+    return fail(YGL_ERR_INVALID, "bvh was built for a different scene");
+  if (ctx->bound_scene == scene && ctx->bound_bvh == bvh && ctx->bound_lights == lights &&
+      ctx->bound_epoch == scene->epoch)
+    return YGL_OK;
+  if (int rc = bvh_upload(bvh)) return rc;
+  if (lights)
+    if (int rc = lights_upload(lights)) return rc;
+  const Arena& S = scene->arena;
+  const Arena& B = bvh->arena;
+  std::vector<DShape> shapes(scene->num_shapes);
+  for (int i = 0; i < scene->num_shapes; i++) {
+    auto&   o = scene->shapes[i];
+    DShape& d = shapes[i];
+    d.nodes     = B.ptr<float4>(bvh->off_nodes[i]);
+    d.packets   = B.ptr<float4>(bvh->off_packets[i]);
+    d.prims     = B.ptr<int>(bvh->off_prims[i]);
+    d.num_nodes = (int)bvh->host.shapes[i].nodes.size();
+    d.bvh_kind  = bvh->host.shape_kind[i];
+    d.eval_kind = o.nt > 0 ? kElemTriangles : o.nq > 0 ? kElemQuads : o.nl > 0 ? kElemLines : o.np > 0 ? kElemPoints : kElemNone;
+    d.pad0      = 0;
+    d.points    = S.ptr<int>(o.points);
+    d.lines     = S.ptr<int>(o.lines);
+    d.triangles = S.ptr<int>(o.triangles);
+    d.quads     = S.ptr<int>(o.quads);
+    d.positions = S.ptr<float>(o.positions);
+    d.normals   = o.nnormals ? S.ptr<float>(o.normals) : nullptr;
+    d.texcoords = o.ntexcoords ? S.ptr<float>(o.texcoords) : nullptr;
+    d.colors    = o.ncolors ? S.ptr<float>(o.colors) : nullptr;
+    d.radius    = o.nradius ? S.ptr<float>(o.radius) : nullptr;
+    d.num_points = o.np, d.num_lines = o.nl, d.num_triangles = o.nt, d.num_quads = o.nq;
+  }
+  if (ctx->d_shapes) cudaFree(ctx->d_shapes), ctx->d_shapes = nullptr;
+  if (ctx->d_lights) cudaFree(ctx->d_lights), ctx->d_lights = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&ctx->d_shapes, std::max<size_t>(1, shapes.size()) * sizeof(DShape)));
+  CUDA_TRY(cudaMemcpy(ctx->d_shapes, shapes.data(), shapes.size() * sizeof(DShape), cudaMemcpyHostToDevice));
+  int nlights = lights ? (int)lights->host.size() : 0;
+  if (nlights) {
+    std::vector<DLight> dl(nlights);
+    for (int i = 0; i < nlights; i++) {
+      auto& l = lights->host[i];
+      dl[i]   = {l.instance, l.environment, lights->arena.ptr<float>(lights->off_cdf[i]), (int)l.cdf.size(), 0};
+    }
+    CUDA_TRY(cudaMalloc((void**)&ctx->d_lights, dl.size() * sizeof(DLight)));
+    CUDA_TRY(cudaMemcpy(ctx->d_lights, dl.data(), dl.size() * sizeof(DLight), cudaMemcpyHostToDevice));
+  }
+  DScene& D          = ctx->dscene;
+  D.cameras          = S.ptr<DCamera>(scene->off_cameras);
+  D.instances        = S.ptr<DInstance>(scene->off_instances);
+  D.inst_packets     = B.ptr<DInstancePacket>(bvh->off_inst_packets);
+  D.materials        = S.ptr<DMaterial>(scene->off_materials);
+  D.environments     = S.ptr<DEnvironment>(scene->off_environments);
+  D.textures         = S.ptr<DTexture>(scene->off_textures);
+  D.shapes           = ctx->d_shapes;
+  D.num_cameras      = scene->num_cameras;
+  D.num_instances    = scene->num_instances;
+  D.num_materials    = scene->num_materials;
+  D.num_environments = scene->num_environments;
+  D.num_textures     = scene->num_textures;
+  D.num_shapes       = scene->num_shapes;
+  D.top_nodes        = B.ptr<float4>(bvh->off_top_nodes);
+  D.top_packets      = B.ptr<DInstancePacket>(bvh->off_top_packets);
+  D.top_prims        = B.ptr<int>(bvh->off_top_prims);
+  D.top_num_nodes    = (int)bvh->host.top.nodes.size();
+  D.lights           = ctx->d_lights;
+  D.num_lights       = nlights;
+  ctx->bound_scene = scene, ctx->bound_bvh = bvh, ctx->bound_lights = lights, ctx->bound_epoch = scene->epoch;
+  return YGL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+int ygl_make_state_rngs(const ygl_scene_desc* desc, const ygl_trace_params* params, int* width, int* height,
+    uint64_t* rngs) {
+  if (!desc || !params) return fail(YGL_ERR_INVALID, "null argument");
+  int         w, h;
+  std::string error;
+  if (!state_size(*desc, *params, w, h, error)) return fail(YGL_ERR_INVALID, error);
+  if (width) *width = w;
+  if (height) *height = h;
+  if (rngs) state_rngs(*params, w, h, rngs);
+  return YGL_OK;
+}
+
+int ygl_state_create_tile(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
+    int row_begin, int row_end, ygl_state** out) {
+  if (!ctx || !desc || !params || !out) return fail(YGL_ERR_INVALID, "null argument");
+  int         w, h;
+  std::string error;
+  if (!state_size(*desc, *params, w, h, error)) return fail(YGL_ERR_INVALID, error);
+  if (row_end < 0) row_end = h;
+  if (row_begin < 0 || row_begin > row_end || row_end > h) return fail(YGL_ERR_INVALID, "bad row range");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto state       = std::make_unique<ygl_state>();
+  state->ctx       = ctx;
+  state->width     = w;
+  state->height    = h;
+  state->row_begin = row_begin;
+  state->row_end   = row_end;
+  size_t n         = (size_t)w * (row_end - row_begin);
+  size_t lanes     = std::max<size_t>(n, 1);
+  // one allocation, 256-B aligned slices
+  size_t off = 0;
+  auto   take = [&](size_t bytes) {
+    size_t o = off;
+    off      = (off + bytes + 255) & ~size_t(255);
+    return o;
+  };
+  size_t o_image = take(lanes * 16), o_albedo = take(lanes * 12), o_normal = take(lanes * 12), o_hits = take(lanes * 4),
+         o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_ro = take(lanes * 16), o_rd = take(lanes * 16),
+         o_rad = take(lanes * 16), o_w = take(lanes * 16), o_huvd = take(lanes * 16), o_hid = take(lanes * 8),
+         o_a0 = take(lanes * 16), o_n0 = take(lanes * 16), o_va = take(lanes * 16), o_vb = take(lanes * 16),
+         o_pend = take(lanes * 16);
+  CUDA_TRY(cudaMalloc((void**)&state->mem, off));
+  CUDA_TRY(cudaMemset(state->mem, 0, off));
+  PathState& st = state->st;
+  st.num_lanes  = (int)n;
+  st.width = w, st.height = h, st.row_begin = row_begin;
+  uint8_t* m  = state->mem;
+  st.image    = (float4*)(m + o_image);
+  st.albedo   = (float*)(m + o_albedo);
+  st.normal   = (float*)(m + o_normal);
+  st.hits     = (int*)(m + o_hits);
+  st.rngs     = (ulonglong2*)(m + o_rngs);
+  st.sample   = (int*)(m + o_sample);
+  st.ray_o    = (float4*)(m + o_ro);
+  st.ray_d    = (float4*)(m + o_rd);
+  st.radiance = (float4*)(m + o_rad);
+  st.weight   = (float4*)(m + o_w);
+  st.hit_uvd  = (float4*)(m + o_huvd);
+  st.hit_ids  = (int2*)(m + o_hid);
+  st.albedo0  = (float4*)(m + o_a0);
+  st.normal0  = (float4*)(m + o_n0);
+  st.vol_a    = (float4*)(m + o_va);
+  st.vol_b    = (float4*)(m + o_vb);
+  st.pend     = (float4*)(m + o_pend);
+  // rng table: seeded sequentially over the FULL image (yocto_trace.cpp:1512-1515), tile slice uploaded
+  std::vector<uint64_t> rngs((size_t)w * h * 2);
+  state_rngs(*params, w, h, rngs.data());
+  if (n) CUDA_TRY(cudaMemcpy(st.rngs, rngs.data() + (size_t)row_begin * w * 2, n * 16, cudaMemcpyHostToDevice));
+  *out = state.release();
+  return YGL_OK;
+}
+
+int ygl_state_create(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params, ygl_state** out) {
+  return ygl_state_create_tile(ctx, desc, params, 0, -1, out);
+}
+
+int ygl_state_size(const ygl_state* state, int* width, int* height, int* samples) {
+  if (!state) return fail(YGL_ERR_INVALID, "null state");
+  if (width) *width = state->width;
+  if (height) *height = state->height;
+  if (samples) *samples = state->samples;
+  return YGL_OK;
+}
+int ygl_state_rows(const ygl_state* state, int* row_begin, int* row_end) {
+  if (!state) return fail(YGL_ERR_INVALID, "null state");
+  if (row_begin) *row_begin = state->row_begin;
+  if (row_end) *row_end = state->row_end;
+  return YGL_OK;
+}
+
+int ygl_state_download(ygl_state* state, float* image, float* albedo, float* normal, int32_t* hits, uint64_t* rngs) {
+  if (!state) return fail(YGL_ERR_INVALID, "null state");
+  CUDA_TRY(cudaSetDevice(state->ctx->device));
+  cudaStream_t s = state->ctx->stream;
+  size_t       n = state->st.num_lanes;
+  if (image) CUDA_TRY(cudaMemcpyAsync(image, state->st.image, n * 16, cudaMemcpyDeviceToHost, s));
+  if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo, state->st.albedo, n * 12, cudaMemcpyDeviceToHost, s));
+  if (normal) CUDA_TRY(cudaMemcpyAsync(normal, state->st.normal, n * 12, cudaMemcpyDeviceToHost, s));
+  if (hits) CUDA_TRY(cudaMemcpyAsync(hits, state->st.hits, n * 4, cudaMemcpyDeviceToHost, s));
+  if (rngs) CUDA_TRY(cudaMemcpyAsync(rngs, state->st.rngs, n * 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return YGL_OK;
+}
+
+int ygl_state_upload(ygl_state* state, int samples, const float* image, const float* albedo, const float* normal,
+    const int32_t* hits, const uint64_t* rngs) {
+  if (!state) return fail(YGL_ERR_INVALID, "null state");
+  CUDA_TRY(cudaSetDevice(state->ctx->device));
+  cudaStream_t s = state->ctx->stream;
+  size_t       n = state->st.num_lanes;
+  if (image) CUDA_TRY(cudaMemcpyAsync(state->st.image, image, n * 16, cudaMemcpyHostToDevice, s));
+  if (albedo) CUDA_TRY(cudaMemcpyAsync(state->st.albedo, albedo, n * 12, cudaMemcpyHostToDevice, s));
+  if (normal) CUDA_TRY(cudaMemcpyAsync(state->st.normal, normal, n * 12, cudaMemcpyHostToDevice, s));
+  if (hits) CUDA_TRY(cudaMemcpyAsync(state->st.hits, hits, n * 4, cudaMemcpyHostToDevice, s));
+  if (rngs) CUDA_TRY(cudaMemcpyAsync(state->st.rngs, rngs, n * 16, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  state->samples = samples;
+  return YGL_OK;
+}
+
+void ygl_state_destroy(ygl_state* state) {
+  if (!state) return;
+  cudaSetDevice(state->ctx->device);
+  if (state->mem) cudaFree(state->mem);
+  delete state;
+}
+
+// ------------------------------------------------------------------------------------------
+static int ensure_queues(ygl_context* ctx, int lanes) {
+  if (lanes <= ctx->queue_lanes) return YGL_OK;
+  if (ctx->queue_mem) cudaFree(ctx->queue_mem), ctx->queue_mem = nullptr;
+  size_t per = ((size_t)lanes + 63) & ~size_t(63);
+  CUDA_TRY(cudaMalloc((void**)&ctx->queue_mem, per * 6 * sizeof(int)));
+  ctx->queue_lanes = lanes;
+  return YGL_OK;
+}
+static Queues make_queues(ygl_context* ctx) {
+  size_t per = ((size_t)ctx->queue_lanes + 63) & ~size_t(63);
+  Queues q;
+  q.gen[0]   = ctx->queue_mem + 0 * per;
+  q.gen[1]   = ctx->queue_mem + 1 * per;
+  q.ext[0]   = ctx->queue_mem + 2 * per;
+  q.ext[1]   = ctx->queue_mem + 3 * per;
+  q.lpdf     = ctx->queue_mem + 4 * per;
+  q.acc      = ctx->queue_mem + 5 * per;
+  q.counters = ctx->counters;
+  return q;
+}
+
+// The wavefront driver: runs `nsamples` more samples on every lane of the state.
+static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
+  cudaStream_t s  = ctx->stream;
+  PathState&   st = state->st;
+  if (st.num_lanes == 0 || nsamples <= 0) return YGL_OK;
+  if (int rc = ensure_queues(ctx, st.num_lanes)) return rc;
+  Queues  q = make_queues(ctx);
+  KParams kp;
+  kp.camera = params.camera, kp.sampler = params.sampler, kp.falsecolor = params.falsecolor;
+  kp.bounces = params.bounces, kp.clamp = params.clamp;
+  kp.nocaustics = params.nocaustics, kp.envhidden = params.envhidden, kp.tentfilter = params.tentfilter;
+  kp.sample_end = state->samples + nsamples;
+
+  // persistent-style grids: a multiple of the SM count, capped by the work available
+  auto grid_for = [&](int threads, int per_sm) {
+    int blocks = std::min(ctx->num_sms * per_sm, (st.num_lanes + threads - 1) / threads);
+    return LaunchCfg{std::max(blocks, 1), threads};
+  };
+  LaunchCfg light = grid_for(256, 8), heavy = grid_for(256, 8);
+
+  launch_seed_lanes(s, light, st, q, 0, state->samples);
+  const bool path_like = params.sampler == YGL_SAMPLER_PATH;
+  int        parity = 0, slot = 0;
+  uint64_t   iterations = 0, launches = 1;
+  bool       pending[2] = {false, false};
+  const int  check_every = 4;
+  ctx->h_done[0] = ctx->h_done[1] = 0;
+  while (true) {
+    for (int k = 0; k < check_every; k++) {
+      launch_begin_iteration(s, q, parity);
+      launch_generate(s, light, ctx->dscene, st, q, kp, parity);
+      launch_extend(s, heavy, ctx->dscene, st, q, parity);
+      launch_shade(s, heavy, ctx->dscene, st, q, kp, parity);
+      if (path_like) launch_lightpdf(s, heavy, ctx->dscene, st, q, kp, parity);
+      launch_accumulate(s, light, ctx->dscene, st, q, kp, parity);
+      parity = 1 - parity;
+      iterations++;
+      launches += path_like ? 6 : 5;
+    }
+    // wait for the check issued one round ago (keeps <= 2 rounds of launches in flight)
+    int prev = 1 - slot;
+    if (pending[prev]) {
+      CUDA_TRY(cudaEventSynchronize(ctx->ev[prev]));
+      pending[prev] = false;
+      if (ctx->h_done[prev] >= st.num_lanes) break;
+    }
+    CUDA_TRY(cudaMemcpyAsync(&ctx->h_done[slot], &ctx->counters->done_lanes, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(ctx->ev[slot], s));
+    pending[slot] = true;
+    slot          = 1 - slot;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  Counters c;
+  CUDA_TRY(cudaMemcpy(&c, ctx->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+  ctx->stats[0] += c.camera_samples;
+  ctx->stats[1] += c.scene_rays;
+  ctx->stats[2] += c.instance_rays;
+  ctx->stats[3] += iterations;
+  ctx->stats[4] += launches;
+  state->samples += nsamples;
+  return YGL_OK;
+}
+
+static int check_sampler(const ygl_trace_params& p) {
+  switch (p.sampler) {
+    case YGL_SAMPLER_PATH:
+    case YGL_SAMPLER_EYELIGHT:
+    case YGL_SAMPLER_FALSECOLOR: return YGL_OK;
+    case YGL_SAMPLER_PATHDIRECT:
+    case YGL_SAMPLER_PATHMIS:
+    case YGL_SAMPLER_PATHTEST:
+    case YGL_SAMPLER_NAIVE:
+    case YGL_SAMPLER_DIAGRAM:
+    case YGL_SAMPLER_FURNACE: return fail(YGL_ERR_RUNTIME, "sampler not implemented on the B200 path yet");
+    default: return fail(YGL_ERR_RUNTIME, "sampler unknown");  // yocto_trace.cpp:1437
+  }
+}
+
+int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
+    const ygl_lights* lights, const ygl_trace_params* params) {
+  if (!ctx || !state || !params) return fail(YGL_ERR_INVALID, "null argument");
+  if (state->ctx != ctx) return fail(YGL_ERR_INVALID, "state belongs to another context");
+  if (int rc = check_sampler(*params)) return rc;
+  if (params->camera < 0 || params->camera >= (scene ? scene->num_cameras : 0))
+    return fail(YGL_ERR_INVALID, "camera id out of range");
+  if (state->samples >= params->samples) return YGL_OK;  // yocto_trace.cpp:1598
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (int rc = bind_scene(ctx, scene, bvh, lights)) return rc;
+  memset(ctx->stats, 0, sizeof(ctx->stats));
+  return run_wavefront(ctx, state, *params, params->batch);
+}
+
+int ygl_trace_counters(ygl_context* ctx, uint64_t counters[8]) {
+  if (!ctx || !counters) return fail(YGL_ERR_INVALID, "null argument");
+  memcpy(counters, ctx->stats, sizeof(ctx->stats));
+  return YGL_OK;
+}
+
+int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params, int* width,
+    int* height, float* image) {
+  if (!ctx || !desc || !params) return fail(YGL_ERR_INVALID, "null argument");
+  int         w, h;
+  std::string error;
+  if (!state_size(*desc, *params, w, h, error)) return fail(YGL_ERR_INVALID, error);
+  if (width) *width = w;
+  if (height) *height = h;
+  if (!image) return YGL_OK;
+  if (int rc = check_sampler(*params)) return rc;
+  ygl_scene*  scene  = nullptr;
+  ygl_bvh*    bvh    = nullptr;
+  ygl_lights* lights = nullptr;
+  ygl_state*  state  = nullptr;
+  int         rc     = YGL_OK;
+  do {
+    if ((rc = ygl_bvh_build(desc, params->highqualitybvh, &bvh))) break;
+    if ((rc = ygl_lights_create(desc, &lights))) break;
+    if ((rc = ygl_scene_create(ctx, desc, &scene))) break;
+    if ((rc = ygl_state_create(ctx, desc, params, &state))) break;
+    if ((rc = bind_scene(ctx, scene, bvh, lights))) break;
+    memset(ctx->stats, 0, sizeof(ctx->stats));
+    // trace_image calls trace_samples `samples` times with `batch` samples each until
+    // state.samples >= params.samples (yocto_trace.cpp:1588-1590); results are batch-invariant,
+    // so the same total runs as one wavefront launch sequence.
+    int batch = std::max(1, params->batch);
+    int total = ((params->samples + batch - 1) / batch) * batch;
+    if (params->samples <= 0) total = 0;
+    if ((rc = run_wavefront(ctx, state, *params, total))) break;
+    rc = ygl_state_download(state, image, nullptr, nullptr, nullptr, nullptr);
+  } while (false);
+  std::string keep = g_error;
+  ygl_state_destroy(state);
+  ctx->bound_scene = nullptr;
+  ygl_scene_destroy(scene);
+  ygl_lights_destroy(lights);
+  ygl_bvh_destroy(bvh);
+  g_error = keep;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+int ygl_intersect_rays_device(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const void* d_rays,
+    int64_t n, int instance, int find_any, void* d_out, void* d_counters) {
+  if (!ctx) return fail(YGL_ERR_INVALID, "null context");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (int rc = bind_scene(ctx, scene, bvh, ctx->bound_scene == scene && ctx->bound_bvh == bvh ? ctx->bound_lights : nullptr))
+    return rc;
+  if (instance >= scene->num_instances) return fail(YGL_ERR_INVALID, "instance id out of range");
+  if (n <= 0) return YGL_OK;
+  int       threads = 128;
+  long long blocks  = std::min<long long>((long long)ctx->num_sms * 16, (n + threads - 1) / threads);
+  launch_intersect_rays(ctx->stream, LaunchCfg{(int)std::max<long long>(blocks, 1), threads}, ctx->dscene,
+      (const float4*)d_rays, n, instance, find_any, d_out, (unsigned long long*)d_counters);
+  CUDA_TRY(cudaGetLastError());
+  return YGL_OK;
+}
+
+int ygl_intersect_rays(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_ray* rays, int64_t n,
+    int instance, int find_any, ygl_intersection* out) {
+  if (!ctx || !rays || !out) return fail(YGL_ERR_INVALID, "null argument");
+  if (n <= 0) return YGL_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  void *d_rays = nullptr, *d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_rays, n * sizeof(ygl_ray)));
+  cudaError_t e = cudaMalloc(&d_out, n * sizeof(ygl_intersection));
+  if (e != cudaSuccess) {
+    cudaFree(d_rays);
+    return fail(YGL_ERR_CUDA, "out of device memory");
+  }
+  int rc = YGL_OK;
+  do {
+    if (cudaMemcpyAsync(d_rays, rays, n * sizeof(ygl_ray), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+      rc = fail(YGL_ERR_CUDA, "H2D copy failed");
+      break;
+    }
+    if ((rc = ygl_intersect_rays_device(ctx, scene, bvh, d_rays, n, instance, find_any, d_out, nullptr))) break;
+    if (cudaMemcpyAsync(out, d_out, n * sizeof(ygl_intersection), cudaMemcpyDeviceToHost, ctx->stream) !=
+            cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      rc = fail(YGL_ERR_CUDA, std::string("intersect failed: ") + cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+  } while (false);
+  cudaFree(d_rays);
+  cudaFree(d_out);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU: one process per device; NCCL is loaded lazily (dlopen) so single-GPU users and the
+// CPU-only symbol check need no NCCL at all.
+struct ncclUniqueIdBlob {  // ncclUniqueId: 128 opaque bytes (nccl.h NCCL_UNIQUE_ID_BYTES)
+  char internal[128];
+};
+typedef int (*pfn_ncclGetUniqueId)(ncclUniqueIdBlob*);
+typedef int (*pfn_ncclCommInitRank)(void**, int, ncclUniqueIdBlob, int);
+typedef int (*pfn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*pfn_ncclCommDestroy)(void*);
+typedef const char* (*pfn_ncclGetErrorString)(int);
+
+static void* nccl_open(std::string& error) {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (auto name : names) {
+    if (void* lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)) return lib;
+  }
+  error = std::string("cannot load NCCL: ") + dlerror();
+  return nullptr;
+}
+
+int ygl_comm_id_size(void) { return (int)sizeof(ncclUniqueIdBlob); }
+
+int ygl_comm_create_id(void* id_blob) {
+  std::string error;
+  void*       lib = nccl_open(error);
+  if (!lib) return fail(YGL_ERR_NCCL, error);
+  auto fn = (pfn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+  if (!fn) return fail(YGL_ERR_NCCL, "ncclGetUniqueId missing");
+  if (int rc = fn((ncclUniqueIdBlob*)id_blob)) return fail(YGL_ERR_NCCL, "ncclGetUniqueId failed: " + std::to_string(rc));
+  return YGL_OK;
+}
+
+int ygl_comm_init(ygl_context* ctx, const void* id_blob, int rank, int nranks) {
+  if (!ctx || !id_blob) return fail(YGL_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  std::string error;
+  if (!ctx->nccl_lib) ctx->nccl_lib = nccl_open(error);
+  if (!ctx->nccl_lib) return fail(YGL_ERR_NCCL, error);
+  auto fn = (pfn_ncclCommInitRank)dlsym(ctx->nccl_lib, "ncclCommInitRank");
+  if (!fn) return fail(YGL_ERR_NCCL, "ncclCommInitRank missing");
+  ncclUniqueIdBlob id;
+  memcpy(&id, id_blob, sizeof(id));
+  if (int rc = fn(&ctx->nccl_comm, nranks, id, rank))
+    return fail(YGL_ERR_NCCL, "ncclCommInitRank failed: " + std::to_string(rc));
+  ctx->rank = rank, ctx->nranks = nranks;
+  return YGL_OK;
+}
+
+void ygl_tile_rows(int height, int rank, int nranks, int* row_begin, int* row_end) {
+  int per = (height + nranks - 1) / nranks;
+  int b = std::min(height, rank * per), e = std::min(height, (rank + 1) * per);
+  if (row_begin) *row_begin = b;
+  if (row_end) *row_end = e;
+}
+
+int ygl_gather_image(ygl_context* ctx, ygl_state* state, float* image) {
+  if (!ctx || !state) return fail(YGL_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int w = state->width, h = state->height;
+  if (ctx->nranks == 1) {
+    if (state->row_begin != 0 || state->row_end != h) return fail(YGL_ERR_INVALID, "state is a partial tile but no communicator");
+    return image ? ygl_state_download(state, image, nullptr, nullptr, nullptr, nullptr) : YGL_OK;
+  }
+  if (!ctx->nccl_comm) return fail(YGL_ERR_NCCL, "communicator not initialised");
+  int rb, re;
+  ygl_tile_rows(h, ctx->rank, ctx->nranks, &rb, &re);
+  if (rb != state->row_begin || re != state->row_end) return fail(YGL_ERR_INVALID, "state rows do not match this rank's tile");
+  auto allgather = (pfn_ncclAllGather)dlsym(ctx->nccl_lib, "ncclAllGather");
+  if (!allgather) return fail(YGL_ERR_NCCL, "ncclAllGather missing");
+  // equal-sized send buffers of ceil(h / nranks) rows; the last tile is padded
+  int     per   = (h + ctx->nranks - 1) / ctx->nranks;
+  size_t  count = (size_t)per * w * 4;  // floats per rank
+  float * d_send = nullptr, *d_recv = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_send, count * sizeof(float)));
+  cudaError_t e = cudaMalloc((void**)&d_recv, count * sizeof(float) * ctx->nranks);
+  if (e != cudaSuccess) {
+    cudaFree(d_send);
+    return fail(YGL_ERR_CUDA, "out of device memory");
+  }
+  int rc = YGL_OK;
+  do {
+    cudaMemsetAsync(d_send, 0, count * sizeof(float), ctx->stream);
+    cudaMemcpyAsync(d_send, state->st.image, (size_t)state->st.num_lanes * 16, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (int nrc = allgather(d_send, d_recv, count, /*ncclFloat*/ 7, ctx->nccl_comm, ctx->stream)) {
+      rc = fail(YGL_ERR_NCCL, "ncclAllGather failed: " + std::to_string(nrc));
+      break;
+    }
+    if (image) cudaMemcpyAsync(image, d_recv, (size_t)w * h * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(YGL_ERR_CUDA, "gather failed");
+  } while (false);
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  return rc;
+}
+
+void ygl_comm_destroy(ygl_context* ctx) {
+  if (!ctx || !ctx->nccl_comm) return;
+  auto fn = (pfn_ncclCommDestroy)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+  if (fn) fn(ctx->nccl_comm);
+  ctx->nccl_comm = nullptr;
+  ctx->nranks    = 1;
+  ctx->rank      = 0;
+}
+
+}  // extern "C"

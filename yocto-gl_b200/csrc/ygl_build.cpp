@@ -1,0 +1,403 @@
+// ygl_build.cpp — host-side preparation for the hot path (not timed, but its output order
+// defines hit-id parity): the two-level BVH in the reference's node and primitive order
+// (libs/yocto/yocto_bvh.cpp:108-396), the traversal packets described in ygl_scene.cuh, the
+// light CDFs (yocto_trace.cpp:1528-1581) and the per-pixel rng table (yocto_trace.cpp:1495-1520).
+// Compiled with -ffp-contract=off so every float op rounds exactly like the reference build.
+#include "ygl_build.h"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "ygl_sampling.cuh"
+
+namespace ygl {
+
+namespace {
+
+constexpr float kLowest = -kFltMax;  // flt_min = numeric_limits<float>::lowest(), yocto_math.h:78
+
+struct box3 {
+  f3 min = {kFltMax, kFltMax, kFltMax};  // invalidb3f, yocto_geometry.h:77-87
+  f3 max = {kLowest, kLowest, kLowest};
+};
+
+box3 merge(const box3& a, const f3& b) { return {vmin(a.min, b), vmax(a.max, b)}; }
+box3 merge(const box3& a, const box3& b) { return {vmin(a.min, b.min), vmax(a.max, b.max)}; }
+f3   center(const box3& a) { return (a.min + a.max) / 2; }
+
+f3 P(const float* positions, int i) { return {positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]}; }
+
+// primitive bounds, yocto_geometry.h:475-498
+box3 point_bounds(const f3& p, float r) { return {vmin(p - r, p + r), vmax(p - r, p + r)}; }
+box3 line_bounds(const f3& p0, const f3& p1, float r0, float r1) {
+  return {vmin(p0 - r0, p1 - r1), vmax(p0 + r0, p1 + r1)};
+}
+box3 triangle_bounds(const f3& p0, const f3& p1, const f3& p2) {
+  return {vmin(p0, vmin(p1, p2)), vmax(p0, vmax(p1, p2))};
+}
+box3 quad_bounds(const f3& p0, const f3& p1, const f3& p2, const f3& p3) {
+  return {vmin(p0, vmin(p1, vmin(p2, p3))), vmax(p0, vmax(p1, vmax(p2, p3)))};
+}
+
+// split_middle, yocto_bvh.cpp:202-232
+std::pair<int, int> split_middle(std::vector<int>& prims, const std::vector<f3>& centers, int start, int end) {
+  box3 cb;
+  for (int i = start; i < end; i++) cb = merge(cb, centers[prims[i]]);
+  f3 csize = cb.max - cb.min;
+  if (is_zero(csize)) return {(start + end) / 2, 0};
+  int axis = 0;
+  if (csize.x >= csize.y && csize.x >= csize.z) axis = 0;
+  if (csize.y >= csize.x && csize.y >= csize.z) axis = 1;
+  if (csize.z >= csize.x && csize.z >= csize.y) axis = 2;
+  float split  = comp(center(cb), axis);
+  int   middle = (int)(std::partition(prims.data() + start, prims.data() + end,
+                         [&](int prim) { return comp(centers[prim], axis) < split; }) -
+                     prims.data());
+  if (middle == start || middle == end) return {(start + end) / 2, axis};
+  return {middle, axis};
+}
+
+// split_sah, yocto_bvh.cpp:108-164 (16 bins per axis; cost normalised by the centroid box area)
+std::pair<int, int> split_sah(std::vector<int>& prims, const std::vector<box3>& bboxes, const std::vector<f3>& centers,
+    int start, int end) {
+  box3 cb;
+  for (int i = start; i < end; i++) cb = merge(cb, centers[prims[i]]);
+  f3 csize = cb.max - cb.min;
+  if (is_zero(csize)) return {(start + end) / 2, 0};
+  int       axis     = 0;
+  const int nbins    = 16;
+  float     split    = 0.0f;
+  float     min_cost = kFltMax;
+  auto      area     = [](const box3& b) {
+    f3 size = b.max - b.min;
+    return 1e-12f + 2 * size.x * size.y + 2 * size.x * size.z + 2 * size.y * size.z;
+  };
+  for (int saxis = 0; saxis < 3; saxis++) {
+    for (int b = 1; b < nbins; b++) {
+      float bsplit = comp(cb.min, saxis) + b * comp(csize, saxis) / nbins;
+      box3  lbox, rbox;
+      int   ln = 0, rn = 0;
+      for (int i = start; i < end; i++) {
+        if (comp(centers[prims[i]], saxis) < bsplit) {
+          lbox = merge(lbox, bboxes[prims[i]]);
+          ln += 1;
+        } else {
+          rbox = merge(rbox, bboxes[prims[i]]);
+          rn += 1;
+        }
+      }
+      float cost = 1 + ln * area(lbox) / area(cb) + rn * area(rbox) / area(cb);
+      if (cost < min_cost) {
+        min_cost = cost;
+        split    = bsplit;
+        axis     = saxis;
+      }
+    }
+  }
+  int middle = (int)(std::partition(prims.data() + start, prims.data() + end,
+                         [&](int prim) { return comp(centers[prim], axis) < split; }) -
+                     prims.data());
+  if (middle == start || middle == end) return {(start + end) / 2, axis};
+  return {middle, axis};
+}
+
+// make_bvh, yocto_bvh.cpp:238-302: explicit LIFO of {node, start, end}; children allocated
+// adjacently when the parent is visited; leaves hold <= 4 primitives.
+HostTree make_tree(const std::vector<box3>& bboxes, bool highquality) {
+  const int kMaxPrims = 4;
+  HostTree  tree;
+  tree.prims.resize(bboxes.size());
+  for (size_t i = 0; i < bboxes.size(); i++) tree.prims[i] = (int)i;
+  std::vector<f3> centers(bboxes.size());
+  for (size_t i = 0; i < bboxes.size(); i++) centers[i] = center(bboxes[i]);
+
+  struct item {
+    int node, start, end;
+  };
+  std::vector<item> stack = {{0, 0, (int)bboxes.size()}};
+  tree.nodes.reserve(bboxes.size() * 2 + 1);
+  tree.nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
+  while (!stack.empty()) {
+    item it = stack.back();
+    stack.pop_back();
+    box3 bb;
+    for (int i = it.start; i < it.end; i++) bb = merge(bb, bboxes[tree.prims[i]]);
+    ygl_bvh_node node = {{bb.min.x, bb.min.y, bb.min.z}, {bb.max.x, bb.max.y, bb.max.z}, 0, 0, 0, 0};
+    if (it.end - it.start > kMaxPrims) {
+      auto [mid, axis] = highquality ? split_sah(tree.prims, bboxes, centers, it.start, it.end)
+                                     : split_middle(tree.prims, centers, it.start, it.end);
+      node.internal = 1;
+      node.axis     = (int8_t)axis;
+      node.num      = 2;
+      node.start    = (int)tree.nodes.size();
+      tree.nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
+      tree.nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
+      stack.push_back({node.start + 0, it.start, mid});
+      stack.push_back({node.start + 1, mid, it.end});
+    } else {
+      node.internal = 0;
+      node.num      = (int16_t)(it.end - it.start);
+      node.start    = it.start;
+    }
+    tree.nodes[it.node] = node;
+  }
+  // stack need of a traversal = deepest level + 1
+  if (!tree.nodes.empty()) {
+    std::vector<std::pair<int, int>> todo = {{0, 1}};
+    while (!todo.empty()) {
+      auto [n, depth] = todo.back();
+      todo.pop_back();
+      tree.max_stack = std::max(tree.max_stack, depth);
+      if (tree.nodes[n].internal) {
+        todo.push_back({tree.nodes[n].start, depth + 1});
+        todo.push_back({tree.nodes[n].start + 1, depth + 1});
+      }
+    }
+  }
+  return tree;
+}
+
+float as_float(int v) {
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
+
+std::vector<float4h> pack_nodes(const HostTree& tree) {
+  std::vector<float4h> out(tree.nodes.size() * 2);
+  for (size_t i = 0; i < tree.nodes.size(); i++) {
+    auto& n    = tree.nodes[i];
+    int   meta = ((int)(uint16_t)n.num) | ((int)(uint8_t)n.axis << 16) | ((int)n.internal << 24);
+    out[2 * i + 0] = {n.bbox_min[0], n.bbox_min[1], n.bbox_min[2], n.bbox_max[0]};
+    out[2 * i + 1] = {n.bbox_max[1], n.bbox_max[2], as_float(n.start), as_float(meta)};
+  }
+  return out;
+}
+
+frame3 to_frame(const ygl_frame3f& f) {
+  return {{f.x[0], f.x[1], f.x[2]}, {f.y[0], f.y[1], f.y[2]}, {f.z[0], f.z[1], f.z[2]}, {f.o[0], f.o[1], f.o[2]}};
+}
+
+void pack_instance(float4h* out, const ygl_instance& inst, int id) {
+  frame3 inv = frame_inverse(to_frame(inst.frame), true);  // inverse(frame, true), yocto_bvh.cpp:602
+  out[0]     = {inv.x.x, inv.x.y, inv.x.z, inv.y.x};
+  out[1]     = {inv.y.y, inv.y.z, inv.z.x, inv.z.y};
+  out[2]     = {inv.z.z, inv.o.x, inv.o.y, inv.o.z};
+  out[3]     = {as_float(inst.shape), as_float(id), 0, 0};
+}
+
+}  // namespace
+
+bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error) {
+  const int nshapes = desc.num_shapes;
+  out.shapes.resize(nshapes);
+  out.shape_kind.assign(nshapes, 0);
+  out.shape_nodes.resize(nshapes);
+  out.shape_packets.resize(nshapes);
+  for (int si = 0; si < nshapes; si++) {
+    const ygl_shape& s = desc.shapes[si];
+    // make_shape_bvh, yocto_bvh.cpp:321-362: points > lines > triangles > quads
+    std::vector<box3> bboxes;
+    auto check = [&](int v) { return v >= 0 && v < s.num_positions; };
+    int  kind  = 0;
+    if (s.num_points > 0) {
+      kind = 1;
+      bboxes.resize(s.num_points);
+      if (s.num_radius < s.num_positions) {
+        error = "shape " + std::to_string(si) + ": points need a radius per vertex";
+        return false;
+      }
+      for (int i = 0; i < s.num_points; i++) {
+        int p = s.points[i];
+        if (!check(p)) return error = "point index out of range", false;
+        bboxes[i] = point_bounds(P(s.positions, p), s.radius[p]);
+      }
+    } else if (s.num_lines > 0) {
+      kind = 2;
+      bboxes.resize(s.num_lines);
+      if (s.num_radius < s.num_positions) {
+        error = "shape " + std::to_string(si) + ": lines need a radius per vertex";
+        return false;
+      }
+      for (int i = 0; i < s.num_lines; i++) {
+        int a = s.lines[2 * i], b = s.lines[2 * i + 1];
+        if (!check(a) || !check(b)) return error = "line index out of range", false;
+        bboxes[i] = line_bounds(P(s.positions, a), P(s.positions, b), s.radius[a], s.radius[b]);
+      }
+    } else if (s.num_triangles > 0) {
+      kind = 3;
+      bboxes.resize(s.num_triangles);
+      for (int i = 0; i < s.num_triangles; i++) {
+        int a = s.triangles[3 * i], b = s.triangles[3 * i + 1], c = s.triangles[3 * i + 2];
+        if (!check(a) || !check(b) || !check(c)) return error = "triangle index out of range", false;
+        bboxes[i] = triangle_bounds(P(s.positions, a), P(s.positions, b), P(s.positions, c));
+      }
+    } else if (s.num_quads > 0) {
+      kind = 4;
+      bboxes.resize(s.num_quads);
+      for (int i = 0; i < s.num_quads; i++) {
+        const int* q = s.quads + 4 * i;
+        if (!check(q[0]) || !check(q[1]) || !check(q[2]) || !check(q[3]))
+          return error = "quad index out of range", false;
+        bboxes[i] = quad_bounds(P(s.positions, q[0]), P(s.positions, q[1]), P(s.positions, q[2]), P(s.positions, q[3]));
+      }
+    }
+    out.shape_kind[si] = kind;
+    HostTree& tree     = out.shapes[si];
+    tree               = make_tree(bboxes, highquality);
+    // (an empty shape still gets a single empty root leaf, exactly like the reference's make_bvh)
+    out.shape_nodes[si] = pack_nodes(tree);
+    // leaf packets in primitive order
+    auto& pk = out.shape_packets[si];
+    if (kind == 3) {
+      pk.resize(tree.prims.size() * 3);
+      for (size_t k = 0; k < tree.prims.size(); k++) {
+        const int* t  = s.triangles + 3 * tree.prims[k];
+        f3         p0 = P(s.positions, t[0]), e1 = P(s.positions, t[1]) - p0, e2 = P(s.positions, t[2]) - p0;
+        pk[3 * k + 0] = {p0.x, p0.y, p0.z, e1.x};
+        pk[3 * k + 1] = {e1.y, e1.z, e2.x, e2.y};
+        pk[3 * k + 2] = {e2.z, 0, 0, 0};
+      }
+    } else if (kind == 4) {
+      pk.resize(tree.prims.size() * 4);
+      for (size_t k = 0; k < tree.prims.size(); k++) {
+        const int* q = s.quads + 4 * tree.prims[k];
+        for (int c = 0; c < 4; c++) {
+          f3 p          = P(s.positions, q[c]);
+          pk[4 * k + c] = {p.x, p.y, p.z, 0};
+        }
+      }
+    } else if (kind == 2) {
+      pk.resize(tree.prims.size() * 2);
+      for (size_t k = 0; k < tree.prims.size(); k++) {
+        const int* l  = s.lines + 2 * tree.prims[k];
+        f3         p0 = P(s.positions, l[0]), p1 = P(s.positions, l[1]);
+        pk[2 * k + 0] = {p0.x, p0.y, p0.z, s.radius[l[0]]};
+        pk[2 * k + 1] = {p1.x, p1.y, p1.z, s.radius[l[1]]};
+      }
+    } else if (kind == 1) {
+      pk.resize(tree.prims.size());
+      for (size_t k = 0; k < tree.prims.size(); k++) {
+        int p = s.points[tree.prims[k]];
+        f3  v = P(s.positions, p);
+        pk[k] = {v.x, v.y, v.z, s.radius[p]};
+      }
+    }
+    if (tree.max_stack > 64) {
+      error = "shape " + std::to_string(si) + ": BVH depth " + std::to_string(tree.max_stack) +
+              " exceeds the device traversal stack (64)";
+      return false;
+    }
+  }
+
+  // instance boxes, yocto_bvh.cpp:382-389 (transform_bbox: merge of the 8 transformed corners)
+  std::vector<box3> ibox(desc.num_instances);
+  for (int i = 0; i < desc.num_instances; i++) {
+    const ygl_instance& inst = desc.instances[i];
+    if (inst.shape < 0 || inst.shape >= nshapes) return error = "instance shape id out of range", false;
+    if (inst.material < 0 || inst.material >= desc.num_materials)
+      return error = "instance material id out of range", false;
+    const HostTree& st = out.shapes[inst.shape];  // never empty: make_bvh always emits a root
+    auto&  n  = st.nodes[0];
+    f3     mn = {n.bbox_min[0], n.bbox_min[1], n.bbox_min[2]}, mx = {n.bbox_max[0], n.bbox_max[1], n.bbox_max[2]};
+    frame3 fr = to_frame(inst.frame);
+    f3     corners[8] = {{mn.x, mn.y, mn.z}, {mn.x, mn.y, mx.z}, {mn.x, mx.y, mn.z}, {mn.x, mx.y, mx.z},
+            {mx.x, mn.y, mn.z}, {mx.x, mn.y, mx.z}, {mx.x, mx.y, mn.z}, {mx.x, mx.y, mx.z}};
+    box3   xf;
+    for (auto& c : corners) xf = merge(xf, transform_point(fr, c));
+    ibox[i] = xf;
+  }
+  out.top = make_tree(ibox, highquality);
+  if (out.top.max_stack > 64) return error = "instance BVH too deep for the device traversal stack", false;
+  out.top_nodes = pack_nodes(out.top);
+  out.top_packets.resize(out.top.prims.size() * 4);
+  for (size_t k = 0; k < out.top.prims.size(); k++)
+    pack_instance(&out.top_packets[4 * k], desc.instances[out.top.prims[k]], out.top.prims[k]);
+  out.inst_packets.resize((size_t)desc.num_instances * 4);
+  for (int i = 0; i < desc.num_instances; i++) pack_instance(&out.inst_packets[4 * (size_t)i], desc.instances[i], i);
+  return true;
+}
+
+// make_trace_lights, yocto_trace.cpp:1528-1581. Host libm (glibc sinf) as in the reference.
+void build_lights(const ygl_scene_desc& desc, std::vector<HostLight>& lights) {
+  lights.clear();
+  auto tri_area = [](const f3& p0, const f3& p1, const f3& p2) { return length(cross(p1 - p0, p2 - p0)) / 2; };
+  for (int i = 0; i < desc.num_instances; i++) {
+    const ygl_instance& inst = desc.instances[i];
+    const ygl_material& mat  = desc.materials[inst.material];
+    if (mat.emission[0] == 0 && mat.emission[1] == 0 && mat.emission[2] == 0) continue;
+    const ygl_shape& s = desc.shapes[inst.shape];
+    if (s.num_triangles == 0 && s.num_quads == 0) continue;
+    HostLight light;
+    light.instance = i;
+    if (s.num_triangles > 0) {
+      light.cdf.resize(s.num_triangles);
+      for (int e = 0; e < s.num_triangles; e++) {
+        const int* t = s.triangles + 3 * e;
+        light.cdf[e] = tri_area(P(s.positions, t[0]), P(s.positions, t[1]), P(s.positions, t[2]));
+        if (e != 0) light.cdf[e] += light.cdf[e - 1];
+      }
+    }
+    if (s.num_quads > 0) {
+      light.cdf.assign(s.num_quads, 0.0f);
+      for (int e = 0; e < s.num_quads; e++) {
+        const int* q = s.quads + 4 * e;
+        f3 p0 = P(s.positions, q[0]), p1 = P(s.positions, q[1]), p2 = P(s.positions, q[2]), p3 = P(s.positions, q[3]);
+        light.cdf[e] = tri_area(p0, p1, p3) + tri_area(p2, p3, p1);
+        if (e != 0) light.cdf[e] += light.cdf[e - 1];
+      }
+    }
+    lights.push_back(std::move(light));
+  }
+  for (int i = 0; i < desc.num_environments; i++) {
+    const ygl_environment& env = desc.environments[i];
+    if (env.emission[0] == 0 && env.emission[1] == 0 && env.emission[2] == 0) continue;
+    HostLight light;
+    light.environment = i;
+    if (env.emission_tex >= 0) {
+      const ygl_texture& tex = desc.textures[env.emission_tex];
+      light.cdf.resize((size_t)tex.width * tex.height);
+      for (size_t idx = 0; idx < light.cdf.size(); idx++) {
+        int   ix = (int)idx % tex.width, iy = (int)idx / tex.width;
+        float th = (iy + 0.5f) * kPi / tex.height;
+        float v[4];
+        if (tex.pixelsf) {
+          for (int c = 0; c < 4; c++) v[c] = tex.pixelsf[4 * ((size_t)iy * tex.width + ix) + c];
+        } else {
+          for (int c = 0; c < 4; c++) v[c] = tex.pixelsb[4 * ((size_t)iy * tex.width + ix) + c] / 255.0f;
+        }
+        float m        = ymax(ymax(ymax(v[0], v[1]), v[2]), v[3]);  // max(vec4f), yocto_math.h:1519
+        light.cdf[idx] = m * std::sin(th);
+        if (idx != 0) light.cdf[idx] += light.cdf[idx - 1];
+      }
+    }
+    lights.push_back(std::move(light));
+  }
+}
+
+bool state_size(const ygl_scene_desc& desc, const ygl_trace_params& params, int& width, int& height,
+    std::string& error) {
+  if (params.camera < 0 || params.camera >= desc.num_cameras) return error = "camera id out of range", false;
+  if (params.resolution <= 0) return error = "resolution must be positive", false;
+  const ygl_camera& camera = desc.cameras[params.camera];
+  if (camera.aspect >= 1) {
+    width  = params.resolution;
+    height = (int)std::round(params.resolution / camera.aspect);
+  } else {
+    height = params.resolution;
+    width  = (int)std::round(params.resolution * camera.aspect);
+  }
+  return true;
+}
+
+void state_rngs(const ygl_trace_params& params, int width, int height, uint64_t* rngs) {
+  rng_t seq = rng_make(1301081, 1);
+  for (size_t i = 0; i < (size_t)width * height; i++) {
+    rng_t rng       = rng_make(params.seed, (uint64_t)(rand1i(seq, (int)(1u << 31)) / 2 + 1));
+    rngs[2 * i + 0] = rng.state;
+    rngs[2 * i + 1] = rng.inc;
+  }
+}
+
+}  // namespace ygl

@@ -1,0 +1,49 @@
+// ygl_build.h — host-side preparation that precedes the hot path: BVH build in the reference's
+// node/primitive order, leaf/instance packets, light CDFs and the per-pixel rng table.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/ygl_b200.h"
+
+namespace ygl {
+
+struct HostTree {
+  std::vector<ygl_bvh_node> nodes;
+  std::vector<int32_t>      prims;
+  int                       max_stack = 0;  // stack entries a traversal can need (depth + 1)
+};
+
+struct float4h {
+  float x, y, z, w;
+};
+
+struct HostBvh {
+  HostTree              top;
+  std::vector<HostTree> shapes;
+  std::vector<int>      shape_kind;  // element type each shape tree is built over (kElem*)
+  // device-ready data (see ygl_scene.cuh)
+  std::vector<std::vector<float4h>> shape_nodes;    // 2 float4 per node
+  std::vector<std::vector<float4h>> shape_packets;  // leaf packets, primitive order
+  std::vector<float4h>              top_nodes;
+  std::vector<float4h>              top_packets;   // 4 float4 per instance, leaf order
+  std::vector<float4h>              inst_packets;  // 4 float4 per instance, id order
+};
+
+struct HostLight {
+  int                instance = -1, environment = -1;
+  std::vector<float> cdf;
+};
+
+// make_scene_bvh, yocto_bvh.cpp:364-396 (+ make_shape_bvh :321-362, make_bvh :238-302)
+bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error);
+// make_trace_lights, yocto_trace.cpp:1528-1581
+void build_lights(const ygl_scene_desc& desc, std::vector<HostLight>& lights);
+// image size + rng table of make_trace_state, yocto_trace.cpp:1495-1520
+bool state_size(const ygl_scene_desc& desc, const ygl_trace_params& params, int& width, int& height,
+    std::string& error);
+void state_rngs(const ygl_trace_params& params, int width, int height, uint64_t* rngs);
+
+}  // namespace ygl

@@ -1,0 +1,597 @@
+// ygl_kernels.cu — the wavefront path tracer: sm_100a kernels linked by compacted lane queues.
+//
+//   generate  (ray generation)        sample_camera                       yocto_trace.cpp:338, 1461-1468
+//   extend    (closest-hit traversal) intersect_scene_bvh                 yocto_bvh.cpp:554
+//   shade     (eval + sample)         trace_path / eyelight / falsecolor  yocto_trace.cpp:453, 1111, 1341
+//   lightpdf  (instance traversal)    sample_lights_pdf + MIS weight + RR yocto_trace.cpp:391, 532-590
+//   accumulate                        trace_sample tail                   yocto_trace.cpp:1469-1491
+//
+// Every kernel is persistent-style: a fixed grid (multiple of the SM count) strides over the
+// queue whose length it reads from device memory, so the host never synchronises inside the
+// sample loop. Survivors are appended to the next queue with one atomicAdd per warp
+// (__ballot_sync + __popc + __shfl_sync). Compiled with -fmad=false: see ygl_math.cuh.
+#include "ygl_eval.cuh"
+#include "ygl_kernels.cuh"
+#include "ygl_traverse.cuh"
+
+namespace ygl {
+
+enum : int { kDestNone = 0, kDestExt = 1, kDestLpdf = 2, kDestAcc = 3 };
+enum : int { kFlagHit = 1, kFlagVolume = 2 };
+enum : int {
+  kSamplerPath = 0, kSamplerPathDirect, kSamplerPathMis, kSamplerPathTest, kSamplerNaive, kSamplerEyelight,
+  kSamplerDiagram, kSamplerFurnace, kSamplerFalsecolor
+};
+
+YGL_D void queue_push(int* __restrict__ q, int* counter, bool pred, int value) {
+  unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (!m) return;
+  int lane   = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  int base   = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+YGL_D float4 pack(const f3& v, float w) { return make_float4(v.x, v.y, v.z, w); }
+YGL_D float4 pack(const f3& v, int w) { return make_float4(v.x, v.y, v.z, __int_as_float(w)); }
+YGL_D f3     unpack3(const float4& v) { return f3{v.x, v.y, v.z}; }
+
+YGL_D rng_t load_rng(const PathState& st, int lane) {
+  ulonglong2 r = st.rngs[lane];
+  return rng_t{r.x, r.y};
+}
+YGL_D void store_rng(const PathState& st, int lane, const rng_t& rng) {
+  st.rngs[lane] = make_ulonglong2(rng.state, rng.inc);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_begin_iteration(Counters* c, int parity) {
+  c->n_ext[1 - parity] = 0;
+  c->n_gen[1 - parity] = 0;
+  c->n_lpdf            = 0;
+  c->n_acc             = 0;
+}
+
+__global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begin) {
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int l = tid; l < st.num_lanes; l += gridDim.x * blockDim.x) {
+    st.sample[l]      = sample_begin;
+    q.gen[parity][l]  = l;
+  }
+  if (tid == 0) {
+    Counters* c          = q.counters;
+    c->n_gen[parity]     = st.num_lanes;
+    c->n_gen[1 - parity] = 0;
+    c->n_ext[0] = c->n_ext[1] = 0;
+    c->n_lpdf = c->n_acc = 0;
+    c->done_lanes        = 0;
+    c->camera_samples = c->scene_rays = c->instance_rays = c->shade_calls = 0;
+  }
+}
+
+// ---- ray generation: trace_sample head, yocto_trace.cpp:1461-1468. g++ evaluates the two rand2f
+// arguments right-to-left, so the lens sample `luv` is drawn BEFORE the pixel sample `puv`. ----
+__global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Queues q, KParams p, int parity) {
+  Counters* c   = q.counters;
+  const int n   = c->n_gen[parity];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
+  const DCamera& camera = scene.cameras[p.camera];
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    int  i     = i0 + wl;
+    bool valid = i < n;
+    int  lane  = 0;
+    if (valid) {
+      lane      = q.gen[parity][i];
+      int idx   = lane + st.row_begin * st.width;
+      int px    = idx % st.width, py = idx / st.width;
+      rng_t rng = load_rng(st, lane);
+      f2 luv    = rand2f(rng);
+      f2 puv    = rand2f(rng);
+      f3 o, d;
+      sample_camera(camera, px, py, st.width, st.height, puv, luv, p.tentfilter != 0, o, d);
+      store_rng(st, lane, rng);
+      st.ray_o[lane]    = pack(o, 0);
+      st.ray_d[lane]    = pack(d, 0);
+      st.radiance[lane] = pack(f3{0, 0, 0}, 0);
+      st.weight[lane]   = pack(f3{1, 1, 1}, 0.0f);
+      st.albedo0[lane]  = pack(f3{0, 0, 0}, 0.0f);
+      st.normal0[lane]  = pack(-d, 0.0f);
+    }
+    queue_push(q.ext[parity], &c->n_ext[parity], valid, lane);
+  }
+  if (tid == 0) atomicAdd(&c->camera_samples, (unsigned long long)n);
+}
+
+// ---- extend: closest hit over the instance BVH for every queued ray ----
+__global__ void __launch_bounds__(256) k_extend(DScene scene, PathState st, Queues q, int parity) {
+  Counters* c   = q.counters;
+  const int n   = c->n_ext[parity];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  trav_counters tc;
+  for (int i = tid; i < n; i += stride) {
+    int    lane = q.ext[parity][i];
+    float4 o = st.ray_o[lane], d = st.ray_d[lane];
+    hit_t  h = traverse_scene<false>(scene, unpack3(o), unpack3(d), kRayEps, kFltMax, false, tc);
+    st.hit_uvd[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
+    st.hit_ids[lane] = make_int2(h.instance, h.element);
+  }
+  if (tid == 0) atomicAdd(&c->scene_rays, (unsigned long long)n);
+}
+
+// ---- light sampling, yocto_trace.cpp:361-388 ----
+YGL_D f3 sample_lights(const DScene& scene, const f3& position, float rl, float rel, const f2& ruv) {
+  if (scene.num_lights == 0) return {0, 0, 0};  // the reference indexes lights[-1] here (UB); we stop the path
+  int           light_id = sample_uniform(scene.num_lights, rl);
+  const DLight& light    = scene.lights[light_id];
+  if (light.instance >= 0) {
+    const DInstance& inst  = scene.instances[light.instance];
+    const DShape&    shape = scene.shapes[inst.shape];
+    int  element   = sample_discrete(light.cdf, light.cdf_size, rel);
+    f2   uv        = (shape.num_triangles > 0) ? sample_triangle(ruv) : ruv;
+    auto lposition = eval_position(scene, inst, element, uv);
+    return normalize(lposition - position);
+  } else if (light.environment >= 0) {
+    const DEnvironment& env = scene.environments[light.environment];
+    if (env.emission_tex >= 0) {
+      const DTexture& tex = scene.textures[env.emission_tex];
+      int idx = sample_discrete(light.cdf, light.cdf_size, rel);
+      f2  uv  = f2{((idx % tex.width) + 0.5f) / tex.width, ((idx / tex.width) + 0.5f) / tex.height};
+      return transform_direction(env.frame, f3{ycos(uv.x * 2 * kPi) * ysin(uv.y * kPi), ycos(uv.y * kPi),
+                                                ysin(uv.x * 2 * kPi) * ysin(uv.y * kPi)});
+    } else {
+      return sample_sphere(ruv);
+    }
+  }
+  return {0, 0, 0};
+}
+
+// ---- sample_lights_pdf, yocto_trace.cpp:391-443. Returns the number of instance rays traced. ----
+YGL_D float sample_lights_pdf(const DScene& scene, const f3& position, const f3& direction, unsigned& rays) {
+  float pdf = 0.0f;
+  trav_counters tc;
+  for (int li = 0; li < scene.num_lights; li++) {
+    const DLight& light = scene.lights[li];
+    if (light.instance >= 0) {
+      const DInstance& inst = scene.instances[light.instance];
+      float lpdf          = 0.0f;
+      f3    next_position = position;
+      for (int bounce = 0; bounce < 100; bounce++) {
+        hit_t h = traverse_single_instance<false>(scene, light.instance, next_position, direction, kRayEps, kFltMax,
+            false, tc);
+        rays++;
+        if (!h.hit) break;
+        auto lposition = eval_position(scene, inst, h.element, h.uv);
+        auto lnormal   = eval_element_normal(scene, inst, h.element);
+        auto area      = __ldg(light.cdf + light.cdf_size - 1);
+        lpdf += distance_squared(lposition, position) / (yabs(dot(lnormal, direction)) * area);
+        next_position = lposition + direction * 1e-3f;
+      }
+      pdf += lpdf;
+    } else if (light.environment >= 0) {
+      const DEnvironment& env = scene.environments[light.environment];
+      if (env.emission_tex >= 0) {
+        const DTexture& tex = scene.textures[env.emission_tex];
+        auto wl       = transform_direction(env.inv_frame, direction);
+        auto texcoord = f2{yatan2(wl.z, wl.x) / (2 * kPi), yacos(yclamp(wl.y, -1.0f, 1.0f)) / kPi};
+        if (texcoord.x < 0) texcoord.x += 1;
+        int  i    = iclamp((int)(texcoord.x * tex.width), 0, tex.width - 1);
+        int  j    = iclamp((int)(texcoord.y * tex.height), 0, tex.height - 1);
+        auto prob = sample_discrete_pdf(light.cdf, j * tex.width + i) / __ldg(light.cdf + light.cdf_size - 1);
+        auto angle = (2 * kPi / tex.width) * (kPi / tex.height) * ysin(kPi * (j + 0.5f) / tex.height);
+        pdf += prob / angle;
+      } else {
+        pdf += 1 / (4 * kPi);
+      }
+    }
+  }
+  pdf *= sample_uniform_pdf(scene.num_lights);
+  return pdf;
+}
+
+// tail of one trace_path iteration, yocto_trace.cpp:581-591 + the for-loop increment
+YGL_D int finish_bounce(f3& weight, int& bounce, rng_t& rng, const KParams& p) {
+  if (is_zero(weight) || !vfinite(weight)) return kDestAcc;
+  if (bounce > 3) {
+    auto rr_prob = ymin((float)0.99, max3(weight));
+    if (rand1f(rng) >= rr_prob) return kDestAcc;
+    weight = weight * (1 / rr_prob);
+  }
+  bounce += 1;
+  return bounce < p.bounces ? kDestExt : kDestAcc;
+}
+
+// hashed_color of trace_falsecolor, yocto_trace.cpp:1357-1361 (std::hash<int> is the identity)
+YGL_D f3 hashed_color(int id) {
+  rng_t rng = rng_make(961748941ull, (uint64_t)(int64_t)id);
+  f3    r   = rand3f(rng);
+  f3    v   = 0.5f + 0.5f * r;
+  return {ypow(v.x, 2.2f), ypow(v.y, 2.2f), ypow(v.z, 2.2f)};
+}
+
+// ---- shade one lane. Returns the destination queue. ----
+template <int SAMPLER>
+YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p, int lane, unsigned& inst_rays) {
+  float4 ro = st.ray_o[lane], rd = st.ray_d[lane], rad4 = st.radiance[lane], w4 = st.weight[lane];
+  float4 huvd = st.hit_uvd[lane];
+  f3  o = unpack3(ro), d = unpack3(rd), radiance = unpack3(rad4), weight = unpack3(w4);
+  int bounce = __float_as_int(ro.w), opbounce = __float_as_int(rd.w), flags = __float_as_int(rad4.w);
+  float max_roughness = w4.w;
+  bool  hit           = __float_as_int(huvd.w) != 0;
+
+  // ---- falsecolor: single intersection, yocto_trace.cpp:1341-1419 ----
+  if (SAMPLER == kSamplerFalsecolor) {
+    if (!hit) return kDestAcc;  // trace_result{}: radiance 0, hit false
+    int2 ids = st.hit_ids[lane];
+    const DInstance& inst = scene.instances[ids.x];
+    f2   uv       = {huvd.x, huvd.y};
+    auto outgoing = -d;
+    auto position = eval_shading_position(scene, inst, ids.y, uv);
+    auto normal   = eval_shading_normal(scene, inst, ids.y, uv, outgoing);
+    auto gnormal  = eval_element_normal(scene, inst, ids.y);
+    auto texcoord = eval_texcoord(scene, inst, ids.y, uv);
+    auto material = eval_material(scene, inst, ids.y, uv);
+    auto delta    = is_delta(material) ? 1.0f : 0.0f;
+    f3   result   = {0, 0, 0};
+    switch (p.falsecolor) {
+      case 0: result = position * 0.5f + 0.5f; break;
+      case 1: result = normal * 0.5f + 0.5f; break;
+      case 2: result = dot(normal, -d) > 0 ? f3{0, 1, 0} : f3{1, 0, 0}; break;
+      case 3: result = gnormal * 0.5f + 0.5f; break;
+      case 4: result = dot(gnormal, -d) > 0 ? f3{0, 1, 0} : f3{1, 0, 0}; break;
+      case 5: result = {yfmod(texcoord.x, 1.0f), yfmod(texcoord.y, 1.0f), 0}; break;
+      case 6: result = hashed_color(material.type); break;
+      case 7: result = material.color; break;
+      case 8: result = material.emission; break;
+      case 9: result = {material.roughness, material.roughness, material.roughness}; break;
+      case 10: result = {material.opacity, material.opacity, material.opacity}; break;
+      case 11: result = {material.metallic, material.metallic, material.metallic}; break;
+      case 12: result = {delta, delta, delta}; break;
+      case 13: result = hashed_color(ids.x); break;
+      case 14: result = hashed_color(inst.shape); break;
+      case 15: result = hashed_color(inst.material); break;
+      case 16: result = hashed_color(ids.y); break;
+      case 17: {
+        if (is_zero(material.emission)) material.emission = {0.2f, 0.2f, 0.2f};
+        result = material.emission * yabs(dot(-d, normal));
+      } break;
+      default: result = {0, 0, 0};
+    }
+    radiance          = {srgb_to_rgb(result.x), srgb_to_rgb(result.y), srgb_to_rgb(result.z)};
+    st.radiance[lane] = pack(radiance, kFlagHit);
+    st.albedo0[lane]  = pack(material.color, 0.0f);
+    st.normal0[lane]  = pack(normal, 0.0f);
+    return kDestAcc;
+  }
+
+  // ---- miss: environment, yocto_trace.cpp:469-473 / :1127-1131 ----
+  if (!hit) {
+    if (bounce > 0 || !p.envhidden) radiance = radiance + weight * eval_environment(scene, d);
+    st.radiance[lane] = pack(radiance, flags);
+    return kDestAcc;
+  }
+
+  int2 ids = st.hit_ids[lane];
+  const DInstance& inst = scene.instances[ids.x];
+  f2    uv       = {huvd.x, huvd.y};
+  float distance = huvd.z;
+  rng_t rng      = load_rng(st, lane);
+  int   dest     = kDestAcc;
+
+  // ---- participating medium, yocto_trace.cpp:476-488 (path only). Draw order: rd, then rl. ----
+  bool   in_volume = false;
+  vsdf_t vsdf      = {};
+  if (SAMPLER == kSamplerPath && (flags & kFlagVolume)) {
+    float4 va = st.vol_a[lane], vb = st.vol_b[lane];
+    vsdf     = {unpack3(va), unpack3(vb), va.w};
+    float r_d = rand1f(rng);
+    float r_l = rand1f(rng);
+    float dist = sample_transmittance(vsdf.density, distance, r_l, r_d);
+    weight     = weight * (eval_transmittance(vsdf.density, dist) / sample_transmittance_pdf(vsdf.density, dist, distance));
+    in_volume  = dist < distance;
+    distance   = dist;
+  }
+
+  if (!in_volume) {
+    auto outgoing = -d;
+    auto position = eval_shading_position(scene, inst, ids.y, uv);
+    auto normal   = eval_shading_normal(scene, inst, ids.y, uv, outgoing);
+    auto material = eval_material(scene, inst, ids.y, uv);
+
+    if (SAMPLER == kSamplerPath && p.nocaustics) {
+      max_roughness      = ymax(material.roughness, max_roughness);
+      material.roughness = max_roughness;
+    }
+
+    // opacity pass-through, yocto_trace.cpp:505-510 (rng drawn only when opacity < 1)
+    if (material.opacity < 1 && rand1f(rng) >= material.opacity) {
+      store_rng(st, lane, rng);
+      if (opbounce++ > 128) {
+        st.radiance[lane] = pack(radiance, flags);
+        return kDestAcc;
+      }
+      st.ray_o[lane]  = pack(position + d * 1e-2f, bounce);  // bounce -= 1; continue; bounce++
+      st.ray_d[lane]  = pack(d, opbounce);
+      st.weight[lane] = pack(weight, max_roughness);
+      return kDestExt;
+    }
+
+    if (bounce == 0) {
+      flags |= kFlagHit;
+      st.albedo0[lane] = pack(material.color, 0.0f);
+      st.normal0[lane] = pack(normal, 0.0f);
+    }
+
+    radiance = radiance + weight * eval_emission(material, normal, outgoing);
+
+    if (SAMPLER == kSamplerEyelight) {
+      // yocto_trace.cpp:1155-1172
+      auto incoming = outgoing;
+      radiance      = radiance + weight * kPi * eval_bsdfcos(material, normal, outgoing, incoming);
+      dest          = kDestAcc;
+      if (is_delta(material)) {
+        incoming = sample_delta(material, normal, outgoing, rand1f(rng));
+        if (!is_zero(incoming)) {
+          weight = weight * (eval_delta(material, normal, outgoing, incoming) /
+                                sample_delta_pdf(material, normal, outgoing, incoming));
+          if (!(is_zero(weight) || !vfinite(weight))) {
+            bounce += 1;
+            if (bounce < imax(p.bounces, 4)) {
+              dest           = kDestExt;
+              st.ray_o[lane] = pack(position, bounce);
+              st.ray_d[lane] = pack(incoming, opbounce);
+            }
+          }
+        }
+      }
+      store_rng(st, lane, rng);
+      st.radiance[lane] = pack(radiance, flags);
+      st.weight[lane]   = pack(weight, max_roughness);
+      return dest;
+    }
+
+    // ---- next direction, yocto_trace.cpp:522-542 ----
+    f3 incoming = {0, 0, 0};
+    if (!is_delta(material)) {
+      if (rand1f(rng) < 0.5f) {
+        f2    rn  = rand2f(rng);  // g++: rand2f evaluated before rand1f
+        float rnl = rand1f(rng);
+        incoming  = sample_bsdfcos(material, normal, outgoing, rnl, rn);
+      } else {
+        f2    ruv = rand2f(rng);  // g++ order: ruv, rel, rl
+        float rel = rand1f(rng);
+        float rl  = rand1f(rng);
+        incoming  = sample_lights(scene, position, rl, rel, ruv);
+      }
+      store_rng(st, lane, rng);
+      if (is_zero(incoming)) {
+        st.radiance[lane] = pack(radiance, flags);
+        return kDestAcc;
+      }
+      auto bsdfcos   = eval_bsdfcos(material, normal, outgoing, incoming);
+      auto bsdf_pdf  = sample_bsdfcos_pdf(material, normal, outgoing, incoming);
+      st.pend[lane]  = pack(bsdfcos, bsdf_pdf);
+      dest           = kDestLpdf;
+    } else {
+      incoming = sample_delta(material, normal, outgoing, rand1f(rng));
+      weight   = weight * (eval_delta(material, normal, outgoing, incoming) /
+                            sample_delta_pdf(material, normal, outgoing, incoming));
+    }
+
+    // ---- volume slot update, yocto_trace.cpp:545-553 (independent of the pending weight) ----
+    const DMaterial& mat = scene.materials[inst.material];
+    if (is_volumetric_type(mat.type) && dot(normal, outgoing) * dot(normal, incoming) < 0) {
+      if (!(flags & kFlagVolume)) {
+        auto vm        = eval_material(scene, inst, ids.y, uv);
+        st.vol_a[lane] = pack(vm.density, vm.scanisotropy);
+        st.vol_b[lane] = pack(vm.scattering, 0.0f);
+        flags |= kFlagVolume;
+      } else {
+        flags &= ~kFlagVolume;
+      }
+    }
+
+    if (dest != kDestLpdf) {  // delta: finish the bounce here
+      dest = finish_bounce(weight, bounce, rng, p);
+      store_rng(st, lane, rng);
+    }
+    st.ray_o[lane]    = pack(position, bounce);
+    st.ray_d[lane]    = pack(incoming, opbounce);
+    st.radiance[lane] = pack(radiance, flags);
+    st.weight[lane]   = pack(weight, max_roughness);
+    return dest;
+  } else {
+    // ---- scattering event inside the medium, yocto_trace.cpp:557-579 ----
+    auto outgoing = -d;
+    auto position = o + d * distance;
+    f3   incoming = {0, 0, 0};
+    if (rand1f(rng) < 0.5f) {
+      f2    rn  = rand2f(rng);
+      float rnl = rand1f(rng);  // drawn and unused, as in the reference
+      (void)rnl;
+      incoming = sample_scattering(vsdf, outgoing, rn);
+    } else {
+      f2    ruv = rand2f(rng);
+      float rel = rand1f(rng);
+      float rl  = rand1f(rng);
+      incoming  = sample_lights(scene, position, rl, rel, ruv);
+    }
+    store_rng(st, lane, rng);
+    st.radiance[lane] = pack(radiance, flags);
+    if (is_zero(incoming)) return kDestAcc;
+    st.pend[lane]   = pack(eval_scattering(vsdf, outgoing, incoming), sample_scattering_pdf(vsdf, outgoing, incoming));
+    st.ray_o[lane]  = pack(position, bounce);
+    st.ray_d[lane]  = pack(incoming, opbounce);
+    st.weight[lane] = pack(weight, max_roughness);
+    return kDestLpdf;
+  }
+}
+
+template <int SAMPLER>
+__global__ void __launch_bounds__(256) k_shade(DScene scene, PathState st, Queues q, KParams p, int parity) {
+  Counters* c   = q.counters;
+  const int n   = c->n_ext[parity];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
+  unsigned inst_rays = 0;
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    int i    = i0 + wl;
+    int lane = 0, dest = kDestNone;
+    if (i < n) {
+      lane = q.ext[parity][i];
+      dest = shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
+    }
+    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, lane);
+    queue_push(q.lpdf, &c->n_lpdf, dest == kDestLpdf, lane);
+    queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
+  }
+  if (tid == 0) atomicAdd(&c->shade_calls, (unsigned long long)n);
+}
+
+// ---- lightpdf: sample_lights_pdf for the pending direction, then the MIS weight, weight checks,
+// russian roulette and the loop increment (yocto_trace.cpp:532-536 / :573-576, :581-591) ----
+__global__ void __launch_bounds__(256) k_lightpdf(DScene scene, PathState st, Queues q, KParams p, int parity) {
+  Counters* c   = q.counters;
+  const int n   = c->n_lpdf;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
+  unsigned rays = 0;
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    int i    = i0 + wl;
+    int lane = 0, dest = kDestNone;
+    if (i < n) {
+      lane       = q.lpdf[i];
+      float4 ro = st.ray_o[lane], rd = st.ray_d[lane], w4 = st.weight[lane], pd = st.pend[lane];
+      f3    position = unpack3(ro), incoming = unpack3(rd), weight = unpack3(w4);
+      int   bounce   = __float_as_int(ro.w);
+      float lpdf     = sample_lights_pdf(scene, position, incoming, rays);
+      weight         = weight * (unpack3(pd) / (0.5f * pd.w + 0.5f * lpdf));
+      rng_t rng      = load_rng(st, lane);
+      dest           = finish_bounce(weight, bounce, rng, p);
+      store_rng(st, lane, rng);
+      st.ray_o[lane]  = pack(position, bounce);
+      st.weight[lane] = pack(weight, w4.w);
+    }
+    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, lane);
+    queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
+  }
+  // one atomic per warp for the instance-ray count
+  for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
+  if (wl == 0 && rays) atomicAdd(&c->instance_rays, (unsigned long long)rays);
+}
+
+// ---- accumulate: trace_sample tail, yocto_trace.cpp:1469-1491 ----
+__global__ void __launch_bounds__(256) k_accumulate(DScene scene, PathState st, Queues q, KParams p, int parity) {
+  Counters* c   = q.counters;
+  const int n   = c->n_acc;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
+  int       finished = 0;
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    int  i    = i0 + wl;
+    int  lane = 0;
+    bool more = false;
+    if (i < n) {
+      lane          = q.acc[i];
+      float4 rad4   = st.radiance[lane];
+      f3     radiance = unpack3(rad4);
+      bool   hit    = (__float_as_int(rad4.w) & kFlagHit) != 0;
+      int    sample = st.sample[lane];
+      if (!vfinite(radiance)) radiance = {0, 0, 0};
+      if (max3(radiance) > p.clamp) radiance = radiance * (p.clamp / max3(radiance));
+      float  w   = 1.0f / (sample + 1);
+      float4 im4 = st.image[lane];
+      f4     image  = {im4.x, im4.y, im4.z, im4.w};
+      f3     albedo = ld3(st.albedo, lane), normal = ld3(st.normal, lane);
+      f3     n0     = unpack3(st.normal0[lane]);
+      if (hit) {
+        image  = lerp4(image, f4{radiance.x, radiance.y, radiance.z, 1}, w);
+        albedo = lerp3(albedo, unpack3(st.albedo0[lane]), w);
+        normal = lerp3(normal, n0, w);
+        st.hits[lane] += 1;
+      } else if (!p.envhidden && scene.num_environments > 0) {
+        image  = lerp4(image, f4{radiance.x, radiance.y, radiance.z, 1}, w);
+        albedo = lerp3(albedo, f3{1, 1, 1}, w);
+        normal = lerp3(normal, n0, w);
+        st.hits[lane] += 1;
+      } else {
+        image  = lerp4(image, f4{0, 0, 0, 0}, w);
+        albedo = lerp3(albedo, f3{0, 0, 0}, w);
+        normal = lerp3(normal, n0, w);
+      }
+      st.image[lane]          = make_float4(image.x, image.y, image.z, image.w);
+      st.albedo[3 * lane + 0] = albedo.x, st.albedo[3 * lane + 1] = albedo.y, st.albedo[3 * lane + 2] = albedo.z;
+      st.normal[3 * lane + 0] = normal.x, st.normal[3 * lane + 1] = normal.y, st.normal[3 * lane + 2] = normal.z;
+      sample += 1;
+      st.sample[lane] = sample;
+      more            = sample < p.sample_end;
+      if (!more) finished++;
+    }
+    queue_push(q.gen[1 - parity], &c->n_gen[1 - parity], more, lane);
+  }
+  for (int off = 16; off > 0; off >>= 1) finished += __shfl_down_sync(0xffffffffu, finished, off);
+  if (wl == 0 && finished) atomicAdd(&c->done_lanes, finished);
+}
+
+// ---- batch form of intersect_scene_bvh / intersect_instance_bvh ----
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_intersect_rays(DScene scene, const float4* __restrict__ rays, long long n,
+    int instance, int find_any, int2* __restrict__ out, unsigned long long* counters) {
+  long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  trav_counters tc = {0, 0, 0, 0};
+  unsigned      nhits = 0;
+  for (long long i = tid; i < n; i += stride) {
+    float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+    f3     o = {a.x, a.y, a.z}, d = {a.w, b.x, b.y};
+    hit_t  h = instance < 0 ? traverse_scene<COUNT>(scene, o, d, b.z, b.w, find_any != 0, tc)
+                            : traverse_single_instance<COUNT>(scene, instance, o, d, b.z, b.w, find_any != 0, tc);
+    out[3 * i + 0] = make_int2(h.instance, h.element);
+    out[3 * i + 1] = make_int2(__float_as_int(h.uv.x), __float_as_int(h.uv.y));
+    out[3 * i + 2] = make_int2(__float_as_int(h.distance), h.hit ? 1 : 0);
+    nhits += h.hit ? 1 : 0;
+  }
+  if (COUNT) {
+    atomicAdd(counters + 0, (unsigned long long)tc.top_nodes);
+    atomicAdd(counters + 1, (unsigned long long)tc.bot_nodes);
+    atomicAdd(counters + 2, (unsigned long long)tc.instances);
+    atomicAdd(counters + 3, (unsigned long long)tc.prims);
+    atomicAdd(counters + 4, (unsigned long long)nhits);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+void launch_begin_iteration(cudaStream_t s, Queues q, int parity) { k_begin_iteration<<<1, 1, 0, s>>>(q.counters, parity); }
+void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin) {
+  k_seed_lanes<<<cfg.blocks, cfg.threads, 0, s>>>(st, q, parity, sample_begin);
+}
+void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
+  k_generate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+}
+void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity) {
+  k_extend<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, parity);
+}
+void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
+  if (p.sampler == kSamplerFalsecolor)
+    k_shade<kSamplerFalsecolor><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+  else if (p.sampler == kSamplerEyelight)
+    k_shade<kSamplerEyelight><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+  else
+    k_shade<kSamplerPath><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+}
+void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
+  k_lightpdf<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+}
+void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
+  k_accumulate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+}
+void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const float4* rays, long long n, int instance,
+    int find_any, void* out, unsigned long long* counters) {
+  if (counters)
+    k_intersect_rays<true><<<cfg.blocks, cfg.threads, 0, s>>>(scene, rays, n, instance, find_any, (int2*)out, counters);
+  else
+    k_intersect_rays<false><<<cfg.blocks, cfg.threads, 0, s>>>(scene, rays, n, instance, find_any, (int2*)out, nullptr);
+}
+
+}  // namespace ygl

@@ -1,0 +1,79 @@
+// ygl_kernels.cuh — launch-side declarations shared by ygl_kernels.cu (device) and ygl_host.cpp.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ygl_scene.cuh"
+
+namespace ygl {
+
+// Per-lane wavefront state, SoA of 16-byte records so that each stage moves whole 128-bit words.
+// One lane = one pixel of the tile (the only legal parallel axis: each pixel's samples form a
+// sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
+struct PathState {
+  int num_lanes;  // pixels in this tile
+  int width, height, row_begin;
+  // ---- trace_state accumulators (reference layout, yocto_trace.h:147-157) ----
+  float4*     image;   // vec4f
+  float*      albedo;  // vec3f packed
+  float*      normal;  // vec3f packed
+  int*        hits;
+  ulonglong2* rngs;  // rng_state {state, inc}
+  // ---- per-lane progress ----
+  int* sample;  // index of the sample in flight
+  // ---- path in flight ----
+  float4* ray_o;     // origin.xyz, w: bounce (int bits)
+  float4* ray_d;     // direction.xyz, w: opbounce (int bits)
+  float4* radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
+  float4* weight;    // rgb, w: max_roughness
+  float4* hit_uvd;   // uv.x uv.y distance hit(int bits)
+  int2*   hit_ids;   // instance, element
+  float4* albedo0;   // bounce-0 albedo rgb, w unused
+  float4* normal0;   // bounce-0 normal (or -camera dir on miss) xyz
+  float4* vol_a;     // volume slot: density.xyz, scanisotropy
+  float4* vol_b;     // volume slot: scattering.xyz
+  float4* pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
+};
+
+// Work queues: lane ids compacted with warp-ballot / one atomic per warp.
+struct Queues {
+  int* gen[2];  // lanes that start a new sample
+  int* ext[2];  // lanes with a ray to trace (then shade)
+  int* lpdf;    // lanes waiting for sample_lights_pdf
+  int* acc;     // lanes whose sample finished
+  // counters (device): see QueueCounters
+  struct Counters* counters;
+};
+
+struct Counters {
+  int n_gen[2], n_ext[2], n_lpdf, n_acc;
+  int done_lanes;  // lanes that finished all their samples
+  int pad;
+  unsigned long long camera_samples, scene_rays, instance_rays, shade_calls;
+};
+
+struct KParams {  // trace_params subset used on device (yocto_trace.h:95-113)
+  int   camera, sampler, falsecolor, bounces;
+  float clamp;
+  int   nocaustics, envhidden, tentfilter;
+  int   sample_end;  // lanes stop when sample index reaches this
+};
+
+struct LaunchCfg {
+  int blocks, threads;
+};
+
+void launch_begin_iteration(cudaStream_t s, Queues q, int parity);
+void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin);
+void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity);
+void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+
+// batch intersect (test hook + traversal micro-benchmark). counters may be null.
+void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const float4* rays, long long n, int instance,
+    int find_any, void* out, unsigned long long* counters);
+
+}  // namespace ygl

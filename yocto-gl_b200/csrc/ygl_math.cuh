@@ -1,0 +1,176 @@
+// ygl_math.cuh — fp32 vector algebra with a FIXED evaluation order.
+//
+// Parity contract (SURVEY.md §7 hard part 1): the reference CPU renderer is compiled
+// without FMA contraction, so every product/sum below is a separately rounded IEEE
+// operation, written in exactly the association order of the reference expression
+// it stands for (cited per function, paths under libs/yocto/). This translation unit is
+// compiled with -fmad=false (device) and -ffp-contract=off (host); division and sqrt
+// are IEEE-exact (-prec-div/-prec-sqrt defaults). Transcendentals are evaluated in
+// fp64 and rounded once to fp32 (DESIGN.md "libm"); the reference calls glibc's float
+// routines, which differ from the correctly rounded value on a tiny fraction of inputs.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define YGL_HD __host__ __device__ __forceinline__
+#define YGL_D __device__ __forceinline__
+#else
+#define YGL_HD inline
+#endif
+
+namespace ygl {
+
+constexpr float kPi     = 3.14159265358979323846f;  // pif, yocto_math.h:73
+constexpr float kFltMax = 3.402823466e+38f;         // flt_max, yocto_math.h:77
+constexpr float kRayEps = 1e-4f;                    // ray_eps, yocto_geometry.h:125
+
+struct f2 {
+  float x, y;
+};
+struct f3 {
+  float x, y, z;
+};
+struct f4 {
+  float x, y, z, w;
+};
+struct frame3 {
+  f3 x, y, z, o;
+};
+struct mat3 {
+  f3 x, y, z;
+};
+
+// ---- scalar helpers with yocto's NaN behaviour (yocto_math.h:1045-1050) ----
+YGL_HD float yabs(float a) { return a < 0 ? -a : a; }
+YGL_HD float ymin(float a, float b) { return (a < b) ? a : b; }
+YGL_HD float ymax(float a, float b) { return (a > b) ? a : b; }
+YGL_HD float yclamp(float a, float lo, float hi) { return ymin(ymax(a, lo), hi); }
+YGL_HD int   imin(int a, int b) { return (a < b) ? a : b; }
+YGL_HD int   imax(int a, int b) { return (a > b) ? a : b; }
+YGL_HD int   iclamp(int a, int lo, int hi) { return imin(imax(a, lo), hi); }
+YGL_HD bool  yfinite(float a) { return isfinite(a); }
+
+// ---- transcendental functions: fp64 evaluation rounded once to fp32 ----
+YGL_HD float ysqrt(float a) { return sqrtf(a); }  // IEEE exact
+YGL_HD float ysin(float a) { return (float)sin((double)a); }
+YGL_HD float ycos(float a) { return (float)cos((double)a); }
+YGL_HD float yatan(float a) { return (float)atan((double)a); }
+YGL_HD float yacos(float a) { return (float)acos((double)a); }
+YGL_HD float yatan2(float a, float b) { return (float)atan2((double)a, (double)b); }
+YGL_HD float ylog(float a) { return (float)log((double)a); }
+YGL_HD float yexp(float a) { return (float)exp((double)a); }
+YGL_HD float ypow(float a, float b) { return (float)pow((double)a, (double)b); }
+YGL_HD float yfmod(float a, float b) { return fmodf(a, b); }  // exact by definition
+
+// ---- f3 operators (yocto_math.h:1254-1292) ----
+YGL_HD f3 make3(float x, float y, float z) { return f3{x, y, z}; }
+YGL_HD f3 operator-(const f3& a) { return {-a.x, -a.y, -a.z}; }
+YGL_HD f3 operator+(const f3& a, const f3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+YGL_HD f3 operator+(const f3& a, float b) { return {a.x + b, a.y + b, a.z + b}; }
+YGL_HD f3 operator+(float a, const f3& b) { return {a + b.x, a + b.y, a + b.z}; }
+YGL_HD f3 operator-(const f3& a, const f3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+YGL_HD f3 operator-(const f3& a, float b) { return {a.x - b, a.y - b, a.z - b}; }
+YGL_HD f3 operator-(float a, const f3& b) { return {a - b.x, a - b.y, a - b.z}; }
+YGL_HD f3 operator*(const f3& a, const f3& b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+YGL_HD f3 operator*(const f3& a, float b) { return {a.x * b, a.y * b, a.z * b}; }
+YGL_HD f3 operator*(float a, const f3& b) { return {a * b.x, a * b.y, a * b.z}; }
+YGL_HD f3 operator/(const f3& a, const f3& b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }
+YGL_HD f3 operator/(const f3& a, float b) { return {a.x / b, a.y / b, a.z / b}; }
+YGL_HD f3 operator/(float a, const f3& b) { return {a / b.x, a / b.y, a / b.z}; }
+YGL_HD bool operator==(const f3& a, const f3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+YGL_HD bool is_zero(const f3& a) { return a.x == 0 && a.y == 0 && a.z == 0; }
+
+YGL_HD f2 operator+(const f2& a, const f2& b) { return {a.x + b.x, a.y + b.y}; }
+YGL_HD f2 operator*(const f2& a, float b) { return {a.x * b, a.y * b}; }
+YGL_HD f2 operator-(float a, const f2& b) { return {a - b.x, a - b.y}; }
+
+YGL_HD f4 operator+(const f4& a, const f4& b) { return {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+YGL_HD f4 operator*(const f4& a, float b) { return {a.x * b, a.y * b, a.z * b, a.w * b}; }
+YGL_HD f3 xyz(const f4& a) { return {a.x, a.y, a.z}; }
+
+// yocto_math.h:1302-1312
+YGL_HD float dot(const f3& a, const f3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+YGL_HD f3    cross(const f3& a, const f3& b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+YGL_HD float length(const f3& a) { return ysqrt(dot(a, a)); }
+YGL_HD f3    normalize(const f3& a) {  // yocto_math.h:1314-1317
+  auto l = length(a);
+  return (l != 0) ? a / l : a;
+}
+YGL_HD float distance_squared(const f3& a, const f3& b) { return dot(a - b, a - b); }
+YGL_HD f3 orthonormalize(const f3& a, const f3& b) { return normalize(a - b * dot(a, b)); }  // :1331
+YGL_HD f3 reflect(const f3& w, const f3& n) { return -w + 2 * dot(n, w) * n; }               // :1336
+YGL_HD f3 refract(const f3& w, const f3& n, float inv_eta) {                                 // :1339
+  auto cosine = dot(n, w);
+  auto k      = 1 + inv_eta * inv_eta * (cosine * cosine - 1);
+  if (k < 0) return {0, 0, 0};
+  return -w * inv_eta + (inv_eta * cosine - ysqrt(k)) * n;
+}
+
+YGL_HD float max3(const f3& a) { return ymax(ymax(a.x, a.y), a.z); }  // yocto_math.h:1369
+YGL_HD float min3(const f3& a) { return ymin(ymin(a.x, a.y), a.z); }
+YGL_HD float sum3(const f3& a) { return a.x + a.y + a.z; }
+YGL_HD float mean3(const f3& a) { return sum3(a) / 3; }
+YGL_HD f3    vmin(const f3& a, const f3& b) { return {ymin(a.x, b.x), ymin(a.y, b.y), ymin(a.z, b.z)}; }
+YGL_HD f3    vmax(const f3& a, const f3& b) { return {ymax(a.x, b.x), ymax(a.y, b.y), ymax(a.z, b.z)}; }
+YGL_HD f3    vclamp(const f3& a, float lo, float hi) {
+  return {yclamp(a.x, lo, hi), yclamp(a.y, lo, hi), yclamp(a.z, lo, hi)};
+}
+YGL_HD f3   vsqrt(const f3& a) { return {ysqrt(a.x), ysqrt(a.y), ysqrt(a.z)}; }
+YGL_HD f3   vexp(const f3& a) { return {yexp(a.x), yexp(a.y), yexp(a.z)}; }
+YGL_HD f3   vlog(const f3& a) { return {ylog(a.x), ylog(a.y), ylog(a.z)}; }
+YGL_HD bool vfinite(const f3& a) { return yfinite(a.x) && yfinite(a.y) && yfinite(a.z); }
+YGL_HD f3   lerp3(const f3& a, const f3& b, float u) { return a * (1 - u) + b * u; }  // :1362
+YGL_HD f4   lerp4(const f4& a, const f4& b, float u) { return a * (1 - u) + b * u; }  // :1512
+YGL_HD float comp(const f3& a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// ---- frames and 3x3 matrices ----
+// transform_point / transform_vector / transform_direction, yocto_math.h:2263-2271
+YGL_HD f3 transform_point(const frame3& a, const f3& b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.o;
+}
+YGL_HD f3 transform_vector(const frame3& a, const f3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+YGL_HD f3 transform_direction(const frame3& a, const f3& b) { return normalize(transform_vector(a, b)); }
+// transform_normal(frame, n, non_rigid = false), yocto_math.h:2272-2279
+YGL_HD f3 transform_normal(const frame3& a, const f3& b) { return normalize(transform_vector(a, b)); }
+YGL_HD f3 mat_mul(const mat3& a, const f3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // :1942
+
+// inverse(frame, non_rigid): yocto_math.h:2114-2122 with adjoint/determinant :1965-1972
+YGL_HD frame3 frame_inverse(const frame3& a, bool non_rigid) {
+  mat3 minv;
+  if (non_rigid) {
+    auto cyz = cross(a.y, a.z), czx = cross(a.z, a.x), cxy = cross(a.x, a.y);
+    auto det = dot(a.x, cross(a.y, a.z));
+    auto idt = 1 / det;
+    // adjoint = transpose({cyz, czx, cxy}); inverse = adjoint * (1/det)
+    minv.x = f3{cyz.x, czx.x, cxy.x} * idt;
+    minv.y = f3{cyz.y, czx.y, cxy.y} * idt;
+    minv.z = f3{cyz.z, czx.z, cxy.z} * idt;
+  } else {
+    minv.x = {a.x.x, a.y.x, a.z.x};
+    minv.y = {a.x.y, a.y.y, a.z.y};
+    minv.z = {a.x.z, a.y.z, a.z.z};
+  }
+  auto o = -mat_mul(minv, a.o);
+  return {minv.x, minv.y, minv.z, o};
+}
+
+// basis_fromz, yocto_math.h:1977-1986 (Duff et al. orthonormal basis)
+YGL_HD mat3 basis_fromz(const f3& v) {
+  auto z    = normalize(v);
+  auto sign = copysignf(1.0f, z.z);
+  auto a    = -1.0f / (sign + z.z);
+  auto b    = z.x * z.y * a;
+  auto x    = f3{1.0f + sign * z.x * z.x * a, sign * b, -sign * z.x};
+  auto y    = f3{b, sign + z.y * z.y * a, -z.y};
+  return {x, y, z};
+}
+// transform_direction(mat3, v), yocto_math.h:2236
+YGL_HD f3 transform_direction(const mat3& a, const f3& b) { return normalize(mat_mul(a, b)); }
+
+}  // namespace ygl

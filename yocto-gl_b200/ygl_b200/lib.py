@@ -1,0 +1,293 @@
+"""ctypes binding of yocto-gl_b200/lib/libygl_b200.so — the C ABI of include/ygl_b200.h.
+
+The Python surface mirrors the reference's free functions (yocto_trace.h:116-190):
+trace_image / make_trace_bvh / make_trace_lights / make_trace_state / trace_samples / get_image,
+plus the batch form of intersect_scene_bvh / intersect_instance_bvh. There is no fallback: if
+the extension is missing or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libygl_b200.so"))
+_lib = None
+
+EXPORTS = [
+    "ygl_last_error", "ygl_version", "ygl_trace_params_default", "ygl_context_create",
+    "ygl_context_destroy", "ygl_context_synchronize", "ygl_context_stream", "ygl_scene_create",
+    "ygl_scene_update_cameras", "ygl_scene_destroy", "ygl_bvh_build", "ygl_bvh_tree_size",
+    "ygl_bvh_tree_get", "ygl_bvh_destroy", "ygl_lights_create", "ygl_lights_count",
+    "ygl_lights_get", "ygl_lights_destroy", "ygl_state_create", "ygl_state_create_tile",
+    "ygl_state_size", "ygl_state_rows", "ygl_state_download", "ygl_state_upload",
+    "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
+    "ygl_trace_counters", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_comm_id_size",
+    "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
+]
+
+
+class YglError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the extension; raises (loudly) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise YglError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                       "g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    P = C.POINTER
+    lib.ygl_last_error.restype = C.c_char_p
+    lib.ygl_version.restype = C.c_char_p
+    lib.ygl_context_stream.restype = vp
+    lib.ygl_context_stream.argtypes = [vp]
+    lib.ygl_context_create.argtypes = [i32, P(vp)]
+    lib.ygl_context_destroy.argtypes = [vp]
+    lib.ygl_context_synchronize.argtypes = [vp]
+    lib.ygl_scene_create.argtypes = [vp, P(abi.SceneDesc), P(vp)]
+    lib.ygl_scene_update_cameras.argtypes = [vp, P(abi.Camera), i32]
+    lib.ygl_scene_destroy.argtypes = [vp]
+    lib.ygl_bvh_build.argtypes = [P(abi.SceneDesc), i32, P(vp)]
+    lib.ygl_bvh_tree_size.argtypes = [vp, i32, P(i32), P(i32)]
+    lib.ygl_bvh_tree_get.argtypes = [vp, i32, vp, vp]
+    lib.ygl_bvh_destroy.argtypes = [vp]
+    lib.ygl_lights_create.argtypes = [P(abi.SceneDesc), P(vp)]
+    lib.ygl_lights_count.argtypes = [vp]
+    lib.ygl_lights_get.argtypes = [vp, i32, P(i32), P(i32), P(i32), vp]
+    lib.ygl_lights_destroy.argtypes = [vp]
+    lib.ygl_state_create.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), P(vp)]
+    lib.ygl_state_create_tile.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), i32, i32, P(vp)]
+    lib.ygl_state_size.argtypes = [vp, P(i32), P(i32), P(i32)]
+    lib.ygl_state_rows.argtypes = [vp, P(i32), P(i32)]
+    lib.ygl_state_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ygl_state_upload.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.ygl_state_destroy.argtypes = [vp]
+    lib.ygl_make_state_rngs.argtypes = [P(abi.SceneDesc), P(abi.TraceParams), P(i32), P(i32), vp]
+    lib.ygl_trace_samples.argtypes = [vp, vp, vp, vp, vp, P(abi.TraceParams)]
+    lib.ygl_trace_image.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), P(i32), P(i32), vp]
+    lib.ygl_trace_counters.argtypes = [vp, vp]
+    lib.ygl_intersect_rays.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.ygl_intersect_rays_device.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
+    lib.ygl_comm_create_id.argtypes = [vp]
+    lib.ygl_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.ygl_tile_rows.argtypes = [i32, i32, i32, P(i32), P(i32)]
+    lib.ygl_tile_rows.restype = None
+    lib.ygl_gather_image.argtypes = [vp, vp, vp]
+    lib.ygl_comm_destroy.argtypes = [vp]
+    lib.ygl_comm_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise YglError(f"ygl error {rc}: {load().ygl_last_error().decode()}")
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Bvh:
+    """make_trace_bvh (host build in the reference's node order)."""
+
+    def __init__(self, scene, highquality=False):
+        self.lib = load()
+        self.desc = scene.desc()
+        self.h = C.c_void_p()
+        _check(self.lib.ygl_bvh_build(C.byref(self.desc), int(highquality), C.byref(self.h)))
+
+    def tree(self, shape):
+        nn, npr = C.c_int(), C.c_int()
+        _check(self.lib.ygl_bvh_tree_size(self.h, shape, C.byref(nn), C.byref(npr)))
+        nodes = np.zeros(nn.value, abi.NODE_DTYPE)
+        prims = np.zeros(npr.value, np.int32)
+        _check(self.lib.ygl_bvh_tree_get(self.h, shape, nodes.ctypes.data, prims.ctypes.data))
+        return nodes, prims
+
+    def __del__(self):
+        try:
+            self.lib.ygl_bvh_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Lights:
+    """make_trace_lights."""
+
+    def __init__(self, scene):
+        self.lib = load()
+        self.desc = scene.desc()
+        self.h = C.c_void_p()
+        _check(self.lib.ygl_lights_create(C.byref(self.desc), C.byref(self.h)))
+
+    def items(self):
+        res = []
+        for i in range(self.lib.ygl_lights_count(self.h)):
+            inst, env, n = C.c_int(), C.c_int(), C.c_int()
+            _check(self.lib.ygl_lights_get(self.h, i, C.byref(inst), C.byref(env), C.byref(n), None))
+            cdf = np.zeros(n.value, np.float32)
+            _check(self.lib.ygl_lights_get(self.h, i, C.byref(inst), C.byref(env), C.byref(n),
+                                           cdf.ctypes.data))
+            res.append((inst.value, env.value, cdf))
+        return res
+
+    def __del__(self):
+        try:
+            self.lib.ygl_lights_destroy(self.h)
+        except Exception:
+            pass
+
+
+def make_state_rngs(scene, params):
+    """Image size and rng table of make_trace_state (host only)."""
+    lib = load()
+    desc = scene.desc()
+    w, h = C.c_int(), C.c_int()
+    _check(lib.ygl_make_state_rngs(C.byref(desc), C.byref(params), C.byref(w), C.byref(h), None))
+    rngs = np.zeros((w.value * h.value, 2), np.uint64)
+    _check(lib.ygl_make_state_rngs(C.byref(desc), C.byref(params), C.byref(w), C.byref(h),
+                                   rngs.ctypes.data))
+    return w.value, h.value, rngs
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        _check(self.lib.ygl_context_create(device, C.byref(self.h)))
+
+    def synchronize(self):
+        _check(self.lib.ygl_context_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.ygl_context_stream(self.h)
+
+    def counters(self):
+        c = np.zeros(8, np.uint64)
+        _check(self.lib.ygl_trace_counters(self.h, c.ctypes.data))
+        return dict(camera_samples=int(c[0]), scene_rays=int(c[1]), instance_rays=int(c[2]),
+                    iterations=int(c[3]), launches=int(c[4]))
+
+    def trace_image(self, scene, params):
+        """trace_image: host scene -> host rgba image, everything inside one call."""
+        desc = scene.desc()
+        w, h = C.c_int(), C.c_int()
+        _check(self.lib.ygl_trace_image(self.h, C.byref(desc), C.byref(params), C.byref(w),
+                                        C.byref(h), None))
+        image = np.zeros((h.value, w.value, 4), np.float32)
+        _check(self.lib.ygl_trace_image(self.h, C.byref(desc), C.byref(params), C.byref(w),
+                                        C.byref(h), image.ctypes.data))
+        return image
+
+    def __del__(self):
+        try:
+            self.lib.ygl_context_destroy(self.h)
+        except Exception:
+            pass
+
+
+class DeviceScene:
+    """Device-resident scene + bvh + lights (make_cutrace_scene-style upload)."""
+
+    def __init__(self, ctx, scene, highquality=False):
+        self.ctx, self.lib, self.scene = ctx, ctx.lib, scene
+        self.desc = scene.desc()
+        self.h = C.c_void_p()
+        _check(self.lib.ygl_scene_create(ctx.h, C.byref(self.desc), C.byref(self.h)))
+        self.bvh = Bvh(scene, highquality)
+        self.lights = Lights(scene)
+
+    def make_state(self, params, rows=None):
+        return State(self, params, rows)
+
+    def trace_samples(self, state, params):
+        _check(self.lib.ygl_trace_samples(self.ctx.h, state.h, self.h, self.bvh.h, self.lights.h,
+                                          C.byref(params)))
+
+    def intersect(self, rays, instance=-1, find_any=False):
+        rays = np.ascontiguousarray(rays, abi.RAY_DTYPE)
+        out = np.zeros(len(rays), abi.ISEC_DTYPE)
+        _check(self.lib.ygl_intersect_rays(self.ctx.h, self.h, self.bvh.h, rays.ctypes.data,
+                                           len(rays), instance, int(find_any), out.ctypes.data))
+        return out
+
+    def intersect_device(self, d_rays, n, d_out, instance=-1, find_any=False, d_counters=None):
+        _check(self.lib.ygl_intersect_rays_device(self.ctx.h, self.h, self.bvh.h, d_rays, n,
+                                                  instance, int(find_any), d_out, d_counters))
+
+    def __del__(self):
+        try:
+            self.lib.ygl_scene_destroy(self.h)
+        except Exception:
+            pass
+
+
+class State:
+    """trace_state: resumable per-pixel accumulators + rng streams, resident on the device."""
+
+    def __init__(self, dscene, params, rows=None):
+        self.lib, self.ctx = dscene.lib, dscene.ctx
+        self.h = C.c_void_p()
+        if rows is None:
+            _check(self.lib.ygl_state_create(self.ctx.h, C.byref(dscene.desc), C.byref(params),
+                                             C.byref(self.h)))
+        else:
+            _check(self.lib.ygl_state_create_tile(self.ctx.h, C.byref(dscene.desc),
+                                                  C.byref(params), rows[0], rows[1],
+                                                  C.byref(self.h)))
+        w, h, s = C.c_int(), C.c_int(), C.c_int()
+        _check(self.lib.ygl_state_size(self.h, C.byref(w), C.byref(h), C.byref(s)))
+        rb, re = C.c_int(), C.c_int()
+        _check(self.lib.ygl_state_rows(self.h, C.byref(rb), C.byref(re)))
+        self.width, self.height, self.rows = w.value, h.value, (rb.value, re.value)
+
+    @property
+    def samples(self):
+        s = C.c_int()
+        _check(self.lib.ygl_state_size(self.h, None, None, C.byref(s)))
+        return s.value
+
+    def download(self, full=False):
+        nrows = self.rows[1] - self.rows[0]
+        image = np.zeros((nrows, self.width, 4), np.float32)
+        if not full:
+            _check(self.lib.ygl_state_download(self.h, _p(image), None, None, None, None))
+            return dict(image=image)
+        albedo = np.zeros((nrows, self.width, 3), np.float32)
+        normal = np.zeros((nrows, self.width, 3), np.float32)
+        hits = np.zeros((nrows, self.width), np.int32)
+        rngs = np.zeros((nrows * self.width, 2), np.uint64)
+        _check(self.lib.ygl_state_download(self.h, _p(image), _p(albedo), _p(normal), _p(hits),
+                                           _p(rngs)))
+        return dict(image=image, albedo=albedo, normal=normal, hits=hits, rngs=rngs)
+
+    def upload(self, samples, image=None, albedo=None, normal=None, hits=None, rngs=None):
+        _check(self.lib.ygl_state_upload(self.h, samples, _p(image), _p(albedo), _p(normal),
+                                         _p(hits), _p(rngs)))
+
+    def gather_image(self):
+        """ncclAllGather of the tiles (identity on one rank) -> full host image."""
+        image = np.zeros((self.height, self.width, 4), np.float32)
+        _check(self.lib.ygl_gather_image(self.ctx.h, self.h, image.ctypes.data))
+        return image
+
+    def __del__(self):
+        try:
+            self.lib.ygl_state_destroy(self.h)
+        except Exception:
+            pass
+
+
+def tile_rows(height, rank, nranks):
+    rb, re = C.c_int(), C.c_int()
+    load().ygl_tile_rows(height, rank, nranks, C.byref(rb), C.byref(re))
+    return rb.value, re.value
