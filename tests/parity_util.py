@@ -1,0 +1,70 @@
+"""Shared helpers for the parity tests: seeded ray batches and image comparison."""
+import numpy as np
+
+from ygl_b200 import abi
+
+
+def scene_bounds(scene):
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for inst in scene.instances:
+        p = scene.shapes[inst["shape"]]["positions"].astype(np.float64)
+        if not len(p):
+            continue
+        f = inst["frame"].astype(np.float64)
+        w = p @ f[:3] + f[3]
+        lo, hi = np.minimum(lo, w.min(0)), np.maximum(hi, w.max(0))
+    return lo, hi
+
+
+def random_rays(scene, n, seed=7, tmax=None):
+    """Origins uniform in 1.2x the scene box, uniform directions."""
+    rng = np.random.default_rng(seed)
+    lo, hi = scene_bounds(scene)
+    c, e = (lo + hi) / 2, (hi - lo) / 2 * 1.2 + 1e-3
+    rays = np.zeros(n, abi.RAY_DTYPE)
+    rays["o"] = (c + rng.uniform(-1, 1, size=(n, 3)) * e).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["d"] = d.astype(np.float32)
+    rays["tmin"] = 1e-4
+    rays["tmax"] = np.finfo(np.float32).max if tmax is None else tmax
+    return rays
+
+
+def axis_rays(scene, n, seed=3):
+    """Axis-aligned rays (zero direction components -> inf/NaN slabs) starting on box faces."""
+    rng = np.random.default_rng(seed)
+    lo, hi = scene_bounds(scene)
+    rays = random_rays(scene, n, seed)
+    axis = rng.integers(0, 3, n)
+    sign = rng.choice([-1.0, 1.0], n)
+    d = np.zeros((n, 3), np.float32)
+    d[np.arange(n), axis] = sign
+    rays["d"] = d
+    snap = rng.random(n) < 0.5
+    o = rays["o"].copy()
+    k = rng.integers(0, 3, n)
+    o[snap, k[snap]] = np.where(rng.random(snap.sum()) < 0.5, lo[k[snap]], hi[k[snap]]).astype(np.float32)
+    rays["o"] = o
+    return rays
+
+
+def compare_hits(a, b):
+    """Returns the number of rays whose scene_intersection differs in any bit."""
+    hit = a["hit"] != 0
+    bad = a["hit"] != b["hit"]
+    for f in ("instance", "element"):
+        bad |= hit & (a[f] != b[f])
+    bad |= hit & (a["distance"].view(np.uint32) != b["distance"].view(np.uint32))
+    bad |= hit & (a["uv"].view(np.uint32) != b["uv"].view(np.uint32)).any(axis=1)
+    return int(bad.sum())
+
+
+def image_stats(a, b):
+    a64, b64 = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    diff = a64 - b64
+    rmse = float(np.sqrt(np.mean(diff ** 2)))
+    per_pixel = np.abs(diff).max(axis=-1)
+    exact = (a.view(np.uint32) == b.view(np.uint32)).all(axis=-1)
+    return dict(rmse=rmse, max_abs=float(per_pixel.max()), frac_exact=float(exact.mean()),
+                frac_gt_1e4=float((per_pixel > 1e-4).mean()))
