@@ -1,0 +1,45 @@
+"""Development tool (run under gpurun): times trace_samples on one of the BASELINE configs.
+usage: gpu_perf.py [config] [resolution] [spp] [repeats]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("yocto-gl_b200", "oracle", "tests", "."):
+    sys.path.insert(0, os.path.join(ROOT, p))
+from ygl_b200 import abi, lib, scenes  # noqa: E402
+
+config = sys.argv[1] if len(sys.argv) > 1 else "c3"
+res = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
+spp = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+
+t0 = time.time()
+if config == "c3":
+    scene, bounces = scenes.instanced_spheres(10), 8
+elif config == "c1":
+    scene, bounces = scenes.cornellbox(), 4
+elif config == "c2":
+    scene, bounces = scenes.bunny_like(6), 8
+elif config == "c5":
+    scene, bounces = scenes.hair_scene(), 12
+else:
+    raise SystemExit("unknown config")
+print(f"scene built in {time.time() - t0:.2f}s", flush=True)
+ctx = lib.Context(0)
+t0 = time.time()
+ds = lib.DeviceScene(ctx, scene)
+print(f"bvh+lights+upload in {time.time() - t0:.2f}s", flush=True)
+params = abi.trace_params(resolution=res, samples=spp * (reps + 1), bounces=bounces, batch=spp)
+state = ds.make_state(params)
+for r in range(reps + 1):
+    t0 = time.time()
+    ds.trace_samples(state, params)
+    ctx.synchronize()
+    dt = time.time() - t0
+    c = ctx.counters()
+    n = state.width * state.height * spp
+    print(f"{config} {state.width}x{state.height} {spp}spp: {dt * 1e3:.1f} ms  {n / dt / 1e6:.2f} Msamples/s  "
+          f"{(c['scene_rays'] + c['instance_rays']) / dt / 1e6:.1f} Mrays/s  rays/sample "
+          f"{c['scene_rays'] / n:.2f}+{c['instance_rays'] / n:.2f}  iters {c['iterations']} launches {c['launches']}",
+          flush=True)

@@ -382,7 +382,23 @@ static int bvh_upload(const ygl_bvh* bvh) {
   bvh->off_top_packets  = A.add(H.top_packets.data(), H.top_packets.size() * 16);
   bvh->off_top_prims    = A.add(H.top.prims.data(), H.top.prims.size() * 4);
   bvh->off_inst_packets = A.add(H.inst_packets.data(), H.inst_packets.size() * 16);
-  CUDA_TRY(A.upload());
+  // allocate first so the instance packets can carry the device pointers of their shape's tree
+  CUDA_TRY(cudaMalloc((void**)&A.dev, A.host.size()));
+  auto patch = [&](size_t off, size_t count) {
+    for (size_t k = 0; k < count; k++) {
+      float4h* q     = (float4h*)(A.host.data() + off) + k * kInstancePacketQuads;
+      int      shape = 0;
+      memcpy(&shape, &q[3].x, 4);
+      const void* ptrs[3] = {A.ptr<uint8_t>(bvh->off_nodes[shape]), A.ptr<uint8_t>(bvh->off_packets[shape]),
+          A.ptr<uint8_t>(bvh->off_prims[shape])};
+      memcpy(&q[4].x, &ptrs[0], 8);
+      memcpy(&q[4].z, &ptrs[1], 8);
+      memcpy(&q[5].x, &ptrs[2], 8);
+    }
+  };
+  patch(bvh->off_top_packets, H.top.prims.size());
+  patch(bvh->off_inst_packets, H.inst_packets.size() / kInstancePacketQuads);
+  CUDA_TRY(cudaMemcpy(A.dev, A.host.data(), A.host.size(), cudaMemcpyHostToDevice));
   A.host.clear();
   A.host.shrink_to_fit();
   bvh->uploaded = true;
@@ -431,7 +447,7 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
   if (!scene || !bvh) return fail(YGL_ERR_INVALID, "null scene or bvh");
   if (scene->device != ctx->device) return fail(YGL_ERR_INVALID, "scene lives on another device");
   if ((int)bvh->host.shapes.size() != scene->num_shapes ||
-      (int)(bvh->host.inst_packets.size() / 4) != scene->num_instances)
+      (int)(bvh->host.inst_packets.size() / kInstancePacketQuads) != scene->num_instances)
     return fail(YGL_ERR_INVALID, "bvh was built for a different scene");
   if (ctx->bound_scene == scene && ctx->bound_bvh == bvh && ctx->bound_lights == lights &&
       ctx->bound_epoch == scene->epoch)

@@ -179,12 +179,14 @@ frame3 to_frame(const ygl_frame3f& f) {
   return {{f.x[0], f.x[1], f.x[2]}, {f.y[0], f.y[1], f.y[2]}, {f.z[0], f.z[1], f.z[2]}, {f.o[0], f.o[1], f.o[2]}};
 }
 
-void pack_instance(float4h* out, const ygl_instance& inst, int id) {
+void pack_instance(float4h* out, const ygl_instance& inst, int id, int kind, int num_nodes) {
   frame3 inv = frame_inverse(to_frame(inst.frame), true);  // inverse(frame, true), yocto_bvh.cpp:602
   out[0]     = {inv.x.x, inv.x.y, inv.x.z, inv.y.x};
   out[1]     = {inv.y.y, inv.y.z, inv.z.x, inv.z.y};
   out[2]     = {inv.z.z, inv.o.x, inv.o.y, inv.o.z};
-  out[3]     = {as_float(inst.shape), as_float(id), 0, 0};
+  out[3]     = {as_float(inst.shape), as_float(id), as_float(kind), as_float(num_nodes)};
+  out[4]     = {0, 0, 0, 0};  // device pointers of the shape's tree: patched at upload (ygl_api.cpp)
+  out[5]     = {0, 0, 0, 0};
 }
 
 }  // namespace
@@ -311,11 +313,14 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
   out.top = make_tree(ibox, highquality);
   if (out.top.max_stack > 64) return error = "instance BVH too deep for the device traversal stack", false;
   out.top_nodes = pack_nodes(out.top);
-  out.top_packets.resize(out.top.prims.size() * 4);
-  for (size_t k = 0; k < out.top.prims.size(); k++)
-    pack_instance(&out.top_packets[4 * k], desc.instances[out.top.prims[k]], out.top.prims[k]);
-  out.inst_packets.resize((size_t)desc.num_instances * 4);
-  for (int i = 0; i < desc.num_instances; i++) pack_instance(&out.inst_packets[4 * (size_t)i], desc.instances[i], i);
+  auto pack = [&](float4h* dst, int id) {
+    const ygl_instance& inst = desc.instances[id];
+    pack_instance(dst, inst, id, out.shape_kind[inst.shape], (int)out.shapes[inst.shape].nodes.size());
+  };
+  out.top_packets.resize(out.top.prims.size() * kInstancePacketQuads);
+  for (size_t k = 0; k < out.top.prims.size(); k++) pack(&out.top_packets[kInstancePacketQuads * k], out.top.prims[k]);
+  out.inst_packets.resize((size_t)desc.num_instances * kInstancePacketQuads);
+  for (int i = 0; i < desc.num_instances; i++) pack(&out.inst_packets[kInstancePacketQuads * (size_t)i], i);
   return true;
 }
 

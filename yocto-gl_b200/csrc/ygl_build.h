@@ -19,6 +19,7 @@ struct HostTree {
 struct float4h {
   float x, y, z, w;
 };
+constexpr int kInstancePacketQuads = 6;  // float4 per DInstancePacket (ygl_scene.cuh)
 
 struct HostBvh {
   HostTree              top;
@@ -28,8 +29,8 @@ struct HostBvh {
   std::vector<std::vector<float4h>> shape_nodes;    // 2 float4 per node
   std::vector<std::vector<float4h>> shape_packets;  // leaf packets, primitive order
   std::vector<float4h>              top_nodes;
-  std::vector<float4h>              top_packets;   // 4 float4 per instance, leaf order
-  std::vector<float4h>              inst_packets;  // 4 float4 per instance, id order
+  std::vector<float4h>              top_packets;   // 6 float4 per instance, leaf order
+  std::vector<float4h>              inst_packets;  // 6 float4 per instance, id order
 };
 
 struct HostLight {

@@ -106,17 +106,28 @@ __global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Qu
 }
 
 // ---- extend: closest hit over the instance BVH for every queued ray ----
+// Warps walk the queue in lock-step (32 consecutive entries per warp per step) because trace_ray is
+// warp-cooperative.
 __global__ void __launch_bounds__(256) k_extend(DScene scene, PathState st, Queues q, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_ext[parity];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
   trav_counters tc;
-  for (int i = tid; i < n; i += stride) {
-    int    lane = q.ext[parity][i];
-    float4 o = st.ray_o[lane], d = st.ray_d[lane];
-    hit_t  h = traverse_scene<false>(scene, unpack3(o), unpack3(d), kRayEps, kFltMax, false, tc);
-    st.hit_uvd[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
-    st.hit_ids[lane] = make_int2(h.instance, h.element);
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    const int  i     = i0 + wl;
+    const bool valid = i < n;
+    int        lane  = 0;
+    float4     o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
+    if (valid) {
+      lane = q.ext[parity][i];
+      o = st.ray_o[lane], d = st.ray_d[lane];
+    }
+    hit_t h = trace_ray<false, false>(scene, valid, unpack3(o), unpack3(d), kRayEps, kFltMax, -1, tc);
+    if (valid) {
+      st.hit_uvd[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
+      st.hit_ids[lane] = make_int2(h.instance, h.element);
+    }
   }
   if (tid == 0) atomicAdd(&c->scene_rays, (unsigned long long)n);
 }
@@ -148,42 +159,67 @@ YGL_D f3 sample_lights(const DScene& scene, const f3& position, float rl, float 
   return {0, 0, 0};
 }
 
-// ---- sample_lights_pdf, yocto_trace.cpp:391-443. Returns the number of instance rays traced. ----
-YGL_D float sample_lights_pdf(const DScene& scene, const f3& position, const f3& direction, unsigned& rays) {
-  float pdf = 0.0f;
+// ---- sample_lights_pdf, yocto_trace.cpp:391-443. WARP-COOPERATIVE (calls trace_ray): the per-light
+// chain of up to 100 instance rays is unrolled into one warp-uniform loop in which every lane that
+// still owes a ray traces its next one; lanes add their terms in the reference's order. ----
+YGL_D float sample_lights_pdf(const DScene& scene, bool valid, const f3& position, const f3& direction,
+    unsigned& rays) {
+  float pdf = 0.0f, lpdf = 0.0f;
+  int   li = 0, bounce = 0;
+  f3    next_position = position;
+  bool  done          = !valid;
   trav_counters tc;
-  for (int li = 0; li < scene.num_lights; li++) {
-    const DLight& light = scene.lights[li];
-    if (light.instance >= 0) {
-      const DInstance& inst = scene.instances[light.instance];
-      float lpdf          = 0.0f;
-      f3    next_position = position;
-      for (int bounce = 0; bounce < 100; bounce++) {
-        hit_t h = traverse_single_instance<false>(scene, light.instance, next_position, direction, kRayEps, kFltMax,
-            false, tc);
-        rays++;
-        if (!h.hit) break;
+  while (true) {
+    // walk this lane's light list up to the next area light (environment terms need no ray)
+    int instance = -1;
+    while (!done) {
+      if (li >= scene.num_lights) {
+        done = true;
+        break;
+      }
+      const DLight& light = scene.lights[li];
+      if (light.instance >= 0) {
+        instance = light.instance;
+        break;
+      }
+      if (light.environment >= 0) {
+        const DEnvironment& env = scene.environments[light.environment];
+        if (env.emission_tex >= 0) {
+          const DTexture& tex = scene.textures[env.emission_tex];
+          auto wl       = transform_direction(env.inv_frame, direction);
+          auto texcoord = f2{yatan2(wl.z, wl.x) / (2 * kPi), yacos(yclamp(wl.y, -1.0f, 1.0f)) / kPi};
+          if (texcoord.x < 0) texcoord.x += 1;
+          int  i    = iclamp((int)(texcoord.x * tex.width), 0, tex.width - 1);
+          int  j    = iclamp((int)(texcoord.y * tex.height), 0, tex.height - 1);
+          auto prob = sample_discrete_pdf(light.cdf, j * tex.width + i) / __ldg(light.cdf + light.cdf_size - 1);
+          auto angle = (2 * kPi / tex.width) * (kPi / tex.height) * ysin(kPi * (j + 0.5f) / tex.height);
+          pdf += prob / angle;
+        } else {
+          pdf += 1 / (4 * kPi);
+        }
+      }
+      li++;
+    }
+    const bool want = !done;
+    if (!__any_sync(kFullWarp, want)) break;
+    hit_t h = trace_ray<false, false>(scene, want, next_position, direction, kRayEps, kFltMax, want ? instance : -1, tc);
+    if (want) {
+      rays++;
+      bool next_light = !h.hit;
+      if (h.hit) {
+        const DLight&    light = scene.lights[li];
+        const DInstance& inst  = scene.instances[instance];
         auto lposition = eval_position(scene, inst, h.element, h.uv);
         auto lnormal   = eval_element_normal(scene, inst, h.element);
         auto area      = __ldg(light.cdf + light.cdf_size - 1);
         lpdf += distance_squared(lposition, position) / (yabs(dot(lnormal, direction)) * area);
         next_position = lposition + direction * 1e-3f;
+        next_light    = ++bounce >= 100;
       }
-      pdf += lpdf;
-    } else if (light.environment >= 0) {
-      const DEnvironment& env = scene.environments[light.environment];
-      if (env.emission_tex >= 0) {
-        const DTexture& tex = scene.textures[env.emission_tex];
-        auto wl       = transform_direction(env.inv_frame, direction);
-        auto texcoord = f2{yatan2(wl.z, wl.x) / (2 * kPi), yacos(yclamp(wl.y, -1.0f, 1.0f)) / kPi};
-        if (texcoord.x < 0) texcoord.x += 1;
-        int  i    = iclamp((int)(texcoord.x * tex.width), 0, tex.width - 1);
-        int  j    = iclamp((int)(texcoord.y * tex.height), 0, tex.height - 1);
-        auto prob = sample_discrete_pdf(light.cdf, j * tex.width + i) / __ldg(light.cdf + light.cdf_size - 1);
-        auto angle = (2 * kPi / tex.width) * (kPi / tex.height) * ysin(kPi * (j + 0.5f) / tex.height);
-        pdf += prob / angle;
-      } else {
-        pdf += 1 / (4 * kPi);
+      if (next_light) {
+        pdf += lpdf;
+        lpdf = 0.0f, bounce = 0, next_position = position;
+        li++;
       }
     }
   }
@@ -459,15 +495,19 @@ __global__ void __launch_bounds__(256) k_lightpdf(DScene scene, PathState st, Qu
   const int wl  = threadIdx.x & 31;
   unsigned rays = 0;
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
-    int i    = i0 + wl;
-    int lane = 0, dest = kDestNone;
+    int    i    = i0 + wl;
+    int    lane = 0, dest = kDestNone;
+    float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 1, 0);
     if (i < n) {
-      lane       = q.lpdf[i];
-      float4 ro = st.ray_o[lane], rd = st.ray_d[lane], w4 = st.weight[lane], pd = st.pend[lane];
-      f3    position = unpack3(ro), incoming = unpack3(rd), weight = unpack3(w4);
-      int   bounce   = __float_as_int(ro.w);
-      float lpdf     = sample_lights_pdf(scene, position, incoming, rays);
-      weight         = weight * (unpack3(pd) / (0.5f * pd.w + 0.5f * lpdf));
+      lane = q.lpdf[i];
+      ro = st.ray_o[lane], rd = st.ray_d[lane];
+    }
+    float lpdf = sample_lights_pdf(scene, i < n, unpack3(ro), unpack3(rd), rays);
+    if (i < n) {
+      float4 w4 = st.weight[lane], pd = st.pend[lane];
+      f3     position = unpack3(ro), weight = unpack3(w4);
+      int    bounce   = __float_as_int(ro.w);
+      weight          = weight * (unpack3(pd) / (0.5f * pd.w + 0.5f * lpdf));
       rng_t rng      = load_rng(st, lane);
       dest           = finish_bounce(weight, bounce, rng, p);
       store_rng(st, lane, rng);
@@ -540,17 +580,23 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256) k_intersect_rays(DScene scene, const float4* __restrict__ rays, long long n,
     int instance, int find_any, int2* __restrict__ out, unsigned long long* counters) {
   long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
   trav_counters tc = {0, 0, 0, 0};
   unsigned      nhits = 0;
-  for (long long i = tid; i < n; i += stride) {
-    float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
-    f3     o = {a.x, a.y, a.z}, d = {a.w, b.x, b.y};
-    hit_t  h = instance < 0 ? traverse_scene<COUNT>(scene, o, d, b.z, b.w, find_any != 0, tc)
-                            : traverse_single_instance<COUNT>(scene, instance, o, d, b.z, b.w, find_any != 0, tc);
-    out[3 * i + 0] = make_int2(h.instance, h.element);
-    out[3 * i + 1] = make_int2(__float_as_int(h.uv.x), __float_as_int(h.uv.y));
-    out[3 * i + 2] = make_int2(__float_as_int(h.distance), h.hit ? 1 : 0);
-    nhits += h.hit ? 1 : 0;
+  for (long long i0 = tid - wl; i0 < n; i0 += stride) {
+    const long long i     = i0 + wl;
+    const bool      valid = i < n;
+    float4 a = make_float4(0, 0, 0, 0), b = make_float4(1, 0, 0, 0);
+    if (valid) a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+    f3    o = {a.x, a.y, a.z}, d = {a.w, b.x, b.y};
+    hit_t h = find_any ? trace_ray<true, COUNT>(scene, valid, o, d, b.z, b.w, instance, tc)
+                       : trace_ray<false, COUNT>(scene, valid, o, d, b.z, b.w, instance, tc);
+    if (valid) {
+      out[3 * i + 0] = make_int2(h.instance, h.element);
+      out[3 * i + 1] = make_int2(__float_as_int(h.uv.x), __float_as_int(h.uv.y));
+      out[3 * i + 2] = make_int2(__float_as_int(h.distance), h.hit ? 1 : 0);
+      nhits += h.hit ? 1 : 0;
+    }
   }
   if (COUNT) {
     atomicAdd(counters + 0, (unsigned long long)tc.top_nodes);

@@ -18,8 +18,12 @@
 #include <cuda_runtime.h>
 #define YGL_HD __host__ __device__ __forceinline__
 #define YGL_D __device__ __forceinline__
+// fp64 libm bodies are large: one out-of-line copy per kernel keeps the shading kernels inside the
+// instruction cache (the first profile showed k_shade stalled on instruction fetch).
+#define YGL_HD_NOINLINE __host__ __device__ __noinline__ inline
 #else
 #define YGL_HD inline
+#define YGL_HD_NOINLINE inline
 #endif
 
 namespace ygl {
@@ -56,14 +60,14 @@ YGL_HD bool  yfinite(float a) { return isfinite(a); }
 
 // ---- transcendental functions: fp64 evaluation rounded once to fp32 ----
 YGL_HD float ysqrt(float a) { return sqrtf(a); }  // IEEE exact
-YGL_HD float ysin(float a) { return (float)sin((double)a); }
-YGL_HD float ycos(float a) { return (float)cos((double)a); }
-YGL_HD float yatan(float a) { return (float)atan((double)a); }
-YGL_HD float yacos(float a) { return (float)acos((double)a); }
-YGL_HD float yatan2(float a, float b) { return (float)atan2((double)a, (double)b); }
-YGL_HD float ylog(float a) { return (float)log((double)a); }
-YGL_HD float yexp(float a) { return (float)exp((double)a); }
-YGL_HD float ypow(float a, float b) { return (float)pow((double)a, (double)b); }
+YGL_HD_NOINLINE float ysin(float a) { return (float)sin((double)a); }
+YGL_HD_NOINLINE float ycos(float a) { return (float)cos((double)a); }
+YGL_HD_NOINLINE float yatan(float a) { return (float)atan((double)a); }
+YGL_HD_NOINLINE float yacos(float a) { return (float)acos((double)a); }
+YGL_HD_NOINLINE float yatan2(float a, float b) { return (float)atan2((double)a, (double)b); }
+YGL_HD_NOINLINE float ylog(float a) { return (float)log((double)a); }
+YGL_HD_NOINLINE float yexp(float a) { return (float)exp((double)a); }
+YGL_HD_NOINLINE float ypow(float a, float b) { return (float)pow((double)a, (double)b); }
 YGL_HD float yfmod(float a, float b) { return fmodf(a, b); }  // exact by definition
 
 // ---- f3 operators (yocto_math.h:1254-1292) ----
