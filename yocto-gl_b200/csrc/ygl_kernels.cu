@@ -52,6 +52,7 @@ __global__ void k_begin_iteration(Counters* c, int parity) {
   c->n_gen[1 - parity] = 0;
   c->n_lpdf            = 0;
   c->n_acc             = 0;
+  c->ext_head          = 0;
 }
 
 __global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begin) {
@@ -67,6 +68,7 @@ __global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begi
     c->n_ext[0] = c->n_ext[1] = 0;
     c->n_lpdf = c->n_acc = 0;
     c->done_lanes        = 0;
+    c->ext_head          = 0;
     c->camera_samples = c->scene_rays = c->instance_rays = c->shade_calls = 0;
   }
 }
@@ -106,30 +108,40 @@ __global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Qu
 }
 
 // ---- extend: closest hit over the instance BVH for every queued ray ----
-// Warps walk the queue in lock-step (32 consecutive entries per warp per step) because trace_ray is
-// warp-cooperative.
-__global__ void __launch_bounds__(256) k_extend(DScene scene, PathState st, Queues q, int parity) {
-  Counters* c   = q.counters;
-  const int n   = c->n_ext[parity];
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-  const int wl  = threadIdx.x & 31;
-  trav_counters tc;
-  for (int i0 = tid - wl; i0 < n; i0 += stride) {
-    const int  i     = i0 + wl;
-    const bool valid = i < n;
-    int        lane  = 0;
-    float4     o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
-    if (valid) {
-      lane = q.ext[parity][i];
-      o = st.ray_o[lane], d = st.ray_d[lane];
-    }
-    hit_t h = trace_ray<false, false>(scene, valid, unpack3(o), unpack3(d), kRayEps, kFltMax, -1, tc);
-    if (valid) {
-      st.hit_uvd[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
-      st.hit_ids[lane] = make_int2(h.instance, h.element);
-    }
+// Persistent warps: each warp keeps 32 rays in flight and refills finished lanes from the queue
+// (extend_stream in ygl_traverse.cuh), so short rays (sky misses) do not idle lanes while long ones walk.
+struct ExtendSource {
+  const int* __restrict__ queue;
+  int        n;
+  int*       head;
+  PathState  st;
+  int        lane;
+  YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more) {
+    const unsigned m    = __ballot_sync(kFullWarp, idle);
+    const int      wl   = threadIdx.x & 31;
+    int            base = 0;
+    if (wl == __ffs(m) - 1) base = atomicAdd(head, __popc(m));
+    base         = __shfl_sync(kFullWarp, base, __ffs(m) - 1);
+    const int my = base + __popc(m & ((1u << wl) - 1u));
+    more         = base + __popc(m) < n;
+    if (!idle || my >= n) return false;
+    lane     = queue[my];
+    float4 a = st.ray_o[lane], b = st.ray_d[lane];
+    o = unpack3(a), d = unpack3(b);
+    return true;
   }
-  if (tid == 0) atomicAdd(&c->scene_rays, (unsigned long long)n);
+  YGL_D void commit(const hit_t& h) {
+    st.hit_uvd[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
+    st.hit_ids[lane] = make_int2(h.instance, h.element);
+  }
+};
+
+__global__ void __launch_bounds__(128) k_extend(DScene scene, PathState st, Queues q, int parity) {
+  Counters*    c = q.counters;
+  const int    n = c->n_ext[parity];
+  ExtendSource src{q.ext[parity], n, &c->ext_head, st, 0};
+  trace_stream(scene, src);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->scene_rays, (unsigned long long)n);
 }
 
 // ---- light sampling, yocto_trace.cpp:361-388 ----
@@ -616,7 +628,23 @@ void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, 
   k_generate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }
 void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity) {
-  k_extend<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, parity);
+  // persistent kernel: exactly the resident capacity (SMs x blocks/SM from the occupancy API), capped
+  // by the lanes that can exist; cfg.blocks carries the SM count x per-SM factor chosen by the host
+  static int per_sm = 0;
+  static int sms    = 0;
+  if (!per_sm) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend, 128, 0);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (per_sm < 1) per_sm = 1;
+  }
+  int blocks = sms * per_sm;
+  int needed = (st.num_lanes + 127) / 128;
+  if (blocks > needed) blocks = needed;
+  if (blocks < 1) blocks = 1;
+  (void)cfg;
+  k_extend<<<blocks, 128, 0, s>>>(scene, st, q, parity);
 }
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   if (p.sampler == kSamplerFalsecolor)

@@ -49,7 +49,7 @@ struct Queues {
 struct Counters {
   int n_gen[2], n_ext[2], n_lpdf, n_acc;
   int done_lanes;  // lanes that finished all their samples
-  int pad;
+  int ext_head;    // work cursor of the persistent extend kernel (reset every iteration)
   unsigned long long camera_samples, scene_rays, instance_rays, shade_calls;
 };
 

@@ -205,13 +205,43 @@ YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f
     return 0;  // shape root (make_bvh always emits one)
   };
 
-  int cur = kMarkDone;
+  // pop + resolve the cheap markers (instance exit, end of an instance leaf) until the lane holds a node,
+  // an ENTER entry or is done
+  auto advance = [&]() {
+    while (true) {
+      int v = pop();
+      if (v == kMarkExit) {
+        ray    = world;
+        nodes  = scene.top_nodes;
+        bottom = false;
+        continue;
+      }
+      if (ANY && v == kMarkLeafEnd) {
+        if (res.hit) {  // yocto_bvh.cpp:613
+          sp = 0;
+          return kMarkDone;
+        }
+        continue;
+      }
+      return v;
+    }
+  };
+
+  int cur = kMarkDone;  // >= 0: node to visit; kMarkLeaf: primitive leaf in progress; < 0 else: ENTER ~idx / done
   if (active) cur = start_instance >= 0 ? enter(scene.inst_packets + start_instance) : (scene.top_num_nodes > 0 ? 0 : kMarkDone);
 
-  int leaf_start = 0, leaf_num = 0;
+  int leaf_next = 0, leaf_end = 0;
+  // Warp-level greedy scheduling of the three code paths: each round the path wanted by most lanes runs
+  // for those lanes (node visit / one primitive test / instance entry); the others keep their state.
   while (true) {
-    // ---- phase A: every lane pops + slab-tests nodes until it holds a leaf or a marker ----
-    while (__any_sync(kFullWarp, cur >= 0)) {
+    const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0);
+    const unsigned want_prim  = __ballot_sync(kFullWarp, cur == kMarkLeaf);
+    const unsigned want_enter = __ballot_sync(kFullWarp, cur < 0 && cur > kMarkLeaf);
+    if (!(want_node | want_prim | want_enter)) break;
+    const int n_node = __popc(want_node), n_prim = __popc(want_prim), n_enter = __popc(want_enter);
+
+    if (n_node >= n_prim && n_node >= n_enter) {
+      // ---- node visit: pop + slab test, yocto_bvh.cpp:485-503 / :579-598 ----
       if (cur >= 0) {
         float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
         if (COUNT) {
@@ -223,85 +253,198 @@ YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f
         int      start = __float_as_int(n1.z);
         unsigned meta  = (unsigned)__float_as_int(n1.w);
         if (!inside) {
-          cur = pop();
+          cur = advance();
         } else if (meta >> 24) {
           // internal: the reference pushes both children ordered by ray_dsign[axis] and pops the last
           // pushed; visiting that one directly and stacking the other is the same sequence.
           int neg     = (ray.sgn >> ((meta >> 16) & 0xff)) & 1;
           stack[sp++] = start + 1 - neg;
           cur         = start + neg;
+        } else if (bottom) {
+          leaf_next = start;
+          leaf_end  = start + (int)(meta & 0xffff);
+          cur       = leaf_next < leaf_end ? kMarkLeaf : advance();
         } else {
-          leaf_start = start;
-          leaf_num   = (int)(meta & 0xffff);
-          cur        = kMarkLeaf;
+          // leaf of the instance tree: instances are visited in order, each seeing the tmax left by the
+          // previous one (yocto_bvh.cpp:599-610) -> stack them in reverse
+          if (ANY) stack[sp++] = kMarkLeafEnd;
+          for (int idx = start + (int)(meta & 0xffff) - 1; idx >= start; idx--) stack[sp++] = ~idx;
+          cur = advance();
         }
       }
+    } else if (n_prim >= n_enter) {
+      // ---- one primitive test per round, yocto_bvh.cpp:505-545 ----
+      if (cur == kMarkLeaf) {
+        const int idx = leaf_next++;
+        if (COUNT) cnt.prims++;
+        f2    puv = {0, 0};
+        float pd  = 0;
+        bool  h;
+        if (kind == kElemTriangles) {
+          float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
+          h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
+        } else if (kind == kElemQuads) {
+          float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
+                 e = __ldg(packets + 4 * idx + 3);
+          h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
+              f3{e.x, e.y, e.z}, puv, pd);
+        } else if (kind == kElemLines) {
+          float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
+          h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
+        } else {
+          float4 a = __ldg(packets + idx);
+          h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
+        }
+        if (h) {
+          res       = {cur_instance, __ldg(prims + idx), puv, pd, true};
+          tmax      = pd;
+          shape_hit = true;
+        }
+        if (leaf_next == leaf_end) {
+          if (ANY && shape_hit) sp = inst_sp;  // intersect_shape_bvh returns at once: unwind to EXIT
+          cur = advance();
+        }
+      }
+    } else {
+      // ---- instance entry ----
+      if (cur < 0 && cur > kMarkLeaf) cur = enter(scene.top_packets + ~cur);
     }
-    if (__all_sync(kFullWarp, cur == kMarkDone)) break;
+  }
+  return res;
+}
 
-    // ---- phase B: leaves and markers, as predicated blocks every lane walks through ----
-    const bool prim_leaf = cur == kMarkLeaf && bottom;
-    if (__any_sync(kFullWarp, prim_leaf)) {
-      for (int k = 0; k < 4; k++) {  // bvh_max_prims = 4, yocto_bvh.cpp:235
-        const bool test = prim_leaf && k < leaf_num;
-        if (!__any_sync(kFullWarp, test)) break;
-        if (test) {
-          const int idx = leaf_start + k;
-          if (COUNT) cnt.prims++;
-          f2    puv = {0, 0};
-          float pd  = 0;
-          bool  h;
-          if (kind == kElemTriangles) {
-            float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
-            h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
-          } else if (kind == kElemQuads) {
-            float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
-                   e = __ldg(packets + 4 * idx + 3);
-            h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
-                f3{e.x, e.y, e.z}, puv, pd);
-          } else if (kind == kElemLines) {
-            float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
-            h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
-          } else {
-            float4 a = __ldg(packets + idx);
-            h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
-          }
-          if (h) {
-            res       = {cur_instance, __ldg(prims + idx), puv, pd, true};
-            tmax      = pd;
-            shape_hit = true;
-          }
-        }
-      }
-      if (prim_leaf) {
-        if (ANY && shape_hit) sp = inst_sp;  // intersect_shape_bvh returns at once: unwind to EXIT
-        cur = pop();
-      }
-    }
-    if (cur == kMarkLeaf) {
-      // leaf of the instance tree: instances are visited in order, each seeing the tmax left by the
-      // previous one (yocto_bvh.cpp:599-610) -> stack them in reverse
-      if (ANY) stack[sp++] = kMarkLeafEnd;
-      for (int idx = leaf_start + leaf_num - 1; idx >= leaf_start; idx--) stack[sp++] = ~idx;
-      cur = pop();
-    }
-    if (cur == kMarkExit) {
+// Persistent closest-hit stream (intersect_scene_bvh with the default ray range tmin = ray_eps,
+// tmax = flt_max): the same per-ray walk as trace_ray, but a warp keeps refilling finished lanes from
+// `src` (src.fetch hands out rays, src.commit stores a finished lane's hit). Must be called by full,
+// converged warps.
+constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
+
+template <class Source>
+YGL_D void trace_stream(const DScene& scene, Source& src) {
+  int   stack[2 * kStackSize + 8];
+  int   sp  = 0;
+  hit_t res = {-1, -1, {0, 0}, 0, false};
+
+  const float tmin = kRayEps;
+  float       tmax = kFltMax;
+  ray_setup   world = make_ray(f3{0, 0, 0}, f3{0, 0, 1});
+  ray_setup   ray   = world;
+
+  const float4* __restrict__ nodes = scene.top_nodes;
+  const float4* packets            = nullptr;
+  const int*    prims              = nullptr;
+  int  kind = kElemNone, cur_instance = -1;
+  bool bottom = false, have = false, more = true;
+
+  auto pop   = [&]() { return sp > 0 ? stack[--sp] : kMarkDone; };
+  auto enter = [&](const DInstancePacket* pk) {
+    float4 a = __ldg(&pk->q[0]), b = __ldg(&pk->q[1]), c = __ldg(&pk->q[2]), e = __ldg(&pk->q[3]);
+    float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
+    frame3 inv = {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}, {c.y, c.z, c.w}};
+    ray          = make_ray(transform_point(inv, world.o), transform_vector(inv, world.d));
+    cur_instance = __float_as_int(e.y);
+    kind         = __float_as_int(e.z);
+    nodes   = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.y) << 32) | (unsigned)__float_as_int(p0.x));
+    packets = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.w) << 32) | (unsigned)__float_as_int(p0.z));
+    prims   = (const int*)(((unsigned long long)(unsigned)__float_as_int(p1.y) << 32) | (unsigned)__float_as_int(p1.x));
+    bottom      = true;
+    stack[sp++] = kMarkExit;
+    return 0;
+  };
+  auto advance = [&]() {
+    while (true) {
+      int v = pop();
+      if (v != kMarkExit) return v;
       ray    = world;
       nodes  = scene.top_nodes;
       bottom = false;
-      cur    = pop();
     }
-    if (ANY && cur == kMarkLeafEnd) {
-      if (res.hit) {  // yocto_bvh.cpp:613
-        sp  = 0;
-        cur = kMarkDone;
-      } else {
-        cur = pop();
+  };
+
+  int cur = kMarkDone, leaf_next = 0, leaf_end = 0;
+  while (true) {
+    const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0);
+    const unsigned want_prim  = __ballot_sync(kFullWarp, cur == kMarkLeaf);
+    const unsigned want_enter = __ballot_sync(kFullWarp, cur < 0 && cur > kMarkLeaf);
+    const unsigned busy       = want_node | want_prim | want_enter;
+    const int      n_idle     = 32 - __popc(busy);
+
+    if (more && n_idle >= kRefillThreshold) {
+      // ---- refill: finished lanes hand over their hit and take the next queued ray ----
+      const bool idle = cur == kMarkDone;
+      if (idle && have) src.commit(res);
+      f3 o, d;
+      const bool got = src.fetch(idle, o, d, more);
+      if (idle) have = got;
+      if (got) {
+        world = make_ray(o, d);
+        ray   = world;
+        tmax  = kFltMax;
+        res   = {-1, -1, {0, 0}, 0, false};
+        sp = 0, bottom = false;
+        nodes = scene.top_nodes;
+        cur   = scene.top_num_nodes > 0 ? 0 : kMarkDone;
       }
+      continue;
     }
-    if (cur < 0 && cur > kMarkLeaf) cur = enter(scene.top_packets + ~cur);
+    if (!busy) break;
+    const int n_node = __popc(want_node), n_prim = __popc(want_prim), n_enter = __popc(want_enter);
+
+    if (n_node >= n_prim && n_node >= n_enter) {
+      if (cur >= 0) {
+        float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
+        bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
+                                : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
+        int      start = __float_as_int(n1.z);
+        unsigned meta  = (unsigned)__float_as_int(n1.w);
+        if (!inside) {
+          cur = advance();
+        } else if (meta >> 24) {
+          int neg     = (ray.sgn >> ((meta >> 16) & 0xff)) & 1;
+          stack[sp++] = start + 1 - neg;
+          cur         = start + neg;
+        } else if (bottom) {
+          leaf_next = start;
+          leaf_end  = start + (int)(meta & 0xffff);
+          cur       = leaf_next < leaf_end ? kMarkLeaf : advance();
+        } else {
+          for (int idx = start + (int)(meta & 0xffff) - 1; idx >= start; idx--) stack[sp++] = ~idx;
+          cur = advance();
+        }
+      }
+    } else if (n_prim >= n_enter) {
+      if (cur == kMarkLeaf) {
+        const int idx = leaf_next++;
+        f2    puv = {0, 0};
+        float pd  = 0;
+        bool  h;
+        if (kind == kElemTriangles) {
+          float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
+          h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
+        } else if (kind == kElemQuads) {
+          float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
+                 e = __ldg(packets + 4 * idx + 3);
+          h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
+              f3{e.x, e.y, e.z}, puv, pd);
+        } else if (kind == kElemLines) {
+          float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
+          h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
+        } else {
+          float4 a = __ldg(packets + idx);
+          h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
+        }
+        if (h) {
+          res  = {cur_instance, __ldg(prims + idx), puv, pd, true};
+          tmax = pd;
+        }
+        if (leaf_next == leaf_end) cur = advance();
+      }
+    } else {
+      if (cur < 0 && cur > kMarkLeaf) cur = enter(scene.top_packets + ~cur);
+    }
   }
-  return res;
+  // lanes still holding an uncommitted result (more == false path)
+  if (have && cur == kMarkDone) src.commit(res);
 }
 
 }  // namespace ygl
