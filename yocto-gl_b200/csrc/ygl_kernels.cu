@@ -136,7 +136,7 @@ struct ExtendSource {
   }
 };
 
-__global__ void __launch_bounds__(128) k_extend(DScene scene, PathState st, Queues q, int parity) {
+__global__ void __launch_bounds__(128, 6) k_extend(DScene scene, PathState st, Queues q, int parity) {
   Counters*    c = q.counters;
   const int    n = c->n_ext[parity];
   ExtendSource src{q.ext[parity], n, &c->ext_head, st, 0};

@@ -321,8 +321,9 @@ constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
 
 template <class Source>
 YGL_D void trace_stream(const DScene& scene, Source& src) {
-  int   stack[2 * kStackSize + 8];
-  int   sp  = 0;
+  int stack[2 * kStackSize + 8];
+  stack[0]  = kMarkDone;  // sentinel: popping an empty stack yields "done"
+  int   sp  = 1;
   hit_t res = {-1, -1, {0, 0}, 0, false};
 
   const float tmin = kRayEps;
@@ -336,8 +337,11 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
   int  kind = kElemNone, cur_instance = -1;
   bool bottom = false, have = false, more = true;
 
-  auto pop   = [&]() { return sp > 0 ? stack[--sp] : kMarkDone; };
-  auto enter = [&](const DInstancePacket* pk) {
+  // ENTER entries carry a run of instances of one top-level leaf: ~(first | (count - 1) << 28)
+  auto enter = [&](int entry) {
+    const int run = ~entry, first = run & 0x0fffffff, left = run >> 28;
+    if (left > 0) stack[sp++] = ~((first + 1) | ((left - 1) << 28));  // next instance of the leaf, same order
+    const DInstancePacket* pk = scene.top_packets + first;
     float4 a = __ldg(&pk->q[0]), b = __ldg(&pk->q[1]), c = __ldg(&pk->q[2]), e = __ldg(&pk->q[3]);
     float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
     frame3 inv = {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}, {c.y, c.z, c.w}};
@@ -352,13 +356,15 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
     return 0;
   };
   auto advance = [&]() {
-    while (true) {
-      int v = pop();
-      if (v != kMarkExit) return v;
+    int v = stack[--sp];
+    if (v == kMarkExit) {  // leaving an instance: back to the world-space ray; never two EXITs in a row
       ray    = world;
       nodes  = scene.top_nodes;
       bottom = false;
+      v      = stack[--sp];
     }
+    if (v == kMarkDone) sp = 1;
+    return v;
   };
 
   int cur = kMarkDone, leaf_next = 0, leaf_end = 0;
@@ -381,7 +387,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
         ray   = world;
         tmax  = kFltMax;
         res   = {-1, -1, {0, 0}, 0, false};
-        sp = 0, bottom = false;
+        sp = 1, bottom = false;
         nodes = scene.top_nodes;
         cur   = scene.top_num_nodes > 0 ? 0 : kMarkDone;
       }
@@ -408,8 +414,9 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
           leaf_end  = start + (int)(meta & 0xffff);
           cur       = leaf_next < leaf_end ? kMarkLeaf : advance();
         } else {
-          for (int idx = start + (int)(meta & 0xffff) - 1; idx >= start; idx--) stack[sp++] = ~idx;
-          cur = advance();
+          // leaf of the instance tree (<= 4 instances, visited in order): one ENTER entry for the run
+          const int num = (int)(meta & 0xffff);
+          cur           = num > 0 ? ~(start | ((num - 1) << 28)) : advance();
         }
       }
     } else if (n_prim >= n_enter) {
@@ -440,7 +447,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
         if (leaf_next == leaf_end) cur = advance();
       }
     } else {
-      if (cur < 0 && cur > kMarkLeaf) cur = enter(scene.top_packets + ~cur);
+      if (cur < 0 && cur > kMarkLeaf) cur = enter(cur);
     }
   }
   // lanes still holding an uncommitted result (more == false path)
