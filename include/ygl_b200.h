@@ -261,9 +261,19 @@ int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene
 int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
     int* width, int* height, float* image);
 /* Work counters of the last ygl_trace_samples / ygl_trace_image on this context:
- * [0] camera samples, [1] scene rays (intersect_scene calls), [2] instance rays
- * (intersect_instance calls), [3] wavefront iterations, [4] kernel launches */
-int ygl_trace_counters(ygl_context* ctx, uint64_t counters[8]);
+ * [0] camera samples, [1] scene rays (intersect_scene calls), [2] instance rays (intersect_instance
+ * calls), [3] wavefront iterations, [4] kernel launches, [5] extend-kernel launches; with traversal
+ * counting enabled (ygl_context_set_profiling) also, for the scene rays of the extend kernel:
+ * [6] instance-tree nodes popped, [7] shape-tree nodes popped, [8] instance visits,
+ * [9] triangle, [10] quad, [11] line, [12] point tests (SURVEY.md 8d algorithmic-bytes inputs). */
+int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]);
+/* Measurement hooks. time_kernels != 0: bracket every extend-kernel launch and the whole sample loop
+ * with CUDA events on the context stream. count_traversal != 0: run the counting variant of the
+ * extend kernel (slower; never combine with timing you report). */
+int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_traversal);
+/* Timings of the last ygl_trace_samples / ygl_trace_image with time_kernels on:
+ * [0] sum of extend-kernel launch durations (ms), [1] whole sample loop (ms), [2] extend launches. */
+int ygl_trace_timings(ygl_context* ctx, double ms[4]);
 
 /* Batch form of intersect_scene_bvh (instance < 0) / intersect_instance_bvh (instance >= 0).
  * rays/out are HOST arrays of n elements. */

@@ -66,5 +66,16 @@ def image_stats(a, b):
     rmse = float(np.sqrt(np.mean(diff ** 2)))
     per_pixel = np.abs(diff).max(axis=-1)
     exact = (a.view(np.uint32) == b.view(np.uint32)).all(axis=-1)
-    return dict(rmse=rmse, max_abs=float(per_pixel.max()), frac_exact=float(exact.mean()),
-                frac_gt_1e4=float((per_pixel > 1e-4).mean()))
+    keep = per_pixel <= 1e-4  # pixels without a diverged path (see tolerance note in test_gpu_parity)
+    rmse_same_paths = float(np.sqrt(np.mean(diff[keep] ** 2))) if keep.any() else 0.0
+    return dict(rmse=rmse, rmse_same_paths=rmse_same_paths, max_abs=float(per_pixel.max()),
+                frac_exact=float(exact.mean()), frac_gt_1e4=float((per_pixel > 1e-4).mean()))
+
+
+def assert_close_to_reference(stats):
+    """Stated float tolerance against the UNMODIFIED reference (glibc float libm): pixels whose
+    paths took the same decisions agree to RMSE < 1e-5; a last-bit libm difference may flip a
+    discrete decision of a path (light pick, lobe choice, russian roulette), which we bound at
+    < 0.2 % of pixels differing by more than 1e-4 at these low sample counts."""
+    assert stats["rmse_same_paths"] < 1e-5, stats
+    assert stats["frac_gt_1e4"] < 2e-3, stats

@@ -74,7 +74,12 @@ struct ygl_context {
   Counters* counters    = nullptr;
   int*      h_done      = nullptr;  // pinned
   cudaEvent_t ev[2]     = {nullptr, nullptr};
-  uint64_t  stats[8]    = {0};
+  uint64_t  stats[16]   = {0};
+  double    timings[4]  = {0};
+  bool      time_kernels = false, count_traversal = false;
+  unsigned long long*      d_trav = nullptr;  // 7 traversal counters
+  std::vector<cudaEvent_t> ev_pool;           // event pairs around extend launches
+  cudaEvent_t              ev_loop[2] = {nullptr, nullptr};
   // binding cache: DShape table for a (scene, bvh, lights) triple
   const ygl_scene*  bound_scene  = nullptr;
   const ygl_bvh*    bound_bvh    = nullptr;
@@ -167,6 +172,9 @@ int ygl_context_create(int device, ygl_context** out) {
   CUDA_TRY(cudaHostAlloc((void**)&ctx->h_done, 2 * sizeof(int), cudaHostAllocDefault));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreate(&ctx->ev_loop[0]));
+  CUDA_TRY(cudaEventCreate(&ctx->ev_loop[1]));
+  CUDA_TRY(cudaMalloc((void**)&ctx->d_trav, 8 * sizeof(unsigned long long)));
   *out = ctx.release();
   return YGL_OK;
 }
@@ -183,6 +191,10 @@ void ygl_context_destroy(ygl_context* ctx) {
   if (ctx->h_done) cudaFreeHost(ctx->h_done);
   if (ctx->d_shapes) cudaFree(ctx->d_shapes);
   if (ctx->d_lights) cudaFree(ctx->d_lights);
+  if (ctx->d_trav) cudaFree(ctx->d_trav);
+  for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_loop)
+    if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -694,11 +706,28 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   bool       pending[2] = {false, false};
   const int  check_every = 4;
   ctx->h_done[0] = ctx->h_done[1] = 0;
+  const bool timing = ctx->time_kernels;
+  unsigned long long* trav = ctx->count_traversal ? ctx->d_trav : nullptr;
+  if (trav) CUDA_TRY(cudaMemsetAsync(trav, 0, 8 * sizeof(unsigned long long), s));
+  size_t ev_used = 0;
+  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[0], s));
   while (true) {
     for (int k = 0; k < check_every; k++) {
       launch_begin_iteration(s, q, parity);
       launch_generate(s, light, ctx->dscene, st, q, kp, parity);
-      launch_extend(s, heavy, ctx->dscene, st, q, parity);
+      if (timing) {
+        while (ctx->ev_pool.size() < ev_used + 2) {
+          cudaEvent_t e;
+          CUDA_TRY(cudaEventCreate(&e));
+          ctx->ev_pool.push_back(e);
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used], s));
+      }
+      launch_extend(s, heavy, ctx->dscene, st, q, parity, trav);
+      if (timing) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used + 1], s));
+        ev_used += 2;
+      }
       launch_shade(s, heavy, ctx->dscene, st, q, kp, parity);
       if (path_like) launch_lightpdf(s, heavy, ctx->dscene, st, q, kp, parity);
       launch_accumulate(s, light, ctx->dscene, st, q, kp, parity);
@@ -718,6 +747,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     pending[slot] = true;
     slot          = 1 - slot;
   }
+  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[1], s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
   Counters c;
@@ -727,6 +757,25 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   ctx->stats[2] += c.instance_rays;
   ctx->stats[3] += iterations;
   ctx->stats[4] += launches;
+  ctx->stats[5] += iterations;
+  if (trav) {
+    unsigned long long t[8];
+    CUDA_TRY(cudaMemcpy(t, trav, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 7; k++) ctx->stats[6 + k] += t[k];
+  }
+  if (timing) {
+    double ext_ms = 0;
+    for (size_t k = 0; k + 1 < ev_used; k += 2) {
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]));
+      ext_ms += ms;
+    }
+    float loop_ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&loop_ms, ctx->ev_loop[0], ctx->ev_loop[1]));
+    ctx->timings[0] += ext_ms;
+    ctx->timings[1] += loop_ms;
+    ctx->timings[2] += (double)(ev_used / 2);
+  }
   state->samples += nsamples;
   return YGL_OK;
 }
@@ -757,12 +806,24 @@ int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (int rc = bind_scene(ctx, scene, bvh, lights)) return rc;
   memset(ctx->stats, 0, sizeof(ctx->stats));
+  memset(ctx->timings, 0, sizeof(ctx->timings));
   return run_wavefront(ctx, state, *params, params->batch);
 }
 
-int ygl_trace_counters(ygl_context* ctx, uint64_t counters[8]) {
+int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]) {
   if (!ctx || !counters) return fail(YGL_ERR_INVALID, "null argument");
   memcpy(counters, ctx->stats, sizeof(ctx->stats));
+  return YGL_OK;
+}
+int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_traversal) {
+  if (!ctx) return fail(YGL_ERR_INVALID, "null context");
+  ctx->time_kernels    = time_kernels != 0;
+  ctx->count_traversal = count_traversal != 0;
+  return YGL_OK;
+}
+int ygl_trace_timings(ygl_context* ctx, double ms[4]) {
+  if (!ctx || !ms) return fail(YGL_ERR_INVALID, "null argument");
+  memcpy(ms, ctx->timings, sizeof(ctx->timings));
   return YGL_OK;
 }
 
@@ -788,6 +849,7 @@ int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trac
     if ((rc = ygl_state_create(ctx, desc, params, &state))) break;
     if ((rc = bind_scene(ctx, scene, bvh, lights))) break;
     memset(ctx->stats, 0, sizeof(ctx->stats));
+    memset(ctx->timings, 0, sizeof(ctx->timings));
     // trace_image calls trace_samples `samples` times with `batch` samples each until
     // state.samples >= params.samples (yocto_trace.cpp:1588-1590); results are batch-invariant,
     // so the same total runs as one wavefront launch sequence.

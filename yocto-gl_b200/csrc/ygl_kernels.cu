@@ -136,11 +136,24 @@ struct ExtendSource {
   }
 };
 
-__global__ void __launch_bounds__(128, 6) k_extend(DScene scene, PathState st, Queues q, int parity) {
-  Counters*    c = q.counters;
-  const int    n = c->n_ext[parity];
-  ExtendSource src{q.ext[parity], n, &c->ext_head, st, 0};
-  trace_stream(scene, src);
+template <bool COUNT>
+__global__ void __launch_bounds__(128, 6) k_extend(DScene scene, PathState st, Queues q, int parity,
+    unsigned long long* trav) {
+  Counters*     c = q.counters;
+  const int     n = c->n_ext[parity];
+  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0};
+  trav_counters tc = {};
+  trace_stream<COUNT>(scene, src, tc);
+  if (COUNT) {
+    // traversal statistics for the algorithmic-bytes formula; counting runs are not timed
+    unsigned vals[7] = {tc.top_nodes, tc.bot_nodes, tc.instances, tc.prims_by_kind[kElemTriangles],
+        tc.prims_by_kind[kElemQuads], tc.prims_by_kind[kElemLines], tc.prims_by_kind[kElemPoints]};
+    for (int k = 0; k < 7; k++) {
+      unsigned v = vals[k];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFullWarp, v, off);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(trav + k, (unsigned long long)v);
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->scene_rays, (unsigned long long)n);
 }
 
@@ -627,13 +640,14 @@ void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, in
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   k_generate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }
-void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity) {
+void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity,
+    unsigned long long* trav) {
   // persistent kernel: exactly the resident capacity (SMs x blocks/SM from the occupancy API), capped
-  // by the lanes that can exist; cfg.blocks carries the SM count x per-SM factor chosen by the host
+  // by the lanes that can exist
   static int per_sm = 0;
   static int sms    = 0;
   if (!per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend<false>, 128, 0);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -644,7 +658,10 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
   if (blocks > needed) blocks = needed;
   if (blocks < 1) blocks = 1;
   (void)cfg;
-  k_extend<<<blocks, 128, 0, s>>>(scene, st, q, parity);
+  if (trav)
+    k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav);
+  else
+    k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr);
 }
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   if (p.sampler == kSamplerFalsecolor)

@@ -67,7 +67,9 @@ struct LaunchCfg {
 void launch_begin_iteration(cudaStream_t s, Queues q, int parity);
 void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin);
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
-void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity);
+// trav: device array of 7 counters {top nodes, bottom nodes, instance visits, tri, quad, line, point tests} or null
+void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity,
+    unsigned long long* trav);
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);

@@ -28,6 +28,7 @@ struct hit_t {
 
 struct trav_counters {  // per-thread traversal statistics (SURVEY.md §8d algorithmic bytes)
   unsigned top_nodes, bot_nodes, instances, prims;
+  unsigned prims_by_kind[5];  // indexed by kElem* (trace_stream only)
 };
 
 // intersect_bbox(ray, ray_dinv, bbox), yocto_geometry.h:854-864, with yocto's min/max
@@ -319,8 +320,8 @@ YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f
 // converged warps.
 constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
 
-template <class Source>
-YGL_D void trace_stream(const DScene& scene, Source& src) {
+template <bool COUNT, class Source>
+YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   int stack[2 * kStackSize + 8];
   stack[0]  = kMarkDone;  // sentinel: popping an empty stack yields "done"
   int   sp  = 1;
@@ -346,6 +347,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
     float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
     frame3 inv = {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}, {c.y, c.z, c.w}};
     ray          = make_ray(transform_point(inv, world.o), transform_vector(inv, world.d));
+    if (COUNT) cnt.instances++;
     cur_instance = __float_as_int(e.y);
     kind         = __float_as_int(e.z);
     nodes   = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.y) << 32) | (unsigned)__float_as_int(p0.x));
@@ -399,6 +401,10 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
     if (n_node >= n_prim && n_node >= n_enter) {
       if (cur >= 0) {
         float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
+        if (COUNT) {
+          if (bottom) cnt.bot_nodes++;
+          else cnt.top_nodes++;
+        }
         bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
                                 : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
         int      start = __float_as_int(n1.z);
@@ -422,6 +428,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src) {
     } else if (n_prim >= n_enter) {
       if (cur == kMarkLeaf) {
         const int idx = leaf_next++;
+        if (COUNT) cnt.prims_by_kind[kind]++;
         f2    puv = {0, 0};
         float pd  = 0;
         bool  h;

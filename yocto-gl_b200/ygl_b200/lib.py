@@ -24,7 +24,7 @@ EXPORTS = [
     "ygl_lights_get", "ygl_lights_destroy", "ygl_state_create", "ygl_state_create_tile",
     "ygl_state_size", "ygl_state_rows", "ygl_state_download", "ygl_state_upload",
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
-    "ygl_trace_counters", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_comm_id_size",
+    "ygl_trace_counters", "ygl_context_set_profiling", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
 ]
 
@@ -73,6 +73,8 @@ def load():
     lib.ygl_trace_samples.argtypes = [vp, vp, vp, vp, vp, P(abi.TraceParams)]
     lib.ygl_trace_image.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), P(i32), P(i32), vp]
     lib.ygl_trace_counters.argtypes = [vp, vp]
+    lib.ygl_context_set_profiling.argtypes = [vp, i32, i32]
+    lib.ygl_trace_timings.argtypes = [vp, vp]
     lib.ygl_intersect_rays.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.ygl_intersect_rays_device.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.ygl_comm_create_id.argtypes = [vp]
@@ -146,6 +148,15 @@ class Lights:
             pass
 
 
+def state_size(scene, params):
+    """Image size make_trace_state would choose (yocto_trace.cpp:1499-1505)."""
+    lib = load()
+    desc = scene.desc()
+    w, h = C.c_int(), C.c_int()
+    _check(lib.ygl_make_state_rngs(C.byref(desc), C.byref(params), C.byref(w), C.byref(h), None))
+    return w.value, h.value
+
+
 def make_state_rngs(scene, params):
     """Image size and rng table of make_trace_state (host only)."""
     lib = load()
@@ -172,10 +183,20 @@ class Context:
         return self.lib.ygl_context_stream(self.h)
 
     def counters(self):
-        c = np.zeros(8, np.uint64)
+        c = np.zeros(16, np.uint64)
         _check(self.lib.ygl_trace_counters(self.h, c.ctypes.data))
-        return dict(camera_samples=int(c[0]), scene_rays=int(c[1]), instance_rays=int(c[2]),
-                    iterations=int(c[3]), launches=int(c[4]))
+        names = ["camera_samples", "scene_rays", "instance_rays", "iterations", "launches",
+                 "extend_launches", "top_nodes", "bottom_nodes", "instance_visits", "triangle_tests",
+                 "quad_tests", "line_tests", "point_tests"]
+        return {k: int(v) for k, v in zip(names, c)}
+
+    def set_profiling(self, time_kernels=False, count_traversal=False):
+        _check(self.lib.ygl_context_set_profiling(self.h, int(time_kernels), int(count_traversal)))
+
+    def timings(self):
+        t = np.zeros(4, np.float64)
+        _check(self.lib.ygl_trace_timings(self.h, t.ctypes.data))
+        return dict(extend_ms=float(t[0]), loop_ms=float(t[1]), extend_launches=int(t[2]))
 
     def trace_image(self, scene, params):
         """trace_image: host scene -> host rgba image, everything inside one call."""
