@@ -190,3 +190,14 @@ def test_unsupported_sampler_and_errors(ctx):
         ctx.trace_image(scene, abi.trace_params(resolution=16, samples=1, camera=3))
     with pytest.raises(lib.YglError):
         lib.Context(99)
+
+
+def test_reference_side_shim_runs():
+    """The C++ drop-in (yocto::b200::trace_image through yocto_b200trace.h) next to yocto::trace_image
+    in one reference-side program (oracle/shim_demo.cpp, prebuilt where the reference headers exist)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "shim_demo")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shim_demo not built")
+    out = subprocess.run([exe, "96", "8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr

@@ -124,3 +124,21 @@ def test_tile_rows_partition():
             rows = [lib.tile_rows(h, r, n) for r in range(n)]
             assert rows[0][0] == 0 and rows[-1][1] == h
             assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+def test_reference_side_shim_compiles(tmp_path):
+    """yocto-gl_b200/host/yocto_b200trace.h (the binding a Yocto/GL maintainer would add) compiles
+    against the reference's own headers and links against libygl_b200.so; without a GPU the drop-in
+    fails loudly instead of falling back."""
+    import shutil
+    import subprocess
+    ref_root = "/root/reference/libs"
+    if not os.path.exists(os.path.join(ref_root, "yocto", "yocto_trace.h")) or not shutil.which("g++"):
+        pytest.skip("reference headers not available here")
+    src = tmp_path / "use_shim.cpp"
+    src.write_text('#include "yocto-gl_b200/host/yocto_b200trace.h"\n'
+                   "int main() { yocto::scene_data s; yocto::trace_params p; "
+                   "try { yocto::b200::trace_image(s, p); } catch (std::exception&) { return 7; } return 0; }\n")
+    obj = tmp_path / "use_shim.o"
+    subprocess.run(["g++", "-std=c++17", "-include", "cstdint", "-I", ref_root, "-I", ROOT, "-c", str(src), "-o",
+                    str(obj)], check=True)

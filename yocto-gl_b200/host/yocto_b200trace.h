@@ -1,0 +1,171 @@
+//
+// yocto_b200trace.h — the reference-side binding of libygl_b200.so.
+//
+// This is the file a Yocto/GL maintainer adds next to libs/yocto/yocto_cutrace.h: it mirrors the
+// CPU renderer's API (yocto_trace.h:116-190) one-to-one on top of the C ABI in include/ygl_b200.h,
+// exactly as yocto_cutrace.h:71-146 mirrors it for OptiX. It needs the reference headers
+// (<yocto/yocto_scene.h>, <yocto/yocto_trace.h>) and is therefore compiled only where they exist
+// (tests/test_host_parity.py::test_reference_side_shim_compiles does so in the dev container).
+//
+//   yocto::trace_image(scene, params)            ->  yocto::b200::trace_image(scene, params)
+//   make_trace_bvh / make_trace_lights / make_trace_state / trace_samples / get_image likewise.
+//
+// Errors of the C ABI come back as the exceptions the reference uses (yocto_trace.cpp:1437,
+// :1679-1691): YGL_ERR_INVALID -> std::invalid_argument, everything else -> std::runtime_error.
+//
+#ifndef YOCTO_B200TRACE_H
+#define YOCTO_B200TRACE_H
+
+#include <yocto/yocto_scene.h>
+#include <yocto/yocto_trace.h>
+
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/ygl_b200.h"
+
+namespace yocto::b200 {
+
+inline void check(int status) {
+  if (status == YGL_OK) return;
+  if (status == YGL_ERR_INVALID) throw std::invalid_argument{ygl_last_error()};
+  throw std::runtime_error{ygl_last_error()};
+}
+
+// Flat views of scene_data for the C ABI (storage for the converted PODs lives here).
+struct scene_views {
+  std::vector<ygl_camera>      cameras;
+  std::vector<ygl_instance>    instances;
+  std::vector<ygl_environment> environments;
+  std::vector<ygl_material>    materials;
+  std::vector<ygl_texture>     textures;
+  std::vector<ygl_shape>       shapes;
+  ygl_scene_desc               desc = {};
+};
+
+inline ygl_frame3f to_abi(const frame3f& f) {
+  return {{f.x.x, f.x.y, f.x.z}, {f.y.x, f.y.y, f.y.z}, {f.z.x, f.z.y, f.z.z}, {f.o.x, f.o.y, f.o.z}};
+}
+
+inline scene_views make_views(const scene_data& scene) {
+  auto v = scene_views{};
+  for (auto& c : scene.cameras)
+    v.cameras.push_back({to_abi(c.frame), c.orthographic ? 1 : 0, c.lens, c.film, c.aspect, c.focus, c.aperture});
+  for (auto& i : scene.instances) v.instances.push_back({to_abi(i.frame), i.shape, i.material});
+  for (auto& e : scene.environments)
+    v.environments.push_back({to_abi(e.frame), {e.emission.x, e.emission.y, e.emission.z}, e.emission_tex});
+  for (auto& m : scene.materials)
+    v.materials.push_back({(int)m.type, {m.emission.x, m.emission.y, m.emission.z}, {m.color.x, m.color.y, m.color.z},
+        m.roughness, m.metallic, m.ior, {m.scattering.x, m.scattering.y, m.scattering.z}, m.scanisotropy, m.trdepth,
+        m.opacity, m.emission_tex, m.color_tex, m.roughness_tex, m.scattering_tex, m.normal_tex});
+  for (auto& t : scene.textures)
+    v.textures.push_back({t.width, t.height, t.linear ? 1 : 0, t.nearest ? 1 : 0, t.clamp ? 1 : 0,
+        t.pixelsf.empty() ? nullptr : (const float*)t.pixelsf.data(),
+        t.pixelsb.empty() ? nullptr : (const uint8_t*)t.pixelsb.data()});
+  for (auto& s : scene.shapes)
+    v.shapes.push_back({(int)s.points.size(), (int)s.lines.size(), (int)s.triangles.size(), (int)s.quads.size(),
+        (const int32_t*)s.points.data(), (const int32_t*)s.lines.data(), (const int32_t*)s.triangles.data(),
+        (const int32_t*)s.quads.data(), (int)s.positions.size(), (int)s.normals.size(), (int)s.texcoords.size(),
+        (int)s.colors.size(), (int)s.radius.size(), (const float*)s.positions.data(), (const float*)s.normals.data(),
+        (const float*)s.texcoords.data(), (const float*)s.colors.data(), (const float*)s.radius.data()});
+  v.desc = {(int)v.cameras.size(), (int)v.instances.size(), (int)v.environments.size(), (int)v.shapes.size(),
+      (int)v.textures.size(), (int)v.materials.size(), v.cameras.data(), v.instances.data(), v.environments.data(),
+      v.shapes.data(), v.textures.data(), v.materials.data()};
+  return v;
+}
+
+inline ygl_trace_params to_abi(const trace_params& p) {
+  auto a = ygl_trace_params{};
+  a.camera = p.camera, a.resolution = p.resolution, a.sampler = (int)p.sampler, a.falsecolor = (int)p.falsecolor;
+  a.samples = p.samples, a.bounces = p.bounces, a.clamp = p.clamp;
+  a.nocaustics = p.nocaustics, a.envhidden = p.envhidden, a.tentfilter = p.tentfilter, a.seed = p.seed;
+  a.embreebvh = p.embreebvh, a.highqualitybvh = p.highqualitybvh, a.noparallel = p.noparallel;
+  a.pratio = p.pratio, a.denoise = p.denoise, a.batch = p.batch;
+  return a;
+}
+
+// RAII owners, like the cutrace_* types (yocto_cutrace.h:270-397)
+struct b200_context {
+  ygl_context* handle = nullptr;
+  explicit b200_context(int device = 0) { check(ygl_context_create(device, &handle)); }
+  b200_context(const b200_context&)            = delete;
+  b200_context& operator=(const b200_context&) = delete;
+  ~b200_context() { ygl_context_destroy(handle); }
+};
+struct b200_scene {
+  ygl_scene* handle = nullptr;
+  ~b200_scene() { ygl_scene_destroy(handle); }
+};
+struct b200_bvh {
+  ygl_bvh* handle = nullptr;
+  ~b200_bvh() { ygl_bvh_destroy(handle); }
+};
+struct b200_lights {
+  ygl_lights* handle = nullptr;
+  ~b200_lights() { ygl_lights_destroy(handle); }
+};
+struct b200_state {
+  ygl_state* handle = nullptr;
+  int        width = 0, height = 0;
+  ~b200_state() { ygl_state_destroy(handle); }
+};
+
+// make_cutrace_scene-style upload of scene_data
+inline std::unique_ptr<b200_scene> make_b200_scene(b200_context& ctx, const scene_data& scene) {
+  auto views = make_views(scene);
+  auto out   = std::make_unique<b200_scene>();
+  check(ygl_scene_create(ctx.handle, &views.desc, &out->handle));
+  return out;
+}
+// make_trace_bvh (yocto_trace.cpp:88)
+inline std::unique_ptr<b200_bvh> make_trace_bvh(const scene_data& scene, const trace_params& params) {
+  auto views = make_views(scene);
+  auto out   = std::make_unique<b200_bvh>();
+  check(ygl_bvh_build(&views.desc, params.highqualitybvh ? 1 : 0, &out->handle));
+  return out;
+}
+// make_trace_lights (yocto_trace.cpp:1528)
+inline std::unique_ptr<b200_lights> make_trace_lights(const scene_data& scene, const trace_params&) {
+  auto views = make_views(scene);
+  auto out   = std::make_unique<b200_lights>();
+  check(ygl_lights_create(&views.desc, &out->handle));
+  return out;
+}
+// make_trace_state (yocto_trace.cpp:1495)
+inline std::unique_ptr<b200_state> make_trace_state(
+    b200_context& ctx, const scene_data& scene, const trace_params& params) {
+  auto views = make_views(scene);
+  auto abi   = to_abi(params);
+  auto out   = std::make_unique<b200_state>();
+  check(ygl_state_create(ctx.handle, &views.desc, &abi, &out->handle));
+  check(ygl_state_size(out->handle, &out->width, &out->height, nullptr));
+  return out;
+}
+// trace_samples (yocto_trace.cpp:1595)
+inline void trace_samples(b200_context& ctx, b200_state& state, const b200_scene& scene, const b200_bvh& bvh,
+    const b200_lights& lights, const trace_params& params) {
+  auto abi = to_abi(params);
+  check(ygl_trace_samples(ctx.handle, state.handle, scene.handle, bvh.handle, lights.handle, &abi));
+}
+// get_image (yocto_trace.cpp:1694)
+inline image_data get_image(b200_state& state) {
+  auto image = make_image(state.width, state.height, true);
+  check(ygl_state_download(state.handle, (float*)image.pixels.data(), nullptr, nullptr, nullptr, nullptr));
+  return image;
+}
+// trace_image (yocto_trace.cpp:1584): the drop-in
+inline image_data trace_image(const scene_data& scene, const trace_params& params, int device = 0) {
+  auto ctx   = b200_context{device};
+  auto views = make_views(scene);
+  auto abi   = to_abi(params);
+  int  w = 0, h = 0;
+  check(ygl_trace_image(ctx.handle, &views.desc, &abi, &w, &h, nullptr));
+  auto image = make_image(w, h, true);
+  check(ygl_trace_image(ctx.handle, &views.desc, &abi, &w, &h, (float*)image.pixels.data()));
+  return image;
+}
+
+}  // namespace yocto::b200
+
+#endif
