@@ -209,10 +209,14 @@ def main():
         blob = idb.cpu().numpy()
         lib._check(lib.load().ygl_comm_init(ctx.h, blob.ctypes.data, rank, world))
 
+    def mk_state(p):
+        # N > 1: interleaved rows (row j -> rank j % N) balance sky against geometry; values are unaffected
+        return ds.make_state(p, interleave=(rank, world)) if world > 1 else ds.make_state(p)
+
     # ---- untimed counting pass: traversal statistics of THIS workload for the roofline ----
     ctx.set_profiling(False, True)
     cp = abi.trace_params(resolution=params.resolution, samples=2, bounces=params.bounces, batch=2)
-    cstate = ds.make_state(cp, rows=rows)
+    cstate = mk_state(cp)
     ds.trace_samples(cstate, cp)
     cc = ctx.counters()
     bytes_per_ray = algorithmic_bytes_per_ray(cc)
@@ -223,7 +227,7 @@ def main():
     n_total = args.warmup + args.steps
     steps_per_image = (spp_total + spp_step - 1) // spp_step
     n_states = (n_total + steps_per_image - 1) // steps_per_image
-    states = [ds.make_state(params, rows=rows) for _ in range(n_states)]
+    states = [mk_state(params) for _ in range(n_states)]
     stream = torch.cuda.ExternalStream(ctx.stream)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -286,7 +290,7 @@ def main():
         t0 = time.perf_counter()
         ep = abi.trace_params(resolution=params.resolution, samples=spp_total, bounces=params.bounces, batch=spp_total)
         eds = lib.DeviceScene(ctx, scene)          # host BVH/lights build + H2D of the whole scene arena
-        est = eds.make_state(ep, rows=rows)        # rng table build + H2D
+        est = eds.make_state(ep, interleave=(rank, world)) if world > 1 else eds.make_state(ep)  # rng table + H2D
         eds.trace_samples(est, ep)
         img = est.gather_image() if world > 1 else est.download()["image"]  # D2H (after ncclAllGather)
         sync_all()
@@ -296,8 +300,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             te = float(tt[0])
         assert np.isfinite(img).all()
-        h2d = scene_bytes(scene) + (rows[1] - rows[0]) * W * 16
-        d2h = W * H * 16 if world > 1 else (rows[1] - rows[0]) * W * 16
+        h2d = scene_bytes(scene) + est.num_rows * W * 16
+        d2h = W * H * 16
         e2e = {"value": W * H * spp_total / te / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "seconds": te,
                "what": "DeviceScene(host scene)+make_state+trace_samples(all spp)+image download, wall clock"}
@@ -341,7 +345,7 @@ def main():
         "ms_per_step": 1e3 * elapsed / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "spp_per_step": spp_step, "steps_per_image": steps_per_image,
-                   "image": [W, H], "tile_rows": list(rows), "l2": "per-step working set (path state 200 B/pixel "
+                   "image": [W, H], "tiling": "full image" if world == 1 else f"interleaved rows j % {world} == rank", "l2": "per-step working set (path state 200 B/pixel "
                    "x 2.07M pixels = 415 MB) exceeds the 126 MB L2", "parallelism": f"tiles{world}"},
         "Mrays_per_s_rank0": (agg["scene_rays"] + agg["instance_rays"]) / elapsed / 1e6,
         "wall_seconds": wall, "device_seconds": elapsed,

@@ -237,7 +237,13 @@ int  ygl_state_create(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_tr
  * table is still seeded for the full image so values equal the single-device run. */
 int  ygl_state_create_tile(ygl_context* ctx, const ygl_scene_desc* desc,
      const ygl_trace_params* params, int row_begin, int row_end, ygl_state** out);
+/* Interleaved tile for multi-GPU load balance: image rows rank, rank + nranks, rank + 2 nranks, ...
+ * (sky and geometry rows are spread evenly over the ranks; values are unaffected). */
+int  ygl_state_create_interleaved(ygl_context* ctx, const ygl_scene_desc* desc,
+     const ygl_trace_params* params, int rank, int nranks, ygl_state** out);
 int  ygl_state_size(const ygl_state* state, int* width, int* height, int* samples);
+/* first row, row stride and number of rows held by this state */
+int  ygl_state_layout(const ygl_state* state, int* row_first, int* row_step, int* num_rows);
 int  ygl_state_rows(const ygl_state* state, int* row_begin, int* row_end);
 /* Any pointer may be NULL. image: w*h*4 floats, albedo/normal: w*h*3, hits: w*h ints,
  * rngs: w*h*2 uint64 {state, inc} (rows of this tile only). */
@@ -294,7 +300,8 @@ int ygl_comm_init(ygl_context* ctx, const void* id_blob, int rank, int nranks);
 /* Row range of `rank` for an image of `height` rows: contiguous blocks of ceil(height/nranks). */
 void ygl_tile_rows(int height, int rank, int nranks, int* row_begin, int* row_end);
 /* ncclAllGather of every rank's tile of state.image into a full host image (w*h*4 floats,
- * may be NULL on ranks that do not want it) — the single collective of the path. */
+ * may be NULL on ranks that do not want it) — the single collective of the path. Accepts the
+ * contiguous tiling of ygl_tile_rows and the interleaved tiling of ygl_state_create_interleaved. */
 int  ygl_gather_image(ygl_context* ctx, ygl_state* state, float* image);
 void ygl_comm_destroy(ygl_context* ctx);
 

@@ -147,6 +147,14 @@ def test_tiles_equal_full_image(ctx):
         got[rows[0]:rows[1]] = st.download()["image"]
     assert want.tobytes() == got.tobytes()
     assert full.gather_image().tobytes() == want.tobytes()  # single rank: gather == download
+    # interleaved tiling (row j -> rank j % n), the layout bench.py uses for N > 1
+    got2 = np.zeros_like(want)
+    for r in range(4):
+        st = ds.make_state(params, interleave=(r, 4))
+        assert (st.row_first, st.row_step) == (r, 4)
+        ds.trace_samples(st, params)
+        got2[r::4] = st.download()["image"]
+    assert want.tobytes() == got2.tobytes()
 
 
 def test_golden_images(ctx):

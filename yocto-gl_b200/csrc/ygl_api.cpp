@@ -128,7 +128,8 @@ struct ygl_lights {
 struct ygl_state {
   ygl_context* ctx   = nullptr;
   int          width = 0, height = 0, samples = 0;
-  int          row_begin = 0, row_end = 0;
+  int          row_begin = 0, row_end = 0;  // rows [row_begin, row_end) with stride row_step
+  int          row_step = 1, num_rows = 0;
   PathState    st    = {};
   uint8_t*     mem   = nullptr;
 };
@@ -542,14 +543,16 @@ int ygl_make_state_rngs(const ygl_scene_desc* desc, const ygl_trace_params* para
   return YGL_OK;
 }
 
-int ygl_state_create_tile(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
-    int row_begin, int row_end, ygl_state** out) {
+// Rows row_begin, row_begin + row_step, ... below row_end of the full image.
+static int state_create_rows(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
+    int row_begin, int row_end, int row_step, ygl_state** out) {
   if (!ctx || !desc || !params || !out) return fail(YGL_ERR_INVALID, "null argument");
   int         w, h;
   std::string error;
   if (!state_size(*desc, *params, w, h, error)) return fail(YGL_ERR_INVALID, error);
   if (row_end < 0) row_end = h;
-  if (row_begin < 0 || row_begin > row_end || row_end > h) return fail(YGL_ERR_INVALID, "bad row range");
+  if (row_begin < 0 || row_begin > row_end || row_end > h || row_step < 1) return fail(YGL_ERR_INVALID, "bad row range");
+  const int num_rows = (row_end - row_begin + row_step - 1) / row_step;
   CUDA_TRY(cudaSetDevice(ctx->device));
   auto state       = std::make_unique<ygl_state>();
   state->ctx       = ctx;
@@ -557,7 +560,9 @@ int ygl_state_create_tile(ygl_context* ctx, const ygl_scene_desc* desc, const yg
   state->height    = h;
   state->row_begin = row_begin;
   state->row_end   = row_end;
-  size_t n         = (size_t)w * (row_end - row_begin);
+  state->row_step  = row_step;
+  state->num_rows  = num_rows;
+  size_t n         = (size_t)w * num_rows;
   size_t lanes     = std::max<size_t>(n, 1);
   // one allocation, 256-B aligned slices
   size_t off = 0;
@@ -575,7 +580,7 @@ int ygl_state_create_tile(ygl_context* ctx, const ygl_scene_desc* desc, const yg
   CUDA_TRY(cudaMemset(state->mem, 0, off));
   PathState& st = state->st;
   st.num_lanes  = (int)n;
-  st.width = w, st.height = h, st.row_begin = row_begin;
+  st.width = w, st.height = h, st.row_begin = row_begin, st.row_step = row_step;
   uint8_t* m  = state->mem;
   st.image    = (float4*)(m + o_image);
   st.albedo   = (float*)(m + o_albedo);
@@ -597,9 +602,25 @@ int ygl_state_create_tile(ygl_context* ctx, const ygl_scene_desc* desc, const yg
   // rng table: seeded sequentially over the FULL image (yocto_trace.cpp:1512-1515), tile slice uploaded
   std::vector<uint64_t> rngs((size_t)w * h * 2);
   state_rngs(*params, w, h, rngs.data());
-  if (n) CUDA_TRY(cudaMemcpy(st.rngs, rngs.data() + (size_t)row_begin * w * 2, n * 16, cudaMemcpyHostToDevice));
+  if (n)
+    CUDA_TRY(cudaMemcpy2D(st.rngs, (size_t)w * 16, rngs.data() + (size_t)row_begin * w * 2, (size_t)row_step * w * 16,
+        (size_t)w * 16, num_rows, cudaMemcpyHostToDevice));
   *out = state.release();
   return YGL_OK;
+}
+
+int ygl_state_create_tile(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
+    int row_begin, int row_end, ygl_state** out) {
+  return state_create_rows(ctx, desc, params, row_begin, row_end, 1, out);
+}
+int ygl_state_create_interleaved(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
+    int rank, int nranks, ygl_state** out) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(YGL_ERR_INVALID, "bad rank");
+  int         w, h;
+  std::string error;
+  if (!desc || !params) return fail(YGL_ERR_INVALID, "null argument");
+  if (!state_size(*desc, *params, w, h, error)) return fail(YGL_ERR_INVALID, error);
+  return state_create_rows(ctx, desc, params, std::min(rank, h), h, nranks, out);
 }
 
 int ygl_state_create(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params, ygl_state** out) {
@@ -617,6 +638,13 @@ int ygl_state_rows(const ygl_state* state, int* row_begin, int* row_end) {
   if (!state) return fail(YGL_ERR_INVALID, "null state");
   if (row_begin) *row_begin = state->row_begin;
   if (row_end) *row_end = state->row_end;
+  return YGL_OK;
+}
+int ygl_state_layout(const ygl_state* state, int* row_first, int* row_step, int* num_rows) {
+  if (!state) return fail(YGL_ERR_INVALID, "null state");
+  if (row_first) *row_first = state->row_begin;
+  if (row_step) *row_step = state->row_step;
+  if (num_rows) *num_rows = state->num_rows;
   return YGL_OK;
 }
 
@@ -978,21 +1006,26 @@ int ygl_gather_image(ygl_context* ctx, ygl_state* state, float* image) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   const int w = state->width, h = state->height;
   if (ctx->nranks == 1) {
-    if (state->row_begin != 0 || state->row_end != h) return fail(YGL_ERR_INVALID, "state is a partial tile but no communicator");
+    if (state->row_begin != 0 || state->row_end != h || state->row_step != 1)
+      return fail(YGL_ERR_INVALID, "state is a partial tile but no communicator");
     return image ? ygl_state_download(state, image, nullptr, nullptr, nullptr, nullptr) : YGL_OK;
   }
   if (!ctx->nccl_comm) return fail(YGL_ERR_NCCL, "communicator not initialised");
-  int rb, re;
-  ygl_tile_rows(h, ctx->rank, ctx->nranks, &rb, &re);
-  if (rb != state->row_begin || re != state->row_end) return fail(YGL_ERR_INVALID, "state rows do not match this rank's tile");
+  // two tilings: contiguous blocks of ceil(h/n) rows (ygl_tile_rows) or interleaved rows j % n == rank
+  const int  n           = ctx->nranks;
+  const bool interleaved = state->row_step == n && state->row_begin == std::min(ctx->rank, h) && n > 1;
+  int        rb, re;
+  ygl_tile_rows(h, ctx->rank, n, &rb, &re);
+  if (!interleaved && !(state->row_step == 1 && rb == state->row_begin && re == state->row_end))
+    return fail(YGL_ERR_INVALID, "state rows do not match this rank's tile");
   auto allgather = (pfn_ncclAllGather)dlsym(ctx->nccl_lib, "ncclAllGather");
   if (!allgather) return fail(YGL_ERR_NCCL, "ncclAllGather missing");
-  // equal-sized send buffers of ceil(h / nranks) rows; the last tile is padded
-  int     per   = (h + ctx->nranks - 1) / ctx->nranks;
+  // equal-sized send buffers of ceil(h / nranks) rows; short tiles are padded
+  int     per   = (h + n - 1) / n;
   size_t  count = (size_t)per * w * 4;  // floats per rank
   float * d_send = nullptr, *d_recv = nullptr;
   CUDA_TRY(cudaMalloc((void**)&d_send, count * sizeof(float)));
-  cudaError_t e = cudaMalloc((void**)&d_recv, count * sizeof(float) * ctx->nranks);
+  cudaError_t e = cudaMalloc((void**)&d_recv, count * sizeof(float) * n);
   if (e != cudaSuccess) {
     cudaFree(d_send);
     return fail(YGL_ERR_CUDA, "out of device memory");
@@ -1005,7 +1038,19 @@ int ygl_gather_image(ygl_context* ctx, ygl_state* state, float* image) {
       rc = fail(YGL_ERR_NCCL, "ncclAllGather failed: " + std::to_string(nrc));
       break;
     }
-    if (image) cudaMemcpyAsync(image, d_recv, (size_t)w * h * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (image) {
+      if (!interleaved) {
+        cudaMemcpyAsync(image, d_recv, (size_t)w * h * 16, cudaMemcpyDeviceToHost, ctx->stream);
+      } else {
+        // chunk r holds rows r, r+n, r+2n, ...: de-interleave with one strided copy per rank
+        const size_t rowb = (size_t)w * 16;
+        for (int r = 0; r < n && r < h; r++) {
+          int nrows = (h - r + n - 1) / n;
+          cudaMemcpy2DAsync((char*)image + r * rowb, n * rowb, (const char*)d_recv + (size_t)r * per * rowb, rowb, rowb,
+              nrows, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+      }
+    }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(YGL_ERR_CUDA, "gather failed");
   } while (false);
   cudaFree(d_send);

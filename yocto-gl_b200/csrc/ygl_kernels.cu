@@ -87,8 +87,7 @@ __global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Qu
     int  lane  = 0;
     if (valid) {
       lane      = q.gen[parity][i];
-      int idx   = lane + st.row_begin * st.width;
-      int px    = idx % st.width, py = idx / st.width;
+      int px = lane % st.width, py = st.row_begin + (lane / st.width) * st.row_step;
       rng_t rng = load_rng(st, lane);
       f2 luv    = rand2f(rng);
       f2 puv    = rand2f(rng);

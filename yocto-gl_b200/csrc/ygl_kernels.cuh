@@ -13,7 +13,7 @@ namespace ygl {
 // sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
 struct PathState {
   int num_lanes;  // pixels in this tile
-  int width, height, row_begin;
+  int width, height, row_begin, row_step;  // lane l <-> pixel (l % width, row_begin + (l / width) * row_step)
   // ---- trace_state accumulators (reference layout, yocto_trace.h:147-157) ----
   float4*     image;   // vec4f
   float*      albedo;  // vec3f packed

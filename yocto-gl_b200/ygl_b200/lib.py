@@ -22,7 +22,7 @@ EXPORTS = [
     "ygl_scene_update_cameras", "ygl_scene_destroy", "ygl_bvh_build", "ygl_bvh_tree_size",
     "ygl_bvh_tree_get", "ygl_bvh_destroy", "ygl_lights_create", "ygl_lights_count",
     "ygl_lights_get", "ygl_lights_destroy", "ygl_state_create", "ygl_state_create_tile",
-    "ygl_state_size", "ygl_state_rows", "ygl_state_download", "ygl_state_upload",
+    "ygl_state_create_interleaved", "ygl_state_layout", "ygl_state_size", "ygl_state_rows", "ygl_state_download", "ygl_state_upload",
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
     "ygl_trace_counters", "ygl_context_set_profiling", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
@@ -64,6 +64,8 @@ def load():
     lib.ygl_lights_destroy.argtypes = [vp]
     lib.ygl_state_create.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), P(vp)]
     lib.ygl_state_create_tile.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), i32, i32, P(vp)]
+    lib.ygl_state_create_interleaved.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), i32, i32, P(vp)]
+    lib.ygl_state_layout.argtypes = [vp, P(i32), P(i32), P(i32)]
     lib.ygl_state_size.argtypes = [vp, P(i32), P(i32), P(i32)]
     lib.ygl_state_rows.argtypes = [vp, P(i32), P(i32)]
     lib.ygl_state_download.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -227,8 +229,9 @@ class DeviceScene:
         self.bvh = Bvh(scene, highquality)
         self.lights = Lights(scene)
 
-    def make_state(self, params, rows=None):
-        return State(self, params, rows)
+    def make_state(self, params, rows=None, interleave=None):
+        """rows=(begin, end): contiguous tile; interleave=(rank, nranks): rows rank, rank+nranks, ..."""
+        return State(self, params, rows, interleave)
 
     def trace_samples(self, state, params):
         _check(self.lib.ygl_trace_samples(self.ctx.h, state.h, self.h, self.bvh.h, self.lights.h,
@@ -255,10 +258,14 @@ class DeviceScene:
 class State:
     """trace_state: resumable per-pixel accumulators + rng streams, resident on the device."""
 
-    def __init__(self, dscene, params, rows=None):
+    def __init__(self, dscene, params, rows=None, interleave=None):
         self.lib, self.ctx = dscene.lib, dscene.ctx
         self.h = C.c_void_p()
-        if rows is None:
+        if interleave is not None:
+            _check(self.lib.ygl_state_create_interleaved(self.ctx.h, C.byref(dscene.desc),
+                                                         C.byref(params), interleave[0],
+                                                         interleave[1], C.byref(self.h)))
+        elif rows is None:
             _check(self.lib.ygl_state_create(self.ctx.h, C.byref(dscene.desc), C.byref(params),
                                              C.byref(self.h)))
         else:
@@ -270,6 +277,9 @@ class State:
         rb, re = C.c_int(), C.c_int()
         _check(self.lib.ygl_state_rows(self.h, C.byref(rb), C.byref(re)))
         self.width, self.height, self.rows = w.value, h.value, (rb.value, re.value)
+        first, step, nrows = C.c_int(), C.c_int(), C.c_int()
+        _check(self.lib.ygl_state_layout(self.h, C.byref(first), C.byref(step), C.byref(nrows)))
+        self.row_first, self.row_step, self.num_rows = first.value, step.value, nrows.value
 
     @property
     def samples(self):
@@ -278,7 +288,7 @@ class State:
         return s.value
 
     def download(self, full=False):
-        nrows = self.rows[1] - self.rows[0]
+        nrows = self.num_rows
         image = np.zeros((nrows, self.width, 4), np.float32)
         if not full:
             _check(self.lib.ygl_state_download(self.h, _p(image), None, None, None, None))
