@@ -31,15 +31,17 @@ t0 = time.time()
 ds = lib.DeviceScene(ctx, scene)
 print(f"bvh+lights+upload in {time.time() - t0:.2f}s", flush=True)
 params = abi.trace_params(resolution=res, samples=spp * (reps + 1), bounces=bounces, batch=spp)
-state = ds.make_state(params)
+tile = os.environ.get("TILE")  # "rank,nranks": emulate one rank of an N-GPU run
+state = ds.make_state(params, interleave=tuple(int(x) for x in tile.split(","))) if tile else ds.make_state(params)
+ctx.set_profiling(bool(os.environ.get("PROFILE")), False)
 for r in range(reps + 1):
     t0 = time.time()
     ds.trace_samples(state, params)
     ctx.synchronize()
     dt = time.time() - t0
     c = ctx.counters()
-    n = state.width * state.height * spp
+    n = state.width * state.num_rows * spp
     print(f"{config} {state.width}x{state.height} {spp}spp: {dt * 1e3:.1f} ms  {n / dt / 1e6:.2f} Msamples/s  "
           f"{(c['scene_rays'] + c['instance_rays']) / dt / 1e6:.1f} Mrays/s  rays/sample "
           f"{c['scene_rays'] / n:.2f}+{c['instance_rays'] / n:.2f}  iters {c['iterations']} launches {c['launches']}",
-          flush=True)
+          ctx.timings() if os.environ.get("PROFILE") else "", flush=True)

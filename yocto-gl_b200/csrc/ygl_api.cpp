@@ -68,12 +68,19 @@ struct ygl_context {
   int          device = 0;
   cudaStream_t stream = nullptr;
   int          num_sms = 0;
-  // scratch queues sized for the largest state seen
-  int       queue_lanes = 0;
-  int*      queue_mem   = nullptr;
-  Counters* counters    = nullptr;
-  int*      h_done      = nullptr;  // pinned
-  cudaEvent_t ev[2]     = {nullptr, nullptr};
+  // Wavefront pipelines: lanes of a state are split over up to kMaxPipes independent queue sets that run
+  // on their own streams, so one pipeline's kernel ramp-up/drain overlaps the other's work (matters when a
+  // tile is small, i.e. multi-GPU). Pipe 0 runs on `stream`.
+  static constexpr int kMaxPipes = 2;
+  struct Pipe {
+    cudaStream_t stream      = nullptr;
+    int          queue_lanes = 0;
+    int*         queue_mem   = nullptr;
+    Counters*    counters    = nullptr;
+    int*         h_done      = nullptr;  // pinned, 2 slots
+    cudaEvent_t  ev[2]       = {nullptr, nullptr};
+    cudaEvent_t  join        = nullptr;
+  } pipes[kMaxPipes];
   uint64_t  stats[16]   = {0};
   double    timings[4]  = {0};
   bool      time_kernels = false, count_traversal = false;
@@ -168,11 +175,17 @@ int ygl_context_create(int device, ygl_context** out) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaMalloc((void**)&ctx->counters, sizeof(Counters)));
-  CUDA_TRY(cudaMemset(ctx->counters, 0, sizeof(Counters)));
-  CUDA_TRY(cudaHostAlloc((void**)&ctx->h_done, 2 * sizeof(int), cudaHostAllocDefault));
-  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming));
+  for (int k = 0; k < ygl_context::kMaxPipes; k++) {
+    auto& pipe = ctx->pipes[k];
+    if (k == 0) pipe.stream = ctx->stream;
+    else CUDA_TRY(cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc((void**)&pipe.counters, sizeof(Counters)));
+    CUDA_TRY(cudaMemset(pipe.counters, 0, sizeof(Counters)));
+    CUDA_TRY(cudaHostAlloc((void**)&pipe.h_done, 2 * sizeof(int), cudaHostAllocDefault));
+    CUDA_TRY(cudaEventCreateWithFlags(&pipe.ev[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&pipe.ev[1], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&pipe.join, cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaEventCreate(&ctx->ev_loop[0]));
   CUDA_TRY(cudaEventCreate(&ctx->ev_loop[1]));
   CUDA_TRY(cudaMalloc((void**)&ctx->d_trav, 8 * sizeof(unsigned long long)));
@@ -187,16 +200,22 @@ void ygl_context_destroy(ygl_context* ctx) {
   cudaSetDevice(ctx->device);
   ygl_comm_destroy(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  if (ctx->queue_mem) cudaFree(ctx->queue_mem);
-  if (ctx->counters) cudaFree(ctx->counters);
-  if (ctx->h_done) cudaFreeHost(ctx->h_done);
+  for (int k = 0; k < ygl_context::kMaxPipes; k++) {
+    auto& pipe = ctx->pipes[k];
+    if (pipe.stream) cudaStreamSynchronize(pipe.stream);
+    if (pipe.queue_mem) cudaFree(pipe.queue_mem);
+    if (pipe.counters) cudaFree(pipe.counters);
+    if (pipe.h_done) cudaFreeHost(pipe.h_done);
+    for (auto& e : pipe.ev)
+      if (e) cudaEventDestroy(e);
+    if (pipe.join) cudaEventDestroy(pipe.join);
+    if (k > 0 && pipe.stream) cudaStreamDestroy(pipe.stream);
+  }
   if (ctx->d_shapes) cudaFree(ctx->d_shapes);
   if (ctx->d_lights) cudaFree(ctx->d_lights);
   if (ctx->d_trav) cudaFree(ctx->d_trav);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   for (auto& e : ctx->ev_loop)
-    if (e) cudaEventDestroy(e);
-  for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -686,106 +705,149 @@ void ygl_state_destroy(ygl_state* state) {
 }
 
 // ------------------------------------------------------------------------------------------
-static int ensure_queues(ygl_context* ctx, int lanes) {
-  if (lanes <= ctx->queue_lanes) return YGL_OK;
-  if (ctx->queue_mem) cudaFree(ctx->queue_mem), ctx->queue_mem = nullptr;
+static int ensure_queues(ygl_context::Pipe& pipe, int lanes) {
+  if (lanes <= pipe.queue_lanes) return YGL_OK;
+  if (pipe.queue_mem) cudaFree(pipe.queue_mem), pipe.queue_mem = nullptr;
   size_t per = ((size_t)lanes + 63) & ~size_t(63);
-  CUDA_TRY(cudaMalloc((void**)&ctx->queue_mem, per * 6 * sizeof(int)));
-  ctx->queue_lanes = lanes;
+  CUDA_TRY(cudaMalloc((void**)&pipe.queue_mem, per * 6 * sizeof(int)));
+  pipe.queue_lanes = lanes;
   return YGL_OK;
 }
-static Queues make_queues(ygl_context* ctx) {
-  size_t per = ((size_t)ctx->queue_lanes + 63) & ~size_t(63);
+static Queues make_queues(ygl_context::Pipe& pipe) {
+  size_t per = ((size_t)pipe.queue_lanes + 63) & ~size_t(63);
   Queues q;
-  q.gen[0]   = ctx->queue_mem + 0 * per;
-  q.gen[1]   = ctx->queue_mem + 1 * per;
-  q.ext[0]   = ctx->queue_mem + 2 * per;
-  q.ext[1]   = ctx->queue_mem + 3 * per;
-  q.lpdf     = ctx->queue_mem + 4 * per;
-  q.acc      = ctx->queue_mem + 5 * per;
-  q.counters = ctx->counters;
+  q.gen[0]   = pipe.queue_mem + 0 * per;
+  q.gen[1]   = pipe.queue_mem + 1 * per;
+  q.ext[0]   = pipe.queue_mem + 2 * per;
+  q.ext[1]   = pipe.queue_mem + 3 * per;
+  q.lpdf     = pipe.queue_mem + 4 * per;
+  q.acc      = pipe.queue_mem + 5 * per;
+  q.counters = pipe.counters;
   return q;
 }
 
 // The wavefront driver: runs `nsamples` more samples on every lane of the state.
 static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
-  cudaStream_t s  = ctx->stream;
-  PathState&   st = state->st;
+  PathState& st = state->st;
   if (st.num_lanes == 0 || nsamples <= 0) return YGL_OK;
-  if (int rc = ensure_queues(ctx, st.num_lanes)) return rc;
-  Queues  q = make_queues(ctx);
   KParams kp;
   kp.camera = params.camera, kp.sampler = params.sampler, kp.falsecolor = params.falsecolor;
   kp.bounces = params.bounces, kp.clamp = params.clamp;
   kp.nocaustics = params.nocaustics, kp.envhidden = params.envhidden, kp.tentfilter = params.tentfilter;
   kp.sample_end = state->samples + nsamples;
 
-  // persistent-style grids: a multiple of the SM count, capped by the work available
-  auto grid_for = [&](int threads, int per_sm) {
-    int blocks = std::min(ctx->num_sms * per_sm, (st.num_lanes + threads - 1) / threads);
-    return LaunchCfg{std::max(blocks, 1), threads};
-  };
-  LaunchCfg light = grid_for(256, 8), heavy = grid_for(256, 8);
+  // Pipelines: lanes can be split over independent queue sets on separate streams (ramp-up/drain of one
+  // overlapping the other).
+  int npipes = 1;  // measured on B200 (C3, 1/8 tile): 2 pipelines were 7 % slower than 1 -> opt-in via YGL_PIPES
+  if (const char* env = getenv("YGL_PIPES")) npipes = std::max(1, std::min(ygl_context::kMaxPipes, atoi(env)));
+  struct Run {
+    ygl_context::Pipe* pipe;
+    Queues             q;
+    int                lo, hi, parity = 0, slot = 0;
+    bool               pending[2] = {false, false}, done = false;
+    LaunchCfg          light, heavy;
+  } runs[ygl_context::kMaxPipes];
+  for (int j = 0; j < npipes; j++) {
+    Run& r = runs[j];
+    r.pipe = &ctx->pipes[j];
+    r.lo   = (int)((long long)st.num_lanes * j / npipes);
+    r.hi   = (int)((long long)st.num_lanes * (j + 1) / npipes);
+    if (int rc = ensure_queues(*r.pipe, r.hi - r.lo)) return rc;
+    r.q = make_queues(*r.pipe);
+    // persistent-style grids: a multiple of the SM count, capped by the work available
+    int lanes  = r.hi - r.lo;
+    int blocks = std::max(1, std::min(ctx->num_sms * 8, (lanes + 255) / 256));
+    r.light = r.heavy = LaunchCfg{blocks, 256};
+    r.pipe->h_done[0] = r.pipe->h_done[1] = 0;
+  }
+  cudaStream_t s0 = ctx->stream;
 
-  launch_seed_lanes(s, light, st, q, 0, state->samples);
   const bool path_like = params.sampler == YGL_SAMPLER_PATH;
-  int        parity = 0, slot = 0;
-  uint64_t   iterations = 0, launches = 1;
-  bool       pending[2] = {false, false};
+  uint64_t   iterations = 0, launches = 0;
   const int  check_every = 4;
-  ctx->h_done[0] = ctx->h_done[1] = 0;
   const bool timing = ctx->time_kernels;
   unsigned long long* trav = ctx->count_traversal ? ctx->d_trav : nullptr;
-  if (trav) CUDA_TRY(cudaMemsetAsync(trav, 0, 8 * sizeof(unsigned long long), s));
+  if (trav) CUDA_TRY(cudaMemsetAsync(trav, 0, 8 * sizeof(unsigned long long), s0));
   size_t ev_used = 0;
-  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[0], s));
-  while (true) {
-    for (int k = 0; k < check_every; k++) {
-      launch_begin_iteration(s, q, parity);
-      launch_generate(s, light, ctx->dscene, st, q, kp, parity);
-      if (timing) {
-        while (ctx->ev_pool.size() < ev_used + 2) {
-          cudaEvent_t e;
-          CUDA_TRY(cudaEventCreate(&e));
-          ctx->ev_pool.push_back(e);
-        }
-        CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used], s));
-      }
-      launch_extend(s, heavy, ctx->dscene, st, q, parity, trav);
-      if (timing) {
-        CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used + 1], s));
-        ev_used += 2;
-      }
-      launch_shade(s, heavy, ctx->dscene, st, q, kp, parity);
-      if (path_like) launch_lightpdf(s, heavy, ctx->dscene, st, q, kp, parity);
-      launch_accumulate(s, light, ctx->dscene, st, q, kp, parity);
-      parity = 1 - parity;
-      iterations++;
-      launches += path_like ? 6 : 5;
-    }
-    // wait for the check issued one round ago (keeps <= 2 rounds of launches in flight)
-    int prev = 1 - slot;
-    if (pending[prev]) {
-      CUDA_TRY(cudaEventSynchronize(ctx->ev[prev]));
-      pending[prev] = false;
-      if (ctx->h_done[prev] >= st.num_lanes) break;
-    }
-    CUDA_TRY(cudaMemcpyAsync(&ctx->h_done[slot], &ctx->counters->done_lanes, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaEventRecord(ctx->ev[slot], s));
-    pending[slot] = true;
-    slot          = 1 - slot;
+  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[0], s0));
+  // the other pipelines start after everything already queued on the context stream
+  for (int j = 1; j < npipes; j++) {
+    CUDA_TRY(cudaEventRecord(runs[j].pipe->join, s0));
+    CUDA_TRY(cudaStreamWaitEvent(runs[j].pipe->stream, runs[j].pipe->join, 0));
   }
-  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[1], s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int j = 0; j < npipes; j++) {
+    launch_seed_lanes(runs[j].pipe->stream, runs[j].light, st, runs[j].q, 0, state->samples, runs[j].lo, runs[j].hi);
+    launches++;
+  }
+  int remaining = npipes;
+  while (remaining > 0) {
+    for (int k = 0; k < check_every; k++) {
+      for (int j = 0; j < npipes; j++) {
+        Run& r = runs[j];
+        if (r.done) continue;
+        cudaStream_t s = r.pipe->stream;
+        launch_begin_iteration(s, r.q, r.parity);
+        launch_generate(s, r.light, ctx->dscene, st, r.q, kp, r.parity);
+        if (timing) {
+          while (ctx->ev_pool.size() < ev_used + 2) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            ctx->ev_pool.push_back(e);
+          }
+          CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used], s));
+        }
+        launch_extend(s, r.heavy, ctx->dscene, st, r.q, r.parity, trav);
+        if (timing) {
+          CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used + 1], s));
+          ev_used += 2;
+        }
+        launch_shade(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
+        if (path_like) launch_lightpdf(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
+        launch_accumulate(s, r.light, ctx->dscene, st, r.q, kp, r.parity);
+        r.parity = 1 - r.parity;
+        launches += path_like ? 6 : 5;
+      }
+      iterations++;
+    }
+    for (int j = 0; j < npipes; j++) {
+      Run& r = runs[j];
+      if (r.done) continue;
+      // wait for the check issued one round ago (keeps <= 2 rounds of launches in flight per pipeline)
+      int prev = 1 - r.slot;
+      if (r.pending[prev]) {
+        CUDA_TRY(cudaEventSynchronize(r.pipe->ev[prev]));
+        r.pending[prev] = false;
+        if (r.pipe->h_done[prev] >= r.hi - r.lo) {
+          r.done = true;
+          remaining--;
+          continue;
+        }
+      }
+      CUDA_TRY(cudaMemcpyAsync(&r.pipe->h_done[r.slot], &r.pipe->counters->done_lanes, sizeof(int),
+          cudaMemcpyDeviceToHost, r.pipe->stream));
+      CUDA_TRY(cudaEventRecord(r.pipe->ev[r.slot], r.pipe->stream));
+      r.pending[r.slot] = true;
+      r.slot            = 1 - r.slot;
+    }
+  }
+  // join: later work on the context stream (downloads, the tile gather) is ordered after every pipeline
+  for (int j = 1; j < npipes; j++) {
+    CUDA_TRY(cudaEventRecord(runs[j].pipe->join, runs[j].pipe->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s0, runs[j].pipe->join, 0));
+  }
+  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[1], s0));
+  for (int j = 0; j < npipes; j++) CUDA_TRY(cudaStreamSynchronize(runs[j].pipe->stream));
   CUDA_TRY(cudaGetLastError());
-  Counters c;
-  CUDA_TRY(cudaMemcpy(&c, ctx->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
-  ctx->stats[0] += c.camera_samples;
-  ctx->stats[1] += c.scene_rays;
-  ctx->stats[2] += c.instance_rays;
+  for (int j = 0; j < npipes; j++) {
+    Counters c;
+    CUDA_TRY(cudaMemcpy(&c, runs[j].pipe->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+    ctx->stats[0] += c.camera_samples;
+    ctx->stats[1] += c.scene_rays;
+    ctx->stats[2] += c.instance_rays;
+  }
   ctx->stats[3] += iterations;
   ctx->stats[4] += launches;
-  ctx->stats[5] += iterations;
+  ctx->stats[5] += ev_used / 2;
   if (trav) {
     unsigned long long t[8];
     CUDA_TRY(cudaMemcpy(t, trav, sizeof(t), cudaMemcpyDeviceToHost));
@@ -803,6 +865,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     ctx->timings[0] += ext_ms;
     ctx->timings[1] += loop_ms;
     ctx->timings[2] += (double)(ev_used / 2);
+    ctx->timings[3] = npipes;
   }
   state->samples += nsamples;
   return YGL_OK;

@@ -10,6 +10,9 @@
 // queue whose length it reads from device memory, so the host never synchronises inside the
 // sample loop. Survivors are appended to the next queue with one atomicAdd per warp
 // (__ballot_sync + __popc + __shfl_sync). Compiled with -fmad=false: see ygl_math.cuh.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ygl_eval.cuh"
 #include "ygl_kernels.cuh"
 #include "ygl_traverse.cuh"
@@ -55,15 +58,15 @@ __global__ void k_begin_iteration(Counters* c, int parity) {
   c->ext_head          = 0;
 }
 
-__global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begin) {
+__global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begin, int lane_lo, int lane_hi) {
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int l = tid; l < st.num_lanes; l += gridDim.x * blockDim.x) {
-    st.sample[l]      = sample_begin;
-    q.gen[parity][l]  = l;
+  for (int l = lane_lo + tid; l < lane_hi; l += gridDim.x * blockDim.x) {
+    st.sample[l]               = sample_begin;
+    q.gen[parity][l - lane_lo] = l;
   }
   if (tid == 0) {
     Counters* c          = q.counters;
-    c->n_gen[parity]     = st.num_lanes;
+    c->n_gen[parity]     = lane_hi - lane_lo;
     c->n_gen[1 - parity] = 0;
     c->n_ext[0] = c->n_ext[1] = 0;
     c->n_lpdf = c->n_acc = 0;
@@ -633,8 +636,9 @@ __global__ void __launch_bounds__(256) k_intersect_rays(DScene scene, const floa
 
 // ------------------------------------------------------------------------------------------
 void launch_begin_iteration(cudaStream_t s, Queues q, int parity) { k_begin_iteration<<<1, 1, 0, s>>>(q.counters, parity); }
-void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin) {
-  k_seed_lanes<<<cfg.blocks, cfg.threads, 0, s>>>(st, q, parity, sample_begin);
+void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin,
+    int lane_lo, int lane_hi) {
+  k_seed_lanes<<<cfg.blocks, cfg.threads, 0, s>>>(st, q, parity, sample_begin, lane_lo, lane_hi);
 }
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   k_generate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
@@ -653,6 +657,7 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
     if (per_sm < 1) per_sm = 1;
   }
   int blocks = sms * per_sm;
+  if (const char* env = getenv("YGL_EXT_BLOCKS_PER_SM")) blocks = sms * std::max(1, std::min(per_sm, atoi(env)));
   int needed = (st.num_lanes + 127) / 128;
   if (blocks > needed) blocks = needed;
   if (blocks < 1) blocks = 1;

@@ -65,7 +65,8 @@ struct LaunchCfg {
 };
 
 void launch_begin_iteration(cudaStream_t s, Queues q, int parity);
-void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin);
+void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin,
+    int lane_lo, int lane_hi);
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 // trav: device array of 7 counters {top nodes, bottom nodes, instance visits, tri, quad, line, point tests} or null
 void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity,
