@@ -1,0 +1,94 @@
+"""Pins the plain-C restatement (oracle/restate/ygl_oracle.c) against the REAL reference
+(oracle/_ref) and against the committed golden fixtures: trees, hits and rendered images must be
+bit-identical (same host libm, same operation order). No GPU involved."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import restate
+from parity_util import axis_rays, compare_hits, random_rays
+from ygl_b200 import abi, scenes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+pytestmark = pytest.mark.skipif(not restate.available(), reason="oracle/_build/libygl_oracle.so not built")
+
+SCENES = {
+    "cornell": scenes.cornellbox,
+    "cornell_quads": scenes.cornellbox_quads,
+    "instanced3": lambda: scenes.instanced_spheres(3),
+    "features": scenes.features,  # traversal only (its materials/textures are outside the restatement)
+    "hair": lambda: scenes.hair_scene(1500, 6, 2),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("hq", [False, True])
+def test_trees_match_reference(ref, name, hq):
+    if hq and name == "hair":
+        pytest.skip("covered by the smaller scenes")
+    scene = SCENES[name]()
+    rs, mine = ref.scene(scene), restate.OracleScene(scene, hq)
+    for shape in [-1] + list(range(len(scene.shapes))):
+        a, b = rs.bvh_tree(shape, hq), mine.tree(shape)
+        assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), (name, shape)
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_hits_match_reference(ref, name):
+    scene = SCENES[name]()
+    rs, mine = ref.scene(scene), restate.OracleScene(scene)
+    rays = np.concatenate([random_rays(scene, 20000), axis_rays(scene, 4000)])
+    assert compare_hits(rs.intersect(rays), mine.intersect(rays)) == 0
+    assert compare_hits(rs.intersect(rays, find_any=True), mine.intersect(rays, find_any=True)) == 0
+    assert compare_hits(rs.intersect(rays[:5000], instance=0), mine.intersect(rays[:5000], instance=0)) == 0
+
+
+def test_golden_rays():
+    g = np.load(os.path.join(GOLDEN, "rays_features.npz"))
+    mine = restate.OracleScene(scenes.features())
+    out = mine.intersect(g["rays"].view(abi.RAY_DTYPE).reshape(-1))
+    assert compare_hits(g["hits"].view(abi.ISEC_DTYPE).reshape(-1), out) == 0
+
+
+def test_rng_table_and_known_answers(ref):
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    scene = scenes.cornellbox()
+    mine = restate.OracleScene(scene)
+    p = abi.trace_params(resolution=8)
+    _, _, r = mine.state_rngs(p)
+    assert [int(x) >> 1 for x in r[:3, 1]] == kat["pixel_seq_ids"]
+    w, h, rr = ref.scene(scene).state_rngs(abi.trace_params(resolution=40, seed=77))
+    w2, h2, r2 = mine.state_rngs(abi.trace_params(resolution=40, seed=77))
+    assert (w, h) == (w2, h2) and np.array_equal(rr, r2)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("cornell", dict(resolution=64, samples=4, bounces=4)),
+    ("cornell_quads", dict(resolution=48, samples=3, bounces=8)),
+    ("instanced3", dict(resolution=64, samples=3, bounces=8)),
+])
+def test_images_bit_identical_to_reference(ref, name, kw):
+    scene = SCENES[name]()
+    mine = restate.OracleScene(scene)
+    assert mine.supported()
+    p = abi.trace_params(**kw)
+    assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes()
+
+
+def test_golden_image_and_checksum():
+    g = np.load(os.path.join(GOLDEN, "renders.npz"))
+    scene = scenes.cornellbox()
+    mine = restate.OracleScene(scene)
+    kw = {k: int(v) for k, v in zip(g["cornell_path.param_names"], g["cornell_path.param_values"])}
+    assert mine.trace_image(abi.trace_params(**kw)).tobytes() == g["cornell_path.image"].tobytes()
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    img = mine.trace_image(abi.trace_params(resolution=256, samples=16, bounces=4))
+    assert abs(float(img[..., :3].astype(np.float64).sum()) - kat["cornell_256_16spp_4b_sum_rgb"]) < 1e-9
+
+
+def test_unsupported_features_are_reported():
+    assert not restate.OracleScene(scenes.features()).supported()
+    with pytest.raises(NotImplementedError):
+        restate.OracleScene(scenes.features()).trace_image(abi.trace_params(resolution=8, samples=1))
