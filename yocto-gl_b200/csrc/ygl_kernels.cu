@@ -118,6 +118,7 @@ struct ExtendSource {
   int*       head;
   PathState  st;
   int        lane;
+  int        refill_thr, node_reps;  // tuning knobs (see launch_extend)
   YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more) {
     const unsigned m    = __ballot_sync(kFullWarp, idle);
     const int      wl   = threadIdx.x & 31;
@@ -138,12 +139,15 @@ struct ExtendSource {
   }
 };
 
+#ifndef YGL_EXT_MINBLOCKS
+#define YGL_EXT_MINBLOCKS 7  // measured on B200 (C3): 4/5/6/7/8 blocks/SM -> 249/249/233/224/227 ms per 32 spp
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128, 6) k_extend(DScene scene, PathState st, Queues q, int parity,
-    unsigned long long* trav) {
+__global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene, PathState st, Queues q, int parity,
+    unsigned long long* trav, int refill_thr, int node_reps) {
   Counters*     c = q.counters;
   const int     n = c->n_ext[parity];
-  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0};
+  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps};
   trav_counters tc = {};
   trace_stream<COUNT>(scene, src, tc);
   if (COUNT) {
@@ -662,10 +666,12 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
   if (blocks > needed) blocks = needed;
   if (blocks < 1) blocks = 1;
   (void)cfg;
+  static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
+  static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
   if (trav)
-    k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav);
+    k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps);
   else
-    k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr);
+    k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr, refill_thr, node_reps);
 }
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   if (p.sampler == kSamplerFalsecolor)

@@ -319,12 +319,29 @@ YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f
 // `src` (src.fetch hands out rays, src.commit stores a finished lane's hit). Must be called by full,
 // converged warps.
 constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
+constexpr int kStreamThreads   = 128;  // block size of kernels that call trace_stream
+constexpr int kSharedStack     = 28;   // stack entries per lane kept in shared memory (14 KB per block)
 
 template <bool COUNT, class Source>
 YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
-  int stack[2 * kStackSize + 8];
-  stack[0]  = kMarkDone;  // sentinel: popping an empty stack yields "done"
-  int   sp  = 1;
+  // Traversal stack: the first kSharedStack entries of every lane live in shared memory, laid out
+  // [entry][thread] so a lane always hits its own bank (conflict-free whatever the lanes' depths are);
+  // deeper entries spill to a per-thread local array (rare: kSharedStack covers a 1000-instance tree
+  // plus a 64K-primitive shape tree).
+  __shared__ int s_stack[kSharedStack][kStreamThreads];
+  int            l_stack[2 * kStackSize + 8 - kSharedStack];
+  const int      tix  = threadIdx.x;
+  int            sp   = 1;
+  auto           push = [&](int v) {
+    if (sp < kSharedStack) s_stack[sp][tix] = v;
+    else l_stack[sp - kSharedStack] = v;
+    sp++;
+  };
+  auto pop_raw = [&]() {
+    --sp;
+    return sp < kSharedStack ? s_stack[sp][tix] : l_stack[sp - kSharedStack];
+  };
+  s_stack[0][tix] = kMarkDone;  // sentinel: popping an empty stack yields "done"
   hit_t res = {-1, -1, {0, 0}, 0, false};
 
   const float tmin = kRayEps;
@@ -341,7 +358,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   // ENTER entries carry a run of instances of one top-level leaf: ~(first | (count - 1) << 28)
   auto enter = [&](int entry) {
     const int run = ~entry, first = run & 0x0fffffff, left = run >> 28;
-    if (left > 0) stack[sp++] = ~((first + 1) | ((left - 1) << 28));  // next instance of the leaf, same order
+    if (left > 0) push(~((first + 1) | ((left - 1) << 28)));  // next instance of the leaf, same order
     const DInstancePacket* pk = scene.top_packets + first;
     float4 a = __ldg(&pk->q[0]), b = __ldg(&pk->q[1]), c = __ldg(&pk->q[2]), e = __ldg(&pk->q[3]);
     float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
@@ -354,16 +371,16 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     packets = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.w) << 32) | (unsigned)__float_as_int(p0.z));
     prims   = (const int*)(((unsigned long long)(unsigned)__float_as_int(p1.y) << 32) | (unsigned)__float_as_int(p1.x));
     bottom      = true;
-    stack[sp++] = kMarkExit;
+    push(kMarkExit);
     return 0;
   };
   auto advance = [&]() {
-    int v = stack[--sp];
+    int v = pop_raw();
     if (v == kMarkExit) {  // leaving an instance: back to the world-space ray; never two EXITs in a row
       ray    = world;
       nodes  = scene.top_nodes;
       bottom = false;
-      v      = stack[--sp];
+      v      = pop_raw();
     }
     if (v == kMarkDone) sp = 1;
     return v;
@@ -377,7 +394,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     const unsigned busy       = want_node | want_prim | want_enter;
     const int      n_idle     = 32 - __popc(busy);
 
-    if (more && n_idle >= kRefillThreshold) {
+    if (more && n_idle >= src.refill_thr) {
       // ---- refill: finished lanes hand over their hit and take the next queued ray ----
       const bool idle = cur == kMarkDone;
       if (idle && have) src.commit(res);
@@ -399,6 +416,9 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     const int n_node = __popc(want_node), n_prim = __popc(want_prim), n_enter = __popc(want_enter);
 
     if (n_node >= n_prim && n_node >= n_enter) {
+      // two node visits per scheduling round: halves the vote overhead on the most frequent path
+#pragma unroll 1
+      for (int rep = 0; rep < src.node_reps; rep++)
       if (cur >= 0) {
         float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
         if (COUNT) {
@@ -413,7 +433,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
           cur = advance();
         } else if (meta >> 24) {
           int neg     = (ray.sgn >> ((meta >> 16) & 0xff)) & 1;
-          stack[sp++] = start + 1 - neg;
+          push(start + 1 - neg);
           cur         = start + neg;
         } else if (bottom) {
           leaf_next = start;
@@ -426,33 +446,39 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
         }
       }
     } else if (n_prim >= n_enter) {
-      if (cur == kMarkLeaf) {
-        const int idx = leaf_next++;
-        if (COUNT) cnt.prims_by_kind[kind]++;
-        f2    puv = {0, 0};
-        float pd  = 0;
-        bool  h;
-        if (kind == kElemTriangles) {
-          float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
-          h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
-        } else if (kind == kElemQuads) {
-          float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
-                 e = __ldg(packets + 4 * idx + 3);
-          h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
-              f3{e.x, e.y, e.z}, puv, pd);
-        } else if (kind == kElemLines) {
-          float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
-          h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
-        } else {
-          float4 a = __ldg(packets + idx);
-          h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
+      // all primitives of the lane's leaf (<= 4, bvh_max_prims) in one go, warp-uniform trip count
+      const bool in_leaf = cur == kMarkLeaf;
+      for (int k = 0; k < 4; k++) {
+        const bool test = in_leaf && leaf_next < leaf_end;
+        if (!__any_sync(kFullWarp, test)) break;
+        if (test) {
+          const int idx = leaf_next++;
+          if (COUNT) cnt.prims_by_kind[kind]++;
+          f2    puv = {0, 0};
+          float pd  = 0;
+          bool  h;
+          if (kind == kElemTriangles) {
+            float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
+            h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
+          } else if (kind == kElemQuads) {
+            float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
+                   e = __ldg(packets + 4 * idx + 3);
+            h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
+                f3{e.x, e.y, e.z}, puv, pd);
+          } else if (kind == kElemLines) {
+            float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
+            h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
+          } else {
+            float4 a = __ldg(packets + idx);
+            h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
+          }
+          if (h) {
+            res  = {cur_instance, __ldg(prims + idx), puv, pd, true};
+            tmax = pd;
+          }
         }
-        if (h) {
-          res  = {cur_instance, __ldg(prims + idx), puv, pd, true};
-          tmax = pd;
-        }
-        if (leaf_next == leaf_end) cur = advance();
       }
+      if (in_leaf) cur = advance();
     } else {
       if (cur < 0 && cur > kMarkLeaf) cur = enter(cur);
     }
