@@ -496,8 +496,14 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
   }
 }
 
+#ifndef YGL_SHADE_THREADS
+#define YGL_SHADE_THREADS 256
+#endif
+#ifndef YGL_SHADE_MINBLOCKS
+#define YGL_SHADE_MINBLOCKS 4  // measured on B200 (C3, ms per 32 spp): 256x1 361, 256x3 350, 256x4 338, 128x6 352
+#endif
 template <int SAMPLER>
-__global__ void __launch_bounds__(256) k_shade(DScene scene, PathState st, Queues q, KParams p, int parity) {
+__global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shade(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_ext[parity];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -519,7 +525,10 @@ __global__ void __launch_bounds__(256) k_shade(DScene scene, PathState st, Queue
 
 // ---- lightpdf: sample_lights_pdf for the pending direction, then the MIS weight, weight checks,
 // russian roulette and the loop increment (yocto_trace.cpp:532-536 / :573-576, :581-591) ----
-__global__ void __launch_bounds__(256) k_lightpdf(DScene scene, PathState st, Queues q, KParams p, int parity) {
+#ifndef YGL_LPDF_MINBLOCKS
+#define YGL_LPDF_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_lpdf;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -674,12 +683,14 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
     k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr, refill_thr, node_reps);
 }
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
+  const int threads = YGL_SHADE_THREADS;
+  const int blocks  = std::max(1, cfg.blocks * cfg.threads / threads);
   if (p.sampler == kSamplerFalsecolor)
-    k_shade<kSamplerFalsecolor><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+    k_shade<kSamplerFalsecolor><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else if (p.sampler == kSamplerEyelight)
-    k_shade<kSamplerEyelight><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+    k_shade<kSamplerEyelight><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else
-    k_shade<kSamplerPath><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+    k_shade<kSamplerPath><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
 }
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   k_lightpdf<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);

@@ -13,7 +13,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libygl_b200.so"))
+LIB_PATH = os.environ.get("YGL_B200_LIB") or os.path.normpath(os.path.join(_HERE, "..", "lib", "libygl_b200.so"))
 _lib = None
 
 EXPORTS = [
