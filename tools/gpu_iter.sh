@@ -1,9 +1,10 @@
 #!/bin/bash
 # Development loop on the GPU box: parity summary, C3/C1 timing, optional ncu capture of one kernel.
+# Every step runs under a short timeout: a hung kernel must never reach gpurun's own limit.
 # usage: tools/gpu_iter.sh [tag] [kernel-regex]
 TAG=${1:-x}; KRE=${2:-}
 mkdir -p gpurun_out
-timeout 400 python tools/gpu_check.py > gpurun_out/check_$TAG.log 2>&1
+timeout 150 python tools/gpu_check.py > gpurun_out/check_$TAG.log 2>&1 || { echo "gpu_check FAILED/TIMEOUT"; tail -3 gpurun_out/check_$TAG.log; exit 1; }
 python - <<PY
 import json
 d = json.load(open("gpurun_out/gpu_check.json"))
@@ -15,10 +16,9 @@ for k, v in d.items():
         bad += sum(r["vs_ref_dlibm"]["frac_exact"] != 1.0 for r in v)
 print("PARITY", "OK" if bad == 0 else f"FAIL({bad})", {k: [round(r["vs_ref"]["rmse"], 10) for r in v] for k, v in d.items() if k.startswith("render_")})
 PY
-tail -2 gpurun_out/check_$TAG.log | cut -c1-200
-timeout 300 python tools/gpu_perf.py c3 1920 8 2 2>&1 | tail -2
-timeout 100 python tools/gpu_perf.py c1 256 16 2 2>&1 | tail -1
+timeout 100 python tools/gpu_perf.py c3 1920 8 2 2>&1 | tail -2
+timeout 60 python tools/gpu_perf.py c1 256 16 2 2>&1 | tail -1
 if [ -n "$KRE" ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s 2 -c 1 -o gpurun_out/prof_$TAG python tools/gpu_perf.py c3 1920 2 0 > gpurun_out/ncu_$TAG.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s 2 -c 1 -o gpurun_out/prof_$TAG python tools/gpu_perf.py c3 1920 2 0 > gpurun_out/ncu_$TAG.log 2>&1
   tail -1 gpurun_out/ncu_$TAG.log
 fi

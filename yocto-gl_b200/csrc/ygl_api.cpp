@@ -594,7 +594,7 @@ static int state_create_rows(ygl_context* ctx, const ygl_scene_desc* desc, const
          o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_ro = take(lanes * 16), o_rd = take(lanes * 16),
          o_rad = take(lanes * 16), o_w = take(lanes * 16), o_huvd = take(lanes * 16), o_hid = take(lanes * 8),
          o_a0 = take(lanes * 16), o_n0 = take(lanes * 16), o_va = take(lanes * 16), o_vb = take(lanes * 16),
-         o_pend = take(lanes * 16);
+         o_pend = take(lanes * 16), o_susp = take(lanes * 4 * 48);
   CUDA_TRY(cudaMalloc((void**)&state->mem, off));
   CUDA_TRY(cudaMemset(state->mem, 0, off));
   PathState& st = state->st;
@@ -618,6 +618,7 @@ static int state_create_rows(ygl_context* ctx, const ygl_scene_desc* desc, const
   st.vol_a    = (float4*)(m + o_va);
   st.vol_b    = (float4*)(m + o_vb);
   st.pend     = (float4*)(m + o_pend);
+  st.susp     = (int*)(m + o_susp);
   // rng table: seeded sequentially over the FULL image (yocto_trace.cpp:1512-1515), tile slice uploaded
   std::vector<uint64_t> rngs((size_t)w * h * 2);
   state_rngs(*params, w, h, rngs.data());

@@ -118,8 +118,10 @@ struct ExtendSource {
   int*       head;
   PathState  st;
   int        lane;
-  int        refill_thr, node_reps;  // tuning knobs (see launch_extend)
-  YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more) {
+  int        refill_thr, node_reps, suspend_below;  // tuning knobs (see launch_extend)
+  unsigned   finished;                              // rays completed by this thread (scene_rays counter)
+  // Queue entries: lane id; bit 31 set = the ray was suspended by the previous launch (resume it).
+  YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more, bool& resume) {
     const unsigned m    = __ballot_sync(kFullWarp, idle);
     const int      wl   = threadIdx.x & 31;
     int            base = 0;
@@ -128,7 +130,9 @@ struct ExtendSource {
     const int my = base + __popc(m & ((1u << wl) - 1u));
     more         = base + __popc(m) < n;
     if (!idle || my >= n) return false;
-    lane     = queue[my];
+    const int entry = queue[my];
+    lane     = entry & 0x7fffffff;
+    resume   = entry < 0;
     float4 a = st.ray_o[lane], b = st.ray_d[lane];
     o = unpack3(a), d = unpack3(b);
     return true;
@@ -136,7 +140,10 @@ struct ExtendSource {
   YGL_D void commit(const hit_t& h) {
     st.hit_uvd[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
     st.hit_ids[lane] = make_int2(h.instance, h.element);
+    finished++;
   }
+  YGL_D int* saved() { return st.susp + (size_t)lane * kSuspendWords; }
+  YGL_D void commit_suspended() { st.hit_uvd[lane] = make_float4(0, 0, 0, __int_as_float(2)); }
 };
 
 #ifndef YGL_EXT_MINBLOCKS
@@ -144,12 +151,17 @@ struct ExtendSource {
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene, PathState st, Queues q, int parity,
-    unsigned long long* trav, int refill_thr, int node_reps) {
+    unsigned long long* trav, int refill_thr, int node_reps, int suspend_below) {
   Counters*     c = q.counters;
   const int     n = c->n_ext[parity];
-  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps};
+  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps, suspend_below, 0};
   trav_counters tc = {};
   trace_stream<COUNT>(scene, src, tc);
+  {
+    unsigned v = src.finished;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFullWarp, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&c->scene_rays, (unsigned long long)v);
+  }
   if (COUNT) {
     // traversal statistics for the algorithmic-bytes formula; counting runs are not timed
     unsigned vals[7] = {tc.top_nodes, tc.bot_nodes, tc.instances, tc.prims_by_kind[kElemTriangles],
@@ -160,7 +172,6 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene,
       if ((threadIdx.x & 31) == 0 && v) atomicAdd(trav + k, (unsigned long long)v);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->scene_rays, (unsigned long long)n);
 }
 
 // ---- light sampling, yocto_trace.cpp:361-388 ----
@@ -512,11 +523,19 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
     int i    = i0 + wl;
     int lane = 0, dest = kDestNone;
+    int entry = 0;
     if (i < n) {
-      lane = q.ext[parity][i];
-      dest = shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
+      lane = q.ext[parity][i] & 0x7fffffff;
+      if (__float_as_int(st.hit_uvd[lane].w) == 2) {
+        // the extend kernel suspended this ray: it stays in the extend queue, flagged for resumption
+        dest  = kDestExt;
+        entry = lane | (int)0x80000000;
+      } else {
+        dest  = shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
+        entry = lane;
+      }
     }
-    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, lane);
+    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
     queue_push(q.lpdf, &c->n_lpdf, dest == kDestLpdf, lane);
     queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
   }
@@ -677,10 +696,11 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
   (void)cfg;
   static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
   static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
+  static int suspend    = getenv("YGL_SUSPEND") ? atoi(getenv("YGL_SUSPEND")) : kSuspendBelow;
   if (trav)
-    k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps);
+    k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps, suspend);
   else
-    k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr, refill_thr, node_reps);
+    k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr, refill_thr, node_reps, suspend);
 }
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   const int threads = YGL_SHADE_THREADS;

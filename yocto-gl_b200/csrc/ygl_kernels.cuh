@@ -34,6 +34,7 @@ struct PathState {
   float4* vol_a;     // volume slot: density.xyz, scanisotropy
   float4* vol_b;     // volume slot: scattering.xyz
   float4* pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
+  int*    susp;      // kSuspendWords ints per lane: traversal state of a ray suspended by k_extend
 };
 
 // Work queues: lane ids compacted with warp-ballot / one atomic per warp.

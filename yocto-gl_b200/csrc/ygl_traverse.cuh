@@ -320,7 +320,11 @@ YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f
 // converged warps.
 constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
 constexpr int kStreamThreads   = 128;  // block size of kernels that call trace_stream
-constexpr int kSharedStack     = 28;   // stack entries per lane kept in shared memory (14 KB per block)
+constexpr int kSharedStack     = 28;
+constexpr int kSuspendWords    = 48;   // words of saved traversal state per lane (12 header + 36 stack)
+constexpr int kSuspendStack    = kSuspendWords - 12;
+constexpr int kSuspendMinRounds = 96;  // a warp walks at least this many rounds per launch before suspending: progress guarantee
+constexpr int kSuspendBelow    = 8;    // suspend a drained warp's stragglers once this few lanes are busy (0 = never)   // stack entries per lane kept in shared memory (14 KB per block)
 
 template <bool COUNT, class Source>
 YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
@@ -352,13 +356,14 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   const float4* __restrict__ nodes = scene.top_nodes;
   const float4* packets            = nullptr;
   const int*    prims              = nullptr;
-  int  kind = kElemNone, cur_instance = -1;
+  int  kind = kElemNone, cur_instance = -1, cur_packet = -1;
   bool bottom = false, have = false, more = true;
 
   // ENTER entries carry a run of instances of one top-level leaf: ~(first | (count - 1) << 28)
   auto enter = [&](int entry) {
     const int run = ~entry, first = run & 0x0fffffff, left = run >> 28;
     if (left > 0) push(~((first + 1) | ((left - 1) << 28)));  // next instance of the leaf, same order
+    cur_packet = first;
     const DInstancePacket* pk = scene.top_packets + first;
     float4 a = __ldg(&pk->q[0]), b = __ldg(&pk->q[1]), c = __ldg(&pk->q[2]), e = __ldg(&pk->q[3]);
     float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
@@ -374,19 +379,35 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     push(kMarkExit);
     return 0;
   };
+  // the part of `enter` that only depends on the packet (used to resume a suspended ray)
+  auto reload_instance = [&](int first) {
+    const DInstancePacket* pk = scene.top_packets + first;
+    float4 a = __ldg(&pk->q[0]), b = __ldg(&pk->q[1]), c = __ldg(&pk->q[2]), e = __ldg(&pk->q[3]);
+    float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
+    frame3 inv = {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}, {c.y, c.z, c.w}};
+    ray          = make_ray(transform_point(inv, world.o), transform_vector(inv, world.d));
+    cur_instance = __float_as_int(e.y);
+    kind         = __float_as_int(e.z);
+    nodes   = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.y) << 32) | (unsigned)__float_as_int(p0.x));
+    packets = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.w) << 32) | (unsigned)__float_as_int(p0.z));
+    prims   = (const int*)(((unsigned long long)(unsigned)__float_as_int(p1.y) << 32) | (unsigned)__float_as_int(p1.x));
+    bottom       = true;
+    cur_packet   = first;
+  };
   auto advance = [&]() {
     int v = pop_raw();
     if (v == kMarkExit) {  // leaving an instance: back to the world-space ray; never two EXITs in a row
-      ray    = world;
-      nodes  = scene.top_nodes;
-      bottom = false;
-      v      = pop_raw();
+      ray        = world;
+      nodes      = scene.top_nodes;
+      bottom     = false;
+      cur_packet = -1;
+      v          = pop_raw();
     }
     if (v == kMarkDone) sp = 1;
     return v;
   };
 
-  int cur = kMarkDone, leaf_next = 0, leaf_end = 0;
+  int cur = kMarkDone, leaf_next = 0, leaf_end = 0, rounds = 0;
   while (true) {
     const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0);
     const unsigned want_prim  = __ballot_sync(kFullWarp, cur == kMarkLeaf);
@@ -398,21 +419,53 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       // ---- refill: finished lanes hand over their hit and take the next queued ray ----
       const bool idle = cur == kMarkDone;
       if (idle && have) src.commit(res);
-      f3 o, d;
-      const bool got = src.fetch(idle, o, d, more);
+      f3   o, d;
+      bool resume = false;
+      const bool got = src.fetch(idle, o, d, more, resume);
       if (idle) have = got;
       if (got) {
         world = make_ray(o, d);
         ray   = world;
         tmax  = kFltMax;
         res   = {-1, -1, {0, 0}, 0, false};
-        sp = 1, bottom = false;
+        sp = 1, bottom = false, cur_packet = -1;
         nodes = scene.top_nodes;
         cur   = scene.top_num_nodes > 0 ? 0 : kMarkDone;
+        if (resume) {
+          // a ray suspended by the previous launch: restore its walk exactly where it stopped
+          const int* sv = src.saved();
+          cur = sv[0], sp = sv[1], leaf_next = sv[2], leaf_end = sv[3];
+          const int pkt = sv[4];
+          tmax = __int_as_float(sv[5]);
+          res  = {sv[6], sv[7], {__int_as_float(sv[8]), __int_as_float(sv[9])}, __int_as_float(sv[10]), sv[11] != 0};
+          for (int k = 1; k < sp; k++) {
+            if (k < kSharedStack) s_stack[k][tix] = sv[12 + k];
+            else l_stack[k - kSharedStack] = sv[12 + k];
+          }
+          if (pkt >= 0) reload_instance(pkt);
+        }
       }
       continue;
     }
     if (!busy) break;
+    if (!more && src.suspend_below > 0 && ++rounds >= kSuspendMinRounds && __popc(busy) <= src.suspend_below) {
+      // ---- suspend: the queue is exhausted and this warp is running nearly empty. Instead of draining
+      // the stragglers at 1-2 lanes per instruction, save their traversal state; they resume in the next
+      // launch (one wavefront iteration later — a per-lane delay only, the walk itself is unchanged). ----
+      const bool mine = cur != kMarkDone && sp <= kSuspendStack;
+      if (mine) {
+        int* sv = src.saved();
+        sv[0] = cur, sv[1] = sp, sv[2] = leaf_next, sv[3] = leaf_end, sv[4] = cur_packet;
+        sv[5] = __float_as_int(tmax);
+        sv[6] = res.instance, sv[7] = res.element, sv[8] = __float_as_int(res.uv.x), sv[9] = __float_as_int(res.uv.y);
+        sv[10] = __float_as_int(res.distance), sv[11] = res.hit ? 1 : 0;
+        for (int k = 1; k < sp; k++) sv[12 + k] = k < kSharedStack ? s_stack[k][tix] : l_stack[k - kSharedStack];
+        src.commit_suspended();
+        cur = kMarkDone, sp = 1, have = false;
+      }
+      if (!__any_sync(kFullWarp, cur != kMarkDone)) break;
+      // lanes with a deeper stack than the save area keep walking
+    }
     const int n_node = __popc(want_node), n_prim = __popc(want_prim), n_enter = __popc(want_enter);
 
     if (n_node >= n_prim && n_node >= n_enter) {
