@@ -291,6 +291,10 @@ int ygl_intersect_rays(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* 
 int ygl_intersect_rays_device(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh,
     const void* d_rays, int64_t n, int instance, int find_any, void* d_out, void* d_counters);
 
+/* Test hook: the device-side libm (glibc's float routines restated for the GPU) applied to host arrays.
+ * fn: 0 sin, 1 cos, 2 exp, 3 log, 4 atan, 5 acos, 6 atan2(x[i], y[i]), 7 pow(x[i], y[i]), 8 sqrt, 9 fmod. */
+int ygl_debug_libm(ygl_context* ctx, int fn, const float* x, const float* y, int64_t n, float* out);
+
 /* ---- multi-GPU: one process per device, row tiles, one all-gather at the end ---- */
 /* Size in bytes of the opaque NCCL unique id blob. */
 int ygl_comm_id_size(void);

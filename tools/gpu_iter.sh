@@ -13,8 +13,8 @@ for k, v in d.items():
     if k.startswith("rays_"):
         bad += v["mismatch"] + v.get("instance_mismatch", 0) + v["any_mismatch"]
     else:
-        bad += sum(r["vs_ref_dlibm"]["frac_exact"] != 1.0 for r in v)
-print("PARITY", "OK" if bad == 0 else f"FAIL({bad})", {k: [round(r["vs_ref"]["rmse"], 10) for r in v] for k, v in d.items() if k.startswith("render_")})
+        bad += sum(r["vs_ref"]["frac_exact"] != 1.0 for r in v)
+print("PARITY(bit-exact vs unmodified reference)", "OK" if bad == 0 else f"FAIL({bad})", {k: [r["vs_ref"]["frac_exact"] for r in v] for k, v in d.items() if k.startswith("render_")})
 PY
 timeout 100 python tools/gpu_perf.py c3 1920 8 2 2>&1 | tail -2
 timeout 60 python tools/gpu_perf.py c1 256 16 2 2>&1 | tail -1

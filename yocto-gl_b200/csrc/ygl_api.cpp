@@ -1009,6 +1009,27 @@ int ygl_intersect_rays(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* 
   return rc;
 }
 
+// Test hook: evaluates the device libm function `fn` (0 sin, 1 cos, 2 exp, 3 log, 4 atan, 5 acos,
+// 6 atan2(x,y) with x as first argument, 7 pow(x,y), 8 sqrt, 9 fmod(x,y)) on host arrays.
+int ygl_debug_libm(ygl_context* ctx, int fn, const float* x, const float* y, int64_t n, float* out) {
+  if (!ctx || !x || !out || n < 0) return fail(YGL_ERR_INVALID, "bad argument");
+  if (n == 0) return YGL_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&dx, n * 4));
+  CUDA_TRY(cudaMalloc((void**)&dout, n * 4));
+  if (y) CUDA_TRY(cudaMalloc((void**)&dy, n * 4));
+  cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (y) cudaMemcpyAsync(dy, y, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  launch_debug_libm(ctx->stream, fn, dx, dy, n, dout);
+  cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dx), cudaFree(dout);
+  if (dy) cudaFree(dy);
+  if (e != cudaSuccess) return fail(YGL_ERR_CUDA, cudaGetErrorString(e));
+  return YGL_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Multi-GPU: one process per device; NCCL is loaded lazily (dlopen) so single-GPU users and the
 // CPU-only symbol check need no NCCL at all.

@@ -666,6 +666,30 @@ __global__ void __launch_bounds__(256) k_intersect_rays(DScene scene, const floa
   }
 }
 
+// ---- test hook: the device libm (ygl_math.cuh) on arrays, compared against the host libm by the tests ----
+__global__ void k_debug_libm(int fn, const float* __restrict__ x, const float* __restrict__ y, long long n,
+    float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = x[i], b = y ? y[i] : 0.0f, r = 0;
+    switch (fn) {
+      case 0: r = ysin(a); break;
+      case 1: r = ycos(a); break;
+      case 2: r = yexp(a); break;
+      case 3: r = ylog(a); break;
+      case 4: r = yatan(a); break;
+      case 5: r = yacos(a); break;
+      case 6: r = yatan2(a, b); break;
+      case 7: r = ypow(a, b); break;
+      case 8: r = ysqrt(a); break;
+      case 9: r = yfmod(a, b); break;
+    }
+    out[i] = r;
+  }
+}
+void launch_debug_libm(cudaStream_t s, int fn, const float* x, const float* y, long long n, float* out) {
+  k_debug_libm<<<1184, 256, 0, s>>>(fn, x, y, n, out);
+}
+
 // ------------------------------------------------------------------------------------------
 void launch_begin_iteration(cudaStream_t s, Queues q, int parity) { k_begin_iteration<<<1, 1, 0, s>>>(q.counters, parity); }
 void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin,

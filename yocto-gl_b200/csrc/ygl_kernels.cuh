@@ -80,4 +80,6 @@ void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st
 void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const float4* rays, long long n, int instance,
     int find_any, void* out, unsigned long long* counters);
 
+void launch_debug_libm(cudaStream_t s, int fn, const float* x, const float* y, long long n, float* out);
+
 }  // namespace ygl

@@ -5,9 +5,8 @@
 // operation, written in exactly the association order of the reference expression
 // it stands for (cited per function, paths under libs/yocto/). This translation unit is
 // compiled with -fmad=false (device) and -ffp-contract=off (host); division and sqrt
-// are IEEE-exact (-prec-div/-prec-sqrt defaults). Transcendentals are evaluated in
-// fp64 and rounded once to fp32 (DESIGN.md "libm"); the reference calls glibc's float
-// routines, which differ from the correctly rounded value on a tiny fraction of inputs.
+// are IEEE-exact (-prec-div/-prec-sqrt defaults). Transcendentals restate glibc's float
+// routines bit for bit on device (ygl_glibm.cuh, DESIGN.md "libm").
 #pragma once
 
 #include <math.h>
@@ -24,6 +23,9 @@
 #else
 #define YGL_HD inline
 #define YGL_HD_NOINLINE inline
+#endif
+#ifdef __CUDACC__
+#include "ygl_glibm.cuh"
 #endif
 
 namespace ygl {
@@ -58,16 +60,48 @@ YGL_HD int   imax(int a, int b) { return (a > b) ? a : b; }
 YGL_HD int   iclamp(int a, int lo, int hi) { return imin(imax(a, lo), hi); }
 YGL_HD bool  yfinite(float a) { return isfinite(a); }
 
-// ---- transcendental functions: fp64 evaluation rounded once to fp32 ----
+// ---- transcendental functions ----
+// Device: the glibc 2.39 x86-64 float routines restated bit for bit (ygl_glibm.cuh): sinf/cosf/
+// expf/logf/powf as their FMA builds (what glibc's ifunc selects on FMA-capable hosts), atanf/acosf/
+// atan2f as the plain fdlibm kernels — verified exhaustively against the host libm
+// (tools/libm_check_host.cpp: 0 mismatches over every float input in the covered ranges).
+// Arguments outside those ranges (|x| >= 120 for sin/cos, overflow/underflow/special operands)
+// fall back to fp64 evaluation rounded once. Host: the host libm itself.
 YGL_HD float ysqrt(float a) { return sqrtf(a); }  // IEEE exact
-YGL_HD_NOINLINE float ysin(float a) { return (float)sin((double)a); }
-YGL_HD_NOINLINE float ycos(float a) { return (float)cos((double)a); }
-YGL_HD_NOINLINE float yatan(float a) { return (float)atan((double)a); }
-YGL_HD_NOINLINE float yacos(float a) { return (float)acos((double)a); }
-YGL_HD_NOINLINE float yatan2(float a, float b) { return (float)atan2((double)a, (double)b); }
-YGL_HD_NOINLINE float ylog(float a) { return (float)log((double)a); }
-YGL_HD_NOINLINE float yexp(float a) { return (float)exp((double)a); }
-YGL_HD_NOINLINE float ypow(float a, float b) { return (float)pow((double)a, (double)b); }
+#ifdef __CUDA_ARCH__
+#define YGL_LIBM1(name, impl, fallback)            \
+  YGL_HD_NOINLINE float name(float a) {            \
+    float r;                                       \
+    if (glibm::impl(a, &r)) return r;              \
+    return (float)fallback((double)a);             \
+  }
+YGL_LIBM1(ysin, sinf_<true>, sin)
+YGL_LIBM1(ycos, cosf_<true>, cos)
+YGL_LIBM1(yexp, expf_<true>, exp)
+YGL_LIBM1(ylog, logf_<true>, log)
+YGL_LIBM1(yatan, atanf_<false>, atan)
+YGL_LIBM1(yacos, acosf_<false>, acos)
+#undef YGL_LIBM1
+YGL_HD_NOINLINE float yatan2(float a, float b) {
+  float r;
+  if (glibm::atan2f_<false>(a, b, &r)) return r;
+  return (float)atan2((double)a, (double)b);
+}
+YGL_HD_NOINLINE float ypow(float a, float b) {
+  float r;
+  if (glibm::powf_<true>(a, b, &r)) return r;
+  return (float)pow((double)a, (double)b);
+}
+#else
+YGL_HD float ysin(float a) { return sinf(a); }
+YGL_HD float ycos(float a) { return cosf(a); }
+YGL_HD float yatan(float a) { return atanf(a); }
+YGL_HD float yacos(float a) { return acosf(a); }
+YGL_HD float yatan2(float a, float b) { return atan2f(a, b); }
+YGL_HD float ylog(float a) { return logf(a); }
+YGL_HD float yexp(float a) { return expf(a); }
+YGL_HD float ypow(float a, float b) { return powf(a, b); }
+#endif
 YGL_HD float yfmod(float a, float b) { return fmodf(a, b); }  // exact by definition
 
 // ---- f3 operators (yocto_math.h:1254-1292) ----

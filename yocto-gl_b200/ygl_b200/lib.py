@@ -24,7 +24,7 @@ EXPORTS = [
     "ygl_lights_get", "ygl_lights_destroy", "ygl_state_create", "ygl_state_create_tile",
     "ygl_state_create_interleaved", "ygl_state_layout", "ygl_state_size", "ygl_state_rows", "ygl_state_download", "ygl_state_upload",
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
-    "ygl_trace_counters", "ygl_context_set_profiling", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_comm_id_size",
+    "ygl_trace_counters", "ygl_context_set_profiling", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
 ]
 
@@ -79,6 +79,7 @@ def load():
     lib.ygl_trace_timings.argtypes = [vp, vp]
     lib.ygl_intersect_rays.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.ygl_intersect_rays_device.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
+    lib.ygl_debug_libm.argtypes = [vp, i32, vp, vp, i64, vp]
     lib.ygl_comm_create_id.argtypes = [vp]
     lib.ygl_comm_init.argtypes = [vp, vp, i32, i32]
     lib.ygl_tile_rows.argtypes = [i32, i32, i32, P(i32), P(i32)]
@@ -199,6 +200,14 @@ class Context:
         t = np.zeros(4, np.float64)
         _check(self.lib.ygl_trace_timings(self.h, t.ctypes.data))
         return dict(extend_ms=float(t[0]), loop_ms=float(t[1]), extend_launches=int(t[2]))
+
+    def libm(self, fn, x, y=None):
+        """Device libm on arrays (test hook); fn as in ygl_debug_libm."""
+        x = np.ascontiguousarray(x, np.float32)
+        y = None if y is None else np.ascontiguousarray(y, np.float32)
+        out = np.zeros_like(x)
+        _check(self.lib.ygl_debug_libm(self.h, fn, x.ctypes.data, _p(y), x.size, out.ctypes.data))
+        return out
 
     def trace_image(self, scene, params):
         """trace_image: host scene -> host rgba image, everything inside one call."""
