@@ -82,6 +82,10 @@ RENDERS = [
     ("features", dict(resolution=96, samples=1, sampler=abi.SAMPLER_FALSECOLOR, falsecolor=abi.FC_INSTANCE)),
     ("features", dict(resolution=96, samples=1, sampler=abi.SAMPLER_FALSECOLOR, falsecolor=abi.FC_TEXCOORD)),
     ("hair", dict(resolution=96, samples=4, bounces=8)),
+    ("features", dict(resolution=96, samples=3, bounces=8, sampler=abi.SAMPLER_NAIVE)),
+    ("cornell", dict(resolution=64, samples=4, bounces=6, sampler=abi.SAMPLER_NAIVE)),
+    ("features", dict(resolution=96, samples=3, bounces=8, sampler=abi.SAMPLER_FURNACE)),
+    ("features", dict(resolution=96, samples=2, bounces=8, sampler=abi.SAMPLER_FURNACE, camera=1, envhidden=1)),
 ]
 
 

@@ -56,6 +56,8 @@ renders = [
     ("features", dict(resolution=128, samples=1, bounces=8, sampler=abi.SAMPLER_FALSECOLOR, falsecolor=abi.FC_ELEMENT)),
     ("features", dict(resolution=128, samples=1, bounces=8, sampler=abi.SAMPLER_FALSECOLOR, falsecolor=abi.FC_COLOR)),
     ("hair", dict(resolution=128, samples=4, bounces=8)),
+    ("features", dict(resolution=128, samples=3, bounces=8, sampler=abi.SAMPLER_NAIVE)),
+    ("features", dict(resolution=128, samples=3, bounces=8, sampler=abi.SAMPLER_FURNACE)),
 ]
 for name, kw in renders:
     sc = cases[name]

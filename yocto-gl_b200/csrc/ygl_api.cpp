@@ -876,13 +876,13 @@ static int check_sampler(const ygl_trace_params& p) {
   switch (p.sampler) {
     case YGL_SAMPLER_PATH:
     case YGL_SAMPLER_EYELIGHT:
+    case YGL_SAMPLER_NAIVE:
+    case YGL_SAMPLER_FURNACE:
     case YGL_SAMPLER_FALSECOLOR: return YGL_OK;
     case YGL_SAMPLER_PATHDIRECT:
     case YGL_SAMPLER_PATHMIS:
     case YGL_SAMPLER_PATHTEST:
-    case YGL_SAMPLER_NAIVE:
-    case YGL_SAMPLER_DIAGRAM:
-    case YGL_SAMPLER_FURNACE: return fail(YGL_ERR_RUNTIME, "sampler not implemented on the B200 path yet");
+    case YGL_SAMPLER_DIAGRAM: return fail(YGL_ERR_RUNTIME, "sampler not implemented on the B200 path yet");
     default: return fail(YGL_ERR_RUNTIME, "sampler unknown");  // yocto_trace.cpp:1437
   }
 }

@@ -344,6 +344,14 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
     return kDestAcc;
   }
 
+  // ---- furnace: a path that left the object stops at the next loop head, yocto_trace.cpp:1262-1266
+  // (the ray was traced but its hit is ignored, which is equivalent: tracing has no side effect) ----
+  if (SAMPLER == kSamplerFurnace && bounce > 0 && !(flags & kFlagVolume)) {
+    radiance          = radiance + weight * eval_environment(scene, d);
+    st.radiance[lane] = pack(radiance, flags);
+    return kDestAcc;
+  }
+
   // ---- miss: environment, yocto_trace.cpp:469-473 / :1127-1131 ----
   if (!hit) {
     if (bounce > 0 || !p.envhidden) radiance = radiance + weight * eval_environment(scene, d);
@@ -374,7 +382,8 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
 
   if (!in_volume) {
     auto outgoing = -d;
-    auto position = eval_shading_position(scene, inst, ids.y, uv);
+    auto position = SAMPLER == kSamplerFurnace ? eval_position(scene, inst, ids.y, uv)  // yocto_trace.cpp:1282
+                                               : eval_shading_position(scene, inst, ids.y, uv);
     auto normal   = eval_shading_normal(scene, inst, ids.y, uv, outgoing);
     auto material = eval_material(scene, inst, ids.y, uv);
 
@@ -425,6 +434,32 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
         }
       }
       store_rng(st, lane, rng);
+      st.radiance[lane] = pack(radiance, flags);
+      st.weight[lane]   = pack(weight, max_roughness);
+      return dest;
+    }
+
+    if (SAMPLER == kSamplerNaive || SAMPLER == kSamplerFurnace) {
+      // trace_naive / trace_furnace, yocto_trace.cpp:1078-1100 / :1305-1336: bsdf sampling only
+      f3 incoming = {0, 0, 0};
+      if (material.roughness != 0) {
+        f2    rn  = rand2f(rng);  // g++: rand2f evaluated before rand1f
+        float rnl = rand1f(rng);
+        incoming  = sample_bsdfcos(material, normal, outgoing, rnl, rn);
+        if (!is_zero(incoming))
+          weight = weight * (eval_bsdfcos(material, normal, outgoing, incoming) /
+                                sample_bsdfcos_pdf(material, normal, outgoing, incoming));
+      } else {
+        incoming = sample_delta(material, normal, outgoing, rand1f(rng));
+        if (!is_zero(incoming))
+          weight = weight * (eval_delta(material, normal, outgoing, incoming) /
+                                sample_delta_pdf(material, normal, outgoing, incoming));
+      }
+      dest = is_zero(incoming) ? kDestAcc : finish_bounce(weight, bounce, rng, p);
+      if (SAMPLER == kSamplerFurnace && dot(normal, outgoing) * dot(normal, incoming) < 0) flags ^= kFlagVolume;
+      store_rng(st, lane, rng);
+      st.ray_o[lane]    = pack(position, bounce);
+      st.ray_d[lane]    = pack(incoming, opbounce);
       st.radiance[lane] = pack(radiance, flags);
       st.weight[lane]   = pack(weight, max_roughness);
       return dest;
@@ -733,6 +768,10 @@ void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Que
     k_shade<kSamplerFalsecolor><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else if (p.sampler == kSamplerEyelight)
     k_shade<kSamplerEyelight><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+  else if (p.sampler == kSamplerNaive)
+    k_shade<kSamplerNaive><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+  else if (p.sampler == kSamplerFurnace)
+    k_shade<kSamplerFurnace><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else
     k_shade<kSamplerPath><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
 }
