@@ -86,6 +86,14 @@ RENDERS = [
     ("cornell", dict(resolution=64, samples=4, bounces=6, sampler=abi.SAMPLER_NAIVE)),
     ("features", dict(resolution=96, samples=3, bounces=8, sampler=abi.SAMPLER_FURNACE)),
     ("features", dict(resolution=96, samples=2, bounces=8, sampler=abi.SAMPLER_FURNACE, camera=1, envhidden=1)),
+    ("features", dict(resolution=96, samples=3, bounces=8, sampler=abi.SAMPLER_PATHDIRECT)),
+    ("features", dict(resolution=96, samples=2, bounces=6, sampler=abi.SAMPLER_PATHDIRECT, camera=1, nocaustics=1, envhidden=1)),
+    ("cornell", dict(resolution=64, samples=4, bounces=8, sampler=abi.SAMPLER_PATHDIRECT)),
+    ("hair", dict(resolution=64, samples=2, bounces=8, sampler=abi.SAMPLER_PATHDIRECT)),
+    ("features", dict(resolution=96, samples=3, bounces=8, sampler=abi.SAMPLER_PATHMIS)),
+    ("features", dict(resolution=96, samples=2, bounces=6, sampler=abi.SAMPLER_PATHMIS, camera=1, nocaustics=1, envhidden=1)),
+    ("cornell", dict(resolution=64, samples=4, bounces=8, sampler=abi.SAMPLER_PATHMIS)),
+    ("instanced4", dict(resolution=64, samples=2, bounces=8, sampler=abi.SAMPLER_PATHMIS)),
 ]
 
 
@@ -251,3 +259,8 @@ def test_device_libm_matches_host_glibc(ctx):
     check(6, "atan2f", pad(u * 2 - 1), v)
     for e in (5.0, 6.0, 2.2, 2.4, 0.75, 2.0):
         check(7, "powf", pad(u), np.full(n + len(edges), e, np.float32))
+    # negative bases (the refraction lobes square a signed quantity), tiny bases (underflow), deep expf tails
+    check(7, "powf", pad(u * 4 - 2), np.full(n + len(edges), 2.0, np.float32))
+    check(7, "powf", pad(u * 1e-7), np.full(n + len(edges), 5.0, np.float32))
+    check(2, "expf", pad(-80 - u * 30))
+    check(3, "logf", pad(u * 1e-38))

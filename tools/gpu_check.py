@@ -58,6 +58,10 @@ renders = [
     ("hair", dict(resolution=128, samples=4, bounces=8)),
     ("features", dict(resolution=128, samples=3, bounces=8, sampler=abi.SAMPLER_NAIVE)),
     ("features", dict(resolution=128, samples=3, bounces=8, sampler=abi.SAMPLER_FURNACE)),
+    ("features", dict(resolution=128, samples=3, bounces=8, sampler=abi.SAMPLER_PATHDIRECT)),
+    ("cornell", dict(resolution=64, samples=4, bounces=8, sampler=abi.SAMPLER_PATHDIRECT)),
+    ("features", dict(resolution=128, samples=3, bounces=8, sampler=abi.SAMPLER_PATHMIS)),
+    ("cornell", dict(resolution=64, samples=4, bounces=8, sampler=abi.SAMPLER_PATHMIS)),
 ]
 for name, kw in renders:
     sc = cases[name]

@@ -594,7 +594,9 @@ static int state_create_rows(ygl_context* ctx, const ygl_scene_desc* desc, const
          o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_ro = take(lanes * 16), o_rd = take(lanes * 16),
          o_rad = take(lanes * 16), o_w = take(lanes * 16), o_huvd = take(lanes * 16), o_hid = take(lanes * 8),
          o_a0 = take(lanes * 16), o_n0 = take(lanes * 16), o_va = take(lanes * 16), o_vb = take(lanes * 16),
-         o_pend = take(lanes * 16), o_susp = take(lanes * 4 * 48);
+         o_pend = take(lanes * 16), o_susp = take(lanes * 4 * 48), o_ao = take(lanes * 16), o_ad = take(lanes * 16),
+         o_ab = take(lanes * 16), o_au = take(lanes * 16), o_ai = take(lanes * 8), o_nu = take(lanes * 16),
+         o_ni = take(lanes * 8);
   CUDA_TRY(cudaMalloc((void**)&state->mem, off));
   CUDA_TRY(cudaMemset(state->mem, 0, off));
   PathState& st = state->st;
@@ -619,6 +621,13 @@ static int state_create_rows(ygl_context* ctx, const ygl_scene_desc* desc, const
   st.vol_b    = (float4*)(m + o_vb);
   st.pend     = (float4*)(m + o_pend);
   st.susp     = (int*)(m + o_susp);
+  st.aux_o    = (float4*)(m + o_ao);
+  st.aux_dir  = (float4*)(m + o_ad);
+  st.aux_bsdf = (float4*)(m + o_ab);
+  st.aux_uvd  = (float4*)(m + o_au);
+  st.aux_ids  = (int2*)(m + o_ai);
+  st.next_uvd = (float4*)(m + o_nu);
+  st.next_ids = (int2*)(m + o_ni);
   // rng table: seeded sequentially over the FULL image (yocto_trace.cpp:1512-1515), tile slice uploaded
   std::vector<uint64_t> rngs((size_t)w * h * 2);
   state_rngs(*params, w, h, rngs.data());
@@ -763,7 +772,8 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   }
   cudaStream_t s0 = ctx->stream;
 
-  const bool path_like = params.sampler == YGL_SAMPLER_PATH;
+  const bool path_like = params.sampler == YGL_SAMPLER_PATH || params.sampler == YGL_SAMPLER_PATHDIRECT ||
+                         params.sampler == YGL_SAMPLER_PATHMIS;  // samplers with a light-pdf stage
   uint64_t   iterations = 0, launches = 0;
   const int  check_every = 4;
   const bool timing = ctx->time_kernels;
@@ -878,9 +888,9 @@ static int check_sampler(const ygl_trace_params& p) {
     case YGL_SAMPLER_EYELIGHT:
     case YGL_SAMPLER_NAIVE:
     case YGL_SAMPLER_FURNACE:
-    case YGL_SAMPLER_FALSECOLOR: return YGL_OK;
     case YGL_SAMPLER_PATHDIRECT:
     case YGL_SAMPLER_PATHMIS:
+    case YGL_SAMPLER_FALSECOLOR: return YGL_OK;
     case YGL_SAMPLER_PATHTEST:
     case YGL_SAMPLER_DIAGRAM: return fail(YGL_ERR_RUNTIME, "sampler not implemented on the B200 path yet");
     default: return fail(YGL_ERR_RUNTIME, "sampler unknown");  // yocto_trace.cpp:1437

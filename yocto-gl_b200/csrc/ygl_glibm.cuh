@@ -152,7 +152,26 @@ YGL_GLIBM_FN bool cosf_(float y, float* out) {
 // e_expf.c. kExp2fRest = {shift_scaled, poly[3], shift, invln2_scaled, poly_scaled[3]}
 template <bool FMA>
 YGL_GLIBM_FN bool expf_(float x, float* out) {
-  if (abstop12(x) >= abstop12(88.0f)) return false;  // overflow / underflow / nan handling: fallback
+  if (abstop12(x) >= abstop12(88.0f)) {
+    // |x| >= 88 or nan: glibc's special cases (__math_oflowf / __math_uflowf / __math_may_uflowf results)
+    if (asuint(x) == 0xff800000u) {
+      *out = 0.0f;
+      return true;
+    }
+    if (abstop12(x) >= abstop12(asfloat(0x7f800000u))) return false;  // +inf, nan: fallback
+    if (x > 0x1.62e42ep6f) {
+      *out = asfloat(0x7f800000u);
+      return true;
+    }
+    if (x < -0x1.9fe368p6f) {
+      *out = 0.0f;
+      return true;
+    }
+    if (x < -0x1.9d1d9ep6f) {
+      *out = asfloat(1u);  // 0x1.4p-75f * 0x1.4p-75f rounds to the smallest subnormal
+      return true;
+    }
+  }
   double             xd = x;
   double             z  = kExp2fRest[5] * xd;
   double             kd = z + kExp2fRest[4];
@@ -180,7 +199,11 @@ YGL_GLIBM_FN bool logf_(float x, float* out) {
     *out = 0;
     return true;
   }
-  if (ix - 0x00800000 >= 0x7f800000 - 0x00800000) return false;  // zero, negative, subnormal, inf, nan: fallback
+  if (ix - 0x00800000 >= 0x7f800000 - 0x00800000) {
+    if (ix == 0 || ix >= 0x7f800000) return false;  // zero, negative, inf, nan: fallback (exact in fp64)
+    ix = asuint(x * 0x1p23f);                         // subnormal x: normalize
+    ix -= 23u << 23;
+  }
   unsigned tmp = ix - 0x3f330000;
   int      i   = (tmp >> (23 - 4)) % 16;
   int      k   = (int)tmp >> 23;
@@ -254,14 +277,33 @@ YGL_GLIBM_FN bool atanf_(float x, float* out) {
   return true;
 }
 
-// e_powf.c (log2_inline + exp2_inline) for normal positive x and finite non-zero y with
-// |y*log2(x)| < 126; everything else (zero/negative/subnormal/inf/nan operands, overflow and
+// e_powf.c (log2_inline + exp2_inline) for normal x (negative x only with an integer y: the result
+// takes the sign (-1)^y, as glibc's sign_bias does) and finite non-zero y with |y*log2|x|| < 126;
+// everything else (zero/subnormal/inf/nan operands, negative x with fractional y, overflow and
 // underflow handling) falls back. kExp2fRest[0] = shift_scaled, [1..3] = poly.
 template <bool FMA>
 YGL_GLIBM_FN bool powf_(float x, float y, float* out) {
   unsigned ix = asuint(x), iy = asuint(y);
-  if (ix - 0x00800000 >= 0x7f800000 - 0x00800000) return false;
   if (2 * iy - 1 >= 2u * 0x7f800000 - 1) return false;  // zeroinfnan(iy)
+  if (ix & 0x80000000u) {
+    // checkint(iy): 0 = not an integer, 1 = odd, 2 = even
+    int e = (int)(iy >> 23 & 0xff), yint;
+    if (e < 0x7f) yint = 0;
+    else if (e > 0x7f + 23) yint = 2;
+    else if (iy & ((1u << (0x7f + 23 - e)) - 1)) yint = 0;
+    else yint = (iy & (1u << (0x7f + 23 - e))) ? 1 : 2;
+    if (yint == 0) return false;
+    float r;
+    if (!powf_<FMA>(asfloat(ix & 0x7fffffffu), y, &r)) return false;
+    *out = yint == 1 ? -r : r;
+    return true;
+  }
+  if (ix - 0x00800000 >= 0x7f800000 - 0x00800000) {
+    if (ix == 0 || ix >= 0x7f800000) return false;  // zero, inf, nan: fallback (exact in fp64)
+    ix = asuint(x * 0x1p23f);                         // subnormal x: normalize
+    ix &= 0x7fffffff;
+    ix -= 23u << 23;
+  }
   unsigned tmp = ix - 0x3f330000;
   int      i   = (tmp >> (23 - 4)) % 16;
   unsigned top = tmp & 0xff800000;
@@ -279,7 +321,22 @@ YGL_GLIBM_FN bool powf_(float x, float y, float* out) {
   q         = mad<FMA>(p, r2, q);
   double logx  = mad<FMA>(yy, r4, q);
   double ylogx = (double)y * logx;
-  if ((asuint64(ylogx) >> 47 & 0xffff) >= asuint64(126.0) >> 47) return false;
+  if ((asuint64(ylogx) >> 47 & 0xffff) >= asuint64(126.0) >> 47) {
+    // |y*log2(x)| >= 126 (or nan): glibc's overflow / underflow results
+    if (!(ylogx == ylogx)) return false;
+    if (ylogx > 0x1.fffffffd1d571p+6) {
+      *out = asfloat(0x7f800000u);
+      return true;
+    }
+    if (ylogx <= -150.0) {
+      *out = 0.0f;
+      return true;
+    }
+    if (ylogx < -149.0) {
+      *out = asfloat(1u);
+      return true;
+    }
+  }
   double             kd = ylogx + kExp2fRest[0];
   unsigned long long ki = asuint64(kd);
   kd -= kExp2fRest[0];

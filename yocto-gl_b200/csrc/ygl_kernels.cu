@@ -20,7 +20,12 @@
 namespace ygl {
 
 enum : int { kDestNone = 0, kDestExt = 1, kDestLpdf = 2, kDestAcc = 3 };
-enum : int { kFlagHit = 1, kFlagVolume = 2 };
+enum : int { kFlagHit = 1, kFlagVolume = 2, kFlagNoEmission = 4 };  // NoEmission: next_emission == false
+// extend-queue entry = lane id | flags
+enum : int { kEntryResume = (int)0x80000000, kEntryShadow = 0x40000000, kEntryPass = 0x20000000, kEntryLane = 0x1fffffff };
+// phases of a pathdirect / pathmis bounce (PathState::aux_bsdf.w)
+enum : int { kPhaseMain = 0, kPhaseDirectPdf = 1, kPhaseShadowHit = 2, kPhaseShadowSkip = 3, kPhaseNextPdf = 4,
+  kPhaseBsdfPdf = 5, kPhaseBsdfHit = 6, kPhaseBsdfSkip = 7 };
 enum : int {
   kSamplerPath = 0, kSamplerPathDirect, kSamplerPathMis, kSamplerPathTest, kSamplerNaive, kSamplerEyelight,
   kSamplerDiagram, kSamplerFurnace, kSamplerFalsecolor
@@ -103,6 +108,11 @@ __global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Qu
       st.weight[lane]   = pack(f3{1, 1, 1}, 0.0f);
       st.albedo0[lane]  = pack(f3{0, 0, 0}, 0.0f);
       st.normal0[lane]  = pack(-d, 0.0f);
+      if (p.sampler == kSamplerPathDirect || p.sampler == kSamplerPathMis) {
+        st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseMain);
+        st.next_uvd[lane] = make_float4(0, 0, 0, __int_as_float(0));  // next_intersection = {}
+        st.next_ids[lane] = make_int2(-1, -1);
+      }
     }
     queue_push(q.ext[parity], &c->n_ext[parity], valid, lane);
   }
@@ -120,6 +130,7 @@ struct ExtendSource {
   int        lane;
   int        refill_thr, node_reps, suspend_below;  // tuning knobs (see launch_extend)
   unsigned   finished;                              // rays completed by this thread (scene_rays counter)
+  bool       shadow;                                // current ray is a shadow ray (pathdirect / pathmis)
   // Queue entries: lane id; bit 31 set = the ray was suspended by the previous launch (resume it).
   YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more, bool& resume) {
     const unsigned m    = __ballot_sync(kFullWarp, idle);
@@ -131,19 +142,21 @@ struct ExtendSource {
     more         = base + __popc(m) < n;
     if (!idle || my >= n) return false;
     const int entry = queue[my];
-    lane     = entry & 0x7fffffff;
+    if (entry & kEntryPass) return false;  // the lane skips this extend (its hit record is already in place)
+    lane     = entry & kEntryLane;
     resume   = entry < 0;
-    float4 a = st.ray_o[lane], b = st.ray_d[lane];
+    shadow   = (entry & kEntryShadow) != 0;
+    float4 a = shadow ? st.aux_o[lane] : st.ray_o[lane], b = shadow ? st.aux_dir[lane] : st.ray_d[lane];
     o = unpack3(a), d = unpack3(b);
     return true;
   }
   YGL_D void commit(const hit_t& h) {
-    st.hit_uvd[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
-    st.hit_ids[lane] = make_int2(h.instance, h.element);
+    (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
+    (shadow ? st.aux_ids : st.hit_ids)[lane] = make_int2(h.instance, h.element);
     finished++;
   }
   YGL_D int* saved() { return st.susp + (size_t)lane * kSuspendWords; }
-  YGL_D void commit_suspended() { st.hit_uvd[lane] = make_float4(0, 0, 0, __int_as_float(2)); }
+  YGL_D void commit_suspended() { (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(0, 0, 0, __int_as_float(2)); }
 };
 
 #ifndef YGL_EXT_MINBLOCKS
@@ -154,7 +167,7 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene,
     unsigned long long* trav, int refill_thr, int node_reps, int suspend_below) {
   Counters*     c = q.counters;
   const int     n = c->n_ext[parity];
-  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps, suspend_below, 0};
+  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps, suspend_below, 0, false};
   trav_counters tc = {};
   trace_stream<COUNT>(scene, src, tc);
   {
@@ -542,6 +555,251 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
   }
 }
 
+
+// ---- pathdirect / pathmis: trace_pathdirect (yocto_trace.cpp:599-767) and trace_pathmis (:770-950). A non-delta
+// bounce needs extra light-pdf and shadow-ray stages, so a lane passes through shade several times per bounce;
+// the phase (PathState::aux_bsdf.w) says where it is. Returns dest | extend-entry flags. ----
+YGL_D float mis_heuristic(float this_pdf, float other_pdf) {  // yocto_trace.cpp:785-788
+  return (this_pdf * this_pdf) / (this_pdf * this_pdf + other_pdf * other_pdf);
+}
+// emission seen along a shadow ray, yocto_trace.cpp:667-677 / :874-886
+YGL_D f3 shadow_emission(const DScene& scene, const PathState& st, int lane, const f3& incoming) {
+  float4 h = st.aux_uvd[lane];
+  if (__float_as_int(h.w) == 0) return eval_environment(scene, incoming);
+  int2             ids  = st.aux_ids[lane];
+  const DInstance& inst = scene.instances[ids.x];
+  f2               uv   = {h.x, h.y};
+  auto material = eval_material(scene, inst, ids.y, uv);
+  auto normal   = eval_shading_normal(scene, inst, ids.y, uv, -incoming);
+  return eval_emission(material, normal, -incoming);
+}
+
+template <int SAMPLER>
+YGL_D int shade_multi(const DScene& scene, const PathState& st, const KParams& p, int lane) {
+  constexpr bool MIS = SAMPLER == kSamplerPathMis;
+  float4 ro = st.ray_o[lane], rd = st.ray_d[lane], rad4 = st.radiance[lane], w4 = st.weight[lane];
+  float4 huvd = st.hit_uvd[lane], ab = st.aux_bsdf[lane];
+  f3  o = unpack3(ro), d = unpack3(rd), radiance = unpack3(rad4), weight = unpack3(w4);
+  int bounce = __float_as_int(ro.w), opbounce = __float_as_int(rd.w), flags = __float_as_int(rad4.w);
+  float max_roughness = w4.w;
+  bool  hit   = __float_as_int(huvd.w) != 0;
+  int   phase = __float_as_int(ab.w);
+  const bool next_emission = !(flags & kFlagNoEmission);
+
+  if (!hit) {  // only reachable in kPhaseMain (a lane in a later phase has a surface hit)
+    if ((bounce > 0 || !p.envhidden) && next_emission) radiance = radiance + weight * eval_environment(scene, d);
+    st.radiance[lane] = pack(radiance, flags);
+    return kDestAcc;
+  }
+  int2 ids = st.hit_ids[lane];
+  const DInstance& inst = scene.instances[ids.x];
+  f2    uv       = {huvd.x, huvd.y};
+  float distance = huvd.z;
+  rng_t rng      = load_rng(st, lane);
+
+  auto store_common = [&]() {
+    store_rng(st, lane, rng);
+    st.radiance[lane] = pack(radiance, flags);
+    st.weight[lane]   = pack(weight, max_roughness);
+  };
+
+  // ---- participating medium (first pass of the bounce only) ----
+  if (phase == kPhaseMain && (flags & kFlagVolume)) {
+    float4 va = st.vol_a[lane], vb = st.vol_b[lane];
+    vsdf_t vsdf = {unpack3(va), unpack3(vb), va.w};
+    float  r_d = rand1f(rng), r_l = rand1f(rng);
+    float  dist = sample_transmittance(vsdf.density, distance, r_l, r_d);
+    weight = weight * (eval_transmittance(vsdf.density, dist) / sample_transmittance_pdf(vsdf.density, dist, distance));
+    if (dist < distance) {
+      // scattering event, yocto_trace.cpp:738-757 / :921-941 (pathmis has no zero-direction check)
+      auto outgoing = -d;
+      auto position = o + d * dist;
+      f3   incoming = {0, 0, 0};
+      if (rand1f(rng) < 0.5f) {
+        f2 rn = rand2f(rng);
+        (void)rand1f(rng);
+        incoming = sample_scattering(vsdf, outgoing, rn);
+      } else {
+        f2    ruv = rand2f(rng);
+        float rel = rand1f(rng), rl = rand1f(rng);
+        incoming  = sample_lights(scene, position, rl, rel, ruv);
+      }
+      if (MIS) flags &= ~kFlagNoEmission;  // next_emission = true
+      store_common();
+      if (!MIS && is_zero(incoming)) return kDestAcc;
+      st.pend[lane]     = pack(eval_scattering(vsdf, outgoing, incoming), sample_scattering_pdf(vsdf, outgoing, incoming));
+      st.ray_o[lane]    = pack(position, bounce);
+      st.ray_d[lane]    = pack(incoming, opbounce);
+      st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseNextPdf);
+      return kDestLpdf;
+    }
+  }
+
+  // ---- the surface point (recomputed identically on every pass: it is a pure function of the hit) ----
+  auto outgoing = -d;
+  auto position = eval_shading_position(scene, inst, ids.y, uv);
+  auto normal   = eval_shading_normal(scene, inst, ids.y, uv, outgoing);
+  auto material = eval_material(scene, inst, ids.y, uv);
+  if (p.nocaustics) {
+    max_roughness      = ymax(material.roughness, max_roughness);
+    material.roughness = max_roughness;
+  }
+  const bool delta = is_delta(material);
+  f3         incoming = {0, 0, 0};
+  bool       have_next = false;  // `incoming` is the path's next direction and its weight update is done/pending
+
+  if (phase == kPhaseMain) {
+    if (material.opacity < 1 && rand1f(rng) >= material.opacity) {
+      store_rng(st, lane, rng);
+      if (opbounce++ > 128) {
+        st.radiance[lane] = pack(radiance, flags);
+        return kDestAcc;
+      }
+      st.ray_o[lane]  = pack(position + d * 1e-2f, bounce);
+      st.ray_d[lane]  = pack(d, opbounce);
+      st.weight[lane] = pack(weight, max_roughness);
+      // pathmis after a non-delta bounce re-uses next_intersection instead of tracing (yocto_trace.cpp:793-794):
+      // the lane's hit record stays as it is and the extend is skipped
+      return kDestExt | ((MIS && !next_emission) ? kEntryPass : 0);
+    }
+    if (bounce == 0) {
+      flags |= kFlagHit;
+      st.albedo0[lane] = pack(material.color, 0.0f);
+      st.normal0[lane] = pack(normal, 0.0f);
+    }
+    if (next_emission) radiance = radiance + weight * eval_emission(material, normal, outgoing);
+    if (!delta) {
+      // first direct sample: the lights (draw order ruv, rel, rl)
+      f2    ruv = rand2f(rng);
+      float rel = rand1f(rng), rl = rand1f(rng);
+      f3    dl  = sample_lights(scene, position, rl, rel, ruv);
+      if (MIS && is_zero(dl)) {
+        // `break` out of the sample loop: the indirect update then runs with incoming = 0 (yocto_trace.cpp:857, :892)
+        weight = weight * (eval_bsdfcos(material, normal, outgoing, dl) / sample_bsdfcos_pdf(material, normal, outgoing, dl));
+        flags |= kFlagNoEmission;
+        incoming = dl, have_next = true;
+      } else {
+        auto bsdfcos = eval_bsdfcos(material, normal, outgoing, dl);
+        st.aux_o[lane]    = pack(position, MIS ? sample_bsdfcos_pdf(material, normal, outgoing, dl) : 0.0f);
+        st.aux_dir[lane]  = pack(dl, 0.0f);
+        st.aux_bsdf[lane] = pack(bsdfcos, kPhaseDirectPdf);
+        store_common();
+        return kDestLpdf;
+      }
+    } else if (!MIS) {
+      flags &= ~kFlagNoEmission;  // pathdirect: next_emission = true after a delta surface
+    }
+  }
+
+  if (phase == kPhaseShadowHit || phase == kPhaseShadowSkip) {
+    // contribution of the light sample
+    float4 ad = st.aux_dir[lane];
+    if (phase == kPhaseShadowHit) {
+      f3 emission = shadow_emission(scene, st, lane, unpack3(ad));
+      if (MIS) radiance = radiance + weight * unpack3(ab) * emission * ad.w;
+      else radiance = radiance + weight * unpack3(ab) * emission / ad.w;
+    }
+    if (!MIS) {
+      flags |= kFlagNoEmission;  // pathdirect: next_emission = false
+    } else {
+      // second direct sample: the bsdf (draw order rn, rnl)
+      f2    rn  = rand2f(rng);
+      float rnl = rand1f(rng);
+      f3    db  = sample_bsdfcos(material, normal, outgoing, rnl, rn);
+      if (is_zero(db)) {
+        weight = weight * (eval_bsdfcos(material, normal, outgoing, db) / sample_bsdfcos_pdf(material, normal, outgoing, db));
+        flags |= kFlagNoEmission;
+        incoming = db, have_next = true;
+      } else {
+        auto bsdfcos = eval_bsdfcos(material, normal, outgoing, db);
+        st.aux_o[lane]    = pack(position, sample_bsdfcos_pdf(material, normal, outgoing, db));
+        st.aux_dir[lane]  = pack(db, 0.0f);
+        st.aux_bsdf[lane] = pack(bsdfcos, kPhaseBsdfPdf);
+        store_common();
+        return kDestLpdf;
+      }
+    }
+  }
+
+  if (MIS && (phase == kPhaseBsdfHit || phase == kPhaseBsdfSkip)) {
+    float4 ad = st.aux_dir[lane], ao = st.aux_o[lane];
+    incoming  = unpack3(ad);
+    if (phase == kPhaseBsdfHit) {
+      st.next_uvd[lane] = st.aux_uvd[lane];  // next_intersection = intersection (yocto_trace.cpp:873)
+      st.next_ids[lane] = st.aux_ids[lane];
+      f3 emission       = shadow_emission(scene, st, lane, incoming);
+      radiance          = radiance + weight * unpack3(ab) * emission * ad.w;
+    }
+    weight = weight * (unpack3(ab) / ao.w);  // eval_bsdfcos / sample_bsdfcos_pdf of the bsdf sample (same values)
+    flags |= kFlagNoEmission;
+    have_next = true;
+  }
+
+  int dest;
+  if (!have_next) {
+    if (!delta) {
+      // pathdirect: next direction with one-sample MIS exactly like trace_path (yocto_trace.cpp:691-707)
+      if (rand1f(rng) < 0.5f) {
+        f2    rn  = rand2f(rng);
+        float rnl = rand1f(rng);
+        incoming  = sample_bsdfcos(material, normal, outgoing, rnl, rn);
+      } else {
+        f2    ruv = rand2f(rng);
+        float rel = rand1f(rng), rl = rand1f(rng);
+        incoming  = sample_lights(scene, position, rl, rel, ruv);
+      }
+      if (is_zero(incoming)) {
+        store_common();
+        return kDestAcc;
+      }
+      st.pend[lane]     = pack(eval_bsdfcos(material, normal, outgoing, incoming),
+              sample_bsdfcos_pdf(material, normal, outgoing, incoming));
+      st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseNextPdf);
+      dest              = kDestLpdf;
+    } else {
+      incoming = sample_delta(material, normal, outgoing, rand1f(rng));
+      if (!MIS && is_zero(incoming)) {  // pathdirect only (yocto_trace.cpp:710)
+        store_common();
+        return kDestAcc;
+      }
+      weight = weight * (eval_delta(material, normal, outgoing, incoming) /
+                            sample_delta_pdf(material, normal, outgoing, incoming));
+      if (MIS) flags &= ~kFlagNoEmission;  // next_emission = true
+      dest = kDestNone;
+    }
+  } else {
+    dest = kDestNone;
+  }
+
+  // ---- volume slot update, yocto_trace.cpp:716-724 / :903-911 ----
+  const DMaterial& mat = scene.materials[inst.material];
+  if (is_volumetric_type(mat.type) && dot(normal, outgoing) * dot(normal, incoming) < 0) {
+    if (!(flags & kFlagVolume)) {
+      auto vm        = eval_material(scene, inst, ids.y, uv);
+      st.vol_a[lane] = pack(vm.density, vm.scanisotropy);
+      st.vol_b[lane] = pack(vm.scattering, 0.0f);
+      flags |= kFlagVolume;
+    } else {
+      flags &= ~kFlagVolume;
+    }
+  }
+  int entry_flags = 0;
+  if (dest != kDestLpdf) {
+    dest = finish_bounce(weight, bounce, rng, p);
+    st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseMain);
+    if (MIS && dest == kDestExt && (flags & kFlagNoEmission)) {
+      // the next loop iteration uses next_intersection instead of tracing
+      st.hit_uvd[lane] = st.next_uvd[lane];
+      st.hit_ids[lane] = st.next_ids[lane];
+      entry_flags      = kEntryPass;
+    }
+  }
+  st.ray_o[lane] = pack(position, bounce);
+  st.ray_d[lane] = pack(incoming, opbounce);
+  store_common();
+  return dest | entry_flags;
+}
+
 #ifndef YGL_SHADE_THREADS
 #define YGL_SHADE_THREADS 256
 #endif
@@ -560,14 +818,19 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
     int lane = 0, dest = kDestNone;
     int entry = 0;
     if (i < n) {
-      lane = q.ext[parity][i] & 0x7fffffff;
-      if (__float_as_int(st.hit_uvd[lane].w) == 2) {
+      const int in_entry = q.ext[parity][i];
+      lane               = in_entry & kEntryLane;
+      const bool shadow  = (in_entry & kEntryShadow) != 0;
+      if (!(in_entry & kEntryPass) && __float_as_int((shadow ? st.aux_uvd : st.hit_uvd)[lane].w) == 2) {
         // the extend kernel suspended this ray: it stays in the extend queue, flagged for resumption
         dest  = kDestExt;
-        entry = lane | (int)0x80000000;
+        entry = lane | kEntryResume | (in_entry & kEntryShadow);
       } else {
-        dest  = shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
-        entry = lane;
+        int r = (SAMPLER == kSamplerPathDirect || SAMPLER == kSamplerPathMis)
+                    ? shade_multi<SAMPLER>(scene, st, p, lane)
+                    : shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
+        dest  = r & 3;
+        entry = lane | (r & (kEntryShadow | kEntryPass));
       }
     }
     queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
@@ -592,12 +855,36 @@ __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene sce
     int    i    = i0 + wl;
     int    lane = 0, dest = kDestNone;
     float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 1, 0);
+    const bool multi = p.sampler == kSamplerPathDirect || p.sampler == kSamplerPathMis;
+    int        phase = kPhaseMain, entry = 0;
     if (i < n) {
       lane = q.lpdf[i];
-      ro = st.ray_o[lane], rd = st.ray_d[lane];
+      if (multi) phase = __float_as_int(st.aux_bsdf[lane].w);
+      const bool direct = phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf;  // pdf of a direct sample at aux_o
+      ro = direct ? st.aux_o[lane] : st.ray_o[lane], rd = direct ? st.aux_dir[lane] : st.ray_d[lane];
     }
     float lpdf = sample_lights_pdf(scene, i < n, unpack3(ro), unpack3(rd), rays);
-    if (i < n) {
+    if (i < n && (phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf)) {
+      // direct lighting: decide whether the shadow ray is needed (yocto_trace.cpp:662-665 / :860-869)
+      float4 ab      = st.aux_bsdf[lane];
+      f3     bsdfcos = unpack3(ab);
+      bool   trace;
+      if (p.sampler == kSamplerPathDirect) {
+        st.aux_dir[lane] = pack(unpack3(rd), lpdf);
+        trace            = !is_zero(bsdfcos) && lpdf > 0;
+      } else {
+        float bsdf_pdf   = ro.w;
+        float mis_weight = phase == kPhaseDirectPdf ? mis_heuristic(lpdf, bsdf_pdf) / lpdf
+                                                    : mis_heuristic(bsdf_pdf, lpdf) / bsdf_pdf;
+        st.aux_dir[lane] = pack(unpack3(rd), mis_weight);
+        trace            = !is_zero(bsdfcos) && mis_weight != 0;
+      }
+      int next_phase    = phase == kPhaseDirectPdf ? (trace ? kPhaseShadowHit : kPhaseShadowSkip)
+                                                   : (trace ? kPhaseBsdfHit : kPhaseBsdfSkip);
+      st.aux_bsdf[lane] = pack(bsdfcos, next_phase);
+      dest              = kDestExt;
+      entry             = lane | (trace ? kEntryShadow : kEntryPass);
+    } else if (i < n) {
       float4 w4 = st.weight[lane], pd = st.pend[lane];
       f3     position = unpack3(ro), weight = unpack3(w4);
       int    bounce   = __float_as_int(ro.w);
@@ -607,8 +894,10 @@ __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene sce
       store_rng(st, lane, rng);
       st.ray_o[lane]  = pack(position, bounce);
       st.weight[lane] = pack(weight, w4.w);
+      if (multi) st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseMain);
+      entry = lane;
     }
-    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, lane);
+    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
     queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
   }
   // one atomic per warp for the instance-ray count
@@ -772,6 +1061,10 @@ void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Que
     k_shade<kSamplerNaive><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else if (p.sampler == kSamplerFurnace)
     k_shade<kSamplerFurnace><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+  else if (p.sampler == kSamplerPathDirect)
+    k_shade<kSamplerPathDirect><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+  else if (p.sampler == kSamplerPathMis)
+    k_shade<kSamplerPathMis><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else
     k_shade<kSamplerPath><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
 }

@@ -35,6 +35,14 @@ struct PathState {
   float4* vol_b;     // volume slot: scattering.xyz
   float4* pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
   int*    susp;      // kSuspendWords ints per lane: traversal state of a ray suspended by k_extend
+  // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
+  float4* aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
+  float4* aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
+  float4* aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
+  float4* aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
+  int2*   aux_ids;   // shadow-ray hit: instance, element
+  float4* next_uvd;  // pathmis next_intersection (persists across bounces)
+  int2*   next_ids;
 };
 
 // Work queues: lane ids compacted with warp-ballot / one atomic per warp.

@@ -65,8 +65,9 @@ YGL_HD bool  yfinite(float a) { return isfinite(a); }
 // expf/logf/powf as their FMA builds (what glibc's ifunc selects on FMA-capable hosts), atanf/acosf/
 // atan2f as the plain fdlibm kernels — verified exhaustively against the host libm
 // (tools/libm_check_host.cpp: 0 mismatches over every float input in the covered ranges).
-// Arguments outside those ranges (|x| >= 120 for sin/cos, overflow/underflow/special operands)
-// fall back to fp64 evaluation rounded once. Host: the host libm itself.
+// expf/logf/powf cover every finite operand, including negative bases with integer exponents,
+// subnormals and the overflow/underflow results; what is left (|x| >= 120 for sin/cos, zero/inf/nan
+// operands, where fp64 is exact) falls back to fp64 evaluation rounded once. Host: the host libm itself.
 YGL_HD float ysqrt(float a) { return sqrtf(a); }  // IEEE exact
 #ifdef __CUDA_ARCH__
 #define YGL_LIBM1(name, impl, fallback)            \
