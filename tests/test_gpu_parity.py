@@ -94,6 +94,11 @@ RENDERS = [
     ("features", dict(resolution=96, samples=2, bounces=6, sampler=abi.SAMPLER_PATHMIS, camera=1, nocaustics=1, envhidden=1)),
     ("cornell", dict(resolution=64, samples=4, bounces=8, sampler=abi.SAMPLER_PATHMIS)),
     ("instanced4", dict(resolution=64, samples=2, bounces=8, sampler=abi.SAMPLER_PATHMIS)),
+    ("features", dict(resolution=96, samples=3, bounces=8, sampler=abi.SAMPLER_PATHTEST)),
+    ("cornell", dict(resolution=64, samples=3, bounces=5, sampler=abi.SAMPLER_PATHTEST, envhidden=1)),
+    ("features", dict(resolution=96, samples=3, bounces=8, sampler=abi.SAMPLER_DIAGRAM)),
+    ("features", dict(resolution=96, samples=2, bounces=2, sampler=abi.SAMPLER_DIAGRAM, camera=1)),
+    ("cornell", dict(resolution=64, samples=2, bounces=4, sampler=abi.SAMPLER_DIAGRAM)),
 ]
 
 
@@ -107,6 +112,23 @@ def test_render_matches_oracle(ctx, ref, ref_dlibm, name, kw):
     assert image.tobytes() == exact.tobytes(), image_stats(exact, image)
     # cross-check: the double-rounded-libm twin of the reference stays within the stated float tolerance
     assert_close_to_reference(image_stats(ref_dlibm.scene(scene).trace_image(params)["image"], image))
+
+
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_PATHDIRECT, abi.SAMPLER_PATHMIS, abi.SAMPLER_PATHTEST, abi.SAMPLER_NAIVE,
+                                     abi.SAMPLER_EYELIGHT, abi.SAMPLER_DIAGRAM, abi.SAMPLER_FURNACE, abi.SAMPLER_FALSECOLOR])
+def test_full_state_every_sampler(ctx, ref, sampler):
+    """Every sampler of get_trace_sampler_func (yocto_trace.cpp:1422-1438): image, denoise guides (albedo,
+    normal), hit counts and the advanced rng streams all match the unmodified reference bit for bit."""
+    scene = get_scene("features")
+    params = abi.trace_params(resolution=72, samples=2, bounces=6, batch=2, sampler=sampler)
+    want = ref.scene(scene).trace_image(params, full=True)
+    ds = lib.DeviceScene(ctx, scene)
+    st = ds.make_state(params)
+    ds.trace_samples(st, params)
+    got = st.download(full=True)
+    for k in ("image", "albedo", "normal", "hits"):
+        assert got[k].tobytes() == want[k].tobytes(), k
+    np.testing.assert_array_equal(got["rngs"], want["rngs"])
 
 
 def test_full_state_and_resume(ctx, ref):

@@ -773,7 +773,8 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   cudaStream_t s0 = ctx->stream;
 
   const bool path_like = params.sampler == YGL_SAMPLER_PATH || params.sampler == YGL_SAMPLER_PATHDIRECT ||
-                         params.sampler == YGL_SAMPLER_PATHMIS;  // samplers with a light-pdf stage
+                         params.sampler == YGL_SAMPLER_PATHMIS ||
+                         params.sampler == YGL_SAMPLER_PATHTEST;  // samplers with a light-pdf stage
   uint64_t   iterations = 0, launches = 0;
   const int  check_every = 4;
   const bool timing = ctx->time_kernels;
@@ -890,9 +891,9 @@ static int check_sampler(const ygl_trace_params& p) {
     case YGL_SAMPLER_FURNACE:
     case YGL_SAMPLER_PATHDIRECT:
     case YGL_SAMPLER_PATHMIS:
-    case YGL_SAMPLER_FALSECOLOR: return YGL_OK;
     case YGL_SAMPLER_PATHTEST:
-    case YGL_SAMPLER_DIAGRAM: return fail(YGL_ERR_RUNTIME, "sampler not implemented on the B200 path yet");
+    case YGL_SAMPLER_DIAGRAM:
+    case YGL_SAMPLER_FALSECOLOR: return YGL_OK;
     default: return fail(YGL_ERR_RUNTIME, "sampler unknown");  // yocto_trace.cpp:1437
   }
 }

@@ -367,7 +367,15 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
 
   // ---- miss: environment, yocto_trace.cpp:469-473 / :1127-1131 ----
   if (!hit) {
-    if (bounce > 0 || !p.envhidden) radiance = radiance + weight * eval_environment(scene, d);
+    if (SAMPLER == kSamplerDiagram) {
+      // trace_diagram, yocto_trace.cpp:1194-1199: a miss is white and counts as a hit (albedo / normal stay
+      // at their bounce-0 values, or zero if there was no surface before)
+      radiance = radiance + weight * f3{1, 1, 1};
+      if (!(flags & kFlagHit)) st.normal0[lane] = pack(f3{0, 0, 0}, 0.0f);
+      flags |= kFlagHit;
+    } else if (bounce > 0 || !p.envhidden) {
+      radiance = radiance + weight * eval_environment(scene, d);
+    }
     st.radiance[lane] = pack(radiance, flags);
     return kDestAcc;
   }
@@ -405,8 +413,10 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
       material.roughness = max_roughness;
     }
 
-    // opacity pass-through, yocto_trace.cpp:505-510 (rng drawn only when opacity < 1)
-    if (material.opacity < 1 && rand1f(rng) >= material.opacity) {
+    if (SAMPLER == kSamplerPathTest) material.type = kMatte;  // yocto_trace.cpp:981 (after eval_material)
+
+    // opacity pass-through, yocto_trace.cpp:505-510 (rng drawn only when opacity < 1); trace_pathtest has none
+    if (SAMPLER != kSamplerPathTest && material.opacity < 1 && rand1f(rng) >= material.opacity) {
       store_rng(st, lane, rng);
       if (opbounce++ > 128) {
         st.radiance[lane] = pack(radiance, flags);
@@ -426,8 +436,8 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
 
     radiance = radiance + weight * eval_emission(material, normal, outgoing);
 
-    if (SAMPLER == kSamplerEyelight) {
-      // yocto_trace.cpp:1155-1172
+    if (SAMPLER == kSamplerEyelight || SAMPLER == kSamplerDiagram) {
+      // yocto_trace.cpp:1155-1172 / :1224-1240 (trace_diagram differs from trace_eyelight only on a miss)
       auto incoming = outgoing;
       radiance      = radiance + weight * kPi * eval_bsdfcos(material, normal, outgoing, incoming);
       dest          = kDestAcc;
@@ -508,7 +518,8 @@ YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p,
 
     // ---- volume slot update, yocto_trace.cpp:545-553 (independent of the pending weight) ----
     const DMaterial& mat = scene.materials[inst.material];
-    if (is_volumetric_type(mat.type) && dot(normal, outgoing) * dot(normal, incoming) < 0) {
+    if (SAMPLER != kSamplerPathTest && is_volumetric_type(mat.type) &&
+        dot(normal, outgoing) * dot(normal, incoming) < 0) {
       if (!(flags & kFlagVolume)) {
         auto vm        = eval_material(scene, inst, ids.y, uv);
         st.vol_a[lane] = pack(vm.density, vm.scanisotropy);
@@ -1061,6 +1072,10 @@ void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Que
     k_shade<kSamplerNaive><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else if (p.sampler == kSamplerFurnace)
     k_shade<kSamplerFurnace><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+  else if (p.sampler == kSamplerPathTest)
+    k_shade<kSamplerPathTest><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+  else if (p.sampler == kSamplerDiagram)
+    k_shade<kSamplerDiagram><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else if (p.sampler == kSamplerPathDirect)
     k_shade<kSamplerPathDirect><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else if (p.sampler == kSamplerPathMis)
