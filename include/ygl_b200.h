@@ -277,6 +277,13 @@ int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]);
  * with CUDA events on the context stream. count_traversal != 0: run the counting variant of the
  * extend kernel (slower; never combine with timing you report). */
 int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_traversal);
+/* Scheduling mode of ygl_trace_samples / ygl_trace_image (both give bit-identical results):
+ * YGL_MODE_WAVEFRONT (default) - one kernel per stage and iteration, linked by compacted lane queues;
+ * YGL_MODE_PERSISTENT - ONE resident kernel per call, stage-specialised SMs linked by ring queues in global memory
+ * (independent of the tile size, no per-iteration launches; opt-in). The environment variable YGL_MODE
+ * (wavefront|persistent) sets the default of new contexts. */
+enum { YGL_MODE_WAVEFRONT = 0, YGL_MODE_PERSISTENT = 1 };
+int ygl_context_set_mode(ygl_context* ctx, int mode);
 /* Timings of the last ygl_trace_samples / ygl_trace_image with time_kernels on:
  * [0] sum of extend-kernel launch durations (ms), [1] whole sample loop (ms), [2] extend launches. */
 int ygl_trace_timings(ygl_context* ctx, double ms[4]);

@@ -131,6 +131,29 @@ def test_full_state_every_sampler(ctx, ref, sampler):
     np.testing.assert_array_equal(got["rngs"], want["rngs"])
 
 
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_PATH, abi.SAMPLER_PATHMIS, abi.SAMPLER_PATHDIRECT, abi.SAMPLER_NAIVE,
+                                     abi.SAMPLER_EYELIGHT, abi.SAMPLER_FALSECOLOR])
+def test_persistent_mode_matches_reference(ref, sampler):
+    """YGL_MODE_PERSISTENT (one resident kernel, SM-specialised stages linked by ring queues) is a scheduling
+    change only: full state bit-identical to the unmodified reference, incl. a resumed second batch, on a frame
+    large enough to use SM-specialised blocks and on a tiny one (mixed blocks)."""
+    pctx = lib.Context(0)
+    pctx.set_mode("persistent")
+    scene = get_scene("features")
+    for res, spp in ((256, 4), (40, 2)):
+        params = abi.trace_params(resolution=res, samples=spp, bounces=6, batch=spp // 2, sampler=sampler)
+        want = ref.scene(scene).trace_image(params, full=True)
+        ds = lib.DeviceScene(pctx, scene)
+        st = ds.make_state(params)
+        ds.trace_samples(st, params)
+        ds.trace_samples(st, params)
+        assert st.samples == spp
+        got = st.download(full=True)
+        for k in ("image", "albedo", "normal", "hits"):
+            assert got[k].tobytes() == want[k].tobytes(), (k, res)
+        np.testing.assert_array_equal(got["rngs"], want["rngs"])
+
+
 def test_full_state_and_resume(ctx, ref):
     ref_dlibm = ref  # (name kept below) the unmodified reference
     """trace_state semantics: albedo/normal/hits/rngs match, and batches of 1,2,3 samples resume to

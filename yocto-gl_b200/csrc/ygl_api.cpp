@@ -10,6 +10,8 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "../../include/ygl_b200.h"
@@ -84,9 +86,13 @@ struct ygl_context {
   uint64_t  stats[16]   = {0};
   double    timings[4]  = {0};
   bool      time_kernels = false, count_traversal = false;
+  int       mode = YGL_MODE_WAVEFRONT;
   unsigned long long*      d_trav = nullptr;  // 7 traversal counters
   std::vector<cudaEvent_t> ev_pool;           // event pairs around extend launches
   cudaEvent_t              ev_loop[2] = {nullptr, nullptr};
+  // persistent mode: three ring queues + their cursors (see PQueues)
+  int*     ring_mem = nullptr;
+  unsigned ring_cap = 0;
   // binding cache: DShape table for a (scene, bvh, lights) triple
   const ygl_scene*  bound_scene  = nullptr;
   const ygl_bvh*    bound_bvh    = nullptr;
@@ -174,6 +180,7 @@ int ygl_context_create(int device, ygl_context** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char* env = getenv("YGL_MODE")) ctx->mode = !strcmp(env, "persistent") ? YGL_MODE_PERSISTENT : YGL_MODE_WAVEFRONT;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int k = 0; k < ygl_context::kMaxPipes; k++) {
     auto& pipe = ctx->pipes[k];
@@ -214,6 +221,7 @@ void ygl_context_destroy(ygl_context* ctx) {
   if (ctx->d_shapes) cudaFree(ctx->d_shapes);
   if (ctx->d_lights) cudaFree(ctx->d_lights);
   if (ctx->d_trav) cudaFree(ctx->d_trav);
+  if (ctx->ring_mem) cudaFree(ctx->ring_mem);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   for (auto& e : ctx->ev_loop)
     if (e) cudaEventDestroy(e);
@@ -754,7 +762,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     ygl_context::Pipe* pipe;
     Queues             q;
     int                lo, hi, parity = 0, slot = 0;
-    bool               pending[2] = {false, false}, done = false;
+    bool               pending[2] = {false, false}, done = false, first = true;
     LaunchCfg          light, heavy;
   } runs[ygl_context::kMaxPipes];
   for (int j = 0; j < npipes; j++) {
@@ -799,7 +807,9 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
         if (r.done) continue;
         cudaStream_t s = r.pipe->stream;
         launch_begin_iteration(s, r.q, r.parity);
-        launch_generate(s, r.light, ctx->dscene, st, r.q, kp, r.parity);
+        // only the first iteration has lanes to seed: afterwards the shading kernels accumulate a finished path
+        // and start the lane's next camera sample themselves (end_of_path)
+        if (r.first) launch_generate(s, r.light, ctx->dscene, st, r.q, kp, r.parity), launches++;
         if (timing) {
           while (ctx->ev_pool.size() < ev_used + 2) {
             cudaEvent_t e;
@@ -815,9 +825,9 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
         }
         launch_shade(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
         if (path_like) launch_lightpdf(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
-        launch_accumulate(s, r.light, ctx->dscene, st, r.q, kp, r.parity);
+        r.first  = false;
         r.parity = 1 - r.parity;
-        launches += path_like ? 6 : 5;
+        launches += path_like ? 4 : 3;
       }
       iterations++;
     }
@@ -883,6 +893,115 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   return YGL_OK;
 }
 
+
+// The persistent driver: ONE kernel launch renders `nsamples` more samples on every lane (k_persistent). The host
+// only watches for progress: if the device counters stand still for YGL_WATCHDOG_S seconds (default 20) it raises
+// the abort flag, every warp leaves, and the call fails - a scheduling bug must never hang the GPU.
+static int run_persistent(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
+  PathState& st = state->st;
+  if (st.num_lanes == 0 || nsamples <= 0) return YGL_OK;
+  KParams kp;
+  kp.camera = params.camera, kp.sampler = params.sampler, kp.falsecolor = params.falsecolor;
+  kp.bounces = params.bounces, kp.clamp = params.clamp;
+  kp.nocaustics = params.nocaustics, kp.envhidden = params.envhidden, kp.tentfilter = params.tentfilter;
+  kp.sample_end = state->samples + nsamples;
+
+  cudaStream_t s   = ctx->stream;
+  // ring capacity: every lane can sit in a ring, and every consumer thread of the grid can hold a ticket that runs
+  // ahead of the producers; two live tickets must never share a slot
+  const unsigned max_threads = (unsigned)ctx->num_sms * 2048u;
+  unsigned       cap         = 1024;
+  while (cap < (unsigned)st.num_lanes + max_threads) cap <<= 1;
+  constexpr int kCtrWords = 256;  // every cursor on its own 128-byte line
+  if (cap > ctx->ring_cap) {
+    if (ctx->ring_mem) cudaFree(ctx->ring_mem), ctx->ring_mem = nullptr, ctx->ring_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&ctx->ring_mem, ((size_t)3 * cap + kCtrWords) * sizeof(int)));
+    ctx->ring_cap = cap;
+  }
+  cap            = ctx->ring_cap;
+  int*      base = ctx->ring_mem;
+  unsigned* ctr  = (unsigned*)(base + (size_t)3 * cap);
+  CUDA_TRY(cudaMemsetAsync(base, 0xff, (size_t)3 * cap * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(ctr, 0, kCtrWords * sizeof(int), s));
+  Counters* counters = ctx->pipes[0].counters;
+  CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(Counters), s));
+  PQueues q;
+  // head and tail of a ring share one 8-byte word (polled with a single load); rings on separate 128-byte lines
+  q.ext         = Ring{base, ctr + 0, ctr + 1, cap - 1};
+  q.shade       = Ring{base + cap, ctr + 64, ctr + 65, cap - 1};
+  q.lpdf        = Ring{base + (size_t)2 * cap, ctr + 128, ctr + 129, cap - 1};
+  q.seed_cursor = ctr + 192;
+  q.abort       = (int*)(ctr + 224);
+  q.counters    = counters;
+
+  const bool timing = ctx->time_kernels;
+  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[0], s));
+  launch_persistent(s, ctx->num_sms, ctx->dscene, st, q, kp, 0, st.num_lanes, state->samples);
+  CUDA_TRY(cudaGetLastError());
+  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[1], s));
+  cudaEvent_t fin = ctx->pipes[0].ev[0];
+  CUDA_TRY(cudaEventRecord(fin, s));
+
+  // ---- wait + watchdog ----
+  static const double watchdog_s = getenv("YGL_WATCHDOG_S") ? atof(getenv("YGL_WATCHDOG_S")) : 20.0;
+  cudaStream_t side = ctx->pipes[1].stream;
+  int*         h    = ctx->pipes[1].h_done;  // pinned, 2 ints
+  long long    last_progress = -1;
+  auto         t_last = std::chrono::steady_clock::now(), t_check = t_last;
+  bool         aborted = false;
+  for (int spin = 0;; spin++) {
+    cudaError_t e = cudaEventQuery(fin);
+    if (e == cudaSuccess) break;
+    if (e != cudaErrorNotReady) return fail(YGL_ERR_CUDA, cudaGetErrorString(e));
+    if (spin > 200) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    auto now = std::chrono::steady_clock::now();
+    if (std::chrono::duration<double>(now - t_check).count() < 0.25) continue;
+    t_check = now;
+    unsigned long long cam = 0;
+    CUDA_TRY(cudaMemcpyAsync(h, &counters->done_lanes, sizeof(int), cudaMemcpyDeviceToHost, side));
+    CUDA_TRY(cudaMemcpyAsync(h + 1, &counters->camera_samples, sizeof(int), cudaMemcpyDeviceToHost, side));
+    CUDA_TRY(cudaStreamSynchronize(side));
+    cam = (unsigned)h[1];
+    long long progress = (long long)h[0] * 1000003ll + (long long)cam;
+    if (progress != last_progress) {
+      last_progress = progress;
+      t_last        = now;
+    } else if (!aborted && std::chrono::duration<double>(now - t_last).count() > watchdog_s) {
+      h[0] = 1;
+      CUDA_TRY(cudaMemcpyAsync(q.abort, h, sizeof(int), cudaMemcpyHostToDevice, side));
+      CUDA_TRY(cudaStreamSynchronize(side));
+      aborted = true;
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  int      abort_flag = 0;
+  Counters c;
+  CUDA_TRY(cudaMemcpy(&abort_flag, q.abort, sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&c, counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+  if (abort_flag || c.done_lanes != st.num_lanes)
+    return fail(YGL_ERR_RUNTIME, "persistent kernel stopped by the watchdog (no progress)");
+  ctx->stats[0] += c.camera_samples;
+  ctx->stats[1] += c.scene_rays;
+  ctx->stats[2] += c.instance_rays;
+  ctx->stats[3] += 1;
+  ctx->stats[4] += 1;
+  if (timing) {
+    float loop_ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&loop_ms, ctx->ev_loop[0], ctx->ev_loop[1]));
+    ctx->timings[1] += loop_ms;
+    ctx->timings[3] = 0;  // persistent mode: no separate extend launches to time
+  }
+  state->samples += nsamples;
+  return YGL_OK;
+}
+
+// Traversal counting needs the wavefront's counting extend kernel.
+static int run_render(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
+  if (ctx->mode == YGL_MODE_PERSISTENT && !ctx->count_traversal) return run_persistent(ctx, state, params, nsamples);
+  return run_wavefront(ctx, state, params, nsamples);
+}
+
 static int check_sampler(const ygl_trace_params& p) {
   switch (p.sampler) {
     case YGL_SAMPLER_PATH:
@@ -910,7 +1029,7 @@ int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene
   if (int rc = bind_scene(ctx, scene, bvh, lights)) return rc;
   memset(ctx->stats, 0, sizeof(ctx->stats));
   memset(ctx->timings, 0, sizeof(ctx->timings));
-  return run_wavefront(ctx, state, *params, params->batch);
+  return run_render(ctx, state, *params, params->batch);
 }
 
 int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]) {
@@ -918,6 +1037,13 @@ int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]) {
   memcpy(counters, ctx->stats, sizeof(ctx->stats));
   return YGL_OK;
 }
+int ygl_context_set_mode(ygl_context* ctx, int mode) {
+  if (!ctx) return fail(YGL_ERR_INVALID, "null context");
+  if (mode != YGL_MODE_WAVEFRONT && mode != YGL_MODE_PERSISTENT) return fail(YGL_ERR_INVALID, "unknown mode");
+  ctx->mode = mode;
+  return YGL_OK;
+}
+
 int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_traversal) {
   if (!ctx) return fail(YGL_ERR_INVALID, "null context");
   ctx->time_kernels    = time_kernels != 0;
@@ -959,7 +1085,7 @@ int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trac
     int batch = std::max(1, params->batch);
     int total = ((params->samples + batch - 1) / batch) * batch;
     if (params->samples <= 0) total = 0;
-    if ((rc = run_wavefront(ctx, state, *params, total))) break;
+    if ((rc = run_render(ctx, state, *params, total))) break;
     rc = ygl_state_download(state, image, nullptr, nullptr, nullptr, nullptr);
   } while (false);
   std::string keep = g_error;

@@ -83,36 +83,41 @@ __global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begi
 
 // ---- ray generation: trace_sample head, yocto_trace.cpp:1461-1468. g++ evaluates the two rand2f
 // arguments right-to-left, so the lens sample `luv` is drawn BEFORE the pixel sample `puv`. ----
+YGL_D bool accumulate_lane(const DScene& scene, const PathState& st, const KParams& p, int lane);
+
+YGL_D void generate_lane(const DScene& scene, const PathState& st, const KParams& p, int lane) {
+  const DCamera& camera = scene.cameras[p.camera];
+  int px = lane % st.width, py = st.row_begin + (lane / st.width) * st.row_step;
+  rng_t rng = load_rng(st, lane);
+  f2 luv    = rand2f(rng);
+  f2 puv    = rand2f(rng);
+  f3 o, d;
+  sample_camera(camera, px, py, st.width, st.height, puv, luv, p.tentfilter != 0, o, d);
+  store_rng(st, lane, rng);
+  st.ray_o[lane]    = pack(o, 0);
+  st.ray_d[lane]    = pack(d, 0);
+  st.radiance[lane] = pack(f3{0, 0, 0}, 0);
+  st.weight[lane]   = pack(f3{1, 1, 1}, 0.0f);
+  st.albedo0[lane]  = pack(f3{0, 0, 0}, 0.0f);
+  st.normal0[lane]  = pack(-d, 0.0f);
+  if (p.sampler == kSamplerPathDirect || p.sampler == kSamplerPathMis) {
+    st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseMain);
+    st.next_uvd[lane] = make_float4(0, 0, 0, __int_as_float(0));  // next_intersection = {}
+    st.next_ids[lane] = make_int2(-1, -1);
+  }
+}
 __global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_gen[parity];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   const int wl  = threadIdx.x & 31;
-  const DCamera& camera = scene.cameras[p.camera];
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
     int  i     = i0 + wl;
     bool valid = i < n;
     int  lane  = 0;
     if (valid) {
-      lane      = q.gen[parity][i];
-      int px = lane % st.width, py = st.row_begin + (lane / st.width) * st.row_step;
-      rng_t rng = load_rng(st, lane);
-      f2 luv    = rand2f(rng);
-      f2 puv    = rand2f(rng);
-      f3 o, d;
-      sample_camera(camera, px, py, st.width, st.height, puv, luv, p.tentfilter != 0, o, d);
-      store_rng(st, lane, rng);
-      st.ray_o[lane]    = pack(o, 0);
-      st.ray_d[lane]    = pack(d, 0);
-      st.radiance[lane] = pack(f3{0, 0, 0}, 0);
-      st.weight[lane]   = pack(f3{1, 1, 1}, 0.0f);
-      st.albedo0[lane]  = pack(f3{0, 0, 0}, 0.0f);
-      st.normal0[lane]  = pack(-d, 0.0f);
-      if (p.sampler == kSamplerPathDirect || p.sampler == kSamplerPathMis) {
-        st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseMain);
-        st.next_uvd[lane] = make_float4(0, 0, 0, __int_as_float(0));  // next_intersection = {}
-        st.next_ids[lane] = make_int2(-1, -1);
-      }
+      lane = q.gen[parity][i];
+      generate_lane(scene, st, p, lane);
     }
     queue_push(q.ext[parity], &c->n_ext[parity], valid, lane);
   }
@@ -150,7 +155,9 @@ struct ExtendSource {
     o = unpack3(a), d = unpack3(b);
     return true;
   }
-  YGL_D void commit(const hit_t& h) {
+  static constexpr bool kPolling = false;  // the queue is complete when the kernel starts
+  YGL_D void commit_finished(bool flag, const hit_t& h) {
+    if (!flag) return;
     (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
     (shadow ? st.aux_ids : st.hit_ids)[lane] = make_int2(h.instance, h.element);
     finished++;
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene,
   const int     n = c->n_ext[parity];
   ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps, suspend_below, 0, false};
   trav_counters tc = {};
-  trace_stream<COUNT>(scene, src, tc);
+  trace_stream<COUNT, kStreamThreads>(scene, src, tc);
   {
     unsigned v = src.finished;
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFullWarp, v, off);
@@ -811,6 +818,34 @@ YGL_D int shade_multi(const DScene& scene, const PathState& st, const KParams& p
   return dest | entry_flags;
 }
 
+
+// End of a path inside a shading-side kernel: accumulate the sample and, if the lane has more samples to do, start
+// its next camera ray at once (the lane goes straight back to the extend queue - no accumulate / generate launches).
+// WARP-UNIFORM. `counts`: x = samples started, y = lanes finished (per thread).
+YGL_D void end_of_path(const DScene& scene, const PathState& st, const KParams& p, int lane, int& dest, int& entry,
+    int2& counts) {
+  if (dest == kDestAcc) {
+    if (accumulate_lane(scene, st, p, lane)) {
+      generate_lane(scene, st, p, lane);
+      dest = kDestExt, entry = lane;
+      counts.x++;
+    } else {
+      dest = kDestNone;
+      counts.y++;
+    }
+  }
+}
+YGL_D void flush_counts(Counters* c, int2 counts) {
+  for (int off = 16; off > 0; off >>= 1) {
+    counts.x += __shfl_down_sync(0xffffffffu, counts.x, off);
+    counts.y += __shfl_down_sync(0xffffffffu, counts.y, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (counts.x) atomicAdd(&c->camera_samples, (unsigned long long)counts.x);
+    if (counts.y) atomicAdd(&c->done_lanes, counts.y);
+  }
+}
+
 #ifndef YGL_SHADE_THREADS
 #define YGL_SHADE_THREADS 256
 #endif
@@ -824,6 +859,7 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   const int wl  = threadIdx.x & 31;
   unsigned inst_rays = 0;
+  int2     counts    = make_int2(0, 0);
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
     int i    = i0 + wl;
     int lane = 0, dest = kDestNone;
@@ -832,7 +868,7 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
       const int in_entry = q.ext[parity][i];
       lane               = in_entry & kEntryLane;
       const bool shadow  = (in_entry & kEntryShadow) != 0;
-      if (!(in_entry & kEntryPass) && __float_as_int((shadow ? st.aux_uvd : st.hit_uvd)[lane].w) == 2) {
+      if (!(in_entry & kEntryPass) && __float_as_int(float4((shadow ? st.aux_uvd : st.hit_uvd)[lane]).w) == 2) {
         // the extend kernel suspended this ray: it stays in the extend queue, flagged for resumption
         dest  = kDestExt;
         entry = lane | kEntryResume | (in_entry & kEntryShadow);
@@ -844,10 +880,11 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
         entry = lane | (r & (kEntryShadow | kEntryPass));
       }
     }
+    end_of_path(scene, st, p, lane, dest, entry, counts);
     queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
     queue_push(q.lpdf, &c->n_lpdf, dest == kDestLpdf, lane);
-    queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
   }
+  flush_counts(c, counts);
   if (tid == 0) atomicAdd(&c->shade_calls, (unsigned long long)n);
 }
 
@@ -856,67 +893,111 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
 #ifndef YGL_LPDF_MINBLOCKS
 #define YGL_LPDF_MINBLOCKS 3
 #endif
+// One warp-wide step (WARP-COOPERATIVE: every lane of the warp must call it; `valid` marks lanes that hold a queued
+// lane id). Outputs the lane's destination queue and its extend-queue entry.
+YGL_D void lightpdf_lane(const DScene& scene, const PathState& st, const KParams& p, bool valid, int lane,
+    unsigned& rays, int& dest, int& entry) {
+  float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 1, 0);
+  const bool multi = p.sampler == kSamplerPathDirect || p.sampler == kSamplerPathMis;
+  int        phase = kPhaseMain;
+  dest = kDestNone, entry = 0;
+  if (valid) {
+    if (multi) phase = __float_as_int(float4(st.aux_bsdf[lane]).w);
+    const bool direct = phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf;  // pdf of a direct sample at aux_o
+    ro = direct ? st.aux_o[lane] : st.ray_o[lane], rd = direct ? st.aux_dir[lane] : st.ray_d[lane];
+  }
+  float lpdf = sample_lights_pdf(scene, valid, unpack3(ro), unpack3(rd), rays);
+  if (valid && (phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf)) {
+    // direct lighting: decide whether the shadow ray is needed (yocto_trace.cpp:662-665 / :860-869)
+    float4 ab      = st.aux_bsdf[lane];
+    f3     bsdfcos = unpack3(ab);
+    bool   trace;
+    if (p.sampler == kSamplerPathDirect) {
+      st.aux_dir[lane] = pack(unpack3(rd), lpdf);
+      trace            = !is_zero(bsdfcos) && lpdf > 0;
+    } else {
+      float bsdf_pdf   = ro.w;
+      float mis_weight = phase == kPhaseDirectPdf ? mis_heuristic(lpdf, bsdf_pdf) / lpdf
+                                                  : mis_heuristic(bsdf_pdf, lpdf) / bsdf_pdf;
+      st.aux_dir[lane] = pack(unpack3(rd), mis_weight);
+      trace            = !is_zero(bsdfcos) && mis_weight != 0;
+    }
+    int next_phase    = phase == kPhaseDirectPdf ? (trace ? kPhaseShadowHit : kPhaseShadowSkip)
+                                                 : (trace ? kPhaseBsdfHit : kPhaseBsdfSkip);
+    st.aux_bsdf[lane] = pack(bsdfcos, next_phase);
+    dest              = kDestExt;
+    entry             = lane | (trace ? kEntryShadow : kEntryPass);
+  } else if (valid) {
+    float4 w4 = st.weight[lane], pd = st.pend[lane];
+    f3     position = unpack3(ro), weight = unpack3(w4);
+    int    bounce   = __float_as_int(ro.w);
+    weight          = weight * (unpack3(pd) / (0.5f * pd.w + 0.5f * lpdf));
+    rng_t rng      = load_rng(st, lane);
+    dest           = finish_bounce(weight, bounce, rng, p);
+    store_rng(st, lane, rng);
+    st.ray_o[lane]  = pack(position, bounce);
+    st.weight[lane] = pack(weight, w4.w);
+    if (multi) st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseMain);
+    entry = lane;
+  }
+}
 __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_lpdf;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   const int wl  = threadIdx.x & 31;
-  unsigned rays = 0;
+  unsigned rays   = 0;
+  int2     counts = make_int2(0, 0);
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
-    int    i    = i0 + wl;
-    int    lane = 0, dest = kDestNone;
-    float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 1, 0);
-    const bool multi = p.sampler == kSamplerPathDirect || p.sampler == kSamplerPathMis;
-    int        phase = kPhaseMain, entry = 0;
-    if (i < n) {
-      lane = q.lpdf[i];
-      if (multi) phase = __float_as_int(st.aux_bsdf[lane].w);
-      const bool direct = phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf;  // pdf of a direct sample at aux_o
-      ro = direct ? st.aux_o[lane] : st.ray_o[lane], rd = direct ? st.aux_dir[lane] : st.ray_d[lane];
-    }
-    float lpdf = sample_lights_pdf(scene, i < n, unpack3(ro), unpack3(rd), rays);
-    if (i < n && (phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf)) {
-      // direct lighting: decide whether the shadow ray is needed (yocto_trace.cpp:662-665 / :860-869)
-      float4 ab      = st.aux_bsdf[lane];
-      f3     bsdfcos = unpack3(ab);
-      bool   trace;
-      if (p.sampler == kSamplerPathDirect) {
-        st.aux_dir[lane] = pack(unpack3(rd), lpdf);
-        trace            = !is_zero(bsdfcos) && lpdf > 0;
-      } else {
-        float bsdf_pdf   = ro.w;
-        float mis_weight = phase == kPhaseDirectPdf ? mis_heuristic(lpdf, bsdf_pdf) / lpdf
-                                                    : mis_heuristic(bsdf_pdf, lpdf) / bsdf_pdf;
-        st.aux_dir[lane] = pack(unpack3(rd), mis_weight);
-        trace            = !is_zero(bsdfcos) && mis_weight != 0;
-      }
-      int next_phase    = phase == kPhaseDirectPdf ? (trace ? kPhaseShadowHit : kPhaseShadowSkip)
-                                                   : (trace ? kPhaseBsdfHit : kPhaseBsdfSkip);
-      st.aux_bsdf[lane] = pack(bsdfcos, next_phase);
-      dest              = kDestExt;
-      entry             = lane | (trace ? kEntryShadow : kEntryPass);
-    } else if (i < n) {
-      float4 w4 = st.weight[lane], pd = st.pend[lane];
-      f3     position = unpack3(ro), weight = unpack3(w4);
-      int    bounce   = __float_as_int(ro.w);
-      weight          = weight * (unpack3(pd) / (0.5f * pd.w + 0.5f * lpdf));
-      rng_t rng      = load_rng(st, lane);
-      dest           = finish_bounce(weight, bounce, rng, p);
-      store_rng(st, lane, rng);
-      st.ray_o[lane]  = pack(position, bounce);
-      st.weight[lane] = pack(weight, w4.w);
-      if (multi) st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseMain);
-      entry = lane;
-    }
+    int i    = i0 + wl;
+    int lane = i < n ? q.lpdf[i] : 0, dest, entry;
+    lightpdf_lane(scene, st, p, i < n, lane, rays, dest, entry);
+    end_of_path(scene, st, p, lane, dest, entry, counts);
     queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
-    queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
   }
+  flush_counts(c, counts);
   // one atomic per warp for the instance-ray count
   for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
   if (wl == 0 && rays) atomicAdd(&c->instance_rays, (unsigned long long)rays);
 }
 
-// ---- accumulate: trace_sample tail, yocto_trace.cpp:1469-1491 ----
+// ---- accumulate: trace_sample tail, yocto_trace.cpp:1469-1491. Returns whether the lane has more samples to do. ----
+YGL_D bool accumulate_lane(const DScene& scene, const PathState& st, const KParams& p, int lane) {
+  float4 rad4   = st.radiance[lane];
+  f3     radiance = unpack3(rad4);
+  bool   hit    = (__float_as_int(rad4.w) & kFlagHit) != 0;
+  int    sample = st.sample[lane];
+  if (!vfinite(radiance)) radiance = {0, 0, 0};
+  if (max3(radiance) > p.clamp) radiance = radiance * (p.clamp / max3(radiance));
+  float  w   = 1.0f / (sample + 1);
+  float4 im4 = st.image[lane];
+  f4     image  = {im4.x, im4.y, im4.z, im4.w};
+  // plain loads (not __ldg): in persistent mode the lane's accumulators may have been written on another SM
+  f3     albedo = {st.albedo[3 * lane + 0], st.albedo[3 * lane + 1], st.albedo[3 * lane + 2]};
+  f3     normal = {st.normal[3 * lane + 0], st.normal[3 * lane + 1], st.normal[3 * lane + 2]};
+  f3     n0     = unpack3(st.normal0[lane]);
+  if (hit) {
+    image  = lerp4(image, f4{radiance.x, radiance.y, radiance.z, 1}, w);
+    albedo = lerp3(albedo, unpack3(st.albedo0[lane]), w);
+    normal = lerp3(normal, n0, w);
+    st.hits[lane] += 1;
+  } else if (!p.envhidden && scene.num_environments > 0) {
+    image  = lerp4(image, f4{radiance.x, radiance.y, radiance.z, 1}, w);
+    albedo = lerp3(albedo, f3{1, 1, 1}, w);
+    normal = lerp3(normal, n0, w);
+    st.hits[lane] += 1;
+  } else {
+    image  = lerp4(image, f4{0, 0, 0, 0}, w);
+    albedo = lerp3(albedo, f3{0, 0, 0}, w);
+    normal = lerp3(normal, n0, w);
+  }
+  st.image[lane]          = make_float4(image.x, image.y, image.z, image.w);
+  st.albedo[3 * lane + 0] = albedo.x, st.albedo[3 * lane + 1] = albedo.y, st.albedo[3 * lane + 2] = albedo.z;
+  st.normal[3 * lane + 0] = normal.x, st.normal[3 * lane + 1] = normal.y, st.normal[3 * lane + 2] = normal.z;
+  sample += 1;
+  st.sample[lane] = sample;
+  return sample < p.sample_end;
+}
 __global__ void __launch_bounds__(256) k_accumulate(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_acc;
@@ -928,45 +1009,264 @@ __global__ void __launch_bounds__(256) k_accumulate(DScene scene, PathState st, 
     int  lane = 0;
     bool more = false;
     if (i < n) {
-      lane          = q.acc[i];
-      float4 rad4   = st.radiance[lane];
-      f3     radiance = unpack3(rad4);
-      bool   hit    = (__float_as_int(rad4.w) & kFlagHit) != 0;
-      int    sample = st.sample[lane];
-      if (!vfinite(radiance)) radiance = {0, 0, 0};
-      if (max3(radiance) > p.clamp) radiance = radiance * (p.clamp / max3(radiance));
-      float  w   = 1.0f / (sample + 1);
-      float4 im4 = st.image[lane];
-      f4     image  = {im4.x, im4.y, im4.z, im4.w};
-      f3     albedo = ld3(st.albedo, lane), normal = ld3(st.normal, lane);
-      f3     n0     = unpack3(st.normal0[lane]);
-      if (hit) {
-        image  = lerp4(image, f4{radiance.x, radiance.y, radiance.z, 1}, w);
-        albedo = lerp3(albedo, unpack3(st.albedo0[lane]), w);
-        normal = lerp3(normal, n0, w);
-        st.hits[lane] += 1;
-      } else if (!p.envhidden && scene.num_environments > 0) {
-        image  = lerp4(image, f4{radiance.x, radiance.y, radiance.z, 1}, w);
-        albedo = lerp3(albedo, f3{1, 1, 1}, w);
-        normal = lerp3(normal, n0, w);
-        st.hits[lane] += 1;
-      } else {
-        image  = lerp4(image, f4{0, 0, 0, 0}, w);
-        albedo = lerp3(albedo, f3{0, 0, 0}, w);
-        normal = lerp3(normal, n0, w);
-      }
-      st.image[lane]          = make_float4(image.x, image.y, image.z, image.w);
-      st.albedo[3 * lane + 0] = albedo.x, st.albedo[3 * lane + 1] = albedo.y, st.albedo[3 * lane + 2] = albedo.z;
-      st.normal[3 * lane + 0] = normal.x, st.normal[3 * lane + 1] = normal.y, st.normal[3 * lane + 2] = normal.z;
-      sample += 1;
-      st.sample[lane] = sample;
-      more            = sample < p.sample_end;
+      lane = q.acc[i];
+      more = accumulate_lane(scene, st, p, lane);
       if (!more) finished++;
     }
     queue_push(q.gen[1 - parity], &c->n_gen[1 - parity], more, lane);
   }
   for (int off = 16; off > 0; off >>= 1) finished += __shfl_down_sync(0xffffffffu, finished, off);
   if (wl == 0 && finished) atomicAdd(&c->done_lanes, finished);
+}
+
+
+// ==========================================================================================
+// Persistent mode. ONE kernel renders a whole batch: every block hosts traversal warps (trace_stream fed by the
+// extend ring), shading warps (shade -> accumulate -> next camera sample) and light-pdf warps, linked by ring
+// queues in global memory, so lanes flow from stage to stage without kernel boundaries: no drain tail per
+// wavefront iteration, no launch gaps, no host polling.
+//
+// Ring protocol (ticket queue, no CAS - a CAS-claimed head lets one of thousands of contending warps win per L2
+// round trip): a producer reserves an index with one atomicAdd on `tail` per warp and publishes the entry into
+// slot[index]; a consumer lane takes a ticket with one atomicAdd on `head` per warp and polls slot[ticket] - its
+// own address, so waiting never hammers a shared cache line. A ticket may run ahead of the producers; the lane
+// simply waits for its slot. Every ring has dedicated consumers in every block, and producers never wait
+// (except for the wrap-around guard), so there is no cyclic wait; warps leave when all lanes are done.
+//
+// Memory model: a lane's state is written by one warp and read by another, possibly on another SM. All state
+// loads go through SArr (ld.global.cg, served by L2 where every store lands); read-only scene data keeps its
+// L1 residency. A producer publishes with st.release.gpu (its state writes are performed first); the consumer's
+// state loads depend on the slot value (address dependency), so no acquire fence - which would invalidate the
+// SM's whole L1, BVH nodes included (CCTL.IVALL) - is needed.
+// ==========================================================================================
+YGL_D int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+YGL_D void st_relaxed(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+YGL_D void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// WARP-UNIFORM: lanes with `pred` reserve one slot each (null otherwise). The caller publishes with ring_publish.
+YGL_D int* ring_reserve(const Ring& r, bool pred) {
+  const unsigned m = __ballot_sync(kFullWarp, pred);
+  if (!m) return nullptr;
+  const int wl = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned  base = 0;
+  if (wl == leader) base = atomicAdd(r.tail, (unsigned)__popc(m));
+  base = __shfl_sync(kFullWarp, base, leader);
+  return pred ? r.slots + ((base + __popc(m & ((1u << wl) - 1u))) & r.mask) : nullptr;
+}
+YGL_D void ring_publish(int* slot, int value, int* abort) {
+  // wrap-around guard: the slot's previous entry (one ring capacity ago) must have been taken. Practically never
+  // spins: the capacity exceeds the number of lanes, each of which sits in at most one ring.
+  int spins = 0;
+  while (ld_relaxed(slot) != -1)
+    if (++spins > (1 << 22)) {
+      st_relaxed(abort, 1);
+      break;
+    }
+  st_release(slot, value);
+}
+YGL_D void ring_push(const Ring& r, bool pred, int value, int* abort) {
+  int* slot = ring_reserve(r, pred);
+  if (slot) ring_publish(slot, value, abort);
+}
+// WARP-UNIFORM, NON-BLOCKING: lanes with `want` that hold no ticket take one; every ticket holder then looks
+// at its slot once. Returns true for lanes that received an entry (their ticket is used up).
+YGL_D bool ring_take(const Ring& r, bool want, unsigned& ticket, bool& held, int& entry) {
+  const unsigned m = __ballot_sync(kFullWarp, want && !held);
+  if (m) {
+    const int wl = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned  base = 0;
+    if (wl == leader) base = atomicAdd(r.head, (unsigned)__popc(m));
+    base = __shfl_sync(kFullWarp, base, leader);
+    if (want && !held) ticket = base + __popc(m & ((1u << wl) - 1u)), held = true;
+  }
+  if (!(want && held)) return false;
+  int*      slot = r.slots + (ticket & r.mask);
+  const int v    = ld_relaxed(slot);
+  if (v == -1) return false;
+  st_relaxed(slot, -1);
+  held  = false;
+  entry = v;
+  return true;
+}
+
+struct RingSource {
+  PQueues   q;
+  PathState st;
+  int       lane, total;
+  int       refill_thr, node_reps, suspend_below;
+  unsigned  finished, taken, ticket;
+  bool      shadow, held;
+  static constexpr bool kPolling = true;  // the ring is fed by other warps while this one runs
+  YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more, bool& resume) {
+    resume     = false;
+    int  entry = 0;
+    const bool got = ring_take(q.ext, idle, ticket, held, entry);
+    if (!__any_sync(kFullWarp, got)) {
+      // nothing arrived: the job may be over
+      if (ld_relaxed(&q.counters->done_lanes) >= total || ld_relaxed(q.abort)) more = false;
+    }
+    if (!got) return false;
+    lane     = entry & kEntryLane;
+    shadow   = (entry & kEntryShadow) != 0;
+    float4 a = shadow ? st.aux_o[lane] : st.ray_o[lane], b = shadow ? st.aux_dir[lane] : st.ray_d[lane];
+    o = unpack3(a), d = unpack3(b);
+    taken++;
+    return true;
+  }
+  YGL_D void commit_finished(bool flag, const hit_t& h) {
+    if (flag) {
+      (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
+      (shadow ? st.aux_ids : st.hit_ids)[lane] = make_int2(h.instance, h.element);
+      finished++;
+    }
+    ring_push(q.shade, flag, lane, q.abort);
+  }
+  YGL_D int* saved() { return st.susp; }  // never used: rays are not suspended in persistent mode
+  YGL_D void commit_suspended() {}
+};
+
+// Send a shaded lane on (WARP-UNIFORM). A finished path is accumulated here and the lane's next camera sample
+// starts at once; a lane that needs no ray this round (kEntryPass) goes straight back to the shade ring.
+template <bool USES_LPDF>
+YGL_D void route_lane(const DScene& scene, const PathState& st, const PQueues& q, const KParams& p, int lane, int dest,
+    int out) {
+  bool to_shade = dest == kDestExt && (out & kEntryPass) != 0;
+  bool to_ext   = dest == kDestExt && !to_shade;
+  bool started = false, ended = false;
+  if (dest == kDestAcc) {
+    if (accumulate_lane(scene, st, p, lane)) {
+      generate_lane(scene, st, p, lane);
+      to_ext = started = true;
+      out    = lane;
+    } else {
+      ended = true;
+    }
+  }
+  const unsigned ms = __ballot_sync(kFullWarp, started), me = __ballot_sync(kFullWarp, ended);
+  if ((threadIdx.x & 31) == 0) {
+    if (ms) atomicAdd(&q.counters->camera_samples, (unsigned long long)__popc(ms));
+    if (me) atomicAdd(&q.counters->done_lanes, __popc(me));
+  }
+  // one release store per lane, whatever its destination ring (a single MEMBAR for the warp)
+  int* slot = ring_reserve(q.ext, to_ext);
+  int* s1   = ring_reserve(q.shade, to_shade);
+  if (s1) slot = s1, out = lane;
+  if (USES_LPDF) {
+    int* s2 = ring_reserve(q.lpdf, dest == kDestLpdf);
+    if (s2) slot = s2, out = lane;
+  }
+  if (slot) ring_publish(slot, out, q.abort);
+}
+
+enum : int { kRoleExt = 0, kRoleShade = 1, kRoleLpdf = 2 };
+#ifndef YGL_PERSIST_MINBLOCKS
+#define YGL_PERSIST_MINBLOCKS 2
+#endif
+// 12 warps per block, 2 blocks per SM. Roles are assigned per SM where possible (`sm_roles`): with traversal,
+// shading and light-pdf warps interleaved on one SM the combined code footprint thrashes the instruction caches
+// (ncu: 70 % of the stall samples were "no instruction"); SM-specialised blocks keep each SM's I-cache on one
+// stage's code, and lane state travels through L2 anyway.
+constexpr int kPersistThreads = 384;
+
+template <int SAMPLER>
+__global__ void __launch_bounds__(kPersistThreads, YGL_PERSIST_MINBLOCKS) k_persistent(DScene scene, PathState st, PQueues q,
+    KParams p, int lane_lo, int lane_hi, int sample_begin, unsigned roles, int num_sms, int refill_thr, int node_reps) {
+  constexpr bool multi     = SAMPLER == kSamplerPathDirect || SAMPLER == kSamplerPathMis;
+  constexpr bool uses_lpdf = SAMPLER == kSamplerPath || SAMPLER == kSamplerPathTest || multi;
+  Counters* c     = q.counters;
+  const int wl    = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int total = lane_hi - lane_lo;
+  unsigned  inst_rays = 0, n_shade = 0, n_ext = 0;
+  // ---- first camera sample of every lane (dynamic chunks: only resident warps take part) ----
+  while (true) {
+    unsigned base = 0;
+    if (wl == 0) base = atomicAdd(q.seed_cursor, 32u);
+    base = __shfl_sync(kFullWarp, base, 0);
+    if (base >= (unsigned)total) break;
+    const bool valid = base + wl < (unsigned)total;
+    const int  lane  = lane_lo + (int)base + wl;
+    if (valid) {
+      st.sample[lane] = sample_begin;
+      generate_lane(scene, st, p, lane);
+    }
+    const unsigned mv = __ballot_sync(kFullWarp, valid);
+    if (wl == 0) atomicAdd(&c->camera_samples, (unsigned long long)__popc(mv));
+    ring_push(q.ext, valid, lane, q.abort);
+  }
+  // roles: bits 0..23 = per-warp pattern of a mixed block (2 bits per warp); bits 24..27 = traversal SMs per 10
+  // (0 = every block is mixed); bits 28..31 = light-pdf warps of a shading block
+  int role;
+  const int ext_tenths = (roles >> 24) & 15, lpdf_warps = (roles >> 28) & 15;
+  if (ext_tenths == 0 || gridDim.x < 20) {
+    role = (roles >> (2 * warp)) & 3;
+  } else {
+    const int  slot   = (int)(blockIdx.x % (unsigned)num_sms);  // blocks i and i + num_sms share an SM (round-robin placement)
+    const bool ext_sm = slot % 10 < ext_tenths;
+    role              = ext_sm ? kRoleExt : (warp < lpdf_warps ? kRoleLpdf : kRoleShade);
+  }
+  if (role == kRoleLpdf && !uses_lpdf) role = kRoleShade;
+  unsigned backoff = 64;
+  if (role == kRoleExt) {
+    // ---- traversal warps ----
+    RingSource    src{q, st, 0, total, refill_thr, node_reps, 0, 0, 0, 0, false, false};
+    trav_counters tc = {};
+    while (true) {
+      const unsigned before = src.taken;
+      trace_stream<false, kPersistThreads>(scene, src, tc);
+      if (__any_sync(kFullWarp, src.taken != before)) {
+        backoff = 64;
+        continue;
+      }
+      if (ld_relaxed(&c->done_lanes) >= total || ld_relaxed(q.abort)) break;
+      __nanosleep(backoff);
+      backoff = min(backoff * 2, 4096u);
+    }
+    n_ext = src.finished;
+  } else {
+    // ---- shading / light-pdf warps: collect a full warp of lanes (or what arrived after a short wait) ----
+    const Ring& ring = role == kRoleLpdf ? q.lpdf : q.shade;
+    unsigned    ticket = 0;
+    bool        held = false, has = false;
+    int         entry = 0, waited = 0;
+    while (true) {
+      if (ring_take(ring, !has, ticket, held, entry)) has = true;
+      const int n_has = __popc(__ballot_sync(kFullWarp, has));
+      if (n_has == 32 || (n_has > 0 && waited >= 3)) {
+        int lane = has ? entry : 0, dest = kDestNone, out = 0;
+        if (role == kRoleLpdf) {
+          lightpdf_lane(scene, st, p, has, lane, inst_rays, dest, out);
+        } else if (has) {
+          int r = multi ? shade_multi<SAMPLER>(scene, st, p, lane) : shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
+          dest  = r & 3;
+          out   = lane | (r & (kEntryShadow | kEntryPass));
+          n_shade++;
+        }
+        route_lane<uses_lpdf>(scene, st, q, p, lane, dest, out);
+        has = false, waited = 0, backoff = 64;
+        continue;
+      }
+      if (n_has == 0 && (ld_relaxed(&c->done_lanes) >= total || ld_relaxed(q.abort))) break;
+      __nanosleep(backoff);
+      backoff = min(backoff * 2, 2048u);
+      waited++;
+    }
+  }
+  // ---- tallies ----
+  unsigned v0 = n_ext, v1 = inst_rays, v2 = n_shade;
+  for (int off = 16; off > 0; off >>= 1) {
+    v0 += __shfl_down_sync(kFullWarp, v0, off);
+    v1 += __shfl_down_sync(kFullWarp, v1, off);
+    v2 += __shfl_down_sync(kFullWarp, v2, off);
+  }
+  if (wl == 0) {
+    if (v0) atomicAdd(&c->scene_rays, (unsigned long long)v0);
+    if (v1) atomicAdd(&c->instance_rays, (unsigned long long)v1);
+    if (v2) atomicAdd(&c->shade_calls, (unsigned long long)v2);
+  }
 }
 
 // ---- batch form of intersect_scene_bvh / intersect_instance_bvh ----
@@ -1055,11 +1355,69 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
   (void)cfg;
   static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
   static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
-  static int suspend    = getenv("YGL_SUSPEND") ? atoi(getenv("YGL_SUSPEND")) : kSuspendBelow;
+  // suspension knobs: busy-lane threshold (low byte) and the rounds a drained warp walks first (progress guarantee)
+  static int suspend_b  = getenv("YGL_SUSPEND") ? atoi(getenv("YGL_SUSPEND")) : kSuspendBelow;
+  static int suspend_r  = getenv("YGL_SUSPEND_ROUNDS") ? atoi(getenv("YGL_SUSPEND_ROUNDS")) : kSuspendMinRounds;
+  static int suspend    = suspend_b > 0 ? (std::min(suspend_b, 31) | std::max(1, suspend_r) << 8) : 0;
   if (trav)
     k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps, suspend);
   else
     k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr, refill_thr, node_reps, suspend);
+}
+
+template <int SAMPLER>
+static void launch_persistent_t(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p,
+    int lane_lo, int lane_hi, int sample_begin) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<SAMPLER>, kPersistThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  if (const char* env = getenv("YGL_PERSIST_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(env)));
+  int blocks = num_sms * per_sm;
+  // tiny tiles: no more warps than there are lanes to keep busy (every block hosts all roles)
+  const int needed = std::max(1, (lane_hi - lane_lo + 31) / 32 / 6);
+  blocks           = std::max(1, std::min(blocks, needed));
+  // YGL_PERSIST_ROLES: per-warp pattern of a mixed block, E = traversal, S = shading, L = light pdf (one letter per
+  // warp). YGL_PERSIST_EXT_SMS: traversal SMs per 10 (0 = mixed blocks everywhere). YGL_PERSIST_LPDF_WARPS:
+  // light-pdf warps in a shading block.
+  static unsigned roles = 0;
+  if (!roles) {
+    const int   nw  = kPersistThreads / 32;
+    const char* pat = getenv("YGL_PERSIST_ROLES");
+    if (!pat || (int)strlen(pat) != nw) pat = "EESLEESLEESL";
+    bool has_e = false, has_s = false, has_l = false;
+    for (int w = 0; w < nw; w++) {
+      int r = pat[w] == 'E' ? kRoleExt : pat[w] == 'L' ? kRoleLpdf : kRoleShade;
+      has_e |= r == kRoleExt, has_s |= r == kRoleShade, has_l |= r == kRoleLpdf;
+      roles |= (unsigned)r << (2 * w);
+    }
+    if (!(has_e && has_s && has_l)) {  // every ring needs a consumer in every mixed block
+      roles = 0;
+      for (int w = 0; w < nw; w++) roles |= (unsigned)(w % 4 < 2 ? kRoleExt : w % 4 == 2 ? kRoleShade : kRoleLpdf) << (2 * w);
+    }
+    int ext_sms = getenv("YGL_PERSIST_EXT_SMS") ? atoi(getenv("YGL_PERSIST_EXT_SMS")) : 6;
+    int lw      = getenv("YGL_PERSIST_LPDF_WARPS") ? atoi(getenv("YGL_PERSIST_LPDF_WARPS")) : 2;
+    ext_sms     = std::max(0, std::min(9, ext_sms));
+    lw          = std::max(1, std::min(nw - 1, lw));
+    roles |= (unsigned)ext_sms << 24 | (unsigned)lw << 28;
+  }
+  static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
+  static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
+  k_persistent<SAMPLER><<<blocks, kPersistThreads, 0, s>>>(scene, st, q, p, lane_lo, lane_hi, sample_begin, roles,
+      num_sms, refill_thr, node_reps);
+}
+void launch_persistent(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p, int lane_lo,
+    int lane_hi, int sample_begin) {
+  switch (p.sampler) {
+    case kSamplerPath: launch_persistent_t<kSamplerPath>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    case kSamplerPathDirect: launch_persistent_t<kSamplerPathDirect>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    case kSamplerPathMis: launch_persistent_t<kSamplerPathMis>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    case kSamplerPathTest: launch_persistent_t<kSamplerPathTest>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    case kSamplerNaive: launch_persistent_t<kSamplerNaive>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    case kSamplerEyelight: launch_persistent_t<kSamplerEyelight>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    case kSamplerDiagram: launch_persistent_t<kSamplerDiagram>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    case kSamplerFurnace: launch_persistent_t<kSamplerFurnace>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    default: launch_persistent_t<kSamplerFalsecolor>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+  }
 }
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   const int threads = YGL_SHADE_THREADS;

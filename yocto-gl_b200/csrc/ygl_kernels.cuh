@@ -8,6 +8,41 @@
 
 namespace ygl {
 
+// Lane state is written by one warp and read by another - in persistent mode possibly on another SM, inside the
+// same kernel. L1 is not coherent across SMs, so every state LOAD goes through SArr: ld.global.cg (served by L2,
+// where all stores land). Stores are plain (L1 is write-through). Read-only scene data keeps normal L1 caching.
+template <class T>
+struct SRef {
+  T* p;
+#ifdef __CUDACC__
+  __device__ __forceinline__ operator T() const { return __ldcg(p); }
+  __device__ __forceinline__ const SRef& operator=(const T& v) const {
+    *p = v;
+    return *this;
+  }
+  __device__ __forceinline__ const SRef& operator=(const SRef& o) const {
+    *p = __ldcg(o.p);
+    return *this;
+  }
+  __device__ __forceinline__ const SRef& operator+=(const T& v) const {
+    *p = __ldcg(p) + v;
+    return *this;
+  }
+#endif
+};
+template <class T>
+struct SArr {
+  T* p;
+#ifdef __CUDACC__
+  __device__ __forceinline__ SRef<T> operator[](long long i) const { return SRef<T>{p + i}; }
+#endif
+  __host__ __device__ operator T*() const { return p; }
+  __host__ __device__ SArr& operator=(T* q) {
+    p = q;
+    return *this;
+  }
+};
+
 // Per-lane wavefront state, SoA of 16-byte records so that each stage moves whole 128-bit words.
 // One lane = one pixel of the tile (the only legal parallel axis: each pixel's samples form a
 // sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
@@ -15,34 +50,34 @@ struct PathState {
   int num_lanes;  // pixels in this tile
   int width, height, row_begin, row_step;  // lane l <-> pixel (l % width, row_begin + (l / width) * row_step)
   // ---- trace_state accumulators (reference layout, yocto_trace.h:147-157) ----
-  float4*     image;   // vec4f
-  float*      albedo;  // vec3f packed
-  float*      normal;  // vec3f packed
-  int*        hits;
-  ulonglong2* rngs;  // rng_state {state, inc}
+  SArr<float4>     image;   // vec4f
+  SArr<float>      albedo;  // vec3f packed
+  SArr<float>      normal;  // vec3f packed
+  SArr<int>        hits;
+  SArr<ulonglong2> rngs;  // rng_state {state, inc}
   // ---- per-lane progress ----
-  int* sample;  // index of the sample in flight
+  SArr<int> sample;  // index of the sample in flight
   // ---- path in flight ----
-  float4* ray_o;     // origin.xyz, w: bounce (int bits)
-  float4* ray_d;     // direction.xyz, w: opbounce (int bits)
-  float4* radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
-  float4* weight;    // rgb, w: max_roughness
-  float4* hit_uvd;   // uv.x uv.y distance hit(int bits)
-  int2*   hit_ids;   // instance, element
-  float4* albedo0;   // bounce-0 albedo rgb, w unused
-  float4* normal0;   // bounce-0 normal (or -camera dir on miss) xyz
-  float4* vol_a;     // volume slot: density.xyz, scanisotropy
-  float4* vol_b;     // volume slot: scattering.xyz
-  float4* pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
-  int*    susp;      // kSuspendWords ints per lane: traversal state of a ray suspended by k_extend
+  SArr<float4> ray_o;     // origin.xyz, w: bounce (int bits)
+  SArr<float4> ray_d;     // direction.xyz, w: opbounce (int bits)
+  SArr<float4> radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
+  SArr<float4> weight;    // rgb, w: max_roughness
+  SArr<float4> hit_uvd;   // uv.x uv.y distance hit(int bits)
+  SArr<int2>   hit_ids;   // instance, element
+  SArr<float4> albedo0;   // bounce-0 albedo rgb, w unused
+  SArr<float4> normal0;   // bounce-0 normal (or -camera dir on miss) xyz
+  SArr<float4> vol_a;     // volume slot: density.xyz, scanisotropy
+  SArr<float4> vol_b;     // volume slot: scattering.xyz
+  SArr<float4> pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
+  SArr<int>    susp;      // kSuspendWords ints per lane: traversal state of a ray suspended by k_extend
   // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
-  float4* aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
-  float4* aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
-  float4* aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
-  float4* aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
-  int2*   aux_ids;   // shadow-ray hit: instance, element
-  float4* next_uvd;  // pathmis next_intersection (persists across bounces)
-  int2*   next_ids;
+  SArr<float4> aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
+  SArr<float4> aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
+  SArr<float4> aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
+  SArr<float4> aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
+  SArr<int2>   aux_ids;   // shadow-ray hit: instance, element
+  SArr<float4> next_uvd;  // pathmis next_intersection (persists across bounces)
+  SArr<int2>   next_ids;
 };
 
 // Work queues: lane ids compacted with warp-ballot / one atomic per warp.
@@ -60,6 +95,22 @@ struct Counters {
   int done_lanes;  // lanes that finished all their samples
   int ext_head;    // work cursor of the persistent extend kernel (reset every iteration)
   unsigned long long camera_samples, scene_rays, instance_rays, shade_calls;
+};
+
+// ---- persistent mode: ring queues shared by the role-specialised warps of ONE resident kernel ----
+// A ring holds lane ids (extend ring: lane | kEntryShadow). Its capacity (a power of two >= the number of lanes)
+// can never overflow: a lane is in at most one ring at a time. Empty slots hold -1.
+struct Ring {
+  int*      slots;
+  unsigned* head;  // next index to consume (monotonic)
+  unsigned* tail;  // next index to produce (monotonic)
+  unsigned  mask;  // capacity - 1
+};
+struct PQueues {
+  Ring      ext, shade, lpdf;
+  Counters* counters;
+  unsigned* seed_cursor;  // lanes handed out for their first camera sample
+  int*      abort;        // set by the watchdog (host or device): every warp leaves
 };
 
 struct KParams {  // trace_params subset used on device (yocto_trace.h:95-113)
@@ -83,6 +134,9 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+// persistent mode: one launch renders samples [sample_begin, p.sample_end) of lanes [lane_lo, lane_hi)
+void launch_persistent(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p, int lane_lo,
+    int lane_hi, int sample_begin);
 
 // batch intersect (test hook + traversal micro-benchmark). counters may be null.
 void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const float4* rays, long long n, int instance,

@@ -319,6 +319,8 @@ YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f
 // `src` (src.fetch hands out rays, src.commit stores a finished lane's hit). Must be called by full,
 // converged warps.
 constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
+constexpr int kPollInterval    = 6;  // scheduling rounds between two polls of an empty ring queue ...
+constexpr int kPollMaxInterval = 96;  // ... doubling up to this while it stays empty
 constexpr int kStreamThreads   = 128;  // block size of kernels that call trace_stream
 constexpr int kSharedStack     = 28;
 constexpr int kSuspendWords    = 48;   // words of saved traversal state per lane (12 header + 36 stack)
@@ -326,13 +328,13 @@ constexpr int kSuspendStack    = kSuspendWords - 12;
 constexpr int kSuspendMinRounds = 96;  // a warp walks at least this many rounds per launch before suspending: progress guarantee
 constexpr int kSuspendBelow    = 8;    // suspend a drained warp's stragglers once this few lanes are busy (0 = never)   // stack entries per lane kept in shared memory (14 KB per block)
 
-template <bool COUNT, class Source>
+template <bool COUNT, int THREADS, class Source>
 YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   // Traversal stack: the first kSharedStack entries of every lane live in shared memory, laid out
   // [entry][thread] so a lane always hits its own bank (conflict-free whatever the lanes' depths are);
   // deeper entries spill to a per-thread local array (rare: kSharedStack covers a 1000-instance tree
   // plus a 64K-primitive shape tree).
-  __shared__ int s_stack[kSharedStack][kStreamThreads];
+  __shared__ int s_stack[kSharedStack][THREADS];
   int            l_stack[2 * kStackSize + 8 - kSharedStack];
   const int      tix  = threadIdx.x;
   int            sp   = 1;
@@ -407,7 +409,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     return v;
   };
 
-  int cur = kMarkDone, leaf_next = 0, leaf_end = 0, rounds = 0;
+  int cur = kMarkDone, leaf_next = 0, leaf_end = 0, rounds = 0, poll_wait = 0, poll_gap = kPollInterval;
   while (true) {
     const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0);
     const unsigned want_prim  = __ballot_sync(kFullWarp, cur == kMarkLeaf);
@@ -415,10 +417,10 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     const unsigned busy       = want_node | want_prim | want_enter;
     const int      n_idle     = 32 - __popc(busy);
 
-    if (more && n_idle >= src.refill_thr) {
+    if (more && n_idle >= src.refill_thr && (!Source::kPolling || !busy || --poll_wait < 0)) {
       // ---- refill: finished lanes hand over their hit and take the next queued ray ----
       const bool idle = cur == kMarkDone;
-      if (idle && have) src.commit(res);
+      src.commit_finished(idle && have, res);
       f3   o, d;
       bool resume = false;
       const bool got = src.fetch(idle, o, d, more, resume);
@@ -445,10 +447,19 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
           if (pkt >= 0) reload_instance(pkt);
         }
       }
-      continue;
+      if (!Source::kPolling) continue;
+      // a polling source (ring queue fed by other warps while this one runs) may have had nothing to hand out:
+      // keep walking the busy lanes and ask again a few rounds later; a fully idle warp returns to its caller
+      if (__any_sync(kFullWarp, got)) {
+        poll_wait = 0, poll_gap = kPollInterval;
+        continue;
+      }
+      poll_wait = poll_gap;  // empty ring: exponential back-off keeps idle polls off the L2 hot line
+      poll_gap  = min(2 * poll_gap, kPollMaxInterval);
+      if (!busy) break;
     }
     if (!busy) break;
-    if (!more && src.suspend_below > 0 && ++rounds >= kSuspendMinRounds && __popc(busy) <= src.suspend_below) {
+    if (!more && src.suspend_below > 0 && ++rounds >= (src.suspend_below >> 8) && __popc(busy) <= (src.suspend_below & 0xff)) {
       // ---- suspend: the queue is exhausted and this warp is running nearly empty. Instead of draining
       // the stragglers at 1-2 lanes per instruction, save their traversal state; they resume in the next
       // launch (one wavefront iteration later — a per-lane delay only, the walk itself is unchanged). ----
@@ -537,7 +548,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     }
   }
   // lanes still holding an uncommitted result (more == false path)
-  if (have && cur == kMarkDone) src.commit(res);
+  src.commit_finished(have && cur == kMarkDone, res);
 }
 
 }  // namespace ygl

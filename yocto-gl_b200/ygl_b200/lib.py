@@ -24,7 +24,7 @@ EXPORTS = [
     "ygl_lights_get", "ygl_lights_destroy", "ygl_state_create", "ygl_state_create_tile",
     "ygl_state_create_interleaved", "ygl_state_layout", "ygl_state_size", "ygl_state_rows", "ygl_state_download", "ygl_state_upload",
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
-    "ygl_trace_counters", "ygl_context_set_profiling", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
+    "ygl_trace_counters", "ygl_context_set_profiling", "ygl_context_set_mode", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
 ]
 
@@ -76,6 +76,7 @@ def load():
     lib.ygl_trace_image.argtypes = [vp, P(abi.SceneDesc), P(abi.TraceParams), P(i32), P(i32), vp]
     lib.ygl_trace_counters.argtypes = [vp, vp]
     lib.ygl_context_set_profiling.argtypes = [vp, i32, i32]
+    lib.ygl_context_set_mode.argtypes = [vp, i32]
     lib.ygl_trace_timings.argtypes = [vp, vp]
     lib.ygl_intersect_rays.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.ygl_intersect_rays_device.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
@@ -192,6 +193,10 @@ class Context:
                  "extend_launches", "top_nodes", "bottom_nodes", "instance_visits", "triangle_tests",
                  "quad_tests", "line_tests", "point_tests"]
         return {k: int(v) for k, v in zip(names, c)}
+
+    def set_mode(self, mode):
+        """'wavefront' (default) or 'persistent' (one resident kernel per call); results are bit-identical."""
+        _check(self.lib.ygl_context_set_mode(self.h, {"wavefront": 0, "persistent": 1}[mode]))
 
     def set_profiling(self, time_kernels=False, count_traversal=False):
         _check(self.lib.ygl_context_set_profiling(self.h, int(time_kernels), int(count_traversal)))
