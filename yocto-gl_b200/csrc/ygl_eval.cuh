@@ -93,7 +93,7 @@ YGL_D f4 eval_texture(const DTexture& tex, const f2& uv, bool as_linear, bool no
          lookup_texture(tex, ii, jj, as_linear) * u * v;
 }
 // eval_texture(scene, id, uv, as_linear), yocto_scene.cpp:167-171
-YGL_D f4 eval_texture(const DScene& scene, int texture, const f2& uv, bool as_linear) {
+YGL_D_BIG f4 eval_texture(const DScene& scene, int texture, const f2& uv, bool as_linear) {
   if (texture < 0) return {1, 1, 1, 1};
   const DTexture& tex = scene.textures[texture];
   return eval_texture(tex, uv, as_linear, tex.nearest != 0, tex.clamp != 0);
@@ -315,7 +315,7 @@ YGL_D f3 eval_shading_position(const DScene& scene, const DInstance& inst, int e
   return {0, 0, 0};
 }
 // eval_shading_normal, yocto_scene.cpp:486-505
-YGL_D f3 eval_shading_normal(const DScene& scene, const DInstance& inst, int element, const f2& uv, const f3& outgoing) {
+YGL_D_BIG f3 eval_shading_normal(const DScene& scene, const DInstance& inst, int element, const f2& uv, const f3& outgoing) {
   const DShape&    s   = scene.shapes[inst.shape];
   const DMaterial& mat = scene.materials[inst.material];
   if (s.num_triangles > 0 || s.num_quads > 0) {
@@ -333,7 +333,7 @@ YGL_D f3 eval_shading_normal(const DScene& scene, const DInstance& inst, int ele
 }
 
 // eval_material, yocto_scene.cpp:531-581
-YGL_D mpoint eval_material(const DScene& scene, const DInstance& inst, int element, const f2& uv) {
+YGL_D_BIG mpoint eval_material(const DScene& scene, const DInstance& inst, int element, const f2& uv) {
   const DMaterial& mat = scene.materials[inst.material];
   auto texcoord        = eval_texcoord(scene, inst, element, uv);
   auto emission_tex    = eval_texture(scene, mat.emission_tex, texcoord, true);
@@ -374,7 +374,7 @@ YGL_D bool is_volumetric_type(int type) {  // yocto_scene.cpp:257-261
 }
 
 // eval_environment, yocto_scene.cpp:596-613
-YGL_D f3 eval_environment(const DScene& scene, const f3& direction) {
+YGL_D_BIG f3 eval_environment(const DScene& scene, const f3& direction) {
   f3 emission = {0, 0, 0};
   for (int e = 0; e < scene.num_environments; e++) {
     const DEnvironment& env = scene.environments[e];

@@ -118,6 +118,7 @@ struct KParams {  // trace_params subset used on device (yocto_trace.h:95-113)
   float clamp;
   int   nocaustics, envhidden, tentfilter;
   int   sample_end;  // lanes stop when sample index reaches this
+  int   fuse;        // shading kernels finish a path themselves (accumulate + next camera sample); 0 = separate kernels
 };
 
 struct LaunchCfg {

@@ -435,7 +435,7 @@ YGL_HD bool is_delta(const mpoint& m) {  // yocto_scene.cpp:263-271
 YGL_HD f3 eval_emission(const mpoint& m, const f3& n, const f3& o) {
   return dot(n, o) >= 0 ? m.emission : f3{0, 0, 0};
 }
-YGL_HD f3 eval_bsdfcos(const mpoint& m, const f3& n, const f3& o, const f3& i) {
+YGL_HD_BIG f3 eval_bsdfcos(const mpoint& m, const f3& n, const f3& o, const f3& i) {
   if (m.roughness == 0) return {0, 0, 0};
   switch (m.type) {
     case kMatte: return eval_matte(m.color, n, o, i);
@@ -458,7 +458,7 @@ YGL_HD f3 eval_delta(const mpoint& m, const f3& n, const f3& o, const f3& i) {
     default: return {0, 0, 0};
   }
 }
-YGL_HD f3 sample_bsdfcos(const mpoint& m, const f3& n, const f3& o, float rnl, const f2& rn) {
+YGL_HD_BIG f3 sample_bsdfcos(const mpoint& m, const f3& n, const f3& o, float rnl, const f2& rn) {
   if (m.roughness == 0) return {0, 0, 0};
   switch (m.type) {
     case kMatte: return sample_matte(n, o, rn);
@@ -481,7 +481,7 @@ YGL_HD f3 sample_delta(const mpoint& m, const f3& n, const f3& o, float rnl) {
     default: return {0, 0, 0};
   }
 }
-YGL_HD float sample_bsdfcos_pdf(const mpoint& m, const f3& n, const f3& o, const f3& i) {
+YGL_HD_BIG float sample_bsdfcos_pdf(const mpoint& m, const f3& n, const f3& o, const f3& i) {
   if (m.roughness == 0) return 0;
   switch (m.type) {
     case kMatte: return sample_matte_pdf(n, o, i);

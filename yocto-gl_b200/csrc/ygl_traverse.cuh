@@ -410,6 +410,70 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   };
 
   int cur = kMarkDone, leaf_next = 0, leaf_end = 0, rounds = 0, poll_wait = 0, poll_gap = kPollInterval;
+  // one node visit of the lane's walk (cur >= 0)
+  auto visit_node = [&]() {
+    float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
+    if (COUNT) {
+      if (bottom) cnt.bot_nodes++;
+      else cnt.top_nodes++;
+    }
+    bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
+                            : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
+    int      start = __float_as_int(n1.z);
+    unsigned meta  = (unsigned)__float_as_int(n1.w);
+    if (!inside) {
+      cur = advance();
+    } else if (meta >> 24) {
+      int neg = (ray.sgn >> ((meta >> 16) & 0xff)) & 1;
+      push(start + 1 - neg);
+      cur = start + neg;
+    } else if (bottom) {
+      leaf_next = start;
+      leaf_end  = start + (int)(meta & 0xffff);
+      cur       = leaf_next < leaf_end ? kMarkLeaf : advance();
+    } else {
+      // leaf of the instance tree (<= 4 instances, visited in order): one ENTER entry for the run
+      const int num = (int)(meta & 0xffff);
+      cur           = num > 0 ? ~(start | ((num - 1) << 28)) : advance();
+    }
+  };
+  // one primitive of the current leaf
+  auto test_prim = [&](int idx) {
+    if (COUNT) cnt.prims_by_kind[kind]++;
+    f2    puv = {0, 0};
+    float pd  = 0;
+    bool  h;
+    if (kind == kElemTriangles) {
+      float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
+      h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
+    } else if (kind == kElemQuads) {
+      float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
+             e = __ldg(packets + 4 * idx + 3);
+      h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
+          f3{e.x, e.y, e.z}, puv, pd);
+    } else if (kind == kElemLines) {
+      float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
+      h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
+    } else {
+      float4 a = __ldg(packets + idx);
+      h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
+    }
+    if (h) {
+      res  = {cur_instance, __ldg(prims + idx), puv, pd, true};
+      tmax = pd;
+    }
+  };
+  // park the lane's unfinished walk in its save area; it resumes in the next launch exactly where it stopped
+  auto suspend_lane = [&]() {
+    int* sv = src.saved();
+    sv[0] = cur, sv[1] = sp, sv[2] = leaf_next, sv[3] = leaf_end, sv[4] = cur_packet;
+    sv[5] = __float_as_int(tmax);
+    sv[6] = res.instance, sv[7] = res.element, sv[8] = __float_as_int(res.uv.x), sv[9] = __float_as_int(res.uv.y);
+    sv[10] = __float_as_int(res.distance), sv[11] = res.hit ? 1 : 0;
+    for (int k = 1; k < sp; k++) sv[12 + k] = k < kSharedStack ? s_stack[k][tix] : l_stack[k - kSharedStack];
+    src.commit_suspended();
+    cur = kMarkDone, sp = 1, have = false;
+  };
   while (true) {
     const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0);
     const unsigned want_prim  = __ballot_sync(kFullWarp, cur == kMarkLeaf);
@@ -463,84 +527,47 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       // ---- suspend: the queue is exhausted and this warp is running nearly empty. Instead of draining
       // the stragglers at 1-2 lanes per instruction, save their traversal state; they resume in the next
       // launch (one wavefront iteration later — a per-lane delay only, the walk itself is unchanged). ----
-      const bool mine = cur != kMarkDone && sp <= kSuspendStack;
-      if (mine) {
-        int* sv = src.saved();
-        sv[0] = cur, sv[1] = sp, sv[2] = leaf_next, sv[3] = leaf_end, sv[4] = cur_packet;
-        sv[5] = __float_as_int(tmax);
-        sv[6] = res.instance, sv[7] = res.element, sv[8] = __float_as_int(res.uv.x), sv[9] = __float_as_int(res.uv.y);
-        sv[10] = __float_as_int(res.distance), sv[11] = res.hit ? 1 : 0;
-        for (int k = 1; k < sp; k++) sv[12 + k] = k < kSharedStack ? s_stack[k][tix] : l_stack[k - kSharedStack];
-        src.commit_suspended();
-        cur = kMarkDone, sp = 1, have = false;
-      }
+      if (cur != kMarkDone && sp <= kSuspendStack) suspend_lane();
       if (!__any_sync(kFullWarp, cur != kMarkDone)) break;
       // lanes with a deeper stack than the save area keep walking
+    }
+    if (!more && src.lone_below > 0 && __popc(busy) <= src.lone_below) {
+      // ---- tail: the queue is exhausted and only a few rays of this warp are left. Their remaining walk is a
+      // chain of dependent steps; without the per-round votes each step is ~20 % shorter. ----
+      // lone_steps > 0 caps the tail: a ray that still walks after that many more steps is parked for the next
+      // launch (only the extreme stragglers get there; a parked ray always advances lone_steps per launch)
+      const int limit = src.lone_steps > 0 ? src.lone_steps : 0x7fffffff;
+      int       steps = 0;
+      while (cur != kMarkDone) {
+        if (++steps > limit && sp <= kSuspendStack) {
+          suspend_lane();
+          break;
+        }
+        if (cur >= 0) {
+          visit_node();
+        } else if (cur == kMarkLeaf) {
+          while (leaf_next < leaf_end) test_prim(leaf_next++);
+          cur = advance();
+        } else {
+          cur = enter(cur);
+        }
+      }
+      break;
     }
     const int n_node = __popc(want_node), n_prim = __popc(want_prim), n_enter = __popc(want_enter);
 
     if (n_node >= n_prim && n_node >= n_enter) {
-      // two node visits per scheduling round: halves the vote overhead on the most frequent path
+      // several node visits per scheduling round: cuts the vote overhead on the most frequent path
 #pragma unroll 1
       for (int rep = 0; rep < src.node_reps; rep++)
-      if (cur >= 0) {
-        float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
-        if (COUNT) {
-          if (bottom) cnt.bot_nodes++;
-          else cnt.top_nodes++;
-        }
-        bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
-                                : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
-        int      start = __float_as_int(n1.z);
-        unsigned meta  = (unsigned)__float_as_int(n1.w);
-        if (!inside) {
-          cur = advance();
-        } else if (meta >> 24) {
-          int neg     = (ray.sgn >> ((meta >> 16) & 0xff)) & 1;
-          push(start + 1 - neg);
-          cur         = start + neg;
-        } else if (bottom) {
-          leaf_next = start;
-          leaf_end  = start + (int)(meta & 0xffff);
-          cur       = leaf_next < leaf_end ? kMarkLeaf : advance();
-        } else {
-          // leaf of the instance tree (<= 4 instances, visited in order): one ENTER entry for the run
-          const int num = (int)(meta & 0xffff);
-          cur           = num > 0 ? ~(start | ((num - 1) << 28)) : advance();
-        }
-      }
+        if (cur >= 0) visit_node();
     } else if (n_prim >= n_enter) {
       // all primitives of the lane's leaf (<= 4, bvh_max_prims) in one go, warp-uniform trip count
       const bool in_leaf = cur == kMarkLeaf;
       for (int k = 0; k < 4; k++) {
         const bool test = in_leaf && leaf_next < leaf_end;
         if (!__any_sync(kFullWarp, test)) break;
-        if (test) {
-          const int idx = leaf_next++;
-          if (COUNT) cnt.prims_by_kind[kind]++;
-          f2    puv = {0, 0};
-          float pd  = 0;
-          bool  h;
-          if (kind == kElemTriangles) {
-            float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
-            h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
-          } else if (kind == kElemQuads) {
-            float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
-                   e = __ldg(packets + 4 * idx + 3);
-            h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
-                f3{e.x, e.y, e.z}, puv, pd);
-          } else if (kind == kElemLines) {
-            float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
-            h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
-          } else {
-            float4 a = __ldg(packets + idx);
-            h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
-          }
-          if (h) {
-            res  = {cur_instance, __ldg(prims + idx), puv, pd, true};
-            tmax = pd;
-          }
-        }
+        if (test) test_prim(leaf_next++);
       }
       if (in_leaf) cur = advance();
     } else {
