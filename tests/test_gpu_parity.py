@@ -14,6 +14,7 @@ from ygl_b200 import abi, lib, scenes
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SCENES = {
     "cornell": scenes.cornellbox,
@@ -152,6 +153,38 @@ def test_persistent_mode_matches_reference(ref, sampler):
         for k in ("image", "albedo", "normal", "hits"):
             assert got[k].tobytes() == want[k].tobytes(), (k, res)
         np.testing.assert_array_equal(got["rngs"], want["rngs"])
+
+
+@pytest.mark.parametrize("env", [
+    dict(YGL_SUSPEND="8", YGL_SUSPEND_ROUNDS="8", YGL_LONE="0"),    # park the last lanes of a drained warp early and often
+    dict(YGL_SUSPEND="0", YGL_LONE="32", YGL_LONE_STEPS="40"),      # vote-free tail walk, parked after 40 steps
+    dict(YGL_SUSPEND="0", YGL_LONE="0", YGL_FUSE="0"),              # plain drain, separate accumulate / generate kernels
+    dict(YGL_FUSE="1", YGL_REFILL="4", YGL_NODE_REPS="1"),
+])
+def test_tail_strategies_are_bit_exact(ref, env, tmp_path):
+    """The extend kernel's tail strategies (parking stragglers for the next launch, the vote-free walk, its step
+    cap) and the path-end fusion are chosen by tile size at run time; each is a scheduling change only. They are
+    read from the environment once per process, so each setting renders in its own process."""
+    import subprocess
+    import sys as _sys
+    out = tmp_path / "img.npy"
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = [%r, %r]\n"
+        "from ygl_b200 import abi, lib, scenes\n"
+        "ctx = lib.Context(0)\n"
+        "p = abi.trace_params(resolution=160, samples=4, bounces=8, batch=2)\n"
+        "sc = scenes.features()\n"
+        "ds = lib.DeviceScene(ctx, sc)\n"
+        "st = ds.make_state(p)\n"
+        "ds.trace_samples(st, p); ds.trace_samples(st, p)\n"
+        "np.save(%r, st.download(full=True)['image'])\n"
+    ) % (os.path.join(ROOT, "yocto-gl_b200"), os.path.join(ROOT, "oracle"), str(out))
+    full_env = dict(os.environ, **env)
+    subprocess.run([_sys.executable, "-c", code], check=True, env=full_env, timeout=120)
+    params = abi.trace_params(resolution=160, samples=4, bounces=8, batch=2)
+    want = ref.scene(get_scene("features")).trace_image(params)["image"]
+    assert np.load(out).tobytes() == want.tobytes(), env
 
 
 def test_full_state_and_resume(ctx, ref):

@@ -46,11 +46,13 @@ YGL_D float4 pack(const f3& v, float w) { return make_float4(v.x, v.y, v.z, w); 
 YGL_D float4 pack(const f3& v, int w) { return make_float4(v.x, v.y, v.z, __int_as_float(w)); }
 YGL_D f3     unpack3(const float4& v) { return f3{v.x, v.y, v.z}; }
 
-YGL_D rng_t load_rng(const PathState& st, int lane) {
+template <class PS>
+YGL_D rng_t load_rng(const PS& st, int lane) {
   ulonglong2 r = st.rngs[lane];
   return rng_t{r.x, r.y};
 }
-YGL_D void store_rng(const PathState& st, int lane, const rng_t& rng) {
+template <class PS>
+YGL_D void store_rng(const PS& st, int lane, const rng_t& rng) {
   st.rngs[lane] = make_ulonglong2(rng.state, rng.inc);
 }
 
@@ -83,9 +85,11 @@ __global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begi
 
 // ---- ray generation: trace_sample head, yocto_trace.cpp:1461-1468. g++ evaluates the two rand2f
 // arguments right-to-left, so the lens sample `luv` is drawn BEFORE the pixel sample `puv`. ----
-YGL_D bool accumulate_lane(const DScene& scene, const PathState& st, const KParams& p, int lane);
+template <class PS>
+YGL_D bool accumulate_lane(const DScene& scene, const PS& st, const KParams& p, int lane);
 
-YGL_D void generate_lane(const DScene& scene, const PathState& st, const KParams& p, int lane) {
+template <class PS>
+YGL_D void generate_lane(const DScene& scene, const PS& st, const KParams& p, int lane) {
   const DCamera& camera = scene.cameras[p.camera];
   int px = lane % st.width, py = st.row_begin + (lane / st.width) * st.row_step;
   rng_t rng = load_rng(st, lane);
@@ -310,8 +314,8 @@ YGL_D f3 hashed_color(int id) {
 }
 
 // ---- shade one lane. Returns the destination queue. ----
-template <int SAMPLER>
-YGL_D int shade_lane(const DScene& scene, const PathState& st, const KParams& p, int lane, unsigned& inst_rays) {
+template <int SAMPLER, class PS>
+YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int lane, unsigned& inst_rays) {
   float4 ro = st.ray_o[lane], rd = st.ray_d[lane], rad4 = st.radiance[lane], w4 = st.weight[lane];
   float4 huvd = st.hit_uvd[lane];
   f3  o = unpack3(ro), d = unpack3(rd), radiance = unpack3(rad4), weight = unpack3(w4);
@@ -581,7 +585,8 @@ YGL_D float mis_heuristic(float this_pdf, float other_pdf) {  // yocto_trace.cpp
   return (this_pdf * this_pdf) / (this_pdf * this_pdf + other_pdf * other_pdf);
 }
 // emission seen along a shadow ray, yocto_trace.cpp:667-677 / :874-886
-YGL_D f3 shadow_emission(const DScene& scene, const PathState& st, int lane, const f3& incoming) {
+template <class PS>
+YGL_D f3 shadow_emission(const DScene& scene, const PS& st, int lane, const f3& incoming) {
   float4 h = st.aux_uvd[lane];
   if (__float_as_int(h.w) == 0) return eval_environment(scene, incoming);
   int2             ids  = st.aux_ids[lane];
@@ -592,8 +597,8 @@ YGL_D f3 shadow_emission(const DScene& scene, const PathState& st, int lane, con
   return eval_emission(material, normal, -incoming);
 }
 
-template <int SAMPLER>
-YGL_D int shade_multi(const DScene& scene, const PathState& st, const KParams& p, int lane) {
+template <int SAMPLER, class PS>
+YGL_D int shade_multi(const DScene& scene, const PS& st, const KParams& p, int lane) {
   constexpr bool MIS = SAMPLER == kSamplerPathMis;
   float4 ro = st.ray_o[lane], rd = st.ray_d[lane], rad4 = st.radiance[lane], w4 = st.weight[lane];
   float4 huvd = st.hit_uvd[lane], ab = st.aux_bsdf[lane];
@@ -822,7 +827,8 @@ YGL_D int shade_multi(const DScene& scene, const PathState& st, const KParams& p
 // End of a path inside a shading-side kernel: accumulate the sample and, if the lane has more samples to do, start
 // its next camera ray at once (the lane goes straight back to the extend queue - no accumulate / generate launches).
 // WARP-UNIFORM. `counts`: x = samples started, y = lanes finished (per thread).
-YGL_D void end_of_path(const DScene& scene, const PathState& st, const KParams& p, int lane, int& dest, int& entry,
+template <class PS>
+YGL_D void end_of_path(const DScene& scene, const PS& st, const KParams& p, int lane, int& dest, int& entry,
     int2& counts) {
   if (dest == kDestAcc && p.fuse) {
     if (accumulate_lane(scene, st, p, lane)) {
@@ -896,7 +902,8 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
 #endif
 // One warp-wide step (WARP-COOPERATIVE: every lane of the warp must call it; `valid` marks lanes that hold a queued
 // lane id). Outputs the lane's destination queue and its extend-queue entry.
-YGL_D void lightpdf_lane(const DScene& scene, const PathState& st, const KParams& p, bool valid, int lane,
+template <class PS>
+YGL_D void lightpdf_lane(const DScene& scene, const PS& st, const KParams& p, bool valid, int lane,
     unsigned& rays, int& dest, int& entry) {
   float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 1, 0);
   const bool multi = p.sampler == kSamplerPathDirect || p.sampler == kSamplerPathMis;
@@ -964,7 +971,8 @@ __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene sce
 }
 
 // ---- accumulate: trace_sample tail, yocto_trace.cpp:1469-1491. Returns whether the lane has more samples to do. ----
-YGL_D bool accumulate_lane(const DScene& scene, const PathState& st, const KParams& p, int lane) {
+template <class PS>
+YGL_D bool accumulate_lane(const DScene& scene, const PS& st, const KParams& p, int lane) {
   float4 rad4   = st.radiance[lane];
   f3     radiance = unpack3(rad4);
   bool   hit    = (__float_as_int(rad4.w) & kFlagHit) != 0;
@@ -1096,8 +1104,8 @@ YGL_D bool ring_take(const Ring& r, bool want, unsigned& ticket, bool& held, int
 }
 
 struct RingSource {
-  PQueues   q;
-  PathState st;
+  PQueues    q;
+  PathStateC st;
   int       lane, total;
   int       refill_thr, node_reps, suspend_below, lone_below, lone_steps;
   unsigned  finished, taken, ticket;
@@ -1133,8 +1141,8 @@ struct RingSource {
 
 // Send a shaded lane on (WARP-UNIFORM). A finished path is accumulated here and the lane's next camera sample
 // starts at once; a lane that needs no ray this round (kEntryPass) goes straight back to the shade ring.
-template <bool USES_LPDF>
-YGL_D void route_lane(const DScene& scene, const PathState& st, const PQueues& q, const KParams& p, int lane, int dest,
+template <bool USES_LPDF, class PS>
+YGL_D void route_lane(const DScene& scene, const PS& st, const PQueues& q, const KParams& p, int lane, int dest,
     int out) {
   bool to_shade = dest == kDestExt && (out & kEntryPass) != 0;
   bool to_ext   = dest == kDestExt && !to_shade;
@@ -1175,7 +1183,7 @@ enum : int { kRoleExt = 0, kRoleShade = 1, kRoleLpdf = 2 };
 constexpr int kPersistThreads = 384;
 
 template <int SAMPLER>
-__global__ void __launch_bounds__(kPersistThreads, YGL_PERSIST_MINBLOCKS) k_persistent(DScene scene, PathState st, PQueues q,
+__global__ void __launch_bounds__(kPersistThreads, YGL_PERSIST_MINBLOCKS) k_persistent(DScene scene, PathStateC st, PQueues q,
     KParams p, int lane_lo, int lane_hi, int sample_begin, unsigned roles, int num_sms, int refill_thr, int node_reps) {
   constexpr bool multi     = SAMPLER == kSamplerPathDirect || SAMPLER == kSamplerPathMis;
   constexpr bool uses_lpdf = SAMPLER == kSamplerPath || SAMPLER == kSamplerPathTest || multi;
@@ -1357,14 +1365,19 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
   (void)cfg;
   static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
   static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
-  // suspension knobs: busy-lane threshold (low byte) and the rounds a drained warp walks first (progress guarantee)
-  static int suspend_b  = getenv("YGL_SUSPEND") ? atoi(getenv("YGL_SUSPEND")) : 0;  // measured: never pays off
+  // Tail knobs (the queue is exhausted, the warp drains). Two alternatives, chosen by the size of the tile
+  // (measured on B200, C3): on a full 1080p frame (2.07 M lanes, ~9 rays per slot and launch) parking the last
+  // <= 8 busy lanes of a warp for the next launch once it has walked 96 more rounds wins 2 %; on small tiles
+  // (one ray per slot: the launch time IS the tail) parking only adds iterations, and finishing the last
+  // <= 12 lanes in a vote-free per-lane loop wins 8 % (1/8 tile: 78.8 -> 72.4 ms per 32 spp).
+  static int suspend_b  = getenv("YGL_SUSPEND") ? atoi(getenv("YGL_SUSPEND")) : -1;
   static int suspend_r  = getenv("YGL_SUSPEND_ROUNDS") ? atoi(getenv("YGL_SUSPEND_ROUNDS")) : kSuspendMinRounds;
-  static int suspend    = suspend_b > 0 ? (std::min(suspend_b, 31) | std::max(1, suspend_r) << 8) : 0;
-  // tail knobs: once the queue is exhausted and <= lone lanes of a warp are busy they finish vote-free
-  // (measured on B200, 1/8 tile of C3: 78.8 -> 72.4 ms per 32 spp; full frame unchanged)
-  static int lone       = getenv("YGL_LONE") ? atoi(getenv("YGL_LONE")) : 12;
+  static int lone_env   = getenv("YGL_LONE") ? atoi(getenv("YGL_LONE")) : -1;
   static int lone_steps = getenv("YGL_LONE_STEPS") ? atoi(getenv("YGL_LONE_STEPS")) : 0;
+  const bool big_tile   = st.num_lanes > 800000;
+  const int  sb         = suspend_b >= 0 ? suspend_b : (big_tile ? kSuspendBelow : 0);
+  const int  suspend    = sb > 0 ? (std::min(sb, 31) | std::max(1, suspend_r) << 8) : 0;
+  const int  lone       = lone_env >= 0 ? lone_env : (big_tile ? 0 : 12);
   if (trav)
     k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps, suspend, lone, lone_steps);
   else
@@ -1408,7 +1421,9 @@ static void launch_persistent_t(cudaStream_t s, int num_sms, DScene scene, PathS
   }
   static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
   static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
-  k_persistent<SAMPLER><<<blocks, kPersistThreads, 0, s>>>(scene, st, q, p, lane_lo, lane_hi, sample_begin, roles,
+  PathStateC stc;  // same layout, coherent loads (see SArr)
+  memcpy(&stc, &st, sizeof(stc));
+  k_persistent<SAMPLER><<<blocks, kPersistThreads, 0, s>>>(scene, stc, q, p, lane_lo, lane_hi, sample_begin, roles,
       num_sms, refill_thr, node_reps);
 }
 void launch_persistent(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p, int lane_lo,

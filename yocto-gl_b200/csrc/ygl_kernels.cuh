@@ -8,33 +8,36 @@
 
 namespace ygl {
 
-// Lane state is written by one warp and read by another - in persistent mode possibly on another SM, inside the
-// same kernel. L1 is not coherent across SMs, so every state LOAD goes through SArr: ld.global.cg (served by L2,
-// where all stores land). Stores are plain (L1 is write-through). Read-only scene data keeps normal L1 caching.
-template <class T>
+// Lane state is written by one warp and read by another. In the wavefront mode a kernel boundary lies in between
+// and plain loads are fine. In persistent mode the reader may sit on another SM inside the same kernel, and L1 is
+// not coherent across SMs: there every state LOAD must be ld.global.cg (served by L2, where all stores land). The
+// policy is part of the state's type (COH), so one set of stage functions serves both kernels and a missed load
+// cannot happen. Stores are plain (L1 is write-through). Read-only scene data keeps normal L1 caching.
+template <class T, bool COH>
 struct SRef {
   T* p;
 #ifdef __CUDACC__
-  __device__ __forceinline__ operator T() const { return __ldcg(p); }
+  __device__ __forceinline__ T load() const { return COH ? __ldcg(p) : *p; }
+  __device__ __forceinline__ operator T() const { return load(); }
   __device__ __forceinline__ const SRef& operator=(const T& v) const {
     *p = v;
     return *this;
   }
   __device__ __forceinline__ const SRef& operator=(const SRef& o) const {
-    *p = __ldcg(o.p);
+    *p = o.load();
     return *this;
   }
   __device__ __forceinline__ const SRef& operator+=(const T& v) const {
-    *p = __ldcg(p) + v;
+    *p = load() + v;
     return *this;
   }
 #endif
 };
-template <class T>
+template <class T, bool COH>
 struct SArr {
   T* p;
 #ifdef __CUDACC__
-  __device__ __forceinline__ SRef<T> operator[](long long i) const { return SRef<T>{p + i}; }
+  __device__ __forceinline__ SRef<T, COH> operator[](long long i) const { return SRef<T, COH>{p + i}; }
 #endif
   __host__ __device__ operator T*() const { return p; }
   __host__ __device__ SArr& operator=(T* q) {
@@ -46,39 +49,43 @@ struct SArr {
 // Per-lane wavefront state, SoA of 16-byte records so that each stage moves whole 128-bit words.
 // One lane = one pixel of the tile (the only legal parallel axis: each pixel's samples form a
 // sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
-struct PathState {
+template <bool COH>
+struct PathStateT {
   int num_lanes;  // pixels in this tile
   int width, height, row_begin, row_step;  // lane l <-> pixel (l % width, row_begin + (l / width) * row_step)
   // ---- trace_state accumulators (reference layout, yocto_trace.h:147-157) ----
-  SArr<float4>     image;   // vec4f
-  SArr<float>      albedo;  // vec3f packed
-  SArr<float>      normal;  // vec3f packed
-  SArr<int>        hits;
-  SArr<ulonglong2> rngs;  // rng_state {state, inc}
+  SArr<float4, COH>     image;   // vec4f
+  SArr<float, COH>      albedo;  // vec3f packed
+  SArr<float, COH>      normal;  // vec3f packed
+  SArr<int, COH>        hits;
+  SArr<ulonglong2, COH> rngs;  // rng_state {state, inc}
   // ---- per-lane progress ----
-  SArr<int> sample;  // index of the sample in flight
+  SArr<int, COH> sample;  // index of the sample in flight
   // ---- path in flight ----
-  SArr<float4> ray_o;     // origin.xyz, w: bounce (int bits)
-  SArr<float4> ray_d;     // direction.xyz, w: opbounce (int bits)
-  SArr<float4> radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
-  SArr<float4> weight;    // rgb, w: max_roughness
-  SArr<float4> hit_uvd;   // uv.x uv.y distance hit(int bits)
-  SArr<int2>   hit_ids;   // instance, element
-  SArr<float4> albedo0;   // bounce-0 albedo rgb, w unused
-  SArr<float4> normal0;   // bounce-0 normal (or -camera dir on miss) xyz
-  SArr<float4> vol_a;     // volume slot: density.xyz, scanisotropy
-  SArr<float4> vol_b;     // volume slot: scattering.xyz
-  SArr<float4> pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
-  SArr<int>    susp;      // kSuspendWords ints per lane: traversal state of a ray suspended by k_extend
+  SArr<float4, COH> ray_o;     // origin.xyz, w: bounce (int bits)
+  SArr<float4, COH> ray_d;     // direction.xyz, w: opbounce (int bits)
+  SArr<float4, COH> radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
+  SArr<float4, COH> weight;    // rgb, w: max_roughness
+  SArr<float4, COH> hit_uvd;   // uv.x uv.y distance hit(int bits)
+  SArr<int2, COH>   hit_ids;   // instance, element
+  SArr<float4, COH> albedo0;   // bounce-0 albedo rgb, w unused
+  SArr<float4, COH> normal0;   // bounce-0 normal (or -camera dir on miss) xyz
+  SArr<float4, COH> vol_a;     // volume slot: density.xyz, scanisotropy
+  SArr<float4, COH> vol_b;     // volume slot: scattering.xyz
+  SArr<float4, COH> pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
+  SArr<int, COH>    susp;      // kSuspendWords ints per lane: traversal state of a ray suspended by k_extend
   // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
-  SArr<float4> aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
-  SArr<float4> aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
-  SArr<float4> aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
-  SArr<float4> aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
-  SArr<int2>   aux_ids;   // shadow-ray hit: instance, element
-  SArr<float4> next_uvd;  // pathmis next_intersection (persists across bounces)
-  SArr<int2>   next_ids;
+  SArr<float4, COH> aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
+  SArr<float4, COH> aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
+  SArr<float4, COH> aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
+  SArr<float4, COH> aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
+  SArr<int2, COH>   aux_ids;   // shadow-ray hit: instance, element
+  SArr<float4, COH> next_uvd;  // pathmis next_intersection (persists across bounces)
+  SArr<int2, COH>   next_ids;
 };
+using PathState  = PathStateT<false>;  // wavefront kernels, host
+using PathStateC = PathStateT<true>;   // persistent kernel: same layout, L1-bypassing loads
+static_assert(sizeof(PathState) == sizeof(PathStateC), "the two views of the lane state must share one layout");
 
 // Work queues: lane ids compacted with warp-ballot / one atomic per warp.
 struct Queues {
