@@ -31,8 +31,20 @@ cases = {
     "features_path": ("features", dict(resolution=64, samples=2, bounces=6)),
     "features_falsecolor": ("features", dict(resolution=64, samples=1, sampler=abi.SAMPLER_FALSECOLOR,
                                              falsecolor=abi.FC_ELEMENT)),
+    # one case per remaining sampler of get_trace_sampler_func (yocto_trace.cpp:1422-1438)
+    "features_pathdirect": ("features", dict(resolution=56, samples=2, bounces=6, sampler=abi.SAMPLER_PATHDIRECT)),
+    "features_pathmis": ("features", dict(resolution=56, samples=2, bounces=6, sampler=abi.SAMPLER_PATHMIS)),
+    "features_pathtest": ("features", dict(resolution=56, samples=2, bounces=6, sampler=abi.SAMPLER_PATHTEST)),
+    "features_naive": ("features", dict(resolution=56, samples=2, bounces=6, sampler=abi.SAMPLER_NAIVE)),
+    "features_eyelight": ("features", dict(resolution=56, samples=2, bounces=6, sampler=abi.SAMPLER_EYELIGHT)),
+    "features_diagram": ("features", dict(resolution=56, samples=2, bounces=6, sampler=abi.SAMPLER_DIAGRAM)),
+    "features_furnace": ("features", dict(resolution=56, samples=2, bounces=6, sampler=abi.SAMPLER_FURNACE)),
+    "cornell_pathmis": ("cornell", dict(resolution=40, samples=3, bounces=5, sampler=abi.SAMPLER_PATHMIS)),
+    "instanced_path": ("instanced4", dict(resolution=64, samples=2, bounces=8)),
+    "hair_path": ("hair", dict(resolution=48, samples=2, bounces=8)),
 }
-factories = {"cornell": scenes.cornellbox, "features": scenes.features}
+factories = {"cornell": scenes.cornellbox, "features": scenes.features,
+             "instanced4": lambda: scenes.instanced_spheres(4), "hair": lambda: scenes.hair_scene(4000, 8, 3)}
 out = {}
 for name, (scene_name, kw) in cases.items():
     scene = factories[scene_name]()
