@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Qu
 // ---- extend: closest hit over the instance BVH for every queued ray ----
 // Persistent warps: each warp keeps 32 rays in flight and refills finished lanes from the queue
 // (extend_stream in ygl_traverse.cuh), so short rays (sky misses) do not idle lanes while long ones walk.
+// TAIL: how a drained warp ends a launch - 0 = park the stragglers for the next launch, 1 = vote-free walk (see
+// launch_extend). A compile-time choice so that each kernel variant carries only its own tail code.
+template <int TAIL>
 struct ExtendSource {
   const int* __restrict__ queue;
   int        n;
@@ -160,6 +163,7 @@ struct ExtendSource {
     return true;
   }
   static constexpr bool kPolling = false;  // the queue is complete when the kernel starts
+  static constexpr bool kPark = TAIL == 0, kLone = TAIL == 1;
   YGL_D void commit_finished(bool flag, const hit_t& h) {
     if (!flag) return;
     (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
@@ -173,12 +177,12 @@ struct ExtendSource {
 #ifndef YGL_EXT_MINBLOCKS
 #define YGL_EXT_MINBLOCKS 7  // measured on B200 (C3): 4/5/6/7/8 blocks/SM -> 249/249/233/224/227 ms per 32 spp
 #endif
-template <bool COUNT>
+template <bool COUNT, int TAIL>
 __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene, PathState st, Queues q, int parity,
     unsigned long long* trav, int refill_thr, int node_reps, int suspend_below, int lone_below, int lone_steps) {
   Counters*     c = q.counters;
   const int     n = c->n_ext[parity];
-  ExtendSource  src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps, suspend_below, lone_below, lone_steps, 0, false};
+  ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps, suspend_below, lone_below, lone_steps, 0, false};
   trav_counters tc = {};
   trace_stream<COUNT, kStreamThreads>(scene, src, tc);
   {
@@ -1111,6 +1115,7 @@ struct RingSource {
   unsigned  finished, taken, ticket;
   bool      shadow, held;
   static constexpr bool kPolling = true;  // the ring is fed by other warps while this one runs
+  static constexpr bool kPark = false, kLone = false;  // no launch boundary, no tail
   YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more, bool& resume) {
     resume     = false;
     int  entry = 0;
@@ -1351,7 +1356,7 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
   static int per_sm = 0;
   static int sms    = 0;
   if (!per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend<false>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_extend<false, 0>), 128, 0);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1378,10 +1383,8 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
   const int  sb         = suspend_b >= 0 ? suspend_b : (big_tile ? kSuspendBelow : 0);
   const int  suspend    = sb > 0 ? (std::min(sb, 31) | std::max(1, suspend_r) << 8) : 0;
   const int  lone       = lone_env >= 0 ? lone_env : (big_tile ? 0 : 12);
-  if (trav)
-    k_extend<true><<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps, suspend, lone, lone_steps);
-  else
-    k_extend<false><<<blocks, 128, 0, s>>>(scene, st, q, parity, nullptr, refill_thr, node_reps, suspend, lone, lone_steps);
+  auto* kernel = lone > 0 ? (trav ? k_extend<true, 1> : k_extend<false, 1>) : (trav ? k_extend<true, 0> : k_extend<false, 0>);
+  kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps, suspend, lone, lone_steps);
 }
 
 template <int SAMPLER>

@@ -523,7 +523,8 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       if (!busy) break;
     }
     if (!busy) break;
-    if (!more && src.suspend_below > 0 && ++rounds >= (src.suspend_below >> 8) && __popc(busy) <= (src.suspend_below & 0xff)) {
+    if (Source::kPark && !more && src.suspend_below > 0 && ++rounds >= (src.suspend_below >> 8) &&
+        __popc(busy) <= (src.suspend_below & 0xff)) {
       // ---- suspend: the queue is exhausted and this warp is running nearly empty. Instead of draining
       // the stragglers at 1-2 lanes per instruction, save their traversal state; they resume in the next
       // launch (one wavefront iteration later — a per-lane delay only, the walk itself is unchanged). ----
@@ -531,7 +532,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       if (!__any_sync(kFullWarp, cur != kMarkDone)) break;
       // lanes with a deeper stack than the save area keep walking
     }
-    if (!more && src.lone_below > 0 && __popc(busy) <= src.lone_below) {
+    if (Source::kLone && !more && src.lone_below > 0 && __popc(busy) <= src.lone_below) {
       // ---- tail: the queue is exhausted and only a few rays of this warp are left. Their remaining walk is a
       // chain of dependent steps; without the per-round votes each step is ~20 % shorter. ----
       // lone_steps > 0 caps the tail: a ray that still walks after that many more steps is parked for the next
