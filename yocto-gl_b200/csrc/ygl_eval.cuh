@@ -68,19 +68,23 @@ YGL_D f4 lookup_texture(const DTexture& tex, int i, int j, bool as_linear) {
   }
   return color;
 }
-// eval_texture, yocto_scene.cpp:127-160
-YGL_D f4 eval_texture(const DTexture& tex, const f2& uv, bool as_linear, bool no_interpolation,
-    bool clamp_to_edge) {
+// eval_texture, yocto_scene.cpp:127-160. The fetch (wrap, four taps, sRGB decode with one powf per channel) is ~700
+// SASS instructions and used to be inlined at six call sites of the shading kernels, whose profile is dominated by
+// instruction-fetch stalls; untextured materials (texture id < 0) never reach it. One out-of-line copy per kernel:
+// pure code layout, the arithmetic is unchanged.
+static __device__ __noinline__ f4 eval_texture_fetch(const DTexture* texp, float uvx, float uvy, bool as_linear,
+    bool no_interpolation, bool clamp_to_edge) {
+  const DTexture& tex = *texp;
   if (tex.width == 0 || tex.height == 0) return {0, 0, 0, 0};
   int   sx = tex.width, sy = tex.height;
   float s = 0.0f, t = 0.0f;
   if (clamp_to_edge) {
-    s = yclamp(uv.x, 0.0f, 1.0f) * sx;
-    t = yclamp(uv.y, 0.0f, 1.0f) * sy;
+    s = yclamp(uvx, 0.0f, 1.0f) * sx;
+    t = yclamp(uvy, 0.0f, 1.0f) * sy;
   } else {
-    s = yfmod(uv.x, 1.0f) * sx;
+    s = yfmod(uvx, 1.0f) * sx;
     if (s < 0) s += sx;
-    t = yfmod(uv.y, 1.0f) * sy;
+    t = yfmod(uvy, 1.0f) * sy;
     if (t < 0) t += sy;
   }
   int   i = iclamp((int)s, 0, sx - 1), j = iclamp((int)t, 0, sy - 1);
@@ -91,6 +95,10 @@ YGL_D f4 eval_texture(const DTexture& tex, const f2& uv, bool as_linear, bool no
          lookup_texture(tex, i, jj, as_linear) * (1 - u) * v +
          lookup_texture(tex, ii, j, as_linear) * u * (1 - v) +
          lookup_texture(tex, ii, jj, as_linear) * u * v;
+}
+YGL_D f4 eval_texture(const DTexture& tex, const f2& uv, bool as_linear, bool no_interpolation,
+    bool clamp_to_edge) {
+  return eval_texture_fetch(&tex, uv.x, uv.y, as_linear, no_interpolation, clamp_to_edge);
 }
 // eval_texture(scene, id, uv, as_linear), yocto_scene.cpp:167-171
 YGL_D_BIG f4 eval_texture(const DScene& scene, int texture, const f2& uv, bool as_linear) {
