@@ -160,6 +160,10 @@ def test_persistent_mode_matches_reference(ref, sampler):
     dict(YGL_SUSPEND="0", YGL_LONE="32", YGL_LONE_STEPS="40"),      # vote-free tail walk, parked after 40 steps
     dict(YGL_SUSPEND="0", YGL_LONE="0", YGL_FUSE="0"),              # plain drain, separate accumulate / generate kernels
     dict(YGL_FUSE="1", YGL_REFILL="4", YGL_NODE_REPS="1"),
+    # experimental shade-queue binning (off by default; written after the round's GPU budget was spent, so its first
+    # GPU run is this test: a failure here must not mask the rest of the suite)
+    pytest.param(dict(YGL_BIN="1", YGL_FUSE="0"), marks=pytest.mark.xfail(strict=False, reason="experimental, unmeasured")),
+    pytest.param(dict(YGL_BIN="1", YGL_FUSE="1"), marks=pytest.mark.xfail(strict=False, reason="experimental, unmeasured")),
 ])
 def test_tail_strategies_are_bit_exact(ref, env, tmp_path):
     """The extend kernel's tail strategies (parking stragglers for the next launch, the vote-free walk, its step

@@ -727,7 +727,7 @@ static int ensure_queues(ygl_context::Pipe& pipe, int lanes) {
   if (lanes <= pipe.queue_lanes) return YGL_OK;
   if (pipe.queue_mem) cudaFree(pipe.queue_mem), pipe.queue_mem = nullptr;
   size_t per = ((size_t)lanes + 63) & ~size_t(63);
-  CUDA_TRY(cudaMalloc((void**)&pipe.queue_mem, per * 6 * sizeof(int)));
+  CUDA_TRY(cudaMalloc((void**)&pipe.queue_mem, per * 8 * sizeof(int)));  // 6 queues + sorted copy + key bytes
   pipe.queue_lanes = lanes;
   return YGL_OK;
 }
@@ -756,6 +756,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   // The shading kernels can finish a path themselves (accumulate + next camera sample: two launches fewer per
   // iteration) - measured on B200: 4-6 % faster on small tiles (1/8 of C3, Cornell), 7 % slower on the full 1080p
   // frame, where the extra divergence in k_shade costs more than the launches. Hence: by lane count.
+  static const int bin_queue = getenv("YGL_BIN") ? atoi(getenv("YGL_BIN")) : 0;  // experimental, not yet measured
   static const int fuse_env = getenv("YGL_FUSE") ? atoi(getenv("YGL_FUSE")) : -1;
   const int        fuse     = fuse_env >= 0 ? fuse_env : (st.num_lanes <= 800000 ? 1 : 0);
   kp.fuse = fuse;
@@ -829,7 +830,18 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
           CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used + 1], s));
           ev_used += 2;
         }
-        launch_shade(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
+        if (bin_queue) {
+          // experimental: shade from a copy of the extend queue grouped by kind of work (see launch_bin_queue)
+          size_t per    = ((size_t)r.pipe->queue_lanes + 63) & ~size_t(63);
+          int*   sorted = r.pipe->queue_mem + 6 * per;
+          launch_bin_queue(s, r.light, ctx->dscene, st, r.q, r.parity, sorted, (unsigned char*)(r.pipe->queue_mem + 7 * per));
+          Queues qs         = r.q;
+          qs.ext[r.parity]  = sorted;
+          launch_shade(s, r.heavy, ctx->dscene, st, qs, kp, r.parity);
+          launches += 2;
+        } else {
+          launch_shade(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
+        }
         if (path_like) launch_lightpdf(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
         if (!fuse) launch_accumulate(s, r.light, ctx->dscene, st, r.q, kp, r.parity), launches++;
         r.first  = false;

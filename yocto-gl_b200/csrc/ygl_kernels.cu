@@ -63,6 +63,7 @@ __global__ void k_begin_iteration(Counters* c, int parity) {
   c->n_lpdf            = 0;
   c->n_acc             = 0;
   c->ext_head          = 0;
+  for (int k = 0; k < 16; k++) c->n_bin[k] = 0, c->bin_cursor[k] = 0;
 }
 
 __global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begin, int lane_lo, int lane_hi) {
@@ -899,6 +900,65 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
   if (tid == 0) atomicAdd(&c->shade_calls, (unsigned long long)n);
 }
 
+
+// ---- experimental (YGL_BIN=1): group the extend queue by the kind of shading work before k_shade ----
+// k_shade runs 8 of 32 lanes per instruction on C3 and is bound by instruction fetch: lanes of one warp hit different
+// materials or miss. Two small kernels copy the queue into `sorted`, grouped by key = miss | 1 + material type |
+// parked ray, so that a shading warp runs one kind of lane (the order inside a group is irrelevant: lanes are
+// independent). k_shade itself is unchanged - it is handed `sorted` as its input queue.
+constexpr int kBinMiss = 0, kBinParked = 9, kNumBins = 10;
+__global__ void __launch_bounds__(256) k_bin_count(DScene scene, PathState st, Queues q, int parity, unsigned char* keys) {
+  Counters* c   = q.counters;
+  const int n   = c->n_ext[parity];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    const int      i      = i0 + wl;
+    const bool     valid  = i < n;
+    const unsigned active = __ballot_sync(kFullWarp, valid);
+    if (!valid) continue;
+    const int  entry  = q.ext[parity][i];
+    const int  lane   = entry & kEntryLane;
+    const bool shadow = (entry & kEntryShadow) != 0;
+    int        key;
+    if (!(entry & kEntryPass) && __float_as_int(float4((shadow ? st.aux_uvd : st.hit_uvd)[lane]).w) == 2) {
+      key = kBinParked;
+    } else if (__float_as_int(float4(st.hit_uvd[lane]).w) == 0) {
+      key = kBinMiss;
+    } else {
+      const int2 ids = st.hit_ids[lane];
+      key            = 1 + (scene.materials[scene.instances[ids.x].material].type & 7);
+    }
+    keys[i]              = (unsigned char)key;
+    const unsigned peers = __match_any_sync(active, key);
+    if (wl == __ffs(peers) - 1) atomicAdd(&c->n_bin[key], __popc(peers));
+  }
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(Queues q, int parity, const unsigned char* keys, int* sorted) {
+  Counters* c   = q.counters;
+  const int n   = c->n_ext[parity];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
+  int       off[kNumBins];
+  for (int k = 0, sum = 0; k < kNumBins; k++) off[k] = sum, sum += c->n_bin[k];
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    const int      i      = i0 + wl;
+    const bool     valid  = i < n;
+    const unsigned active = __ballot_sync(kFullWarp, valid);
+    if (!valid) continue;
+    const int      key    = keys[i];
+    const unsigned peers  = __match_any_sync(active, key);
+    const int      leader = __ffs(peers) - 1;
+    int            base   = 0;
+    if (wl == leader) base = atomicAdd(&c->bin_cursor[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    int start = 0;
+    for (int k = 0; k < kNumBins; k++)
+      if (k == key) start = off[k];
+    sorted[start + base + __popc(peers & ((1u << wl) - 1u))] = q.ext[parity][i];
+  }
+}
+
 // ---- lightpdf: sample_lights_pdf for the pending direction, then the MIS weight, weight checks,
 // russian roulette and the loop increment (yocto_trace.cpp:532-536 / :573-576, :581-591) ----
 #ifndef YGL_LPDF_MINBLOCKS
@@ -1464,6 +1524,11 @@ void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Que
     k_shade<kSamplerPathMis><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
   else
     k_shade<kSamplerPath><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+}
+void launch_bin_queue(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity, int* sorted,
+    unsigned char* keys) {
+  k_bin_count<<<cfg.blocks, 256, 0, s>>>(scene, st, q, parity, keys);
+  k_bin_scatter<<<cfg.blocks, 256, 0, s>>>(q, parity, keys, sorted);
 }
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   k_lightpdf<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);

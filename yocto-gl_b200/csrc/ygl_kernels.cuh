@@ -101,6 +101,7 @@ struct Counters {
   int n_gen[2], n_ext[2], n_lpdf, n_acc;
   int done_lanes;  // lanes that finished all their samples
   int ext_head;    // work cursor of the persistent extend kernel (reset every iteration)
+  int n_bin[16], bin_cursor[16];  // shade-queue binning (experimental, YGL_BIN=1): entries per key / append cursors
   unsigned long long camera_samples, scene_rays, instance_rays, shade_calls;
 };
 
@@ -141,6 +142,10 @@ void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Qu
     unsigned long long* trav);
 void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+// experimental: copy the extend queue into `sorted`, grouped by (miss | material type | parked), so that the warps of
+// k_shade run one kind of lane each. keys: one byte per queue entry (scratch).
+void launch_bin_queue(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity, int* sorted,
+    unsigned char* keys);
 void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 // persistent mode: one launch renders samples [sample_begin, p.sample_end) of lanes [lane_lo, lane_hi)
 void launch_persistent(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p, int lane_lo,
