@@ -1,15 +1,18 @@
-// ygl_kernels.cu — the wavefront path tracer: sm_100a kernels linked by compacted lane queues.
+// ygl_kernels.cu — the path tracer's stages as device functions, and the two schedulers that drive them (sm_100a).
 //
-//   generate  (ray generation)        sample_camera                       yocto_trace.cpp:338, 1461-1468
-//   extend    (closest-hit traversal) intersect_scene_bvh                 yocto_bvh.cpp:554
-//   shade     (eval + sample)         trace_path / eyelight / falsecolor  yocto_trace.cpp:453, 1111, 1341
-//   lightpdf  (instance traversal)    sample_lights_pdf + MIS weight + RR yocto_trace.cpp:391, 532-590
-//   accumulate                        trace_sample tail                   yocto_trace.cpp:1469-1491
+//   generate_lane    (ray generation)        sample_camera                       yocto_trace.cpp:338, 1461-1468
+//   trace_stream     (closest-hit traversal) intersect_scene_bvh                 yocto_bvh.cpp:554  (ygl_traverse.cuh)
+//   shade_lane       (eval + sample)         trace_path / pathtest / naive / eyelight / diagram / furnace / falsecolor
+//   shade_multi                              trace_pathdirect / trace_pathmis    yocto_trace.cpp:599-950
+//   lightpdf_lane    (instance traversal)    sample_lights_pdf + MIS weight + RR yocto_trace.cpp:391, 532-590
+//   accumulate_lane                          trace_sample tail                   yocto_trace.cpp:1469-1491
 //
-// Every kernel is persistent-style: a fixed grid (multiple of the SM count) strides over the
-// queue whose length it reads from device memory, so the host never synchronises inside the
-// sample loop. Survivors are appended to the next queue with one atomicAdd per warp
-// (__ballot_sync + __popc + __shfl_sync). Compiled with -fmad=false: see ygl_math.cuh.
+// Wavefront scheduler (default): k_generate / k_extend / k_shade / k_lightpdf / k_accumulate, linked by compacted lane
+// queues. Every kernel is persistent-style: a fixed grid (multiple of the SM count) strides over the queue whose
+// length it reads from device memory, so the host never synchronises inside the sample loop. Survivors are appended
+// to the next queue with one atomicAdd per warp (__ballot_sync + __popc + __shfl_sync).
+// Persistent scheduler (opt-in): k_persistent, one resident kernel with SM-specialised stages linked by ticket ring
+// queues (see the block comment above it). Compiled with -fmad=false: see ygl_math.cuh.
 #include <algorithm>
 #include <cstdlib>
 
