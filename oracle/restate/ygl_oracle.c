@@ -13,8 +13,10 @@
  * intersect_scene_bvh / intersect_instance_bvh; sample_camera/eval_camera; eval_position / normals /
  * material for untextured scenes; constant environments; matte, glossy, reflective and gltfpbr lobes;
  * make_trace_lights, sample_lights, sample_lights_pdf for area lights and constant environments;
- * trace_path, trace_sample, trace_samples, trace_image. Textures, volumes and transmission lobes are
- * NOT restated (oracle_supported() says so; those paths are checked against oracle/_ref only).
+ * trace_path, trace_pathdirect, trace_pathmis, trace_pathtest, trace_naive, trace_eyelight, trace_diagram,
+ * trace_sample, trace_samples, trace_image. Textures, volumes, transmission lobes, opacity < 1, nocaustics, the
+ * tent filter and the furnace / falsecolor samplers are NOT restated (oracle_supported() / oracle_trace_image()
+ * say so; those paths are checked against oracle/_ref only).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this.
  */
@@ -725,6 +727,231 @@ static trace_result trace_path(const oracle_scene* sc, ray_t ray, rng_t* rng, co
   return r;
 }
 
+
+/* ---- the other samplers of get_trace_sampler_func (yocto_trace.cpp:1422-1438), restated for the scenes
+ * oracle_supported() admits: no textures, no volumes, opacity 1 (so the opacity and volume branches of the
+ * reference loops are not taken), nocaustics off. Same right-to-left draw order as trace_path above. ---- */
+static v3 eval_emission(const mpoint* m, v3 n, v3 o) { return dot(n, o) >= 0 ? m->emission : V3(0, 0, 0); } /* yocto_trace.cpp:166-170 */
+static int finish_bounce(v3* weight, int bounce, rng_t* rng) { /* weight check + russian roulette, :581-591; 0 = break */
+  if (zero3(*weight) || !finite3(*weight)) return 0;
+  if (bounce > 3) {
+    float rr = minf_((float)0.99, max3(*weight));
+    if (rand1f(rng) >= rr) return 0;
+    *weight = muls(*weight, 1 / rr);
+  }
+  return 1;
+}
+/* emission seen along a shadow ray, :667-677 / :874-886 */
+static v3 shadow_emission(const oracle_scene* sc, v3 position, v3 incoming, ygl_intersection* out) {
+  ray_t sr = {position, incoming, 1e-4f, FLT_MAX};
+  ygl_intersection is = intersect_scene(sc, sr, 0);
+  if (out) *out = is;
+  if (!is.hit) return eval_environment(sc, incoming);
+  v2 uv = {is.uv[0], is.uv[1]};
+  mpoint m = eval_material(sc, is.instance);
+  return eval_emission(&m, eval_shading_normal(sc, is.instance, is.element, uv, neg(incoming)), neg(incoming));
+}
+/* one-sample MIS next direction of trace_path / pathdirect / pathtest, :522-542. Returns 0 on `break`. */
+static int next_direction(const oracle_scene* sc, const mpoint* m, v3 position, v3 normal, v3 outgoing, rng_t* rng,
+    v3* incoming, v3* weight, int delta_zero_check) {
+  if (!is_delta(m)) {
+    if (rand1f(rng) < 0.5f) { v2 rn = rand2f(rng); float rnl = rand1f(rng); *incoming = sample_bsdfcos(m, normal, outgoing, rnl, rn); }
+    else { v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng); *incoming = sample_lights(sc, position, rl, rel, ruv); }
+    if (zero3(*incoming)) return 0;
+    *weight = mul(*weight, divs(eval_bsdfcos(m, normal, outgoing, *incoming),
+        0.5f * sample_bsdfcos_pdf(m, normal, outgoing, *incoming) + 0.5f * sample_lights_pdf(sc, position, *incoming)));
+  } else {
+    (void)rand1f(rng);
+    *incoming = reflect(outgoing, up_of(normal, outgoing));
+    if (delta_zero_check && zero3(*incoming)) return 0;
+    *weight = mul(*weight, divs(eval_delta(m, normal, outgoing, *incoming), sample_delta_pdf(m, normal, outgoing, *incoming)));
+  }
+  return 1;
+}
+static trace_result trace_pathdirect(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :599-767 */
+  v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
+  int hit = 0, next_emission = 1;
+  for (int bounce = 0; bounce < p->bounces; bounce++) {
+    ygl_intersection isec = intersect_scene(sc, ray, 0);
+    if (!isec.hit) {
+      if ((bounce > 0 || !p->envhidden) && next_emission) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
+      break;
+    }
+    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+    mpoint m = eval_material(sc, isec.instance);
+    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+    if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+    if (!is_delta(&m)) {
+      v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng);
+      v3 dl = sample_lights(sc, position, rl, rel, ruv);
+      float pdf = sample_lights_pdf(sc, position, dl);
+      v3 bsdfcos = eval_bsdfcos(&m, normal, outgoing, dl);
+      if (!zero3(bsdfcos) && pdf > 0) {
+        v3 emission = shadow_emission(sc, position, dl, 0);
+        radiance = add(radiance, divs(mul(mul(weight, bsdfcos), emission), pdf));
+      }
+      next_emission = 0;
+    } else {
+      next_emission = 1;
+    }
+    v3 incoming;
+    if (!next_direction(sc, &m, position, normal, outgoing, rng, &incoming, &weight, 1)) break;
+    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
+    if (!finish_bounce(&weight, bounce, rng)) break;
+  }
+  trace_result r = {radiance, hit, hit_albedo, hit_normal};
+  return r;
+}
+static float mis_heuristic(float this_pdf, float other_pdf) { return (this_pdf * this_pdf) / (this_pdf * this_pdf + other_pdf * other_pdf); } /* :785-788 */
+static trace_result trace_pathmis(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :770-950 */
+  v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
+  int hit = 0, next_emission = 1;
+  ygl_intersection next_intersection = no_hit();
+  for (int bounce = 0; bounce < p->bounces; bounce++) {
+    ygl_intersection isec = next_emission ? intersect_scene(sc, ray, 0) : next_intersection;
+    if (!isec.hit) {
+      if ((bounce > 0 || !p->envhidden) && next_emission) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
+      break;
+    }
+    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+    mpoint m = eval_material(sc, isec.instance);
+    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+    if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+    v3 incoming = V3(0, 0, 0);
+    if (!is_delta(&m)) {
+      for (int k = 0; k < 2; k++) { /* sample_light : {true, false} */
+        int sample_light = k == 0;
+        if (sample_light) { v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng); incoming = sample_lights(sc, position, rl, rel, ruv); }
+        else { v2 rn = rand2f(rng); float rnl = rand1f(rng); incoming = sample_bsdfcos(&m, normal, outgoing, rnl, rn); }
+        if (zero3(incoming)) break;
+        v3 bsdfcos = eval_bsdfcos(&m, normal, outgoing, incoming);
+        float light_pdf = sample_lights_pdf(sc, position, incoming);
+        float bsdf_pdf = sample_bsdfcos_pdf(&m, normal, outgoing, incoming);
+        float mis_weight = sample_light ? mis_heuristic(light_pdf, bsdf_pdf) / light_pdf : mis_heuristic(bsdf_pdf, light_pdf) / bsdf_pdf;
+        if (!zero3(bsdfcos) && mis_weight != 0) {
+          ygl_intersection sh;
+          v3 emission = shadow_emission(sc, position, incoming, &sh);
+          if (!sample_light) next_intersection = sh;
+          radiance = add(radiance, muls(mul(mul(weight, bsdfcos), emission), mis_weight));
+        }
+      }
+      weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming), sample_bsdfcos_pdf(&m, normal, outgoing, incoming)));
+      next_emission = 0;
+    } else {
+      (void)rand1f(rng);
+      incoming = reflect(outgoing, up_of(normal, outgoing));
+      weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+      next_emission = 1;
+    }
+    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
+    if (!finish_bounce(&weight, bounce, rng)) break;
+  }
+  trace_result r = {radiance, hit, hit_albedo, hit_normal};
+  return r;
+}
+static trace_result trace_pathtest(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :953-1029 */
+  v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
+  int hit = 0;
+  for (int bounce = 0; bounce < p->bounces; bounce++) {
+    ygl_intersection isec = intersect_scene(sc, ray, 0);
+    if (!isec.hit) {
+      if (bounce > 0 || !p->envhidden) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
+      break;
+    }
+    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+    mpoint m = eval_material(sc, isec.instance);
+    m.type = YGL_MATERIAL_MATTE; /* :981, after eval_material: the roughness keeps the original type's clamp */
+    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+    radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+    v3 incoming;
+    if (!next_direction(sc, &m, position, normal, outgoing, rng, &incoming, &weight, 0)) break;
+    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
+    if (!finish_bounce(&weight, bounce, rng)) break;
+  }
+  trace_result r = {radiance, hit, hit_albedo, hit_normal};
+  return r;
+}
+static trace_result trace_naive(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :1032-1108 */
+  v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
+  int hit = 0;
+  for (int bounce = 0; bounce < p->bounces; bounce++) {
+    ygl_intersection isec = intersect_scene(sc, ray, 0);
+    if (!isec.hit) {
+      if (bounce > 0 || !p->envhidden) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
+      break;
+    }
+    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+    mpoint m = eval_material(sc, isec.instance);
+    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+    radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+    v3 incoming;
+    if (m.roughness != 0) {
+      v2 rn = rand2f(rng); float rnl = rand1f(rng);
+      incoming = sample_bsdfcos(&m, normal, outgoing, rnl, rn);
+      if (zero3(incoming)) break;
+      weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming), sample_bsdfcos_pdf(&m, normal, outgoing, incoming)));
+    } else {
+      (void)rand1f(rng);
+      incoming = (m.type == YGL_MATERIAL_REFLECTIVE) ? reflect(outgoing, up_of(normal, outgoing)) : V3(0, 0, 0);
+      if (zero3(incoming)) break;
+      weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+    }
+    if (!finish_bounce(&weight, bounce, rng)) break;
+    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
+  }
+  trace_result r = {radiance, hit, hit_albedo, hit_normal};
+  return r;
+}
+/* trace_eyelight (:1111-1175) and trace_diagram (:1178-1244): they differ only on a miss */
+static trace_result trace_eyelight_like(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p, int diagram) {
+  v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
+  int hit = 0, nb = p->bounces > 4 ? p->bounces : 4;
+  for (int bounce = 0; bounce < nb; bounce++) {
+    ygl_intersection isec = intersect_scene(sc, ray, 0);
+    if (!isec.hit) {
+      if (diagram) { radiance = add(radiance, mul(weight, V3(1, 1, 1))); hit = 1; }
+      else if (bounce > 0 || !p->envhidden) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
+      break;
+    }
+    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+    mpoint m = eval_material(sc, isec.instance);
+    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+    v3 incoming = outgoing;
+    radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+    radiance = add(radiance, mul(muls(weight, pif), eval_bsdfcos(&m, normal, outgoing, incoming)));
+    if (!is_delta(&m)) break;
+    (void)rand1f(rng);
+    incoming = reflect(outgoing, up_of(normal, outgoing));
+    if (zero3(incoming)) break;
+    weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+    if (zero3(weight) || !finite3(weight)) break;
+    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
+  }
+  trace_result r = {radiance, hit, hit_albedo, hit_normal};
+  return r;
+}
+static trace_result trace_any(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* get_trace_sampler_func, :1422-1438 */
+  switch (p->sampler) {
+    case YGL_SAMPLER_PATH: return trace_path(sc, ray, rng, p);
+    case YGL_SAMPLER_PATHDIRECT: return trace_pathdirect(sc, ray, rng, p);
+    case YGL_SAMPLER_PATHMIS: return trace_pathmis(sc, ray, rng, p);
+    case YGL_SAMPLER_PATHTEST: return trace_pathtest(sc, ray, rng, p);
+    case YGL_SAMPLER_NAIVE: return trace_naive(sc, ray, rng, p);
+    case YGL_SAMPLER_EYELIGHT: return trace_eyelight_like(sc, ray, rng, p, 0);
+    default: return trace_eyelight_like(sc, ray, rng, p, 1); /* YGL_SAMPLER_DIAGRAM (the caller filters the rest) */
+  }
+}
+
 /* ---- make_trace_state + trace_samples + trace_image, yocto_trace.cpp:1461-1619 ---- */
 void oracle_state_size(const ygl_scene_desc* d, const ygl_trace_params* p, int* w, int* h) {
   const ygl_camera* c = &d->cameras[p->camera];
@@ -738,9 +965,11 @@ void oracle_state_rngs(const ygl_trace_params* p, int w, int h, uint64_t* rngs) 
     rngs[2 * i] = r.state; rngs[2 * i + 1] = r.inc;
   }
 }
-/* image: w*h*4 floats. Only the path sampler is restated. Returns 0 on success. */
+/* image: w*h*4 floats. Restated samplers: path, pathdirect, pathmis, pathtest, naive, eyelight, diagram (furnace and
+ * falsecolor are not). Returns 0 on success, -1 for anything outside the restatement. */
 int oracle_trace_image(const oracle_scene* sc, const ygl_trace_params* p, int nsamples, float* image) {
-  if (p->sampler != YGL_SAMPLER_PATH || !oracle_supported(sc->d) || p->tentfilter) return -1;
+  if (p->sampler == YGL_SAMPLER_FURNACE || p->sampler == YGL_SAMPLER_FALSECOLOR || p->sampler < 0 ||
+      p->sampler > YGL_SAMPLER_FALSECOLOR || !oracle_supported(sc->d) || p->tentfilter || p->nocaustics) return -1;
   int w, h; oracle_state_size(sc->d, p, &w, &h);
   uint64_t* rngs = malloc(sizeof(uint64_t) * 2 * (size_t)w * h);
   oracle_state_rngs(p, w, h, rngs);
@@ -754,7 +983,7 @@ int oracle_trace_image(const oracle_scene* sc, const ygl_trace_params* p, int ns
       v2 luv = rand2f(&rng), puv = rand2f(&rng); /* right-to-left: luv first */
       v2 uv = {(i + puv.x) / w, (j + puv.y) / h};
       ray_t ray = eval_camera(cam, uv, sample_disk(luv));
-      trace_result r = trace_path(sc, ray, &rng, p);
+      trace_result r = trace_any(sc, ray, &rng, p);
       v3 rad = r.radiance;
       if (!finite3(rad)) rad = V3(0, 0, 0);
       if (max3(rad) > p->clamp) rad = muls(rad, p->clamp / max3(rad));

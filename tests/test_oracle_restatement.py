@@ -77,6 +77,30 @@ def test_images_bit_identical_to_reference(ref, name, kw):
     assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes()
 
 
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_PATHDIRECT, abi.SAMPLER_PATHMIS, abi.SAMPLER_PATHTEST, abi.SAMPLER_NAIVE,
+                                     abi.SAMPLER_EYELIGHT, abi.SAMPLER_DIAGRAM])
+@pytest.mark.parametrize("name,kw", [
+    ("cornell", dict(resolution=56, samples=3, bounces=6)),
+    ("instanced3", dict(resolution=56, samples=2, bounces=8, envhidden=1)),
+])
+def test_other_samplers_bit_identical_to_reference(ref, name, kw, sampler):
+    """The restated trace_pathdirect / pathmis / pathtest / naive / eyelight / diagram (yocto_trace.cpp:599-1244)
+    against the reference's own, on the scenes the restatement supports."""
+    scene = SCENES[name]()
+    mine = restate.OracleScene(scene)
+    assert mine.supported()
+    p = abi.trace_params(sampler=sampler, **kw)
+    assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes()
+
+
+def test_restatement_rejects_what_it_does_not_cover():
+    scene = SCENES["cornell"]()
+    mine = restate.OracleScene(scene)
+    for kw in (dict(sampler=abi.SAMPLER_FURNACE), dict(sampler=abi.SAMPLER_FALSECOLOR), dict(nocaustics=1), dict(tentfilter=1)):
+        with pytest.raises(NotImplementedError):
+            mine.trace_image(abi.trace_params(resolution=16, samples=1, **kw))
+
+
 def test_golden_image_and_checksum():
     g = np.load(os.path.join(GOLDEN, "renders.npz"))
     scene = scenes.cornellbox()
