@@ -14,8 +14,8 @@
  * material for untextured scenes; constant environments; matte, glossy, reflective and gltfpbr lobes;
  * make_trace_lights, sample_lights, sample_lights_pdf for area lights and constant environments;
  * trace_path, trace_pathdirect, trace_pathmis, trace_pathtest, trace_naive, trace_eyelight, trace_diagram,
- * trace_sample, trace_samples, trace_image. Textures, volumes, transmission lobes, opacity < 1, nocaustics, the
- * tent filter and the furnace / falsecolor samplers are NOT restated (oracle_supported() / oracle_trace_image()
+ * trace_furnace, trace_falsecolor, trace_sample, trace_samples, trace_image. Textures, volumes, transmission lobes,
+ * opacity < 1, nocaustics and the tent filter are NOT restated (oracle_supported() / oracle_trace_image()
  * say so; those paths are checked against oracle/_ref only).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this.
@@ -940,6 +940,103 @@ static trace_result trace_eyelight_like(const oracle_scene* sc, ray_t ray, rng_t
   trace_result r = {radiance, hit, hit_albedo, hit_normal};
   return r;
 }
+
+/* ---- trace_furnace, yocto_trace.cpp:1247-1338 (opacity is 1 on supported scenes) ---- */
+static trace_result trace_furnace(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) {
+  v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
+  int hit = 0, in_volume = 0;
+  for (int bounce = 0; bounce < p->bounces; bounce++) {
+    if (bounce > 0 && !in_volume) { radiance = add(radiance, mul(weight, eval_environment(sc, ray.d))); break; }
+    ygl_intersection isec = intersect_scene(sc, ray, 0);
+    if (!isec.hit) {
+      if (bounce > 0 || !p->envhidden) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
+      break;
+    }
+    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+    v3 position = eval_position(sc, isec.instance, isec.element, uv); /* :1281: eval_position, not eval_shading_position */
+    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+    mpoint m = eval_material(sc, isec.instance);
+    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+    radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+    v3 incoming;
+    if (m.roughness != 0) {
+      v2 rn = rand2f(rng); float rnl = rand1f(rng);
+      incoming = sample_bsdfcos(&m, normal, outgoing, rnl, rn);
+      if (zero3(incoming)) break;
+      weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming), sample_bsdfcos_pdf(&m, normal, outgoing, incoming)));
+    } else {
+      (void)rand1f(rng);
+      incoming = (m.type == YGL_MATERIAL_REFLECTIVE) ? reflect(outgoing, up_of(normal, outgoing)) : V3(0, 0, 0);
+      if (zero3(incoming)) break;
+      weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+    }
+    if (!finish_bounce(&weight, bounce, rng)) break;
+    if (dot(normal, outgoing) * dot(normal, incoming) < 0) in_volume = !in_volume;
+    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
+  }
+  trace_result r = {radiance, hit, hit_albedo, hit_normal};
+  return r;
+}
+/* ---- trace_falsecolor, yocto_trace.cpp:1341-1419 ---- */
+static float srgb_to_rgb1(float srgb) { /* yocto_color.h:235-238: the threshold is a double literal */
+  return ((double)srgb <= 0.04045) ? srgb / 12.92f : powf((srgb + 0.055f) / (1.0f + 0.055f), 2.4f);
+}
+static v3 hashed_color(int id) { /* :1358-1362: std::hash<int> is the identity; rand3f draws x, y, z in order */
+  rng_t r = make_rng(961748941, (uint64_t)(size_t)id);
+  float x = rand1f(&r), y = rand1f(&r), z = rand1f(&r);
+  return V3(powf(0.5f + 0.5f * x, 2.2f), powf(0.5f + 0.5f * y, 2.2f), powf(0.5f + 0.5f * z, 2.2f));
+}
+static v2 eval_texcoord(const oracle_scene* sc, int instance, int e, v2 uv) { /* yocto_scene.cpp:369-391 */
+  const ygl_shape* s = &sc->d->shapes[sc->d->instances[instance].shape];
+  if (!s->num_texcoords) return uv;
+  const float* tc = s->texcoords;
+#define TC(i) V3(tc[2 * (i)], tc[2 * (i) + 1], 0)
+  v3 r = V3(0, 0, 0);
+  if (s->num_triangles) { const int32_t* t = s->triangles + 3 * e; r = interp_tri(TC(t[0]), TC(t[1]), TC(t[2]), uv); }
+  else if (s->num_quads) { const int32_t* q = s->quads + 4 * e; r = interp_quad(TC(q[0]), TC(q[1]), TC(q[2]), TC(q[3]), uv); }
+  else if (s->num_lines) { const int32_t* l = s->lines + 2 * e; r = add(muls(TC(l[0]), 1 - uv.x), muls(TC(l[1]), uv.x)); }
+  else if (s->num_points) r = TC(s->points[e]);
+#undef TC
+  v2 o = {r.x, r.y};
+  return o;
+}
+static trace_result trace_falsecolor(const oracle_scene* sc, ray_t ray, const ygl_trace_params* p) {
+  trace_result none = {V3(0, 0, 0), 0, V3(0, 0, 0), V3(0, 0, 0)};
+  ygl_intersection isec = intersect_scene(sc, ray, 0);
+  if (!isec.hit) return none;
+  v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+  v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+  v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+  v3 gnormal = eval_element_normal(sc, isec.instance, isec.element);
+  v2 texcoord = eval_texcoord(sc, isec.instance, isec.element, uv);
+  mpoint m = eval_material(sc, isec.instance);
+  float delta = is_delta(&m) ? 1.0f : 0.0f;
+  const ygl_instance* in = &sc->d->instances[isec.instance];
+  v3 result = V3(0, 0, 0);
+  switch (p->falsecolor) {
+    case 0: result = adds(muls(position, 0.5f), 0.5f); break;
+    case 1: result = adds(muls(normal, 0.5f), 0.5f); break;
+    case 2: result = dot(normal, neg(ray.d)) > 0 ? V3(0, 1, 0) : V3(1, 0, 0); break;
+    case 3: result = adds(muls(gnormal, 0.5f), 0.5f); break;
+    case 4: result = dot(gnormal, neg(ray.d)) > 0 ? V3(0, 1, 0) : V3(1, 0, 0); break;
+    case 5: result = V3(fmodf(texcoord.x, 1.0f), fmodf(texcoord.y, 1.0f), 0); break;
+    case 6: result = hashed_color(m.type); break;
+    case 7: result = m.color; break;
+    case 8: result = m.emission; break;
+    case 9: result = V3(m.roughness, m.roughness, m.roughness); break;
+    case 10: result = V3(m.opacity, m.opacity, m.opacity); break;
+    case 11: result = V3(m.metallic, m.metallic, m.metallic); break;
+    case 12: result = V3(delta, delta, delta); break;
+    case 13: result = hashed_color(isec.instance); break;
+    case 14: result = hashed_color(in->shape); break;
+    case 15: result = hashed_color(in->material); break;
+    case 16: result = hashed_color(isec.element); break;
+    case 17: { if (zero3(m.emission)) m.emission = V3(0.2f, 0.2f, 0.2f); result = muls(m.emission, absf_(dot(neg(ray.d), normal))); } break;
+    default: result = V3(0, 0, 0);
+  }
+  trace_result r = {V3(srgb_to_rgb1(result.x), srgb_to_rgb1(result.y), srgb_to_rgb1(result.z)), 1, m.color, normal};
+  return r;
+}
 static trace_result trace_any(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* get_trace_sampler_func, :1422-1438 */
   switch (p->sampler) {
     case YGL_SAMPLER_PATH: return trace_path(sc, ray, rng, p);
@@ -948,7 +1045,9 @@ static trace_result trace_any(const oracle_scene* sc, ray_t ray, rng_t* rng, con
     case YGL_SAMPLER_PATHTEST: return trace_pathtest(sc, ray, rng, p);
     case YGL_SAMPLER_NAIVE: return trace_naive(sc, ray, rng, p);
     case YGL_SAMPLER_EYELIGHT: return trace_eyelight_like(sc, ray, rng, p, 0);
-    default: return trace_eyelight_like(sc, ray, rng, p, 1); /* YGL_SAMPLER_DIAGRAM (the caller filters the rest) */
+    case YGL_SAMPLER_DIAGRAM: return trace_eyelight_like(sc, ray, rng, p, 1);
+    case YGL_SAMPLER_FURNACE: return trace_furnace(sc, ray, rng, p);
+    default: return trace_falsecolor(sc, ray, p); /* YGL_SAMPLER_FALSECOLOR (the caller filters unknown values) */
   }
 }
 
@@ -965,11 +1064,9 @@ void oracle_state_rngs(const ygl_trace_params* p, int w, int h, uint64_t* rngs) 
     rngs[2 * i] = r.state; rngs[2 * i + 1] = r.inc;
   }
 }
-/* image: w*h*4 floats. Restated samplers: path, pathdirect, pathmis, pathtest, naive, eyelight, diagram (furnace and
- * falsecolor are not). Returns 0 on success, -1 for anything outside the restatement. */
+/* image: w*h*4 floats, any of the nine samplers. Returns 0 on success, -1 for anything outside the restatement. */
 int oracle_trace_image(const oracle_scene* sc, const ygl_trace_params* p, int nsamples, float* image) {
-  if (p->sampler == YGL_SAMPLER_FURNACE || p->sampler == YGL_SAMPLER_FALSECOLOR || p->sampler < 0 ||
-      p->sampler > YGL_SAMPLER_FALSECOLOR || !oracle_supported(sc->d) || p->tentfilter || p->nocaustics) return -1;
+  if (p->sampler < 0 || p->sampler > YGL_SAMPLER_FALSECOLOR || !oracle_supported(sc->d) || p->tentfilter || p->nocaustics) return -1;
   int w, h; oracle_state_size(sc->d, p, &w, &h);
   uint64_t* rngs = malloc(sizeof(uint64_t) * 2 * (size_t)w * h);
   oracle_state_rngs(p, w, h, rngs);

@@ -78,14 +78,14 @@ def test_images_bit_identical_to_reference(ref, name, kw):
 
 
 @pytest.mark.parametrize("sampler", [abi.SAMPLER_PATHDIRECT, abi.SAMPLER_PATHMIS, abi.SAMPLER_PATHTEST, abi.SAMPLER_NAIVE,
-                                     abi.SAMPLER_EYELIGHT, abi.SAMPLER_DIAGRAM])
+                                     abi.SAMPLER_EYELIGHT, abi.SAMPLER_DIAGRAM, abi.SAMPLER_FURNACE])
 @pytest.mark.parametrize("name,kw", [
     ("cornell", dict(resolution=56, samples=3, bounces=6)),
     ("instanced3", dict(resolution=56, samples=2, bounces=8, envhidden=1)),
 ])
 def test_other_samplers_bit_identical_to_reference(ref, name, kw, sampler):
-    """The restated trace_pathdirect / pathmis / pathtest / naive / eyelight / diagram (yocto_trace.cpp:599-1244)
-    against the reference's own, on the scenes the restatement supports."""
+    """The restated trace_pathdirect / pathmis / pathtest / naive / eyelight / diagram / furnace
+    (yocto_trace.cpp:599-1338) against the reference's own, on the scenes the restatement supports."""
     scene = SCENES[name]()
     mine = restate.OracleScene(scene)
     assert mine.supported()
@@ -93,10 +93,19 @@ def test_other_samplers_bit_identical_to_reference(ref, name, kw, sampler):
     assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes()
 
 
+@pytest.mark.parametrize("fc", range(18))
+def test_falsecolor_bit_identical_to_reference(ref, fc):
+    """trace_falsecolor (yocto_trace.cpp:1341-1419), every trace_falsecolor_type."""
+    for name in ("cornell_quads", "instanced3"):
+        scene = SCENES[name]()
+        p = abi.trace_params(resolution=48, samples=1, sampler=abi.SAMPLER_FALSECOLOR, falsecolor=fc)
+        assert restate.OracleScene(scene).trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), name
+
+
 def test_restatement_rejects_what_it_does_not_cover():
     scene = SCENES["cornell"]()
     mine = restate.OracleScene(scene)
-    for kw in (dict(sampler=abi.SAMPLER_FURNACE), dict(sampler=abi.SAMPLER_FALSECOLOR), dict(nocaustics=1), dict(tentfilter=1)):
+    for kw in (dict(nocaustics=1), dict(tentfilter=1), dict(sampler=9)):
         with pytest.raises(NotImplementedError):
             mine.trace_image(abi.trace_params(resolution=16, samples=1, **kw))
 
