@@ -14,8 +14,8 @@
  * material for untextured scenes; constant environments; matte, glossy, reflective and gltfpbr lobes;
  * make_trace_lights, sample_lights, sample_lights_pdf for area lights and constant environments;
  * trace_path, trace_pathdirect, trace_pathmis, trace_pathtest, trace_naive, trace_eyelight, trace_diagram,
- * trace_furnace, trace_falsecolor, trace_sample, trace_samples, trace_image. Textures, volumes, transmission lobes,
- * opacity < 1, nocaustics and the tent filter are NOT restated (oracle_supported() / oracle_trace_image()
+ * trace_furnace, trace_falsecolor, trace_sample, trace_samples, trace_image, incl. opacity pass-through, nocaustics
+ * and the tent filter. Textures, vertex colors, volumes and transmission lobes are NOT restated (oracle_supported() / oracle_trace_image()
  * say so; those paths are checked against oracle/_ref only).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this.
@@ -407,7 +407,6 @@ int oracle_supported(const ygl_scene_desc* d) {
     if (m->type != YGL_MATERIAL_MATTE && m->type != YGL_MATERIAL_GLOSSY && m->type != YGL_MATERIAL_REFLECTIVE &&
         m->type != YGL_MATERIAL_GLTFPBR) return 0;
     if (m->emission_tex >= 0 || m->color_tex >= 0 || m->roughness_tex >= 0 || m->scattering_tex >= 0 || m->normal_tex >= 0) return 0;
-    if (m->opacity < 1) return 0;
   }
   for (int i = 0; i < d->num_environments; i++) if (d->environments[i].emission_tex >= 0) return 0;
   /* texcoords only feed texture lookups, which are excluded above; vertex colors change eval_material */
@@ -685,12 +684,27 @@ static ray_t eval_camera(const ygl_camera* c, v2 iuv, v2 luv) {
   return r;
 }
 
+
+/* opacity pass-through of the sampler loops (e.g. yocto_trace.cpp:505-510): the rng is drawn only when opacity < 1 */
+#define OPACITY_PASS(m, position)                                                  \
+  if ((m).opacity < 1 && rand1f(rng) >= (m).opacity) {                               \
+    if (opbounce++ > 128) break;                                                   \
+    ray.o = add(position, muls(ray.d, 1e-2f)); ray.tmin = 1e-4f; ray.tmax = FLT_MAX; \
+    bounce -= 1;                                                                   \
+    continue;                                                                      \
+  }
+/* nocaustics roughness clamp (yocto_trace.cpp:496-500) */
+#define NOCAUSTICS(m)                                                \
+  if (p->nocaustics) {                                               \
+    max_roughness = maxf_((m).roughness, max_roughness);             \
+    (m).roughness = max_roughness;                                   \
+  }
 /* ---- trace_path, yocto_trace.cpp:453-596. g++ evaluates call arguments right to left: the rand2f of
  * sample_bsdfcos / sample_lights is drawn before the rand1f's. ---- */
 typedef struct { v3 radiance; int hit; v3 albedo, normal; } trace_result;
 static trace_result trace_path(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) {
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0;
+  int hit = 0, opbounce = 0; float max_roughness = 0.0f;
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     ygl_intersection isec = intersect_scene(sc, ray, 0);
     if (!isec.hit) {
@@ -701,6 +715,8 @@ static trace_result trace_path(const oracle_scene* sc, ray_t ray, rng_t* rng, co
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
     mpoint m = eval_material(sc, isec.instance);
+    NOCAUSTICS(m)
+    OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     radiance = add(radiance, mul(weight, dot(normal, outgoing) >= 0 ? m.emission : V3(0, 0, 0)));
     v3 incoming;
@@ -729,8 +745,7 @@ static trace_result trace_path(const oracle_scene* sc, ray_t ray, rng_t* rng, co
 
 
 /* ---- the other samplers of get_trace_sampler_func (yocto_trace.cpp:1422-1438), restated for the scenes
- * oracle_supported() admits: no textures, no volumes, opacity 1 (so the opacity and volume branches of the
- * reference loops are not taken), nocaustics off. Same right-to-left draw order as trace_path above. ---- */
+ * oracle_supported() admits: no textures, no volumes (so the volume branches of the reference loops are not taken). Same right-to-left draw order as trace_path above. ---- */
 static v3 eval_emission(const mpoint* m, v3 n, v3 o) { return dot(n, o) >= 0 ? m->emission : V3(0, 0, 0); } /* yocto_trace.cpp:166-170 */
 static int finish_bounce(v3* weight, int bounce, rng_t* rng) { /* weight check + russian roulette, :581-591; 0 = break */
   if (zero3(*weight) || !finite3(*weight)) return 0;
@@ -770,7 +785,7 @@ static int next_direction(const oracle_scene* sc, const mpoint* m, v3 position, 
 }
 static trace_result trace_pathdirect(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :599-767 */
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0, next_emission = 1;
+  int hit = 0, next_emission = 1, opbounce = 0; float max_roughness = 0.0f;
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     ygl_intersection isec = intersect_scene(sc, ray, 0);
     if (!isec.hit) {
@@ -781,6 +796,8 @@ static trace_result trace_pathdirect(const oracle_scene* sc, ray_t ray, rng_t* r
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
     mpoint m = eval_material(sc, isec.instance);
+    NOCAUSTICS(m)
+    OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
     if (!is_delta(&m)) {
@@ -807,7 +824,7 @@ static trace_result trace_pathdirect(const oracle_scene* sc, ray_t ray, rng_t* r
 static float mis_heuristic(float this_pdf, float other_pdf) { return (this_pdf * this_pdf) / (this_pdf * this_pdf + other_pdf * other_pdf); } /* :785-788 */
 static trace_result trace_pathmis(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :770-950 */
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0, next_emission = 1;
+  int hit = 0, next_emission = 1, opbounce = 0; float max_roughness = 0.0f;
   ygl_intersection next_intersection = no_hit();
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     ygl_intersection isec = next_emission ? intersect_scene(sc, ray, 0) : next_intersection;
@@ -819,6 +836,8 @@ static trace_result trace_pathmis(const oracle_scene* sc, ray_t ray, rng_t* rng,
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
     mpoint m = eval_material(sc, isec.instance);
+    NOCAUSTICS(m)
+    OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
     v3 incoming = V3(0, 0, 0);
@@ -879,7 +898,7 @@ static trace_result trace_pathtest(const oracle_scene* sc, ray_t ray, rng_t* rng
 }
 static trace_result trace_naive(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :1032-1108 */
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0;
+  int hit = 0, opbounce = 0;
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     ygl_intersection isec = intersect_scene(sc, ray, 0);
     if (!isec.hit) {
@@ -890,6 +909,7 @@ static trace_result trace_naive(const oracle_scene* sc, ray_t ray, rng_t* rng, c
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
     mpoint m = eval_material(sc, isec.instance);
+    OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
     v3 incoming;
@@ -913,7 +933,7 @@ static trace_result trace_naive(const oracle_scene* sc, ray_t ray, rng_t* rng, c
 /* trace_eyelight (:1111-1175) and trace_diagram (:1178-1244): they differ only on a miss */
 static trace_result trace_eyelight_like(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p, int diagram) {
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0, nb = p->bounces > 4 ? p->bounces : 4;
+  int hit = 0, opbounce = 0, nb = p->bounces > 4 ? p->bounces : 4;
   for (int bounce = 0; bounce < nb; bounce++) {
     ygl_intersection isec = intersect_scene(sc, ray, 0);
     if (!isec.hit) {
@@ -925,6 +945,7 @@ static trace_result trace_eyelight_like(const oracle_scene* sc, ray_t ray, rng_t
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
     mpoint m = eval_material(sc, isec.instance);
+    OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     v3 incoming = outgoing;
     radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
@@ -944,7 +965,7 @@ static trace_result trace_eyelight_like(const oracle_scene* sc, ray_t ray, rng_t
 /* ---- trace_furnace, yocto_trace.cpp:1247-1338 (opacity is 1 on supported scenes) ---- */
 static trace_result trace_furnace(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) {
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0, in_volume = 0;
+  int hit = 0, in_volume = 0, opbounce = 0;
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     if (bounce > 0 && !in_volume) { radiance = add(radiance, mul(weight, eval_environment(sc, ray.d))); break; }
     ygl_intersection isec = intersect_scene(sc, ray, 0);
@@ -956,6 +977,7 @@ static trace_result trace_furnace(const oracle_scene* sc, ray_t ray, rng_t* rng,
     v3 position = eval_position(sc, isec.instance, isec.element, uv); /* :1281: eval_position, not eval_shading_position */
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
     mpoint m = eval_material(sc, isec.instance);
+    OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
     v3 incoming;
@@ -1066,7 +1088,7 @@ void oracle_state_rngs(const ygl_trace_params* p, int w, int h, uint64_t* rngs) 
 }
 /* image: w*h*4 floats, any of the nine samplers. Returns 0 on success, -1 for anything outside the restatement. */
 int oracle_trace_image(const oracle_scene* sc, const ygl_trace_params* p, int nsamples, float* image) {
-  if (p->sampler < 0 || p->sampler > YGL_SAMPLER_FALSECOLOR || !oracle_supported(sc->d) || p->tentfilter || p->nocaustics) return -1;
+  if (p->sampler < 0 || p->sampler > YGL_SAMPLER_FALSECOLOR || !oracle_supported(sc->d)) return -1;
   int w, h; oracle_state_size(sc->d, p, &w, &h);
   uint64_t* rngs = malloc(sizeof(uint64_t) * 2 * (size_t)w * h);
   oracle_state_rngs(p, w, h, rngs);
@@ -1078,7 +1100,13 @@ int oracle_trace_image(const oracle_scene* sc, const ygl_trace_params* p, int ns
     rng_t rng = {rngs[2 * idx], rngs[2 * idx + 1]};
     for (int s = 0; s < nsamples; s++) {
       v2 luv = rand2f(&rng), puv = rand2f(&rng); /* right-to-left: luv first */
-      v2 uv = {(i + puv.x) / w, (j + puv.y) / h};
+      v2 fuv = puv;
+      if (p->tentfilter) { /* sample_camera, yocto_trace.cpp:345-357 */
+        const float width = 2.0f, offset = 0.5f;
+        fuv.x = width * (puv.x < 0.5f ? sqrtf(2 * puv.x) - 1 : 1 - sqrtf(2 - 2 * puv.x)) + offset;
+        fuv.y = width * (puv.y < 0.5f ? sqrtf(2 * puv.y) - 1 : 1 - sqrtf(2 - 2 * puv.y)) + offset;
+      }
+      v2 uv = {(i + fuv.x) / w, (j + fuv.y) / h};
       ray_t ray = eval_camera(cam, uv, sample_disk(luv));
       trace_result r = trace_any(sc, ray, &rng, p);
       v3 rad = r.radiance;

@@ -102,10 +102,26 @@ def test_falsecolor_bit_identical_to_reference(ref, fc):
         assert restate.OracleScene(scene).trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), name
 
 
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_PATH, abi.SAMPLER_PATHDIRECT, abi.SAMPLER_PATHMIS, abi.SAMPLER_NAIVE,
+                                     abi.SAMPLER_EYELIGHT, abi.SAMPLER_DIAGRAM, abi.SAMPLER_FURNACE])
+def test_opacity_nocaustics_tentfilter_bit_identical_to_reference(ref, sampler):
+    """Opacity pass-through (rng drawn only when opacity < 1, bounce not counted, <= 128 passes), the nocaustics
+    roughness clamp and the tent pixel filter, for every sampler that has them."""
+    scene = scenes.instanced_spheres(3)
+    for k, m in enumerate(scene.materials):
+        if k % 2 == 0 and not np.any(np.asarray(m["emission"])):
+            m["opacity"] = 0.35 + 0.2 * (k % 3)
+    mine = restate.OracleScene(scene)
+    assert mine.supported()
+    for extra in (dict(), dict(nocaustics=1, tentfilter=1, envhidden=1)):
+        p = abi.trace_params(resolution=56, samples=3, bounces=8, sampler=sampler, **extra)
+        assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), extra
+
+
 def test_restatement_rejects_what_it_does_not_cover():
     scene = SCENES["cornell"]()
     mine = restate.OracleScene(scene)
-    for kw in (dict(nocaustics=1), dict(tentfilter=1), dict(sampler=9)):
+    for kw in (dict(sampler=9), dict(sampler=-1)):
         with pytest.raises(NotImplementedError):
             mine.trace_image(abi.trace_params(resolution=16, samples=1, **kw))
 
