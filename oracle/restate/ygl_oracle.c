@@ -404,8 +404,7 @@ void oracle_scene_destroy(oracle_scene* sc) {
 int oracle_supported(const ygl_scene_desc* d) {
   for (int i = 0; i < d->num_materials; i++) {
     const ygl_material* m = &d->materials[i];
-    if (m->type != YGL_MATERIAL_MATTE && m->type != YGL_MATERIAL_GLOSSY && m->type != YGL_MATERIAL_REFLECTIVE &&
-        m->type != YGL_MATERIAL_GLTFPBR) return 0;
+    if (m->type < YGL_MATERIAL_MATTE || m->type > YGL_MATERIAL_GLTFPBR) return 0;
     if (m->emission_tex >= 0 || m->color_tex >= 0 || m->roughness_tex >= 0 || m->scattering_tex >= 0 || m->normal_tex >= 0) return 0;
   }
   for (int i = 0; i < d->num_environments; i++) if (d->environments[i].emission_tex >= 0) return 0;
@@ -478,7 +477,7 @@ static v3 eval_shading_position(const oracle_scene* sc, int instance, int e, v2 
   if (s->num_points) return P(s, s->points[e]); /* object space: reference quirk */
   return V3(0, 0, 0);
 }
-typedef struct { int type; v3 emission, color; float opacity, roughness, metallic, ior; } mpoint;
+typedef struct { int type; v3 emission, color; float opacity, roughness, metallic, ior; v3 density, scattering; float scanisotropy, trdepth; } mpoint;
 static mpoint eval_material(const oracle_scene* sc, int instance) { /* :531-581, all textures absent -> factor 1 */
   const ygl_material* m = &sc->d->materials[sc->d->instances[instance].material];
   mpoint p; p.type = m->type;
@@ -487,8 +486,15 @@ static mpoint eval_material(const oracle_scene* sc, int instance) { /* :531-581,
   p.color = mul(mul(V3(m->color[0], m->color[1], m->color[2]), one), one);
   p.opacity = m->opacity * 1.0f * 1.0f; p.metallic = m->metallic * 1.0f;
   p.roughness = m->roughness * 1.0f; p.roughness = p.roughness * p.roughness; p.ior = m->ior;
+  p.scattering = mul(V3(m->scattering[0], m->scattering[1], m->scattering[2]), one);
+  p.scanisotropy = m->scanisotropy; p.trdepth = m->trdepth;
+  if (p.type == YGL_MATERIAL_REFRACTIVE || p.type == YGL_MATERIAL_VOLUMETRIC || p.type == YGL_MATERIAL_SUBSURFACE) {
+    v3 c = vclamp(p.color, 0.0001f, 1.0f);
+    p.density = divs(neg(V3(logf(c.x), logf(c.y), logf(c.z))), p.trdepth);
+  } else p.density = V3(0, 0, 0);
   const float min_roughness = 0.03f * 0.03f;
   if (p.type == YGL_MATERIAL_MATTE || p.type == YGL_MATERIAL_GLTFPBR || p.type == YGL_MATERIAL_GLOSSY) p.roughness = clampf_(p.roughness, min_roughness, 1.0f);
+  else if (p.type == YGL_MATERIAL_VOLUMETRIC) p.roughness = 0;
   else if (p.roughness < min_roughness) p.roughness = 0;
   return p;
 }
@@ -563,8 +569,157 @@ static v3 sample_microfacet(float rough, v3 n, v2 rn) {
 static float sample_microfacet_pdf(float rough, v3 n, v3 h) { float c = dot(n, h); if (c < 0) return 0; return mf_distribution(rough, n, h) * c; }
 static int same_hemisphere(v3 n, v3 o, v3 i) { return dot(n, o) * dot(n, i) >= 0; }
 
+
+/* ---- transmission lobes, yocto_shading.h:791-1048, and refract (yocto_math.h:1339) ---- */
+static v3 refract_(v3 w, v3 n, float inv_eta) {
+  float cosine = dot(n, w), k = 1 + inv_eta * inv_eta * (cosine * cosine - 1);
+  if (k < 0) return V3(0, 0, 0);
+  return add(muls(neg(w), inv_eta), muls(n, inv_eta * cosine - sqrtf(k)));
+}
+static v3 ones_times(float a) { return V3(1 * a, 1 * a, 1 * a); }
+static v3 eval_transparent(v3 color, float ior, float rough, v3 n, v3 o, v3 i) { /* :791-812 */
+  v3 up = up_of(n, o);
+  if (dot(n, i) * dot(n, o) >= 0) {
+    v3 h = normalize(add(i, o));
+    float F = fresnel_dielectric(ior, h, o), D = mf_distribution(rough, up, h), G = mf_shadowing(rough, up, h, o, i);
+    return muls(divs(muls(muls(ones_times(F), D), G), 4 * dot(up, o) * dot(up, i)), absf_(dot(up, i)));
+  } else {
+    v3 refl = reflect(neg(i), up), h = normalize(add(refl, o));
+    float F = fresnel_dielectric(ior, h, o), D = mf_distribution(rough, up, h), G = mf_shadowing(rough, up, h, o, refl);
+    return muls(divs(muls(muls(muls(color, 1 - F), D), G), 4 * dot(up, o) * dot(up, refl)), absf_(dot(up, refl)));
+  }
+}
+static v3 sample_transparent(float ior, float rough, v3 n, v3 o, float rnl, v2 rn) { /* :815-832 */
+  v3 up = up_of(n, o), h = sample_microfacet(rough, up, rn);
+  if (rnl < fresnel_dielectric(ior, h, o)) {
+    v3 inc = reflect(o, h);
+    if (!same_hemisphere(up, o, inc)) return V3(0, 0, 0);
+    return inc;
+  } else {
+    v3 refl = reflect(o, h), inc = neg(reflect(refl, up));
+    if (same_hemisphere(up, o, inc)) return V3(0, 0, 0);
+    return inc;
+  }
+}
+static float sample_transparent_pdf(float ior, float rough, v3 n, v3 o, v3 i) { /* :835-849 */
+  v3 up = up_of(n, o);
+  if (dot(n, i) * dot(n, o) >= 0) {
+    v3 h = normalize(add(i, o));
+    return fresnel_dielectric(ior, h, o) * sample_microfacet_pdf(rough, up, h) / (4 * absf_(dot(o, h)));
+  } else {
+    v3 refl = reflect(neg(i), up), h = normalize(add(refl, o));
+    float d = (1 - fresnel_dielectric(ior, h, o)) * sample_microfacet_pdf(rough, up, h);
+    return d / (4 * absf_(dot(o, h)));
+  }
+}
+static v3 eval_transparent_delta(v3 color, float ior, v3 n, v3 o, v3 i) { /* :852-862 */
+  v3 up = up_of(n, o);
+  if (dot(n, i) * dot(n, o) >= 0) return ones_times(fresnel_dielectric(ior, up, o));
+  return muls(color, 1 - fresnel_dielectric(ior, up, o));
+}
+static v3 sample_transparent_delta(float ior, v3 n, v3 o, float rnl) { /* :865-872 */
+  v3 up = up_of(n, o);
+  if (rnl < fresnel_dielectric(ior, up, o)) return reflect(o, up);
+  return neg(o);
+}
+static float sample_transparent_delta_pdf(float ior, v3 n, v3 o, v3 i) { /* :875-881 */
+  v3 up = up_of(n, o);
+  if (dot(n, i) * dot(n, o) >= 0) return fresnel_dielectric(ior, up, o);
+  return 1 - fresnel_dielectric(ior, up, o);
+}
+/* g++ -O2 expands pow(x, 2.0f) to x * x (no libm call): yocto_shading.h:907,952 */
+static float sqr_(float a) { return a * a; }
+static v3 eval_refractive(float ior, float rough, v3 n, v3 o, v3 i) { /* :884-911 */
+  int entering = dot(n, o) >= 0; v3 up = entering ? n : neg(n); float rel = entering ? ior : (1 / ior);
+  if (dot(n, i) * dot(n, o) >= 0) {
+    v3 h = normalize(add(i, o));
+    float F = fresnel_dielectric(rel, h, o), D = mf_distribution(rough, up, h), G = mf_shadowing(rough, up, h, o, i);
+    return muls(divs(muls(muls(ones_times(F), D), G), absf_(4 * dot(n, o) * dot(n, i))), absf_(dot(n, i)));
+  } else {
+    v3 h = muls(neg(normalize(add(muls(i, rel), o))), entering ? 1.0f : -1.0f);
+    float F = fresnel_dielectric(rel, h, o), D = mf_distribution(rough, up, h), G = mf_shadowing(rough, up, h, o, i);
+    v3 a = ones_times(absf_((dot(o, h) * dot(i, h)) / (dot(o, n) * dot(i, n))));
+    return muls(divs(muls(muls(muls(a, 1 - F), D), G), sqr_(rel * dot(h, i) + dot(h, o))), absf_(dot(n, i)));
+  }
+}
+static v3 sample_refractive(float ior, float rough, v3 n, v3 o, float rnl, v2 rn) { /* :914-932 */
+  int entering = dot(n, o) >= 0; v3 up = entering ? n : neg(n);
+  v3 h = sample_microfacet(rough, up, rn);
+  if (rnl < fresnel_dielectric(entering ? ior : (1 / ior), h, o)) {
+    v3 inc = reflect(o, h);
+    if (!same_hemisphere(up, o, inc)) return V3(0, 0, 0);
+    return inc;
+  } else {
+    v3 inc = refract_(o, h, entering ? (1 / ior) : ior);
+    if (same_hemisphere(up, o, inc)) return V3(0, 0, 0);
+    return inc;
+  }
+}
+static float sample_refractive_pdf(float ior, float rough, v3 n, v3 o, v3 i) { /* :935-957 */
+  int entering = dot(n, o) >= 0; v3 up = entering ? n : neg(n); float rel = entering ? ior : (1 / ior);
+  if (dot(n, i) * dot(n, o) >= 0) {
+    v3 h = normalize(add(i, o));
+    return fresnel_dielectric(rel, h, o) * sample_microfacet_pdf(rough, up, h) / (4 * absf_(dot(o, h)));
+  } else {
+    v3 h = muls(neg(normalize(add(muls(i, rel), o))), entering ? 1.0f : -1.0f);
+    return (1 - fresnel_dielectric(rel, h, o)) * sample_microfacet_pdf(rough, up, h) * absf_(dot(h, i)) / sqr_(rel * dot(h, i) + dot(h, o));
+  }
+}
+static int ior_is_one(float ior) { return (double)absf_(ior - 1) < 1e-3; } /* the literal is a double, :961 */
+static v3 eval_refractive_delta(float ior, v3 n, v3 o, v3 i) { /* :960-975 */
+  if (ior_is_one(ior)) return dot(n, i) * dot(n, o) <= 0 ? V3(1, 1, 1) : V3(0, 0, 0);
+  int entering = dot(n, o) >= 0; v3 up = entering ? n : neg(n); float rel = entering ? ior : (1 / ior);
+  if (dot(n, i) * dot(n, o) >= 0) return ones_times(fresnel_dielectric(rel, up, o));
+  return muls(ones_times(1 / (rel * rel)), 1 - fresnel_dielectric(rel, up, o));
+}
+static v3 sample_refractive_delta(float ior, v3 n, v3 o, float rnl) { /* :978-989 */
+  if (ior_is_one(ior)) return neg(o);
+  int entering = dot(n, o) >= 0; v3 up = entering ? n : neg(n); float rel = entering ? ior : (1 / ior);
+  if (rnl < fresnel_dielectric(rel, up, o)) return reflect(o, up);
+  return refract_(o, up, 1 / rel);
+}
+static float sample_refractive_delta_pdf(float ior, v3 n, v3 o, v3 i) { /* :992-1005 */
+  if (ior_is_one(ior)) return dot(n, i) * dot(n, o) < 0 ? 1.0f : 0.0f;
+  int entering = dot(n, o) >= 0; v3 up = entering ? n : neg(n); float rel = entering ? ior : (1 / ior);
+  if (dot(n, i) * dot(n, o) >= 0) return fresnel_dielectric(rel, up, o);
+  return 1 - fresnel_dielectric(rel, up, o);
+}
+/* ---- volumes, yocto_shading.h:1056-1111 ---- */
+static v3 vexp_(v3 a) { return V3(expf(a.x), expf(a.y), expf(a.z)); }
+static v3 eval_transmittance(v3 density, float distance) { return vexp_(muls(neg(density), distance)); }
+static float sample_transmittance(v3 density, float max_distance, float rl, float rd) {
+  int channel = clampi_((int)(rl * 3), 0, 2);
+  float dc = comp(density, channel);
+  float distance = (dc == 0) ? FLT_MAX : -logf(1 - rd) / dc;
+  return minf_(distance, max_distance);
+}
+static float sample_transmittance_pdf(v3 density, float distance, float max_distance) {
+  if (distance < max_distance) { v3 t = mul(density, vexp_(muls(neg(density), distance))); return (t.x + t.y + t.z) / 3; }
+  v3 t = vexp_(muls(neg(density), max_distance)); return (t.x + t.y + t.z) / 3;
+}
+static float eval_phasefunction(float g, v3 o, v3 i) {
+  float cosine = -dot(o, i), denom = 1 + g * g - 2 * g * cosine;
+  return (1 - g * g) / (4 * pif * denom * sqrtf(denom));
+}
+static v3 sample_phasefunction(float g, v3 o, v2 rn) {
+  float cos_theta;
+  if (absf_(g) < 1e-3f) cos_theta = 1 - 2 * rn.y;
+  else { float square = (1 - g * g) / (1 + g - 2 * g * rn.y); cos_theta = (1 + g * g - square * square) / (2 * g); }
+  float sin_theta = sqrtf(maxf_(0.0f, 1 - cos_theta * cos_theta)), phi = 2 * pif * rn.x;
+  m3 b = basis_fromz(neg(o));
+  return m3_mul(&b, V3(sin_theta * cosf(phi), sin_theta * sinf(phi), cos_theta));
+}
+typedef struct { v3 density, scattering; float scanisotropy; } vsdf_t;
+static v3 eval_scattering(const vsdf_t* v, v3 o, v3 i) { if (zero3(v->density)) return V3(0, 0, 0); return muls(mul(v->scattering, v->density), eval_phasefunction(v->scanisotropy, o, i)); }
+static v3 sample_scattering(const vsdf_t* v, v3 o, v2 rn) { if (zero3(v->density)) return V3(0, 0, 0); return sample_phasefunction(v->scanisotropy, o, rn); }
+static float sample_scattering_pdf(const vsdf_t* v, v3 o, v3 i) { if (zero3(v->density)) return 0; return eval_phasefunction(v->scanisotropy, o, i); }
+static int is_volumetric_type(int t) { return t == YGL_MATERIAL_REFRACTIVE || t == YGL_MATERIAL_VOLUMETRIC || t == YGL_MATERIAL_SUBSURFACE; } /* yocto_scene.cpp:257-261 */
+
 static v3 eval_bsdfcos(const mpoint* m, v3 n, v3 o, v3 i) { /* yocto_trace.cpp:173-198 */
   if (m->roughness == 0) return V3(0, 0, 0);
+  if (m->type == YGL_MATERIAL_TRANSPARENT) return eval_transparent(m->color, m->ior, m->roughness, n, o, i);
+  if (m->type == YGL_MATERIAL_REFRACTIVE || m->type == YGL_MATERIAL_SUBSURFACE) return eval_refractive(m->ior, m->roughness, n, o, i);
+  if (m->type == YGL_MATERIAL_VOLUMETRIC) return V3(0, 0, 0);
   if (dot(n, i) * dot(n, o) <= 0) return V3(0, 0, 0);
   v3 up = up_of(n, o);
   if (m->type == YGL_MATERIAL_MATTE) return muls(divs(m->color, pif), absf_(dot(n, i)));
@@ -589,6 +744,8 @@ static v3 eval_bsdfcos(const mpoint* m, v3 n, v3 o, v3 i) { /* yocto_trace.cpp:1
 }
 static v3 sample_bsdfcos(const mpoint* m, v3 n, v3 o, float rnl, v2 rn) { /* yocto_trace.cpp:221-246 */
   if (m->roughness == 0) return V3(0, 0, 0);
+  if (m->type == YGL_MATERIAL_TRANSPARENT) return sample_transparent(m->ior, m->roughness, n, o, rnl, rn);
+  if (m->type == YGL_MATERIAL_REFRACTIVE || m->type == YGL_MATERIAL_SUBSURFACE) return sample_refractive(m->ior, m->roughness, n, o, rnl, rn);
   v3 up = up_of(n, o);
   if (m->type == YGL_MATERIAL_MATTE) return sample_hemisphere_cos(up, rn);
   int specular;
@@ -607,6 +764,9 @@ static v3 sample_bsdfcos(const mpoint* m, v3 n, v3 o, float rnl, v2 rn) { /* yoc
 }
 static float sample_bsdfcos_pdf(const mpoint* m, v3 n, v3 o, v3 i) { /* yocto_trace.cpp:266-291 */
   if (m->roughness == 0) return 0;
+  if (m->type == YGL_MATERIAL_TRANSPARENT) return sample_transparent_pdf(m->ior, m->roughness, n, o, i);
+  if (m->type == YGL_MATERIAL_REFRACTIVE || m->type == YGL_MATERIAL_SUBSURFACE) return sample_refractive_pdf(m->ior, m->roughness, n, o, i);
+  if (m->type == YGL_MATERIAL_VOLUMETRIC) return 0;
   if (dot(n, i) * dot(n, o) <= 0) return 0;
   v3 up = up_of(n, o);
   if (m->type == YGL_MATERIAL_MATTE) return sample_hemisphere_cos_pdf(up, i);
@@ -617,16 +777,42 @@ static float sample_bsdfcos_pdf(const mpoint* m, v3 n, v3 o, v3 i) { /* yocto_tr
   else { v3 refl = lerp3(eta_to_reflectivity(V3(m->ior, m->ior, m->ior)), m->color, m->metallic); v3 f = fresnel_schlick(refl, up, o); F = (f.x + f.y + f.z) / 3; }
   return F * sample_microfacet_pdf(m->roughness, up, h) / (4 * absf_(dot(o, h))) + (1 - F) * sample_hemisphere_cos_pdf(up, i);
 }
-static int is_delta(const mpoint* m) { return m->type == YGL_MATERIAL_REFLECTIVE && m->roughness == 0; }
-/* delta reflective, yocto_shading.h:693-712 */
-static v3 eval_delta(const mpoint* m, v3 n, v3 o, v3 i) {
-  if (m->roughness != 0 || m->type != YGL_MATERIAL_REFLECTIVE) return V3(0, 0, 0);
-  if (dot(n, i) * dot(n, o) <= 0) return V3(0, 0, 0);
-  return fresnel_conductor(reflectivity_to_eta(m->color), V3(0, 0, 0), up_of(n, o), o);
+static int is_delta(const mpoint* m) { /* yocto_scene.cpp:263-271 */
+  return (m->type == YGL_MATERIAL_REFLECTIVE && m->roughness == 0) || (m->type == YGL_MATERIAL_REFRACTIVE && m->roughness == 0) ||
+         (m->type == YGL_MATERIAL_TRANSPARENT && m->roughness == 0) || m->type == YGL_MATERIAL_VOLUMETRIC;
 }
-static float sample_delta_pdf(const mpoint* m, v3 n, v3 o, v3 i) {
-  if (m->roughness != 0 || m->type != YGL_MATERIAL_REFLECTIVE) return 0;
-  return (dot(n, i) * dot(n, o) <= 0) ? 0.0f : 1.0f;
+/* delta lobes: reflective yocto_shading.h:693-712, transparent :852-881, refractive :960-1005, passthrough :1028-1048 */
+static v3 eval_delta(const mpoint* m, v3 n, v3 o, v3 i) { /* yocto_trace.cpp:200-219 */
+  if (m->roughness != 0) return V3(0, 0, 0);
+  switch (m->type) {
+    case YGL_MATERIAL_REFLECTIVE:
+      if (dot(n, i) * dot(n, o) <= 0) return V3(0, 0, 0);
+      return fresnel_conductor(reflectivity_to_eta(m->color), V3(0, 0, 0), up_of(n, o), o);
+    case YGL_MATERIAL_TRANSPARENT: return eval_transparent_delta(m->color, m->ior, n, o, i);
+    case YGL_MATERIAL_REFRACTIVE: return eval_refractive_delta(m->ior, n, o, i);
+    case YGL_MATERIAL_VOLUMETRIC: return (dot(n, i) * dot(n, o) >= 0) ? V3(0, 0, 0) : V3(1, 1, 1);
+    default: return V3(0, 0, 0);
+  }
+}
+static v3 sample_delta(const mpoint* m, v3 n, v3 o, float rnl) { /* yocto_trace.cpp:248-264 */
+  if (m->roughness != 0) return V3(0, 0, 0);
+  switch (m->type) {
+    case YGL_MATERIAL_REFLECTIVE: return reflect(o, up_of(n, o));
+    case YGL_MATERIAL_TRANSPARENT: return sample_transparent_delta(m->ior, n, o, rnl);
+    case YGL_MATERIAL_REFRACTIVE: return sample_refractive_delta(m->ior, n, o, rnl);
+    case YGL_MATERIAL_VOLUMETRIC: return neg(o);
+    default: return V3(0, 0, 0);
+  }
+}
+static float sample_delta_pdf(const mpoint* m, v3 n, v3 o, v3 i) { /* yocto_trace.cpp:293-310 */
+  if (m->roughness != 0) return 0;
+  switch (m->type) {
+    case YGL_MATERIAL_REFLECTIVE: return (dot(n, i) * dot(n, o) <= 0) ? 0.0f : 1.0f;
+    case YGL_MATERIAL_TRANSPARENT: return sample_transparent_delta_pdf(m->ior, n, o, i);
+    case YGL_MATERIAL_REFRACTIVE: return sample_refractive_delta_pdf(m->ior, n, o, i);
+    case YGL_MATERIAL_VOLUMETRIC: return (dot(n, i) * dot(n, o) >= 0) ? 0.0f : 1.0f;
+    default: return 0;
+  }
 }
 
 /* ---- lights, yocto_trace.cpp:361-443 ---- */
@@ -699,39 +885,84 @@ static ray_t eval_camera(const ygl_camera* c, v2 iuv, v2 luv) {
     max_roughness = maxf_((m).roughness, max_roughness);             \
     (m).roughness = max_roughness;                                   \
   }
+
+/* participating media of the path samplers (e.g. yocto_trace.cpp:476-488, 545-579): the reference's volume stack never
+ * holds more than one entry, so it is a slot. Draw order of sample_transmittance's arguments (g++): rd, then rl. */
+#define VOLUME_TRANSMITTANCE                                                                              \
+  int in_volume = 0;                                                                                      \
+  if (has_volume) {                                                                                       \
+    float rd_ = rand1f(rng);                                                                              \
+    float rl_ = rand1f(rng);                                                                              \
+    float dist_ = sample_transmittance(vsdf.density, isec.distance, rl_, rd_);                            \
+    weight = mul(weight, divs(eval_transmittance(vsdf.density, dist_),                                    \
+                             sample_transmittance_pdf(vsdf.density, dist_, isec.distance)));             \
+    in_volume     = dist_ < isec.distance;                                                                \
+    isec.distance = dist_;                                                                                \
+  }
+#define VOLUME_STACK_UPDATE                                                                                         \
+  if (is_volumetric_type(sc->d->materials[sc->d->instances[isec.instance].material].type) &&                        \
+      dot(normal, outgoing) * dot(normal, incoming) < 0) {                                                          \
+    if (!has_volume) {                                                                                              \
+      mpoint vm = eval_material(sc, isec.instance);                                                                 \
+      vsdf.density = vm.density; vsdf.scattering = vm.scattering; vsdf.scanisotropy = vm.scanisotropy;             \
+      has_volume = 1;                                                                                               \
+    } else {                                                                                                        \
+      has_volume = 0;                                                                                               \
+    }                                                                                                               \
+  }
+/* next direction of a scattering event inside the medium (:557-572): phase function or lights, one-sample MIS */
+static v3 sample_volume_direction(const oracle_scene* sc, const vsdf_t* vsdf, v3 position, v3 outgoing, rng_t* rng) {
+  if (rand1f(rng) < 0.5f) { v2 rn = rand2f(rng); (void)rand1f(rng); return sample_scattering(vsdf, outgoing, rn); }
+  v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng);
+  return sample_lights(sc, position, rl, rel, ruv);
+}
+static v3 volume_weight(const oracle_scene* sc, const vsdf_t* vsdf, v3 position, v3 outgoing, v3 incoming) { /* :574-576 */
+  return divs(eval_scattering(vsdf, outgoing, incoming),
+      0.5f * sample_scattering_pdf(vsdf, outgoing, incoming) + 0.5f * sample_lights_pdf(sc, position, incoming));
+}
 /* ---- trace_path, yocto_trace.cpp:453-596. g++ evaluates call arguments right to left: the rand2f of
  * sample_bsdfcos / sample_lights is drawn before the rand1f's. ---- */
 typedef struct { v3 radiance; int hit; v3 albedo, normal; } trace_result;
 static trace_result trace_path(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) {
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0, opbounce = 0; float max_roughness = 0.0f;
+  int hit = 0, opbounce = 0, has_volume = 0; float max_roughness = 0.0f;
+  vsdf_t vsdf = {{0, 0, 0}, {0, 0, 0}, 0};
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     ygl_intersection isec = intersect_scene(sc, ray, 0);
     if (!isec.hit) {
       if (bounce > 0 || !p->envhidden) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
       break;
     }
-    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
-    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
-    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-    mpoint m = eval_material(sc, isec.instance);
-    NOCAUSTICS(m)
-    OPACITY_PASS(m, position)
-    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
-    radiance = add(radiance, mul(weight, dot(normal, outgoing) >= 0 ? m.emission : V3(0, 0, 0)));
-    v3 incoming;
-    if (!is_delta(&m)) {
-      if (rand1f(rng) < 0.5f) { v2 rn = rand2f(rng); float rnl = rand1f(rng); incoming = sample_bsdfcos(&m, normal, outgoing, rnl, rn); }
-      else { v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng); incoming = sample_lights(sc, position, rl, rel, ruv); }
-      if (zero3(incoming)) break;
-      weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming),
-          0.5f * sample_bsdfcos_pdf(&m, normal, outgoing, incoming) + 0.5f * sample_lights_pdf(sc, position, incoming)));
+    VOLUME_TRANSMITTANCE
+    if (!in_volume) {
+      v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+      v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+      v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+      mpoint m = eval_material(sc, isec.instance);
+      NOCAUSTICS(m)
+      OPACITY_PASS(m, position)
+      if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+      radiance = add(radiance, mul(weight, dot(normal, outgoing) >= 0 ? m.emission : V3(0, 0, 0)));
+      v3 incoming;
+      if (!is_delta(&m)) {
+        if (rand1f(rng) < 0.5f) { v2 rn = rand2f(rng); float rnl = rand1f(rng); incoming = sample_bsdfcos(&m, normal, outgoing, rnl, rn); }
+        else { v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng); incoming = sample_lights(sc, position, rl, rel, ruv); }
+        if (zero3(incoming)) break;
+        weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming),
+            0.5f * sample_bsdfcos_pdf(&m, normal, outgoing, incoming) + 0.5f * sample_lights_pdf(sc, position, incoming)));
+      } else {
+        incoming = sample_delta(&m, normal, outgoing, rand1f(rng));
+        weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+      }
+      VOLUME_STACK_UPDATE
+      ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     } else {
-      (void)rand1f(rng);
-      incoming = reflect(outgoing, up_of(normal, outgoing));
-      weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+      v3 outgoing = neg(ray.d), position = add(ray.o, muls(ray.d, isec.distance));
+      v3 incoming = sample_volume_direction(sc, &vsdf, position, outgoing, rng);
+      if (zero3(incoming)) break;
+      weight = mul(weight, volume_weight(sc, &vsdf, position, outgoing, incoming));
+      ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     }
-    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     if (zero3(weight) || !finite3(weight)) break;
     if (bounce > 3) {
       float rr = minf_((float)0.99, max3(weight));
@@ -776,8 +1007,7 @@ static int next_direction(const oracle_scene* sc, const mpoint* m, v3 position, 
     *weight = mul(*weight, divs(eval_bsdfcos(m, normal, outgoing, *incoming),
         0.5f * sample_bsdfcos_pdf(m, normal, outgoing, *incoming) + 0.5f * sample_lights_pdf(sc, position, *incoming)));
   } else {
-    (void)rand1f(rng);
-    *incoming = reflect(outgoing, up_of(normal, outgoing));
+    *incoming = sample_delta(m, normal, outgoing, rand1f(rng));
     if (delta_zero_check && zero3(*incoming)) return 0;
     *weight = mul(*weight, divs(eval_delta(m, normal, outgoing, *incoming), sample_delta_pdf(m, normal, outgoing, *incoming)));
   }
@@ -785,37 +1015,48 @@ static int next_direction(const oracle_scene* sc, const mpoint* m, v3 position, 
 }
 static trace_result trace_pathdirect(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :599-767 */
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0, next_emission = 1, opbounce = 0; float max_roughness = 0.0f;
+  int hit = 0, next_emission = 1, opbounce = 0, has_volume = 0; float max_roughness = 0.0f;
+  vsdf_t vsdf = {{0, 0, 0}, {0, 0, 0}, 0};
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     ygl_intersection isec = intersect_scene(sc, ray, 0);
     if (!isec.hit) {
       if ((bounce > 0 || !p->envhidden) && next_emission) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
       break;
     }
-    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
-    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
-    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-    mpoint m = eval_material(sc, isec.instance);
-    NOCAUSTICS(m)
-    OPACITY_PASS(m, position)
-    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
-    if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
-    if (!is_delta(&m)) {
-      v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng);
-      v3 dl = sample_lights(sc, position, rl, rel, ruv);
-      float pdf = sample_lights_pdf(sc, position, dl);
-      v3 bsdfcos = eval_bsdfcos(&m, normal, outgoing, dl);
-      if (!zero3(bsdfcos) && pdf > 0) {
-        v3 emission = shadow_emission(sc, position, dl, 0);
-        radiance = add(radiance, divs(mul(mul(weight, bsdfcos), emission), pdf));
+    VOLUME_TRANSMITTANCE
+    if (!in_volume) {
+      v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+      v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+      v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+      mpoint m = eval_material(sc, isec.instance);
+      NOCAUSTICS(m)
+      OPACITY_PASS(m, position)
+      if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+      if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+      if (!is_delta(&m)) {
+        v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng);
+        v3 dl = sample_lights(sc, position, rl, rel, ruv);
+        float pdf = sample_lights_pdf(sc, position, dl);
+        v3 bsdfcos = eval_bsdfcos(&m, normal, outgoing, dl);
+        if (!zero3(bsdfcos) && pdf > 0) {
+          v3 emission = shadow_emission(sc, position, dl, 0);
+          radiance = add(radiance, divs(mul(mul(weight, bsdfcos), emission), pdf));
+        }
+        next_emission = 0;
+      } else {
+        next_emission = 1;
       }
-      next_emission = 0;
+      v3 incoming;
+      if (!next_direction(sc, &m, position, normal, outgoing, rng, &incoming, &weight, 1)) break;
+      VOLUME_STACK_UPDATE
+      ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     } else {
-      next_emission = 1;
+      v3 outgoing = neg(ray.d), position = add(ray.o, muls(ray.d, isec.distance));
+      v3 incoming = sample_volume_direction(sc, &vsdf, position, outgoing, rng);
+      if (zero3(incoming)) break;
+      weight = mul(weight, volume_weight(sc, &vsdf, position, outgoing, incoming));
+      ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     }
-    v3 incoming;
-    if (!next_direction(sc, &m, position, normal, outgoing, rng, &incoming, &weight, 1)) break;
-    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     if (!finish_bounce(&weight, bounce, rng)) break;
   }
   trace_result r = {radiance, hit, hit_albedo, hit_normal};
@@ -824,7 +1065,8 @@ static trace_result trace_pathdirect(const oracle_scene* sc, ray_t ray, rng_t* r
 static float mis_heuristic(float this_pdf, float other_pdf) { return (this_pdf * this_pdf) / (this_pdf * this_pdf + other_pdf * other_pdf); } /* :785-788 */
 static trace_result trace_pathmis(const oracle_scene* sc, ray_t ray, rng_t* rng, const ygl_trace_params* p) { /* :770-950 */
   v3 radiance = V3(0, 0, 0), weight = V3(1, 1, 1), hit_albedo = V3(0, 0, 0), hit_normal = V3(0, 0, 0);
-  int hit = 0, next_emission = 1, opbounce = 0; float max_roughness = 0.0f;
+  int hit = 0, next_emission = 1, opbounce = 0, has_volume = 0; float max_roughness = 0.0f;
+  vsdf_t vsdf = {{0, 0, 0}, {0, 0, 0}, 0};
   ygl_intersection next_intersection = no_hit();
   for (int bounce = 0; bounce < p->bounces; bounce++) {
     ygl_intersection isec = next_emission ? intersect_scene(sc, ray, 0) : next_intersection;
@@ -832,41 +1074,50 @@ static trace_result trace_pathmis(const oracle_scene* sc, ray_t ray, rng_t* rng,
       if ((bounce > 0 || !p->envhidden) && next_emission) radiance = add(radiance, mul(weight, eval_environment(sc, ray.d)));
       break;
     }
-    v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
-    v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
-    v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-    mpoint m = eval_material(sc, isec.instance);
-    NOCAUSTICS(m)
-    OPACITY_PASS(m, position)
-    if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
-    if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
-    v3 incoming = V3(0, 0, 0);
-    if (!is_delta(&m)) {
-      for (int k = 0; k < 2; k++) { /* sample_light : {true, false} */
-        int sample_light = k == 0;
-        if (sample_light) { v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng); incoming = sample_lights(sc, position, rl, rel, ruv); }
-        else { v2 rn = rand2f(rng); float rnl = rand1f(rng); incoming = sample_bsdfcos(&m, normal, outgoing, rnl, rn); }
-        if (zero3(incoming)) break;
-        v3 bsdfcos = eval_bsdfcos(&m, normal, outgoing, incoming);
-        float light_pdf = sample_lights_pdf(sc, position, incoming);
-        float bsdf_pdf = sample_bsdfcos_pdf(&m, normal, outgoing, incoming);
-        float mis_weight = sample_light ? mis_heuristic(light_pdf, bsdf_pdf) / light_pdf : mis_heuristic(bsdf_pdf, light_pdf) / bsdf_pdf;
-        if (!zero3(bsdfcos) && mis_weight != 0) {
-          ygl_intersection sh;
-          v3 emission = shadow_emission(sc, position, incoming, &sh);
-          if (!sample_light) next_intersection = sh;
-          radiance = add(radiance, muls(mul(mul(weight, bsdfcos), emission), mis_weight));
+    VOLUME_TRANSMITTANCE
+    if (!in_volume) {
+      v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
+      v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
+      v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
+      mpoint m = eval_material(sc, isec.instance);
+      NOCAUSTICS(m)
+      OPACITY_PASS(m, position)
+      if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
+      if (next_emission) radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
+      v3 incoming = V3(0, 0, 0);
+      if (!is_delta(&m)) {
+        for (int k = 0; k < 2; k++) { /* sample_light : {true, false} */
+          int sample_light = k == 0;
+          if (sample_light) { v2 ruv = rand2f(rng); float rel = rand1f(rng); float rl = rand1f(rng); incoming = sample_lights(sc, position, rl, rel, ruv); }
+          else { v2 rn = rand2f(rng); float rnl = rand1f(rng); incoming = sample_bsdfcos(&m, normal, outgoing, rnl, rn); }
+          if (zero3(incoming)) break;
+          v3 bsdfcos = eval_bsdfcos(&m, normal, outgoing, incoming);
+          float light_pdf = sample_lights_pdf(sc, position, incoming);
+          float bsdf_pdf = sample_bsdfcos_pdf(&m, normal, outgoing, incoming);
+          float mis_weight = sample_light ? mis_heuristic(light_pdf, bsdf_pdf) / light_pdf : mis_heuristic(bsdf_pdf, light_pdf) / bsdf_pdf;
+          if (!zero3(bsdfcos) && mis_weight != 0) {
+            ygl_intersection sh;
+            v3 emission = shadow_emission(sc, position, incoming, &sh);
+            if (!sample_light) next_intersection = sh;
+            radiance = add(radiance, muls(mul(mul(weight, bsdfcos), emission), mis_weight));
+          }
         }
+        weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming), sample_bsdfcos_pdf(&m, normal, outgoing, incoming)));
+        next_emission = 0;
+      } else {
+        incoming = sample_delta(&m, normal, outgoing, rand1f(rng));
+        weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+        next_emission = 1;
       }
-      weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming), sample_bsdfcos_pdf(&m, normal, outgoing, incoming)));
-      next_emission = 0;
+      VOLUME_STACK_UPDATE
+      ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     } else {
-      (void)rand1f(rng);
-      incoming = reflect(outgoing, up_of(normal, outgoing));
-      weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
+      v3 outgoing = neg(ray.d), position = add(ray.o, muls(ray.d, isec.distance));
+      v3 incoming = sample_volume_direction(sc, &vsdf, position, outgoing, rng); /* no zero check here, :921-928 */
       next_emission = 1;
+      weight = mul(weight, volume_weight(sc, &vsdf, position, outgoing, incoming));
+      ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     }
-    ray.o = position; ray.d = incoming; ray.tmin = 1e-4f; ray.tmax = FLT_MAX;
     if (!finish_bounce(&weight, bounce, rng)) break;
   }
   trace_result r = {radiance, hit, hit_albedo, hit_normal};
@@ -919,8 +1170,7 @@ static trace_result trace_naive(const oracle_scene* sc, ray_t ray, rng_t* rng, c
       if (zero3(incoming)) break;
       weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming), sample_bsdfcos_pdf(&m, normal, outgoing, incoming)));
     } else {
-      (void)rand1f(rng);
-      incoming = (m.type == YGL_MATERIAL_REFLECTIVE) ? reflect(outgoing, up_of(normal, outgoing)) : V3(0, 0, 0);
+      incoming = sample_delta(&m, normal, outgoing, rand1f(rng));
       if (zero3(incoming)) break;
       weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
     }
@@ -951,8 +1201,7 @@ static trace_result trace_eyelight_like(const oracle_scene* sc, ray_t ray, rng_t
     radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
     radiance = add(radiance, mul(muls(weight, pif), eval_bsdfcos(&m, normal, outgoing, incoming)));
     if (!is_delta(&m)) break;
-    (void)rand1f(rng);
-    incoming = reflect(outgoing, up_of(normal, outgoing));
+    incoming = sample_delta(&m, normal, outgoing, rand1f(rng));
     if (zero3(incoming)) break;
     weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
     if (zero3(weight) || !finite3(weight)) break;
@@ -987,8 +1236,7 @@ static trace_result trace_furnace(const oracle_scene* sc, ray_t ray, rng_t* rng,
       if (zero3(incoming)) break;
       weight = mul(weight, divs(eval_bsdfcos(&m, normal, outgoing, incoming), sample_bsdfcos_pdf(&m, normal, outgoing, incoming)));
     } else {
-      (void)rand1f(rng);
-      incoming = (m.type == YGL_MATERIAL_REFLECTIVE) ? reflect(outgoing, up_of(normal, outgoing)) : V3(0, 0, 0);
+      incoming = sample_delta(&m, normal, outgoing, rand1f(rng));
       if (zero3(incoming)) break;
       weight = mul(weight, divs(eval_delta(&m, normal, outgoing, incoming), sample_delta_pdf(&m, normal, outgoing, incoming)));
     }

@@ -118,6 +118,40 @@ def test_opacity_nocaustics_tentfilter_bit_identical_to_reference(ref, sampler):
         assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), extra
 
 
+def _transmissive_scene():
+    """instanced_spheres(3) with its non-emissive materials turned into every transmission / volume flavour."""
+    scene = scenes.instanced_spheres(3)
+    flavours = [
+        dict(type=abi.REFRACTIVE, roughness=0.0, ior=1.5, color=(0.9, 1.0, 0.9), trdepth=1.0),
+        dict(type=abi.TRANSPARENT, roughness=0.2, ior=1.5, color=(1.0, 0.9, 0.8)),
+        dict(type=abi.SUBSURFACE, roughness=0.2, ior=1.4, color=(0.9, 0.6, 0.5), scattering=(0.6, 0.4, 0.3),
+             scanisotropy=0.3, trdepth=0.2),
+        dict(type=abi.VOLUMETRIC, color=(0.7, 0.8, 0.9), scattering=(0.8, 0.8, 0.8), scanisotropy=-0.2, trdepth=0.6),
+        dict(type=abi.REFRACTIVE, roughness=0.15, ior=1.33, color=(0.8, 0.9, 1.0), scattering=(0.2, 0.2, 0.2), trdepth=0.5),
+        dict(type=abi.TRANSPARENT, roughness=0.0, ior=1.5, color=(0.9, 0.9, 1.0)),
+    ]
+    k = 0
+    for m in scene.materials:
+        if np.any(np.asarray(m["emission"])):
+            continue
+        for key, value in flavours[k % len(flavours)].items():
+            m[key] = value
+        k += 1
+    return scene
+
+
+@pytest.mark.parametrize("sampler", [abi.SAMPLER_PATH, abi.SAMPLER_PATHDIRECT, abi.SAMPLER_PATHMIS, abi.SAMPLER_PATHTEST,
+                                     abi.SAMPLER_NAIVE, abi.SAMPLER_EYELIGHT, abi.SAMPLER_DIAGRAM, abi.SAMPLER_FURNACE])
+def test_transmission_and_volumes_bit_identical_to_reference(ref, sampler):
+    """Transparent / refractive / subsurface / volumetric materials (rough and delta), the volume slot, transmittance
+    sampling and phase-function scattering of trace_path / pathdirect / pathmis, and the in_volume flag of furnace."""
+    scene = _transmissive_scene()
+    mine = restate.OracleScene(scene)
+    assert mine.supported()
+    p = abi.trace_params(resolution=64, samples=3, bounces=10, sampler=sampler)
+    assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes()
+
+
 def test_restatement_rejects_what_it_does_not_cover():
     scene = SCENES["cornell"]()
     mine = restate.OracleScene(scene)
