@@ -118,7 +118,7 @@ def test_opacity_nocaustics_tentfilter_bit_identical_to_reference(ref, sampler):
         assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), extra
 
 
-def _transmissive_scene():
+def _transmissive_scene(offset=0):
     """instanced_spheres(3) with its non-emissive materials turned into every transmission / volume flavour."""
     scene = scenes.instanced_spheres(3)
     flavours = [
@@ -134,7 +134,7 @@ def _transmissive_scene():
     for m in scene.materials:
         if np.any(np.asarray(m["emission"])):
             continue
-        for key, value in flavours[k % len(flavours)].items():
+        for key, value in flavours[(k + offset) % len(flavours)].items():
             m[key] = value
         k += 1
     return scene
@@ -145,11 +145,12 @@ def _transmissive_scene():
 def test_transmission_and_volumes_bit_identical_to_reference(ref, sampler):
     """Transparent / refractive / subsurface / volumetric materials (rough and delta), the volume slot, transmittance
     sampling and phase-function scattering of trace_path / pathdirect / pathmis, and the in_volume flag of furnace."""
-    scene = _transmissive_scene()
-    mine = restate.OracleScene(scene)
-    assert mine.supported()
-    p = abi.trace_params(resolution=64, samples=3, bounces=10, sampler=sampler)
-    assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes()
+    for offset in (0, 3):  # 5 non-emissive materials, 6 flavours: two rotations cover them all
+        scene = _transmissive_scene(offset)
+        mine = restate.OracleScene(scene)
+        assert mine.supported()
+        p = abi.trace_params(resolution=64, samples=3, bounces=10, sampler=sampler)
+        assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), offset
 
 
 def test_restatement_rejects_what_it_does_not_cover():
