@@ -10,13 +10,13 @@
  *
  * Coverage: PCG32 streams and the per-pixel seeding of make_trace_state; make_bvh (split_middle and
  * split_sah) for the two-level BVH; intersect_point/line/triangle/quad/bbox; intersect_shape_bvh /
- * intersect_scene_bvh / intersect_instance_bvh; sample_camera/eval_camera; eval_position / normals /
- * material for untextured scenes; constant environments; matte, glossy, reflective and gltfpbr lobes;
- * make_trace_lights, sample_lights, sample_lights_pdf for area lights and constant environments;
+ * intersect_scene_bvh / intersect_instance_bvh; sample_camera/eval_camera; eval_position / normals / texcoords /
+ * colors / normal maps / material; textures (bilinear, sRGB decode); environments; every lobe of yocto_shading.h the
+ * renderer uses; make_trace_lights, sample_lights, sample_lights_pdf for area lights and (textured) environments;
  * trace_path, trace_pathdirect, trace_pathmis, trace_pathtest, trace_naive, trace_eyelight, trace_diagram,
- * trace_furnace, trace_falsecolor, trace_sample, trace_samples, trace_image, incl. opacity pass-through, nocaustics
- * and the tent filter. Textures, vertex colors, volumes and transmission lobes are NOT restated (oracle_supported() / oracle_trace_image()
- * say so; those paths are checked against oracle/_ref only).
+ * trace_furnace, trace_falsecolor, trace_sample, trace_samples, trace_image, incl. opacity pass-through, nocaustics,
+ * the tent filter, transmission lobes, participating media, textures, vertex colors, normal maps and textured
+ * environments: the whole hot path of SURVEY.md 8a.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this.
  */
@@ -85,6 +85,12 @@ static fr3 frame_inverse(const fr3* a) {
   float det = dot(a->x, cross(a->y, a->z)), idt = 1 / det;
   m3    minv = {muls(V3(cyz.x, czx.x, cxy.x), idt), muls(V3(cyz.y, czx.y, cxy.y), idt), muls(V3(cyz.z, czx.z, cxy.z), idt)};
   fr3   r = {minv.x, minv.y, minv.z, neg(m3_mul(&minv, a->o))};
+  return r;
+}
+/* inverse(frame, non_rigid = false): transpose of the rotation, yocto_math.h:2114-2122 */
+static fr3 frame_inverse_rigid(const fr3* a) {
+  m3  minv = {V3(a->x.x, a->y.x, a->z.x), V3(a->x.y, a->y.y, a->z.y), V3(a->x.z, a->y.z, a->z.z)};
+  fr3 r = {minv.x, minv.y, minv.z, neg(m3_mul(&minv, a->o))};
   return r;
 }
 /* basis_fromz, yocto_math.h:1977-1986 */
@@ -390,6 +396,20 @@ oracle_scene* oracle_scene_create(const ygl_scene_desc* d, int highquality) {
     const ygl_environment* e = &d->environments[i];
     if (e->emission[0] == 0 && e->emission[1] == 0 && e->emission[2] == 0) continue;
     light_t* l = &sc->lights[sc->num_lights++]; l->instance = -1; l->environment = i; l->cdf = NULL; l->n = 0;
+    if (e->emission_tex >= 0) { /* make_trace_lights, yocto_trace.cpp:1562-1576: max(texel) * sin(theta), cumulative */
+      const ygl_texture* t = &d->textures[e->emission_tex];
+      l->n = t->width * t->height; l->cdf = malloc(sizeof(float) * (size_t)(l->n > 0 ? l->n : 1));
+      for (int idx = 0; idx < l->n; idx++) {
+        int ix = idx % t->width, iy = idx / t->width;
+        float th = (iy + 0.5f) * pif / t->height;
+        float v[4];
+        size_t k = 4 * ((size_t)iy * t->width + ix);
+        for (int c = 0; c < 4; c++) v[c] = t->pixelsf ? t->pixelsf[k + c] : t->pixelsb[k + c] / 255.0f;
+        float mx = maxf_(maxf_(maxf_(v[0], v[1]), v[2]), v[3]);
+        l->cdf[idx] = mx * sinf(th);
+        if (idx != 0) l->cdf[idx] += l->cdf[idx - 1];
+      }
+    }
   }
   return sc;
 }
@@ -400,16 +420,11 @@ void oracle_scene_destroy(oracle_scene* sc) {
   for (int i = 0; i < sc->num_lights; i++) free(sc->lights[i].cdf);
   free(sc->lights); free(sc);
 }
-/* 1 if every feature the scene uses is restated here */
+/* 1 if every feature the scene uses is restated here (all material types, textures, vertex colors, normal maps,
+ * textured environments: everything ygl_scene_desc can describe) */
 int oracle_supported(const ygl_scene_desc* d) {
-  for (int i = 0; i < d->num_materials; i++) {
-    const ygl_material* m = &d->materials[i];
-    if (m->type < YGL_MATERIAL_MATTE || m->type > YGL_MATERIAL_GLTFPBR) return 0;
-    if (m->emission_tex >= 0 || m->color_tex >= 0 || m->roughness_tex >= 0 || m->scattering_tex >= 0 || m->normal_tex >= 0) return 0;
-  }
-  for (int i = 0; i < d->num_environments; i++) if (d->environments[i].emission_tex >= 0) return 0;
-  /* texcoords only feed texture lookups, which are excluded above; vertex colors change eval_material */
-  for (int i = 0; i < d->num_shapes; i++) if (d->shapes[i].num_colors) return 0;
+  for (int i = 0; i < d->num_materials; i++)
+    if (d->materials[i].type < YGL_MATERIAL_MATTE || d->materials[i].type > YGL_MATERIAL_GLTFPBR) return 0;
   return 1;
 }
 void oracle_tree_size(const oracle_scene* sc, int shape, int* nn, int* np) {
@@ -460,11 +475,118 @@ static v3 eval_normal(const oracle_scene* sc, int instance, int e, v2 uv) { /* :
   if (s->num_points) return normalize(xf_vector(&f, normalize(N(s, s->points[e]))));
   return V3(0, 0, 0);
 }
+/* ---- textures, yocto_scene.cpp:111-171, yocto_color.h:235-238 ---- */
+typedef struct { float x, y, z, w; } v4;
+static v4 V4(float x, float y, float z, float w) { v4 r = {x, y, z, w}; return r; }
+static v4 add4(v4 a, v4 b) { return V4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+static v4 muls4(v4 a, float b) { return V4(a.x * b, a.y * b, a.z * b, a.w * b); }
+static float srgb_to_rgb1(float srgb) { /* yocto_color.h:235-238: the threshold is a double literal */
+  return ((double)srgb <= 0.04045) ? srgb / 12.92f : powf((srgb + 0.055f) / (1.0f + 0.055f), 2.4f);
+}
+static v4 lookup_texture(const ygl_texture* t, int i, int j, int as_linear) {
+  v4 c;
+  size_t k = 4 * ((size_t)j * t->width + i);
+  if (t->pixelsf) c = V4(t->pixelsf[k], t->pixelsf[k + 1], t->pixelsf[k + 2], t->pixelsf[k + 3]);
+  else c = V4(t->pixelsb[k] / 255.0f, t->pixelsb[k + 1] / 255.0f, t->pixelsb[k + 2] / 255.0f, t->pixelsb[k + 3] / 255.0f);
+  if (as_linear && !t->linear) return V4(srgb_to_rgb1(c.x), srgb_to_rgb1(c.y), srgb_to_rgb1(c.z), c.w);
+  return c;
+}
+static v4 eval_texture_raw(const ygl_texture* t, v2 uv, int as_linear, int no_interpolation, int clamp_to_edge) { /* :127-160 */
+  if (t->width == 0 || t->height == 0) return V4(0, 0, 0, 0);
+  int sx = t->width, sy = t->height;
+  float s_, t_;
+  if (clamp_to_edge) { s_ = clampf_(uv.x, 0.0f, 1.0f) * sx; t_ = clampf_(uv.y, 0.0f, 1.0f) * sy; }
+  else { s_ = fmodf(uv.x, 1.0f) * sx; if (s_ < 0) s_ += sx; t_ = fmodf(uv.y, 1.0f) * sy; if (t_ < 0) t_ += sy; }
+  int i = clampi_((int)s_, 0, sx - 1), j = clampi_((int)t_, 0, sy - 1);
+  int ii = (i + 1) % sx, jj = (j + 1) % sy;
+  float u = s_ - i, v = t_ - j;
+  if (no_interpolation) return lookup_texture(t, i, j, as_linear);
+  return add4(add4(add4(muls4(muls4(lookup_texture(t, i, j, as_linear), 1 - u), 1 - v),
+                        muls4(muls4(lookup_texture(t, i, jj, as_linear), 1 - u), v)),
+                   muls4(muls4(lookup_texture(t, ii, j, as_linear), u), 1 - v)),
+              muls4(muls4(lookup_texture(t, ii, jj, as_linear), u), v));
+}
+static v4 eval_texture(const oracle_scene* sc, int texture, v2 uv, int as_linear) { /* :167-171 */
+  if (texture < 0) return V4(1, 1, 1, 1);
+  const ygl_texture* t = &sc->d->textures[texture];
+  return eval_texture_raw(t, uv, as_linear, t->nearest != 0, t->clamp != 0);
+}
+static v2 eval_texcoord(const oracle_scene* sc, int instance, int e, v2 uv) { /* yocto_scene.cpp:369-391 */
+  const ygl_shape* s = &sc->d->shapes[sc->d->instances[instance].shape];
+  if (!s->num_texcoords) return uv;
+  const float* tc = s->texcoords;
+#define TC(i) V3(tc[2 * (i)], tc[2 * (i) + 1], 0)
+  v3 r = V3(0, 0, 0);
+  if (s->num_triangles) { const int32_t* t = s->triangles + 3 * e; r = interp_tri(TC(t[0]), TC(t[1]), TC(t[2]), uv); }
+  else if (s->num_quads) { const int32_t* q = s->quads + 4 * e; r = interp_quad(TC(q[0]), TC(q[1]), TC(q[2]), TC(q[3]), uv); }
+  else if (s->num_lines) { const int32_t* l = s->lines + 2 * e; r = add(muls(TC(l[0]), 1 - uv.x), muls(TC(l[1]), uv.x)); }
+  else if (s->num_points) r = TC(s->points[e]);
+#undef TC
+  v2 o = {r.x, r.y};
+  return o;
+}
+static v4 eval_color(const oracle_scene* sc, int instance, int e, v2 uv) { /* yocto_scene.cpp:394-416 */
+  const ygl_shape* s = &sc->d->shapes[sc->d->instances[instance].shape];
+  if (!s->num_colors) return V4(1, 1, 1, 1);
+  const float* c = s->colors;
+#define CL(i) V4(c[4 * (i)], c[4 * (i) + 1], c[4 * (i) + 2], c[4 * (i) + 3])
+#define TRI4(a, b, cc, uv_) add4(add4(muls4(a, 1 - (uv_).x - (uv_).y), muls4(b, (uv_).x)), muls4(cc, (uv_).y))
+  if (s->num_triangles) { const int32_t* t = s->triangles + 3 * e; return TRI4(CL(t[0]), CL(t[1]), CL(t[2]), uv); }
+  if (s->num_quads) { const int32_t* q = s->quads + 4 * e;
+    if (uv.x + uv.y <= 1) return TRI4(CL(q[0]), CL(q[1]), CL(q[3]), uv);
+    v2 w = {1 - uv.x, 1 - uv.y}; return TRI4(CL(q[2]), CL(q[3]), CL(q[1]), w); }
+  if (s->num_lines) { const int32_t* l = s->lines + 2 * e; return add4(muls4(CL(l[0]), 1 - uv.x), muls4(CL(l[1]), uv.x)); }
+  if (s->num_points) return CL(s->points[e]);
+#undef TRI4
+#undef CL
+  return V4(0, 0, 0, 0);
+}
+/* eval_element_tangents (yocto_scene.cpp:425-446; quads use their first triangle) and triangle_tangents_fromuv
+ * (yocto_geometry.h:504-522) */
+static v2 TCv(const ygl_shape* s, int i) { v2 r = {s->texcoords[2 * i], s->texcoords[2 * i + 1]}; return r; }
+static void triangle_tangents_fromuv(v3 p0, v3 p1, v3 p2, v2 uv0, v2 uv1, v2 uv2, v3* tu, v3* tv) {
+  v3 p = sub(p1, p0), q = sub(p2, p0);
+  v2 s_ = {uv1.x - uv0.x, uv2.x - uv0.x}, t_ = {uv1.y - uv0.y, uv2.y - uv0.y};
+  float div = s_.x * t_.y - s_.y * t_.x;
+  if (div != 0) {
+    *tu = divs(V3(t_.y * p.x - t_.x * q.x, t_.y * p.y - t_.x * q.y, t_.y * p.z - t_.x * q.z), div);
+    *tv = divs(V3(s_.x * q.x - s_.y * p.x, s_.x * q.y - s_.y * p.y, s_.x * q.z - s_.y * p.z), div);
+  } else { *tu = V3(1, 0, 0); *tv = V3(0, 1, 0); }
+}
+static void eval_element_tangents(const oracle_scene* sc, int instance, int e, v3* tu, v3* tv) {
+  const ygl_instance* in = &sc->d->instances[instance]; const ygl_shape* s = &sc->d->shapes[in->shape]; fr3 f = to_frame(&in->frame);
+  v3 a, b;
+  if (s->num_triangles && s->num_texcoords) { const int32_t* t = s->triangles + 3 * e;
+    triangle_tangents_fromuv(P(s, t[0]), P(s, t[1]), P(s, t[2]), TCv(s, t[0]), TCv(s, t[1]), TCv(s, t[2]), &a, &b);
+  } else if (s->num_quads && s->num_texcoords) { const int32_t* q = s->quads + 4 * e;
+    triangle_tangents_fromuv(P(s, q[0]), P(s, q[1]), P(s, q[3]), TCv(s, q[0]), TCv(s, q[1]), TCv(s, q[3]), &a, &b);
+  } else { *tu = V3(0, 0, 0); *tv = V3(0, 0, 0); return; }
+  *tu = xf_direction(&f, a); *tv = xf_direction(&f, b);
+}
+static v3 eval_normalmap(const oracle_scene* sc, int instance, int e, v2 uv) { /* yocto_scene.cpp:448-468 */
+  const ygl_instance* in = &sc->d->instances[instance]; const ygl_shape* s = &sc->d->shapes[in->shape];
+  const ygl_material* m = &sc->d->materials[in->material];
+  v3 normal = eval_normal(sc, instance, e, uv);
+  v2 texcoord = eval_texcoord(sc, instance, e, uv);
+  if (m->normal_tex >= 0 && (s->num_triangles || s->num_quads)) {
+    const ygl_texture* t = &sc->d->textures[m->normal_tex];
+    v4 tx = eval_texture_raw(t, texcoord, 0, t->nearest != 0, t->clamp != 0);
+    v3 nmap = V3(-1 + 2 * tx.x, -1 + 2 * tx.y, -1 + 2 * tx.z);
+    v3 tu, tv; eval_element_tangents(sc, instance, e, &tu, &tv);
+    v3 fx = normalize(sub(tu, muls(normal, dot(tu, normal)))); /* orthonormalize(tu, normal) */
+    v3 fy = normalize(cross(normal, fx));
+    int flip_v = dot(fy, tv) < 0;
+    nmap.y *= flip_v ? 1 : -1;
+    normal = normalize(add(add(muls(fx, nmap.x), muls(fy, nmap.y)), muls(normal, nmap.z)));
+  }
+  return normal;
+}
 static v3 eval_shading_normal(const oracle_scene* sc, int instance, int e, v2 uv, v3 outgoing) { /* :486-505 */
   const ygl_instance* in = &sc->d->instances[instance]; const ygl_shape* s = &sc->d->shapes[in->shape];
   const ygl_material* m = &sc->d->materials[in->material];
   if (s->num_triangles || s->num_quads) {
     v3 n = eval_normal(sc, instance, e, uv);
+    if (m->normal_tex >= 0) n = eval_normalmap(sc, instance, e, uv);
     if (m->type == YGL_MATERIAL_REFRACTIVE) return n;
     return dot(n, outgoing) >= 0 ? n : neg(n);
   } else if (s->num_lines) { v3 n = eval_normal(sc, instance, e, uv); return normalize(sub(outgoing, muls(n, dot(outgoing, n)))); }
@@ -477,16 +599,24 @@ static v3 eval_shading_position(const oracle_scene* sc, int instance, int e, v2 
   if (s->num_points) return P(s, s->points[e]); /* object space: reference quirk */
   return V3(0, 0, 0);
 }
+
 typedef struct { int type; v3 emission, color; float opacity, roughness, metallic, ior; v3 density, scattering; float scanisotropy, trdepth; } mpoint;
-static mpoint eval_material(const oracle_scene* sc, int instance) { /* :531-581, all textures absent -> factor 1 */
+static mpoint eval_material(const oracle_scene* sc, int instance, int element, v2 uv) { /* yocto_scene.cpp:531-581 */
   const ygl_material* m = &sc->d->materials[sc->d->instances[instance].material];
+  v2 texcoord = eval_texcoord(sc, instance, element, uv);
+  v4 emission_tex = eval_texture(sc, m->emission_tex, texcoord, 1);
+  v4 color_shp = eval_color(sc, instance, element, uv);
+  v4 color_tex = eval_texture(sc, m->color_tex, texcoord, 1);
+  v4 roughness_tex = eval_texture(sc, m->roughness_tex, texcoord, 0);
+  v4 scattering_tex = eval_texture(sc, m->scattering_tex, texcoord, 1);
   mpoint p; p.type = m->type;
-  v3 one = V3(1, 1, 1);
-  p.emission = mul(mul(V3(m->emission[0], m->emission[1], m->emission[2]), one), one);
-  p.color = mul(mul(V3(m->color[0], m->color[1], m->color[2]), one), one);
-  p.opacity = m->opacity * 1.0f * 1.0f; p.metallic = m->metallic * 1.0f;
-  p.roughness = m->roughness * 1.0f; p.roughness = p.roughness * p.roughness; p.ior = m->ior;
-  p.scattering = mul(V3(m->scattering[0], m->scattering[1], m->scattering[2]), one);
+  p.emission = mul(mul(V3(m->emission[0], m->emission[1], m->emission[2]), V3(emission_tex.x, emission_tex.y, emission_tex.z)),
+      V3(color_shp.x, color_shp.y, color_shp.z));
+  p.color = mul(mul(V3(m->color[0], m->color[1], m->color[2]), V3(color_tex.x, color_tex.y, color_tex.z)),
+      V3(color_shp.x, color_shp.y, color_shp.z));
+  p.opacity = m->opacity * color_tex.w * color_shp.w; p.metallic = m->metallic * roughness_tex.z;
+  p.roughness = m->roughness * roughness_tex.y; p.roughness = p.roughness * p.roughness; p.ior = m->ior;
+  p.scattering = mul(V3(m->scattering[0], m->scattering[1], m->scattering[2]), V3(scattering_tex.x, scattering_tex.y, scattering_tex.z));
   p.scanisotropy = m->scanisotropy; p.trdepth = m->trdepth;
   if (p.type == YGL_MATERIAL_REFRACTIVE || p.type == YGL_MATERIAL_VOLUMETRIC || p.type == YGL_MATERIAL_SUBSURFACE) {
     v3 c = vclamp(p.color, 0.0001f, 1.0f);
@@ -498,13 +628,17 @@ static mpoint eval_material(const oracle_scene* sc, int instance) { /* :531-581,
   else if (p.roughness < min_roughness) p.roughness = 0;
   return p;
 }
-static v3 eval_environment(const oracle_scene* sc, v3 direction) { /* :596-613, emission_tex absent */
+static v3 eval_environment(const oracle_scene* sc, v3 direction) { /* yocto_scene.cpp:596-613 */
   v3 e = V3(0, 0, 0);
   for (int i = 0; i < sc->d->num_environments; i++) {
     const ygl_environment* env = &sc->d->environments[i];
-    e = add(e, mul(V3(env->emission[0], env->emission[1], env->emission[2]), V3(1, 1, 1)));
+    fr3 f = to_frame(&env->frame), inv = frame_inverse_rigid(&f);
+    v3 wl = xf_direction(&inv, direction);
+    v2 texcoord = {atan2f(wl.z, wl.x) / (2 * pif), acosf(clampf_(wl.y, -1.0f, 1.0f)) / pif};
+    if (texcoord.x < 0) texcoord.x += 1;
+    v4 t = eval_texture(sc, env->emission_tex, texcoord, 0);
+    e = add(e, mul(V3(env->emission[0], env->emission[1], env->emission[2]), V3(t.x, t.y, t.z)));
   }
-  (void)direction;
   return e;
 }
 
@@ -826,7 +960,18 @@ static v3 sample_lights(const oracle_scene* sc, v3 position, float rl, float rel
     if (s->num_triangles) { uv.x = 1 - sqrtf(ruv.x); uv.y = ruv.y * sqrtf(ruv.x); }
     return normalize(sub(eval_position(sc, l->instance, e, uv), position));
   }
-  return sample_sphere(ruv); /* constant environment */
+  if (l->environment >= 0) { /* :376-386 */
+    const ygl_environment* env = &sc->d->environments[l->environment];
+    if (env->emission_tex >= 0) {
+      const ygl_texture* t = &sc->d->textures[env->emission_tex];
+      int idx = sample_discrete(l->cdf, l->n, rel);
+      v2 uv = {((idx % t->width) + 0.5f) / t->width, ((idx / t->width) + 0.5f) / t->height};
+      fr3 f = to_frame(&env->frame);
+      return xf_direction(&f, V3(cosf(uv.x * 2 * pif) * sinf(uv.y * pif), cosf(uv.y * pif), sinf(uv.x * 2 * pif) * sinf(uv.y * pif)));
+    }
+    return sample_sphere(ruv);
+  }
+  return V3(0, 0, 0);
 }
 static float sample_lights_pdf(const oracle_scene* sc, v3 position, v3 direction) {
   float pdf = 0.0f;
@@ -846,6 +991,18 @@ static float sample_lights_pdf(const oracle_scene* sc, v3 position, v3 direction
         next = add(lp, muls(direction, 1e-3f));
       }
       pdf += lpdf;
+    } else if (sc->d->environments[l->environment].emission_tex >= 0) { /* :424-437 */
+      const ygl_environment* env = &sc->d->environments[l->environment];
+      const ygl_texture* t = &sc->d->textures[env->emission_tex];
+      fr3 f = to_frame(&env->frame), inv = frame_inverse_rigid(&f);
+      v3 wl = xf_direction(&inv, direction);
+      v2 texcoord = {atan2f(wl.z, wl.x) / (2 * pif), acosf(clampf_(wl.y, -1.0f, 1.0f)) / pif};
+      if (texcoord.x < 0) texcoord.x += 1;
+      int i = clampi_((int)(texcoord.x * t->width), 0, t->width - 1), j = clampi_((int)(texcoord.y * t->height), 0, t->height - 1);
+      int idx = j * t->width + i;
+      float prob = (idx == 0 ? l->cdf[0] : l->cdf[idx] - l->cdf[idx - 1]) / l->cdf[l->n - 1];
+      float angle = (2 * pif / t->width) * (pif / t->height) * sinf(pif * (j + 0.5f) / t->height);
+      pdf += prob / angle;
     } else pdf += 1 / (4 * pif);
   }
   pdf *= (float)1 / (float)sc->num_lights;
@@ -903,7 +1060,7 @@ static ray_t eval_camera(const ygl_camera* c, v2 iuv, v2 luv) {
   if (is_volumetric_type(sc->d->materials[sc->d->instances[isec.instance].material].type) &&                        \
       dot(normal, outgoing) * dot(normal, incoming) < 0) {                                                          \
     if (!has_volume) {                                                                                              \
-      mpoint vm = eval_material(sc, isec.instance);                                                                 \
+      mpoint vm = eval_material(sc, isec.instance, isec.element, uv);                                                                 \
       vsdf.density = vm.density; vsdf.scattering = vm.scattering; vsdf.scanisotropy = vm.scanisotropy;             \
       has_volume = 1;                                                                                               \
     } else {                                                                                                        \
@@ -938,7 +1095,7 @@ static trace_result trace_path(const oracle_scene* sc, ray_t ray, rng_t* rng, co
       v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
       v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
       v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-      mpoint m = eval_material(sc, isec.instance);
+      mpoint m = eval_material(sc, isec.instance, isec.element, uv);
       NOCAUSTICS(m)
       OPACITY_PASS(m, position)
       if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
@@ -994,7 +1151,7 @@ static v3 shadow_emission(const oracle_scene* sc, v3 position, v3 incoming, ygl_
   if (out) *out = is;
   if (!is.hit) return eval_environment(sc, incoming);
   v2 uv = {is.uv[0], is.uv[1]};
-  mpoint m = eval_material(sc, is.instance);
+  mpoint m = eval_material(sc, is.instance, is.element, uv);
   return eval_emission(&m, eval_shading_normal(sc, is.instance, is.element, uv, neg(incoming)), neg(incoming));
 }
 /* one-sample MIS next direction of trace_path / pathdirect / pathtest, :522-542. Returns 0 on `break`. */
@@ -1028,7 +1185,7 @@ static trace_result trace_pathdirect(const oracle_scene* sc, ray_t ray, rng_t* r
       v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
       v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
       v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-      mpoint m = eval_material(sc, isec.instance);
+      mpoint m = eval_material(sc, isec.instance, isec.element, uv);
       NOCAUSTICS(m)
       OPACITY_PASS(m, position)
       if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
@@ -1079,7 +1236,7 @@ static trace_result trace_pathmis(const oracle_scene* sc, ray_t ray, rng_t* rng,
       v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
       v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
       v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-      mpoint m = eval_material(sc, isec.instance);
+      mpoint m = eval_material(sc, isec.instance, isec.element, uv);
       NOCAUSTICS(m)
       OPACITY_PASS(m, position)
       if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
@@ -1135,7 +1292,7 @@ static trace_result trace_pathtest(const oracle_scene* sc, ray_t ray, rng_t* rng
     v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-    mpoint m = eval_material(sc, isec.instance);
+    mpoint m = eval_material(sc, isec.instance, isec.element, uv);
     m.type = YGL_MATERIAL_MATTE; /* :981, after eval_material: the roughness keeps the original type's clamp */
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
@@ -1159,7 +1316,7 @@ static trace_result trace_naive(const oracle_scene* sc, ray_t ray, rng_t* rng, c
     v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-    mpoint m = eval_material(sc, isec.instance);
+    mpoint m = eval_material(sc, isec.instance, isec.element, uv);
     OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
@@ -1194,7 +1351,7 @@ static trace_result trace_eyelight_like(const oracle_scene* sc, ray_t ray, rng_t
     v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
     v3 position = eval_shading_position(sc, isec.instance, isec.element, uv);
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-    mpoint m = eval_material(sc, isec.instance);
+    mpoint m = eval_material(sc, isec.instance, isec.element, uv);
     OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     v3 incoming = outgoing;
@@ -1225,7 +1382,7 @@ static trace_result trace_furnace(const oracle_scene* sc, ray_t ray, rng_t* rng,
     v3 outgoing = neg(ray.d); v2 uv = {isec.uv[0], isec.uv[1]};
     v3 position = eval_position(sc, isec.instance, isec.element, uv); /* :1281: eval_position, not eval_shading_position */
     v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
-    mpoint m = eval_material(sc, isec.instance);
+    mpoint m = eval_material(sc, isec.instance, isec.element, uv);
     OPACITY_PASS(m, position)
     if (bounce == 0) { hit = 1; hit_albedo = m.color; hit_normal = normal; }
     radiance = add(radiance, mul(weight, eval_emission(&m, normal, outgoing)));
@@ -1248,27 +1405,10 @@ static trace_result trace_furnace(const oracle_scene* sc, ray_t ray, rng_t* rng,
   return r;
 }
 /* ---- trace_falsecolor, yocto_trace.cpp:1341-1419 ---- */
-static float srgb_to_rgb1(float srgb) { /* yocto_color.h:235-238: the threshold is a double literal */
-  return ((double)srgb <= 0.04045) ? srgb / 12.92f : powf((srgb + 0.055f) / (1.0f + 0.055f), 2.4f);
-}
 static v3 hashed_color(int id) { /* :1358-1362: std::hash<int> is the identity; rand3f draws x, y, z in order */
   rng_t r = make_rng(961748941, (uint64_t)(size_t)id);
   float x = rand1f(&r), y = rand1f(&r), z = rand1f(&r);
   return V3(powf(0.5f + 0.5f * x, 2.2f), powf(0.5f + 0.5f * y, 2.2f), powf(0.5f + 0.5f * z, 2.2f));
-}
-static v2 eval_texcoord(const oracle_scene* sc, int instance, int e, v2 uv) { /* yocto_scene.cpp:369-391 */
-  const ygl_shape* s = &sc->d->shapes[sc->d->instances[instance].shape];
-  if (!s->num_texcoords) return uv;
-  const float* tc = s->texcoords;
-#define TC(i) V3(tc[2 * (i)], tc[2 * (i) + 1], 0)
-  v3 r = V3(0, 0, 0);
-  if (s->num_triangles) { const int32_t* t = s->triangles + 3 * e; r = interp_tri(TC(t[0]), TC(t[1]), TC(t[2]), uv); }
-  else if (s->num_quads) { const int32_t* q = s->quads + 4 * e; r = interp_quad(TC(q[0]), TC(q[1]), TC(q[2]), TC(q[3]), uv); }
-  else if (s->num_lines) { const int32_t* l = s->lines + 2 * e; r = add(muls(TC(l[0]), 1 - uv.x), muls(TC(l[1]), uv.x)); }
-  else if (s->num_points) r = TC(s->points[e]);
-#undef TC
-  v2 o = {r.x, r.y};
-  return o;
 }
 static trace_result trace_falsecolor(const oracle_scene* sc, ray_t ray, const ygl_trace_params* p) {
   trace_result none = {V3(0, 0, 0), 0, V3(0, 0, 0), V3(0, 0, 0)};
@@ -1279,7 +1419,7 @@ static trace_result trace_falsecolor(const oracle_scene* sc, ray_t ray, const yg
   v3 normal = eval_shading_normal(sc, isec.instance, isec.element, uv, outgoing);
   v3 gnormal = eval_element_normal(sc, isec.instance, isec.element);
   v2 texcoord = eval_texcoord(sc, isec.instance, isec.element, uv);
-  mpoint m = eval_material(sc, isec.instance);
+  mpoint m = eval_material(sc, isec.instance, isec.element, uv);
   float delta = is_delta(&m) ? 1.0f : 0.0f;
   const ygl_instance* in = &sc->d->instances[isec.instance];
   v3 result = V3(0, 0, 0);

@@ -18,7 +18,7 @@ SCENES = {
     "cornell": scenes.cornellbox,
     "cornell_quads": scenes.cornellbox_quads,
     "instanced3": lambda: scenes.instanced_spheres(3),
-    "features": scenes.features,  # traversal only (its materials/textures are outside the restatement)
+    "features": scenes.features,
     "hair": lambda: scenes.hair_scene(1500, 6, 2),
 }
 
@@ -153,6 +153,19 @@ def test_transmission_and_volumes_bit_identical_to_reference(ref, sampler):
         assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), offset
 
 
+@pytest.mark.parametrize("sampler", list(range(9)))
+def test_features_scene_bit_identical_to_reference(ref, sampler):
+    """scenes.features(): triangles, quads, lines, points; all 8 material types; opacity; vertex colors; color /
+    roughness / normal / emission textures (byte sRGB and float); textured rotated environment; thin-lens and
+    orthographic cameras - every sampler, bit for bit against the unmodified reference."""
+    scene = scenes.features()
+    mine = restate.OracleScene(scene)
+    assert mine.supported()
+    for extra in (dict(), dict(camera=1, nocaustics=1, tentfilter=1)):
+        p = abi.trace_params(resolution=72, samples=2, bounces=8, sampler=sampler, **extra)
+        assert mine.trace_image(p).tobytes() == ref.scene(scene).trace_image(p)["image"].tobytes(), extra
+
+
 def test_restatement_rejects_what_it_does_not_cover():
     scene = SCENES["cornell"]()
     mine = restate.OracleScene(scene)
@@ -161,18 +174,23 @@ def test_restatement_rejects_what_it_does_not_cover():
             mine.trace_image(abi.trace_params(resolution=16, samples=1, **kw))
 
 
-def test_golden_image_and_checksum():
+GOLDEN_SCENES = {"cornell": scenes.cornellbox, "features": scenes.features,
+                 "instanced4": lambda: scenes.instanced_spheres(4), "hair": lambda: scenes.hair_scene(4000, 8, 3)}
+
+
+def test_every_golden_render_and_checksum():
+    """The committed golden renders (made by the real reference, tests/golden/make_golden.py: every sampler, all four
+    test scenes) are reproduced bit for bit by the restatement - this pins it even where oracle/_ref is absent."""
     g = np.load(os.path.join(GOLDEN, "renders.npz"))
-    scene = scenes.cornellbox()
-    mine = restate.OracleScene(scene)
-    kw = {k: int(v) for k, v in zip(g["cornell_path.param_names"], g["cornell_path.param_values"])}
-    assert mine.trace_image(abi.trace_params(**kw)).tobytes() == g["cornell_path.image"].tobytes()
+    cache = {}
+    names = [k.split(".")[0] for k in g.files if k.endswith(".image")]
+    assert len(names) >= 13
+    for name in names:
+        scene_name = str(g[f"{name}.scene"])
+        if scene_name not in cache:
+            cache[scene_name] = restate.OracleScene(GOLDEN_SCENES[scene_name]())
+        kw = {k: int(v) for k, v in zip(g[f"{name}.param_names"], g[f"{name}.param_values"])}
+        assert cache[scene_name].trace_image(abi.trace_params(**kw)).tobytes() == g[f"{name}.image"].tobytes(), name
     kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
-    img = mine.trace_image(abi.trace_params(resolution=256, samples=16, bounces=4))
+    img = cache["cornell"].trace_image(abi.trace_params(resolution=256, samples=16, bounces=4))
     assert abs(float(img[..., :3].astype(np.float64).sum()) - kat["cornell_256_16spp_4b_sum_rgb"]) < 1e-9
-
-
-def test_unsupported_features_are_reported():
-    assert not restate.OracleScene(scenes.features()).supported()
-    with pytest.raises(NotImplementedError):
-        restate.OracleScene(scenes.features()).trace_image(abi.trace_params(resolution=8, samples=1))
