@@ -63,5 +63,41 @@ int main(int argc, char** argv) {
     snprintf(name, sizeof(name), "powf(x,%g) fma", y);
     run(name, [](float x, float* o) { return powf_<true>(x, yy, o); }, [](float x) { return powf(x, yy); }, nt);
   }
+  // two-argument routines cannot be enumerated: random pairs, half of them arbitrary bit patterns, half in the
+  // renderer's ranges (unit-range operands for atan2f; bases in [0, 4), exponents in [0, 8) for powf)
+  {
+    std::atomic<uint64_t> bad_atan2{0}, bad_pow{0}, covered{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back([&, t]() {
+        uint64_t s = 0x9E3779B97F4A7C15ull * (uint64_t)(t + 1), b0 = 0, b1 = 0, c = 0;
+        for (uint64_t i = 0; i < 30000000ull; i++) {
+          s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+          float x, y, o;
+          if (i & 1) {
+            uint32_t a = (uint32_t)s, b = (uint32_t)(s >> 32);
+            memcpy(&x, &a, 4), memcpy(&y, &b, 4);
+          } else {
+            x = ((int32_t)(uint32_t)s) / 2147483648.0f, y = ((int32_t)(uint32_t)(s >> 32)) / 2147483648.0f;
+          }
+          if (i & 2) {
+            if (!atan2f_<false>(y, x, &o)) continue;
+            float e = atan2f(y, x);
+            c++;
+            if (memcmp(&o, &e, 4) && !(o != o && e != e)) b0++;
+          } else {
+            float bx = (i & 4) ? x * 4 : fabsf(x) * 4, ey = fabsf(y) * 8;
+            if (!powf_<true>(bx, ey, &o)) continue;
+            float e = powf(bx, ey);
+            c++;
+            if (memcmp(&o, &e, 4) && !(o != o && e != e)) b1++;
+          }
+        }
+        bad_atan2 += b0, bad_pow += b1, covered += c;
+      });
+    for (auto& t : th) t.join();
+    printf("atan2f plain / powf(x,y) fma: covered %llu random pairs, mismatches %llu / %llu\n",
+        (unsigned long long)covered.load(), (unsigned long long)bad_atan2.load(), (unsigned long long)bad_pow.load());
+  }
   return 0;
 }
