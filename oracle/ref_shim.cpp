@@ -25,6 +25,13 @@
 #include <vector>
 
 #include "../include/ygl_b200.h"
+#ifdef REF_COUNTERS
+#include "ref_counters.h"
+namespace refcount {
+std::atomic<uint64_t>     g_totals[kNumModes * kPerMode];
+thread_local tls_counters t_counters;
+}  // namespace refcount
+#endif
 
 #ifdef REF_DOUBLE_LIBM
 // Variant used only to localise arithmetic differences: every float libm call of the reference
@@ -364,6 +371,25 @@ double ref_trace_image(void* scene_, const ygl_trace_params* params_, int sample
 }
 
 int ref_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
+
+// ---- instrumented oracle (libyocto_ref_count.so only): traversal counters of SURVEY.md §8d ----
+// out[mode * 8 + k], mode 0 = intersect_scene_bvh queries, 1 = intersect_instance_bvh queries;
+// k = top nodes, bottom nodes, instance visits, point / line / triangle / quad tests, rays (ref_counters.h).
+#ifdef REF_COUNTERS
+int  ref_counters_available() { return 1; }
+void ref_counters_reset() {
+  refcount::t_counters.flush();
+  for (auto& total : refcount::g_totals) total.store(0);
+}
+void ref_counters_read(uint64_t* out) {
+  refcount::t_counters.flush();
+  for (int k = 0; k < refcount::kNumModes * refcount::kPerMode; k++) out[k] = refcount::g_totals[k].load();
+}
+#else
+int  ref_counters_available() { return 0; }
+void ref_counters_reset() {}
+void ref_counters_read(uint64_t* out) { memset(out, 0, 16 * sizeof(uint64_t)); }
+#endif
 
 // PCG32 known-answer helper (yocto_sampling.h:197-214): n floats of make_rng(seed, seq)
 void ref_rng_floats(uint64_t seed, uint64_t seq, int n, float* out, uint64_t* state_inc) {

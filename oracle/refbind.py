@@ -49,6 +49,24 @@ class Ref:
                                         C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp, vp, vp]
         lib.ref_rng_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, vp, vp]
         lib.ref_sizeof.argtypes = [C.c_char_p]
+        lib.ref_counters_read.argtypes = [vp]
+
+    COUNTER_NAMES = ("top_nodes", "bottom_nodes", "instance_visits", "point_tests", "line_tests", "triangle_tests",
+                     "quad_tests", "rays")
+
+    def counters_reset(self):
+        """Instrumented oracle only (variant '_count'): zero the traversal counters (oracle/ref_counters.h)."""
+        if not self.lib.ref_counters_available():
+            raise RuntimeError("this reference build carries no traversal counters: use Ref('_count')")
+        self.lib.ref_counters_reset()
+
+    def counters(self):
+        """{'scene': {...}, 'instance': {...}}: totals since the last reset, split by the kind of query
+        (intersect_scene_bvh / intersect_instance_bvh) that was running."""
+        out = np.zeros(16, np.uint64)
+        self.lib.ref_counters_read(out.ctypes.data)
+        return {mode: {n: int(out[8 * m + k]) for k, n in enumerate(self.COUNTER_NAMES)}
+                for m, mode in enumerate(("scene", "instance"))}
 
     def sizeof(self, name):
         return self.lib.ref_sizeof(name.encode())

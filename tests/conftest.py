@@ -31,6 +31,15 @@ def ref_dlibm():
 
 
 @pytest.fixture(scope="session")
+def ref_count():
+    """The instrumented oracle: the reference with traversal counters (oracle/ref_counters.h)."""
+    import refbind
+    if not refbind.available("_count"):
+        pytest.skip("oracle/_ref/libyocto_ref_count.so not built")
+    return refbind.Ref("_count")
+
+
+@pytest.fixture(scope="session")
 def ctx():
     from ygl_b200 import lib
     return lib.Context(0)

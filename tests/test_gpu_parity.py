@@ -264,24 +264,131 @@ def test_golden_images(ctx):
         assert_close_to_reference(image_stats(g[f"{name}.image_dlibm"], image))
 
 
-def test_full_size_properties(ctx):
-    """BASELINE-size checks that need no oracle: C3 at 1920x1080 — determinism across runs, tile
-    invariance, alpha == 1 exactly where hits == spp, finite radiance, clamp respected."""
-    scene = scenes.instanced_spheres(10)
-    params = abi.trace_params(resolution=1920, samples=2, bounces=8, batch=2)
+# ---- parity AT THE BASELINE SIZES (BASELINE.json configs[1..4]) against the unmodified reference ----
+FULL_SIZE = {
+    # name: (scene factory, trace_params of the config at a sample count the CPU reference renders in seconds)
+    "c3": (lambda: scenes.instanced_spheres(10), dict(resolution=1920, samples=2, bounces=8, batch=2)),
+    "c2": (lambda: scenes.bunny_like(6), dict(resolution=1280, samples=2, bounces=8, batch=2)),
+    "c5": (scenes.hair_stress, dict(resolution=1920, samples=1, bounces=12, batch=1)),
+}
+_full_cache = {}
+
+
+def full_scene(name):
+    if name not in _full_cache:
+        _full_cache[name] = FULL_SIZE[name][0]()
+    return _full_cache[name]
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_render_bit_exact(ctx, ref, name):
+    """C3 at 1920x1080, C2 at 1280x720, C5 at 1920x1080: image, denoise guides, hit counts and rng streams of the
+    whole frame identical to the reference CPU render, bit for bit (tolerance 0 => per-pixel RMSE 0 < 1e-5)."""
+    scene = full_scene(name)
+    params = abi.trace_params(**FULL_SIZE[name][1])
+    want = ref.scene(scene).trace_image(params, full=True)
     ds = lib.DeviceScene(ctx, scene)
     st = ds.make_state(params)
     ds.trace_samples(st, params)
-    a = st.download(full=True)
-    assert a["image"].shape == (1080, 1920, 4) and np.isfinite(a["image"]).all()
-    assert a["image"][..., :3].max() <= 10.0 + 1e-4
-    assert ((a["hits"] == 2) == (a["image"][..., 3] == 1.0)).all()
-    c = ctx.counters()
-    assert c["camera_samples"] == 1920 * 1080 * 2
-    rows = (500, 540)
+    got = st.download(full=True)
+    assert got["image"].shape == want["image"].shape
+    for k in ("image", "albedo", "normal", "hits"):
+        assert got[k].tobytes() == want[k].tobytes(), (name, k, image_stats(want["image"], got["image"]))
+    np.testing.assert_array_equal(got["rngs"], want["rngs"])
+    # ... and to the committed digest of the reference render made in the development container
+    import hashlib
+    import json
+    fixture = json.load(open(os.path.join(GOLDEN, "traversal_counters.json")))[name]
+    assert hashlib.sha256(got["image"].tobytes()).hexdigest() == fixture["image_sha256"]
+    assert hashlib.sha256(got["rngs"].tobytes()).hexdigest() == fixture["rngs_sha256"]
+    # size-independent properties of the same frame
+    assert np.isfinite(got["image"]).all() and got["image"][..., :3].max() <= 10.0 + 1e-4  # clamp respected
+    spp = params.samples
+    assert ((got["hits"] == spp) == (got["image"][..., 3] == 1.0)).all()
+    assert ctx.counters()["camera_samples"] == got["hits"].size * spp
+    # tile invariance at size: a band of rows rendered alone equals the same rows of the frame
+    H = got["image"].shape[0]
+    rows = (H // 2 - 20, H // 2 + 20)
     st2 = ds.make_state(params, rows=rows)
     ds.trace_samples(st2, params)
-    assert st2.download()["image"].tobytes() == a["image"][rows[0]:rows[1]].tobytes()
+    assert st2.download()["image"].tobytes() == got["image"][rows[0]:rows[1]].tobytes()
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_rays_bit_exact(ctx, ref, name):
+    """>= 10^6 rays per config (all-direction rays from the scene box + primary rays of the config's camera)
+    through ygl_intersect_rays: instance, element, uv and distance identical to intersect_scene_bvh."""
+    scene = full_scene(name)
+    params = abi.trace_params(**FULL_SIZE[name][1])
+    ds, rs = lib.DeviceScene(ctx, scene), ref.scene(scene)
+    rays = np.concatenate([random_rays(scene, 600000), scenes.camera_rays(scene, params, 500000),
+                           axis_rays(scene, 50000)])
+    threads = max(8, os.cpu_count() or 8)
+    assert compare_hits(rs.intersect(rays, nthreads=threads), ds.intersect(rays)) == 0
+    some = rays[:200000]
+    assert compare_hits(rs.intersect(some, find_any=True, nthreads=threads), ds.intersect(some, find_any=True)) == 0
+
+
+COUNTER_KEYS = ("top_nodes", "bottom_nodes", "instance_visits", "triangle_tests", "quad_tests", "line_tests", "point_tests")
+
+
+@pytest.mark.parametrize("name", ["c3", "c5"])
+def test_traversal_counters_match_instrumented_oracle(ctx, ref_count, name):
+    """The numerator of bench.py's roofline: the counting variant of k_extend must reproduce, exactly, the
+    per-query counters of the INSTRUMENTED reference (oracle/ref_counters.h: counter sites at
+    yocto_bvh.cpp:466,487,506-545,560,581) on the BASELINE config, and the committed fixture of the same run."""
+    scene = full_scene(name)
+    params = abi.trace_params(**FULL_SIZE[name][1])
+    rs = ref_count.scene(scene)
+    ref_count.counters_reset()
+    rs.trace_image(params)
+    want = ref_count.counters()["scene"]
+    ctx.set_profiling(False, True)
+    try:
+        ds = lib.DeviceScene(ctx, scene)
+        st = ds.make_state(params)
+        ds.trace_samples(st, params)
+        got = ctx.counters()
+    finally:
+        ctx.set_profiling(False, False)
+    assert got["scene_rays"] == want["rays"]
+    for k in COUNTER_KEYS:
+        assert got[k] == want[k], (k, got[k], want[k])
+    assert got["instance_rays"] == ref_count.counters()["instance"]["rays"]
+    import json
+    fixture = json.load(open(os.path.join(GOLDEN, "traversal_counters.json")))[name]
+    assert {k: got[k] for k in COUNTER_KEYS} == {k: fixture["scene"][k] for k in COUNTER_KEYS}
+    assert got["scene_rays"] == fixture["scene"]["rays"]
+
+
+def test_deep_tree_uses_the_full_reference_stack(ctx, ref):
+    """A degenerate (sorted-sliver) mesh whose split_middle tree is a 97-level chain: deeper than the 64 entries
+    the round-1 build accepted, inside the reference's 128 (yocto_bvh.cpp:469). Rays and a render match bit for
+    bit; a 167-level chain, which would overflow the reference's own stack, is rejected with an error."""
+    scene = scenes.sliver_chain(100)
+    ds, rs = lib.DeviceScene(ctx, scene), ref.scene(scene)
+    nodes, _ = ds.bvh.tree(0)
+    depth, todo = 0, [(0, 1)]
+    while todo:
+        i, d = todo.pop()
+        depth = max(depth, d)
+        if nodes[i]["internal"]:
+            todo += [(int(nodes[i]["start"]), d + 1), (int(nodes[i]["start"]) + 1, d + 1)]
+    assert 64 < depth <= 128
+    rng = np.random.default_rng(9)
+    rays = random_rays(scene, 50000)
+    # aim a third of the rays straight at sliver centres, from +x and from -x (both child orders of the chain)
+    k = rng.integers(0, 100, 30000)
+    tgt = scene.shapes[0]["positions"].reshape(-1, 3, 3).mean(1)[k]
+    org = tgt + np.where(rng.random((30000, 1)) < 0.5, 1.0, -1.0) * np.array([[2.0, 0.3, 0.2]], np.float32)
+    d = tgt - org
+    rays["o"][:30000] = org.astype(np.float32)
+    rays["d"][:30000] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    assert compare_hits(rs.intersect(rays), ds.intersect(rays)) == 0
+    params = abi.trace_params(resolution=128, samples=4, bounces=4)
+    assert ctx.trace_image(scene, params).tobytes() == rs.trace_image(params)["image"].tobytes()
+    with pytest.raises(lib.YglError):
+        lib.DeviceScene(ctx, scenes.sliver_chain(170))
 
 
 def test_unsupported_sampler_and_errors(ctx):

@@ -97,7 +97,7 @@ struct ygl_context {
   const ygl_scene*  bound_scene  = nullptr;
   const ygl_bvh*    bound_bvh    = nullptr;
   const ygl_lights* bound_lights = nullptr;
-  uint64_t          bound_epoch  = 0;
+  uint64_t          bound_epoch  = 0, bound_bvh_epoch = 0, bound_lights_epoch = 0;
   DShape*           d_shapes     = nullptr;
   DLight*           d_lights     = nullptr;
   DScene            dscene       = {};
@@ -123,18 +123,22 @@ struct ygl_scene {
 };
 
 struct ygl_bvh {
-  HostBvh host;
-  // device copy (made on first use)
+  HostBvh  host;
+  uint64_t epoch = 0;  // unique per object: a new bvh at a recycled address never matches a cached binding
+  // device copy (made on first use, on the device of the context that first binds it)
   mutable Arena arena;
   mutable bool  uploaded = false;
+  mutable int   device   = -1;
   mutable std::vector<size_t> off_nodes, off_packets, off_prims;
   mutable size_t off_top_nodes = 0, off_top_packets = 0, off_top_prims = 0, off_inst_packets = 0;
 };
 
 struct ygl_lights {
   std::vector<HostLight> host;
+  uint64_t               epoch = 0;
   mutable Arena          arena;
   mutable bool           uploaded = false;
+  mutable int            device   = -1;
   mutable std::vector<size_t> off_cdf;
 };
 
@@ -147,7 +151,7 @@ struct ygl_state {
   uint8_t*     mem   = nullptr;
 };
 
-static uint64_t g_epoch = 1;
+static std::atomic<uint64_t> g_epoch{1};
 
 extern "C" {
 
@@ -377,7 +381,8 @@ int ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
   auto        bvh = std::make_unique<ygl_bvh>();
   std::string error;
   if (!build_scene_bvh(*desc, highquality != 0, bvh->host, error)) return fail(YGL_ERR_INVALID, error);
-  *out = bvh.release();
+  bvh->epoch = g_epoch++;
+  *out       = bvh.release();
   return YGL_OK;
 }
 static const HostTree* pick_tree(const ygl_bvh* bvh, int shape) {
@@ -403,12 +408,17 @@ int ygl_bvh_tree_get(const ygl_bvh* bvh, int shape, ygl_bvh_node* nodes, int32_t
 }
 void ygl_bvh_destroy(ygl_bvh* bvh) {
   if (!bvh) return;
+  if (bvh->uploaded) cudaSetDevice(bvh->device);
   bvh->arena.release();
   delete bvh;
 }
 
-static int bvh_upload(const ygl_bvh* bvh) {
-  if (bvh->uploaded) return YGL_OK;
+static int bvh_upload(const ygl_bvh* bvh, int device) {
+  if (bvh->uploaded) {
+    // the instance packets carry device pointers: one device copy per bvh object
+    if (bvh->device != device) return fail(YGL_ERR_INVALID, "bvh was uploaded to another device: build one per GPU");
+    return YGL_OK;
+  }
   Arena& A  = bvh->arena;
   auto&  H  = bvh->host;
   size_t ns = H.shapes.size();
@@ -442,6 +452,7 @@ static int bvh_upload(const ygl_bvh* bvh) {
   A.host.clear();
   A.host.shrink_to_fit();
   bvh->uploaded = true;
+  bvh->device   = device;
   return YGL_OK;
 }
 
@@ -451,7 +462,8 @@ int ygl_lights_create(const ygl_scene_desc* desc, ygl_lights** out) {
   if (int rc = check_desc(desc)) return rc;
   auto lights = std::make_unique<ygl_lights>();
   build_lights(*desc, lights->host);
-  *out = lights.release();
+  lights->epoch = g_epoch++;
+  *out          = lights.release();
   return YGL_OK;
 }
 int ygl_lights_count(const ygl_lights* lights) { return lights ? (int)lights->host.size() : 0; }
@@ -466,11 +478,15 @@ int ygl_lights_get(const ygl_lights* lights, int i, int* instance, int* environm
 }
 void ygl_lights_destroy(ygl_lights* lights) {
   if (!lights) return;
+  if (lights->uploaded) cudaSetDevice(lights->device);
   lights->arena.release();
   delete lights;
 }
-static int lights_upload(const ygl_lights* lights) {
-  if (lights->uploaded) return YGL_OK;
+static int lights_upload(const ygl_lights* lights, int device) {
+  if (lights->uploaded) {
+    if (lights->device != device) return fail(YGL_ERR_INVALID, "lights were uploaded to another device: create one per GPU");
+    return YGL_OK;
+  }
   Arena& A = lights->arena;
   lights->off_cdf.resize(lights->host.size());
   for (size_t i = 0; i < lights->host.size(); i++)
@@ -479,6 +495,7 @@ static int lights_upload(const ygl_lights* lights) {
   A.host.clear();
   A.host.shrink_to_fit();
   lights->uploaded = true;
+  lights->device   = device;
   return YGL_OK;
 }
 
@@ -489,12 +506,16 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
   if ((int)bvh->host.shapes.size() != scene->num_shapes ||
       (int)(bvh->host.inst_packets.size() / kInstancePacketQuads) != scene->num_instances)
     return fail(YGL_ERR_INVALID, "bvh was built for a different scene");
+  // the cache key is the identity of the three OBJECTS (their epochs), not their addresses: a bvh or lights object
+  // destroyed and re-created at the same heap address must not hit
   if (ctx->bound_scene == scene && ctx->bound_bvh == bvh && ctx->bound_lights == lights &&
-      ctx->bound_epoch == scene->epoch)
+      ctx->bound_epoch == scene->epoch && ctx->bound_bvh_epoch == bvh->epoch &&
+      ctx->bound_lights_epoch == (lights ? lights->epoch : 0))
     return YGL_OK;
-  if (int rc = bvh_upload(bvh)) return rc;
+  ctx->bound_scene = nullptr;  // a failure below must not leave a half-built binding cached
+  if (int rc = bvh_upload(bvh, ctx->device)) return rc;
   if (lights)
-    if (int rc = lights_upload(lights)) return rc;
+    if (int rc = lights_upload(lights, ctx->device)) return rc;
   const Arena& S = scene->arena;
   const Arena& B = bvh->arena;
   std::vector<DShape> shapes(scene->num_shapes);
@@ -554,6 +575,7 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
   D.lights           = ctx->d_lights;
   D.num_lights       = nlights;
   ctx->bound_scene = scene, ctx->bound_bvh = bvh, ctx->bound_lights = lights, ctx->bound_epoch = scene->epoch;
+  ctx->bound_bvh_epoch = bvh->epoch, ctx->bound_lights_epoch = lights ? lights->epoch : 0;
   return YGL_OK;
 }
 
@@ -1110,7 +1132,6 @@ int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trac
   } while (false);
   std::string keep = g_error;
   ygl_state_destroy(state);
-  ctx->bound_scene = nullptr;
   ygl_scene_destroy(scene);
   ygl_lights_destroy(lights);
   ygl_bvh_destroy(bvh);

@@ -286,9 +286,9 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
         pk[k] = {v.x, v.y, v.z, s.radius[p]};
       }
     }
-    if (tree.max_stack > 64) {
+    if (tree.max_stack > kMaxTreeDepth) {
       error = "shape " + std::to_string(si) + ": BVH depth " + std::to_string(tree.max_stack) +
-              " exceeds the device traversal stack (64)";
+              " exceeds the traversal stack (128 entries, as in the reference)";
       return false;
     }
   }
@@ -311,7 +311,7 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
     ibox[i] = xf;
   }
   out.top = make_tree(ibox, highquality);
-  if (out.top.max_stack > 64) return error = "instance BVH too deep for the device traversal stack", false;
+  if (out.top.max_stack > kMaxTreeDepth) return error = "instance BVH too deep for the traversal stack (128 entries)", false;
   out.top_nodes = pack_nodes(out.top);
   auto pack = [&](float4h* dst, int id) {
     const ygl_instance& inst = desc.instances[id];

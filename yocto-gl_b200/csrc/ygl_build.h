@@ -19,6 +19,7 @@ struct HostTree {
 struct float4h {
   float x, y, z, w;
 };
+constexpr int kMaxTreeDepth        = 128;  // levels per tree the device walk accepts = the reference's stack (yocto_bvh.cpp:469)
 constexpr int kInstancePacketQuads = 6;  // float4 per DInstancePacket (ygl_scene.cuh)
 
 struct HostBvh {

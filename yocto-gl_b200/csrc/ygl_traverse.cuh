@@ -17,7 +17,8 @@
 
 namespace ygl {
 
-constexpr int kStackSize = 64;  // per level; host build rejects deeper trees (reference: 128, unchecked)
+constexpr int kStackSize = 128;  // per level, the reference's own stack size (yocto_bvh.cpp:469); the host build rejects
+                                 // deeper trees (the reference's array is unchecked there)
 
 struct hit_t {
   int   instance, element;

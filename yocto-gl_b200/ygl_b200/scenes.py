@@ -261,6 +261,70 @@ def hair_scene(num_strands=65536, steps=8, tri_subdiv=6):
     return sc
 
 
+def hair_stress():
+    """C5 at the size BASELINE.json states: 524,288 line segments (65,536 strands x 8) + 200,704 triangles
+    (subsurface scalp 81,920 + refractive blob 81,920 + glossy sphere 36,864) + floor and light quads; glossy hair,
+    subsurface scalp (volume path), rough refractive blob, area light + environment."""
+    sc = hair_scene(65536, 8, 6)
+    m_glass2 = sc.add_material(abi.REFRACTIVE, color=(0.8, 0.9, 0.95), roughness=0.1, ior=1.45, trdepth=0.4,
+                               scattering=(0.1, 0.1, 0.1))
+    m_ball = sc.add_material(abi.GLOSSY, color=(0.25, 0.3, 0.7), roughness=0.15)
+    blob = sc.add_shape(**geoblob(6, 0.32, bump=0.1, seed=13))
+    ball = sc.add_shape(**{k: v for k, v in uvsphere((192, 96), 0.3).items() if k != "texcoords"})
+    sc.add_instance(blob, m_glass2, translation((-1.15, -0.5, 0.35)))
+    sc.add_instance(ball, m_ball, translation((0.2, -0.55, 1.1)))
+    return sc
+
+
+def sliver_chain(n=100):
+    """A mesh whose split_middle tree degenerates into a chain: triangle k sits at x = 0.45^k (then, once float32
+    runs out of exponent, along y) with a size proportional to its coordinate, so the midpoint of the centroid box
+    peels ONE triangle off per level (yocto_bvh.cpp:202-232). Depth ~ n - 3: n = 100 needs more traversal stack than
+    64 entries but fits the reference's 128 (yocto_bvh.cpp:469); n = 170 does not fit either."""
+    nx = min(n, 105)
+    k = np.arange(n, dtype=np.float64)
+    x = 0.45 ** np.minimum(k, nx - 1)
+    y = np.where(k >= nx, 0.9 * 0.45 ** np.maximum(k - nx, 0), 0.0)
+    s = np.where(k >= nx, y, x) / 8
+    c = np.stack([x, y, np.zeros(n)], 1)
+    p = np.zeros((n, 3, 3))
+    p[:, 0] = c + np.stack([np.zeros(n), -s, -s], 1)
+    p[:, 1] = c + np.stack([np.zeros(n), s, -s], 1)
+    p[:, 2] = c + np.stack([np.zeros(n), np.zeros(n), 2 * s], 1)
+    sc = Scene()
+    sc.add_camera(lookat_frame((3.0, 0.2, 0.1), (0, 0, 0)), lens=0.05, film=0.036, aspect=1.0, focus=3.0, aperture=0.0)
+    m = sc.add_material(abi.MATTE, color=(0.7, 0.7, 0.7))
+    ml = sc.add_material(abi.MATTE, emission=(5, 5, 5))
+    sc.add_instance(sc.add_shape(triangles=np.arange(3 * n, dtype=np.int32).reshape(-1, 3),
+                                 positions=p.reshape(-1, 3).astype(np.float32)), m)
+    light = rect_y(0.5, 0.0)
+    light["positions"] = light["positions"][::-1].copy()
+    sc.add_instance(sc.add_shape(**{k_: v for k_, v in light.items() if k_ != "normals"}), ml, translation((0.5, 1.5, 0)))
+    sc.add_environment(emission=(0.4, 0.4, 0.4))
+    return sc
+
+
+def camera_rays(scene, params, n, seed=5):
+    """n primary rays of the camera the config renders with (pixel positions drawn uniformly; thin-lens centre):
+    input for the batch-intersection parity tests (SURVEY.md §8d "all camera rays of the config")."""
+    cam = scene.cameras[params.camera]
+    rng = np.random.default_rng(seed)
+    uv = rng.random((n, 2)).astype(np.float32)
+    film = np.float32(cam["film"])
+    aspect = np.float32(cam["aspect"])
+    fw, fh = (film, film / aspect) if aspect >= 1 else (film * aspect, film)
+    f = cam["frame"].astype(np.float32)
+    q = np.stack([fw * (np.float32(0.5) - uv[:, 0]), fh * (uv[:, 1] - np.float32(0.5)),
+                  np.full(n, cam["lens"], np.float32)], 1)
+    d = -(q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    rays = np.zeros(n, abi.RAY_DTYPE)
+    rays["d"] = (d @ f[:3]).astype(np.float32)
+    rays["o"] = f[3]
+    rays["tmin"] = 1e-4
+    rays["tmax"] = np.finfo(np.float32).max
+    return rays
+
+
 def features(seed=3):
     """Small scene that touches every code path: triangles, quads, lines, points; all 8 material
     types incl. delta / rough variants, opacity, vertex colors, color/roughness/normal/emission
