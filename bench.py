@@ -58,43 +58,99 @@ def algorithmic_bytes_per_ray(c):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of ONE GPU sampled at 5 Hz during the timed region, on rank 0 only, through
+    NVML in-process (no process is forked inside the timed region); falls back to polling nvidia-smi if the NVML
+    binding is missing."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.rows, self.stop, self.index = [], False, index
+    def __init__(self, index, enabled=True):
+        self.rows, self.stop, self.index, self.enabled = [], False, index, enabled
+        self.nvml = self.handle = None
+        self.sm_max = None
+        if enabled:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.nvml = pynvml
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            except Exception:
+                self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        try:
+            power = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+        except Exception:
+            power = None
+        return [sm, self.sm_max, power] + [bool(mask & b) for b in bits]
+
+    def sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        return [float(r[0]), float(r[1]), float(r[2])] + [x.lower().startswith("active") for x in r[3:7]]
 
     def run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.rows.append(self.sample_nvml() if self.nvml else self.sample_smi())
             except Exception:
                 pass
             time.sleep(0.2)
 
     def __enter__(self):
-        self.t.start()
+        if self.enabled:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.t.join(timeout=2)
+        if self.enabled:
+            self.t.join(timeout=2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for k, n in enumerate(self.NAMES) if any(r[3 + k] for r in self.rows)]
+        power = [r[2] for r in self.rows if r[2] is not None]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(power) if power else None,
+                "source": "NVML in-process, rank 0 only, 5 Hz" if self.nvml else "nvidia-smi polled, rank 0 only"}
+
+
+def host_cpu_info():
+    """What the CPU arm really had: logical CPUs, the affinity mask and cgroup quota of THIS process, CPU model."""
+    info = {"logical_cpus": os.cpu_count()}
+    try:
+        info["affinity_cpus"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_cpu_max"] = open(path).read().strip()
+            break
+        except Exception:
+            pass
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                info["model"] = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return info
 
 
 def scene_bytes(scene):
@@ -127,19 +183,29 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libyocto_ref.so not built"}))
         return
     rs = refbind.Ref().scene(scene)
-    cores = rs.lib.ref_hardware_concurrency()
+    threads = rs.lib.ref_hardware_concurrency()  # what the reference's parallel_for starts (yocto_trace.cpp:58)
     t1 = rs.trace_image(params, samples=1)["seconds"]
     spp_step = int(max(1, min(64, 2.5 / max(t1, 1e-3))))
     w = h = 0
     times = []
+    cpu0, wall0 = None, None
     for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            cpu0, wall0 = sum(os.times()[:2]), time.perf_counter()
         out = rs.trace_image(params, samples=spp_step)
         w, h = out["width"], out["height"]
         if i >= args.warmup:
             times.append(out["seconds"])
+    busy = (sum(os.times()[:2]) - cpu0) / max(time.perf_counter() - wall0, 1e-9)  # mean runnable threads that got a CPU
     total = sum(times)
     value = w * h * spp_step * len(times) / total / 1e6
+    # one thread (params.noparallel), on a quarter-resolution frame of the same scene: the per-core rate
+    p1 = type(params).from_buffer_copy(params)
+    p1.noparallel, p1.resolution = 1, max(64, params.resolution // 4)
+    o1 = rs.trace_image(p1, samples=1)
+    one_thread = o1["width"] * o1["height"] / max(o1["seconds"], 1e-9) / 1e6
     sample = f"{spp_step} spp per step of the {w}x{h} frame (cost is linear in spp), trace_samples loop only"
+    host = host_cpu_info()
     print(json.dumps({
         "impl": "reference",
         "metric": "Msamples/s (rays shaded/s) at 1920x1080x1024spp, 8 bounces" if args.workload == "c3" else "Msamples/s",
@@ -147,7 +213,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "spp_per_step": spp_step},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample,
+                         "threads_started": threads, "busy_cores_measured": round(busy, 1),
+                         "one_thread_value": one_thread,
+                         "one_thread_sample": f"1 spp of {o1['width']}x{o1['height']}, params.noparallel",
+                         "host": host},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -262,8 +332,12 @@ def main():
 
     for i in range(args.warmup):
         do_step(i, False)
+    if world > 1:
+        # NCCL sets its connections up lazily at the first collective: do one un-timed gather so the timed region
+        # pays for the gathers of the path only (round 1 billed the 8-rank connect to the render)
+        states[0].gather_image()
     sync_all()
-    with ClockSampler(local) as cs:
+    with ClockSampler(local, enabled=(rank == 0)) as cs:
         ev0.record(stream)
         t0 = time.perf_counter()
         for i in range(args.warmup, n_total):
@@ -323,16 +397,21 @@ def main():
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     ext_s = agg["extend_ms"] / 1e3
     achieved = bytes_per_ray * agg["scene_rays"] / max(ext_s, 1e-9) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
+        # NOT measured in this run (DRAM counters need ncu): bytes per scene ray of one `ncu --set full` capture of
+        # k_extend on this workload, scaled to this run's rays per launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "extend_traffic.json")))
         traffic = tj["dram_bytes_per_ray"] * agg["scene_rays"] / max(1, agg["extend_launches"])
+        traffic_src = "static: " + tj.get("source", "profiles/extend_traffic.json") + " x this run's rays per launch"
     except Exception:
         pass
     roofline = {
         "kernel": "k_extend (closest-hit two-level BVH traversal)", "bound": "hbm",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": traffic, "algorithmic_bytes_per_ray": bytes_per_ray,
+        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_ray": bytes_per_ray,
+        "algorithmic_bytes_checked": "kernel counters == instrumented reference (tests/test_gpu_parity.py::"
+                                     "test_traversal_counters_match_instrumented_oracle)",
         "rays_per_launch": agg["scene_rays"] / max(1, agg["extend_launches"]),
         "avg_launch_ms": agg["extend_ms"] / max(1, agg["extend_launches"]),
         "kernel_share_of_step": ext_s / max(elapsed, 1e-9), "scene_Mrays_per_s_in_kernel": agg["scene_rays"] / max(ext_s, 1e-9) / 1e6,

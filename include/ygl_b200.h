@@ -220,6 +220,14 @@ int  ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out);
 int  ygl_bvh_tree_size(const ygl_bvh* bvh, int shape, int* num_nodes, int* num_primitives);
 /* Copies the tree out (reference bvh_tree layout) — used by the parity tests. */
 int  ygl_bvh_tree_get(const ygl_bvh* bvh, int shape, ygl_bvh_node* nodes, int32_t* primitives);
+/* Parity mode: adopt trees built elsewhere — e.g. the reference's own make_scene_bvh output (scene_bvh,
+ * yocto_bvh.h:70-79) — verbatim: top_nodes / top_primitives = scene_bvh::bvh, shape_nodes[s] / shape_primitives[s] =
+ * scene_bvh::shapes[s].bvh (bvh_node layout of yocto_shape.h:474-480, which ygl_bvh_node mirrors). The trees are
+ * checked (index ranges, leaves of <= 4 primitives, depth <= 128) and only the traversal packets are derived. */
+int  ygl_bvh_create_from_host(const ygl_scene_desc* desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
+     const int32_t* top_primitives, int num_top_primitives, const ygl_bvh_node* const* shape_nodes,
+     const int* shape_num_nodes, const int32_t* const* shape_primitives, const int* shape_num_primitives,
+     ygl_bvh** out);
 void ygl_bvh_destroy(ygl_bvh* bvh);
 
 /* ---- lights: make_trace_lights (host; CDFs in the reference's summation order) ---- */
@@ -251,6 +259,9 @@ int  ygl_state_download(ygl_state* state, float* image, float* albedo, float* no
      uint64_t* rngs);
 int  ygl_state_upload(ygl_state* state, int samples, const float* image, const float* albedo,
      const float* normal, const int32_t* hits, const uint64_t* rngs);
+/* reset_cutrace_state-style (yocto_cutrace.h:119): zero the accumulators, samples = 0, re-seed the per-pixel rng
+ * streams from params->seed exactly as make_trace_state does (yocto_trace.cpp:1512-1515). */
+int  ygl_state_reset(ygl_state* state, const ygl_trace_params* params);
 void ygl_state_destroy(ygl_state* state);
 /* Host-only helper (no device): image size and the per-pixel rng table of make_trace_state. */
 int  ygl_make_state_rngs(const ygl_scene_desc* desc, const ygl_trace_params* params, int* width,
@@ -262,6 +273,29 @@ int  ygl_make_state_rngs(const ygl_scene_desc* desc, const ygl_trace_params* par
  * results stay on the device until ygl_state_download / ygl_gather_image. */
 int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
     const ygl_lights* lights, const ygl_trace_params* params);
+/* trace_sample (yocto_trace.h:173-175): ONE sample `sample` of pixel (i, j) of the full image — camera sample,
+ * sampler, running-mean accumulation with weight 1 / (sample + 1) — on the pixel's own rng stream. state.samples is
+ * not changed (the reference's trace_sample does not change it either). The pixel must belong to the state's tile. */
+int ygl_trace_sample(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
+    const ygl_lights* lights, int i, int j, int sample, const ygl_trace_params* params);
+/* ---- progressive rendering: trace_start / trace_cancel / trace_done / trace_preview (yocto_trace.h:202-223,
+ * yocto_trace.cpp:1627-1676) ----
+ * ygl_trace_start returns at once; ONE batch (params->batch samples per pixel) renders on a worker thread of the
+ * context. Until ygl_trace_done() reports 1 (or ygl_trace_cancel / ygl_trace_wait returned) the context, the state and
+ * the scene objects belong to the worker — the reference's rule (exclusive access to `state`). ygl_trace_cancel raises
+ * the stop flag — polled by the host between wavefront iterations, or turned into the abort flag of the persistent
+ * kernel — and joins the worker; as in the reference, a cancelled batch leaves the pixels at mixed sample counts
+ * (state.samples is advanced by the batch all the same, yocto_trace.cpp:1641) and the caller resets the state.
+ * ygl_trace_wait joins without cancelling and returns the batch's status. */
+int ygl_trace_start(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
+    const ygl_lights* lights, const ygl_trace_params* params);
+int ygl_trace_cancel(ygl_context* ctx);
+int ygl_trace_wait(ygl_context* ctx);
+int ygl_trace_done(ygl_context* ctx); /* 1 once the started batch has completed, else 0 */
+/* trace_preview: 1 sample at params->resolution / params->pratio, replicated (nearest) into the full-size rgba image
+ * of width x height pixels, exactly like yocto_trace.cpp:1657-1676. */
+int ygl_trace_preview(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_lights* lights,
+    const ygl_trace_params* params, int width, int height, float* image);
 /* trace_image: bvh + lights + state + all samples + get_image, from host scene views to a host
  * rgba float image (image may be NULL to query the size). */
 int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
@@ -280,10 +314,15 @@ int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_trav
 /* Scheduling mode of ygl_trace_samples / ygl_trace_image (both give bit-identical results):
  * YGL_MODE_WAVEFRONT (default) - one kernel per stage and iteration, linked by compacted lane queues;
  * YGL_MODE_PERSISTENT - ONE resident kernel per call, stage-specialised SMs linked by ring queues in global memory
- * (independent of the tile size, no per-iteration launches; opt-in). The environment variable YGL_MODE
- * (wavefront|persistent) sets the default of new contexts. */
+ * (independent of the tile size, no per-iteration launches; opt-in). */
 enum { YGL_MODE_WAVEFRONT = 0, YGL_MODE_PERSISTENT = 1 };
 int ygl_context_set_mode(ygl_context* ctx, int mode);
+/* Scheduling knobs of a context, by name (the library reads no environment variables). None can change a result
+ * bit. Names: "ext_blocks_per_sm", "refill", "node_reps", "suspend", "suspend_rounds", "lone", "lone_steps", "fuse",
+ * "bin", "pipes", "graph", "top_smem", "persist_blocks_per_sm", "persist_ext_sms", "persist_lpdf_warps",
+ * "watchdog_s" (struct Tuning in ygl_kernels.cuh documents each). -1 restores the automatic choice where one exists. */
+int ygl_context_set_option(ygl_context* ctx, const char* name, double value);
+int ygl_context_get_option(ygl_context* ctx, const char* name, double* value);
 /* Timings of the last ygl_trace_samples / ygl_trace_image with time_kernels on:
  * [0] sum of extend-kernel launch durations (ms), [1] whole sample loop (ms), [2] extend launches. */
 int ygl_trace_timings(ygl_context* ctx, double ms[4]);

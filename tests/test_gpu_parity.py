@@ -155,40 +155,82 @@ def test_persistent_mode_matches_reference(ref, sampler):
         np.testing.assert_array_equal(got["rngs"], want["rngs"])
 
 
-@pytest.mark.parametrize("env", [
-    dict(YGL_SUSPEND="8", YGL_SUSPEND_ROUNDS="8", YGL_LONE="0"),    # park the last lanes of a drained warp early and often
-    dict(YGL_SUSPEND="0", YGL_LONE="32", YGL_LONE_STEPS="40"),      # vote-free tail walk, parked after 40 steps
-    dict(YGL_SUSPEND="0", YGL_LONE="0", YGL_FUSE="0"),              # plain drain, separate accumulate / generate kernels
-    dict(YGL_FUSE="1", YGL_REFILL="4", YGL_NODE_REPS="1"),
-    # experimental shade-queue binning (off by default; written after the round's GPU budget was spent, so its first
-    # GPU run is this test: a failure here must not mask the rest of the suite)
-    pytest.param(dict(YGL_BIN="1", YGL_FUSE="0"), marks=pytest.mark.xfail(strict=False, reason="experimental, unmeasured")),
-    pytest.param(dict(YGL_BIN="1", YGL_FUSE="1"), marks=pytest.mark.xfail(strict=False, reason="experimental, unmeasured")),
+@pytest.mark.parametrize("options", [
+    dict(suspend=8, suspend_rounds=8, lone=0),      # park the last lanes of a drained warp early and often
+    dict(suspend=0, lone=32, lone_steps=40),        # vote-free tail walk, parked after 40 steps
+    dict(suspend=0, lone=0, fuse=0),                # plain drain, finished paths go through k_finish
+    dict(fuse=1, refill=4, node_reps=1),
+    dict(bin=0, fuse=0),                            # one shade queue, the unspecialised kernel
+    dict(bin=0, fuse=1),
+    dict(bin=1, fuse=0, suspend=8, suspend_rounds=4),  # class-binned queues + parked rays re-entering the extend queue
+    dict(bin=1, fuse=1, pipes=2),
+    dict(ext_blocks_per_sm=2, bin=1),
 ])
-def test_tail_strategies_are_bit_exact(ref, env, tmp_path):
-    """The extend kernel's tail strategies (parking stragglers for the next launch, the vote-free walk, its step
-    cap) and the path-end fusion are chosen by tile size at run time; each is a scheduling change only. They are
-    read from the environment once per process, so each setting renders in its own process."""
-    import subprocess
-    import sys as _sys
-    out = tmp_path / "img.npy"
-    code = (
-        "import sys, numpy as np\n"
-        "sys.path[:0] = [%r, %r]\n"
-        "from ygl_b200 import abi, lib, scenes\n"
-        "ctx = lib.Context(0)\n"
-        "p = abi.trace_params(resolution=160, samples=4, bounces=8, batch=2)\n"
-        "sc = scenes.features()\n"
-        "ds = lib.DeviceScene(ctx, sc)\n"
-        "st = ds.make_state(p)\n"
-        "ds.trace_samples(st, p); ds.trace_samples(st, p)\n"
-        "np.save(%r, st.download(full=True)['image'])\n"
-    ) % (os.path.join(ROOT, "yocto-gl_b200"), os.path.join(ROOT, "oracle"), str(out))
-    full_env = dict(os.environ, **env)
-    subprocess.run([_sys.executable, "-c", code], check=True, env=full_env, timeout=120)
+def test_scheduling_options_are_bit_exact(ref, options):
+    """Every scheduling knob of a context (ygl_context_set_option: the extend kernel's tail strategies, path-end
+    fusion, class-binned shade queues and per-class kernels, pipelines, grid size) is a scheduling change only:
+    the image of two resumed batches equals the reference bit for bit whatever the setting."""
+    octx = lib.Context(0)
+    for k, v in options.items():
+        octx.set_option(k, v)
+        assert octx.get_option(k) == v
+    with pytest.raises(lib.YglError):
+        octx.set_option("no_such_option", 1)
+    scene = get_scene("features")
     params = abi.trace_params(resolution=160, samples=4, bounces=8, batch=2)
-    want = ref.scene(get_scene("features")).trace_image(params)["image"]
-    assert np.load(out).tobytes() == want.tobytes(), env
+    ds = lib.DeviceScene(octx, scene)
+    st = ds.make_state(params)
+    ds.trace_samples(st, params)
+    ds.trace_samples(st, params)
+    got = st.download(full=True)
+    want = ref.scene(scene).trace_image(params, full=True)
+    for k in ("image", "albedo", "normal", "hits"):
+        assert got[k].tobytes() == want[k].tobytes(), (k, options)
+    np.testing.assert_array_equal(got["rngs"], want["rngs"])
+
+
+def test_state_reset_trace_sample_and_adopted_bvh(ctx, ref):
+    """The rest of the low-level API (yocto_trace.h:160-190, yocto_cutrace.h:119): ygl_state_reset re-seeds and
+    renders the same bits again; per-pixel ygl_trace_sample calls in the reference's loop order reproduce
+    trace_samples; a bvh adopted verbatim from the reference's make_scene_bvh (ygl_bvh_create_from_host) renders
+    the same image, and a corrupted tree is refused."""
+    scene = get_scene("cornell")
+    params = abi.trace_params(resolution=24, samples=2, bounces=4, batch=2)
+    rs = ref.scene(scene)
+    want = rs.trace_image(params, full=True)
+    ds = lib.DeviceScene(ctx, scene)
+    st = ds.make_state(params)
+    ds.trace_samples(st, params)
+    assert st.download()["image"].tobytes() == want["image"].tobytes()
+    st.reset(params)
+    assert st.samples == 0 and not st.download()["image"].any()
+    ds.trace_samples(st, params)
+    assert st.download()["image"].tobytes() == want["image"].tobytes()
+    # trace_sample, pixel by pixel (yocto_trace.cpp:1600-1606: the noparallel loop of trace_samples)
+    st.reset(params)
+    for j in range(0, st.height, 5):
+        for i in range(st.width):
+            for sample in range(2):
+                ds.trace_sample(st, i, j, sample, params)
+    assert st.samples == 0
+    got = st.download(full=True)
+    assert got["image"][::5].tobytes() == want["image"][::5].tobytes()
+    assert got["hits"][::5].tobytes() == want["hits"][::5].tobytes()
+    assert not got["image"][1::5].any()
+    with pytest.raises(lib.YglError):
+        ds.trace_sample(st, st.width, 0, 0, params)
+    # the reference's own trees, adopted verbatim
+    trees = (rs.bvh_tree(-1), [rs.bvh_tree(k) for k in range(len(scene.shapes))])
+    ds2 = lib.DeviceScene(ctx, scene, trees=trees)
+    st2 = ds2.make_state(params)
+    ds2.trace_samples(st2, params)
+    assert st2.download()["image"].tobytes() == want["image"].tobytes()
+    rays = random_rays(scene, 20000)
+    assert compare_hits(rs.intersect(rays), ds2.intersect(rays)) == 0
+    bad_nodes, bad_prims = trees[1][0][0].copy(), trees[1][0][1].copy()
+    bad_prims[0] = 10 ** 6
+    with pytest.raises(lib.YglError):
+        lib.Bvh(scene, trees=(trees[0], [(bad_nodes, bad_prims)] + trees[1][1:]))
 
 
 def test_full_state_and_resume(ctx, ref):
@@ -389,6 +431,51 @@ def test_deep_tree_uses_the_full_reference_stack(ctx, ref):
     assert ctx.trace_image(scene, params).tobytes() == rs.trace_image(params)["image"].tobytes()
     with pytest.raises(lib.YglError):
         lib.DeviceScene(ctx, scenes.sliver_chain(170))
+
+
+@pytest.mark.parametrize("mode", ["wavefront", "persistent"])
+def test_progressive_api(ref, mode):
+    """trace_start / trace_done / trace_cancel / trace_preview (yocto_trace.cpp:1627-1676): batches started
+    asynchronously and waited for give the reference's bits; a cancelled batch returns promptly and leaves a state
+    that ygl_state_reset makes good again; the preview is the 1-spp render at resolution / pratio, replicated."""
+    import time
+    pctx = lib.Context(0)
+    pctx.set_mode(mode)
+    scene = get_scene("features")
+    params = abi.trace_params(resolution=192, samples=4, bounces=6, batch=2)
+    rs = ref.scene(scene)
+    want = rs.trace_image(params, full=True)
+    ds = lib.DeviceScene(pctx, scene)
+    st = ds.make_state(params)
+    while st.samples < params.samples:
+        ds.trace_start(st, params)
+        t0 = time.time()
+        while not pctx.trace_done():
+            assert time.time() - t0 < 60
+            time.sleep(0.001)
+        pctx.trace_wait()
+    assert st.download()["image"].tobytes() == want["image"].tobytes()
+    # cancel a long batch right after starting it
+    big = abi.trace_params(resolution=192, samples=4096, bounces=6, batch=4096)
+    st2 = ds.make_state(big)
+    ds.trace_start(st2, big)
+    time.sleep(0.05)
+    t0 = time.time()
+    pctx.trace_cancel()
+    assert time.time() - t0 < 20 and not pctx.trace_done()
+    assert st2.samples == 4096  # yocto_trace.cpp:1641: the batch is counted even when abandoned
+    st2.reset(params)
+    ds.trace_samples(st2, params)
+    ds.trace_samples(st2, params)
+    assert st2.download()["image"].tobytes() == want["image"].tobytes()
+    # preview
+    pv = abi.trace_params(resolution=192, samples=4, bounces=6, batch=2, pratio=4)
+    W, H = st.width, st.height
+    got = ds.trace_preview(pv, W, H)
+    small = rs.trace_image(abi.trace_params(resolution=192 // 4, samples=1, bounces=6, batch=1))["image"]
+    jj = np.clip(np.arange(H) // 4, 0, small.shape[0] - 1)
+    ii = np.clip(np.arange(W) // 4, 0, small.shape[1] - 1)
+    assert got.tobytes() == small[jj][:, ii].tobytes()
 
 
 def test_unsupported_sampler_and_errors(ctx):

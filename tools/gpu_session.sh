@@ -1,0 +1,35 @@
+#!/bin/bash
+# Development tool: one gpurun call = several bounded steps, every one under its own timeout so that a hung kernel can
+# never reach gpurun's limit. Results land in gpurun_out/<tag>_*.  usage: tools/gpu_session.sh <tag> <step> [<step> ...]
+# steps: tests | tests_fast | bench | ab | launches | ncu | scale2
+TAG=$1; shift
+mkdir -p gpurun_out
+PERF="python tools/gpu_perf.py"
+for STEP in "$@"; do
+  echo "=== $STEP"
+  case $STEP in
+    tests)
+      timeout -s KILL 1500 python -m pytest tests -m gpu -q --maxfail=8 -x --durations=8 > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/${TAG}_tests.log | cut -c1-220 ;;
+    tests_fast)
+      timeout -s KILL 900 python -m pytest tests -m gpu -q --maxfail=8 -k "not full_size and not libm and not counters" > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/${TAG}_tests.log | cut -c1-220 ;;
+    bench)
+      timeout -s KILL 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -c 2500 gpurun_out/${TAG}_bench.json ;;
+    ab)
+      for LIB in lib lib_cls2; do
+        [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
+        for OPTS in "" "bin=0"; do
+          echo "--- $LIB $OPTS"
+          YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c3 1920 16 2 profile=1 $OPTS 2>&1 | tail -n 2 | cut -c1-260
+          YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c3 1920 32 2 tile=0,8 profile=1 $OPTS 2>&1 | tail -n 1 | cut -c1-260
+        done
+      done
+      timeout -s KILL 120 $PERF c1 256 16 2 2>&1 | tail -n 1 | cut -c1-200
+      timeout -s KILL 120 $PERF c2 1280 16 2 2>&1 | tail -n 1 | cut -c1-200
+      timeout -s KILL 120 $PERF c5 1920 8 2 2>&1 | tail -n 1 | cut -c1-200 ;;
+    launches)
+      timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
+      python tools/ncu_summary.py --launches gpurun_out/${TAG}_launches.csv | head -n 20 ;;
+    ncu)
+      timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shade|k_lightpdf|k_finish' -s 40 -c 8 -o gpurun_out/${TAG}_kernels $PERF c3 1920 2 0 > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"; tail -n 2 gpurun_out/${TAG}_ncu.log | cut -c1-200 ;;
+  esac
+done

@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -77,6 +78,7 @@ struct ygl_context {
   struct Pipe {
     cudaStream_t stream      = nullptr;
     int          queue_lanes = 0;
+    unsigned     queue_classes = 0;  // shade queues allocated (bit c = class c)
     int*         queue_mem   = nullptr;
     Counters*    counters    = nullptr;
     int*         h_done      = nullptr;  // pinned, 2 slots
@@ -87,6 +89,7 @@ struct ygl_context {
   double    timings[4]  = {0};
   bool      time_kernels = false, count_traversal = false;
   int       mode = YGL_MODE_WAVEFRONT;
+  Tuning    tune;  // scheduling knobs (ygl_context_set_option)
   unsigned long long*      d_trav = nullptr;  // 7 traversal counters
   std::vector<cudaEvent_t> ev_pool;           // event pairs around extend launches
   cudaEvent_t              ev_loop[2] = {nullptr, nullptr};
@@ -100,7 +103,14 @@ struct ygl_context {
   uint64_t          bound_epoch  = 0, bound_bvh_epoch = 0, bound_lights_epoch = 0;
   DShape*           d_shapes     = nullptr;
   DLight*           d_lights     = nullptr;
+  unsigned char*    d_inst_class = nullptr;  // shading class per instance (1 + material type)
+  unsigned          class_mask   = 0;        // classes present in the bound scene (bit c = class c)
   DScene            dscene       = {};
+  // progressive rendering (ygl_trace_start / cancel / done): one worker thread per context at a time
+  std::thread      worker;
+  std::atomic<int> stop{0}, done{0};
+  int              worker_rc = YGL_OK;
+  std::string      worker_error;
   // nccl
   void* nccl_lib  = nullptr;
   void* nccl_comm = nullptr;
@@ -119,6 +129,10 @@ struct ygl_scene {
     int    np, nl, nt, nq, nnormals, ntexcoords, ncolors, nradius;
   };
   std::vector<ShapeOff> shapes;
+  std::vector<ygl_camera> cameras_host;  // image sizes are derived from the camera aspect (make_trace_state)
+  std::vector<uint8_t>  inst_class;   // shading class per instance: 1 + material type (kClsGeneric if out of range)
+  unsigned              class_mask = 0;  // classes that can occur (bit c), incl. kClsMiss and, with media, kClsGeneric
+  bool                  has_volumes = false;
   uint64_t              epoch = 0;
 };
 
@@ -184,7 +198,6 @@ int ygl_context_create(int device, ygl_context** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
-  if (const char* env = getenv("YGL_MODE")) ctx->mode = !strcmp(env, "persistent") ? YGL_MODE_PERSISTENT : YGL_MODE_WAVEFRONT;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int k = 0; k < ygl_context::kMaxPipes; k++) {
     auto& pipe = ctx->pipes[k];
@@ -208,6 +221,8 @@ void ygl_comm_destroy(ygl_context* ctx);
 
 void ygl_context_destroy(ygl_context* ctx) {
   if (!ctx) return;
+  ctx->stop = 1;
+  if (ctx->worker.joinable()) ctx->worker.join();
   cudaSetDevice(ctx->device);
   ygl_comm_destroy(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -224,6 +239,7 @@ void ygl_context_destroy(ygl_context* ctx) {
   }
   if (ctx->d_shapes) cudaFree(ctx->d_shapes);
   if (ctx->d_lights) cudaFree(ctx->d_lights);
+  if (ctx->d_inst_class) cudaFree(ctx->d_inst_class);
   if (ctx->d_trav) cudaFree(ctx->d_trav);
   if (ctx->ring_mem) cudaFree(ctx->ring_mem);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
@@ -282,6 +298,7 @@ int ygl_scene_create(ygl_context* ctx, const ygl_scene_desc* desc, ygl_scene** o
   for (int i = 0; i < desc->num_cameras; i++) cams[i] = to_dcamera(desc->cameras[i]);
   scene->off_cameras = A.add(cams.data(), cams.size() * sizeof(DCamera));
   scene->num_cameras = desc->num_cameras;
+  scene->cameras_host.assign(desc->cameras, desc->cameras + desc->num_cameras);
 
   std::vector<DInstance> insts(desc->num_instances);
   for (int i = 0; i < desc->num_instances; i++) {
@@ -291,6 +308,20 @@ int ygl_scene_create(ygl_context* ctx, const ygl_scene_desc* desc, ygl_scene** o
   }
   scene->off_instances = A.add(insts.data(), insts.size() * sizeof(DInstance));
   scene->num_instances = desc->num_instances;
+  // shading classes (ygl_kernels.cuh): what kind of shading work a hit on each instance is
+  scene->inst_class.resize(desc->num_instances);
+  scene->class_mask = 1u << kClsMiss;
+  for (int i = 0; i < desc->num_instances; i++) {
+    const int type = desc->materials[desc->instances[i].material].type;
+    const int cls  = type >= 0 && type <= 7 ? 1 + type : kClsGeneric;
+    scene->inst_class[i] = (uint8_t)cls;
+    scene->class_mask |= 1u << cls;
+    // refractive, subsurface and volumetric surfaces open a participating medium (yocto_scene.cpp:257-261): the
+    // lanes inside it are shaded by the unspecialised kernel
+    if (type == YGL_MATERIAL_REFRACTIVE || type == YGL_MATERIAL_SUBSURFACE || type == YGL_MATERIAL_VOLUMETRIC)
+      scene->has_volumes = true;
+  }
+  if (scene->has_volumes) scene->class_mask |= 1u << kClsGeneric;
 
   static_assert(sizeof(DMaterial) == sizeof(ygl_material), "material layout");
   scene->off_materials = A.add(desc->materials, (size_t)desc->num_materials * sizeof(DMaterial));
@@ -364,6 +395,7 @@ int ygl_scene_update_cameras(ygl_scene* scene, const ygl_camera* cameras, int nu
   for (int i = 0; i < num_cameras; i++) cams[i] = to_dcamera(cameras[i]);
   CUDA_TRY(cudaMemcpy(scene->arena.dev + scene->off_cameras, cams.data(), cams.size() * sizeof(DCamera),
       cudaMemcpyHostToDevice));
+  scene->cameras_host.assign(cameras, cameras + num_cameras);
   return YGL_OK;
 }
 
@@ -381,6 +413,28 @@ int ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
   auto        bvh = std::make_unique<ygl_bvh>();
   std::string error;
   if (!build_scene_bvh(*desc, highquality != 0, bvh->host, error)) return fail(YGL_ERR_INVALID, error);
+  bvh->epoch = g_epoch++;
+  *out       = bvh.release();
+  return YGL_OK;
+}
+int ygl_bvh_create_from_host(const ygl_scene_desc* desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
+    const int32_t* top_primitives, int num_top_primitives, const ygl_bvh_node* const* shape_nodes,
+    const int* shape_num_nodes, const int32_t* const* shape_primitives, const int* shape_num_primitives, ygl_bvh** out) {
+  if (!out) return fail(YGL_ERR_INVALID, "null output");
+  if (int rc = check_desc(desc)) return rc;
+  if (!top_nodes || num_top_nodes < 1 || (num_top_primitives > 0 && !top_primitives))
+    return fail(YGL_ERR_INVALID, "instance tree missing");
+  if (desc->num_shapes > 0 && (!shape_nodes || !shape_num_nodes || !shape_primitives || !shape_num_primitives))
+    return fail(YGL_ERR_INVALID, "shape trees missing");
+  for (int i = 0; i < desc->num_shapes; i++)
+    if (!shape_nodes[i] || shape_num_nodes[i] < 1 || shape_num_primitives[i] < 0 ||
+        (shape_num_primitives[i] > 0 && !shape_primitives[i]))
+      return fail(YGL_ERR_INVALID, "shape tree " + std::to_string(i) + " missing");
+  auto        bvh = std::make_unique<ygl_bvh>();
+  std::string error;
+  if (!adopt_scene_bvh(*desc, top_nodes, num_top_nodes, top_primitives, num_top_primitives, shape_nodes, shape_num_nodes,
+          shape_primitives, shape_num_primitives, bvh->host, error))
+    return fail(YGL_ERR_INVALID, error);
   bvh->epoch = g_epoch++;
   *out       = bvh.release();
   return YGL_OK;
@@ -542,6 +596,10 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
   }
   if (ctx->d_shapes) cudaFree(ctx->d_shapes), ctx->d_shapes = nullptr;
   if (ctx->d_lights) cudaFree(ctx->d_lights), ctx->d_lights = nullptr;
+  if (ctx->d_inst_class) cudaFree(ctx->d_inst_class), ctx->d_inst_class = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&ctx->d_inst_class, std::max<size_t>(1, scene->inst_class.size())));
+  CUDA_TRY(cudaMemcpy(ctx->d_inst_class, scene->inst_class.data(), scene->inst_class.size(), cudaMemcpyHostToDevice));
+  ctx->class_mask = scene->class_mask;
   CUDA_TRY(cudaMalloc((void**)&ctx->d_shapes, std::max<size_t>(1, shapes.size()) * sizeof(DShape)));
   CUDA_TRY(cudaMemcpy(ctx->d_shapes, shapes.data(), shapes.size() * sizeof(DShape), cudaMemcpyHostToDevice));
   int nlights = lights ? (int)lights->host.size() : 0;
@@ -574,6 +632,8 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
   D.top_num_nodes    = (int)bvh->host.top.nodes.size();
   D.lights           = ctx->d_lights;
   D.num_lights       = nlights;
+  D.inst_class       = nullptr;  // set per run (binned shade queues: path sampler only)
+  D.has_volumes      = scene->has_volumes ? 1 : 0;
   ctx->bound_scene = scene, ctx->bound_bvh = bvh, ctx->bound_lights = lights, ctx->bound_epoch = scene->epoch;
   ctx->bound_bvh_epoch = bvh->epoch, ctx->bound_lights_epoch = lights ? lights->epoch : 0;
   return YGL_OK;
@@ -593,12 +653,18 @@ int ygl_make_state_rngs(const ygl_scene_desc* desc, const ygl_trace_params* para
 }
 
 // Rows row_begin, row_begin + row_step, ... below row_end of the full image.
+static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_params* params, int row_begin,
+    int row_end, int row_step, ygl_state** out);
 static int state_create_rows(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params,
     int row_begin, int row_end, int row_step, ygl_state** out) {
   if (!ctx || !desc || !params || !out) return fail(YGL_ERR_INVALID, "null argument");
   int         w, h;
   std::string error;
   if (!state_size(*desc, *params, w, h, error)) return fail(YGL_ERR_INVALID, error);
+  return state_create_sized(ctx, w, h, params, row_begin, row_end, row_step, out);
+}
+static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_params* params, int row_begin,
+    int row_end, int row_step, ygl_state** out) {
   if (row_end < 0) row_end = h;
   if (row_begin < 0 || row_begin > row_end || row_end > h || row_step < 1) return fail(YGL_ERR_INVALID, "bad row range");
   const int num_rows = (row_end - row_begin + row_step - 1) / row_step;
@@ -737,6 +803,27 @@ int ygl_state_upload(ygl_state* state, int samples, const float* image, const fl
   return YGL_OK;
 }
 
+int ygl_state_reset(ygl_state* state, const ygl_trace_params* params) {
+  if (!state || !params) return fail(YGL_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(state->ctx->device));
+  cudaStream_t s  = state->ctx->stream;
+  PathState&   st = state->st;
+  const size_t n  = (size_t)st.num_lanes;
+  CUDA_TRY(cudaMemsetAsync((float4*)st.image, 0, n * 16, s));
+  CUDA_TRY(cudaMemsetAsync((float*)st.albedo, 0, n * 12, s));
+  CUDA_TRY(cudaMemsetAsync((float*)st.normal, 0, n * 12, s));
+  CUDA_TRY(cudaMemsetAsync((int*)st.hits, 0, n * 4, s));
+  std::vector<uint64_t> rngs((size_t)state->width * state->height * 2);
+  state_rngs(*params, state->width, state->height, rngs.data());
+  if (n)
+    CUDA_TRY(cudaMemcpy2DAsync((ulonglong2*)st.rngs, (size_t)state->width * 16,
+        rngs.data() + (size_t)state->row_begin * state->width * 2, (size_t)state->row_step * state->width * 16,
+        (size_t)state->width * 16, state->num_rows, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // `rngs` is pageable host memory: keep it alive until the copy is done
+  state->samples = 0;
+  return YGL_OK;
+}
+
 void ygl_state_destroy(ygl_state* state) {
   if (!state) return;
   cudaSetDevice(state->ctx->device);
@@ -745,12 +832,19 @@ void ygl_state_destroy(ygl_state* state) {
 }
 
 // ------------------------------------------------------------------------------------------
-static int ensure_queues(ygl_context::Pipe& pipe, int lanes) {
-  if (lanes <= pipe.queue_lanes) return YGL_OK;
+// Queue memory of a pipeline: gen[2], ext[2], lpdf, acc and one shade queue per class in `classes` (class 0 always).
+static int ensure_queues(ygl_context::Pipe& pipe, int lanes, unsigned classes) {
+  classes |= 1u;
+  if (lanes <= pipe.queue_lanes && (classes & ~pipe.queue_classes) == 0) return YGL_OK;
   if (pipe.queue_mem) cudaFree(pipe.queue_mem), pipe.queue_mem = nullptr;
+  lanes   = std::max(lanes, pipe.queue_lanes);
+  classes |= pipe.queue_classes;
   size_t per = ((size_t)lanes + 63) & ~size_t(63);
-  CUDA_TRY(cudaMalloc((void**)&pipe.queue_mem, per * 8 * sizeof(int)));  // 6 queues + sorted copy + key bytes
-  pipe.queue_lanes = lanes;
+  int    nq  = 6;
+  for (int c = 0; c < kNumClasses; c++) nq += (classes >> c) & 1;
+  CUDA_TRY(cudaMalloc((void**)&pipe.queue_mem, per * nq * sizeof(int)));
+  pipe.queue_lanes   = lanes;
+  pipe.queue_classes = classes;
   return YGL_OK;
 }
 static Queues make_queues(ygl_context::Pipe& pipe) {
@@ -762,31 +856,48 @@ static Queues make_queues(ygl_context::Pipe& pipe) {
   q.ext[1]   = pipe.queue_mem + 3 * per;
   q.lpdf     = pipe.queue_mem + 4 * per;
   q.acc      = pipe.queue_mem + 5 * per;
+  int next   = 6;
+  for (int c = 0; c < kNumClasses; c++) q.shade[c] = (pipe.queue_classes >> c) & 1 ? pipe.queue_mem + (next++) * per : nullptr;
   q.counters = pipe.counters;
   return q;
 }
 
-// The wavefront driver: runs `nsamples` more samples on every lane of the state.
-static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
-  PathState& st = state->st;
-  if (st.num_lanes == 0 || nsamples <= 0) return YGL_OK;
+static KParams make_kparams(const ygl_trace_params& params, int sample_end) {
   KParams kp;
   kp.camera = params.camera, kp.sampler = params.sampler, kp.falsecolor = params.falsecolor;
   kp.bounces = params.bounces, kp.clamp = params.clamp;
   kp.nocaustics = params.nocaustics, kp.envhidden = params.envhidden, kp.tentfilter = params.tentfilter;
-  kp.sample_end = state->samples + nsamples;
-  // The shading kernels can finish a path themselves (accumulate + next camera sample: two launches fewer per
+  kp.sample_end = sample_end;
+  kp.fuse       = 1;
+  return kp;
+}
+
+// The wavefront driver: runs `nsamples` more samples on every lane of the state.
+// `only_lane` >= 0: that lane alone renders sample `only_sample` (trace_sample); state->samples then stays as it is.
+static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples,
+    int only_lane = -1, int only_sample = 0) {
+  PathState& st = state->st;
+  if (st.num_lanes == 0 || nsamples <= 0) return YGL_OK;
+  const Tuning& tune       = ctx->tune;
+  const int  lane_begin    = only_lane >= 0 ? only_lane : 0;
+  const int  lane_end      = only_lane >= 0 ? only_lane + 1 : st.num_lanes;
+  const int  sample_begin  = only_lane >= 0 ? only_sample : state->samples;
+  KParams    kp            = make_kparams(params, sample_begin + nsamples);
+  // The shading kernels can finish a path themselves (accumulate + next camera sample: one launch fewer per
   // iteration) - measured on B200: 4-6 % faster on small tiles (1/8 of C3, Cornell), 7 % slower on the full 1080p
-  // frame, where the extra divergence in k_shade costs more than the launches. Hence: by lane count.
-  static const int bin_queue = getenv("YGL_BIN") ? atoi(getenv("YGL_BIN")) : 0;  // experimental, not yet measured
-  static const int fuse_env = getenv("YGL_FUSE") ? atoi(getenv("YGL_FUSE")) : -1;
-  const int        fuse     = fuse_env >= 0 ? fuse_env : (st.num_lanes <= 800000 ? 1 : 0);
-  kp.fuse = fuse;
+  // frame, where the extra divergence in the shading kernels costs more than the launch. Hence: by lane count.
+  const int fuse = tune.fuse >= 0 ? tune.fuse : (st.num_lanes <= 800000 ? 1 : 0);
+  kp.fuse        = fuse;
+  // Binned shade queues + one kernel per shading class: the path sampler (trace_path). The other samplers run the
+  // unspecialised kernel on one queue.
+  const bool binned     = params.sampler == YGL_SAMPLER_PATH && tune.bin != 0;
+  const unsigned classes = binned ? ctx->class_mask : 1u;
+  DScene     dscene     = ctx->dscene;
+  dscene.inst_class     = binned ? ctx->d_inst_class : nullptr;
 
   // Pipelines: lanes can be split over independent queue sets on separate streams (ramp-up/drain of one
-  // overlapping the other).
-  int npipes = 1;  // measured on B200 (C3, 1/8 tile): 2 pipelines were 7 % slower than 1 -> opt-in via YGL_PIPES
-  if (const char* env = getenv("YGL_PIPES")) npipes = std::max(1, std::min(ygl_context::kMaxPipes, atoi(env)));
+  // overlapping the other). Measured on B200 (C3, 1/8 tile): 2 pipelines were 7 % slower than 1 -> default 1.
+  const int npipes = std::max(1, std::min(ygl_context::kMaxPipes, tune.pipes));
   struct Run {
     ygl_context::Pipe* pipe;
     Queues             q;
@@ -797,9 +908,9 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   for (int j = 0; j < npipes; j++) {
     Run& r = runs[j];
     r.pipe = &ctx->pipes[j];
-    r.lo   = (int)((long long)st.num_lanes * j / npipes);
-    r.hi   = (int)((long long)st.num_lanes * (j + 1) / npipes);
-    if (int rc = ensure_queues(*r.pipe, r.hi - r.lo)) return rc;
+    r.lo   = lane_begin + (int)((long long)(lane_end - lane_begin) * j / npipes);
+    r.hi   = lane_begin + (int)((long long)(lane_end - lane_begin) * (j + 1) / npipes);
+    if (int rc = ensure_queues(*r.pipe, r.hi - r.lo, classes)) return rc;
     r.q = make_queues(*r.pipe);
     // persistent-style grids: a multiple of the SM count, capped by the work available
     int lanes  = r.hi - r.lo;
@@ -812,6 +923,12 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   const bool path_like = params.sampler == YGL_SAMPLER_PATH || params.sampler == YGL_SAMPLER_PATHDIRECT ||
                          params.sampler == YGL_SAMPLER_PATHMIS ||
                          params.sampler == YGL_SAMPLER_PATHTEST;  // samplers with a light-pdf stage
+  int shade_launches = 1;
+  if (binned) {
+    shade_launches = 0;
+    for (int c = 0; c < kNumClasses; c++) shade_launches += (classes >> c) & 1;
+  }
+  const int  per_iteration = 2 + shade_launches + (path_like ? 1 : 0) + (fuse ? 0 : 1);
   uint64_t   iterations = 0, launches = 0;
   const int  check_every = 4;
   const bool timing = ctx->time_kernels;
@@ -825,50 +942,47 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     CUDA_TRY(cudaStreamWaitEvent(runs[j].pipe->stream, runs[j].pipe->join, 0));
   }
   for (int j = 0; j < npipes; j++) {
-    launch_seed_lanes(runs[j].pipe->stream, runs[j].light, st, runs[j].q, 0, state->samples, runs[j].lo, runs[j].hi);
+    launch_seed_lanes(runs[j].pipe->stream, runs[j].light, st, runs[j].q, 0, sample_begin, runs[j].lo, runs[j].hi);
     launches++;
   }
+  // one wavefront iteration of a pipeline: extend -> shade (per class) -> light pdf -> finish
+  auto enqueue_iteration = [&](Run& r, cudaStream_t s, bool with_events) -> int {
+    launch_begin_iteration(s, r.q, r.parity);
+    if (with_events) CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used], s));
+    launch_extend(s, ctx->num_sms, tune, dscene, st, r.q, r.parity, trav);
+    if (with_events) {
+      CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used + 1], s));
+      ev_used += 2;
+    }
+    launch_shade(s, r.heavy, dscene, st, r.q, kp, r.parity, classes);
+    if (path_like) launch_lightpdf(s, r.heavy, dscene, st, r.q, kp, r.parity);
+    if (!fuse) launch_finish(s, r.light, dscene, st, r.q, kp, r.parity);
+    r.parity = 1 - r.parity;
+    launches += per_iteration;
+    return YGL_OK;
+  };
   int remaining = npipes;
   while (remaining > 0) {
+    if (ctx->stop.load(std::memory_order_relaxed)) break;  // trace_cancel: polled between rounds of iterations
     for (int k = 0; k < check_every; k++) {
       for (int j = 0; j < npipes; j++) {
         Run& r = runs[j];
         if (r.done) continue;
         cudaStream_t s = r.pipe->stream;
-        launch_begin_iteration(s, r.q, r.parity);
-        // only the first iteration has lanes to seed: afterwards the shading kernels accumulate a finished path
-        // and start the lane's next camera sample themselves (end_of_path)
-        if (r.first || !fuse) launch_generate(s, r.light, ctx->dscene, st, r.q, kp, r.parity), launches++;
+        if (r.first) {
+          // the lanes' first camera samples; afterwards a finished path's lane starts its next sample in the
+          // kernel that ends the path (end_of_path / k_finish)
+          launch_generate(s, r.light, dscene, st, r.q, kp, r.parity), launches++;
+          r.first = false;
+        }
         if (timing) {
           while (ctx->ev_pool.size() < ev_used + 2) {
             cudaEvent_t e;
             CUDA_TRY(cudaEventCreate(&e));
             ctx->ev_pool.push_back(e);
           }
-          CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used], s));
         }
-        launch_extend(s, r.heavy, ctx->dscene, st, r.q, r.parity, trav);
-        if (timing) {
-          CUDA_TRY(cudaEventRecord(ctx->ev_pool[ev_used + 1], s));
-          ev_used += 2;
-        }
-        if (bin_queue) {
-          // experimental: shade from a copy of the extend queue grouped by kind of work (see launch_bin_queue)
-          size_t per    = ((size_t)r.pipe->queue_lanes + 63) & ~size_t(63);
-          int*   sorted = r.pipe->queue_mem + 6 * per;
-          launch_bin_queue(s, r.light, ctx->dscene, st, r.q, r.parity, sorted, (unsigned char*)(r.pipe->queue_mem + 7 * per));
-          Queues qs         = r.q;
-          qs.ext[r.parity]  = sorted;
-          launch_shade(s, r.heavy, ctx->dscene, st, qs, kp, r.parity);
-          launches += 2;
-        } else {
-          launch_shade(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
-        }
-        if (path_like) launch_lightpdf(s, r.heavy, ctx->dscene, st, r.q, kp, r.parity);
-        if (!fuse) launch_accumulate(s, r.light, ctx->dscene, st, r.q, kp, r.parity), launches++;
-        r.first  = false;
-        r.parity = 1 - r.parity;
-        launches += path_like ? 4 : 3;
+        if (int rc = enqueue_iteration(r, s, timing)) return rc;
       }
       iterations++;
     }
@@ -930,7 +1044,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     ctx->timings[2] += (double)(ev_used / 2);
     ctx->timings[3] = npipes;
   }
-  state->samples += nsamples;
+  if (only_lane < 0) state->samples += nsamples;
   return YGL_OK;
 }
 
@@ -941,12 +1055,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
 static int run_persistent(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
   PathState& st = state->st;
   if (st.num_lanes == 0 || nsamples <= 0) return YGL_OK;
-  KParams kp;
-  kp.camera = params.camera, kp.sampler = params.sampler, kp.falsecolor = params.falsecolor;
-  kp.bounces = params.bounces, kp.clamp = params.clamp;
-  kp.nocaustics = params.nocaustics, kp.envhidden = params.envhidden, kp.tentfilter = params.tentfilter;
-  kp.sample_end = state->samples + nsamples;
-  kp.fuse       = 1;
+  KParams kp = make_kparams(params, state->samples + nsamples);
 
   cudaStream_t s   = ctx->stream;
   // ring capacity: every lane can sit in a ring, and every consumer thread of the grid can hold a ticket that runs
@@ -978,14 +1087,14 @@ static int run_persistent(ygl_context* ctx, ygl_state* state, const ygl_trace_pa
 
   const bool timing = ctx->time_kernels;
   if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[0], s));
-  launch_persistent(s, ctx->num_sms, ctx->dscene, st, q, kp, 0, st.num_lanes, state->samples);
+  launch_persistent(s, ctx->num_sms, ctx->tune, ctx->dscene, st, q, kp, 0, st.num_lanes, state->samples);
   CUDA_TRY(cudaGetLastError());
   if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[1], s));
   cudaEvent_t fin = ctx->pipes[0].ev[0];
   CUDA_TRY(cudaEventRecord(fin, s));
 
   // ---- wait + watchdog ----
-  static const double watchdog_s = getenv("YGL_WATCHDOG_S") ? atof(getenv("YGL_WATCHDOG_S")) : 20.0;
+  const double watchdog_s = ctx->tune.watchdog_s;
   cudaStream_t side = ctx->pipes[1].stream;
   int*         h    = ctx->pipes[1].h_done;  // pinned, 2 ints
   long long    last_progress = -1;
@@ -1008,7 +1117,10 @@ static int run_persistent(ygl_context* ctx, ygl_state* state, const ygl_trace_pa
     if (progress != last_progress) {
       last_progress = progress;
       t_last        = now;
-    } else if (!aborted && std::chrono::duration<double>(now - t_last).count() > watchdog_s) {
+    }
+    // raise the abort flag when the job stalls (watchdog) or the caller cancels (trace_cancel)
+    if (!aborted && (ctx->stop.load(std::memory_order_relaxed) ||
+                        std::chrono::duration<double>(now - t_last).count() > watchdog_s)) {
       h[0] = 1;
       CUDA_TRY(cudaMemcpyAsync(q.abort, h, sizeof(int), cudaMemcpyHostToDevice, side));
       CUDA_TRY(cudaStreamSynchronize(side));
@@ -1021,7 +1133,7 @@ static int run_persistent(ygl_context* ctx, ygl_state* state, const ygl_trace_pa
   Counters c;
   CUDA_TRY(cudaMemcpy(&abort_flag, q.abort, sizeof(int), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(&c, counters, sizeof(Counters), cudaMemcpyDeviceToHost));
-  if (abort_flag || c.done_lanes != st.num_lanes)
+  if ((abort_flag || c.done_lanes != st.num_lanes) && !ctx->stop.load())
     return fail(YGL_ERR_RUNTIME, "persistent kernel stopped by the watchdog (no progress)");
   ctx->stats[0] += c.camera_samples;
   ctx->stats[1] += c.scene_rays;
@@ -1074,6 +1186,106 @@ int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene
   return run_render(ctx, state, *params, params->batch);
 }
 
+int ygl_trace_sample(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
+    const ygl_lights* lights, int i, int j, int sample, const ygl_trace_params* params) {
+  if (!ctx || !state || !params) return fail(YGL_ERR_INVALID, "null argument");
+  if (state->ctx != ctx) return fail(YGL_ERR_INVALID, "state belongs to another context");
+  if (int rc = check_sampler(*params)) return rc;
+  if (params->camera < 0 || params->camera >= (scene ? scene->num_cameras : 0))
+    return fail(YGL_ERR_INVALID, "camera id out of range");
+  if (i < 0 || i >= state->width || j < 0 || j >= state->height || sample < 0)
+    return fail(YGL_ERR_INVALID, "pixel or sample index out of range");
+  if (j < state->row_begin || j >= state->row_end || (j - state->row_begin) % state->row_step != 0)
+    return fail(YGL_ERR_INVALID, "pixel row is not part of this state's tile");
+  const int lane = ((j - state->row_begin) / state->row_step) * state->width + i;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (int rc = bind_scene(ctx, scene, bvh, lights)) return rc;
+  memset(ctx->stats, 0, sizeof(ctx->stats));
+  memset(ctx->timings, 0, sizeof(ctx->timings));
+  return run_wavefront(ctx, state, *params, 1, lane, sample);
+}
+
+// ---- progressive rendering: trace_start / trace_cancel / trace_done / trace_preview (yocto_trace.cpp:1627-1676) ----
+int ygl_trace_start(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
+    const ygl_lights* lights, const ygl_trace_params* params) {
+  if (!ctx || !state || !params) return fail(YGL_ERR_INVALID, "null argument");
+  if (state->ctx != ctx) return fail(YGL_ERR_INVALID, "state belongs to another context");
+  if (ctx->worker.joinable()) {
+    if (!ctx->done.load() && !ctx->stop.load()) return fail(YGL_ERR_INVALID, "a batch is already running: cancel or wait first");
+    ctx->worker.join();
+  }
+  if (int rc = check_sampler(*params)) return rc;
+  if (params->camera < 0 || params->camera >= (scene ? scene->num_cameras : 0))
+    return fail(YGL_ERR_INVALID, "camera id out of range");
+  if (state->samples >= params->samples) return YGL_OK;  // yocto_trace.cpp:1630
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (int rc = bind_scene(ctx, scene, bvh, lights)) return rc;
+  memset(ctx->stats, 0, sizeof(ctx->stats));
+  memset(ctx->timings, 0, sizeof(ctx->timings));
+  ctx->stop = 0, ctx->done = 0;
+  ctx->worker_rc = YGL_OK;
+  ctx->worker_error.clear();
+  const ygl_trace_params p = *params;
+  ctx->worker = std::thread([ctx, state, p]() {
+    // like the reference's worker (yocto_trace.cpp:1633-1648): one batch, abandoned early when stop is raised
+    int rc = cudaSetDevice(ctx->device) == cudaSuccess ? run_render(ctx, state, p, p.batch) : fail(YGL_ERR_CUDA, "cudaSetDevice");
+    ctx->worker_rc = rc;
+    if (rc) ctx->worker_error = g_error;  // g_error is per thread: hand the message to the caller's thread
+    if (!ctx->stop.load() && rc == YGL_OK) ctx->done = 1;
+  });
+  return YGL_OK;
+}
+static int worker_join(ygl_context* ctx) {
+  if (ctx->worker.joinable()) ctx->worker.join();
+  if (ctx->worker_rc) return fail(ctx->worker_rc, ctx->worker_error);
+  return YGL_OK;
+}
+int ygl_trace_cancel(ygl_context* ctx) {
+  if (!ctx) return fail(YGL_ERR_INVALID, "null context");
+  ctx->stop = 1;  // polled between wavefront iterations (wavefront mode) / raises the abort flag (persistent mode)
+  int rc    = worker_join(ctx);
+  ctx->stop = 0;
+  return rc;
+}
+int ygl_trace_wait(ygl_context* ctx) {
+  if (!ctx) return fail(YGL_ERR_INVALID, "null context");
+  return worker_join(ctx);
+}
+int ygl_trace_done(ygl_context* ctx) { return ctx && ctx->done.load() ? 1 : 0; }
+
+int ygl_trace_preview(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_lights* lights,
+    const ygl_trace_params* params, int width, int height, float* image) {
+  if (!ctx || !scene || !params || !image) return fail(YGL_ERR_INVALID, "null argument");
+  if (ctx->worker.joinable() && !ctx->done.load()) return fail(YGL_ERR_INVALID, "a batch is running: cancel or wait first");
+  if (params->camera < 0 || params->camera >= scene->num_cameras) return fail(YGL_ERR_INVALID, "camera id out of range");
+  if (params->pratio < 1) return fail(YGL_ERR_INVALID, "pratio must be >= 1");
+  // yocto_trace.cpp:1661-1675: 1 sample at resolution / pratio, then nearest-neighbour replication to the full frame
+  ygl_trace_params pp = *params;
+  pp.resolution /= params->pratio;
+  pp.samples = 1, pp.batch = 1;
+  if (pp.resolution < 1) return fail(YGL_ERR_INVALID, "resolution / pratio must be >= 1");
+  ygl_scene_desc cam_only = {};
+  cam_only.num_cameras    = scene->num_cameras;
+  cam_only.cameras        = scene->cameras_host.data();
+  int         pw, ph;
+  std::string error;
+  if (!state_size(cam_only, pp, pw, ph, error)) return fail(YGL_ERR_INVALID, error);
+  ygl_state* pstate = nullptr;
+  if (int rc = state_create_sized(ctx, pw, ph, &pp, 0, -1, 1, &pstate)) return rc;
+  int rc = ygl_trace_samples(ctx, pstate, scene, bvh, lights, &pp);
+  std::vector<float> preview((size_t)pw * ph * 4);
+  if (!rc) rc = ygl_state_download(pstate, preview.data(), nullptr, nullptr, nullptr, nullptr);
+  std::string keep = g_error;
+  ygl_state_destroy(pstate);
+  if (rc) return fail(rc, keep);
+  for (int j = 0; j < height; j++)
+    for (int i = 0; i < width; i++) {
+      const int pi = std::max(0, std::min(i / params->pratio, pw - 1)), pj = std::max(0, std::min(j / params->pratio, ph - 1));
+      memcpy(image + ((size_t)j * width + i) * 4, preview.data() + ((size_t)pj * pw + pi) * 4, 16);
+    }
+  return YGL_OK;
+}
+
 int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]) {
   if (!ctx || !counters) return fail(YGL_ERR_INVALID, "null argument");
   memcpy(counters, ctx->stats, sizeof(ctx->stats));
@@ -1084,6 +1296,43 @@ int ygl_context_set_mode(ygl_context* ctx, int mode) {
   if (mode != YGL_MODE_WAVEFRONT && mode != YGL_MODE_PERSISTENT) return fail(YGL_ERR_INVALID, "unknown mode");
   ctx->mode = mode;
   return YGL_OK;
+}
+
+namespace {
+struct OptionRef {
+  const char* name;
+  int Tuning::*  i;
+  double Tuning::* d;
+};
+const OptionRef kOptions[] = {
+    {"ext_blocks_per_sm", &Tuning::ext_blocks_per_sm, nullptr}, {"refill", &Tuning::refill, nullptr},
+    {"node_reps", &Tuning::node_reps, nullptr}, {"suspend", &Tuning::suspend, nullptr},
+    {"suspend_rounds", &Tuning::suspend_rounds, nullptr}, {"lone", &Tuning::lone, nullptr},
+    {"lone_steps", &Tuning::lone_steps, nullptr}, {"fuse", &Tuning::fuse, nullptr}, {"bin", &Tuning::bin, nullptr},
+    {"pipes", &Tuning::pipes, nullptr}, {"graph", &Tuning::graph, nullptr}, {"top_smem", &Tuning::top_smem, nullptr},
+    {"persist_blocks_per_sm", &Tuning::persist_blocks_per_sm, nullptr},
+    {"persist_ext_sms", &Tuning::persist_ext_sms, nullptr}, {"persist_lpdf_warps", &Tuning::persist_lpdf_warps, nullptr},
+    {"watchdog_s", nullptr, &Tuning::watchdog_s},
+};
+}  // namespace
+int ygl_context_set_option(ygl_context* ctx, const char* name, double value) {
+  if (!ctx || !name) return fail(YGL_ERR_INVALID, "null argument");
+  for (auto& o : kOptions)
+    if (!strcmp(o.name, name)) {
+      if (o.i) ctx->tune.*(o.i) = (int)value;
+      else ctx->tune.*(o.d) = value;
+      return YGL_OK;
+    }
+  return fail(YGL_ERR_INVALID, std::string("unknown option: ") + name);
+}
+int ygl_context_get_option(ygl_context* ctx, const char* name, double* value) {
+  if (!ctx || !name || !value) return fail(YGL_ERR_INVALID, "null argument");
+  for (auto& o : kOptions)
+    if (!strcmp(o.name, name)) {
+      *value = o.i ? (double)(ctx->tune.*(o.i)) : ctx->tune.*(o.d);
+      return YGL_OK;
+    }
+  return fail(YGL_ERR_INVALID, std::string("unknown option: ") + name);
 }
 
 int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_traversal) {

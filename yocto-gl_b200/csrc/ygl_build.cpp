@@ -6,8 +6,11 @@
 #include "ygl_build.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <functional>
 #include <limits>
+#include <thread>
 
 #include "ygl_sampling.cuh"
 
@@ -158,6 +161,22 @@ HostTree make_tree(const std::vector<box3>& bboxes, bool highquality) {
   return tree;
 }
 
+// run fn(0..n-1) on the host cores (dynamic: shapes differ wildly in size)
+void parallel_shapes(int n, const std::function<void(int)>& fn) {
+  const int nthreads = std::max(1, std::min<int>(n, (int)std::thread::hardware_concurrency()));
+  if (nthreads <= 1) {
+    for (int i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::atomic<int>         next{0};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++)
+    pool.emplace_back([&]() {
+      for (int i = next++; i < n; i = next++) fn(i);
+    });
+  for (auto& t : pool) t.join();
+}
+
 float as_float(int v) {
   float f;
   memcpy(&f, &v, 4);
@@ -191,113 +210,95 @@ void pack_instance(float4h* out, const ygl_instance& inst, int id, int kind, int
 
 }  // namespace
 
-bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error) {
-  const int nshapes = desc.num_shapes;
-  out.shapes.resize(nshapes);
-  out.shape_kind.assign(nshapes, 0);
-  out.shape_nodes.resize(nshapes);
-  out.shape_packets.resize(nshapes);
-  for (int si = 0; si < nshapes; si++) {
-    const ygl_shape& s = desc.shapes[si];
-    // make_shape_bvh, yocto_bvh.cpp:321-362: points > lines > triangles > quads
-    std::vector<box3> bboxes;
-    auto check = [&](int v) { return v >= 0 && v < s.num_positions; };
-    int  kind  = 0;
-    if (s.num_points > 0) {
-      kind = 1;
-      bboxes.resize(s.num_points);
-      if (s.num_radius < s.num_positions) {
-        error = "shape " + std::to_string(si) + ": points need a radius per vertex";
-        return false;
-      }
-      for (int i = 0; i < s.num_points; i++) {
-        int p = s.points[i];
-        if (!check(p)) return error = "point index out of range", false;
-        bboxes[i] = point_bounds(P(s.positions, p), s.radius[p]);
-      }
-    } else if (s.num_lines > 0) {
-      kind = 2;
-      bboxes.resize(s.num_lines);
-      if (s.num_radius < s.num_positions) {
-        error = "shape " + std::to_string(si) + ": lines need a radius per vertex";
-        return false;
-      }
-      for (int i = 0; i < s.num_lines; i++) {
-        int a = s.lines[2 * i], b = s.lines[2 * i + 1];
-        if (!check(a) || !check(b)) return error = "line index out of range", false;
-        bboxes[i] = line_bounds(P(s.positions, a), P(s.positions, b), s.radius[a], s.radius[b]);
-      }
-    } else if (s.num_triangles > 0) {
-      kind = 3;
-      bboxes.resize(s.num_triangles);
-      for (int i = 0; i < s.num_triangles; i++) {
-        int a = s.triangles[3 * i], b = s.triangles[3 * i + 1], c = s.triangles[3 * i + 2];
-        if (!check(a) || !check(b) || !check(c)) return error = "triangle index out of range", false;
-        bboxes[i] = triangle_bounds(P(s.positions, a), P(s.positions, b), P(s.positions, c));
-      }
-    } else if (s.num_quads > 0) {
-      kind = 4;
-      bboxes.resize(s.num_quads);
-      for (int i = 0; i < s.num_quads; i++) {
-        const int* q = s.quads + 4 * i;
-        if (!check(q[0]) || !check(q[1]) || !check(q[2]) || !check(q[3]))
-          return error = "quad index out of range", false;
-        bboxes[i] = quad_bounds(P(s.positions, q[0]), P(s.positions, q[1]), P(s.positions, q[2]), P(s.positions, q[3]));
-      }
+namespace {
+
+// element type a shape's tree is built over, make_shape_bvh, yocto_bvh.cpp:321-362: points > lines > triangles > quads
+int shape_bvh_kind(const ygl_shape& s) {
+  return s.num_points > 0 ? 1 : s.num_lines > 0 ? 2 : s.num_triangles > 0 ? 3 : s.num_quads > 0 ? 4 : 0;
+}
+
+bool shape_bounds(const ygl_shape& s, int si, int kind, std::vector<box3>& bboxes, std::string& error) {
+  auto check = [&](int v) { return v >= 0 && v < s.num_positions; };
+  if (kind == 1) {
+    bboxes.resize(s.num_points);
+    if (s.num_radius < s.num_positions) return error = "shape " + std::to_string(si) + ": points need a radius per vertex", false;
+    for (int i = 0; i < s.num_points; i++) {
+      int p = s.points[i];
+      if (!check(p)) return error = "point index out of range", false;
+      bboxes[i] = point_bounds(P(s.positions, p), s.radius[p]);
     }
-    out.shape_kind[si] = kind;
-    HostTree& tree     = out.shapes[si];
-    tree               = make_tree(bboxes, highquality);
-    // (an empty shape still gets a single empty root leaf, exactly like the reference's make_bvh)
-    out.shape_nodes[si] = pack_nodes(tree);
-    // leaf packets in primitive order
-    auto& pk = out.shape_packets[si];
-    if (kind == 3) {
-      pk.resize(tree.prims.size() * 3);
-      for (size_t k = 0; k < tree.prims.size(); k++) {
-        const int* t  = s.triangles + 3 * tree.prims[k];
-        f3         p0 = P(s.positions, t[0]), e1 = P(s.positions, t[1]) - p0, e2 = P(s.positions, t[2]) - p0;
-        pk[3 * k + 0] = {p0.x, p0.y, p0.z, e1.x};
-        pk[3 * k + 1] = {e1.y, e1.z, e2.x, e2.y};
-        pk[3 * k + 2] = {e2.z, 0, 0, 0};
-      }
-    } else if (kind == 4) {
-      pk.resize(tree.prims.size() * 4);
-      for (size_t k = 0; k < tree.prims.size(); k++) {
-        const int* q = s.quads + 4 * tree.prims[k];
-        for (int c = 0; c < 4; c++) {
-          f3 p          = P(s.positions, q[c]);
-          pk[4 * k + c] = {p.x, p.y, p.z, 0};
-        }
-      }
-    } else if (kind == 2) {
-      pk.resize(tree.prims.size() * 2);
-      for (size_t k = 0; k < tree.prims.size(); k++) {
-        const int* l  = s.lines + 2 * tree.prims[k];
-        f3         p0 = P(s.positions, l[0]), p1 = P(s.positions, l[1]);
-        pk[2 * k + 0] = {p0.x, p0.y, p0.z, s.radius[l[0]]};
-        pk[2 * k + 1] = {p1.x, p1.y, p1.z, s.radius[l[1]]};
-      }
-    } else if (kind == 1) {
-      pk.resize(tree.prims.size());
-      for (size_t k = 0; k < tree.prims.size(); k++) {
-        int p = s.points[tree.prims[k]];
-        f3  v = P(s.positions, p);
-        pk[k] = {v.x, v.y, v.z, s.radius[p]};
-      }
+  } else if (kind == 2) {
+    bboxes.resize(s.num_lines);
+    if (s.num_radius < s.num_positions) return error = "shape " + std::to_string(si) + ": lines need a radius per vertex", false;
+    for (int i = 0; i < s.num_lines; i++) {
+      int a = s.lines[2 * i], b = s.lines[2 * i + 1];
+      if (!check(a) || !check(b)) return error = "line index out of range", false;
+      bboxes[i] = line_bounds(P(s.positions, a), P(s.positions, b), s.radius[a], s.radius[b]);
     }
-    if (tree.max_stack > kMaxTreeDepth) {
-      error = "shape " + std::to_string(si) + ": BVH depth " + std::to_string(tree.max_stack) +
-              " exceeds the traversal stack (128 entries, as in the reference)";
-      return false;
+  } else if (kind == 3) {
+    bboxes.resize(s.num_triangles);
+    for (int i = 0; i < s.num_triangles; i++) {
+      int a = s.triangles[3 * i], b = s.triangles[3 * i + 1], c = s.triangles[3 * i + 2];
+      if (!check(a) || !check(b) || !check(c)) return error = "triangle index out of range", false;
+      bboxes[i] = triangle_bounds(P(s.positions, a), P(s.positions, b), P(s.positions, c));
+    }
+  } else if (kind == 4) {
+    bboxes.resize(s.num_quads);
+    for (int i = 0; i < s.num_quads; i++) {
+      const int* q = s.quads + 4 * i;
+      if (!check(q[0]) || !check(q[1]) || !check(q[2]) || !check(q[3])) return error = "quad index out of range", false;
+      bboxes[i] = quad_bounds(P(s.positions, q[0]), P(s.positions, q[1]), P(s.positions, q[2]), P(s.positions, q[3]));
     }
   }
+  return true;
+}
 
-  // instance boxes, yocto_bvh.cpp:382-389 (transform_bbox: merge of the 8 transformed corners)
-  std::vector<box3> ibox(desc.num_instances);
+// leaf packets in primitive order (ygl_scene.cuh)
+std::vector<float4h> pack_leaves(const ygl_shape& s, int kind, const HostTree& tree) {
+  std::vector<float4h> pk;
+  if (kind == 3) {
+    pk.resize(tree.prims.size() * 3);
+    for (size_t k = 0; k < tree.prims.size(); k++) {
+      const int* t  = s.triangles + 3 * tree.prims[k];
+      f3         p0 = P(s.positions, t[0]), e1 = P(s.positions, t[1]) - p0, e2 = P(s.positions, t[2]) - p0;
+      pk[3 * k + 0] = {p0.x, p0.y, p0.z, e1.x};
+      pk[3 * k + 1] = {e1.y, e1.z, e2.x, e2.y};
+      pk[3 * k + 2] = {e2.z, 0, 0, 0};
+    }
+  } else if (kind == 4) {
+    pk.resize(tree.prims.size() * 4);
+    for (size_t k = 0; k < tree.prims.size(); k++) {
+      const int* q = s.quads + 4 * tree.prims[k];
+      for (int c = 0; c < 4; c++) {
+        f3 p          = P(s.positions, q[c]);
+        pk[4 * k + c] = {p.x, p.y, p.z, 0};
+      }
+    }
+  } else if (kind == 2) {
+    pk.resize(tree.prims.size() * 2);
+    for (size_t k = 0; k < tree.prims.size(); k++) {
+      const int* l  = s.lines + 2 * tree.prims[k];
+      f3         p0 = P(s.positions, l[0]), p1 = P(s.positions, l[1]);
+      pk[2 * k + 0] = {p0.x, p0.y, p0.z, s.radius[l[0]]};
+      pk[2 * k + 1] = {p1.x, p1.y, p1.z, s.radius[l[1]]};
+    }
+  } else if (kind == 1) {
+    pk.resize(tree.prims.size());
+    for (size_t k = 0; k < tree.prims.size(); k++) {
+      int p = s.points[tree.prims[k]];
+      f3  v = P(s.positions, p);
+      pk[k] = {v.x, v.y, v.z, s.radius[p]};
+    }
+  }
+  return pk;
+}
+
+// instance boxes, yocto_bvh.cpp:382-389 (transform_bbox: merge of the 8 transformed corners)
+bool instance_bounds(const ygl_scene_desc& desc, const HostBvh& out, std::vector<box3>& ibox, std::string& error) {
+  ibox.resize(desc.num_instances);
   for (int i = 0; i < desc.num_instances; i++) {
     const ygl_instance& inst = desc.instances[i];
-    if (inst.shape < 0 || inst.shape >= nshapes) return error = "instance shape id out of range", false;
+    if (inst.shape < 0 || inst.shape >= desc.num_shapes) return error = "instance shape id out of range", false;
     if (inst.material < 0 || inst.material >= desc.num_materials)
       return error = "instance material id out of range", false;
     const HostTree& st = out.shapes[inst.shape];  // never empty: make_bvh always emits a root
@@ -310,8 +311,11 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
     for (auto& c : corners) xf = merge(xf, transform_point(fr, c));
     ibox[i] = xf;
   }
-  out.top = make_tree(ibox, highquality);
-  if (out.top.max_stack > kMaxTreeDepth) return error = "instance BVH too deep for the traversal stack (128 entries)", false;
+  return true;
+}
+
+// the device-ready data of the instance level (node float4s + instance packets)
+void pack_top(const ygl_scene_desc& desc, HostBvh& out) {
   out.top_nodes = pack_nodes(out.top);
   auto pack = [&](float4h* dst, int id) {
     const ygl_instance& inst = desc.instances[id];
@@ -321,6 +325,105 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
   for (size_t k = 0; k < out.top.prims.size(); k++) pack(&out.top_packets[kInstancePacketQuads * k], out.top.prims[k]);
   out.inst_packets.resize((size_t)desc.num_instances * kInstancePacketQuads);
   for (int i = 0; i < desc.num_instances; i++) pack(&out.inst_packets[kInstancePacketQuads * (size_t)i], i);
+}
+
+// depth of a tree (stack entries a traversal can need) + structural checks of an adopted tree
+bool measure_tree(HostTree& tree, int num_prims, const char* what, std::string& error) {
+  tree.max_stack = 0;
+  if (tree.nodes.empty()) return error = std::string(what) + ": a tree needs at least its root", false;
+  if ((int)tree.prims.size() != num_prims) return error = std::string(what) + ": primitive count differs from the shape", false;
+  for (int v : tree.prims)
+    if (v < 0 || v >= num_prims) return error = std::string(what) + ": primitive id out of range", false;
+  std::vector<std::pair<int, int>> todo = {{0, 1}};
+  size_t visited = 0;
+  while (!todo.empty()) {
+    auto [n, depth] = todo.back();
+    todo.pop_back();
+    if (++visited > tree.nodes.size()) return error = std::string(what) + ": node graph is not a tree", false;
+    tree.max_stack = std::max(tree.max_stack, depth);
+    const ygl_bvh_node& node = tree.nodes[n];
+    if (node.internal) {
+      if (node.start < 1 || node.start + 1 >= (int)tree.nodes.size()) return error = std::string(what) + ": child index out of range", false;
+      todo.push_back({node.start, depth + 1});
+      todo.push_back({node.start + 1, depth + 1});
+    } else {
+      if (node.num < 0 || node.num > 4 || node.start < 0 || node.start + node.num > num_prims)
+        return error = std::string(what) + ": leaf range invalid (leaves hold <= 4 primitives, yocto_bvh.cpp:236)", false;
+    }
+  }
+  if (tree.max_stack > kMaxTreeDepth)
+    return error = std::string(what) + ": BVH depth " + std::to_string(tree.max_stack) +
+                   " exceeds the traversal stack (128 entries, as in the reference)", false;
+  return true;
+}
+
+}  // namespace
+
+bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error) {
+  const int nshapes = desc.num_shapes;
+  out.shapes.resize(nshapes);
+  out.shape_kind.assign(nshapes, 0);
+  out.shape_nodes.resize(nshapes);
+  out.shape_packets.resize(nshapes);
+  // one tree per shape: independent, built on all host cores (the reference does the same, yocto_bvh.cpp:376-378)
+  std::vector<std::string> errors(nshapes);
+  parallel_shapes(nshapes, [&](int si) {
+    const ygl_shape&  s    = desc.shapes[si];
+    const int         kind = shape_bvh_kind(s);
+    std::vector<box3> bboxes;
+    if (!shape_bounds(s, si, kind, bboxes, errors[si])) return;
+    out.shape_kind[si] = kind;
+    HostTree& tree     = out.shapes[si];
+    tree               = make_tree(bboxes, highquality);
+    // (an empty shape still gets a single empty root leaf, exactly like the reference's make_bvh)
+    if (tree.max_stack > kMaxTreeDepth) {
+      errors[si] = "shape " + std::to_string(si) + ": BVH depth " + std::to_string(tree.max_stack) +
+                   " exceeds the traversal stack (128 entries, as in the reference)";
+      return;
+    }
+    out.shape_nodes[si]   = pack_nodes(tree);
+    out.shape_packets[si] = pack_leaves(s, kind, tree);
+  });
+  for (auto& e : errors)
+    if (!e.empty()) return error = e, false;
+
+  std::vector<box3> ibox;
+  if (!instance_bounds(desc, out, ibox, error)) return false;
+  out.top = make_tree(ibox, highquality);
+  if (out.top.max_stack > kMaxTreeDepth) return error = "instance BVH too deep for the traversal stack (128 entries)", false;
+  pack_top(desc, out);
+  return true;
+}
+
+// Adopt trees built elsewhere (the reference's make_scene_bvh output): checks + packets only.
+bool adopt_scene_bvh(const ygl_scene_desc& desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
+    const int32_t* top_prims, int num_top_prims, const ygl_bvh_node* const* shape_nodes, const int* shape_num_nodes,
+    const int32_t* const* shape_prims, const int* shape_num_prims, HostBvh& out, std::string& error) {
+  const int nshapes = desc.num_shapes;
+  out.shapes.resize(nshapes);
+  out.shape_kind.assign(nshapes, 0);
+  out.shape_nodes.resize(nshapes);
+  out.shape_packets.resize(nshapes);
+  for (int si = 0; si < nshapes; si++) {
+    const ygl_shape&  s    = desc.shapes[si];
+    const int         kind = shape_bvh_kind(s);
+    std::vector<box3> bboxes;  // only to validate the element indices
+    if (!shape_bounds(s, si, kind, bboxes, error)) return false;
+    out.shape_kind[si] = kind;
+    HostTree& tree     = out.shapes[si];
+    tree.nodes.assign(shape_nodes[si], shape_nodes[si] + shape_num_nodes[si]);
+    tree.prims.assign(shape_prims[si], shape_prims[si] + shape_num_prims[si]);
+    std::string what = "shape " + std::to_string(si);
+    if (!measure_tree(tree, (int)bboxes.size(), what.c_str(), error)) return false;
+    out.shape_nodes[si]   = pack_nodes(tree);
+    out.shape_packets[si] = pack_leaves(s, kind, tree);
+  }
+  std::vector<box3> ibox;  // validates instance ids
+  if (!instance_bounds(desc, out, ibox, error)) return false;
+  out.top.nodes.assign(top_nodes, top_nodes + num_top_nodes);
+  out.top.prims.assign(top_prims, top_prims + num_top_prims);
+  if (!measure_tree(out.top, desc.num_instances, "instance tree", error)) return false;
+  pack_top(desc, out);
   return true;
 }
 

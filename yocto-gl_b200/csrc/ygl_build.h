@@ -41,6 +41,10 @@ struct HostLight {
 
 // make_scene_bvh, yocto_bvh.cpp:364-396 (+ make_shape_bvh :321-362, make_bvh :238-302)
 bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error);
+// the same device-ready data from trees built elsewhere (ygl_bvh_create_from_host): validated, then packed
+bool adopt_scene_bvh(const ygl_scene_desc& desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
+    const int32_t* top_prims, int num_top_prims, const ygl_bvh_node* const* shape_nodes, const int* shape_num_nodes,
+    const int32_t* const* shape_prims, const int* shape_num_prims, HostBvh& out, std::string& error);
 // make_trace_lights, yocto_trace.cpp:1528-1581
 void build_lights(const ygl_scene_desc& desc, std::vector<HostLight>& lights);
 // image size + rng table of make_trace_state, yocto_trace.cpp:1495-1520

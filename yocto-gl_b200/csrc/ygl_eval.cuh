@@ -72,9 +72,12 @@ YGL_D f4 lookup_texture(const DTexture& tex, int i, int j, bool as_linear) {
 // SASS instructions and used to be inlined at six call sites of the shading kernels, whose profile is dominated by
 // instruction-fetch stalls; untextured materials (texture id < 0) never reach it. One out-of-line copy per kernel:
 // pure code layout, the arithmetic is unchanged.
-static __device__ __noinline__ f4 eval_texture_fetch(const DTexture* texp, float uvx, float uvy, bool as_linear,
+// RAW: the copy for callers that never ask for the sRGB decode (environment maps): texel values as stored, no powf.
+template <bool RAW>
+static __device__ __noinline__ f4 eval_texture_fetch(const DTexture* texp, float uvx, float uvy, bool as_linear_,
     bool no_interpolation, bool clamp_to_edge) {
-  const DTexture& tex = *texp;
+  const bool      as_linear = RAW ? false : as_linear_;
+  const DTexture& tex       = *texp;
   if (tex.width == 0 || tex.height == 0) return {0, 0, 0, 0};
   int   sx = tex.width, sy = tex.height;
   float s = 0.0f, t = 0.0f;
@@ -98,13 +101,19 @@ static __device__ __noinline__ f4 eval_texture_fetch(const DTexture* texp, float
 }
 YGL_D f4 eval_texture(const DTexture& tex, const f2& uv, bool as_linear, bool no_interpolation,
     bool clamp_to_edge) {
-  return eval_texture_fetch(&tex, uv.x, uv.y, as_linear, no_interpolation, clamp_to_edge);
+  return eval_texture_fetch<false>(&tex, uv.x, uv.y, as_linear, no_interpolation, clamp_to_edge);
 }
 // eval_texture(scene, id, uv, as_linear), yocto_scene.cpp:167-171
 YGL_D_BIG f4 eval_texture(const DScene& scene, int texture, const f2& uv, bool as_linear) {
   if (texture < 0) return {1, 1, 1, 1};
   const DTexture& tex = scene.textures[texture];
   return eval_texture(tex, uv, as_linear, tex.nearest != 0, tex.clamp != 0);
+}
+// eval_texture(scene, id, uv, false): the values as stored (no sRGB decode)
+YGL_D_BIG f4 eval_texture_raw(const DScene& scene, int texture, const f2& uv) {
+  if (texture < 0) return {1, 1, 1, 1};
+  const DTexture& tex = scene.textures[texture];
+  return eval_texture_fetch<true>(&tex, uv.x, uv.y, false, tex.nearest != 0, tex.clamp != 0);
 }
 
 // ---- interpolation, yocto_geometry.h:536-556 ----
@@ -389,7 +398,7 @@ YGL_D_BIG f3 eval_environment(const DScene& scene, const f3& direction) {
     auto wl       = transform_direction(env.inv_frame, direction);
     auto texcoord = f2{yatan2(wl.z, wl.x) / (2 * kPi), yacos(yclamp(wl.y, -1.0f, 1.0f)) / kPi};
     if (texcoord.x < 0) texcoord.x += 1;
-    emission = emission + env.emission * xyz(eval_texture(scene, env.emission_tex, texcoord, false));
+    emission = emission + env.emission * xyz(eval_texture_raw(scene, env.emission_tex, texcoord));
   }
   return emission;
 }

@@ -7,8 +7,8 @@
 //   lightpdf_lane    (instance traversal)    sample_lights_pdf + MIS weight + RR yocto_trace.cpp:391, 532-590
 //   accumulate_lane                          trace_sample tail                   yocto_trace.cpp:1469-1491
 //
-// Wavefront scheduler (default): k_generate / k_extend / k_shade / k_lightpdf / k_accumulate, linked by compacted lane
-// queues. Every kernel is persistent-style: a fixed grid (multiple of the SM count) strides over the queue whose
+// Wavefront scheduler (default): k_generate / k_extend / k_shade_path<class> (or k_shade<sampler>) / k_lightpdf /
+// k_finish, linked by compacted lane queues. Every kernel is persistent-style: a fixed grid (multiple of the SM count) strides over the queue whose
 // length it reads from device memory, so the host never synchronises inside the sample loop. Survivors are appended
 // to the next queue with one atomicAdd per warp (__ballot_sync + __popc + __shfl_sync).
 // Persistent scheduler (opt-in): k_persistent, one resident kernel with SM-specialised stages linked by ticket ring
@@ -66,7 +66,7 @@ __global__ void k_begin_iteration(Counters* c, int parity) {
   c->n_lpdf            = 0;
   c->n_acc             = 0;
   c->ext_head          = 0;
-  for (int k = 0; k < 16; k++) c->n_bin[k] = 0, c->bin_cursor[k] = 0;
+  for (int k = 0; k < kNumClasses; k++) c->n_shade[k] = 0;
 }
 
 __global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begin, int lane_lo, int lane_hi) {
@@ -81,6 +81,7 @@ __global__ void k_seed_lanes(PathState st, Queues q, int parity, int sample_begi
     c->n_gen[1 - parity] = 0;
     c->n_ext[0] = c->n_ext[1] = 0;
     c->n_lpdf = c->n_acc = 0;
+    for (int k = 0; k < kNumClasses; k++) c->n_shade[k] = 0;
     c->done_lanes        = 0;
     c->ext_head          = 0;
     c->camera_samples = c->scene_rays = c->instance_rays = c->shade_calls = 0;
@@ -137,12 +138,29 @@ __global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Qu
 // (extend_stream in ygl_traverse.cuh), so short rays (sky misses) do not idle lanes while long ones walk.
 // TAIL: how a drained warp ends a launch - 0 = park the stragglers for the next launch, 1 = vote-free walk (see
 // launch_extend). A compile-time choice so that each kernel variant carries only its own tail code.
+// Append to the shade queue of class `cls` (WARP-UNIFORM call; lanes with `pred` take part): the lanes of a warp
+// are grouped by class with __match_any_sync, one atomicAdd per class present in the warp.
+YGL_D void shade_push(const Queues& q, bool pred, int cls, int value) {
+  const unsigned active = __ballot_sync(kFullWarp, pred);
+  if (!active || !pred) return;
+  const unsigned peers  = __match_any_sync(active, cls);
+  const int      wl     = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  int            base   = 0;
+  if (wl == leader) base = atomicAdd(&q.counters->n_shade[cls], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  q.shade[cls][base + __popc(peers & ((1u << wl) - 1u))] = value;
+}
+
 template <int TAIL>
 struct ExtendSource {
   const int* __restrict__ queue;
   int        n;
   int*       head;
   PathState  st;
+  Queues     q;
+  int        parity;
+  const unsigned char* __restrict__ inst_class;  // shading class per instance, or null: every lane goes to class 0
+  int        has_volumes;
   int        lane;
   int        refill_thr, node_reps, suspend_below, lone_below, lone_steps;  // tuning knobs (see launch_extend)
   unsigned   finished;                              // rays completed by this thread (scene_rays counter)
@@ -156,9 +174,12 @@ struct ExtendSource {
     base         = __shfl_sync(kFullWarp, base, __ffs(m) - 1);
     const int my = base + __popc(m & ((1u << wl) - 1u));
     more         = base + __popc(m) < n;
-    if (!idle || my >= n) return false;
-    const int entry = queue[my];
-    if (entry & kEntryPass) return false;  // the lane skips this extend (its hit record is already in place)
+    const bool valid = idle && my < n;
+    const int  entry = valid ? queue[my] : 0;
+    // the lane skips this extend (its hit record is already in place): straight on to shading
+    const bool pass = valid && (entry & kEntryPass) != 0;
+    shade_push(q, pass, kClsGeneric, entry);
+    if (!valid || pass) return false;
     lane     = entry & kEntryLane;
     resume   = entry < 0;
     shadow   = (entry & kEntryShadow) != 0;
@@ -168,14 +189,27 @@ struct ExtendSource {
   }
   static constexpr bool kPolling = false;  // the queue is complete when the kernel starts
   static constexpr bool kPark = TAIL == 0, kLone = TAIL == 1;
+  // WARP-UNIFORM: lanes with `flag` store their hit and join the shade queue of their class
   YGL_D void commit_finished(bool flag, const hit_t& h) {
-    if (!flag) return;
-    (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
-    (shadow ? st.aux_ids : st.hit_ids)[lane] = make_int2(h.instance, h.element);
-    finished++;
+    int cls = kClsGeneric;
+    if (flag) {
+      (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
+      (shadow ? st.aux_ids : st.hit_ids)[lane] = make_int2(h.instance, h.element);
+      finished++;
+      if (inst_class) {
+        cls = h.hit ? (int)__ldg(inst_class + h.instance) : kClsMiss;
+        // a path inside a participating medium takes the unspecialised kernel (transmittance, scattering events)
+        if (has_volumes && (__float_as_int(float4(st.radiance[lane]).w) & kFlagVolume)) cls = kClsGeneric;
+      }
+    }
+    shade_push(q, flag, cls, lane | (shadow ? kEntryShadow : 0));
   }
   YGL_D int* saved() { return st.susp + (size_t)lane * kSuspendWords; }
-  YGL_D void commit_suspended() { (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(0, 0, 0, __int_as_float(2)); }
+  // per-lane (divergent) call: the parked ray goes straight back into the next extend queue, flagged for resumption
+  YGL_D void commit_suspended() {
+    const int pos           = atomicAdd(&q.counters->n_ext[1 - parity], 1);
+    q.ext[1 - parity][pos]  = lane | kEntryResume | (shadow ? kEntryShadow : 0);
+  }
 };
 
 #ifndef YGL_EXT_MINBLOCKS
@@ -186,7 +220,8 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene,
     unsigned long long* trav, int refill_thr, int node_reps, int suspend_below, int lone_below, int lone_steps) {
   Counters*     c = q.counters;
   const int     n = c->n_ext[parity];
-  ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, 0, refill_thr, node_reps, suspend_below, lone_below, lone_steps, 0, false};
+  ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, q, parity, scene.inst_class, scene.has_volumes, 0, refill_thr,
+      node_reps, suspend_below, lone_below, lone_steps, 0, false};
   trav_counters tc = {};
   trace_stream<COUNT, kStreamThreads>(scene, src, tc);
   {
@@ -322,14 +357,19 @@ YGL_D f3 hashed_color(int id) {
 }
 
 // ---- shade one lane. Returns the destination queue. ----
-template <int SAMPLER, class PS>
+// CLS: shading class the lane was queued under (ygl_kernels.cuh). kClsGeneric = any lane. 1 + t = the lane hit a
+// surface whose material has type t and is not inside a medium: the material switches fold to that type's lobes and
+// the medium code drops out. A specialised instantiation computes exactly what the generic one would for such a
+// lane (it only omits code the lane cannot reach). Misses of the path sampler have their own function (miss_lane).
+template <int SAMPLER, int CLS = kClsGeneric, class PS>
 YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int lane, unsigned& inst_rays) {
+  constexpr bool kSurface = CLS >= 1 && CLS <= 8;  // a surface hit of material type CLS - 1, outside any medium
   float4 ro = st.ray_o[lane], rd = st.ray_d[lane], rad4 = st.radiance[lane], w4 = st.weight[lane];
   float4 huvd = st.hit_uvd[lane];
   f3  o = unpack3(ro), d = unpack3(rd), radiance = unpack3(rad4), weight = unpack3(w4);
   int bounce = __float_as_int(ro.w), opbounce = __float_as_int(rd.w), flags = __float_as_int(rad4.w);
   float max_roughness = w4.w;
-  bool  hit           = __float_as_int(huvd.w) != 0;
+  bool  hit           = kSurface ? true : __float_as_int(huvd.w) != 0;
 
   // ---- falsecolor: single intersection, yocto_trace.cpp:1341-1419 ----
   if (SAMPLER == kSamplerFalsecolor) {
@@ -409,7 +449,7 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
   // ---- participating medium, yocto_trace.cpp:476-488 (path only). Draw order: rd, then rl. ----
   bool   in_volume = false;
   vsdf_t vsdf      = {};
-  if (SAMPLER == kSamplerPath && (flags & kFlagVolume)) {
+  if (SAMPLER == kSamplerPath && !kSurface && (flags & kFlagVolume)) {
     float4 va = st.vol_a[lane], vb = st.vol_b[lane];
     vsdf     = {unpack3(va), unpack3(vb), va.w};
     float r_d = rand1f(rng);
@@ -426,6 +466,7 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
                                                : eval_shading_position(scene, inst, ids.y, uv);
     auto normal   = eval_shading_normal(scene, inst, ids.y, uv, outgoing);
     auto material = eval_material(scene, inst, ids.y, uv);
+    if (kSurface) material.type = CLS - 1;  // what eval_material returned: now a compile-time constant
 
     if (SAMPLER == kSamplerPath && p.nocaustics) {
       max_roughness      = ymax(material.roughness, max_roughness);
@@ -536,8 +577,8 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
     }
 
     // ---- volume slot update, yocto_trace.cpp:545-553 (independent of the pending weight) ----
-    const DMaterial& mat = scene.materials[inst.material];
-    if (SAMPLER != kSamplerPathTest && is_volumetric_type(mat.type) &&
+    const int mat_type = kSurface ? CLS - 1 : scene.materials[inst.material].type;
+    if (SAMPLER != kSamplerPathTest && is_volumetric_type(mat_type) &&
         dot(normal, outgoing) * dot(normal, incoming) < 0) {
       if (!(flags & kFlagVolume)) {
         auto vm        = eval_material(scene, inst, ids.y, uv);
@@ -585,6 +626,19 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
   }
 }
 
+
+// trace_path for a ray that left the scene (class kClsMiss), yocto_trace.cpp:469-473: the environment seen along the
+// ray ends the path. Always returns kDestAcc.
+template <class PS>
+YGL_D int miss_lane(const DScene& scene, const PS& st, const KParams& p, int lane) {
+  float4 ro = st.ray_o[lane], rd = st.ray_d[lane], rad4 = st.radiance[lane], w4 = st.weight[lane];
+  const int bounce = __float_as_int(ro.w);
+  if (bounce > 0 || !p.envhidden) {
+    f3 radiance       = unpack3(rad4) + unpack3(w4) * eval_environment(scene, unpack3(rd));
+    st.radiance[lane] = pack(radiance, __float_as_int(rad4.w));
+  }
+  return kDestAcc;
+}
 
 // ---- pathdirect / pathmis: trace_pathdirect (yocto_trace.cpp:599-767) and trace_pathmis (:770-950). A non-delta
 // bounce needs extra light-pdf and shadow-ray stages, so a lane passes through shade several times per bounce;
@@ -864,12 +918,30 @@ YGL_D void flush_counts(Counters* c, int2 counts) {
 #define YGL_SHADE_THREADS 256
 #endif
 #ifndef YGL_SHADE_MINBLOCKS
-#define YGL_SHADE_MINBLOCKS 4  // measured on B200 (C3, ms per 32 spp): 256x1 361, 256x3 350, 256x4 338, 128x6 352
+#define YGL_SHADE_MINBLOCKS 4  // generic kernel, measured on B200 (C3, ms per 32 spp): 256x1 361, 256x3 350, 256x4 338, 128x6 352
 #endif
+#ifndef YGL_SHADE_CLS_MINBLOCKS
+#define YGL_SHADE_CLS_MINBLOCKS 3  // class kernels: 256 x 3 leaves 80 registers per thread (no spills, see the ptxas log)
+#endif
+// Common tail of the shading kernels: finish the path or pass the lane on (WARP-UNIFORM).
+// FUSE (must equal p.fuse != 0): a finished path is accumulated and the lane's next camera sample generated right here;
+// otherwise the lane goes to the acc queue for k_finish. A template parameter so that the kernels of a non-fused run
+// do not carry the accumulate + camera code (~1.5 K instructions) at all.
+template <bool FUSE>
+YGL_D void route_shaded(const DScene& scene, const PathState& st, const Queues& q, const KParams& p, int parity, int lane,
+    int dest, int entry, int2& counts) {
+  Counters* c = q.counters;
+  if (FUSE) end_of_path(scene, st, p, lane, dest, entry, counts);
+  queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
+  queue_push(q.lpdf, &c->n_lpdf, dest == kDestLpdf, lane);
+  if (!FUSE) queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
+}
+
+// The unspecialised shading kernel: every sampler, every kind of lane (queue of class 0).
 template <int SAMPLER>
 __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shade(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
-  const int n   = c->n_ext[parity];
+  const int n   = c->n_shade[kClsGeneric];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   const int wl  = threadIdx.x & 31;
   unsigned inst_rays = 0;
@@ -879,87 +951,42 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
     int lane = 0, dest = kDestNone;
     int entry = 0;
     if (i < n) {
-      const int in_entry = q.ext[parity][i];
-      lane               = in_entry & kEntryLane;
-      const bool shadow  = (in_entry & kEntryShadow) != 0;
-      if (!(in_entry & kEntryPass) && __float_as_int(float4((shadow ? st.aux_uvd : st.hit_uvd)[lane]).w) == 2) {
-        // the extend kernel suspended this ray: it stays in the extend queue, flagged for resumption
-        dest  = kDestExt;
-        entry = lane | kEntryResume | (in_entry & kEntryShadow);
-      } else {
-        int r = (SAMPLER == kSamplerPathDirect || SAMPLER == kSamplerPathMis)
-                    ? shade_multi<SAMPLER>(scene, st, p, lane)
-                    : shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
-        dest  = r & 3;
-        entry = lane | (r & (kEntryShadow | kEntryPass));
-      }
+      lane  = q.shade[kClsGeneric][i] & kEntryLane;
+      int r = (SAMPLER == kSamplerPathDirect || SAMPLER == kSamplerPathMis)
+                  ? shade_multi<SAMPLER>(scene, st, p, lane)
+                  : shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
+      dest  = r & 3;
+      entry = lane | (r & (kEntryShadow | kEntryPass));
     }
-    end_of_path(scene, st, p, lane, dest, entry, counts);
-    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
-    queue_push(q.lpdf, &c->n_lpdf, dest == kDestLpdf, lane);
-    if (!p.fuse) queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
+    if (p.fuse) route_shaded<true>(scene, st, q, p, parity, lane, dest, entry, counts);
+    else route_shaded<false>(scene, st, q, p, parity, lane, dest, entry, counts);
   }
   flush_counts(c, counts);
   if (tid == 0) atomicAdd(&c->shade_calls, (unsigned long long)n);
 }
 
-
-// ---- experimental (YGL_BIN=1): group the extend queue by the kind of shading work before k_shade ----
-// k_shade runs 8 of 32 lanes per instruction on C3 and is bound by instruction fetch: lanes of one warp hit different
-// materials or miss. Two small kernels copy the queue into `sorted`, grouped by key = miss | 1 + material type |
-// parked ray, so that a shading warp runs one kind of lane (the order inside a group is irrelevant: lanes are
-// independent). k_shade itself is unchanged - it is handed `sorted` as its input queue.
-constexpr int kBinMiss = 0, kBinParked = 9, kNumBins = 10;
-__global__ void __launch_bounds__(256) k_bin_count(DScene scene, PathState st, Queues q, int parity, unsigned char* keys) {
+// One kernel per shading class of the path sampler (trace_path): its warps hold lanes of one kind only, and it
+// contains that kind's code only (k_shade<path> carried ~25 K instructions for every lane and ran 8 of 32 lanes per
+// instruction; see DESIGN.md "shading classes").
+template <int CLS, bool FUSE>
+__global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_CLS_MINBLOCKS) k_shade_path(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
-  const int n   = c->n_ext[parity];
+  const int n   = c->n_shade[CLS];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   const int wl  = threadIdx.x & 31;
+  unsigned inst_rays = 0;
+  int2     counts    = make_int2(0, 0);
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
-    const int      i      = i0 + wl;
-    const bool     valid  = i < n;
-    const unsigned active = __ballot_sync(kFullWarp, valid);
-    if (!valid) continue;
-    const int  entry  = q.ext[parity][i];
-    const int  lane   = entry & kEntryLane;
-    const bool shadow = (entry & kEntryShadow) != 0;
-    int        key;
-    if (!(entry & kEntryPass) && __float_as_int(float4((shadow ? st.aux_uvd : st.hit_uvd)[lane]).w) == 2) {
-      key = kBinParked;
-    } else if (__float_as_int(float4(st.hit_uvd[lane]).w) == 0) {
-      key = kBinMiss;
-    } else {
-      const int2 ids = st.hit_ids[lane];
-      key            = 1 + (scene.materials[scene.instances[ids.x].material].type & 7);
+    int i    = i0 + wl;
+    int lane = 0, dest = kDestNone;
+    if (i < n) {
+      lane = q.shade[CLS][i] & kEntryLane;
+      dest = shade_lane<kSamplerPath, CLS>(scene, st, p, lane, inst_rays) & 3;
     }
-    keys[i]              = (unsigned char)key;
-    const unsigned peers = __match_any_sync(active, key);
-    if (wl == __ffs(peers) - 1) atomicAdd(&c->n_bin[key], __popc(peers));
+    route_shaded<FUSE>(scene, st, q, p, parity, lane, dest, lane, counts);
   }
-}
-__global__ void __launch_bounds__(256) k_bin_scatter(Queues q, int parity, const unsigned char* keys, int* sorted) {
-  Counters* c   = q.counters;
-  const int n   = c->n_ext[parity];
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-  const int wl  = threadIdx.x & 31;
-  int       off[kNumBins];
-  for (int k = 0, sum = 0; k < kNumBins; k++) off[k] = sum, sum += c->n_bin[k];
-  for (int i0 = tid - wl; i0 < n; i0 += stride) {
-    const int      i      = i0 + wl;
-    const bool     valid  = i < n;
-    const unsigned active = __ballot_sync(kFullWarp, valid);
-    if (!valid) continue;
-    const int      key    = keys[i];
-    const unsigned peers  = __match_any_sync(active, key);
-    const int      leader = __ffs(peers) - 1;
-    int            base   = 0;
-    if (wl == leader) base = atomicAdd(&c->bin_cursor[key], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    int start = 0;
-    for (int k = 0; k < kNumBins; k++)
-      if (k == key) start = off[k];
-    sorted[start + base + __popc(peers & ((1u << wl) - 1u))] = q.ext[parity][i];
-  }
+  flush_counts(c, counts);
+  if (tid == 0 && n) atomicAdd(&c->shade_calls, (unsigned long long)n);
 }
 
 // ---- lightpdf: sample_lights_pdf for the pending direction, then the MIS weight, weight checks,
@@ -1016,6 +1043,7 @@ YGL_D void lightpdf_lane(const DScene& scene, const PS& st, const KParams& p, bo
     entry = lane;
   }
 }
+template <bool FUSE>
 __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_lpdf;
@@ -1027,9 +1055,9 @@ __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene sce
     int i    = i0 + wl;
     int lane = i < n ? q.lpdf[i] : 0, dest, entry;
     lightpdf_lane(scene, st, p, i < n, lane, rays, dest, entry);
-    end_of_path(scene, st, p, lane, dest, entry, counts);
+    if (FUSE) end_of_path(scene, st, p, lane, dest, entry, counts);
     queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
-    if (!p.fuse) queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
+    if (!FUSE) queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
   }
   flush_counts(c, counts);
   // one atomic per warp for the instance-ray count
@@ -1075,12 +1103,44 @@ YGL_D bool accumulate_lane(const DScene& scene, const PS& st, const KParams& p, 
   st.sample[lane] = sample;
   return sample < p.sample_end;
 }
-__global__ void __launch_bounds__(256) k_accumulate(DScene scene, PathState st, Queues q, KParams p, int parity) {
+// Class kClsMiss of the path sampler: every lane of the warp ends its path on the environment, so the kernel
+// accumulates the sample and starts the lane's next camera ray at once, whatever p.fuse says (the code is coherent,
+// and it saves the lane a trip through k_finish).
+__global__ void __launch_bounds__(256, 4) k_shade_miss(DScene scene, PathState st, Queues q, KParams p, int parity) {
+  Counters* c   = q.counters;
+  const int n   = c->n_shade[kClsMiss];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int wl  = threadIdx.x & 31;
+  int2      counts = make_int2(0, 0);
+  for (int i0 = tid - wl; i0 < n; i0 += stride) {
+    int  i    = i0 + wl;
+    int  lane = 0;
+    bool more = false;
+    if (i < n) {
+      lane = q.shade[kClsMiss][i] & kEntryLane;
+      miss_lane(scene, st, p, lane);
+      more = accumulate_lane(scene, st, p, lane);
+      if (more) {
+        generate_lane(scene, st, p, lane);
+        counts.x++;
+      } else {
+        counts.y++;
+      }
+    }
+    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], more, lane);
+  }
+  flush_counts(c, counts);
+  if (tid == 0 && n) atomicAdd(&c->shade_calls, (unsigned long long)n);
+}
+
+// The finished paths of an iteration (p.fuse == 0): accumulate, then the lane's next camera sample goes straight into
+// the next extend queue.
+__global__ void __launch_bounds__(256) k_finish(DScene scene, PathState st, Queues q, KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_acc;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   const int wl  = threadIdx.x & 31;
-  int       finished = 0;
+  int2      counts = make_int2(0, 0);
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
     int  i    = i0 + wl;
     int  lane = 0;
@@ -1088,12 +1148,16 @@ __global__ void __launch_bounds__(256) k_accumulate(DScene scene, PathState st, 
     if (i < n) {
       lane = q.acc[i];
       more = accumulate_lane(scene, st, p, lane);
-      if (!more) finished++;
+      if (more) {
+        generate_lane(scene, st, p, lane);
+        counts.x++;
+      } else {
+        counts.y++;
+      }
     }
-    queue_push(q.gen[1 - parity], &c->n_gen[1 - parity], more, lane);
+    queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], more, lane);
   }
-  for (int off = 16; off > 0; off >>= 1) finished += __shfl_down_sync(0xffffffffu, finished, off);
-  if (wl == 0 && finished) atomicAdd(&c->done_lanes, finished);
+  flush_counts(c, counts);
 }
 
 
@@ -1412,132 +1476,118 @@ void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, in
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   k_generate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }
-void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity,
+void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, Queues q, int parity,
     unsigned long long* trav) {
   // persistent kernel: exactly the resident capacity (SMs x blocks/SM from the occupancy API), capped
   // by the lanes that can exist
   static int per_sm = 0;
-  static int sms    = 0;
   if (!per_sm) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_extend<false, 0>), 128, 0);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (per_sm < 1) per_sm = 1;
   }
-  int blocks = sms * per_sm;
-  if (const char* env = getenv("YGL_EXT_BLOCKS_PER_SM")) blocks = sms * std::max(1, std::min(per_sm, atoi(env)));
+  int blocks = num_sms * (tune.ext_blocks_per_sm > 0 ? std::min(per_sm, tune.ext_blocks_per_sm) : per_sm);
   int needed = (st.num_lanes + 127) / 128;
   if (blocks > needed) blocks = needed;
   if (blocks < 1) blocks = 1;
-  (void)cfg;
-  static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
-  static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
   // Tail knobs (the queue is exhausted, the warp drains). Two alternatives, chosen by the size of the tile
   // (measured on B200, C3): on a full 1080p frame (2.07 M lanes, ~9 rays per slot and launch) parking the last
   // <= 8 busy lanes of a warp for the next launch once it has walked 96 more rounds wins 2 %; on small tiles
   // (one ray per slot: the launch time IS the tail) parking only adds iterations, and finishing the last
   // <= 12 lanes in a vote-free per-lane loop wins 8 % (1/8 tile: 78.8 -> 72.4 ms per 32 spp).
-  static int suspend_b  = getenv("YGL_SUSPEND") ? atoi(getenv("YGL_SUSPEND")) : -1;
-  static int suspend_r  = getenv("YGL_SUSPEND_ROUNDS") ? atoi(getenv("YGL_SUSPEND_ROUNDS")) : kSuspendMinRounds;
-  static int lone_env   = getenv("YGL_LONE") ? atoi(getenv("YGL_LONE")) : -1;
-  static int lone_steps = getenv("YGL_LONE_STEPS") ? atoi(getenv("YGL_LONE_STEPS")) : 0;
-  const bool big_tile   = st.num_lanes > 800000;
-  const int  sb         = suspend_b >= 0 ? suspend_b : (big_tile ? kSuspendBelow : 0);
-  const int  suspend    = sb > 0 ? (std::min(sb, 31) | std::max(1, suspend_r) << 8) : 0;
-  const int  lone       = lone_env >= 0 ? lone_env : (big_tile ? 0 : 12);
+  const bool big_tile = st.num_lanes > 800000;
+  const int  sb       = tune.suspend >= 0 ? tune.suspend : (big_tile ? kSuspendBelow : 0);
+  const int  suspend  = sb > 0 ? (std::min(sb, 31) | std::max(1, tune.suspend_rounds) << 8) : 0;
+  const int  lone     = tune.lone >= 0 ? tune.lone : (big_tile ? 0 : 12);
   auto* kernel = lone > 0 ? (trav ? k_extend<true, 1> : k_extend<false, 1>) : (trav ? k_extend<true, 0> : k_extend<false, 0>);
-  kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, refill_thr, node_reps, suspend, lone, lone_steps);
+  kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, tune.refill, tune.node_reps, suspend, lone, tune.lone_steps);
 }
 
 template <int SAMPLER>
-static void launch_persistent_t(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p,
-    int lane_lo, int lane_hi, int sample_begin) {
+static void launch_persistent_t(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, PQueues q,
+    KParams p, int lane_lo, int lane_hi, int sample_begin) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<SAMPLER>, kPersistThreads, 0);
   if (per_sm < 1) per_sm = 1;
-  if (const char* env = getenv("YGL_PERSIST_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(env)));
+  if (tune.persist_blocks_per_sm > 0) per_sm = std::min(per_sm, tune.persist_blocks_per_sm);
   int blocks = num_sms * per_sm;
   // tiny tiles: no more warps than there are lanes to keep busy (every block hosts all roles)
   const int needed = std::max(1, (lane_hi - lane_lo + 31) / 32 / 6);
   blocks           = std::max(1, std::min(blocks, needed));
-  // YGL_PERSIST_ROLES: per-warp pattern of a mixed block, E = traversal, S = shading, L = light pdf (one letter per
-  // warp). YGL_PERSIST_EXT_SMS: traversal SMs per 10 (0 = mixed blocks everywhere). YGL_PERSIST_LPDF_WARPS:
-  // light-pdf warps in a shading block.
-  static unsigned roles = 0;
-  if (!roles) {
-    const int   nw  = kPersistThreads / 32;
-    const char* pat = getenv("YGL_PERSIST_ROLES");
-    if (!pat || (int)strlen(pat) != nw) pat = "EESLEESLEESL";
-    bool has_e = false, has_s = false, has_l = false;
-    for (int w = 0; w < nw; w++) {
-      int r = pat[w] == 'E' ? kRoleExt : pat[w] == 'L' ? kRoleLpdf : kRoleShade;
-      has_e |= r == kRoleExt, has_s |= r == kRoleShade, has_l |= r == kRoleLpdf;
-      roles |= (unsigned)r << (2 * w);
-    }
-    if (!(has_e && has_s && has_l)) {  // every ring needs a consumer in every mixed block
-      roles = 0;
-      for (int w = 0; w < nw; w++) roles |= (unsigned)(w % 4 < 2 ? kRoleExt : w % 4 == 2 ? kRoleShade : kRoleLpdf) << (2 * w);
-    }
-    int ext_sms = getenv("YGL_PERSIST_EXT_SMS") ? atoi(getenv("YGL_PERSIST_EXT_SMS")) : 6;
-    int lw      = getenv("YGL_PERSIST_LPDF_WARPS") ? atoi(getenv("YGL_PERSIST_LPDF_WARPS")) : 4;
-    ext_sms     = std::max(0, std::min(9, ext_sms));
-    lw          = std::max(1, std::min(nw - 1, lw));
-    roles |= (unsigned)ext_sms << 24 | (unsigned)lw << 28;
-  }
-  static int refill_thr = getenv("YGL_REFILL") ? atoi(getenv("YGL_REFILL")) : kRefillThreshold;
-  static int node_reps  = getenv("YGL_NODE_REPS") ? atoi(getenv("YGL_NODE_REPS")) : 3;
+  // roles of a mixed block (small grids): per warp E = traversal, S = shading, L = light pdf; on full grids SMs are
+  // specialised: persist_ext_sms of every 10 SMs run traversal warps only, the others shading warps with
+  // persist_lpdf_warps light-pdf warps per block
+  const int nw    = kPersistThreads / 32;
+  unsigned  roles = 0;
+  for (int w = 0; w < nw; w++) roles |= (unsigned)(w % 4 < 2 ? kRoleExt : w % 4 == 2 ? kRoleShade : kRoleLpdf) << (2 * w);
+  const int ext_sms = std::max(0, std::min(9, tune.persist_ext_sms));
+  const int lw      = std::max(1, std::min(nw - 1, tune.persist_lpdf_warps));
+  roles |= (unsigned)ext_sms << 24 | (unsigned)lw << 28;
   PathStateC stc;  // same layout, coherent loads (see SArr)
   memcpy(&stc, &st, sizeof(stc));
   k_persistent<SAMPLER><<<blocks, kPersistThreads, 0, s>>>(scene, stc, q, p, lane_lo, lane_hi, sample_begin, roles,
-      num_sms, refill_thr, node_reps);
+      num_sms, tune.refill, tune.node_reps);
 }
-void launch_persistent(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p, int lane_lo,
-    int lane_hi, int sample_begin) {
+void launch_persistent(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, PQueues q, KParams p,
+    int lane_lo, int lane_hi, int sample_begin) {
+#define YGL_PERSIST_CASE(S) \
+  case S: launch_persistent_t<S>(s, num_sms, tune, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
   switch (p.sampler) {
-    case kSamplerPath: launch_persistent_t<kSamplerPath>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    case kSamplerPathDirect: launch_persistent_t<kSamplerPathDirect>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    case kSamplerPathMis: launch_persistent_t<kSamplerPathMis>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    case kSamplerPathTest: launch_persistent_t<kSamplerPathTest>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    case kSamplerNaive: launch_persistent_t<kSamplerNaive>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    case kSamplerEyelight: launch_persistent_t<kSamplerEyelight>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    case kSamplerDiagram: launch_persistent_t<kSamplerDiagram>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    case kSamplerFurnace: launch_persistent_t<kSamplerFurnace>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-    default: launch_persistent_t<kSamplerFalsecolor>(s, num_sms, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
+    YGL_PERSIST_CASE(kSamplerPath)
+    YGL_PERSIST_CASE(kSamplerPathDirect)
+    YGL_PERSIST_CASE(kSamplerPathMis)
+    YGL_PERSIST_CASE(kSamplerPathTest)
+    YGL_PERSIST_CASE(kSamplerNaive)
+    YGL_PERSIST_CASE(kSamplerEyelight)
+    YGL_PERSIST_CASE(kSamplerDiagram)
+    YGL_PERSIST_CASE(kSamplerFurnace)
+    default: launch_persistent_t<kSamplerFalsecolor>(s, num_sms, tune, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
   }
+#undef YGL_PERSIST_CASE
 }
-void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
+template <int CLS>
+static void launch_shade_class(cudaStream_t s, int blocks, DScene scene, PathState st, Queues q, KParams p, int parity,
+    unsigned class_mask) {
+  if (!(class_mask >> CLS & 1)) return;
+  if (p.fuse) k_shade_path<CLS, true><<<blocks, YGL_SHADE_THREADS, 0, s>>>(scene, st, q, p, parity);
+  else k_shade_path<CLS, false><<<blocks, YGL_SHADE_THREADS, 0, s>>>(scene, st, q, p, parity);
+}
+void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity,
+    unsigned class_mask) {
   const int threads = YGL_SHADE_THREADS;
   const int blocks  = std::max(1, cfg.blocks * cfg.threads / threads);
-  if (p.sampler == kSamplerFalsecolor)
-    k_shade<kSamplerFalsecolor><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else if (p.sampler == kSamplerEyelight)
-    k_shade<kSamplerEyelight><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else if (p.sampler == kSamplerNaive)
-    k_shade<kSamplerNaive><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else if (p.sampler == kSamplerFurnace)
-    k_shade<kSamplerFurnace><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else if (p.sampler == kSamplerPathTest)
-    k_shade<kSamplerPathTest><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else if (p.sampler == kSamplerDiagram)
-    k_shade<kSamplerDiagram><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else if (p.sampler == kSamplerPathDirect)
-    k_shade<kSamplerPathDirect><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else if (p.sampler == kSamplerPathMis)
-    k_shade<kSamplerPathMis><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-  else
-    k_shade<kSamplerPath><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
-}
-void launch_bin_queue(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity, int* sorted,
-    unsigned char* keys) {
-  k_bin_count<<<cfg.blocks, 256, 0, s>>>(scene, st, q, parity, keys);
-  k_bin_scatter<<<cfg.blocks, 256, 0, s>>>(q, parity, keys, sorted);
+  if (p.sampler == kSamplerPath && scene.inst_class) {
+    // binned queues: misses first (each of them starts a new camera ray for the next extend), then one kernel per
+    // material type present in the scene, then the lanes inside media
+    if (class_mask >> kClsMiss & 1) k_shade_miss<<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+    launch_shade_class<1>(s, blocks, scene, st, q, p, parity, class_mask);
+    launch_shade_class<2>(s, blocks, scene, st, q, p, parity, class_mask);
+    launch_shade_class<3>(s, blocks, scene, st, q, p, parity, class_mask);
+    launch_shade_class<4>(s, blocks, scene, st, q, p, parity, class_mask);
+    launch_shade_class<5>(s, blocks, scene, st, q, p, parity, class_mask);
+    launch_shade_class<6>(s, blocks, scene, st, q, p, parity, class_mask);
+    launch_shade_class<7>(s, blocks, scene, st, q, p, parity, class_mask);
+    launch_shade_class<8>(s, blocks, scene, st, q, p, parity, class_mask);
+    if (class_mask & 1u) k_shade<kSamplerPath><<<blocks, threads, 0, s>>>(scene, st, q, p, parity);
+    return;
+  }
+  switch (p.sampler) {
+    case kSamplerFalsecolor: k_shade<kSamplerFalsecolor><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    case kSamplerEyelight: k_shade<kSamplerEyelight><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    case kSamplerNaive: k_shade<kSamplerNaive><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    case kSamplerFurnace: k_shade<kSamplerFurnace><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    case kSamplerPathTest: k_shade<kSamplerPathTest><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    case kSamplerDiagram: k_shade<kSamplerDiagram><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    case kSamplerPathDirect: k_shade<kSamplerPathDirect><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    case kSamplerPathMis: k_shade<kSamplerPathMis><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+    default: k_shade<kSamplerPath><<<blocks, threads, 0, s>>>(scene, st, q, p, parity); break;
+  }
 }
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
-  k_lightpdf<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+  if (p.fuse) k_lightpdf<true><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+  else k_lightpdf<false><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }
-void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
-  k_accumulate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+void launch_finish(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
+  k_finish<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }
 void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const float4* rays, long long n, int instance,
     int find_any, void* out, unsigned long long* counters) {

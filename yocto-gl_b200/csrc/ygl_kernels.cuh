@@ -87,12 +87,21 @@ using PathState  = PathStateT<false>;  // wavefront kernels, host
 using PathStateC = PathStateT<true>;   // persistent kernel: same layout, L1-bypassing loads
 static_assert(sizeof(PathState) == sizeof(PathStateC), "the two views of the lane state must share one layout");
 
+// Shading classes: the extend kernel appends every finished ray to the shade queue of its class, so that a shading
+// warp holds ONE kind of work (one material type, or misses) and each class gets a kernel that contains only its
+// own code. Class 0 is the unspecialised kernel: every lane when binning is off (all samplers but `path`), and,
+// with binning on, the lanes that travel inside a participating medium.
+constexpr int kClsGeneric = 0;  // 1..8 = 1 + material_type (yocto_scene.h:111-120)
+constexpr int kClsMiss    = 9;
+constexpr int kNumClasses = 10;
+
 // Work queues: lane ids compacted with warp-ballot / one atomic per warp.
 struct Queues {
-  int* gen[2];  // lanes that start a new sample
-  int* ext[2];  // lanes with a ray to trace (then shade)
-  int* lpdf;    // lanes waiting for sample_lights_pdf
-  int* acc;     // lanes whose sample finished
+  int* gen[2];              // lanes that start a new sample
+  int* ext[2];              // lanes with a ray to trace
+  int* shade[kNumClasses];  // lanes whose ray has been traced, by shading class (null: class absent from the scene)
+  int* lpdf;                // lanes waiting for sample_lights_pdf
+  int* acc;                 // lanes whose sample finished
   // counters (device): see QueueCounters
   struct Counters* counters;
 };
@@ -101,7 +110,7 @@ struct Counters {
   int n_gen[2], n_ext[2], n_lpdf, n_acc;
   int done_lanes;  // lanes that finished all their samples
   int ext_head;    // work cursor of the persistent extend kernel (reset every iteration)
-  int n_bin[16], bin_cursor[16];  // shade-queue binning (experimental, YGL_BIN=1): entries per key / append cursors
+  int n_shade[kNumClasses];
   unsigned long long camera_samples, scene_rays, instance_rays, shade_calls;
 };
 
@@ -133,23 +142,42 @@ struct LaunchCfg {
   int blocks, threads;
 };
 
+// Scheduling knobs of a context (ygl_context_set_option). None of them can change a result bit: they choose grid
+// sizes, the tail strategy of the extend kernel, which kernels finish a path, and the scheduler's own parameters.
+struct Tuning {
+  int ext_blocks_per_sm = 0;  // extend grid: blocks per SM (0 = the occupancy maximum)
+  int refill            = 8;  // extend: idle lanes of a warp that trigger a refill
+  int node_reps         = 3;  // extend: node visits per scheduling round
+  int suspend           = -1; // extend tail: park a drained warp's stragglers once <= this many lanes are busy (-1 = by tile size, 0 = never)
+  int suspend_rounds    = 96; //   ... after at least this many rounds
+  int lone              = -1; // extend tail: vote-free walk of the last <= this many lanes (-1 = by tile size, 0 = never)
+  int lone_steps        = 0;  //   ... parked after this many steps (0 = never)
+  int fuse              = -1; // shading kernels finish paths themselves (1) or hand them to k_finish (0); -1 = by tile size
+  int bin               = -1; // class-binned shade queues for the path sampler (1/0; -1 = on)
+  int pipes             = 1;  // independent wavefront pipelines (streams) per state
+  int graph             = -1; // submit iterations as a CUDA graph (1/0; -1 = by tile size)
+  int top_smem          = -1; // extend: stage the instance-level tree in shared memory with a bulk async copy (1/0; -1 = default)
+  int persist_blocks_per_sm = 0, persist_ext_sms = 6, persist_lpdf_warps = 4;  // persistent mode (see k_persistent)
+  double watchdog_s     = 20.0;  // persistent mode: abort after this long without progress
+};
+
 void launch_begin_iteration(cudaStream_t s, Queues q, int parity);
 void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, int parity, int sample_begin,
     int lane_lo, int lane_hi);
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
-// trav: device array of 7 counters {top nodes, bottom nodes, instance visits, tri, quad, line, point tests} or null
-void launch_extend(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity,
+// trav: device array of 7 counters {top nodes, bottom nodes, instance visits, tri, quad, line, point tests} or null.
+// Finished rays go to q.shade[class] (class 0 for every lane unless scene.inst_class is set).
+void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, Queues q, int parity,
     unsigned long long* trav);
-void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+// one launch per shading class present (class_mask bit c), or the single generic kernel when binning is off
+void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity,
+    unsigned class_mask);
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
-// experimental: copy the extend queue into `sorted`, grouped by (miss | material type | parked), so that the warps of
-// k_shade run one kind of lane each. keys: one byte per queue entry (scratch).
-void launch_bin_queue(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, int parity, int* sorted,
-    unsigned char* keys);
-void launch_accumulate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
+// accumulate the finished paths of q.acc and start each lane's next camera sample (used when p.fuse == 0)
+void launch_finish(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 // persistent mode: one launch renders samples [sample_begin, p.sample_end) of lanes [lane_lo, lane_hi)
-void launch_persistent(cudaStream_t s, int num_sms, DScene scene, PathState st, PQueues q, KParams p, int lane_lo,
-    int lane_hi, int sample_begin);
+void launch_persistent(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, PQueues q, KParams p,
+    int lane_lo, int lane_hi, int sample_begin);
 
 // batch intersect (test hook + traversal micro-benchmark). counters may be null.
 void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const float4* rays, long long n, int instance,

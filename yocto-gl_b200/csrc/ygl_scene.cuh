@@ -111,6 +111,9 @@ struct DScene {
   // lights
   const DLight* lights;
   int           num_lights;
+  // shading class of a hit on instance i = 1 + material type (ygl_kernels.cuh); null = shade queues are not binned
+  const unsigned char* inst_class;
+  int                  has_volumes;  // some material can start a participating medium (refractive / subsurface / volumetric)
 };
 
 YGL_D f3 ld3(const float* p, int i) { return f3{__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)}; }

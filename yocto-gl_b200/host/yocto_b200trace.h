@@ -8,7 +8,8 @@
 // (tests/test_host_parity.py::test_reference_side_shim_compiles does so in the dev container).
 //
 //   yocto::trace_image(scene, params)            ->  yocto::b200::trace_image(scene, params)
-//   make_trace_bvh / make_trace_lights / make_trace_state / trace_samples / get_image likewise.
+//   make_trace_bvh / make_trace_lights / make_trace_state / trace_samples / trace_sample / get_image /
+//   get_albedo_image / get_normal_image / trace_start / trace_cancel / trace_done / trace_preview likewise.
 //
 // Errors of the C ABI come back as the exceptions the reference uses (yocto_trace.cpp:1437,
 // :1679-1691): YGL_ERR_INVALID -> std::invalid_argument, everything else -> std::runtime_error.
@@ -150,11 +151,86 @@ inline void trace_samples(b200_context& ctx, b200_state& state, const b200_scene
   auto abi = to_abi(params);
   check(ygl_trace_samples(ctx.handle, state.handle, scene.handle, bvh.handle, lights.handle, &abi));
 }
-// get_image (yocto_trace.cpp:1694)
+// make_trace_bvh from trees the reference has already built (trace_bvh::bvh, yocto_trace.h:138): adopted verbatim
+inline std::unique_ptr<b200_bvh> make_trace_bvh(const scene_data& scene, const trace_bvh& built) {
+  static_assert(sizeof(bvh_node) == sizeof(ygl_bvh_node), "bvh_node layout");
+  auto views = make_views(scene);
+  auto nodes = std::vector<const ygl_bvh_node*>{};
+  auto prims = std::vector<const int32_t*>{};
+  auto nn = std::vector<int>{}, np = std::vector<int>{};
+  for (auto& shape : built.bvh.shapes) {
+    nodes.push_back((const ygl_bvh_node*)shape.bvh.nodes.data());
+    prims.push_back((const int32_t*)shape.bvh.primitives.data());
+    nn.push_back((int)shape.bvh.nodes.size());
+    np.push_back((int)shape.bvh.primitives.size());
+  }
+  auto out = std::make_unique<b200_bvh>();
+  check(ygl_bvh_create_from_host(&views.desc, (const ygl_bvh_node*)built.bvh.bvh.nodes.data(),
+      (int)built.bvh.bvh.nodes.size(), (const int32_t*)built.bvh.bvh.primitives.data(),
+      (int)built.bvh.bvh.primitives.size(), nodes.data(), nn.data(), prims.data(), np.data(), &out->handle));
+  return out;
+}
+// trace_sample (yocto_trace.cpp:1461)
+inline void trace_sample(b200_context& ctx, b200_state& state, const b200_scene& scene, const b200_bvh& bvh,
+    const b200_lights& lights, int i, int j, int sample, const trace_params& params) {
+  auto abi = to_abi(params);
+  check(ygl_trace_sample(ctx.handle, state.handle, scene.handle, bvh.handle, lights.handle, i, j, sample, &abi));
+}
+// reset_cutrace_state-style reset (yocto_cutrace.h:119)
+inline void reset_trace_state(b200_state& state, const trace_params& params) {
+  auto abi = to_abi(params);
+  check(ygl_state_reset(state.handle, &abi));
+}
+// check_image, yocto_trace.cpp:1679-1686
+inline void check_image(const image_data& image, int width, int height, bool linear) {
+  if (image.width != width || image.height != height) throw std::invalid_argument{"image should have the same size"};
+  if (image.linear != linear) throw std::invalid_argument{linear ? "expected linear image" : "expected srgb image"};
+}
+// get_image (yocto_trace.cpp:1694-1708)
+inline void get_image(image_data& image, b200_state& state) {
+  image.width = state.width, image.height = state.height, image.linear = true;
+  image.pixels.resize((size_t)state.width * state.height);
+  check(ygl_state_download(state.handle, (float*)image.pixels.data(), nullptr, nullptr, nullptr, nullptr));
+}
 inline image_data get_image(b200_state& state) {
   auto image = make_image(state.width, state.height, true);
-  check(ygl_state_download(state.handle, (float*)image.pixels.data(), nullptr, nullptr, nullptr, nullptr));
+  get_image(image, state);
   return image;
+}
+// get_albedo_image / get_normal_image (yocto_trace.cpp:1767-1790): the denoise guides as rgba images, alpha 1
+inline void get_guide_image(image_data& image, b200_state& state, bool normal) {
+  check_image(image, state.width, state.height, true);
+  auto rgb = std::vector<vec3f>((size_t)state.width * state.height);
+  check(ygl_state_download(state.handle, nullptr, normal ? nullptr : (float*)rgb.data(),
+      normal ? (float*)rgb.data() : nullptr, nullptr, nullptr));
+  for (auto idx = (size_t)0; idx < rgb.size(); idx++) image.pixels[idx] = {rgb[idx].x, rgb[idx].y, rgb[idx].z, 1.0f};
+}
+inline void       get_albedo_image(image_data& image, b200_state& state) { get_guide_image(image, state, false); }
+inline void       get_normal_image(image_data& image, b200_state& state) { get_guide_image(image, state, true); }
+inline image_data get_albedo_image(b200_state& state) {
+  auto image = make_image(state.width, state.height, true);
+  get_albedo_image(image, state);
+  return image;
+}
+inline image_data get_normal_image(b200_state& state) {
+  auto image = make_image(state.width, state.height, true);
+  get_normal_image(image, state);
+  return image;
+}
+// trace_start / trace_cancel / trace_done / trace_preview (yocto_trace.h:209-223): the context plays trace_context
+inline void trace_start(b200_context& ctx, b200_state& state, const b200_scene& scene, const b200_bvh& bvh,
+    const b200_lights& lights, const trace_params& params) {
+  auto abi = to_abi(params);
+  check(ygl_trace_start(ctx.handle, state.handle, scene.handle, bvh.handle, lights.handle, &abi));
+}
+inline void trace_cancel(b200_context& ctx) { check(ygl_trace_cancel(ctx.handle)); }
+inline bool trace_done(const b200_context& ctx) { return ygl_trace_done(ctx.handle) != 0; }
+inline void trace_preview(image_data& image, b200_context& ctx, b200_state& state, const b200_scene& scene,
+    const b200_bvh& bvh, const b200_lights& lights, const trace_params& params) {
+  check_image(image, state.width, state.height, true);
+  auto abi = to_abi(params);
+  check(ygl_trace_preview(ctx.handle, scene.handle, bvh.handle, lights.handle, &abi, state.width, state.height,
+      (float*)image.pixels.data()));
 }
 // trace_image (yocto_trace.cpp:1584): the drop-in
 inline image_data trace_image(const scene_data& scene, const trace_params& params, int device = 0) {

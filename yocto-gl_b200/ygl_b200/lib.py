@@ -26,6 +26,8 @@ EXPORTS = [
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
     "ygl_trace_counters", "ygl_context_set_profiling", "ygl_context_set_mode", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
+    "ygl_trace_start", "ygl_trace_cancel", "ygl_trace_wait", "ygl_trace_done", "ygl_trace_preview",
+    "ygl_context_set_option", "ygl_context_get_option", "ygl_state_reset", "ygl_trace_sample", "ygl_bvh_create_from_host",
 ]
 
 
@@ -78,6 +80,16 @@ def load():
     lib.ygl_context_set_profiling.argtypes = [vp, i32, i32]
     lib.ygl_context_set_mode.argtypes = [vp, i32]
     lib.ygl_trace_timings.argtypes = [vp, vp]
+    lib.ygl_trace_start.argtypes = [vp, vp, vp, vp, vp, P(abi.TraceParams)]
+    lib.ygl_trace_cancel.argtypes = [vp]
+    lib.ygl_trace_wait.argtypes = [vp]
+    lib.ygl_trace_done.argtypes = [vp]
+    lib.ygl_trace_preview.argtypes = [vp, vp, vp, vp, P(abi.TraceParams), i32, i32, vp]
+    lib.ygl_context_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    lib.ygl_context_get_option.argtypes = [vp, C.c_char_p, P(C.c_double)]
+    lib.ygl_state_reset.argtypes = [vp, P(abi.TraceParams)]
+    lib.ygl_trace_sample.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, P(abi.TraceParams)]
+    lib.ygl_bvh_create_from_host.argtypes = [P(abi.SceneDesc), vp, i32, vp, i32, vp, vp, vp, vp, P(vp)]
     lib.ygl_intersect_rays.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.ygl_intersect_rays_device.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.ygl_debug_libm.argtypes = [vp, i32, vp, vp, i64, vp]
@@ -102,13 +114,29 @@ def _p(a):
 
 
 class Bvh:
-    """make_trace_bvh (host build in the reference's node order)."""
+    """make_trace_bvh (host build in the reference's node order), or — trees=(top, [per shape]) with each tree a
+    (nodes, primitives) pair in the reference's bvh_tree layout — trees built elsewhere adopted verbatim."""
 
-    def __init__(self, scene, highquality=False):
+    def __init__(self, scene, highquality=False, trees=None):
         self.lib = load()
         self.desc = scene.desc()
         self.h = C.c_void_p()
-        _check(self.lib.ygl_bvh_build(C.byref(self.desc), int(highquality), C.byref(self.h)))
+        if trees is None:
+            _check(self.lib.ygl_bvh_build(C.byref(self.desc), int(highquality), C.byref(self.h)))
+            return
+        (top_nodes, top_prims), shape_trees = trees
+        keep = [np.ascontiguousarray(top_nodes, abi.NODE_DTYPE), np.ascontiguousarray(top_prims, np.int32)]
+        n = len(shape_trees)
+        node_ptrs, prim_ptrs = (C.c_void_p * max(1, n))(), (C.c_void_p * max(1, n))()
+        num_nodes, num_prims = (C.c_int * max(1, n))(), (C.c_int * max(1, n))()
+        for k, (nodes, prims) in enumerate(shape_trees):
+            nodes, prims = np.ascontiguousarray(nodes, abi.NODE_DTYPE), np.ascontiguousarray(prims, np.int32)
+            keep += [nodes, prims]
+            node_ptrs[k], prim_ptrs[k] = nodes.ctypes.data, prims.ctypes.data
+            num_nodes[k], num_prims[k] = len(nodes), len(prims)
+        _check(self.lib.ygl_bvh_create_from_host(C.byref(self.desc), keep[0].ctypes.data, len(keep[0]),
+                                                 keep[1].ctypes.data, len(keep[1]), node_ptrs, num_nodes,
+                                                 prim_ptrs, num_prims, C.byref(self.h)))
 
     def tree(self, shape):
         nn, npr = C.c_int(), C.c_int()
@@ -198,6 +226,24 @@ class Context:
         """'wavefront' (default) or 'persistent' (one resident kernel per call); results are bit-identical."""
         _check(self.lib.ygl_context_set_mode(self.h, {"wavefront": 0, "persistent": 1}[mode]))
 
+    def trace_cancel(self):
+        _check(self.lib.ygl_trace_cancel(self.h))
+
+    def trace_wait(self):
+        _check(self.lib.ygl_trace_wait(self.h))
+
+    def trace_done(self):
+        return bool(self.lib.ygl_trace_done(self.h))
+
+    def set_option(self, name, value):
+        """Scheduling knob by name (ygl_context_set_option); never changes a result bit."""
+        _check(self.lib.ygl_context_set_option(self.h, name.encode(), float(value)))
+
+    def get_option(self, name):
+        v = C.c_double()
+        _check(self.lib.ygl_context_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
     def set_profiling(self, time_kernels=False, count_traversal=False):
         _check(self.lib.ygl_context_set_profiling(self.h, int(time_kernels), int(count_traversal)))
 
@@ -235,13 +281,30 @@ class Context:
 class DeviceScene:
     """Device-resident scene + bvh + lights (make_cutrace_scene-style upload)."""
 
-    def __init__(self, ctx, scene, highquality=False):
+    def __init__(self, ctx, scene, highquality=False, trees=None):
         self.ctx, self.lib, self.scene = ctx, ctx.lib, scene
         self.desc = scene.desc()
         self.h = C.c_void_p()
         _check(self.lib.ygl_scene_create(ctx.h, C.byref(self.desc), C.byref(self.h)))
-        self.bvh = Bvh(scene, highquality)
+        self.bvh = Bvh(scene, highquality, trees)
         self.lights = Lights(scene)
+
+    def trace_start(self, state, params):
+        """trace_start (yocto_trace.h:212): one batch on a worker thread; poll ctx.trace_done(), or cancel / wait."""
+        self._async_params = params  # keep alive; the library copies it, this is belt and braces
+        _check(self.lib.ygl_trace_start(self.ctx.h, state.h, self.h, self.bvh.h, self.lights.h, C.byref(params)))
+
+    def trace_preview(self, params, width, height):
+        """trace_preview (yocto_trace.h:220): 1 spp at resolution / pratio, replicated to width x height."""
+        image = np.zeros((height, width, 4), np.float32)
+        _check(self.lib.ygl_trace_preview(self.ctx.h, self.h, self.bvh.h, self.lights.h, C.byref(params), width,
+                                          height, image.ctypes.data))
+        return image
+
+    def trace_sample(self, state, i, j, sample, params):
+        """trace_sample (yocto_trace.h:173): one sample of one pixel; state.samples is unchanged."""
+        _check(self.lib.ygl_trace_sample(self.ctx.h, state.h, self.h, self.bvh.h, self.lights.h, i, j, sample,
+                                         C.byref(params)))
 
     def make_state(self, params, rows=None, interleave=None):
         """rows=(begin, end): contiguous tile; interleave=(rank, nranks): rows rank, rank+nranks, ..."""
@@ -314,6 +377,10 @@ class State:
         _check(self.lib.ygl_state_download(self.h, _p(image), _p(albedo), _p(normal), _p(hits),
                                            _p(rngs)))
         return dict(image=image, albedo=albedo, normal=normal, hits=hits, rngs=rngs)
+
+    def reset(self, params):
+        """reset_cutrace_state-style: zero accumulators, samples = 0, rng streams re-seeded from params.seed."""
+        _check(self.lib.ygl_state_reset(self.h, C.byref(params)))
 
     def upload(self, samples, image=None, albedo=None, normal=None, hits=None, rngs=None):
         _check(self.lib.ygl_state_upload(self.h, samples, _p(image), _p(albedo), _p(normal),
