@@ -26,6 +26,19 @@ for STEP in "$@"; do
       timeout -s KILL 120 $PERF c1 256 16 2 2>&1 | tail -n 1 | cut -c1-200
       timeout -s KILL 120 $PERF c2 1280 16 2 2>&1 | tail -n 1 | cut -c1-200
       timeout -s KILL 120 $PERF c5 1920 8 2 2>&1 | tail -n 1 | cut -c1-200 ;;
+    san)
+      timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
+    ab2)
+      for CFG in "lib" "lib node_reps=2" "lib node_reps=4" "lib refill=12" "lib_ext6" "lib_cls2"; do
+        set -- $CFG; LIB=$1; shift
+        [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
+        echo "--- $LIB $*"
+        YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c3 1920 16 2 profile=1 "$@" 2>&1 | tail -n 1 | cut -c1-260
+        YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c3 1920 32 2 tile=0,8 profile=1 "$@" 2>&1 | tail -n 1 | cut -c1-260
+      done
+      timeout -s KILL 120 $PERF c1 256 16 2 2>&1 | tail -n 1 | cut -c1-200
+      timeout -s KILL 120 $PERF c2 1280 16 2 2>&1 | tail -n 1 | cut -c1-200
+      timeout -s KILL 120 $PERF c5 1920 8 2 2>&1 | tail -n 1 | cut -c1-200 ;;
     launches)
       timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
       python tools/ncu_summary.py --launches gpurun_out/${TAG}_launches.csv | head -n 20 ;;

@@ -80,6 +80,8 @@ struct ygl_context {
     int          queue_lanes = 0;
     unsigned     queue_classes = 0;  // shade queues allocated (bit c = class c)
     int*         queue_mem   = nullptr;
+    int*         park_mem    = nullptr;  // Queues::park (two halves)
+    size_t       park_words  = 0;        // words per half
     Counters*    counters    = nullptr;
     int*         h_done      = nullptr;  // pinned, 2 slots
     cudaEvent_t  ev[2]       = {nullptr, nullptr};
@@ -230,6 +232,7 @@ void ygl_context_destroy(ygl_context* ctx) {
     auto& pipe = ctx->pipes[k];
     if (pipe.stream) cudaStreamSynchronize(pipe.stream);
     if (pipe.queue_mem) cudaFree(pipe.queue_mem);
+    if (pipe.park_mem) cudaFree(pipe.park_mem);
     if (pipe.counters) cudaFree(pipe.counters);
     if (pipe.h_done) cudaFreeHost(pipe.h_done);
     for (auto& e : pipe.ev)
@@ -690,7 +693,7 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
          o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_ro = take(lanes * 16), o_rd = take(lanes * 16),
          o_rad = take(lanes * 16), o_w = take(lanes * 16), o_huvd = take(lanes * 16), o_hid = take(lanes * 8),
          o_a0 = take(lanes * 16), o_n0 = take(lanes * 16), o_va = take(lanes * 16), o_vb = take(lanes * 16),
-         o_pend = take(lanes * 16), o_susp = take(lanes * 4 * 48), o_ao = take(lanes * 16), o_ad = take(lanes * 16),
+         o_pend = take(lanes * 16), o_susp = take(lanes * 4), o_ao = take(lanes * 16), o_ad = take(lanes * 16),
          o_ab = take(lanes * 16), o_au = take(lanes * 16), o_ai = take(lanes * 8), o_nu = take(lanes * 16),
          o_ni = take(lanes * 8);
   CUDA_TRY(cudaMalloc((void**)&state->mem, off));
@@ -833,8 +836,12 @@ void ygl_state_destroy(ygl_state* state) {
 
 // ------------------------------------------------------------------------------------------
 // Queue memory of a pipeline: gen[2], ext[2], lpdf, acc and one shade queue per class in `classes` (class 0 always).
-static int ensure_queues(ygl_context::Pipe& pipe, int lanes, unsigned classes) {
+static int ensure_queues(ygl_context::Pipe& pipe, int lanes, unsigned classes, int num_sms) {
   classes |= 1u;
+  if (!pipe.park_mem) {
+    pipe.park_words = (size_t)extend_grid_threads(num_sms) * kSuspendWords;
+    CUDA_TRY(cudaMalloc((void**)&pipe.park_mem, 2 * pipe.park_words * sizeof(int)));
+  }
   if (lanes <= pipe.queue_lanes && (classes & ~pipe.queue_classes) == 0) return YGL_OK;
   if (pipe.queue_mem) cudaFree(pipe.queue_mem), pipe.queue_mem = nullptr;
   lanes   = std::max(lanes, pipe.queue_lanes);
@@ -858,6 +865,8 @@ static Queues make_queues(ygl_context::Pipe& pipe) {
   q.acc      = pipe.queue_mem + 5 * per;
   int next   = 6;
   for (int c = 0; c < kNumClasses; c++) q.shade[c] = (pipe.queue_classes >> c) & 1 ? pipe.queue_mem + (next++) * per : nullptr;
+  q.park[0]  = pipe.park_mem;
+  q.park[1]  = pipe.park_mem + pipe.park_words;
   q.counters = pipe.counters;
   return q;
 }
@@ -910,7 +919,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     r.pipe = &ctx->pipes[j];
     r.lo   = lane_begin + (int)((long long)(lane_end - lane_begin) * j / npipes);
     r.hi   = lane_begin + (int)((long long)(lane_end - lane_begin) * (j + 1) / npipes);
-    if (int rc = ensure_queues(*r.pipe, r.hi - r.lo, classes)) return rc;
+    if (int rc = ensure_queues(*r.pipe, r.hi - r.lo, classes, ctx->num_sms)) return rc;
     r.q = make_queues(*r.pipe);
     // persistent-style grids: a multiple of the SM count, capped by the work available
     int lanes  = r.hi - r.lo;

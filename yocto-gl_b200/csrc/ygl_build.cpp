@@ -183,22 +183,32 @@ float as_float(int v) {
   return f;
 }
 
+// node word (ygl_scene.cuh): internal = 0x80000000 | axis << 28 | first child (28 bits); leaf = num << 26 | first
+// primitive (26 bits). make_tree / measure_tree guarantee the ranges (kMaxTreeNodes, kMaxTreePrims, leaves <= 4).
+int node_word(const ygl_bvh_node& n) {
+  if (n.internal) return (int)(0x80000000u | ((unsigned)(n.axis & 3) << 28) | ((unsigned)n.start & 0x0fffffffu));
+  return (int)(((unsigned)n.num & 7u) << 26 | ((unsigned)n.start & 0x03ffffffu));
+}
 std::vector<float4h> pack_nodes(const HostTree& tree) {
   std::vector<float4h> out(tree.nodes.size() * 2);
   for (size_t i = 0; i < tree.nodes.size(); i++) {
-    auto& n    = tree.nodes[i];
-    int   meta = ((int)(uint16_t)n.num) | ((int)(uint8_t)n.axis << 16) | ((int)n.internal << 24);
+    auto& n        = tree.nodes[i];
     out[2 * i + 0] = {n.bbox_min[0], n.bbox_min[1], n.bbox_min[2], n.bbox_max[0]};
-    out[2 * i + 1] = {n.bbox_max[1], n.bbox_max[2], as_float(n.start), as_float(meta)};
+    out[2 * i + 1] = {n.bbox_max[1], n.bbox_max[2], as_float(n.start), as_float(node_word(n))};
   }
   return out;
+}
+bool tree_fits_node_words(const HostTree& tree, std::string& error) {
+  if (tree.nodes.size() > (size_t)kMaxTreeNodes || tree.prims.size() > (size_t)kMaxTreePrims)
+    return error = "tree too large for the device node words (2^28 nodes, 2^26 primitives per tree)", false;
+  return true;
 }
 
 frame3 to_frame(const ygl_frame3f& f) {
   return {{f.x[0], f.x[1], f.x[2]}, {f.y[0], f.y[1], f.y[2]}, {f.z[0], f.z[1], f.z[2]}, {f.o[0], f.o[1], f.o[2]}};
 }
 
-void pack_instance(float4h* out, const ygl_instance& inst, int id, int kind, int num_nodes) {
+void pack_instance(float4h* out, const ygl_instance& inst, int id, int kind, int num_nodes, const float4h* root) {
   frame3 inv = frame_inverse(to_frame(inst.frame), true);  // inverse(frame, true), yocto_bvh.cpp:602
   out[0]     = {inv.x.x, inv.x.y, inv.x.z, inv.y.x};
   out[1]     = {inv.y.y, inv.y.z, inv.z.x, inv.z.y};
@@ -206,6 +216,8 @@ void pack_instance(float4h* out, const ygl_instance& inst, int id, int kind, int
   out[3]     = {as_float(inst.shape), as_float(id), as_float(kind), as_float(num_nodes)};
   out[4]     = {0, 0, 0, 0};  // device pointers of the shape's tree: patched at upload (ygl_api.cpp)
   out[5]     = {0, 0, 0, 0};
+  out[6]     = root[0];  // the root node of the shape's tree (object space): entering an instance tests it without
+  out[7]     = root[1];  // another dependent load; with it the packet is exactly one 128-byte line
 }
 
 }  // namespace
@@ -319,7 +331,8 @@ void pack_top(const ygl_scene_desc& desc, HostBvh& out) {
   out.top_nodes = pack_nodes(out.top);
   auto pack = [&](float4h* dst, int id) {
     const ygl_instance& inst = desc.instances[id];
-    pack_instance(dst, inst, id, out.shape_kind[inst.shape], (int)out.shapes[inst.shape].nodes.size());
+    pack_instance(dst, inst, id, out.shape_kind[inst.shape], (int)out.shapes[inst.shape].nodes.size(),
+        out.shape_nodes[inst.shape].data());
   };
   out.top_packets.resize(out.top.prims.size() * kInstancePacketQuads);
   for (size_t k = 0; k < out.top.prims.size(); k++) pack(&out.top_packets[kInstancePacketQuads * k], out.top.prims[k]);
@@ -381,6 +394,7 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
                    " exceeds the traversal stack (128 entries, as in the reference)";
       return;
     }
+    if (!tree_fits_node_words(tree, errors[si])) return;
     out.shape_nodes[si]   = pack_nodes(tree);
     out.shape_packets[si] = pack_leaves(s, kind, tree);
   });
@@ -391,6 +405,7 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
   if (!instance_bounds(desc, out, ibox, error)) return false;
   out.top = make_tree(ibox, highquality);
   if (out.top.max_stack > kMaxTreeDepth) return error = "instance BVH too deep for the traversal stack (128 entries)", false;
+  if (!tree_fits_node_words(out.top, error)) return false;
   pack_top(desc, out);
   return true;
 }
@@ -414,7 +429,7 @@ bool adopt_scene_bvh(const ygl_scene_desc& desc, const ygl_bvh_node* top_nodes, 
     tree.nodes.assign(shape_nodes[si], shape_nodes[si] + shape_num_nodes[si]);
     tree.prims.assign(shape_prims[si], shape_prims[si] + shape_num_prims[si]);
     std::string what = "shape " + std::to_string(si);
-    if (!measure_tree(tree, (int)bboxes.size(), what.c_str(), error)) return false;
+    if (!measure_tree(tree, (int)bboxes.size(), what.c_str(), error) || !tree_fits_node_words(tree, error)) return false;
     out.shape_nodes[si]   = pack_nodes(tree);
     out.shape_packets[si] = pack_leaves(s, kind, tree);
   }
@@ -422,7 +437,7 @@ bool adopt_scene_bvh(const ygl_scene_desc& desc, const ygl_bvh_node* top_nodes, 
   if (!instance_bounds(desc, out, ibox, error)) return false;
   out.top.nodes.assign(top_nodes, top_nodes + num_top_nodes);
   out.top.prims.assign(top_prims, top_prims + num_top_prims);
-  if (!measure_tree(out.top, desc.num_instances, "instance tree", error)) return false;
+  if (!measure_tree(out.top, desc.num_instances, "instance tree", error) || !tree_fits_node_words(out.top, error)) return false;
   pack_top(desc, out);
   return true;
 }

@@ -20,7 +20,8 @@ struct float4h {
   float x, y, z, w;
 };
 constexpr int kMaxTreeDepth        = 128;  // levels per tree the device walk accepts = the reference's stack (yocto_bvh.cpp:469)
-constexpr int kInstancePacketQuads = 6;  // float4 per DInstancePacket (ygl_scene.cuh)
+constexpr int kInstancePacketQuads = 8;  // float4 per DInstancePacket (ygl_scene.cuh): one 128-byte line
+constexpr int kMaxTreeNodes        = 1 << 28, kMaxTreePrims = 1 << 26;  // ranges of the device node words
 
 struct HostBvh {
   HostTree              top;
@@ -30,8 +31,8 @@ struct HostBvh {
   std::vector<std::vector<float4h>> shape_nodes;    // 2 float4 per node
   std::vector<std::vector<float4h>> shape_packets;  // leaf packets, primitive order
   std::vector<float4h>              top_nodes;
-  std::vector<float4h>              top_packets;   // 6 float4 per instance, leaf order
-  std::vector<float4h>              inst_packets;  // 6 float4 per instance, id order
+  std::vector<float4h>              top_packets;   // 8 float4 per instance, leaf order
+  std::vector<float4h>              inst_packets;  // 8 float4 per instance, id order
 };
 
 struct HostLight {

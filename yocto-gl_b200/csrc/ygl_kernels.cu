@@ -204,9 +204,13 @@ struct ExtendSource {
     }
     shade_push(q, flag, cls, lane | (shadow ? kEntryShadow : 0));
   }
-  YGL_D int* saved() { return st.susp + (size_t)lane * kSuspendWords; }
+  // Parked rays: a thread parks at most one ray per launch, into ITS slot of this launch's half of the pool; the ray
+  // resumes in the next launch (other parity), which reads that half while parking into the other one.
+  YGL_D int* save_slot() { return q.park[parity] + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * kSuspendWords; }
+  YGL_D const int* load_slot() { return q.park[1 - parity] + (size_t)(int)st.susp[lane] * kSuspendWords; }
   // per-lane (divergent) call: the parked ray goes straight back into the next extend queue, flagged for resumption
   YGL_D void commit_suspended() {
+    st.susp[lane]           = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int pos           = atomicAdd(&q.counters->n_ext[1 - parity], 1);
     q.ext[1 - parity][pos]  = lane | kEntryResume | (shadow ? kEntryShadow : 0);
   }
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene,
   ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, q, parity, scene.inst_class, scene.has_volumes, 0, refill_thr,
       node_reps, suspend_below, lone_below, lone_steps, 0, false};
   trav_counters tc = {};
-  trace_stream<COUNT, kStreamThreads>(scene, src, tc);
+  trace_stream<COUNT, kStreamThreads, kSharedStack>(scene, src, tc);
   {
     unsigned v = src.finished;
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFullWarp, v, off);
@@ -1267,8 +1271,9 @@ struct RingSource {
     }
     ring_push(q.shade, flag, lane, q.abort);
   }
-  YGL_D int* saved() { return st.susp; }  // never used: rays are not suspended in persistent mode
-  YGL_D void commit_suspended() {}
+  YGL_D int*       save_slot() { return nullptr; }  // never used: rays are not parked in persistent mode
+  YGL_D const int* load_slot() { return nullptr; }
+  YGL_D void       commit_suspended() {}
 };
 
 // Send a shaded lane on (WARP-UNIFORM). A finished path is accumulated here and the lane's next camera sample
@@ -1358,7 +1363,7 @@ __global__ void __launch_bounds__(kPersistThreads, YGL_PERSIST_MINBLOCKS) k_pers
     trav_counters tc = {};
     while (true) {
       const unsigned before = src.taken;
-      trace_stream<false, kPersistThreads>(scene, src, tc);
+      trace_stream<false, kPersistThreads, 12>(scene, src, tc);
       if (__any_sync(kFullWarp, src.taken != before)) {
         backoff = 64;
         continue;
@@ -1476,15 +1481,20 @@ void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, in
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   k_generate<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }
-void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, Queues q, int parity,
-    unsigned long long* trav) {
-  // persistent kernel: exactly the resident capacity (SMs x blocks/SM from the occupancy API), capped
-  // by the lanes that can exist
+static int extend_blocks_per_sm() {
   static int per_sm = 0;
   if (!per_sm) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_extend<false, 0>), 128, 0);
     if (per_sm < 1) per_sm = 1;
   }
+  return per_sm;
+}
+int extend_grid_threads(int num_sms) { return num_sms * extend_blocks_per_sm() * 128; }
+void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, Queues q, int parity,
+    unsigned long long* trav) {
+  // persistent kernel: exactly the resident capacity (SMs x blocks/SM from the occupancy API), capped
+  // by the lanes that can exist
+  const int per_sm = extend_blocks_per_sm();
   int blocks = num_sms * (tune.ext_blocks_per_sm > 0 ? std::min(per_sm, tune.ext_blocks_per_sm) : per_sm);
   int needed = (st.num_lanes + 127) / 128;
   if (blocks > needed) blocks = needed;

@@ -73,7 +73,7 @@ struct PathStateT {
   SArr<float4, COH> vol_a;     // volume slot: density.xyz, scanisotropy
   SArr<float4, COH> vol_b;     // volume slot: scattering.xyz
   SArr<float4, COH> pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
-  SArr<int, COH>    susp;      // kSuspendWords ints per lane: traversal state of a ray suspended by k_extend
+  SArr<int, COH>    susp;      // save slot of the lane's ray while it is parked by k_extend (see Queues::park)
   // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
   SArr<float4, COH> aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
   SArr<float4, COH> aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
@@ -102,6 +102,7 @@ struct Queues {
   int* shade[kNumClasses];  // lanes whose ray has been traced, by shading class (null: class absent from the scene)
   int* lpdf;                // lanes waiting for sample_lights_pdf
   int* acc;                 // lanes whose sample finished
+  int* park[2];             // save slots of rays parked by k_extend: [launch parity][thread of its grid][kSuspendWords]
   // counters (device): see QueueCounters
   struct Counters* counters;
 };
@@ -167,6 +168,7 @@ void launch_seed_lanes(cudaStream_t s, LaunchCfg cfg, PathState st, Queues q, in
 void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 // trav: device array of 7 counters {top nodes, bottom nodes, instance visits, tri, quad, line, point tests} or null.
 // Finished rays go to q.shade[class] (class 0 for every lane unless scene.inst_class is set).
+int  extend_grid_threads(int num_sms);  // threads of the largest extend grid (sizes Queues::park)
 void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, Queues q, int parity,
     unsigned long long* trav);
 // one launch per shading class present (class_mask bit c), or the single generic kernel when binning is off

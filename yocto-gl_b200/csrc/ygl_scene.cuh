@@ -1,9 +1,11 @@
 // ygl_scene.cuh — device-resident scene arena (HBM layout) shared by all kernels.
 //
 // Everything the hot path reads lives in one arena per scene (see DESIGN.md "Data layout"):
-//   * BVH nodes as 2 x float4 (32 B, 16-B aligned -> two LDG.128):
-//       n0 = {min.x, min.y, min.z, max.x}   n1 = {max.y, max.z, start(bits), meta(bits)}
-//       meta = num | axis << 16 | internal << 24         (bvh_node, yocto_shape.h:474-480)
+//   * BVH nodes as 2 x float4 (32 B, 16-B aligned -> two LDG.128; the two children of a node are adjacent,
+//     yocto_bvh.cpp:277-279, so one 64-byte fetch brings both):
+//       n0 = {min.x, min.y, min.z, max.x}   n1 = {max.y, max.z, start(bits), word(bits)}
+//       word = internal ? 0x80000000 | axis << 28 | first child : num << 26 | first primitive
+//                                                            (bvh_node, yocto_shape.h:474-480)
 //   * leaf primitives pre-gathered into float4 packets IN bvh.primitives ORDER, so a leaf's
 //     range is one contiguous run of 128-bit loads (vertex indices + positions are not chased):
 //       triangle 3 x float4 {p0.xyz,e1.x}{e1.yz,e2.xy}{e2.z,-,-,-}  with e1=p1-p0, e2=p2-p0
@@ -12,8 +14,8 @@
 //       point    1 x float4 {p,r}
 //     (e1/e2 are pure functions of the inputs evaluated with the reference's own rounding, so
 //      precomputing them cannot change a result bit.)
-//   * instances as 6 x float4 packets {inverse frame (12 floats), shape, instance, kind, #nodes,
-//     node/packet/primitive pointers of the shape's tree}: the
+//   * instances as 8 x float4 packets = one 128-byte line {inverse frame (12 floats), shape, instance, kind,
+//     #nodes, node/packet/primitive pointers of the shape's tree, the root node of that tree}: the
 //     reference recomputes inverse(frame, true) per instance visit (yocto_bvh.cpp:602); it is a
 //     pure function of the frame, so it is evaluated once on the host with the same arithmetic.
 //   * original element/vertex arrays (reference layout) for the shading-side eval_* functions.
@@ -22,6 +24,10 @@
 #include "ygl_shading.cuh"
 
 namespace ygl {
+
+// a ray parked by the extend kernel carries its traversal state to the next launch: 12 header words + its stack
+constexpr int kSuspendStack = 24;                      // stack entries (t0, work word) a parked ray can carry
+constexpr int kSuspendWords = 12 + 2 * kSuspendStack;  // words per save slot
 
 enum : int { kElemNone = 0, kElemPoints = 1, kElemLines = 2, kElemTriangles = 3, kElemQuads = 4 };
 
@@ -47,9 +53,9 @@ struct DShape {
   int          num_points, num_lines, num_triangles, num_quads;
 };
 
-struct DInstancePacket {  // 96 B = 6 x LDG.128, no dependent load to reach the shape's tree
-  float4 q[6];  // q0-q2: inverse frame x,y,z,o (12 floats); q3: shape, instance, bvh kind, num nodes (int bits);
-                // q4: nodes pointer, leaf-packets pointer; q5: primitives pointer, -, -
+struct __align__(128) DInstancePacket {  // 128 B = 8 x LDG.128 of one line, no dependent load to reach the shape's tree
+  float4 q[8];  // q0-q2: inverse frame x,y,z,o (12 floats); q3: shape, instance, bvh kind, num nodes (int bits);
+                // q4: nodes pointer, leaf-packets pointer; q5: primitives pointer, -, -; q6-q7: the tree's root node
 };
 
 struct DInstance {  // shading side: forward frame + ids (instance_data, yocto_scene.h:145)
