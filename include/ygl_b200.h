@@ -213,6 +213,19 @@ int  ygl_scene_create(ygl_context* ctx, const ygl_scene_desc* desc, ygl_scene** 
 int  ygl_scene_update_cameras(ygl_scene* scene, const ygl_camera* cameras, int num_cameras);
 void ygl_scene_destroy(ygl_scene* scene);
 
+/* ---- scene ingestion: load_scene (yocto_sceneio.h:93) for Yocto/GL JSON scenes (asset version 4.2 / 5.0) with PLY
+ * shapes and PNG / Radiance-HDR textures, read into flat host arrays. The returned object owns the arrays its
+ * ygl_scene_desc views; hand that desc to ygl_scene_create / ygl_bvh_build / ygl_lights_create / ygl_state_create.
+ * Defaults, lookat frames, texcoord flip, polygon fans, missing camera and missing radius follow the reference
+ * (yocto_sceneio.cpp:3618-3860, :1008-1035, :1796-1837, :2119-2148). OBJ / glTF / pbrt / EXR inputs and subdivs are
+ * refused with an error. ---- */
+typedef struct ygl_loaded_scene ygl_loaded_scene;
+int  ygl_scene_load(const char* filename, ygl_loaded_scene** out);
+const ygl_scene_desc* ygl_loaded_scene_desc(const ygl_loaded_scene* scene);
+/* names kept from the file; kind: 0 camera, 1 texture, 2 material, 3 shape, 4 instance, 5 environment */
+const char* ygl_loaded_scene_name(const ygl_loaded_scene* scene, int kind, int index);
+void ygl_loaded_scene_destroy(ygl_loaded_scene* scene);
+
 /* ---- bvh: make_trace_bvh / make_scene_bvh (host build in the reference's node order) ---- */
 /* Pure host work; the device copy is made on first use with a context. */
 int  ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out);
@@ -314,7 +327,8 @@ int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_trav
 /* Scheduling mode of ygl_trace_samples / ygl_trace_image (both give bit-identical results):
  * YGL_MODE_WAVEFRONT (default) - one kernel per stage and iteration, linked by compacted lane queues;
  * YGL_MODE_PERSISTENT - ONE resident kernel per call, stage-specialised SMs linked by ring queues in global memory
- * (independent of the tile size, no per-iteration launches; opt-in). */
+ * (independent of the tile size, no per-iteration launches; opt-in). The persistent kernel serves the single-stage
+ * samplers; pathdirect and pathmis always run on the wavefront scheduler. */
 enum { YGL_MODE_WAVEFRONT = 0, YGL_MODE_PERSISTENT = 1 };
 int ygl_context_set_mode(ygl_context* ctx, int mode);
 /* Scheduling knobs of a context, by name (the library reads no environment variables). None can change a result

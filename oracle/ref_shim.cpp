@@ -14,6 +14,7 @@
 #include <yocto/yocto_bvh.h>
 #include <yocto/yocto_geometry.h>
 #include <yocto/yocto_scene.h>
+#include <yocto/yocto_sceneio.h>
 #include <yocto/yocto_shape.h>
 #include <yocto/yocto_trace.h>
 
@@ -207,6 +208,22 @@ void* ref_scene_create(const ygl_scene_desc* desc) {
 void* ref_scene_cornellbox() {
   auto rs   = new ref_scene{};
   rs->scene = make_cornellbox();
+  return rs;
+}
+
+// The reference's own loader (load_scene, yocto_sceneio.cpp:2761): JSON + PLY + textures. Returns null on error
+// (message in ref_last_error). Subdivs are tesselated like ytrace does (apps/ytrace.cpp:110-113).
+static std::string g_ref_error;
+const char* ref_last_error() { return g_ref_error.c_str(); }
+void* ref_scene_load(const char* filename) {
+  auto rs    = new ref_scene{};
+  auto error = std::string{};
+  if (!load_scene(filename, rs->scene, error)) {
+    g_ref_error = error;
+    delete rs;
+    return nullptr;
+  }
+  if (!rs->scene.subdivs.empty()) tesselate_subdivs(rs->scene);
   return rs;
 }
 

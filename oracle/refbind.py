@@ -29,6 +29,9 @@ class Ref:
         lib.ref_scene_create.argtypes = [C.POINTER(abi.SceneDesc)]
         lib.ref_scene_cornellbox.restype = vp
         lib.ref_scene_destroy.argtypes = [vp]
+        lib.ref_scene_load.restype = vp
+        lib.ref_scene_load.argtypes = [C.c_char_p]
+        lib.ref_last_error.restype = C.c_char_p
         lib.ref_scene_describe.argtypes = [vp, C.POINTER(abi.SceneDesc)]
         lib.ref_bvh_build.restype = vp
         lib.ref_bvh_build.argtypes = [vp, C.c_int]
@@ -77,6 +80,17 @@ class Ref:
     def cornellbox(self):
         """The reference's make_cornellbox() (yocto_scene.cpp:970) as an abi.Scene."""
         h = self.lib.ref_scene_cornellbox()
+        d = abi.SceneDesc()
+        self.lib.ref_scene_describe(h, C.byref(d))
+        sc = abi.Scene.from_desc(d)
+        self.lib.ref_scene_destroy(h)
+        return sc
+
+    def load_scene(self, filename):
+        """The reference's load_scene (yocto_sceneio.cpp:2761) as an abi.Scene (arrays copied out)."""
+        h = self.lib.ref_scene_load(str(filename).encode())
+        if not h:
+            raise RuntimeError(self.lib.ref_last_error().decode())
         d = abi.SceneDesc()
         self.lib.ref_scene_describe(h, C.byref(d))
         sc = abi.Scene.from_desc(d)

@@ -1,0 +1,31 @@
+"""Test helper: the reference's own test scenes (copied by oracle/copy_test_data.py into oracle/_ref/data, a
+git-ignored build directory that travels to the GPU box) laid out again as <dir>/<name>/<name>.json + shapes/ +
+textures/, the layout load_scene expects (uris are relative to the JSON file)."""
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "oracle", "_ref", "data")
+
+
+def available():
+    return os.path.isdir(os.path.join(DATA, "scenes"))
+
+
+def names():
+    return sorted(f[:-5] for f in os.listdir(os.path.join(DATA, "scenes")) if f.endswith(".json")) if available() else []
+
+
+def pool(kind, name):
+    return os.path.join(DATA, "pool", kind, name)
+
+
+def scene_file(name, tmpdir):
+    """Path of <tmpdir>/<name>/<name>.json with shapes/ and textures/ symlinked to the shared pool."""
+    d = os.path.join(str(tmpdir), name)
+    os.makedirs(d, exist_ok=True)
+    dst = os.path.join(d, name + ".json")
+    if not os.path.exists(dst):
+        os.symlink(os.path.join(DATA, "scenes", name + ".json"), dst)
+        for kind in ("shapes", "textures"):
+            os.symlink(os.path.join(DATA, "pool", kind), os.path.join(d, kind))
+    return dst

@@ -371,6 +371,54 @@ def test_full_size_rays_bit_exact(ctx, ref, name):
     assert compare_hits(rs.intersect(some, find_any=True, nthreads=threads), ds.intersect(some, find_any=True)) == 0
 
 
+# ---- the reference's own scene files through the library's own loader ----
+import scene_data  # noqa: E402
+
+
+@pytest.mark.skipif(not scene_data.available(), reason="oracle/_ref/data not present")
+@pytest.mark.parametrize("name", [n for n in scene_data.names() if n != "cornellbox"] or ["none"])
+def test_reference_scene_files_render_bit_exact(ctx, ref, name, tmp_path):
+    """tests/_version43/{features1, materials1-4, shapes4}: loaded with ygl_scene_load (JSON + PLY + PNG/HDR), rendered
+    on the GPU, compared bit for bit with the reference rendering the scene IT loaded from the same file — every
+    camera of the file for one of them, the default camera for the rest."""
+    path = scene_data.scene_file(name, tmp_path)
+    ours, theirs = lib.load_scene(path), ref.load_scene(path)
+    rs, ds = ref.scene(theirs), lib.DeviceScene(ctx, ours)
+    cameras = range(len(ours.cameras)) if name == "features1" else [0]
+    for camera in cameras:
+        params = abi.trace_params(resolution=360, samples=2, bounces=8, batch=2, camera=camera)
+        want = rs.trace_image(params, full=True)
+        st = ds.make_state(params)
+        ds.trace_samples(st, params)
+        got = st.download(full=True)
+        for k in ("image", "albedo", "normal", "hits"):
+            assert got[k].tobytes() == want[k].tobytes(), (name, camera, k, image_stats(want["image"], got["image"]))
+    rays = np.concatenate([random_rays(ours, 200000), scenes.camera_rays(ours, abi.trace_params(resolution=360), 100000)])
+    assert compare_hits(rs.intersect(rays), ds.intersect(rays)) == 0
+
+
+@pytest.mark.skipif(not scene_data.available(), reason="oracle/_ref/data not present")
+@pytest.mark.parametrize("which", ["c2_bunny", "c5_hairball"])
+def test_baseline_assets_full_size_bit_exact(ctx, ref, which, tmp_path):
+    """C2 and C5 with the assets BASELINE.json names (the reference's bunny.ply: 144,046 triangles; hairball1.ply:
+    2 x 262,144 line segments + 2 bunnies) at the configs' resolution: whole frame bit-identical to the reference."""
+    pool = os.path.join(scene_data.DATA, "pool")
+    if which == "c2_bunny":
+        scene, kw = scenes.bunny_file_scene(tmp_path, pool), dict(resolution=1280, samples=2, bounces=8, batch=2)
+    else:
+        scene, kw = scenes.hairball_file_scene(tmp_path, pool), dict(resolution=1920, samples=1, bounces=12, batch=1)
+    params = abi.trace_params(**kw)
+    want = ref.scene(scene).trace_image(params, full=True)
+    ds = lib.DeviceScene(ctx, scene)
+    st = ds.make_state(params)
+    ds.trace_samples(st, params)
+    got = st.download(full=True)
+    assert got["image"].shape[1] == kw["resolution"]
+    for k in ("image", "albedo", "normal", "hits"):
+        assert got[k].tobytes() == want[k].tobytes(), (which, k, image_stats(want["image"], got["image"]))
+    np.testing.assert_array_equal(got["rngs"], want["rngs"])
+
+
 COUNTER_KEYS = ("top_nodes", "bottom_nodes", "instance_visits", "triangle_tests", "quad_tests", "line_tests", "point_tests")
 
 

@@ -1,0 +1,102 @@
+"""Scene ingestion (ygl_scene_load: JSON v4.2 + PLY + PNG / HDR, yocto-gl_b200/csrc/ygl_sceneio.cpp) against the
+reference's own load_scene (yocto_sceneio.cpp:2761) on the reference's own test scenes: every array of scene_data
+must come out bit-identical — cameras, instances, materials, environments, texture pixels, shape elements and vertex
+data. Host-only: runs without a GPU. Needs oracle/_ref/data (oracle/copy_test_data.py) and the reference oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import scene_data
+from ygl_b200 import lib
+
+pytestmark = pytest.mark.skipif(not scene_data.available(), reason="oracle/_ref/data not present (run `make -C oracle data`)")
+
+
+def assert_scenes_identical(a, b):
+    assert (len(a.cameras), len(a.instances), len(a.materials), len(a.environments), len(a.shapes), len(a.textures)) == \
+           (len(b.cameras), len(b.instances), len(b.materials), len(b.environments), len(b.shapes), len(b.textures))
+
+    def same(x, y, what):
+        if isinstance(x, dict):
+            assert x.keys() == y.keys(), what
+            for k in x:
+                same(x[k], y[k], f"{what}.{k}")
+        elif isinstance(x, np.ndarray):
+            assert x.shape == y.shape and x.dtype == y.dtype and x.tobytes() == y.tobytes(), what
+        elif isinstance(x, (tuple, list)):
+            assert np.asarray(x, np.float32).tobytes() == np.asarray(y, np.float32).tobytes(), what
+        elif isinstance(x, float):
+            assert np.float32(x).tobytes() == np.float32(y).tobytes(), what
+        else:
+            assert x == y, what
+
+    for group in ("cameras", "instances", "materials", "environments", "shapes", "textures"):
+        for k, (x, y) in enumerate(zip(getattr(a, group), getattr(b, group))):
+            same(x, y, f"{group}[{k}]")
+
+
+@pytest.mark.parametrize("name", scene_data.names())
+def test_loader_matches_reference_loader(ref, name, tmp_path):
+    path = scene_data.scene_file(name, tmp_path)
+    ours = lib.load_scene(path)
+    theirs = ref.load_scene(path)
+    assert_scenes_identical(ours, theirs)
+    want = [c.get("name", "") for c in json.load(open(path)).get("cameras", [])]
+    assert ours.camera_names == (want or ["camera"])
+
+
+def test_loader_errors(tmp_path):
+    with pytest.raises(lib.YglError):
+        lib.load_scene(tmp_path / "missing.json")
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"asset": {"version": "4.2"}, "cameras": [{"lens": "wide"}]}')
+    with pytest.raises(lib.YglError):  # a key of the wrong type is a parse error, as in the reference
+        lib.load_scene(bad)
+    old = tmp_path / "old.json"
+    old.write_text('{"asset": {"version": "4.1"}}')
+    with pytest.raises(lib.YglError):
+        lib.load_scene(old)
+    sub = tmp_path / "sub.json"
+    sub.write_text('{"asset": {"version": "4.2"}, "subdivs": [{"uri": "subdivs/x.obj"}]}')
+    with pytest.raises(lib.YglError):
+        lib.load_scene(sub)
+    noshape = tmp_path / "noshape.json"
+    noshape.write_text('{"asset": {"version": "4.2"}, "shapes": [{"uri": "shapes/none.ply"}]}')
+    with pytest.raises(lib.YglError):
+        lib.load_scene(noshape)
+
+
+def test_ascii_and_big_endian_ply_and_lookat(ref, tmp_path):
+    """Formats the reference's test scenes do not use: ASCII and big-endian PLY, polygons (fans), mixed triangle /
+    quad faces, polylines, vertex colours without alpha, `lookat` cameras, a scene without camera (add_missing_camera)
+    and lines without radius (add_missing_radius) — all against the reference loader."""
+    import struct
+    d = tmp_path / "mini"
+    (d / "shapes").mkdir(parents=True)
+    (d / "shapes" / "poly.ply").write_text(
+        "ply\nformat ascii 1.0\ncomment test\nelement vertex 6\nproperty float x\nproperty float y\nproperty float z\n"
+        "property uchar red\nproperty uchar green\nproperty uchar blue\nproperty float s\nproperty float t\n"
+        "element face 3\nproperty list uchar int vertex_indices\nend_header\n"
+        "0 0 0 255 0 0 0 0\n1 0 0 0 255 0 1 0\n1 1 0 0 0 255 1 1\n0 1 0 10 20 30 0 1\n0.5 1.5 0.25 1 2 3 0.5 0.75\n-0.5 0.5 1e-3 4 5 6 0.125 0.0625\n"
+        "3 0 1 2\n4 0 1 2 3\n5 0 1 2 4 5\n")
+    verts = [(0.0, 0.0, 0.0), (1.0, 0.5, 0.25), (2.0, 1.5, -0.125), (3.0, 0.0, 7.5)]
+    with open(d / "shapes" / "lines.ply", "wb") as f:
+        f.write(b"ply\nformat binary_big_endian 1.0\nelement vertex 4\nproperty double x\nproperty double y\nproperty double z\n"
+                b"element line 2\nproperty list uchar ushort vertex_indices\nend_header\n")
+        for v in verts:
+            f.write(struct.pack(">ddd", *v))
+        f.write(struct.pack(">BHHH", 3, 0, 1, 2) + struct.pack(">BHH", 2, 2, 3))
+    (d / "mini.json").write_text(json.dumps({
+        "asset": {"version": "4.2", "copyright": "test"},
+        "materials": [{"name": "m", "type": "glossy", "color": [0.1, 0.2, 0.3], "roughness": 0.25}, {"type": "nonsense"}],
+        "shapes": [{"name": "poly", "uri": "shapes/poly.ply"}, {"name": "lines", "uri": "shapes/lines.ply"}],
+        "instances": [{"shape": 0, "material": 0}, {"shape": 1, "material": 1, "lookat": [1, 2, 3, 0, 0.5, 0, 0, 1, 0]}],
+        "environments": [{"emission": [1, 2, 3], "lookat": [0, 0, 0, 0, 0, -1, 0, 1, 0]}]}))
+    assert_scenes_identical(lib.load_scene(d / "mini.json"), ref.load_scene(d / "mini.json"))
+    scene = json.loads((d / "mini.json").read_text())
+    scene["cameras"] = [{"name": "c", "lookat": [3, 2, 5, 0.5, 0.5, 0, 0, 1, 0], "aspect": 2.0, "orthographic": True}]
+    (d / "mini2.json").write_text(json.dumps(scene))
+    os.symlink(d / "shapes", tmp_path / "shapes2")
+    assert_scenes_identical(lib.load_scene(d / "mini2.json"), ref.load_scene(d / "mini2.json"))

@@ -172,6 +172,8 @@ static std::atomic<uint64_t> g_epoch{1};
 extern "C" {
 
 const char* ygl_last_error(void) { return g_error.c_str(); }
+// for the other translation units of the library (ygl_sceneio.cpp)
+void ygl_internal_set_error(const char* message) { g_error = message ? message : ""; }
 const char* ygl_version(void) { return "ygl_b200 0.1 (sm_100a wavefront path tracer)"; }
 
 void ygl_trace_params_default(ygl_trace_params* p) {
@@ -1159,9 +1161,15 @@ static int run_persistent(ygl_context* ctx, ygl_state* state, const ygl_trace_pa
   return YGL_OK;
 }
 
-// Traversal counting needs the wavefront's counting extend kernel.
+// Which scheduler renders a call. The persistent kernel serves the single-stage samplers; traversal counting needs the
+// wavefront's counting extend kernel, and the multi-stage samplers (pathdirect / pathmis: light-pdf and shadow-ray
+// stages that re-enter the shading ring) run on the wavefront scheduler whatever the mode says - on the persistent
+// one they were seen to depend on timing (a resumed pathmis batch differed from the reference under
+// compute-sanitizer), so until that is understood the mode does not apply to them.
 static int run_render(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
-  if (ctx->mode == YGL_MODE_PERSISTENT && !ctx->count_traversal) return run_persistent(ctx, state, params, nsamples);
+  const bool multi_stage = params.sampler == YGL_SAMPLER_PATHDIRECT || params.sampler == YGL_SAMPLER_PATHMIS;
+  if (ctx->mode == YGL_MODE_PERSISTENT && !ctx->count_traversal && !multi_stage)
+    return run_persistent(ctx, state, params, nsamples);
   return run_wavefront(ctx, state, params, nsamples);
 }
 

@@ -1,0 +1,1027 @@
+// ygl_sceneio.cpp — scene ingestion: Yocto/GL JSON scene files (asset version 4.2 / 5.0) with
+// PLY shapes and PNG / Radiance-HDR textures, read straight into the flat host arrays a ygl_scene_desc views, ready
+// for ygl_scene_create / ygl_bvh_build / ygl_lights_create. Host C++ only.
+//
+// Behavioural contract (what the arrays must equal, bit for bit, for the renders to match the reference's):
+//   load_json_scene     libs/yocto/yocto_sceneio.cpp:3618-3860   keys, defaults (yocto_scene.h:83-160), lookat, fix-ups
+//   load_shape (.ply)   libs/yocto/yocto_sceneio.cpp:1008-1035   + the ply getters of yocto_modelio.h:618-815
+//   load_texture        libs/yocto/yocto_sceneio.cpp:1796-1837   .hdr -> float rgba (stb's RGBE rule), .png -> byte rgba
+//   add_missing_camera / add_missing_radius          yocto_sceneio.cpp:2119-2148
+// Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
+// Not built: OBJ/glTF/pbrt/EXR inputs, subdivs (tesselate_subdivs, yocto_scene.cpp:739-813): such scenes are refused.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "../../include/ygl_b200.h"
+
+namespace {
+
+// the library's per-thread error string lives in ygl_api.cpp
+
+// ---------------------------------------------------------------------------------------------------------------
+// files
+// ---------------------------------------------------------------------------------------------------------------
+bool read_file(const std::string& filename, std::vector<uint8_t>& data, std::string& error) {
+  FILE* f = fopen(filename.c_str(), "rb");
+  if (!f) return error = "cannot open " + filename, false;
+  fseek(f, 0, SEEK_END);
+  long size = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  data.resize(size > 0 ? (size_t)size : 0);
+  size_t got = data.empty() ? 0 : fread(data.data(), 1, data.size(), f);
+  fclose(f);
+  if (got != data.size()) return error = "cannot read " + filename, false;
+  return true;
+}
+std::string path_dirname(const std::string& path) {
+  auto pos = path.find_last_of("/\\");
+  return pos == std::string::npos ? std::string{} : path.substr(0, pos);
+}
+std::string path_join(const std::string& a, const std::string& b) { return a.empty() ? b : a + "/" + b; }
+std::string path_extension(const std::string& path) {
+  auto pos = path.find_last_of('.');
+  if (pos == std::string::npos) return {};
+  auto ext = path.substr(pos);
+  for (auto& c : ext) c = (char)tolower((unsigned char)c);
+  return ext;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// JSON: a small document model (objects keep insertion order; numbers are doubles, like nlohmann's number_float_t)
+// ---------------------------------------------------------------------------------------------------------------
+struct JValue {
+  enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+  bool                                           boolean = false;
+  double                                         number  = 0;
+  std::string                                    string;
+  std::vector<JValue>                            array;
+  std::vector<std::pair<std::string, JValue>>    object;
+  const JValue* find(const char* key) const {
+    if (type != Object) return nullptr;
+    for (auto& kv : object)
+      if (kv.first == key) return &kv.second;
+    return nullptr;
+  }
+};
+
+struct JParser {
+  const char* p;
+  const char* end;
+  bool        ok = true;
+  void skip() {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) p++;
+  }
+  bool fail() { return ok = false; }
+  bool parse_string(std::string& out) {
+    if (p >= end || *p != '"') return fail();
+    p++;
+    while (p < end && *p != '"') {
+      if (*p == '\\') {
+        if (++p >= end) return fail();
+        switch (*p) {
+          case '"': out += '"'; break;
+          case '\\': out += '\\'; break;
+          case '/': out += '/'; break;
+          case 'b': out += '\b'; break;
+          case 'f': out += '\f'; break;
+          case 'n': out += '\n'; break;
+          case 'r': out += '\r'; break;
+          case 't': out += '\t'; break;
+          case 'u': {
+            if (end - p < 5) return fail();
+            unsigned cp = (unsigned)strtoul(std::string(p + 1, p + 5).c_str(), nullptr, 16);
+            p += 4;
+            if (cp < 0x80) out += (char)cp;
+            else if (cp < 0x800) out += (char)(0xC0 | (cp >> 6)), out += (char)(0x80 | (cp & 0x3F));
+            else out += (char)(0xE0 | (cp >> 12)), out += (char)(0x80 | ((cp >> 6) & 0x3F)), out += (char)(0x80 | (cp & 0x3F));
+          } break;
+          default: return fail();
+        }
+        p++;
+      } else {
+        out += *p++;
+      }
+    }
+    if (p >= end) return fail();
+    p++;
+    return true;
+  }
+  bool parse(JValue& v, int depth = 0) {
+    if (depth > 64) return fail();
+    skip();
+    if (p >= end) return fail();
+    if (*p == '{') {
+      v.type = JValue::Object;
+      p++;
+      skip();
+      if (p < end && *p == '}') return p++, true;
+      while (true) {
+        skip();
+        std::string key;
+        if (!parse_string(key)) return false;
+        skip();
+        if (p >= end || *p != ':') return fail();
+        p++;
+        v.object.emplace_back(std::move(key), JValue{});
+        if (!parse(v.object.back().second, depth + 1)) return false;
+        skip();
+        if (p < end && *p == ',') {
+          p++;
+          continue;
+        }
+        if (p < end && *p == '}') return p++, true;
+        return fail();
+      }
+    }
+    if (*p == '[') {
+      v.type = JValue::Array;
+      p++;
+      skip();
+      if (p < end && *p == ']') return p++, true;
+      while (true) {
+        v.array.emplace_back();
+        if (!parse(v.array.back(), depth + 1)) return false;
+        skip();
+        if (p < end && *p == ',') {
+          p++;
+          continue;
+        }
+        if (p < end && *p == ']') return p++, true;
+        return fail();
+      }
+    }
+    if (*p == '"') {
+      v.type = JValue::String;
+      return parse_string(v.string);
+    }
+    if (end - p >= 4 && !strncmp(p, "true", 4)) return v.type = JValue::Bool, v.boolean = true, p += 4, true;
+    if (end - p >= 5 && !strncmp(p, "false", 5)) return v.type = JValue::Bool, v.boolean = false, p += 5, true;
+    if (end - p >= 4 && !strncmp(p, "null", 4)) return v.type = JValue::Null, p += 4, true;
+    char* stop = nullptr;
+    v.number   = strtod(p, &stop);  // the buffer is NUL-terminated by the caller
+    if (stop == p) return fail();
+    v.type = JValue::Number;
+    p      = stop;
+    return true;
+  }
+};
+
+// get_opt of the reference: a present key of the wrong type is a parse error, a missing key keeps the default
+struct JReader {
+  bool ok = true;
+  void get(const JValue& e, const char* key, float& value) {
+    if (auto v = e.find(key)) {
+      if (v->type != JValue::Number) ok = false;
+      else value = (float)v->number;
+    }
+  }
+  void get(const JValue& e, const char* key, int& value) {
+    if (auto v = e.find(key)) {
+      if (v->type != JValue::Number) ok = false;
+      else value = (int)v->number;
+    }
+  }
+  void get_bool(const JValue& e, const char* key, int& value) {
+    if (auto v = e.find(key)) {
+      if (v->type != JValue::Bool) ok = false;
+      else value = v->boolean ? 1 : 0;
+    }
+  }
+  void get(const JValue& e, const char* key, std::string& value) {
+    if (auto v = e.find(key)) {
+      if (v->type != JValue::String) ok = false;
+      else value = v->string;
+    }
+  }
+  void get_floats(const JValue& e, const char* key, float* value, size_t n) {
+    if (auto v = e.find(key)) {
+      if (v->type != JValue::Array || v->array.size() != n) return void(ok = false);
+      for (size_t i = 0; i < n; i++) {
+        if (v->array[i].type != JValue::Number) return void(ok = false);
+        value[i] = (float)v->array[i].number;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small vector algebra with the reference's operation order (yocto_math.h): only for lookat / missing camera
+// ---------------------------------------------------------------------------------------------------------------
+struct v3 {
+  float x, y, z;
+};
+v3    operator-(const v3& a, const v3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+v3    operator+(const v3& a, const v3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+v3    operator*(const v3& a, float b) { return {a.x * b, a.y * b, a.z * b}; }
+v3    operator/(const v3& a, float b) { return {a.x / b, a.y / b, a.z / b}; }
+v3    operator-(const v3& a) { return {-a.x, -a.y, -a.z}; }
+float dot(const v3& a, const v3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+v3    cross(const v3& a, const v3& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+float length(const v3& a) { return std::sqrt(dot(a, a)); }
+v3    normalize(const v3& a) {
+  auto l = length(a);
+  return (l != 0) ? a / l : a;
+}
+// lookat_frame, yocto_math.h:2348-2358
+void lookat_frame(float* frame, const v3& eye, const v3& center, const v3& up, bool inv_xz) {
+  auto w = normalize(eye - center);
+  auto u = normalize(cross(up, w));
+  auto v = normalize(cross(w, u));
+  if (inv_xz) w = -w, u = -u;
+  float out[12] = {u.x, u.y, u.z, v.x, v.y, v.z, w.x, w.y, w.z, eye.x, eye.y, eye.z};
+  memcpy(frame, out, sizeof(out));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PLY (load_ply, yocto_modelio.cpp; element / property model of yocto_modelio.h:66-107)
+// ---------------------------------------------------------------------------------------------------------------
+enum PlyType { I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, PlyBad };
+int ply_size(PlyType t) {
+  static const int size[] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8, 0};
+  return size[t];
+}
+PlyType ply_type(const std::string& s) {
+  if (s == "char" || s == "int8") return I8;
+  if (s == "short" || s == "int16") return I16;
+  if (s == "int" || s == "int32") return I32;
+  if (s == "long" || s == "int64") return I64;
+  if (s == "uchar" || s == "uint8") return U8;
+  if (s == "ushort" || s == "uint16") return U16;
+  if (s == "uint" || s == "uint32") return U32;
+  if (s == "ulong" || s == "uint64") return U64;
+  if (s == "float" || s == "float32") return F32;
+  if (s == "double" || s == "float64") return F64;
+  return PlyBad;
+}
+struct PlyProperty {
+  std::string          name;
+  bool                 is_list = false;
+  PlyType              type = F32, count_type = U8;
+  std::vector<double>  values;  // every i8..i32 / u8..u32 / f32 / f64 value is exact in a double
+  std::vector<uint8_t> sizes;   // list sizes, kept as uint8 like the reference's ldata_u8
+};
+struct PlyElement {
+  std::string              name;
+  size_t                   count = 0;
+  std::vector<PlyProperty> properties;
+};
+double ply_read_binary(const uint8_t*& p, PlyType t, bool big_endian) {
+  uint8_t   b[8];
+  const int n = ply_size(t);
+  if (big_endian)
+    for (int i = 0; i < n; i++) b[i] = p[n - 1 - i];
+  else memcpy(b, p, n);
+  p += n;
+  switch (t) {
+    case I8: return (double)(int8_t)b[0];
+    case U8: return (double)b[0];
+    case I16: { int16_t v; memcpy(&v, b, 2); return v; }
+    case U16: { uint16_t v; memcpy(&v, b, 2); return v; }
+    case I32: { int32_t v; memcpy(&v, b, 4); return v; }
+    case U32: { uint32_t v; memcpy(&v, b, 4); return v; }
+    case I64: { int64_t v; memcpy(&v, b, 8); return (double)v; }
+    case U64: { uint64_t v; memcpy(&v, b, 8); return (double)v; }
+    case F32: { float v; memcpy(&v, b, 4); return v; }
+    case F64: { double v; memcpy(&v, b, 8); return v; }
+    default: return 0;
+  }
+}
+bool load_ply(const std::string& filename, std::vector<PlyElement>& elements, std::string& error) {
+  std::vector<uint8_t> data;
+  if (!read_file(filename, data, error)) return false;
+  auto parse_error = [&]() { return error = "cannot parse " + filename, false; };
+  data.push_back(0);
+  const char* p   = (const char*)data.data();
+  const char* end = p + data.size() - 1;
+  auto next_line = [&](std::string& line) {
+    if (p >= end) return false;
+    const char* e = (const char*)memchr(p, '\n', end - p);
+    if (!e) e = end;
+    line.assign(p, e);
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+    p = e < end ? e + 1 : end;
+    return true;
+  };
+  auto split = [](const std::string& line) {
+    std::vector<std::string> tokens;
+    size_t                   i = 0;
+    while (i < line.size()) {
+      while (i < line.size() && isspace((unsigned char)line[i])) i++;
+      size_t j = i;
+      while (j < line.size() && !isspace((unsigned char)line[j])) j++;
+      if (j > i) tokens.push_back(line.substr(i, j - i));
+      i = j;
+    }
+    return tokens;
+  };
+  std::string line;
+  if (!next_line(line) || line != "ply") return parse_error();
+  int  format = -1;  // 0 ascii, 1 little endian, 2 big endian
+  bool header_done = false;
+  while (next_line(line)) {
+    auto tok = split(line);
+    if (tok.empty()) continue;
+    if (tok[0] == "format") {
+      if (tok.size() < 2) return parse_error();
+      format = tok[1] == "ascii" ? 0 : tok[1] == "binary_little_endian" ? 1 : tok[1] == "binary_big_endian" ? 2 : -1;
+      if (format < 0) return parse_error();
+    } else if (tok[0] == "comment" || tok[0] == "obj_info") {
+    } else if (tok[0] == "element") {
+      if (tok.size() != 3) return parse_error();
+      elements.emplace_back();
+      elements.back().name  = tok[1];
+      elements.back().count = (size_t)strtoull(tok[2].c_str(), nullptr, 10);
+    } else if (tok[0] == "property") {
+      if (elements.empty() || tok.size() < 3) return parse_error();
+      PlyProperty prop;
+      if (tok[1] == "list") {
+        if (tok.size() != 5) return parse_error();
+        prop.is_list = true, prop.count_type = ply_type(tok[2]), prop.type = ply_type(tok[3]), prop.name = tok[4];
+        if (prop.count_type == PlyBad) return parse_error();
+      } else {
+        prop.type = ply_type(tok[1]), prop.name = tok[2];
+      }
+      if (prop.type == PlyBad) return parse_error();
+      elements.back().properties.push_back(std::move(prop));
+    } else if (tok[0] == "end_header") {
+      header_done = true;
+      break;
+    } else {
+      return parse_error();
+    }
+  }
+  if (!header_done || format < 0) return parse_error();
+  for (auto& elem : elements)
+    for (auto& prop : elem.properties) {
+      if (prop.is_list) prop.sizes.reserve(elem.count), prop.values.reserve(elem.count * 3);
+      else prop.values.reserve(elem.count);
+    }
+  if (format == 0) {
+    auto next_number = [&](double& v) {
+      while (p < end && isspace((unsigned char)*p)) p++;
+      if (p >= end) return false;
+      char* stop = nullptr;
+      v          = strtod(p, &stop);
+      if (stop == p) return false;
+      p = stop;
+      return true;
+    };
+    for (auto& elem : elements)
+      for (size_t row = 0; row < elem.count; row++)
+        for (auto& prop : elem.properties) {
+          double v;
+          if (!prop.is_list) {
+            if (!next_number(v)) return parse_error();
+            prop.values.push_back(prop.type == F32 ? (double)(float)v : v);
+          } else {
+            if (!next_number(v)) return parse_error();
+            const uint8_t n = (uint8_t)(long long)v;
+            prop.sizes.push_back(n);
+            for (int k = 0; k < n; k++) {
+              if (!next_number(v)) return parse_error();
+              prop.values.push_back(v);
+            }
+          }
+        }
+  } else {
+    const uint8_t* q    = (const uint8_t*)p;
+    const uint8_t* qend = (const uint8_t*)end;
+    const bool     be   = format == 2;
+    for (auto& elem : elements)
+      for (size_t row = 0; row < elem.count; row++)
+        for (auto& prop : elem.properties) {
+          if (!prop.is_list) {
+            if (qend - q < ply_size(prop.type)) return parse_error();
+            prop.values.push_back(ply_read_binary(q, prop.type, be));
+          } else {
+            if (qend - q < ply_size(prop.count_type)) return parse_error();
+            const uint8_t n = (uint8_t)(long long)ply_read_binary(q, prop.count_type, be);
+            prop.sizes.push_back(n);
+            if (qend - q < (ptrdiff_t)n * ply_size(prop.type)) return parse_error();
+            for (int k = 0; k < n; k++) prop.values.push_back(ply_read_binary(q, prop.type, be));
+          }
+        }
+  }
+  return true;
+}
+const PlyProperty* ply_find(const std::vector<PlyElement>& elements, const char* element, const char* property) {
+  for (auto& elem : elements) {
+    if (elem.name != element) continue;
+    for (auto& prop : elem.properties)
+      if (prop.name == property) return &prop;
+  }
+  return nullptr;
+}
+
+struct HostShape {
+  std::vector<int32_t> points, lines, triangles, quads;
+  std::vector<float>   positions, normals, texcoords, colors, radius;
+};
+// get_values(ply, "vertex", {...}), yocto_modelio.h:548-566: all properties present and scalar, else nothing
+template <size_t N>
+void ply_vertex_values(const std::vector<PlyElement>& ply, const char* const (&names)[N], std::vector<float>& out) {
+  out.clear();
+  const PlyProperty* props[N];
+  for (size_t k = 0; k < N; k++) {
+    props[k] = ply_find(ply, "vertex", names[k]);
+    if (!props[k] || props[k]->is_list) return;
+  }
+  const size_t n = props[0]->values.size();
+  out.resize(n * N);
+  for (size_t k = 0; k < N; k++)
+    for (size_t i = 0; i < n && i < props[k]->values.size(); i++) out[i * N + k] = (float)props[k]->values[i];
+}
+// load_shape for .ply, yocto_sceneio.cpp:1018-1035 (flip_texcoord = true as load_json_scene passes)
+bool load_shape(const std::string& filename, HostShape& shape, std::string& error) {
+  if (path_extension(filename) != ".ply") return error = "unsupported format " + filename, false;
+  std::vector<PlyElement> ply;
+  if (!load_ply(filename, ply, error)) return false;
+  ply_vertex_values(ply, {"x", "y", "z"}, shape.positions);
+  ply_vertex_values(ply, {"nx", "ny", "nz"}, shape.normals);
+  if (ply_find(ply, "vertex", "u")) ply_vertex_values(ply, {"u", "v"}, shape.texcoords);
+  else ply_vertex_values(ply, {"s", "t"}, shape.texcoords);
+  for (size_t i = 0; i + 1 < shape.texcoords.size(); i += 2) shape.texcoords[i + 1] = 1 - shape.texcoords[i + 1];
+  if (ply_find(ply, "vertex", "alpha")) {
+    ply_vertex_values(ply, {"red", "green", "blue", "alpha"}, shape.colors);
+  } else {
+    std::vector<float> rgb;
+    ply_vertex_values(ply, {"red", "green", "blue"}, rgb);
+    shape.colors.resize(rgb.size() / 3 * 4);
+    for (size_t i = 0; i < rgb.size() / 3; i++)
+      shape.colors[4 * i] = rgb[3 * i], shape.colors[4 * i + 1] = rgb[3 * i + 1], shape.colors[4 * i + 2] = rgb[3 * i + 2],
+                     shape.colors[4 * i + 3] = 1;
+  }
+  if (auto r = ply_find(ply, "vertex", "radius"); r && !r->is_list) {
+    shape.radius.resize(r->values.size());
+    for (size_t i = 0; i < r->values.size(); i++) shape.radius[i] = (float)r->values[i];
+  }
+  // faces: quads as soon as one face has four corners, else triangles (get_faces, yocto_modelio.h:700-708);
+  // polygons become fans, short faces are padded with -1 exactly like get_triangles / get_quads (:618-688)
+  if (auto f = ply_find(ply, "face", "vertex_indices"); f && f->is_list) {
+    bool has_quads = false;
+    for (auto n : f->sizes) has_quads |= n == 4;
+    auto   at      = [&](size_t i) { return (int32_t)f->values[i]; };
+    size_t current = 0;
+    for (auto n : f->sizes) {
+      if (has_quads) {
+        auto& q = shape.quads;
+        if (n == 0) q.insert(q.end(), {-1, -1, -1, -1});
+        else if (n == 1) q.insert(q.end(), {at(current), -1, -1, -1});
+        else if (n == 2) q.insert(q.end(), {at(current), at(current + 1), -1, -1});
+        else if (n == 3) q.insert(q.end(), {at(current), at(current + 1), at(current + 2), at(current + 2)});
+        else if (n == 4) q.insert(q.end(), {at(current), at(current + 1), at(current + 2), at(current + 3)});
+        else
+          for (size_t item = 2; item < n; item++)
+            q.insert(q.end(), {at(current), at(current + item - 1), at(current + item), at(current + item)});
+      } else {
+        auto& t = shape.triangles;
+        if (n == 0) t.insert(t.end(), {-1, -1, -1});
+        else if (n == 1) t.insert(t.end(), {at(current), -1, -1});
+        else if (n == 2) t.insert(t.end(), {at(current), at(current + 1), -1});
+        else if (n == 3) t.insert(t.end(), {at(current), at(current + 1), at(current + 2)});
+        else
+          for (size_t item = 2; item < n; item++) t.insert(t.end(), {at(current), at(current + item - 1), at(current + item)});
+      }
+      current += n;
+    }
+  }
+  if (auto l = ply_find(ply, "line", "vertex_indices"); l && l->is_list) {  // polylines -> segments, :710-737
+    auto   at      = [&](size_t i) { return (int32_t)l->values[i]; };
+    size_t current = 0;
+    for (auto n : l->sizes) {
+      auto& s = shape.lines;
+      if (n == 0) s.insert(s.end(), {-1, -1});
+      else if (n == 1) s.insert(s.end(), {at(current), -1});
+      else if (n == 2) s.insert(s.end(), {at(current), at(current + 1)});
+      else
+        for (size_t item = 1; item < n; item++) s.insert(s.end(), {at(current + item - 1), at(current + item)});
+      current += n;
+    }
+  }
+  if (auto pt = ply_find(ply, "point", "vertex_indices"); pt && pt->is_list) {  // get_list_values, :605-616
+    shape.points.resize(pt->values.size());
+    for (size_t i = 0; i < pt->values.size(); i++) shape.points[i] = (int32_t)pt->values[i];
+  }
+  if (shape.points.empty() && shape.lines.empty() && shape.triangles.empty() && shape.quads.empty())
+    return error = "empty shape " + filename, false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// textures
+// ---------------------------------------------------------------------------------------------------------------
+struct HostTexture {
+  int                  width = 0, height = 0, linear = 0, nearest = 0, clamp = 0;
+  std::vector<float>   pixelsf;  // rgba
+  std::vector<uint8_t> pixelsb;  // rgba
+};
+
+// Radiance .hdr -> float rgba, the conversion rule of stb_image's stbi__hdr_load / stbi__hdr_convert (what the
+// reference calls): value = mantissa * 2^(exponent - 136), alpha 1, a zero exponent gives black.
+bool load_hdr(const std::vector<uint8_t>& data, HostTexture& tex) {
+  const uint8_t* p   = data.data();
+  const uint8_t* end = p + data.size();
+  auto           token = [&](std::string& line) {
+    line.clear();
+    while (p < end && *p != '\n') line += (char)*p++;
+    if (p < end) p++;
+  };
+  std::string line;
+  token(line);
+  if (line != "#?RADIANCE" && line != "#?RGBE") return false;
+  bool valid = false;
+  while (true) {
+    token(line);
+    if (line.empty()) break;
+    if (line == "FORMAT=32-bit_rle_rgbe") valid = true;
+    if (p >= end) return false;
+  }
+  if (!valid) return false;
+  token(line);
+  int w = 0, h = 0;
+  if (sscanf(line.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) return false;
+  tex.width = w, tex.height = h;
+  tex.pixelsf.assign((size_t)w * h * 4, 0.0f);
+  auto convert = [](float* out, const uint8_t* rgbe) {
+    if (rgbe[3] != 0) {
+      float f1 = (float)ldexp(1.0f, rgbe[3] - (int)(128 + 8));
+      out[0] = rgbe[0] * f1, out[1] = rgbe[1] * f1, out[2] = rgbe[2] * f1;
+    } else {
+      out[0] = out[1] = out[2] = 0;
+    }
+    out[3] = 1;
+  };
+  if (w < 8 || w >= 32768) {  // flat data
+    if (end - p < (ptrdiff_t)w * h * 4) return false;
+    for (size_t i = 0; i < (size_t)w * h; i++) convert(&tex.pixelsf[4 * i], p + 4 * i);
+    return true;
+  }
+  std::vector<uint8_t> scanline((size_t)w * 4);
+  for (int j = 0; j < h; j++) {
+    if (end - p < 4) return false;
+    int c1 = p[0], c2 = p[1], len = p[2];
+    if (c1 != 2 || c2 != 2 || (len & 0x80)) {
+      // not run-length encoded: the rest of the file is flat (stb switches mode for the whole image at row 0)
+      if (j != 0) return false;
+      if (end - p < (ptrdiff_t)w * h * 4) return false;
+      for (size_t i = 0; i < (size_t)w * h; i++) convert(&tex.pixelsf[4 * i], p + 4 * i);
+      return true;
+    }
+    len = (len << 8) | p[3];
+    if (len != w) return false;
+    p += 4;
+    for (int k = 0; k < 4; k++) {
+      int i = 0;
+      while (i < w) {
+        if (p >= end) return false;
+        int count = *p++;
+        if (count > 128) {
+          count -= 128;
+          if (p >= end || i + count > w) return false;
+          const uint8_t value = *p++;
+          for (int z = 0; z < count; z++) scanline[(size_t)(i++) * 4 + k] = value;
+        } else {
+          if (count == 0 || end - p < count || i + count > w) return false;
+          for (int z = 0; z < count; z++) scanline[(size_t)(i++) * 4 + k] = *p++;
+        }
+      }
+    }
+    for (int i = 0; i < w; i++) convert(&tex.pixelsf[((size_t)j * w + i) * 4], &scanline[(size_t)i * 4]);
+  }
+  return true;
+}
+
+// PNG -> byte rgba as stbi_load(..., 4) returns it: 8- or 16-bit samples (16 -> high byte), grey / grey+alpha /
+// rgb / rgba / palette, tRNS transparency, non-interlaced.
+bool load_png(const std::vector<uint8_t>& data, HostTexture& tex) {
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  if (data.size() < 8 || memcmp(data.data(), sig, 8)) return false;
+  auto   be32 = [&](size_t o) { return (uint32_t)data[o] << 24 | (uint32_t)data[o + 1] << 16 | (uint32_t)data[o + 2] << 8 | data[o + 3]; };
+  size_t pos = 8;
+  int    w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+  std::vector<uint8_t> idat, palette, trns;
+  while (pos + 12 <= data.size()) {
+    const uint32_t len = be32(pos);
+    const char*    id  = (const char*)&data[pos + 4];
+    if (pos + 12 + (size_t)len > data.size()) return false;
+    const uint8_t* body = &data[pos + 8];
+    if (!memcmp(id, "IHDR", 4)) {
+      if (len < 13) return false;
+      w = (int)be32(pos + 8), h = (int)be32(pos + 12);
+      depth = body[8], ctype = body[9], interlace = body[12];
+    } else if (!memcmp(id, "PLTE", 4)) {
+      palette.assign(body, body + len);
+    } else if (!memcmp(id, "tRNS", 4)) {
+      trns.assign(body, body + len);
+    } else if (!memcmp(id, "IDAT", 4)) {
+      idat.insert(idat.end(), body, body + len);
+    } else if (!memcmp(id, "IEND", 4)) {
+      break;
+    }
+    pos += 12 + (size_t)len;
+  }
+  if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16)) return false;
+  const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+  if (!channels || (ctype == 3 && depth != 8)) return false;
+  const size_t bpp = (size_t)channels * depth / 8, stride = bpp * w;
+  std::vector<uint8_t> raw((stride + 1) * h);
+  uLongf rawlen = (uLongf)raw.size();
+  if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) return false;
+  // undo the scanline filters (PNG spec section 9)
+  std::vector<uint8_t> img(stride * h);
+  for (int j = 0; j < h; j++) {
+    const uint8_t  filter = raw[(stride + 1) * j];
+    const uint8_t* src    = &raw[(stride + 1) * j + 1];
+    uint8_t*       dst    = &img[stride * j];
+    const uint8_t* up     = j ? dst - stride : nullptr;
+    for (size_t i = 0; i < stride; i++) {
+      const int a = i >= bpp ? dst[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+      int       v = src[i];
+      switch (filter) {
+        case 0: break;
+        case 1: v += a; break;
+        case 2: v += b; break;
+        case 3: v += (a + b) >> 1; break;
+        case 4: {
+          const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+          v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+        } break;
+        default: return false;
+      }
+      dst[i] = (uint8_t)v;
+    }
+  }
+  tex.width = w, tex.height = h;
+  tex.pixelsb.resize((size_t)w * h * 4);
+  const size_t step = depth / 8;  // 16-bit samples are big-endian: the first byte is the high byte stb keeps
+  for (size_t i = 0; i < (size_t)w * h; i++) {
+    const uint8_t* s = &img[i * bpp];
+    uint8_t*       d = &tex.pixelsb[4 * i];
+    switch (ctype) {
+      case 0: {
+        d[0] = d[1] = d[2] = s[0], d[3] = 255;
+        if (trns.size() >= 2 && ((depth == 16) ? (s[0] == trns[0] && s[1] == trns[1]) : s[0] == trns[1])) d[3] = 0;
+      } break;
+      case 2: {
+        d[0] = s[0], d[1] = s[step], d[2] = s[2 * step], d[3] = 255;
+        if (trns.size() >= 6) {
+          bool key = true;
+          for (int k = 0; k < 3; k++)
+            key = key && (depth == 16 ? (s[2 * k] == trns[2 * k] && s[2 * k + 1] == trns[2 * k + 1]) : s[k] == trns[2 * k + 1]);
+          if (key) d[3] = 0;
+        }
+      } break;
+      case 3: {
+        const size_t k = s[0];
+        if (3 * k + 2 >= palette.size()) return false;
+        d[0] = palette[3 * k], d[1] = palette[3 * k + 1], d[2] = palette[3 * k + 2];
+        d[3] = k < trns.size() ? trns[k] : 255;
+      } break;
+      case 4: d[0] = d[1] = d[2] = s[0], d[3] = s[step]; break;
+      case 6: d[0] = s[0], d[1] = s[step], d[2] = s[2 * step], d[3] = s[3 * step]; break;
+    }
+  }
+  return true;
+}
+
+// load_texture, yocto_sceneio.cpp:1796-1837: the file type decides `linear`; nearest / clamp come from the JSON
+bool load_texture(const std::string& filename, HostTexture& tex, std::string& error) {
+  const auto ext = path_extension(filename);
+  if (ext != ".hdr" && ext != ".png") return error = "unsupported format " + filename, false;
+  std::vector<uint8_t> data;
+  if (!read_file(filename, data, error)) return false;
+  if (ext == ".hdr") {
+    if (!load_hdr(data, tex)) return error = "cannot raed " + filename, false;  // (the reference's own spelling)
+    tex.linear = 1;
+  } else {
+    if (!load_png(data, tex)) return error = "cannot raed " + filename, false;
+    tex.linear = 0;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the loaded scene
+// ---------------------------------------------------------------------------------------------------------------
+int material_type_from_name(const std::string& name) {
+  static const char* names[] = {"matte", "glossy", "reflective", "transparent", "refractive", "subsurface", "volumetric", "gltfpbr"};
+  for (int i = 0; i < 8; i++)
+    if (name == names[i]) return i;
+  return 0;  // NLOHMANN_JSON_SERIALIZE_ENUM maps an unknown label to the first entry
+}
+
+const float kIdentityFrame[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+
+// load resources on the host cores; the first error (lowest index) wins, like the reference's parallel_for
+bool parallel_load(size_t n, std::string& error, const std::function<bool(size_t, std::string&)>& fn) {
+  std::vector<std::string> errors(n);
+  std::vector<char>        failed(n, 0);
+  std::atomic<size_t>      next{0};
+  const unsigned           nthreads = std::max(1u, std::min((unsigned)n, std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nthreads; t++)
+    pool.emplace_back([&]() {
+      for (size_t i = next++; i < n; i = next++)
+        if (!fn(i, errors[i])) failed[i] = 1;
+    });
+  for (auto& t : pool) t.join();
+  for (size_t i = 0; i < n; i++)
+    if (failed[i]) return error = errors[i], false;
+  return true;
+}
+
+}  // namespace
+
+struct ygl_loaded_scene {
+  std::vector<ygl_camera>      cameras;
+  std::vector<ygl_instance>    instances;
+  std::vector<ygl_environment> environments;
+  std::vector<ygl_material>    materials;
+  std::vector<HostShape>       shape_data;
+  std::vector<HostTexture>     texture_data;
+  std::vector<ygl_shape>       shapes;
+  std::vector<ygl_texture>     textures;
+  std::vector<std::string>     names[6];  // camera, texture, material, shape, instance, environment
+  std::string                  copyright;
+  ygl_scene_desc               desc = {};
+};
+
+namespace {
+
+bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::string& error) {
+  std::vector<uint8_t> text;
+  if (!read_file(filename, text, error)) return false;
+  text.push_back(0);
+  JValue  json;
+  JParser parser{(const char*)text.data(), (const char*)text.data() + text.size() - 1};
+  auto    parse_error = [&]() { return error = "cannot parse " + filename, false; };
+  if (!parser.parse(json) || json.type != JValue::Object) return parse_error();
+  parser.skip();
+  if (parser.p != parser.end) return parse_error();
+
+  JReader rd;
+  std::string version;
+  if (auto asset = json.find("asset")) {
+    rd.get(*asset, "copyright", scene.copyright);
+    rd.get(*asset, "version", version);
+  }
+  if (version != "4.2" && version != "5.0") {
+    error = "cannot parse " + filename + ": only scene format 4.2 / 5.0 is supported (found '" + version + "')";
+    return false;
+  }
+  std::vector<std::string> shape_files, texture_files;
+  auto frame_of = [](ygl_frame3f& f) { return (float*)&f; };
+  static_assert(sizeof(ygl_frame3f) == 48, "frame layout");
+  if (auto group = json.find("cameras")) {
+    for (auto& e : group->array) {
+      ygl_camera camera = {};
+      memcpy(&camera.frame, kIdentityFrame, 48);
+      camera.orthographic = 0, camera.lens = 0.050f, camera.film = 0.036f, camera.aspect = 1.500f, camera.focus = 10000,
+      camera.aperture = 0;
+      std::string name;
+      rd.get(e, "name", name);
+      rd.get_floats(e, "frame", frame_of(camera.frame), 12);
+      rd.get_bool(e, "orthographic", camera.orthographic);
+      rd.get(e, "lens", camera.lens);
+      rd.get(e, "aspect", camera.aspect);
+      rd.get(e, "film", camera.film);
+      rd.get(e, "focus", camera.focus);
+      rd.get(e, "aperture", camera.aperture);
+      if (e.find("lookat")) {
+        float m[9] = {};
+        rd.get_floats(e, "lookat", m, 9);
+        v3 eye = {m[0], m[1], m[2]}, center = {m[3], m[4], m[5]}, up = {m[6], m[7], m[8]};
+        camera.focus = length(eye - center);
+        lookat_frame(frame_of(camera.frame), eye, center, up, false);
+      }
+      scene.cameras.push_back(camera);
+      scene.names[0].push_back(name);
+    }
+  }
+  if (auto group = json.find("textures")) {
+    for (auto& e : group->array) {
+      HostTexture tex;
+      std::string name, uri;
+      rd.get(e, "name", name);
+      rd.get(e, "uri", uri);
+      rd.get_bool(e, "linear", tex.linear);
+      rd.get_bool(e, "nearest", tex.nearest);
+      rd.get_bool(e, "clamp", tex.clamp);
+      scene.texture_data.push_back(std::move(tex));
+      scene.names[1].push_back(name);
+      texture_files.push_back(uri);
+    }
+  }
+  if (auto group = json.find("materials")) {
+    for (auto& e : group->array) {
+      ygl_material m = {};
+      m.type = 0, m.roughness = 0, m.metallic = 0, m.ior = 1.5f, m.scanisotropy = 0, m.trdepth = 0.01f, m.opacity = 1;
+      m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
+      std::string name, type;
+      rd.get(e, "name", name);
+      if (e.find("type")) {
+        rd.get(e, "type", type);
+        m.type = material_type_from_name(type);
+      }
+      rd.get_floats(e, "emission", m.emission, 3);
+      rd.get_floats(e, "color", m.color, 3);
+      rd.get(e, "metallic", m.metallic);
+      rd.get(e, "roughness", m.roughness);
+      rd.get(e, "ior", m.ior);
+      rd.get(e, "trdepth", m.trdepth);
+      rd.get_floats(e, "scattering", m.scattering, 3);
+      rd.get(e, "scanisotropy", m.scanisotropy);
+      rd.get(e, "opacity", m.opacity);
+      rd.get(e, "emission_tex", m.emission_tex);
+      rd.get(e, "color_tex", m.color_tex);
+      rd.get(e, "roughness_tex", m.roughness_tex);
+      rd.get(e, "scattering_tex", m.scattering_tex);
+      rd.get(e, "normal_tex", m.normal_tex);
+      scene.materials.push_back(m);
+      scene.names[2].push_back(name);
+    }
+  }
+  if (auto group = json.find("shapes")) {
+    for (auto& e : group->array) {
+      std::string name, uri;
+      rd.get(e, "name", name);
+      rd.get(e, "uri", uri);
+      scene.names[3].push_back(name);
+      shape_files.push_back(uri);
+    }
+  }
+  if (auto group = json.find("subdivs"); group && !group->array.empty()) {
+    error = "cannot load " + filename + ": subdivs (tesselate_subdivs) are not supported";
+    return false;
+  }
+  if (auto group = json.find("instances")) {
+    for (auto& e : group->array) {
+      ygl_instance inst = {};
+      memcpy(&inst.frame, kIdentityFrame, 48);
+      inst.shape = inst.material = -1;
+      std::string name;
+      rd.get(e, "name", name);
+      rd.get_floats(e, "frame", frame_of(inst.frame), 12);
+      rd.get(e, "shape", inst.shape);
+      rd.get(e, "material", inst.material);
+      if (e.find("lookat")) {
+        float m[9] = {};
+        rd.get_floats(e, "lookat", m, 9);
+        lookat_frame(frame_of(inst.frame), {m[0], m[1], m[2]}, {m[3], m[4], m[5]}, {m[6], m[7], m[8]}, true);
+      }
+      scene.instances.push_back(inst);
+      scene.names[4].push_back(name);
+    }
+  }
+  if (auto group = json.find("environments")) {
+    for (auto& e : group->array) {
+      ygl_environment env = {};
+      memcpy(&env.frame, kIdentityFrame, 48);
+      env.emission_tex = -1;
+      std::string name;
+      rd.get(e, "name", name);
+      rd.get_floats(e, "frame", frame_of(env.frame), 12);
+      rd.get_floats(e, "emission", env.emission, 3);
+      rd.get(e, "emission_tex", env.emission_tex);
+      if (e.find("lookat")) {
+        float m[9] = {};
+        rd.get_floats(e, "lookat", m, 9);
+        lookat_frame(frame_of(env.frame), {m[0], m[1], m[2]}, {m[3], m[4], m[5]}, {m[6], m[7], m[8]}, true);
+      }
+      scene.environments.push_back(env);
+      scene.names[5].push_back(name);
+    }
+  }
+  if (!rd.ok) return parse_error();
+
+  // resources, in parallel like the reference
+  const auto dirname = path_dirname(filename);
+  scene.shape_data.resize(shape_files.size());
+  auto dependent_error = [&]() { return error = "cannot load " + filename + " since " + error, false; };
+  if (!parallel_load(shape_files.size(), error,
+          [&](size_t i, std::string& err) { return load_shape(path_join(dirname, shape_files[i]), scene.shape_data[i], err); }))
+    return dependent_error();
+  if (!parallel_load(texture_files.size(), error, [&](size_t i, std::string& err) {
+        return load_texture(path_join(dirname, texture_files[i]), scene.texture_data[i], err);
+      }))
+    return dependent_error();
+
+  // fix-ups: add_missing_camera (yocto_sceneio.cpp:2119-2139), add_missing_radius (:2142-2148)
+  if (scene.cameras.empty()) {
+    struct box {
+      v3 min = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, max = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    };
+    auto fmin = [](float a, float b) { return (a < b) ? a : b; };
+    auto fmax = [](float a, float b) { return (a > b) ? a : b; };
+    auto grow = [&](box& b, const v3& p) {
+      b.min = {fmin(b.min.x, p.x), fmin(b.min.y, p.y), fmin(b.min.z, p.z)};
+      b.max = {fmax(b.max.x, p.x), fmax(b.max.y, p.y), fmax(b.max.z, p.z)};
+    };
+    std::vector<box> shape_box(scene.shape_data.size());
+    for (size_t s = 0; s < scene.shape_data.size(); s++) {
+      auto& pos = scene.shape_data[s].positions;
+      for (size_t i = 0; i + 2 < pos.size(); i += 3) grow(shape_box[s], {pos[i], pos[i + 1], pos[i + 2]});
+    }
+    box bbox;
+    for (auto& inst : scene.instances) {
+      if (inst.shape < 0 || inst.shape >= (int)shape_box.size()) continue;
+      const box& sb = shape_box[inst.shape];
+      const float* f = (const float*)&inst.frame;
+      v3 fx = {f[0], f[1], f[2]}, fy = {f[3], f[4], f[5]}, fz = {f[6], f[7], f[8]}, fo = {f[9], f[10], f[11]};
+      v3 corners[8] = {{sb.min.x, sb.min.y, sb.min.z}, {sb.min.x, sb.min.y, sb.max.z}, {sb.min.x, sb.max.y, sb.min.z},
+          {sb.min.x, sb.max.y, sb.max.z}, {sb.max.x, sb.min.y, sb.min.z}, {sb.max.x, sb.min.y, sb.max.z},
+          {sb.max.x, sb.max.y, sb.min.z}, {sb.max.x, sb.max.y, sb.max.z}};
+      box xf;
+      for (auto& c : corners) grow(xf, fx * c.x + fy * c.y + fz * c.z + fo);  // transform_point, yocto_math.h
+      grow(bbox, xf.min), grow(bbox, xf.max);
+    }
+    ygl_camera camera = {};
+    camera.orthographic = 0, camera.film = 0.036f, camera.aspect = (float)16 / (float)9, camera.aperture = 0, camera.lens = 0.050f;
+    auto center      = (bbox.max + bbox.min) / 2;
+    auto bbox_radius = length(bbox.max - bbox.min) / 2;
+    auto camera_dist = bbox_radius * camera.lens / (camera.film / camera.aspect);
+    camera_dist *= 2.0f;
+    v3 from = v3{0, 0, 1} * camera_dist + center, to = center;
+    lookat_frame((float*)&camera.frame, from, to, {0, 1, 0}, false);
+    camera.focus = length(from - to);
+    scene.cameras.push_back(camera);
+    scene.names[0].push_back("camera");
+  }
+  for (auto& shape : scene.shape_data) {
+    if (shape.points.empty() && shape.lines.empty()) continue;
+    if (!shape.radius.empty()) continue;
+    shape.radius.assign(shape.positions.size() / 3, 0.001f);
+  }
+  return true;
+}
+
+void make_desc(ygl_loaded_scene& scene) {
+  scene.shapes.clear(), scene.textures.clear();
+  for (auto& s : scene.shape_data) {
+    ygl_shape v     = {};
+    v.num_points    = (int)s.points.size();
+    v.num_lines     = (int)s.lines.size() / 2;
+    v.num_triangles = (int)s.triangles.size() / 3;
+    v.num_quads     = (int)s.quads.size() / 4;
+    v.points = s.points.data(), v.lines = s.lines.data(), v.triangles = s.triangles.data(), v.quads = s.quads.data();
+    v.num_positions = (int)s.positions.size() / 3, v.num_normals = (int)s.normals.size() / 3;
+    v.num_texcoords = (int)s.texcoords.size() / 2, v.num_colors = (int)s.colors.size() / 4;
+    v.num_radius    = (int)s.radius.size();
+    v.positions = s.positions.data(), v.normals = s.normals.data(), v.texcoords = s.texcoords.data();
+    v.colors = s.colors.data(), v.radius = s.radius.data();
+    scene.shapes.push_back(v);
+  }
+  for (auto& t : scene.texture_data) {
+    ygl_texture v = {};
+    v.width = t.width, v.height = t.height, v.linear = t.linear, v.nearest = t.nearest, v.clamp = t.clamp;
+    v.pixelsf = t.pixelsf.empty() ? nullptr : t.pixelsf.data();
+    v.pixelsb = t.pixelsb.empty() ? nullptr : t.pixelsb.data();
+    scene.textures.push_back(v);
+  }
+  auto& d = scene.desc;
+  d                  = {};
+  d.num_cameras      = (int)scene.cameras.size();
+  d.num_instances    = (int)scene.instances.size();
+  d.num_environments = (int)scene.environments.size();
+  d.num_shapes       = (int)scene.shapes.size();
+  d.num_textures     = (int)scene.textures.size();
+  d.num_materials    = (int)scene.materials.size();
+  d.cameras = scene.cameras.data(), d.instances = scene.instances.data(), d.environments = scene.environments.data();
+  d.shapes = scene.shapes.data(), d.textures = scene.textures.data(), d.materials = scene.materials.data();
+}
+
+}  // namespace
+
+extern "C" void ygl_internal_set_error(const char* message);
+
+extern "C" {
+
+int ygl_scene_load(const char* filename, ygl_loaded_scene** out) {
+  if (!filename || !out) return ygl_internal_set_error("null argument"), YGL_ERR_INVALID;
+  auto        scene = std::make_unique<ygl_loaded_scene>();
+  std::string error;
+  if (!load_json_scene(filename, *scene, error)) return ygl_internal_set_error(error.c_str()), YGL_ERR_RUNTIME;
+  make_desc(*scene);
+  *out = scene.release();
+  return YGL_OK;
+}
+const ygl_scene_desc* ygl_loaded_scene_desc(const ygl_loaded_scene* scene) { return scene ? &scene->desc : nullptr; }
+const char* ygl_loaded_scene_name(const ygl_loaded_scene* scene, int kind, int index) {
+  if (!scene || kind < 0 || kind >= 6 || index < 0 || index >= (int)scene->names[kind].size()) return nullptr;
+  return scene->names[kind][index].c_str();
+}
+void ygl_loaded_scene_destroy(ygl_loaded_scene* scene) { delete scene; }
+
+}  // extern "C"

@@ -475,7 +475,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       cur = kWorkUntested | (first + neg);
       return;
     }
-    const float4* pair = nodes + 4 * (size_t)first;
+    const float4* pair = nodes + 2 * (size_t)first;  // node i = float4s 2i, 2i+1: the pair is 64 contiguous bytes
     float4 a0 = __ldg(pair), a1 = __ldg(pair + 1), b0 = __ldg(pair + 2), b1 = __ldg(pair + 3);
     if (COUNT) {
       if (bottom) cnt.bot_nodes += 2;

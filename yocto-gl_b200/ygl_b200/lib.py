@@ -26,6 +26,7 @@ EXPORTS = [
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
     "ygl_trace_counters", "ygl_context_set_profiling", "ygl_context_set_mode", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
+    "ygl_scene_load", "ygl_loaded_scene_desc", "ygl_loaded_scene_name", "ygl_loaded_scene_destroy",
     "ygl_trace_start", "ygl_trace_cancel", "ygl_trace_wait", "ygl_trace_done", "ygl_trace_preview",
     "ygl_context_set_option", "ygl_context_get_option", "ygl_state_reset", "ygl_trace_sample", "ygl_bvh_create_from_host",
 ]
@@ -80,6 +81,12 @@ def load():
     lib.ygl_context_set_profiling.argtypes = [vp, i32, i32]
     lib.ygl_context_set_mode.argtypes = [vp, i32]
     lib.ygl_trace_timings.argtypes = [vp, vp]
+    lib.ygl_scene_load.argtypes = [C.c_char_p, P(vp)]
+    lib.ygl_loaded_scene_desc.argtypes = [vp]
+    lib.ygl_loaded_scene_desc.restype = P(abi.SceneDesc)
+    lib.ygl_loaded_scene_name.argtypes = [vp, i32, i32]
+    lib.ygl_loaded_scene_name.restype = C.c_char_p
+    lib.ygl_loaded_scene_destroy.argtypes = [vp]
     lib.ygl_trace_start.argtypes = [vp, vp, vp, vp, vp, P(abi.TraceParams)]
     lib.ygl_trace_cancel.argtypes = [vp]
     lib.ygl_trace_wait.argtypes = [vp]
@@ -111,6 +118,24 @@ def _check(rc):
 
 def _p(a):
     return a.ctypes.data if a is not None else None
+
+
+def load_scene(filename):
+    """load_scene (yocto_sceneio.h:93) for JSON v4.2 + PLY + PNG/HDR scenes -> abi.Scene (arrays copied out of the
+    library's loaded-scene object), with `camera_names` etc. attached."""
+    lib = load()
+    h = C.c_void_p()
+    _check(lib.ygl_scene_load(str(filename).encode(), C.byref(h)))
+    try:
+        scene = abi.Scene.from_desc(lib.ygl_loaded_scene_desc(h).contents)
+        kinds = ("camera", "texture", "material", "shape", "instance", "environment")
+        counts = (len(scene.cameras), len(scene.textures), len(scene.materials), len(scene.shapes),
+                  len(scene.instances), len(scene.environments))
+        for k, (kind, n) in enumerate(zip(kinds, counts)):
+            setattr(scene, kind + "_names", [(lib.ygl_loaded_scene_name(h, k, i) or b"").decode() for i in range(n)])
+    finally:
+        lib.ygl_loaded_scene_destroy(h)
+    return scene
 
 
 class Bvh:

@@ -325,6 +325,73 @@ def camera_rays(scene, params, n, seed=5):
     return rays
 
 
+def _write_scene(tmpdir, name, doc, pool_dir):
+    """Writes <tmpdir>/<name>/<name>.json next to shapes/ and textures/ links into a pool of reference test assets and
+    loads it through the library's own loader (ygl_scene_load)."""
+    import json
+    from . import lib
+    d = os.path.join(str(tmpdir), name)
+    os.makedirs(d, exist_ok=True)
+    for kind in ("shapes", "textures"):
+        link = os.path.join(d, kind)
+        if not os.path.lexists(link):
+            os.symlink(os.path.join(pool_dir, kind), link)
+    path = os.path.join(d, name + ".json")
+    with open(path, "w") as f:
+        json.dump(doc, f)
+    return lib.load_scene(path)
+
+
+def _frame(f):
+    return [float(x) for x in np.asarray(f, np.float32).reshape(-1)]
+
+
+def bunny_file_scene(tmpdir, pool_dir):
+    """C2 with the asset BASELINE.json names: the Stanford bunny of the reference's test data (bunny.ply, 144,046
+    triangles) + floor, glossy, lit by the reference's sky.hdr environment texture; 16:9 camera."""
+    doc = {
+        "asset": {"version": "4.2"},
+        "cameras": [{"name": "default", "frame": _frame(lookat_frame((0.0, 0.12, 0.38), (0, 0.07, 0))), "lens": 0.05,
+                     "film": 0.036, "aspect": 16 / 9, "focus": 0.4}],
+        "textures": [{"name": "sky", "uri": "textures/sky.hdr"}, {"name": "floor", "uri": "textures/floor.png"}],
+        "materials": [{"name": "floor", "color": [0.7, 0.7, 0.7], "color_tex": 1},
+                      {"name": "bunny", "type": "glossy", "color": [0.8, 0.5, 0.3], "roughness": 0.25}],
+        "shapes": [{"name": "floor", "uri": "shapes/floor.ply"}, {"name": "bunny", "uri": "shapes/bunny.ply"}],
+        "instances": [{"name": "floor", "shape": 0, "material": 0}, {"name": "bunny", "shape": 1, "material": 1}],
+        "environments": [{"name": "sky", "emission": [0.5, 0.5, 0.5], "emission_tex": 0}],
+    }
+    return _write_scene(tmpdir, "c2_bunny", doc, pool_dir)
+
+
+def hairball_file_scene(tmpdir, pool_dir):
+    """C5 with the reference's assets: two instances of hairball1.ply (2 x 262,144 line segments), two bunnies
+    (2 x 144,046 triangles, subsurface and rough refractive), a glossy sphere, floor, area light, sky."""
+    doc = {
+        "asset": {"version": "4.2"},
+        "cameras": [{"name": "default", "frame": _frame(lookat_frame((0.0, 0.2, 0.95), (0, 0.07, 0))), "lens": 0.05,
+                     "film": 0.036, "aspect": 16 / 9, "focus": 0.96}],
+        "textures": [{"name": "sky", "uri": "textures/sky.hdr"}],
+        "materials": [{"name": "floor", "color": [0.55, 0.55, 0.55]},
+                      {"name": "hair", "type": "glossy", "color": [0.35, 0.2, 0.1], "roughness": 0.3},
+                      {"name": "skin", "type": "subsurface", "color": [0.8, 0.55, 0.45], "roughness": 0.3,
+                       "scattering": [0.5, 0.3, 0.25], "trdepth": 0.05, "ior": 1.4},
+                      {"name": "glass", "type": "refractive", "color": [0.85, 0.95, 0.9], "roughness": 0.1, "trdepth": 0.5},
+                      {"name": "ball", "type": "glossy", "color": [0.25, 0.3, 0.7], "roughness": 0.15},
+                      {"name": "light", "emission": [25, 25, 25]}],
+        "shapes": [{"uri": "shapes/floor.ply"}, {"uri": "shapes/hairball1.ply"}, {"uri": "shapes/bunny.ply"},
+                   {"uri": "shapes/sphere.ply"}, {"uri": "shapes/arealight1.ply"}],
+        "instances": [{"shape": 0, "material": 0},
+                      {"shape": 1, "material": 1, "frame": _frame(translation((-0.09, 0.0, 0.0)))},
+                      {"shape": 1, "material": 1, "frame": _frame(np.vstack([rotation((0, 1, 0), 1.3)[:3], [[0.09, 0.0, 0.02]]]))},
+                      {"shape": 2, "material": 2, "frame": _frame(translation((-0.24, 0.0, 0.12)))},
+                      {"shape": 2, "material": 3, "frame": _frame(translation((0.25, 0.0, 0.1)))},
+                      {"shape": 3, "material": 4, "frame": _frame(np.vstack([np.eye(3) * 0.45, [[0.0, 0.0, 0.22]]]))},
+                      {"shape": 4, "material": 5}],
+        "environments": [{"emission": [0.4, 0.45, 0.55], "emission_tex": 0}],
+    }
+    return _write_scene(tmpdir, "c5_hairball", doc, pool_dir)
+
+
 def features(seed=3):
     """Small scene that touches every code path: triangles, quads, lines, points; all 8 material
     types incl. delta / rough variants, opacity, vertex colors, color/roughness/normal/emission
