@@ -229,6 +229,10 @@ void ygl_loaded_scene_destroy(ygl_loaded_scene* scene);
 /* ---- bvh: make_trace_bvh / make_scene_bvh (host build in the reference's node order) ---- */
 /* Pure host work; the device copy is made on first use with a context. */
 int  ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out);
+/* The same trees, bit for bit, with the large ones (>= 4096 primitives, default split) built on the context's device:
+ * level-parallel split_middle that reproduces the reference's node indices and std::partition's permutation
+ * (ygl_bvh_device.cu). highquality (SAH) trees and small trees are built on the host cores. ygl_trace_image uses it. */
+int  ygl_bvh_build_device(ygl_context* ctx, const ygl_scene_desc* desc, int highquality, ygl_bvh** out);
 /* Number of nodes / primitives of tree `shape` (>=0) or of the instance tree (shape == -1). */
 int  ygl_bvh_tree_size(const ygl_bvh* bvh, int shape, int* num_nodes, int* num_primitives);
 /* Copies the tree out (reference bvh_tree layout) — used by the parity tests. */

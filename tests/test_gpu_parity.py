@@ -419,6 +419,65 @@ def test_baseline_assets_full_size_bit_exact(ctx, ref, which, tmp_path):
     np.testing.assert_array_equal(got["rngs"], want["rngs"])
 
 
+def _stress_soup(n=60000, seed=21):
+    """Triangles built to hit the corners of make_bvh: thousands of coincident centroids (csize == 0 fallback), long
+    runs of equal coordinates (predicate splits nothing -> midpoint fallback), signed zeros, a few huge triangles."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, size=(n, 3))
+    c[: n // 6] = c[0]                                # identical centroids
+    c[n // 6: n // 3, 0] = 0.25                       # a plane of equal x
+    c[n // 3: n // 2] = np.round(c[n // 3: n // 2] * 4) / 4  # a coarse lattice: many ties
+    c[n // 2: n // 2 + 500] *= 0.0                    # zeros ...
+    c[n // 2 + 250: n // 2 + 500] *= -1.0             # ... of both signs
+    size = rng.uniform(0.001, 0.02, size=(n, 1, 1))
+    size[:50] = 3.0
+    p = c[:, None, :] + rng.normal(size=(n, 3, 3)) * size
+    p[n // 2: n // 2 + 500] = np.where(rng.random((500, 3, 3)) < 0.5, 0.0, -0.0)  # degenerate, signed-zero boxes
+    sc = scenes.Scene()
+    sc.add_camera(scenes.lookat_frame((0, 0, 4), (0, 0, 0)), lens=0.05, film=0.036, aspect=1.0, focus=4.0, aperture=0.0)
+    m = sc.add_material(abi.MATTE, color=(0.7, 0.7, 0.7))
+    sc.add_instance(sc.add_shape(triangles=np.arange(3 * n, dtype=np.int32).reshape(-1, 3),
+                                 positions=p.reshape(-1, 3).astype(np.float32)), m)
+    return sc
+
+
+@pytest.mark.parametrize("name", ["c2", "c5", "soup", "instances", "chain"])
+def test_device_bvh_build_matches_host_build(ctx, name, tmp_path):
+    """ygl_bvh_build_device (level-parallel split_middle on the GPU, ygl_bvh_device.cu) against the host build - which
+    tests/test_host_parity.py pins to the reference's make_scene_bvh: every node (box bits, start, num, axis, internal)
+    at the same index and the same `primitives` permutation, for every tree of the scene."""
+    import time
+    if name == "soup":
+        scene = _stress_soup()
+    elif name == "instances":
+        scene = scenes.instanced_spheres(17)   # 4913 + 2 instances: the instance tree is built on the device too
+    elif name == "chain":
+        scene = scenes.sliver_chain(100)       # small: stays on the host (and must still be accepted)
+    elif scene_data.available() and name == "c2":
+        scene = scenes.bunny_file_scene(tmp_path, os.path.join(scene_data.DATA, "pool"))
+    elif scene_data.available() and name == "c5":
+        scene = scenes.hairball_file_scene(tmp_path, os.path.join(scene_data.DATA, "pool"))
+    else:
+        scene = full_scene(name)
+    t0 = time.time()
+    host = lib.Bvh(scene)
+    t1 = time.time()
+    dev = lib.Bvh(scene, device_ctx=ctx)
+    t2 = time.time()
+    dev2 = lib.Bvh(scene, device_ctx=ctx)
+    t3 = time.time()
+    print(f"bvh build {name}: host {1e3 * (t1 - t0):.1f} ms, device {1e3 * (t2 - t1):.1f} ms (first), {1e3 * (t3 - t2):.1f} ms")
+    for shape in range(-1, len(scene.shapes)):
+        hn, hp = host.tree(shape)
+        dn, dp = dev.tree(shape)
+        assert hp.tobytes() == dp.tobytes(), (name, shape, "primitives")
+        assert hn.tobytes() == dn.tobytes(), (name, shape, "nodes")
+    # and the trees render: rays through the device-built bvh equal rays through the host-built one
+    ds = lib.DeviceScene(ctx, scene, device_build=True)
+    rays = random_rays(scene, 100000)
+    assert compare_hits(lib.DeviceScene(ctx, scene).intersect(rays), ds.intersect(rays)) == 0
+
+
 COUNTER_KEYS = ("top_nodes", "bottom_nodes", "instance_visits", "triangle_tests", "quad_tests", "line_tests", "point_tests")
 
 

@@ -29,7 +29,7 @@ for STEP in "$@"; do
     san)
       timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
     ab2)
-      for CFG in "lib" "lib node_reps=2" "lib node_reps=4" "lib refill=12" "lib_ext6" "lib_ext6 node_reps=2"; do
+      for CFG in "lib" "lib bin=0" "lib fuse=1" "lib_pair"; do
         set -- $CFG; LIB=$1; shift
         [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
         echo "--- $LIB $*"

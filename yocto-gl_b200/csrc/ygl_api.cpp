@@ -168,6 +168,7 @@ struct ygl_state {
 };
 
 static std::atomic<uint64_t> g_epoch{1};
+constexpr int kShallowStackHost = 72;  // = kShallowStack of ygl_traverse.cuh (stack entries of the shallow extend kernel)
 
 extern "C" {
 
@@ -422,6 +423,18 @@ int ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
   *out       = bvh.release();
   return YGL_OK;
 }
+int ygl_bvh_build_device(ygl_context* ctx, const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
+  if (!ctx || !out) return fail(YGL_ERR_INVALID, "null argument");
+  if (int rc = check_desc(desc)) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  auto        bvh = std::make_unique<ygl_bvh>();
+  std::string error;
+  if (!build_scene_bvh(*desc, highquality != 0, bvh->host, error, (void*)ctx->stream, true))
+    return fail(YGL_ERR_INVALID, error);
+  bvh->epoch = g_epoch++;
+  *out       = bvh.release();
+  return YGL_OK;
+}
 int ygl_bvh_create_from_host(const ygl_scene_desc* desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
     const int32_t* top_primitives, int num_top_primitives, const ygl_bvh_node* const* shape_nodes,
     const int* shape_num_nodes, const int32_t* const* shape_primitives, const int* shape_num_primitives, ygl_bvh** out) {
@@ -559,7 +572,9 @@ static int lights_upload(const ygl_lights* lights, int device) {
 }
 
 // Assemble the DScene for a (scene, bvh, lights) triple; cached on the context.
-static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_lights* lights) {
+// any_lights: the caller does not read lights (batch intersection): whatever light table is bound may stay.
+static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_lights* lights,
+    bool any_lights = false) {
   if (!scene || !bvh) return fail(YGL_ERR_INVALID, "null scene or bvh");
   if (scene->device != ctx->device) return fail(YGL_ERR_INVALID, "scene lives on another device");
   if ((int)bvh->host.shapes.size() != scene->num_shapes ||
@@ -567,9 +582,9 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
     return fail(YGL_ERR_INVALID, "bvh was built for a different scene");
   // the cache key is the identity of the three OBJECTS (their epochs), not their addresses: a bvh or lights object
   // destroyed and re-created at the same heap address must not hit
-  if (ctx->bound_scene == scene && ctx->bound_bvh == bvh && ctx->bound_lights == lights &&
-      ctx->bound_epoch == scene->epoch && ctx->bound_bvh_epoch == bvh->epoch &&
-      ctx->bound_lights_epoch == (lights ? lights->epoch : 0))
+  if (ctx->bound_scene == scene && ctx->bound_bvh == bvh && ctx->bound_epoch == scene->epoch &&
+      ctx->bound_bvh_epoch == bvh->epoch &&
+      (any_lights || (ctx->bound_lights == lights && ctx->bound_lights_epoch == (lights ? lights->epoch : 0))))
     return YGL_OK;
   ctx->bound_scene = nullptr;  // a failure below must not leave a half-built binding cached
   if (int rc = bvh_upload(bvh, ctx->device)) return rc;
@@ -639,6 +654,9 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
   D.num_lights       = nlights;
   D.inst_class       = nullptr;  // set per run (binned shade queues: path sampler only)
   D.has_volumes      = scene->has_volumes ? 1 : 0;
+  int shape_depth = 0;
+  for (auto& tree : bvh->host.shapes) shape_depth = std::max(shape_depth, tree.max_stack);
+  D.deep_stack = bvh->host.top.max_stack + shape_depth + 4 > kShallowStackHost ? 1 : 0;
   ctx->bound_scene = scene, ctx->bound_bvh = bvh, ctx->bound_lights = lights, ctx->bound_epoch = scene->epoch;
   ctx->bound_bvh_epoch = bvh->epoch, ctx->bound_lights_epoch = lights ? lights->epoch : 0;
   return YGL_OK;
@@ -1380,7 +1398,7 @@ int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trac
   ygl_state*  state  = nullptr;
   int         rc     = YGL_OK;
   do {
-    if ((rc = ygl_bvh_build(desc, params->highqualitybvh, &bvh))) break;
+    if ((rc = ygl_bvh_build_device(ctx, desc, params->highqualitybvh, &bvh))) break;
     if ((rc = ygl_lights_create(desc, &lights))) break;
     if ((rc = ygl_scene_create(ctx, desc, &scene))) break;
     if ((rc = ygl_state_create(ctx, desc, params, &state))) break;
@@ -1410,8 +1428,7 @@ int ygl_intersect_rays_device(ygl_context* ctx, const ygl_scene* scene, const yg
     int64_t n, int instance, int find_any, void* d_out, void* d_counters) {
   if (!ctx) return fail(YGL_ERR_INVALID, "null context");
   CUDA_TRY(cudaSetDevice(ctx->device));
-  if (int rc = bind_scene(ctx, scene, bvh, ctx->bound_scene == scene && ctx->bound_bvh == bvh ? ctx->bound_lights : nullptr))
-    return rc;
+  if (int rc = bind_scene(ctx, scene, bvh, nullptr, /*any_lights=*/true)) return rc;
   if (instance >= scene->num_instances) return fail(YGL_ERR_INVALID, "instance id out of range");
   if (n <= 0) return YGL_OK;
   int       threads = 128;

@@ -372,15 +372,40 @@ bool measure_tree(HostTree& tree, int num_prims, const char* what, std::string& 
 
 }  // namespace
 
-bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error) {
+bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error, void* device_stream,
+    bool use_device) {
   const int nshapes = desc.num_shapes;
   out.shapes.resize(nshapes);
   out.shape_kind.assign(nshapes, 0);
   out.shape_nodes.resize(nshapes);
   out.shape_packets.resize(nshapes);
-  // one tree per shape: independent, built on all host cores (the reference does the same, yocto_bvh.cpp:376-378)
+  use_device = use_device && !highquality;
+  static_assert(sizeof(box3) == 24, "box3 is {min.xyz, max.xyz}");
+  auto element_count = [](const ygl_shape& s) {
+    return s.num_points > 0 ? s.num_points : s.num_lines > 0 ? s.num_lines : s.num_triangles > 0 ? s.num_triangles : s.num_quads;
+  };
+  // large trees first, one after the other, on the device; meanwhile nothing else runs, the small ones follow on the host
   std::vector<std::string> errors(nshapes);
+  std::vector<char>        done(nshapes, 0);
+  if (use_device) {
+    for (int si = 0; si < nshapes; si++) {
+      const ygl_shape& s = desc.shapes[si];
+      if (element_count(s) < kDeviceBuildMin) continue;
+      const int         kind = shape_bvh_kind(s);
+      std::vector<box3> bboxes;
+      if (!shape_bounds(s, si, kind, bboxes, error)) return false;
+      out.shape_kind[si] = kind;
+      HostTree& tree     = out.shapes[si];
+      if (!build_tree_device(device_stream, (const float*)bboxes.data(), (int)bboxes.size(), tree, error)) return false;
+      if (!tree_fits_node_words(tree, error)) return false;
+      out.shape_nodes[si]   = pack_nodes(tree);
+      out.shape_packets[si] = pack_leaves(s, kind, tree);
+      done[si]              = 1;
+    }
+  }
+  // one tree per shape: independent, built on all host cores (the reference does the same, yocto_bvh.cpp:376-378)
   parallel_shapes(nshapes, [&](int si) {
+    if (done[si]) return;
     const ygl_shape&  s    = desc.shapes[si];
     const int         kind = shape_bvh_kind(s);
     std::vector<box3> bboxes;
@@ -403,7 +428,11 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
 
   std::vector<box3> ibox;
   if (!instance_bounds(desc, out, ibox, error)) return false;
-  out.top = make_tree(ibox, highquality);
+  if (use_device && (int)ibox.size() >= kDeviceBuildMin) {
+    if (!build_tree_device(device_stream, (const float*)ibox.data(), (int)ibox.size(), out.top, error)) return false;
+  } else {
+    out.top = make_tree(ibox, highquality);
+  }
   if (out.top.max_stack > kMaxTreeDepth) return error = "instance BVH too deep for the traversal stack (128 entries)", false;
   if (!tree_fits_node_words(out.top, error)) return false;
   pack_top(desc, out);

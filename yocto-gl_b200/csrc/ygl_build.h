@@ -40,8 +40,14 @@ struct HostLight {
   std::vector<float> cdf;
 };
 
-// make_scene_bvh, yocto_bvh.cpp:364-396 (+ make_shape_bvh :321-362, make_bvh :238-302)
-bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error);
+// make_scene_bvh, yocto_bvh.cpp:364-396 (+ make_shape_bvh :321-362, make_bvh :238-302).
+// device_stream != null: trees over at least kDeviceBuildMin primitives are built on the current CUDA device
+// (ygl_bvh_device.cu; split_middle only - highquality trees stay on the host), the others on the host cores.
+constexpr int kDeviceBuildMin = 4096;
+bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out, std::string& error,
+    void* device_stream = nullptr, bool use_device = false);
+// one tree on the device, bit-identical to make_tree(bboxes, false) (boxes: n x {min.xyz, max.xyz})
+bool build_tree_device(void* stream, const float* boxes, int n, HostTree& tree, std::string& error);
 // the same device-ready data from trees built elsewhere (ygl_bvh_create_from_host): validated, then packed
 bool adopt_scene_bvh(const ygl_scene_desc& desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
     const int32_t* top_prims, int num_top_prims, const ygl_bvh_node* const* shape_nodes, const int* shape_num_nodes,

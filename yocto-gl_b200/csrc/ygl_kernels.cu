@@ -219,7 +219,7 @@ struct ExtendSource {
 #ifndef YGL_EXT_MINBLOCKS
 #define YGL_EXT_MINBLOCKS 7  // measured on B200 (C3): 4/5/6/7/8 blocks/SM -> 249/249/233/224/227 ms per 32 spp
 #endif
-template <bool COUNT, int TAIL>
+template <bool COUNT, int TAIL, bool DEEP>
 __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene, PathState st, Queues q, int parity,
     unsigned long long* trav, int refill_thr, int node_reps, int suspend_below, int lone_below, int lone_steps) {
   Counters*     c = q.counters;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene,
   ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, q, parity, scene.inst_class, scene.has_volumes, 0, refill_thr,
       node_reps, suspend_below, lone_below, lone_steps, 0, false};
   trav_counters tc = {};
-  trace_stream<COUNT, kStreamThreads, kSharedStack>(scene, src, tc);
+  trace_stream<COUNT, kStreamThreads, kSharedStack, DEEP>(scene, src, tc);
   {
     unsigned v = src.finished;
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFullWarp, v, off);
@@ -1363,7 +1363,11 @@ __global__ void __launch_bounds__(kPersistThreads, YGL_PERSIST_MINBLOCKS) k_pers
     trav_counters tc = {};
     while (true) {
       const unsigned before = src.taken;
-      trace_stream<false, kPersistThreads, 12>(scene, src, tc);
+      #ifdef YGL_PAIR_VISIT
+      trace_stream<false, kPersistThreads, 12, true>(scene, src, tc);
+#else
+      trace_stream<false, kPersistThreads, kSharedStack, true>(scene, src, tc);
+#endif
       if (__any_sync(kFullWarp, src.taken != before)) {
         backoff = 64;
         continue;
@@ -1484,7 +1488,7 @@ void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, 
 static int extend_blocks_per_sm() {
   static int per_sm = 0;
   if (!per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_extend<false, 0>), 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_extend<false, 0, false>), 128, 0);
     if (per_sm < 1) per_sm = 1;
   }
   return per_sm;
@@ -1508,7 +1512,12 @@ void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene
   const int  sb       = tune.suspend >= 0 ? tune.suspend : (big_tile ? kSuspendBelow : 0);
   const int  suspend  = sb > 0 ? (std::min(sb, 31) | std::max(1, tune.suspend_rounds) << 8) : 0;
   const int  lone     = tune.lone >= 0 ? tune.lone : (big_tile ? 0 : 12);
-  auto* kernel = lone > 0 ? (trav ? k_extend<true, 1> : k_extend<false, 1>) : (trav ? k_extend<true, 0> : k_extend<false, 0>);
+  // the variant with the full 128-level stack only for scenes whose trees need it (DScene::deep_stack)
+  auto* kernel = scene.deep_stack
+                     ? (lone > 0 ? (trav ? k_extend<true, 1, true> : k_extend<false, 1, true>)
+                                 : (trav ? k_extend<true, 0, true> : k_extend<false, 0, true>))
+                     : (lone > 0 ? (trav ? k_extend<true, 1, false> : k_extend<false, 1, false>)
+                                 : (trav ? k_extend<true, 0, false> : k_extend<false, 0, false>));
   kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, tune.refill, tune.node_reps, suspend, lone, tune.lone_steps);
 }
 

@@ -119,6 +119,7 @@ struct DScene {
   int           num_lights;
   // shading class of a hit on instance i = 1 + material type (ygl_kernels.cuh); null = shade queues are not binned
   const unsigned char* inst_class;
+  int                  deep_stack;   // the trees need more traversal stack than the shallow kernel variant carries
   int                  has_volumes;  // some material can start a participating medium (refractive / subsurface / volumetric)
 };
 

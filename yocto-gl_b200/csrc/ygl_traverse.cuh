@@ -324,70 +324,49 @@ YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f
   return res;
 }
 
-// ==========================================================================================================
-// Persistent closest-hit stream (intersect_scene_bvh with the default ray range tmin = ray_eps, tmax = flt_max):
-// a warp keeps refilling finished lanes from `src` (src.fetch hands out rays, src.commit_finished stores a
-// finished lane's hit). Must be called by full, converged warps.
-//
-// PAIR VISITS. The reference pops a node, tests its box, and pushes both children (yocto_bvh.cpp:485-503). The two
-// children of a node are adjacent in memory, so this walk tests BOTH child boxes when it expands a node (one
-// 64-byte fetch, no second dependent round trip for the sibling) and stacks the far child only if the ray hits it,
-// together with its entry distance t0. When the far child is popped later, `tmax` may have shrunk; the reference's
-// test at that moment is t0 <= fl(min(t1, tmax) * 1.00000024f). Rounding is monotone, so that equals
-// t0 <= fl(t1 * k) (known true: the child passed with a larger tmax) AND t0 <= fl(tmax * k) (one compare at pop).
-// Hence every node the reference would accept is expanded, every node it would reject is dropped, in the same
-// order: the sequence of primitive tests and tmax updates - and so every hit bit - is the reference's.
-// Rays with an infinite 1/d component (NaN-capable slabs) cannot use the split test; their children are stacked
-// untested and take the reference's pop-test-push route (kWorkUntested).
-// COUNT: a node counts when the reference would pop it: both children of every expanded node, and tree roots.
-// ==========================================================================================================
+#ifdef YGL_PAIR_VISIT
+}  // namespace ygl
+#include "ygl_traverse_pair.cuh"
+namespace ygl {
+#else
+// Persistent closest-hit stream (intersect_scene_bvh with the default ray range tmin = ray_eps,
+// tmax = flt_max): the same per-ray walk as trace_ray, but a warp keeps refilling finished lanes from
+// `src` (src.fetch hands out rays, src.commit stores a finished lane's hit). Must be called by full,
+// converged warps.
 constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
 constexpr int kPollInterval    = 6;  // scheduling rounds between two polls of an empty ring queue ...
 constexpr int kPollMaxInterval = 96;  // ... doubling up to this while it stays empty
 constexpr int kStreamThreads   = 128;  // block size of kernels that call trace_stream
-constexpr int kSharedStack     = 24;   // stack entries (t0, word) per lane kept in shared memory by k_extend (24 KB per 128 threads)
+constexpr int kSharedStack     = 28;   // stack entries per lane kept in shared memory by k_extend (14 KB per block)
+constexpr int kSuspendEntries  = kSuspendWords - 12;  // stack entries a parked ray can carry (12 header words)
+constexpr int kShallowStack    = 72;   // stack capacity of the !DEEP instantiation (both levels + markers)
 constexpr int kSuspendMinRounds = 96;  // a warp walks at least this many rounds per launch before suspending: progress guarantee
 constexpr int kSuspendBelow    = 8;    // suspend a drained warp's stragglers once this few lanes are busy (0 = never)
 
-// work words of a lane (`cur`) and of stack entries. Node words (word_*) are < 0xC0000000 as unsigned.
-constexpr int kWorkDone     = (int)0xC0000000;  // lane idle / bottom of the stack
-constexpr int kWorkExit     = (int)0xC0000001;  // stack only: leave the instance (back to the world-space ray)
-constexpr int kWorkUntested = (int)0xD0000000;  // | node index (28 bits): fetch the node and test its own box
-constexpr int kWorkEnter    = (int)0xE0000000;  // | (count - 1) << 26 | first packet (26 bits): instances of a top-level leaf
-YGL_D bool work_is_leaf(int w) { return w >= 0; }
-YGL_D bool work_is_node(int w) { return (w & (int)0xC0000000) == (int)0x80000000; }
-YGL_D bool work_is_untested(int w) { return (w & (int)0xF0000000) == kWorkUntested; }
-YGL_D bool work_is_enter(int w) { return (unsigned)w >= 0xE0000000u; }
-
-// slab test that also returns the entry distance t0 (fast variant: no operand can be NaN)
-YGL_D bool slab_test_t0(const f3& o, const f3& dinv, float tmin, float tmax, const float4& n0, const float4& n1, float& t0) {
-  float ax = (n0.x - o.x) * dinv.x, bx = (n0.w - o.x) * dinv.x;
-  float ay = (n0.y - o.y) * dinv.y, by = (n1.x - o.y) * dinv.y;
-  float az = (n0.z - o.z) * dinv.z, bz = (n1.y - o.z) * dinv.z;
-  t0       = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), tmin);
-  float t1 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), tmax);
-  t1 *= 1.00000024f;
-  return t0 <= t1;
-}
-
-template <bool COUNT, int THREADS, int SHARED, class Source>
+// DEEP: stack capacity for trees up to the reference's 128 levels per level of the hierarchy (a 1 KB local array per
+// thread: its mere presence in the frame costs the kernel ~8 % through L1 pressure); !DEEP: kShallowStack entries,
+// chosen by the host when the bound scene's trees fit (DScene::deep_stack).
+template <bool COUNT, int THREADS, int SHARED, bool DEEP, class Source>
 YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
-  constexpr int kSharedStack = SHARED;  // entries of this instantiation (static shared memory is limited to 48 KB)
-  // Traversal stack of (t0, work word) entries: the first kSharedStack entries of every lane live in shared memory,
-  // laid out [entry][thread] so a lane always hits its own bank (conflict-free whatever the lanes' depths are);
-  // deeper entries spill to per-thread local arrays (rare).
-  __shared__ float s_t0[kSharedStack][THREADS];
-  __shared__ int   s_wd[kSharedStack][THREADS];
-  float     l_t0[2 * kStackSize + 8 - kSharedStack];
-  int       l_wd[2 * kStackSize + 8 - kSharedStack];
-  const int tix  = threadIdx.x;
-  int       sp   = 1;
-  auto      push = [&](float t0, int w) {
-    if (sp < kSharedStack) s_t0[sp][tix] = t0, s_wd[sp][tix] = w;
-    else l_t0[sp - kSharedStack] = t0, l_wd[sp - kSharedStack] = w;
+  constexpr int kSharedStack = SHARED;
+  // Traversal stack: the first kSharedStack entries of every lane live in shared memory, laid out
+  // [entry][thread] so a lane always hits its own bank (conflict-free whatever the lanes' depths are);
+  // deeper entries spill to a per-thread local array (rare: kSharedStack covers a 1000-instance tree
+  // plus a 64K-primitive shape tree).
+  __shared__ int s_stack[kSharedStack][THREADS];
+  int            l_stack[(DEEP ? 2 * kStackSize + 8 : kShallowStack) - kSharedStack];
+  const int      tix  = threadIdx.x;
+  int            sp   = 1;
+  auto           push = [&](int v) {
+    if (sp < kSharedStack) s_stack[sp][tix] = v;
+    else l_stack[sp - kSharedStack] = v;
     sp++;
   };
-  s_t0[0][tix] = -kFltMax, s_wd[0][tix] = kWorkDone;  // sentinel: popping an empty stack yields "done"
+  auto pop_raw = [&]() {
+    --sp;
+    return sp < kSharedStack ? s_stack[sp][tix] : l_stack[sp - kSharedStack];
+  };
+  s_stack[0][tix] = kMarkDone;  // sentinel: popping an empty stack yields "done"
   hit_t res = {-1, -1, {0, 0}, 0, false};
 
   const float tmin = kRayEps;
@@ -401,31 +380,28 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   int  kind = kElemNone, cur_instance = -1, cur_packet = -1;
   bool bottom = false, have = false, more = true;
 
-  // pop until an entry survives the reference's box test with the current tmax (see the header comment);
-  // markers, ENTER runs and untested nodes carry t0 = -flt_max and always survive
-  auto advance = [&]() {
-    while (true) {
-      --sp;
-      const float t0 = sp < kSharedStack ? s_t0[sp][tix] : l_t0[sp - kSharedStack];
-      const int   w  = sp < kSharedStack ? s_wd[sp][tix] : l_wd[sp - kSharedStack];
-      if (w == kWorkExit) {  // leaving an instance: back to the world-space ray
-        ray        = world;
-        nodes      = scene.top_nodes;
-        bottom     = false;
-        cur_packet = -1;
-        continue;
-      }
-      if (w == kWorkDone) {
-        sp = 1;
-        return w;
-      }
-      if (t0 <= tmax * 1.00000024f) return w;
-    }
-  };
-  // the instance-level part of entering packet `first`: transform_ray(inverse(frame, true), ray), yocto_bvh.cpp:601-604
-  // Returns the work word of the shape's root (its box is tested here: the packet carries the root node).
-  auto load_instance = [&](int first, bool test_root) {
+  // ENTER entries carry a run of instances of one top-level leaf: ~(first | (count - 1) << 28)
+  auto enter = [&](int entry) {
+    const int run = ~entry, first = run & 0x0fffffff, left = run >> 28;
+    if (left > 0) push(~((first + 1) | ((left - 1) << 28)));  // next instance of the leaf, same order
     cur_packet = first;
+    const DInstancePacket* pk = scene.top_packets + first;
+    float4 a = __ldg(&pk->q[0]), b = __ldg(&pk->q[1]), c = __ldg(&pk->q[2]), e = __ldg(&pk->q[3]);
+    float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
+    frame3 inv = {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}, {c.y, c.z, c.w}};
+    ray          = make_ray(transform_point(inv, world.o), transform_vector(inv, world.d));
+    if (COUNT) cnt.instances++;
+    cur_instance = __float_as_int(e.y);
+    kind         = __float_as_int(e.z);
+    nodes   = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.y) << 32) | (unsigned)__float_as_int(p0.x));
+    packets = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.w) << 32) | (unsigned)__float_as_int(p0.z));
+    prims   = (const int*)(((unsigned long long)(unsigned)__float_as_int(p1.y) << 32) | (unsigned)__float_as_int(p1.x));
+    bottom      = true;
+    push(kMarkExit);
+    return 0;
+  };
+  // the part of `enter` that only depends on the packet (used to resume a suspended ray)
+  auto reload_instance = [&](int first) {
     const DInstancePacket* pk = scene.top_packets + first;
     float4 a = __ldg(&pk->q[0]), b = __ldg(&pk->q[1]), c = __ldg(&pk->q[2]), e = __ldg(&pk->q[3]);
     float4 p0 = __ldg(&pk->q[4]), p1 = __ldg(&pk->q[5]);
@@ -436,61 +412,49 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     nodes   = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.y) << 32) | (unsigned)__float_as_int(p0.x));
     packets = (const float4*)(((unsigned long long)(unsigned)__float_as_int(p0.w) << 32) | (unsigned)__float_as_int(p0.z));
     prims   = (const int*)(((unsigned long long)(unsigned)__float_as_int(p1.y) << 32) | (unsigned)__float_as_int(p1.x));
-    bottom  = true;
-    if (!test_root) return kWorkDone;
-    float4 r0 = __ldg(&pk->q[6]), r1 = __ldg(&pk->q[7]);
-    if (COUNT) cnt.instances++, cnt.bot_nodes++;
-    const bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, r0, r1)
-                                  : slab_test_fast(ray.o, ray.dinv, tmin, tmax, r0, r1);
-    return inside ? __float_as_int(r1.w) : kWorkDone;
+    bottom       = true;
+    cur_packet   = first;
   };
-  // ENTER work: the next instance of a top-level leaf's run (instances of a leaf in order, yocto_bvh.cpp:599-610)
-  auto enter = [&](int run) {
-    const int first = run & 0x03ffffff, left = (run >> 26) & 7;
-    if (left > 0) push(-kFltMax, kWorkEnter | ((left - 1) << 26) | (first + 1));
-    push(-kFltMax, kWorkExit);
-    const int w = load_instance(first, true);
-    return w == kWorkDone ? advance() : w;  // root missed: straight to EXIT
+  auto advance = [&]() {
+    int v = pop_raw();
+    if (v == kMarkExit) {  // leaving an instance: back to the world-space ray; never two EXITs in a row
+      ray        = world;
+      nodes      = scene.top_nodes;
+      bottom     = false;
+      cur_packet = -1;
+      v          = pop_raw();
+    }
+    if (v == kMarkDone) sp = 1;
+    return v;
   };
 
-  int cur = kWorkDone, leaf_next = 0, leaf_end = 0, rounds = 0, poll_wait = 0, poll_gap = kPollInterval;
-  // one unit of node work: expand an accepted internal node (test both children), or test an untested node
+  int cur = kMarkDone, leaf_next = 0, leaf_end = 0, rounds = 0, poll_wait = 0, poll_gap = kPollInterval;
+  // one node visit of the lane's walk (cur >= 0)
   auto visit_node = [&]() {
-    if (work_is_untested(cur)) {
-      const int n  = cur & 0x0fffffff;
-      float4    n0 = __ldg(nodes + 2 * n), n1 = __ldg(nodes + 2 * n + 1);
-      if (COUNT) {
-        if (bottom) cnt.bot_nodes++;
-        else cnt.top_nodes++;
-      }
-      const bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
-                                    : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
-      cur = inside ? __float_as_int(n1.w) : advance();
-      return;
-    }
-    const int first = word_first_child(cur);
-    const int neg   = (ray.sgn >> word_axis(cur)) & 1;  // visit child `neg` first (ray_dsign[axis], yocto_bvh.cpp:592-598)
-    if (ray.exact) {
-      push(-kFltMax, kWorkUntested | (first + 1 - neg));
-      cur = kWorkUntested | (first + neg);
-      return;
-    }
-    const float4* pair = nodes + 2 * (size_t)first;  // node i = float4s 2i, 2i+1: the pair is 64 contiguous bytes
-    float4 a0 = __ldg(pair), a1 = __ldg(pair + 1), b0 = __ldg(pair + 2), b1 = __ldg(pair + 3);
+    float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
     if (COUNT) {
-      if (bottom) cnt.bot_nodes += 2;
-      else cnt.top_nodes += 2;
+      if (bottom) cnt.bot_nodes++;
+      else cnt.top_nodes++;
     }
-    float      ta, tb;
-    const bool ha = slab_test_t0(ray.o, ray.dinv, tmin, tmax, a0, a1, ta);
-    const bool hb = slab_test_t0(ray.o, ray.dinv, tmin, tmax, b0, b1, tb);
-    const int  wa = __float_as_int(a1.w), wb = __float_as_int(b1.w);
-    // near = the child the reference visits first, far = the one it stacks
-    const bool  h_near = neg ? hb : ha, h_far = neg ? ha : hb;
-    const int   w_near = neg ? wb : wa, w_far = neg ? wa : wb;
-    const float t_far  = neg ? ta : tb;
-    if (h_far) push(t_far, w_far);
-    cur = h_near ? w_near : advance();
+    bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
+                            : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
+    const int word = __float_as_int(n1.w);
+    if (!inside) {
+      cur = advance();
+    } else if (word_internal(word)) {
+      const int start = word_first_child(word);
+      int       neg   = (ray.sgn >> word_axis(word)) & 1;
+      push(start + 1 - neg);
+      cur = start + neg;
+    } else if (bottom) {
+      leaf_next = word_first_prim(word);
+      leaf_end  = leaf_next + word_num(word);
+      cur       = leaf_next < leaf_end ? kMarkLeaf : advance();
+    } else {
+      // leaf of the instance tree (<= 4 instances, visited in order): one ENTER entry for the run
+      const int num = word_num(word);
+      cur           = num > 0 ? ~(word_first_prim(word) | ((num - 1) << 28)) : advance();
+    }
   };
   // one primitive of the current leaf
   auto test_prim = [&](int idx) {
@@ -518,33 +482,27 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       tmax = pd;
     }
   };
-  // a lane holding a leaf word of the instance tree turns it into an ENTER run
-  auto top_leaf_to_run = [&](int w) { return kWorkEnter | ((word_num(w) - 1) << 26) | word_first_prim(w); };
-  // park the lane's unfinished walk in this thread's save slot; it resumes in the next launch exactly where it stopped
+  // park the lane's unfinished walk in its save area; it resumes in the next launch exactly where it stopped
   auto suspend_lane = [&]() {
     int* sv = src.save_slot();
     sv[0] = cur, sv[1] = sp, sv[2] = leaf_next, sv[3] = leaf_end, sv[4] = cur_packet;
     sv[5] = __float_as_int(tmax);
     sv[6] = res.instance, sv[7] = res.element, sv[8] = __float_as_int(res.uv.x), sv[9] = __float_as_int(res.uv.y);
     sv[10] = __float_as_int(res.distance), sv[11] = res.hit ? 1 : 0;
-    for (int k = 1; k < sp; k++) {
-      sv[12 + 2 * k]     = __float_as_int(k < kSharedStack ? s_t0[k][tix] : l_t0[k - kSharedStack]);
-      sv[12 + 2 * k + 1] = k < kSharedStack ? s_wd[k][tix] : l_wd[k - kSharedStack];
-    }
+    for (int k = 1; k < sp; k++) sv[12 + k] = k < kSharedStack ? s_stack[k][tix] : l_stack[k - kSharedStack];
     src.commit_suspended();
-    cur = kWorkDone, sp = 1, have = false;
+    cur = kMarkDone, sp = 1, have = false;
   };
   while (true) {
-    const bool     is_leaf    = work_is_leaf(cur);
-    const unsigned want_node  = __ballot_sync(kFullWarp, work_is_node(cur) || work_is_untested(cur));
-    const unsigned want_prim  = __ballot_sync(kFullWarp, is_leaf && bottom);
-    const unsigned want_enter = __ballot_sync(kFullWarp, work_is_enter(cur) || (is_leaf && !bottom));
+    const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0);
+    const unsigned want_prim  = __ballot_sync(kFullWarp, cur == kMarkLeaf);
+    const unsigned want_enter = __ballot_sync(kFullWarp, cur < 0 && cur > kMarkLeaf);
     const unsigned busy       = want_node | want_prim | want_enter;
     const int      n_idle     = 32 - __popc(busy);
 
     if (more && n_idle >= src.refill_thr && (!Source::kPolling || !busy || --poll_wait < 0)) {
       // ---- refill: finished lanes hand over their hit and take the next queued ray ----
-      const bool idle = cur == kWorkDone;
+      const bool idle = cur == kMarkDone;
       src.commit_finished(idle && have, res);
       f3   o, d;
       bool resume = false;
@@ -557,7 +515,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
         res   = {-1, -1, {0, 0}, 0, false};
         sp = 1, bottom = false, cur_packet = -1;
         nodes = scene.top_nodes;
-        cur   = scene.top_num_nodes > 0 ? (kWorkUntested | 0) : kWorkDone;  // the root of the instance tree
+        cur   = scene.top_num_nodes > 0 ? 0 : kMarkDone;
         if (resume) {
           // a ray suspended by the previous launch: restore its walk exactly where it stopped
           const int* sv = src.load_slot();
@@ -566,10 +524,10 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
           tmax = __int_as_float(sv[5]);
           res  = {sv[6], sv[7], {__int_as_float(sv[8]), __int_as_float(sv[9])}, __int_as_float(sv[10]), sv[11] != 0};
           for (int k = 1; k < sp; k++) {
-            if (k < kSharedStack) s_t0[k][tix] = __int_as_float(sv[12 + 2 * k]), s_wd[k][tix] = sv[12 + 2 * k + 1];
-            else l_t0[k - kSharedStack] = __int_as_float(sv[12 + 2 * k]), l_wd[k - kSharedStack] = sv[12 + 2 * k + 1];
+            if (k < kSharedStack) s_stack[k][tix] = sv[12 + k];
+            else l_stack[k - kSharedStack] = sv[12 + k];
           }
-          if (pkt >= 0) load_instance(pkt, false);
+          if (pkt >= 0) reload_instance(pkt);
         }
       }
       if (!Source::kPolling) continue;
@@ -589,8 +547,8 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       // ---- suspend: the queue is exhausted and this warp is running nearly empty. Instead of draining
       // the stragglers at 1-2 lanes per instruction, save their traversal state; they resume in the next
       // launch (one wavefront iteration later — a per-lane delay only, the walk itself is unchanged). ----
-      if (cur != kWorkDone && sp <= kSuspendStack) suspend_lane();
-      if (!__any_sync(kFullWarp, cur != kWorkDone)) break;
+      if (cur != kMarkDone && sp <= kSuspendEntries) suspend_lane();
+      if (!__any_sync(kFullWarp, cur != kMarkDone)) break;
       // lanes with a deeper stack than the save area keep walking
     }
     if (Source::kLone && !more && src.lone_below > 0 && __popc(busy) <= src.lone_below) {
@@ -600,18 +558,18 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       // launch (only the extreme stragglers get there; a parked ray always advances lone_steps per launch)
       const int limit = src.lone_steps > 0 ? src.lone_steps : 0x7fffffff;
       int       steps = 0;
-      while (cur != kWorkDone) {
-        if (++steps > limit && sp <= kSuspendStack) {
+      while (cur != kMarkDone) {
+        if (++steps > limit && sp <= kSuspendEntries) {
           suspend_lane();
           break;
         }
-        if (work_is_node(cur) || work_is_untested(cur)) {
+        if (cur >= 0) {
           visit_node();
-        } else if (work_is_leaf(cur) && bottom) {
-          for (int idx = word_first_prim(cur), end = idx + word_num(cur); idx < end; idx++) test_prim(idx);
+        } else if (cur == kMarkLeaf) {
+          while (leaf_next < leaf_end) test_prim(leaf_next++);
           cur = advance();
         } else {
-          cur = work_is_leaf(cur) ? (word_num(cur) > 0 ? enter(top_leaf_to_run(cur)) : advance()) : enter(cur);
+          cur = enter(cur);
         }
       }
       break;
@@ -619,14 +577,13 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     const int n_node = __popc(want_node), n_prim = __popc(want_prim), n_enter = __popc(want_enter);
 
     if (n_node >= n_prim && n_node >= n_enter) {
-      // several units of node work per scheduling round: cuts the vote overhead on the most frequent path
+      // several node visits per scheduling round: cuts the vote overhead on the most frequent path
 #pragma unroll 1
       for (int rep = 0; rep < src.node_reps; rep++)
-        if (work_is_node(cur) || work_is_untested(cur)) visit_node();
+        if (cur >= 0) visit_node();
     } else if (n_prim >= n_enter) {
       // all primitives of the lane's leaf (<= 4, bvh_max_prims) in one go, warp-uniform trip count
-      const bool in_leaf = is_leaf && bottom;
-      if (in_leaf) leaf_next = word_first_prim(cur), leaf_end = leaf_next + word_num(cur);
+      const bool in_leaf = cur == kMarkLeaf;
       for (int k = 0; k < 4; k++) {
         const bool test = in_leaf && leaf_next < leaf_end;
         if (!__any_sync(kFullWarp, test)) break;
@@ -634,12 +591,13 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       }
       if (in_leaf) cur = advance();
     } else {
-      if (is_leaf && !bottom) cur = word_num(cur) > 0 ? enter(top_leaf_to_run(cur)) : advance();
-      else if (work_is_enter(cur)) cur = enter(cur);
+      if (cur < 0 && cur > kMarkLeaf) cur = enter(cur);
     }
   }
   // lanes still holding an uncommitted result (more == false path)
-  src.commit_finished(have && cur == kWorkDone, res);
+  src.commit_finished(have && cur == kMarkDone, res);
 }
+
+#endif  // YGL_PAIR_VISIT
 
 }  // namespace ygl

@@ -26,7 +26,7 @@ EXPORTS = [
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
     "ygl_trace_counters", "ygl_context_set_profiling", "ygl_context_set_mode", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
-    "ygl_scene_load", "ygl_loaded_scene_desc", "ygl_loaded_scene_name", "ygl_loaded_scene_destroy",
+    "ygl_bvh_build_device", "ygl_scene_load", "ygl_loaded_scene_desc", "ygl_loaded_scene_name", "ygl_loaded_scene_destroy",
     "ygl_trace_start", "ygl_trace_cancel", "ygl_trace_wait", "ygl_trace_done", "ygl_trace_preview",
     "ygl_context_set_option", "ygl_context_get_option", "ygl_state_reset", "ygl_trace_sample", "ygl_bvh_create_from_host",
 ]
@@ -58,6 +58,7 @@ def load():
     lib.ygl_scene_update_cameras.argtypes = [vp, P(abi.Camera), i32]
     lib.ygl_scene_destroy.argtypes = [vp]
     lib.ygl_bvh_build.argtypes = [P(abi.SceneDesc), i32, P(vp)]
+    lib.ygl_bvh_build_device.argtypes = [vp, P(abi.SceneDesc), i32, P(vp)]
     lib.ygl_bvh_tree_size.argtypes = [vp, i32, P(i32), P(i32)]
     lib.ygl_bvh_tree_get.argtypes = [vp, i32, vp, vp]
     lib.ygl_bvh_destroy.argtypes = [vp]
@@ -142,10 +143,13 @@ class Bvh:
     """make_trace_bvh (host build in the reference's node order), or — trees=(top, [per shape]) with each tree a
     (nodes, primitives) pair in the reference's bvh_tree layout — trees built elsewhere adopted verbatim."""
 
-    def __init__(self, scene, highquality=False, trees=None):
+    def __init__(self, scene, highquality=False, trees=None, device_ctx=None):
         self.lib = load()
         self.desc = scene.desc()
         self.h = C.c_void_p()
+        if device_ctx is not None:  # large trees on the GPU (ygl_bvh_build_device), bit-identical to the host build
+            _check(self.lib.ygl_bvh_build_device(device_ctx.h, C.byref(self.desc), int(highquality), C.byref(self.h)))
+            return
         if trees is None:
             _check(self.lib.ygl_bvh_build(C.byref(self.desc), int(highquality), C.byref(self.h)))
             return
@@ -306,12 +310,12 @@ class Context:
 class DeviceScene:
     """Device-resident scene + bvh + lights (make_cutrace_scene-style upload)."""
 
-    def __init__(self, ctx, scene, highquality=False, trees=None):
+    def __init__(self, ctx, scene, highquality=False, trees=None, device_build=False):
         self.ctx, self.lib, self.scene = ctx, ctx.lib, scene
         self.desc = scene.desc()
         self.h = C.c_void_p()
         _check(self.lib.ygl_scene_create(ctx.h, C.byref(self.desc), C.byref(self.h)))
-        self.bvh = Bvh(scene, highquality, trees)
+        self.bvh = Bvh(scene, highquality, trees, device_ctx=ctx if device_build else None)
         self.lights = Lights(scene)
 
     def trace_start(self, state, params):
