@@ -300,8 +300,7 @@ int ygl_trace_sample(ygl_context* ctx, ygl_state* state, const ygl_scene* scene,
  * ygl_trace_start returns at once; ONE batch (params->batch samples per pixel) renders on a worker thread of the
  * context. Until ygl_trace_done() reports 1 (or ygl_trace_cancel / ygl_trace_wait returned) the context, the state and
  * the scene objects belong to the worker — the reference's rule (exclusive access to `state`). ygl_trace_cancel raises
- * the stop flag — polled by the host between wavefront iterations, or turned into the abort flag of the persistent
- * kernel — and joins the worker; as in the reference, a cancelled batch leaves the pixels at mixed sample counts
+ * the stop flag — polled by the host between rounds of wavefront iterations — and joins the worker; as in the reference, a cancelled batch leaves the pixels at mixed sample counts
  * (state.samples is advanced by the batch all the same, yocto_trace.cpp:1641) and the caller resets the state.
  * ygl_trace_wait joins without cancelling and returns the batch's status. */
 int ygl_trace_start(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
@@ -328,17 +327,14 @@ int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]);
  * with CUDA events on the context stream. count_traversal != 0: run the counting variant of the
  * extend kernel (slower; never combine with timing you report). */
 int ygl_context_set_profiling(ygl_context* ctx, int time_kernels, int count_traversal);
-/* Scheduling mode of ygl_trace_samples / ygl_trace_image (both give bit-identical results):
- * YGL_MODE_WAVEFRONT (default) - one kernel per stage and iteration, linked by compacted lane queues;
- * YGL_MODE_PERSISTENT - ONE resident kernel per call, stage-specialised SMs linked by ring queues in global memory
- * (independent of the tile size, no per-iteration launches; opt-in). The persistent kernel serves the single-stage
- * samplers; pathdirect and pathmis always run on the wavefront scheduler. */
+/* Round 1 had a second scheduler (one resident kernel, YGL_MODE_PERSISTENT). It was slower than the wavefront on every
+ * tile size and timing-dependent, and has been removed; the call and both values remain for source compatibility and
+ * always select the wavefront scheduler (results never depended on the mode). */
 enum { YGL_MODE_WAVEFRONT = 0, YGL_MODE_PERSISTENT = 1 };
 int ygl_context_set_mode(ygl_context* ctx, int mode);
 /* Scheduling knobs of a context, by name (the library reads no environment variables). None can change a result
  * bit. Names: "ext_blocks_per_sm", "refill", "node_reps", "suspend", "suspend_rounds", "lone", "lone_steps", "fuse",
- * "bin", "pipes", "graph", "top_smem", "persist_blocks_per_sm", "persist_ext_sms", "persist_lpdf_warps",
- * "watchdog_s" (struct Tuning in ygl_kernels.cuh documents each). -1 restores the automatic choice where one exists. */
+ * "bin", "pipes", "graph", "top_smem" (struct Tuning in ygl_kernels.cuh documents each). -1 restores the automatic choice where one exists. */
 int ygl_context_set_option(ygl_context* ctx, const char* name, double value);
 int ygl_context_get_option(ygl_context* ctx, const char* name, double* value);
 /* Timings of the last ygl_trace_samples / ygl_trace_image with time_kernels on:

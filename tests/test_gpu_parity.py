@@ -132,29 +132,6 @@ def test_full_state_every_sampler(ctx, ref, sampler):
     np.testing.assert_array_equal(got["rngs"], want["rngs"])
 
 
-@pytest.mark.parametrize("sampler", [abi.SAMPLER_PATH, abi.SAMPLER_PATHMIS, abi.SAMPLER_PATHDIRECT, abi.SAMPLER_NAIVE,
-                                     abi.SAMPLER_EYELIGHT, abi.SAMPLER_FALSECOLOR])
-def test_persistent_mode_matches_reference(ref, sampler):
-    """YGL_MODE_PERSISTENT (one resident kernel, SM-specialised stages linked by ring queues) is a scheduling
-    change only: full state bit-identical to the unmodified reference, incl. a resumed second batch, on a frame
-    large enough to use SM-specialised blocks and on a tiny one (mixed blocks)."""
-    pctx = lib.Context(0)
-    pctx.set_mode("persistent")
-    scene = get_scene("features")
-    for res, spp in ((256, 4), (40, 2)):
-        params = abi.trace_params(resolution=res, samples=spp, bounces=6, batch=spp // 2, sampler=sampler)
-        want = ref.scene(scene).trace_image(params, full=True)
-        ds = lib.DeviceScene(pctx, scene)
-        st = ds.make_state(params)
-        ds.trace_samples(st, params)
-        ds.trace_samples(st, params)
-        assert st.samples == spp
-        got = st.download(full=True)
-        for k in ("image", "albedo", "normal", "hits"):
-            assert got[k].tobytes() == want[k].tobytes(), (k, res)
-        np.testing.assert_array_equal(got["rngs"], want["rngs"])
-
-
 @pytest.mark.parametrize("options", [
     dict(suspend=8, suspend_rounds=8, lone=0),      # park the last lanes of a drained warp early and often
     dict(suspend=0, lone=32, lone_steps=40),        # vote-free tail walk, parked after 40 steps
@@ -165,6 +142,9 @@ def test_persistent_mode_matches_reference(ref, sampler):
     dict(bin=1, fuse=0, suspend=8, suspend_rounds=4),  # class-binned queues + parked rays re-entering the extend queue
     dict(bin=1, fuse=1, pipes=2),
     dict(ext_blocks_per_sm=2, bin=1),
+    dict(graph=1, fuse=1, bin=1),                   # rounds of iterations submitted as one CUDA graph
+    dict(graph=1, fuse=0, bin=0, lone=8),
+    dict(graph=0, top_smem=1, suspend=8, lone=0),   # instance-level tree staged in shared memory by a bulk async copy
 ])
 def test_scheduling_options_are_bit_exact(ref, options):
     """Every scheduling knob of a context (ygl_context_set_option: the extend kernel's tail strategies, path-end
@@ -540,14 +520,12 @@ def test_deep_tree_uses_the_full_reference_stack(ctx, ref):
         lib.DeviceScene(ctx, scenes.sliver_chain(170))
 
 
-@pytest.mark.parametrize("mode", ["wavefront", "persistent"])
-def test_progressive_api(ref, mode):
+def test_progressive_api(ref):
     """trace_start / trace_done / trace_cancel / trace_preview (yocto_trace.cpp:1627-1676): batches started
     asynchronously and waited for give the reference's bits; a cancelled batch returns promptly and leaves a state
     that ygl_state_reset makes good again; the preview is the 1-spp render at resolution / pratio, replicated."""
     import time
     pctx = lib.Context(0)
-    pctx.set_mode(mode)
     scene = get_scene("features")
     params = abi.trace_params(resolution=192, samples=4, bounces=6, batch=2)
     rs = ref.scene(scene)

@@ -9,7 +9,7 @@ for STEP in "$@"; do
   echo "=== $STEP"
   case $STEP in
     tests)
-      timeout -s KILL 1500 python -m pytest tests -m gpu -q --maxfail=8 -x --durations=8 > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/${TAG}_tests.log | cut -c1-220 ;;
+      timeout -s KILL 1500 python -m pytest tests -m gpu -q --maxfail=12 --durations=12 -s > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; grep -a "bvh build\|passed\|failed\|^FAILED\|^ERROR" gpurun_out/${TAG}_tests.log | tail -n 40 | cut -c1-220 ;;
     tests_fast)
       timeout -s KILL 900 python -m pytest tests -m gpu -q --maxfail=8 -k "not full_size and not libm and not counters" > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/${TAG}_tests.log | cut -c1-220 ;;
     bench)
@@ -29,7 +29,7 @@ for STEP in "$@"; do
     san)
       timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
     ab2)
-      for CFG in "lib" "lib bin=0" "lib fuse=1" "lib_pair"; do
+      for CFG in "lib" "lib top_smem=1" "lib graph=1" "lib graph=0" "lib ext_blocks_per_sm=4" "lib ext_blocks_per_sm=5 graph=1" "lib bin=0 graph=1"; do
         set -- $CFG; LIB=$1; shift
         [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
         echo "--- $LIB $*"

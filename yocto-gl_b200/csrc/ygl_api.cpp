@@ -95,9 +95,6 @@ struct ygl_context {
   unsigned long long*      d_trav = nullptr;  // 7 traversal counters
   std::vector<cudaEvent_t> ev_pool;           // event pairs around extend launches
   cudaEvent_t              ev_loop[2] = {nullptr, nullptr};
-  // persistent mode: three ring queues + their cursors (see PQueues)
-  int*     ring_mem = nullptr;
-  unsigned ring_cap = 0;
   // binding cache: DShape table for a (scene, bvh, lights) triple
   const ygl_scene*  bound_scene  = nullptr;
   const ygl_bvh*    bound_bvh    = nullptr;
@@ -247,7 +244,6 @@ void ygl_context_destroy(ygl_context* ctx) {
   if (ctx->d_lights) cudaFree(ctx->d_lights);
   if (ctx->d_inst_class) cudaFree(ctx->d_inst_class);
   if (ctx->d_trav) cudaFree(ctx->d_trav);
-  if (ctx->ring_mem) cudaFree(ctx->ring_mem);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   for (auto& e : ctx->ev_loop)
     if (e) cudaEventDestroy(e);
@@ -933,6 +929,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     int                lo, hi, parity = 0, slot = 0;
     bool               pending[2] = {false, false}, done = false, first = true;
     LaunchCfg          light, heavy;
+    cudaGraphExec_t    round_graph = nullptr;  // check_every iterations as one graph launch (see use_graph)
   } runs[ygl_context::kMaxPipes];
   for (int j = 0; j < npipes; j++) {
     Run& r = runs[j];
@@ -990,31 +987,60 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     launches += per_iteration;
     return YGL_OK;
   };
+  // A round of check_every iterations is the same launch sequence every time (the queue parity is back where it
+  // started): on small tiles, where an iteration lasts a few hundred microseconds and the gaps between its 7-9
+  // launches are a tenth of that, the round is captured once into a CUDA graph and re-launched as a unit. Not while
+  // timing or counting (those need the individual launches), and pointless on big tiles.
+  const bool use_graph = !timing && !trav && (tune.graph >= 0 ? tune.graph != 0 : st.num_lanes <= 800000);
+  (void)extend_grid_threads(ctx->num_sms);  // occupancy query of the extend kernel: done before any capture
+  auto destroy_graphs = [&]() {
+    for (int j = 0; j < npipes; j++)
+      if (runs[j].round_graph) cudaGraphExecDestroy(runs[j].round_graph), runs[j].round_graph = nullptr;
+  };
   int remaining = npipes;
   while (remaining > 0) {
     if (ctx->stop.load(std::memory_order_relaxed)) break;  // trace_cancel: polled between rounds of iterations
-    for (int k = 0; k < check_every; k++) {
-      for (int j = 0; j < npipes; j++) {
-        Run& r = runs[j];
-        if (r.done) continue;
-        cudaStream_t s = r.pipe->stream;
-        if (r.first) {
-          // the lanes' first camera samples; afterwards a finished path's lane starts its next sample in the
-          // kernel that ends the path (end_of_path / k_finish)
-          launch_generate(s, r.light, dscene, st, r.q, kp, r.parity), launches++;
-          r.first = false;
-        }
-        if (timing) {
-          while (ctx->ev_pool.size() < ev_used + 2) {
-            cudaEvent_t e;
-            CUDA_TRY(cudaEventCreate(&e));
-            ctx->ev_pool.push_back(e);
+    for (int j = 0; j < npipes; j++) {
+      Run& r = runs[j];
+      if (r.done) continue;
+      cudaStream_t s = r.pipe->stream;
+      if (r.first) {
+        // the lanes' first camera samples; afterwards a finished path's lane starts its next sample in the
+        // kernel that ends the path (end_of_path / k_finish)
+        launch_generate(s, r.light, dscene, st, r.q, kp, r.parity), launches++;
+        r.first = false;
+      }
+      if (use_graph) {
+        if (!r.round_graph) {
+          cudaGraph_t graph = nullptr;
+          CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+          const uint64_t before = launches;
+          for (int k = 0; k < check_every; k++) enqueue_iteration(r, s, false);
+          launches = before;
+          cudaError_t e = cudaStreamEndCapture(s, &graph);
+          if (e == cudaSuccess) e = cudaGraphInstantiate(&r.round_graph, graph, 0);
+          if (graph) cudaGraphDestroy(graph);
+          if (e != cudaSuccess) {
+            destroy_graphs();
+            return fail(YGL_ERR_CUDA, std::string("CUDA graph of a wavefront round: ") + cudaGetErrorString(e));
           }
         }
-        if (int rc = enqueue_iteration(r, s, timing)) return rc;
+        CUDA_TRY(cudaGraphLaunch(r.round_graph, s));
+        launches += (uint64_t)per_iteration * check_every;
+      } else {
+        for (int k = 0; k < check_every; k++) {
+          if (timing) {
+            while (ctx->ev_pool.size() < ev_used + 2) {
+              cudaEvent_t e;
+              CUDA_TRY(cudaEventCreate(&e));
+              ctx->ev_pool.push_back(e);
+            }
+          }
+          if (int rc = enqueue_iteration(r, s, timing)) return rc;
+        }
       }
-      iterations++;
     }
+    iterations += check_every;
     for (int j = 0; j < npipes; j++) {
       Run& r = runs[j];
       if (r.done) continue;
@@ -1043,6 +1069,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   }
   if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[1], s0));
   for (int j = 0; j < npipes; j++) CUDA_TRY(cudaStreamSynchronize(runs[j].pipe->stream));
+  destroy_graphs();
   CUDA_TRY(cudaGetLastError());
   for (int j = 0; j < npipes; j++) {
     Counters c;
@@ -1078,116 +1105,7 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
 }
 
 
-// The persistent driver: ONE kernel launch renders `nsamples` more samples on every lane (k_persistent). The host
-// only watches for progress: if the device counters stand still for YGL_WATCHDOG_S seconds (default 20) it raises
-// the abort flag, every warp leaves, and the call fails - a scheduling bug must never hang the GPU.
-static int run_persistent(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
-  PathState& st = state->st;
-  if (st.num_lanes == 0 || nsamples <= 0) return YGL_OK;
-  KParams kp = make_kparams(params, state->samples + nsamples);
-
-  cudaStream_t s   = ctx->stream;
-  // ring capacity: every lane can sit in a ring, and every consumer thread of the grid can hold a ticket that runs
-  // ahead of the producers; two live tickets must never share a slot
-  const unsigned max_threads = (unsigned)ctx->num_sms * 2048u;
-  unsigned       cap         = 1024;
-  while (cap < (unsigned)st.num_lanes + max_threads) cap <<= 1;
-  constexpr int kCtrWords = 256;  // every cursor on its own 128-byte line
-  if (cap > ctx->ring_cap) {
-    if (ctx->ring_mem) cudaFree(ctx->ring_mem), ctx->ring_mem = nullptr, ctx->ring_cap = 0;
-    CUDA_TRY(cudaMalloc((void**)&ctx->ring_mem, ((size_t)3 * cap + kCtrWords) * sizeof(int)));
-    ctx->ring_cap = cap;
-  }
-  cap            = ctx->ring_cap;
-  int*      base = ctx->ring_mem;
-  unsigned* ctr  = (unsigned*)(base + (size_t)3 * cap);
-  CUDA_TRY(cudaMemsetAsync(base, 0xff, (size_t)3 * cap * sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(ctr, 0, kCtrWords * sizeof(int), s));
-  Counters* counters = ctx->pipes[0].counters;
-  CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(Counters), s));
-  PQueues q;
-  // head and tail of a ring share one 8-byte word (polled with a single load); rings on separate 128-byte lines
-  q.ext         = Ring{base, ctr + 0, ctr + 1, cap - 1};
-  q.shade       = Ring{base + cap, ctr + 64, ctr + 65, cap - 1};
-  q.lpdf        = Ring{base + (size_t)2 * cap, ctr + 128, ctr + 129, cap - 1};
-  q.seed_cursor = ctr + 192;
-  q.abort       = (int*)(ctr + 224);
-  q.counters    = counters;
-
-  const bool timing = ctx->time_kernels;
-  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[0], s));
-  launch_persistent(s, ctx->num_sms, ctx->tune, ctx->dscene, st, q, kp, 0, st.num_lanes, state->samples);
-  CUDA_TRY(cudaGetLastError());
-  if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_loop[1], s));
-  cudaEvent_t fin = ctx->pipes[0].ev[0];
-  CUDA_TRY(cudaEventRecord(fin, s));
-
-  // ---- wait + watchdog ----
-  const double watchdog_s = ctx->tune.watchdog_s;
-  cudaStream_t side = ctx->pipes[1].stream;
-  int*         h    = ctx->pipes[1].h_done;  // pinned, 2 ints
-  long long    last_progress = -1;
-  auto         t_last = std::chrono::steady_clock::now(), t_check = t_last;
-  bool         aborted = false;
-  for (int spin = 0;; spin++) {
-    cudaError_t e = cudaEventQuery(fin);
-    if (e == cudaSuccess) break;
-    if (e != cudaErrorNotReady) return fail(YGL_ERR_CUDA, cudaGetErrorString(e));
-    if (spin > 200) std::this_thread::sleep_for(std::chrono::microseconds(50));
-    auto now = std::chrono::steady_clock::now();
-    if (std::chrono::duration<double>(now - t_check).count() < 0.25) continue;
-    t_check = now;
-    unsigned long long cam = 0;
-    CUDA_TRY(cudaMemcpyAsync(h, &counters->done_lanes, sizeof(int), cudaMemcpyDeviceToHost, side));
-    CUDA_TRY(cudaMemcpyAsync(h + 1, &counters->camera_samples, sizeof(int), cudaMemcpyDeviceToHost, side));
-    CUDA_TRY(cudaStreamSynchronize(side));
-    cam = (unsigned)h[1];
-    long long progress = (long long)h[0] * 1000003ll + (long long)cam;
-    if (progress != last_progress) {
-      last_progress = progress;
-      t_last        = now;
-    }
-    // raise the abort flag when the job stalls (watchdog) or the caller cancels (trace_cancel)
-    if (!aborted && (ctx->stop.load(std::memory_order_relaxed) ||
-                        std::chrono::duration<double>(now - t_last).count() > watchdog_s)) {
-      h[0] = 1;
-      CUDA_TRY(cudaMemcpyAsync(q.abort, h, sizeof(int), cudaMemcpyHostToDevice, side));
-      CUDA_TRY(cudaStreamSynchronize(side));
-      aborted = true;
-    }
-  }
-  CUDA_TRY(cudaStreamSynchronize(s));
-  CUDA_TRY(cudaGetLastError());
-  int      abort_flag = 0;
-  Counters c;
-  CUDA_TRY(cudaMemcpy(&abort_flag, q.abort, sizeof(int), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(&c, counters, sizeof(Counters), cudaMemcpyDeviceToHost));
-  if ((abort_flag || c.done_lanes != st.num_lanes) && !ctx->stop.load())
-    return fail(YGL_ERR_RUNTIME, "persistent kernel stopped by the watchdog (no progress)");
-  ctx->stats[0] += c.camera_samples;
-  ctx->stats[1] += c.scene_rays;
-  ctx->stats[2] += c.instance_rays;
-  ctx->stats[3] += 1;
-  ctx->stats[4] += 1;
-  if (timing) {
-    float loop_ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&loop_ms, ctx->ev_loop[0], ctx->ev_loop[1]));
-    ctx->timings[1] += loop_ms;
-    ctx->timings[3] = 0;  // persistent mode: no separate extend launches to time
-  }
-  state->samples += nsamples;
-  return YGL_OK;
-}
-
-// Which scheduler renders a call. The persistent kernel serves the single-stage samplers; traversal counting needs the
-// wavefront's counting extend kernel, and the multi-stage samplers (pathdirect / pathmis: light-pdf and shadow-ray
-// stages that re-enter the shading ring) run on the wavefront scheduler whatever the mode says - on the persistent
-// one they were seen to depend on timing (a resumed pathmis batch differed from the reference under
-// compute-sanitizer), so until that is understood the mode does not apply to them.
 static int run_render(ygl_context* ctx, ygl_state* state, const ygl_trace_params& params, int nsamples) {
-  const bool multi_stage = params.sampler == YGL_SAMPLER_PATHDIRECT || params.sampler == YGL_SAMPLER_PATHMIS;
-  if (ctx->mode == YGL_MODE_PERSISTENT && !ctx->count_traversal && !multi_stage)
-    return run_persistent(ctx, state, params, nsamples);
   return run_wavefront(ctx, state, params, nsamples);
 }
 
@@ -1277,7 +1195,7 @@ static int worker_join(ygl_context* ctx) {
 }
 int ygl_trace_cancel(ygl_context* ctx) {
   if (!ctx) return fail(YGL_ERR_INVALID, "null context");
-  ctx->stop = 1;  // polled between wavefront iterations (wavefront mode) / raises the abort flag (persistent mode)
+  ctx->stop = 1;  // polled by the host between rounds of wavefront iterations
   int rc    = worker_join(ctx);
   ctx->stop = 0;
   return rc;
@@ -1328,45 +1246,35 @@ int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]) {
 }
 int ygl_context_set_mode(ygl_context* ctx, int mode) {
   if (!ctx) return fail(YGL_ERR_INVALID, "null context");
+  // YGL_MODE_PERSISTENT named round 1's single-kernel scheduler, which no longer exists; the value is still accepted
+  // (results never depended on the mode) and selects the wavefront scheduler
   if (mode != YGL_MODE_WAVEFRONT && mode != YGL_MODE_PERSISTENT) return fail(YGL_ERR_INVALID, "unknown mode");
-  ctx->mode = mode;
+  ctx->mode = YGL_MODE_WAVEFRONT;
   return YGL_OK;
 }
 
 namespace {
 struct OptionRef {
   const char* name;
-  int Tuning::*  i;
-  double Tuning::* d;
+  int Tuning::*field;
 };
 const OptionRef kOptions[] = {
-    {"ext_blocks_per_sm", &Tuning::ext_blocks_per_sm, nullptr}, {"refill", &Tuning::refill, nullptr},
-    {"node_reps", &Tuning::node_reps, nullptr}, {"suspend", &Tuning::suspend, nullptr},
-    {"suspend_rounds", &Tuning::suspend_rounds, nullptr}, {"lone", &Tuning::lone, nullptr},
-    {"lone_steps", &Tuning::lone_steps, nullptr}, {"fuse", &Tuning::fuse, nullptr}, {"bin", &Tuning::bin, nullptr},
-    {"pipes", &Tuning::pipes, nullptr}, {"graph", &Tuning::graph, nullptr}, {"top_smem", &Tuning::top_smem, nullptr},
-    {"persist_blocks_per_sm", &Tuning::persist_blocks_per_sm, nullptr},
-    {"persist_ext_sms", &Tuning::persist_ext_sms, nullptr}, {"persist_lpdf_warps", &Tuning::persist_lpdf_warps, nullptr},
-    {"watchdog_s", nullptr, &Tuning::watchdog_s},
+    {"ext_blocks_per_sm", &Tuning::ext_blocks_per_sm}, {"refill", &Tuning::refill}, {"node_reps", &Tuning::node_reps},
+    {"suspend", &Tuning::suspend}, {"suspend_rounds", &Tuning::suspend_rounds}, {"lone", &Tuning::lone},
+    {"lone_steps", &Tuning::lone_steps}, {"fuse", &Tuning::fuse}, {"bin", &Tuning::bin}, {"pipes", &Tuning::pipes},
+    {"graph", &Tuning::graph}, {"top_smem", &Tuning::top_smem},
 };
 }  // namespace
 int ygl_context_set_option(ygl_context* ctx, const char* name, double value) {
   if (!ctx || !name) return fail(YGL_ERR_INVALID, "null argument");
   for (auto& o : kOptions)
-    if (!strcmp(o.name, name)) {
-      if (o.i) ctx->tune.*(o.i) = (int)value;
-      else ctx->tune.*(o.d) = value;
-      return YGL_OK;
-    }
+    if (!strcmp(o.name, name)) return ctx->tune.*(o.field) = (int)value, YGL_OK;
   return fail(YGL_ERR_INVALID, std::string("unknown option: ") + name);
 }
 int ygl_context_get_option(ygl_context* ctx, const char* name, double* value) {
   if (!ctx || !name || !value) return fail(YGL_ERR_INVALID, "null argument");
   for (auto& o : kOptions)
-    if (!strcmp(o.name, name)) {
-      *value = o.i ? (double)(ctx->tune.*(o.i)) : ctx->tune.*(o.d);
-      return YGL_OK;
-    }
+    if (!strcmp(o.name, name)) return *value = (double)(ctx->tune.*(o.field)), YGL_OK;
   return fail(YGL_ERR_INVALID, std::string("unknown option: ") + name);
 }
 

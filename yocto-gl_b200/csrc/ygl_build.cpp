@@ -216,8 +216,10 @@ void pack_instance(float4h* out, const ygl_instance& inst, int id, int kind, int
   out[3]     = {as_float(inst.shape), as_float(id), as_float(kind), as_float(num_nodes)};
   out[4]     = {0, 0, 0, 0};  // device pointers of the shape's tree: patched at upload (ygl_api.cpp)
   out[5]     = {0, 0, 0, 0};
-  out[6]     = root[0];  // the root node of the shape's tree (object space): entering an instance tests it without
-  out[7]     = root[1];  // another dependent load; with it the packet is exactly one 128-byte line
+  if (kInstancePacketQuads == 8) {  // pair-visit build only: the root node of the shape's tree (object space), so that
+    out[6] = root[0];               // entering an instance tests it without another dependent load
+    out[7] = root[1];
+  }
 }
 
 }  // namespace

@@ -20,7 +20,11 @@ struct float4h {
   float x, y, z, w;
 };
 constexpr int kMaxTreeDepth        = 128;  // levels per tree the device walk accepts = the reference's stack (yocto_bvh.cpp:469)
-constexpr int kInstancePacketQuads = 8;  // float4 per DInstancePacket (ygl_scene.cuh): one 128-byte line
+#ifdef YGL_PAIR_VISIT
+constexpr int kInstancePacketQuads = 8;  // float4 per DInstancePacket (ygl_scene.cuh): + the shape's root node
+#else
+constexpr int kInstancePacketQuads = 6;  // float4 per DInstancePacket (ygl_scene.cuh)
+#endif
 constexpr int kMaxTreeNodes        = 1 << 28, kMaxTreePrims = 1 << 26;  // ranges of the device node words
 
 struct HostBvh {

@@ -11,8 +11,9 @@
 // k_finish, linked by compacted lane queues. Every kernel is persistent-style: a fixed grid (multiple of the SM count) strides over the queue whose
 // length it reads from device memory, so the host never synchronises inside the sample loop. Survivors are appended
 // to the next queue with one atomicAdd per warp (__ballot_sync + __popc + __shfl_sync).
-// Persistent scheduler (opt-in): k_persistent, one resident kernel with SM-specialised stages linked by ticket ring
-// queues (see the block comment above it). Compiled with -fmad=false: see ygl_math.cuh.
+// (A second scheduler - one resident kernel with SM-specialised stages linked by ring queues - existed in round 1; it
+// was slower than the wavefront on every tile size and its results turned out to depend on timing, so it was
+// removed: DESIGN.md §3.3.) Compiled with -fmad=false: see ygl_math.cuh.
 #include <algorithm>
 #include <cstdlib>
 
@@ -219,7 +220,7 @@ struct ExtendSource {
 #ifndef YGL_EXT_MINBLOCKS
 #define YGL_EXT_MINBLOCKS 7  // measured on B200 (C3): 4/5/6/7/8 blocks/SM -> 249/249/233/224/227 ms per 32 spp
 #endif
-template <bool COUNT, int TAIL, bool DEEP>
+template <bool COUNT, int TAIL, bool DEEP, bool TOP = false>
 __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene, PathState st, Queues q, int parity,
     unsigned long long* trav, int refill_thr, int node_reps, int suspend_below, int lone_below, int lone_steps) {
   Counters*     c = q.counters;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene,
   ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, q, parity, scene.inst_class, scene.has_volumes, 0, refill_thr,
       node_reps, suspend_below, lone_below, lone_steps, 0, false};
   trav_counters tc = {};
-  trace_stream<COUNT, kStreamThreads, kSharedStack, DEEP>(scene, src, tc);
+  trace_stream<COUNT, kStreamThreads, kSharedStack, DEEP, ExtendSource<TAIL>, TOP>(scene, src, tc);
   {
     unsigned v = src.finished;
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFullWarp, v, off);
@@ -1081,7 +1082,6 @@ YGL_D bool accumulate_lane(const DScene& scene, const PS& st, const KParams& p, 
   float  w   = 1.0f / (sample + 1);
   float4 im4 = st.image[lane];
   f4     image  = {im4.x, im4.y, im4.z, im4.w};
-  // plain loads (not __ldg): in persistent mode the lane's accumulators may have been written on another SM
   f3     albedo = {st.albedo[3 * lane + 0], st.albedo[3 * lane + 1], st.albedo[3 * lane + 2]};
   f3     normal = {st.normal[3 * lane + 0], st.normal[3 * lane + 1], st.normal[3 * lane + 2]};
   f3     n0     = unpack3(st.normal0[lane]);
@@ -1164,261 +1164,6 @@ __global__ void __launch_bounds__(256) k_finish(DScene scene, PathState st, Queu
   flush_counts(c, counts);
 }
 
-
-// ==========================================================================================
-// Persistent mode. ONE kernel renders a whole batch: every block hosts traversal warps (trace_stream fed by the
-// extend ring), shading warps (shade -> accumulate -> next camera sample) and light-pdf warps, linked by ring
-// queues in global memory, so lanes flow from stage to stage without kernel boundaries: no drain tail per
-// wavefront iteration, no launch gaps, no host polling.
-//
-// Ring protocol (ticket queue, no CAS - a CAS-claimed head lets one of thousands of contending warps win per L2
-// round trip): a producer reserves an index with one atomicAdd on `tail` per warp and publishes the entry into
-// slot[index]; a consumer lane takes a ticket with one atomicAdd on `head` per warp and polls slot[ticket] - its
-// own address, so waiting never hammers a shared cache line. A ticket may run ahead of the producers; the lane
-// simply waits for its slot. Every ring has dedicated consumers in every block, and producers never wait
-// (except for the wrap-around guard), so there is no cyclic wait; warps leave when all lanes are done.
-//
-// Memory model: a lane's state is written by one warp and read by another, possibly on another SM. All state
-// loads go through SArr (ld.global.cg, served by L2 where every store lands); read-only scene data keeps its
-// L1 residency. A producer publishes with st.release.gpu (its state writes are performed first); the consumer's
-// state loads depend on the slot value (address dependency), so no acquire fence - which would invalidate the
-// SM's whole L1, BVH nodes included (CCTL.IVALL) - is needed.
-// ==========================================================================================
-YGL_D int ld_relaxed(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-YGL_D void st_relaxed(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-YGL_D void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
-// WARP-UNIFORM: lanes with `pred` reserve one slot each (null otherwise). The caller publishes with ring_publish.
-YGL_D int* ring_reserve(const Ring& r, bool pred) {
-  const unsigned m = __ballot_sync(kFullWarp, pred);
-  if (!m) return nullptr;
-  const int wl = threadIdx.x & 31, leader = __ffs(m) - 1;
-  unsigned  base = 0;
-  if (wl == leader) base = atomicAdd(r.tail, (unsigned)__popc(m));
-  base = __shfl_sync(kFullWarp, base, leader);
-  return pred ? r.slots + ((base + __popc(m & ((1u << wl) - 1u))) & r.mask) : nullptr;
-}
-YGL_D void ring_publish(int* slot, int value, int* abort) {
-  // wrap-around guard: the slot's previous entry (one ring capacity ago) must have been taken. Practically never
-  // spins: the capacity exceeds the number of lanes, each of which sits in at most one ring.
-  int spins = 0;
-  while (ld_relaxed(slot) != -1)
-    if (++spins > (1 << 22)) {
-      st_relaxed(abort, 1);
-      break;
-    }
-  st_release(slot, value);
-}
-YGL_D void ring_push(const Ring& r, bool pred, int value, int* abort) {
-  int* slot = ring_reserve(r, pred);
-  if (slot) ring_publish(slot, value, abort);
-}
-// WARP-UNIFORM, NON-BLOCKING: lanes with `want` that hold no ticket take one; every ticket holder then looks
-// at its slot once. Returns true for lanes that received an entry (their ticket is used up).
-YGL_D bool ring_take(const Ring& r, bool want, unsigned& ticket, bool& held, int& entry) {
-  const unsigned m = __ballot_sync(kFullWarp, want && !held);
-  if (m) {
-    const int wl = threadIdx.x & 31, leader = __ffs(m) - 1;
-    unsigned  base = 0;
-    if (wl == leader) base = atomicAdd(r.head, (unsigned)__popc(m));
-    base = __shfl_sync(kFullWarp, base, leader);
-    if (want && !held) ticket = base + __popc(m & ((1u << wl) - 1u)), held = true;
-  }
-  if (!(want && held)) return false;
-  int*      slot = r.slots + (ticket & r.mask);
-  const int v    = ld_relaxed(slot);
-  if (v == -1) return false;
-  st_relaxed(slot, -1);
-  held  = false;
-  entry = v;
-  return true;
-}
-
-struct RingSource {
-  PQueues    q;
-  PathStateC st;
-  int       lane, total;
-  int       refill_thr, node_reps, suspend_below, lone_below, lone_steps;
-  unsigned  finished, taken, ticket;
-  bool      shadow, held;
-  static constexpr bool kPolling = true;  // the ring is fed by other warps while this one runs
-  static constexpr bool kPark = false, kLone = false;  // no launch boundary, no tail
-  YGL_D bool fetch(bool idle, f3& o, f3& d, bool& more, bool& resume) {
-    resume     = false;
-    int  entry = 0;
-    const bool got = ring_take(q.ext, idle, ticket, held, entry);
-    if (!__any_sync(kFullWarp, got)) {
-      // nothing arrived: the job may be over
-      if (ld_relaxed(&q.counters->done_lanes) >= total || ld_relaxed(q.abort)) more = false;
-    }
-    if (!got) return false;
-    lane     = entry & kEntryLane;
-    shadow   = (entry & kEntryShadow) != 0;
-    float4 a = shadow ? st.aux_o[lane] : st.ray_o[lane], b = shadow ? st.aux_dir[lane] : st.ray_d[lane];
-    o = unpack3(a), d = unpack3(b);
-    taken++;
-    return true;
-  }
-  YGL_D void commit_finished(bool flag, const hit_t& h) {
-    if (flag) {
-      (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
-      (shadow ? st.aux_ids : st.hit_ids)[lane] = make_int2(h.instance, h.element);
-      finished++;
-    }
-    ring_push(q.shade, flag, lane, q.abort);
-  }
-  YGL_D int*       save_slot() { return nullptr; }  // never used: rays are not parked in persistent mode
-  YGL_D const int* load_slot() { return nullptr; }
-  YGL_D void       commit_suspended() {}
-};
-
-// Send a shaded lane on (WARP-UNIFORM). A finished path is accumulated here and the lane's next camera sample
-// starts at once; a lane that needs no ray this round (kEntryPass) goes straight back to the shade ring.
-template <bool USES_LPDF, class PS>
-YGL_D void route_lane(const DScene& scene, const PS& st, const PQueues& q, const KParams& p, int lane, int dest,
-    int out) {
-  bool to_shade = dest == kDestExt && (out & kEntryPass) != 0;
-  bool to_ext   = dest == kDestExt && !to_shade;
-  bool started = false, ended = false;
-  if (dest == kDestAcc) {
-    if (accumulate_lane(scene, st, p, lane)) {
-      generate_lane(scene, st, p, lane);
-      to_ext = started = true;
-      out    = lane;
-    } else {
-      ended = true;
-    }
-  }
-  const unsigned ms = __ballot_sync(kFullWarp, started), me = __ballot_sync(kFullWarp, ended);
-  if ((threadIdx.x & 31) == 0) {
-    if (ms) atomicAdd(&q.counters->camera_samples, (unsigned long long)__popc(ms));
-    if (me) atomicAdd(&q.counters->done_lanes, __popc(me));
-  }
-  // one release store per lane, whatever its destination ring (a single MEMBAR for the warp)
-  int* slot = ring_reserve(q.ext, to_ext);
-  int* s1   = ring_reserve(q.shade, to_shade);
-  if (s1) slot = s1, out = lane;
-  if (USES_LPDF) {
-    int* s2 = ring_reserve(q.lpdf, dest == kDestLpdf);
-    if (s2) slot = s2, out = lane;
-  }
-  if (slot) ring_publish(slot, out, q.abort);
-}
-
-enum : int { kRoleExt = 0, kRoleShade = 1, kRoleLpdf = 2 };
-#ifndef YGL_PERSIST_MINBLOCKS
-#define YGL_PERSIST_MINBLOCKS 2
-#endif
-// 12 warps per block, 2 blocks per SM. Roles are assigned per SM where possible (`sm_roles`): with traversal,
-// shading and light-pdf warps interleaved on one SM the combined code footprint thrashes the instruction caches
-// (ncu: 70 % of the stall samples were "no instruction"); SM-specialised blocks keep each SM's I-cache on one
-// stage's code, and lane state travels through L2 anyway.
-constexpr int kPersistThreads = 384;
-
-template <int SAMPLER>
-__global__ void __launch_bounds__(kPersistThreads, YGL_PERSIST_MINBLOCKS) k_persistent(DScene scene, PathStateC st, PQueues q,
-    KParams p, int lane_lo, int lane_hi, int sample_begin, unsigned roles, int num_sms, int refill_thr, int node_reps) {
-  constexpr bool multi     = SAMPLER == kSamplerPathDirect || SAMPLER == kSamplerPathMis;
-  constexpr bool uses_lpdf = SAMPLER == kSamplerPath || SAMPLER == kSamplerPathTest || multi;
-  Counters* c     = q.counters;
-  const int wl    = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int total = lane_hi - lane_lo;
-  unsigned  inst_rays = 0, n_shade = 0, n_ext = 0;
-  // ---- first camera sample of every lane (dynamic chunks: only resident warps take part) ----
-  while (true) {
-    unsigned base = 0;
-    if (wl == 0) base = atomicAdd(q.seed_cursor, 32u);
-    base = __shfl_sync(kFullWarp, base, 0);
-    if (base >= (unsigned)total) break;
-    const bool valid = base + wl < (unsigned)total;
-    const int  lane  = lane_lo + (int)base + wl;
-    if (valid) {
-      st.sample[lane] = sample_begin;
-      generate_lane(scene, st, p, lane);
-    }
-    const unsigned mv = __ballot_sync(kFullWarp, valid);
-    if (wl == 0) atomicAdd(&c->camera_samples, (unsigned long long)__popc(mv));
-    ring_push(q.ext, valid, lane, q.abort);
-  }
-  // roles: bits 0..23 = per-warp pattern of a mixed block (2 bits per warp); bits 24..27 = traversal SMs per 10
-  // (0 = every block is mixed); bits 28..31 = light-pdf warps of a shading block
-  int role;
-  const int ext_tenths = (roles >> 24) & 15, lpdf_warps = (roles >> 28) & 15;
-  if (ext_tenths == 0 || gridDim.x < 20) {
-    role = (roles >> (2 * warp)) & 3;
-  } else {
-    const int  slot   = (int)(blockIdx.x % (unsigned)num_sms);  // blocks i and i + num_sms share an SM (round-robin placement)
-    const bool ext_sm = slot % 10 < ext_tenths;
-    role              = ext_sm ? kRoleExt : (warp < lpdf_warps ? kRoleLpdf : kRoleShade);
-  }
-  if (role == kRoleLpdf && !uses_lpdf) role = kRoleShade;
-  unsigned backoff = 64;
-  if (role == kRoleExt) {
-    // ---- traversal warps ----
-    RingSource    src{q, st, 0, total, refill_thr, node_reps, 0, 0, 0, 0, 0, 0, false, false};
-    trav_counters tc = {};
-    while (true) {
-      const unsigned before = src.taken;
-      #ifdef YGL_PAIR_VISIT
-      trace_stream<false, kPersistThreads, 12, true>(scene, src, tc);
-#else
-      trace_stream<false, kPersistThreads, kSharedStack, true>(scene, src, tc);
-#endif
-      if (__any_sync(kFullWarp, src.taken != before)) {
-        backoff = 64;
-        continue;
-      }
-      if (ld_relaxed(&c->done_lanes) >= total || ld_relaxed(q.abort)) break;
-      __nanosleep(backoff);
-      backoff = min(backoff * 2, 4096u);
-    }
-    n_ext = src.finished;
-  } else {
-    // ---- shading / light-pdf warps: collect a full warp of lanes (or what arrived after a short wait) ----
-    const Ring& ring = role == kRoleLpdf ? q.lpdf : q.shade;
-    unsigned    ticket = 0;
-    bool        held = false, has = false;
-    int         entry = 0, waited = 0;
-    while (true) {
-      if (ring_take(ring, !has, ticket, held, entry)) has = true;
-      const int n_has = __popc(__ballot_sync(kFullWarp, has));
-      if (n_has == 32 || (n_has > 0 && waited >= 3)) {
-        int lane = has ? entry : 0, dest = kDestNone, out = 0;
-        if (role == kRoleLpdf) {
-          lightpdf_lane(scene, st, p, has, lane, inst_rays, dest, out);
-        } else if (has) {
-          int r = multi ? shade_multi<SAMPLER>(scene, st, p, lane) : shade_lane<SAMPLER>(scene, st, p, lane, inst_rays);
-          dest  = r & 3;
-          out   = lane | (r & (kEntryShadow | kEntryPass));
-          n_shade++;
-        }
-        route_lane<uses_lpdf>(scene, st, q, p, lane, dest, out);
-        has = false, waited = 0, backoff = 64;
-        continue;
-      }
-      if (n_has == 0 && (ld_relaxed(&c->done_lanes) >= total || ld_relaxed(q.abort))) break;
-      __nanosleep(backoff);
-      backoff = min(backoff * 2, 2048u);
-      waited++;
-    }
-  }
-  // ---- tallies ----
-  unsigned v0 = n_ext, v1 = inst_rays, v2 = n_shade;
-  for (int off = 16; off > 0; off >>= 1) {
-    v0 += __shfl_down_sync(kFullWarp, v0, off);
-    v1 += __shfl_down_sync(kFullWarp, v1, off);
-    v2 += __shfl_down_sync(kFullWarp, v2, off);
-  }
-  if (wl == 0) {
-    if (v0) atomicAdd(&c->scene_rays, (unsigned long long)v0);
-    if (v1) atomicAdd(&c->instance_rays, (unsigned long long)v1);
-    if (v2) atomicAdd(&c->shade_calls, (unsigned long long)v2);
-  }
-}
 
 // ---- batch form of intersect_scene_bvh / intersect_instance_bvh ----
 template <bool COUNT>
@@ -1518,51 +1263,24 @@ void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene
                                  : (trav ? k_extend<true, 0, true> : k_extend<false, 0, true>))
                      : (lone > 0 ? (trav ? k_extend<true, 1, false> : k_extend<false, 1, false>)
                                  : (trav ? k_extend<true, 0, false> : k_extend<false, 0, false>));
+#ifndef YGL_PAIR_VISIT
+  // A/B (tune.top_smem = 1): the instance-level tree staged in shared memory by a bulk asynchronous copy; only the
+  // variant the headline workload runs (timed, parked tail, shallow stack) has this instantiation
+  const size_t top_bytes = (size_t)scene.top_num_nodes * 32;
+  if (tune.top_smem > 0 && !trav && lone == 0 && !scene.deep_stack && top_bytes > 0 && top_bytes <= 24 * 1024) {
+    auto* top_kernel = k_extend<false, 0, false, true>;
+    int   top_per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&top_per_sm, top_kernel, 128, top_bytes);
+    int top_blocks = num_sms * std::max(1, tune.ext_blocks_per_sm > 0 ? std::min(top_per_sm, tune.ext_blocks_per_sm) : top_per_sm);
+    top_blocks     = std::max(1, std::min(top_blocks, needed));
+    top_kernel<<<top_blocks, 128, top_bytes, s>>>(scene, st, q, parity, trav, tune.refill, tune.node_reps, suspend, lone,
+        tune.lone_steps);
+    return;
+  }
+#endif
   kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, tune.refill, tune.node_reps, suspend, lone, tune.lone_steps);
 }
 
-template <int SAMPLER>
-static void launch_persistent_t(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, PQueues q,
-    KParams p, int lane_lo, int lane_hi, int sample_begin) {
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent<SAMPLER>, kPersistThreads, 0);
-  if (per_sm < 1) per_sm = 1;
-  if (tune.persist_blocks_per_sm > 0) per_sm = std::min(per_sm, tune.persist_blocks_per_sm);
-  int blocks = num_sms * per_sm;
-  // tiny tiles: no more warps than there are lanes to keep busy (every block hosts all roles)
-  const int needed = std::max(1, (lane_hi - lane_lo + 31) / 32 / 6);
-  blocks           = std::max(1, std::min(blocks, needed));
-  // roles of a mixed block (small grids): per warp E = traversal, S = shading, L = light pdf; on full grids SMs are
-  // specialised: persist_ext_sms of every 10 SMs run traversal warps only, the others shading warps with
-  // persist_lpdf_warps light-pdf warps per block
-  const int nw    = kPersistThreads / 32;
-  unsigned  roles = 0;
-  for (int w = 0; w < nw; w++) roles |= (unsigned)(w % 4 < 2 ? kRoleExt : w % 4 == 2 ? kRoleShade : kRoleLpdf) << (2 * w);
-  const int ext_sms = std::max(0, std::min(9, tune.persist_ext_sms));
-  const int lw      = std::max(1, std::min(nw - 1, tune.persist_lpdf_warps));
-  roles |= (unsigned)ext_sms << 24 | (unsigned)lw << 28;
-  PathStateC stc;  // same layout, coherent loads (see SArr)
-  memcpy(&stc, &st, sizeof(stc));
-  k_persistent<SAMPLER><<<blocks, kPersistThreads, 0, s>>>(scene, stc, q, p, lane_lo, lane_hi, sample_begin, roles,
-      num_sms, tune.refill, tune.node_reps);
-}
-void launch_persistent(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, PQueues q, KParams p,
-    int lane_lo, int lane_hi, int sample_begin) {
-#define YGL_PERSIST_CASE(S) \
-  case S: launch_persistent_t<S>(s, num_sms, tune, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-  switch (p.sampler) {
-    YGL_PERSIST_CASE(kSamplerPath)
-    YGL_PERSIST_CASE(kSamplerPathDirect)
-    YGL_PERSIST_CASE(kSamplerPathMis)
-    YGL_PERSIST_CASE(kSamplerPathTest)
-    YGL_PERSIST_CASE(kSamplerNaive)
-    YGL_PERSIST_CASE(kSamplerEyelight)
-    YGL_PERSIST_CASE(kSamplerDiagram)
-    YGL_PERSIST_CASE(kSamplerFurnace)
-    default: launch_persistent_t<kSamplerFalsecolor>(s, num_sms, tune, scene, st, q, p, lane_lo, lane_hi, sample_begin); break;
-  }
-#undef YGL_PERSIST_CASE
-}
 template <int CLS>
 static void launch_shade_class(cudaStream_t s, int blocks, DScene scene, PathState st, Queues q, KParams p, int parity,
     unsigned class_mask) {

@@ -8,11 +8,9 @@
 
 namespace ygl {
 
-// Lane state is written by one warp and read by another. In the wavefront mode a kernel boundary lies in between
-// and plain loads are fine. In persistent mode the reader may sit on another SM inside the same kernel, and L1 is
-// not coherent across SMs: there every state LOAD must be ld.global.cg (served by L2, where all stores land). The
-// policy is part of the state's type (COH), so one set of stage functions serves both kernels and a missed load
-// cannot happen. Stores are plain (L1 is write-through). Read-only scene data keeps normal L1 caching.
+// Lane state is written by one kernel and read by the next: plain loads and stores. (COH = true turns every state
+// load into ld.global.cg; it served round 1's single-kernel scheduler, where reader and writer could sit on different
+// SMs inside one kernel, and is kept only as a debugging aid.)
 template <class T, bool COH>
 struct SRef {
   T* p;
@@ -83,9 +81,7 @@ struct PathStateT {
   SArr<float4, COH> next_uvd;  // pathmis next_intersection (persists across bounces)
   SArr<int2, COH>   next_ids;
 };
-using PathState  = PathStateT<false>;  // wavefront kernels, host
-using PathStateC = PathStateT<true>;   // persistent kernel: same layout, L1-bypassing loads
-static_assert(sizeof(PathState) == sizeof(PathStateC), "the two views of the lane state must share one layout");
+using PathState = PathStateT<false>;  // a kernel boundary separates every writer of lane state from its readers
 
 // Shading classes: the extend kernel appends every finished ray to the shade queue of its class, so that a shading
 // warp holds ONE kind of work (one material type, or misses) and each class gets a kernel that contains only its
@@ -115,22 +111,6 @@ struct Counters {
   unsigned long long camera_samples, scene_rays, instance_rays, shade_calls;
 };
 
-// ---- persistent mode: ring queues shared by the role-specialised warps of ONE resident kernel ----
-// A ring holds lane ids (extend ring: lane | kEntryShadow). Its capacity (a power of two >= the number of lanes)
-// can never overflow: a lane is in at most one ring at a time. Empty slots hold -1.
-struct Ring {
-  int*      slots;
-  unsigned* head;  // next index to consume (monotonic)
-  unsigned* tail;  // next index to produce (monotonic)
-  unsigned  mask;  // capacity - 1
-};
-struct PQueues {
-  Ring      ext, shade, lpdf;
-  Counters* counters;
-  unsigned* seed_cursor;  // lanes handed out for their first camera sample
-  int*      abort;        // set by the watchdog (host or device): every warp leaves
-};
-
 struct KParams {  // trace_params subset used on device (yocto_trace.h:95-113)
   int   camera, sampler, falsecolor, bounces;
   float clamp;
@@ -158,8 +138,6 @@ struct Tuning {
   int pipes             = 1;  // independent wavefront pipelines (streams) per state
   int graph             = -1; // submit iterations as a CUDA graph (1/0; -1 = by tile size)
   int top_smem          = -1; // extend: stage the instance-level tree in shared memory with a bulk async copy (1/0; -1 = default)
-  int persist_blocks_per_sm = 0, persist_ext_sms = 6, persist_lpdf_warps = 4;  // persistent mode (see k_persistent)
-  double watchdog_s     = 20.0;  // persistent mode: abort after this long without progress
 };
 
 void launch_begin_iteration(cudaStream_t s, Queues q, int parity);
@@ -177,9 +155,6 @@ void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Que
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
 // accumulate the finished paths of q.acc and start each lane's next camera sample (used when p.fuse == 0)
 void launch_finish(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity);
-// persistent mode: one launch renders samples [sample_begin, p.sample_end) of lanes [lane_lo, lane_hi)
-void launch_persistent(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene, PathState st, PQueues q, KParams p,
-    int lane_lo, int lane_hi, int sample_begin);
 
 // batch intersect (test hook + traversal micro-benchmark). counters may be null.
 void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const float4* rays, long long n, int instance,

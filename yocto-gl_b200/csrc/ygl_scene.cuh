@@ -14,8 +14,8 @@
 //       point    1 x float4 {p,r}
 //     (e1/e2 are pure functions of the inputs evaluated with the reference's own rounding, so
 //      precomputing them cannot change a result bit.)
-//   * instances as 8 x float4 packets = one 128-byte line {inverse frame (12 floats), shape, instance, kind,
-//     #nodes, node/packet/primitive pointers of the shape's tree, the root node of that tree}: the
+//   * instances as 6 x float4 packets {inverse frame (12 floats), shape, instance, kind, #nodes,
+//     node/packet/primitive pointers of the shape's tree} (8 with the tree's root node in the pair-visit build): the
 //     reference recomputes inverse(frame, true) per instance visit (yocto_bvh.cpp:602); it is a
 //     pure function of the frame, so it is evaluated once on the host with the same arithmetic.
 //   * original element/vertex arrays (reference layout) for the shading-side eval_* functions.
@@ -53,10 +53,16 @@ struct DShape {
   int          num_points, num_lines, num_triangles, num_quads;
 };
 
-struct __align__(128) DInstancePacket {  // 128 B = 8 x LDG.128 of one line, no dependent load to reach the shape's tree
-  float4 q[8];  // q0-q2: inverse frame x,y,z,o (12 floats); q3: shape, instance, bvh kind, num nodes (int bits);
-                // q4: nodes pointer, leaf-packets pointer; q5: primitives pointer, -, -; q6-q7: the tree's root node
+#ifdef YGL_PAIR_VISIT
+struct __align__(128) DInstancePacket {  // 128 B = one line; q6-q7: the root node of the shape's tree
+  float4 q[8];
 };
+#else
+struct DInstancePacket {  // 96 B = 6 x LDG.128, no dependent load to reach the shape's tree
+  float4 q[6];  // q0-q2: inverse frame x,y,z,o (12 floats); q3: shape, instance, bvh kind, num nodes (int bits);
+                // q4: nodes pointer, leaf-packets pointer; q5: primitives pointer, -, -
+};
+#endif
 
 struct DInstance {  // shading side: forward frame + ids (instance_data, yocto_scene.h:145)
   frame3 frame;

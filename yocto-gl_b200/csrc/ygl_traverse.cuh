@@ -346,9 +346,37 @@ constexpr int kSuspendBelow    = 8;    // suspend a drained warp's stragglers on
 // DEEP: stack capacity for trees up to the reference's 128 levels per level of the hierarchy (a 1 KB local array per
 // thread: its mere presence in the frame costs the kernel ~8 % through L1 pressure); !DEEP: kShallowStack entries,
 // chosen by the host when the bound scene's trees fit (DScene::deep_stack).
-template <bool COUNT, int THREADS, int SHARED, bool DEEP, class Source>
+// TOP: the instance-level tree is staged once per block into (dynamic) shared memory with one bulk asynchronous copy
+// (cp.async.bulk + mbarrier, the TMA engine's 1-D path) and its nodes are then read with LDS instead of through L1.
+// BASELINE.json's north_star names this staging; measured on B200 it is an A/B, not the default.
+template <bool COUNT, int THREADS, int SHARED, bool DEEP, class Source, bool TOP = false>
 YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   constexpr int kSharedStack = SHARED;
+  extern __shared__ __align__(16) float4 s_top[];  // TOP only: top_num_nodes x 2 float4 (dynamic shared memory)
+  if (TOP) {
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned bar   = (unsigned)__cvta_generic_to_shared(&s_bar);
+    const unsigned dst   = (unsigned)__cvta_generic_to_shared(s_top);
+    const unsigned bytes = (unsigned)scene.top_num_nodes * 32u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(scene.top_nodes), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+    unsigned ready = 0;
+    while (!ready)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ready)
+          : "r"(bar), "r"(0u)
+          : "memory");
+  }
   // Traversal stack: the first kSharedStack entries of every lane live in shared memory, laid out
   // [entry][thread] so a lane always hits its own bank (conflict-free whatever the lanes' depths are);
   // deeper entries spill to a per-thread local array (rare: kSharedStack covers a 1000-instance tree
@@ -431,7 +459,9 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   int cur = kMarkDone, leaf_next = 0, leaf_end = 0, rounds = 0, poll_wait = 0, poll_gap = kPollInterval;
   // one node visit of the lane's walk (cur >= 0)
   auto visit_node = [&]() {
-    float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
+    float4 n0, n1;
+    if (TOP && !bottom) n0 = s_top[2 * cur], n1 = s_top[2 * cur + 1];
+    else n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
     if (COUNT) {
       if (bottom) cnt.bot_nodes++;
       else cnt.top_nodes++;

@@ -54,7 +54,7 @@ YGL_D bool slab_test_t0(const f3& o, const f3& dinv, float tmin, float tmax, con
   return t0 <= t1;
 }
 
-template <bool COUNT, int THREADS, int SHARED, bool DEEP, class Source>  // (DEEP is not used: full-depth stack)
+template <bool COUNT, int THREADS, int SHARED, bool DEEP, class Source, bool TOP = false>  // (DEEP, TOP: not used here)
 YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   constexpr int kSharedStack = SHARED;  // entries of this instantiation (static shared memory is limited to 48 KB)
   // Traversal stack of (t0, work word) entries: the first kSharedStack entries of every lane live in shared memory,

@@ -93,8 +93,8 @@ struct b200_context {
   b200_context(const b200_context&)            = delete;
   b200_context& operator=(const b200_context&) = delete;
   ~b200_context() { ygl_context_destroy(handle); }
-  // scheduling only, results are identical: false = wavefront (default), true = one persistent kernel per call
-  void set_persistent(bool on) { check(ygl_context_set_mode(handle, on ? YGL_MODE_PERSISTENT : YGL_MODE_WAVEFRONT)); }
+  // scheduling knobs by name (never change a result): ygl_context_set_option
+  void set_option(const char* name, double value) { check(ygl_context_set_option(handle, name, value)); }
 };
 struct b200_scene {
   ygl_scene* handle = nullptr;

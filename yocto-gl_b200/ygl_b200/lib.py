@@ -252,7 +252,7 @@ class Context:
         return {k: int(v) for k, v in zip(names, c)}
 
     def set_mode(self, mode):
-        """'wavefront' (default) or 'persistent' (one resident kernel per call); results are bit-identical."""
+        """Kept for source compatibility: round 1's 'persistent' scheduler was removed, both names select the wavefront."""
         _check(self.lib.ygl_context_set_mode(self.h, {"wavefront": 0, "persistent": 1}[mode]))
 
     def trace_cancel(self):
