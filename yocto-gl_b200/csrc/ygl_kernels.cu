@@ -341,6 +341,9 @@ YGL_D float sample_lights_pdf(const DScene& scene, bool valid, const f3& positio
   return pdf;
 }
 
+// throughput update of a sampled direction: value / pdf of its lobe (one evaluation gives both)
+YGL_D f3 lobe_weight(const lobe_t& lobe) { return lobe.bsdfcos / lobe.pdf; }
+
 // tail of one trace_path iteration, yocto_trace.cpp:581-591 + the for-loop increment
 YGL_D int finish_bounce(f3& weight, int& bounce, rng_t& rng, const KParams& p) {
   if (is_zero(weight) || !vfinite(weight)) return kDestAcc;
@@ -509,8 +512,7 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
       if (is_delta(material)) {
         incoming = sample_delta(material, normal, outgoing, rand1f(rng));
         if (!is_zero(incoming)) {
-          weight = weight * (eval_delta(material, normal, outgoing, incoming) /
-                                sample_delta_pdf(material, normal, outgoing, incoming));
+          weight = weight * lobe_weight(delta_lobe(material, normal, outgoing, incoming));
           if (!(is_zero(weight) || !vfinite(weight))) {
             bounce += 1;
             if (bounce < imax(p.bounces, 4)) {
@@ -535,13 +537,11 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
         float rnl = rand1f(rng);
         incoming  = sample_bsdfcos(material, normal, outgoing, rnl, rn);
         if (!is_zero(incoming))
-          weight = weight * (eval_bsdfcos(material, normal, outgoing, incoming) /
-                                sample_bsdfcos_pdf(material, normal, outgoing, incoming));
+          weight = weight * lobe_weight(bsdf_lobe(material, normal, outgoing, incoming));
       } else {
         incoming = sample_delta(material, normal, outgoing, rand1f(rng));
         if (!is_zero(incoming))
-          weight = weight * (eval_delta(material, normal, outgoing, incoming) /
-                                sample_delta_pdf(material, normal, outgoing, incoming));
+          weight = weight * lobe_weight(delta_lobe(material, normal, outgoing, incoming));
       }
       dest = is_zero(incoming) ? kDestAcc : finish_bounce(weight, bounce, rng, p);
       if (SAMPLER == kSamplerFurnace && dot(normal, outgoing) * dot(normal, incoming) < 0) flags ^= kFlagVolume;
@@ -571,14 +571,12 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
         st.radiance[lane] = pack(radiance, flags);
         return kDestAcc;
       }
-      auto bsdfcos   = eval_bsdfcos(material, normal, outgoing, incoming);
-      auto bsdf_pdf  = sample_bsdfcos_pdf(material, normal, outgoing, incoming);
-      st.pend[lane]  = pack(bsdfcos, bsdf_pdf);
+      auto lobe      = bsdf_lobe(material, normal, outgoing, incoming);
+      st.pend[lane]  = pack(lobe.bsdfcos, lobe.pdf);
       dest           = kDestLpdf;
     } else {
       incoming = sample_delta(material, normal, outgoing, rand1f(rng));
-      weight   = weight * (eval_delta(material, normal, outgoing, incoming) /
-                            sample_delta_pdf(material, normal, outgoing, incoming));
+      weight   = weight * lobe_weight(delta_lobe(material, normal, outgoing, incoming));
     }
 
     // ---- volume slot update, yocto_trace.cpp:545-553 (independent of the pending weight) ----
@@ -623,7 +621,8 @@ YGL_D int shade_lane(const DScene& scene, const PS& st, const KParams& p, int la
     store_rng(st, lane, rng);
     st.radiance[lane] = pack(radiance, flags);
     if (is_zero(incoming)) return kDestAcc;
-    st.pend[lane]   = pack(eval_scattering(vsdf, outgoing, incoming), sample_scattering_pdf(vsdf, outgoing, incoming));
+    auto phase      = scattering_lobe(vsdf, outgoing, incoming);
+    st.pend[lane]   = pack(phase.bsdfcos, phase.pdf);
     st.ray_o[lane]  = pack(position, bounce);
     st.ray_d[lane]  = pack(incoming, opbounce);
     st.weight[lane] = pack(weight, max_roughness);
@@ -717,7 +716,8 @@ YGL_D int shade_multi(const DScene& scene, const PS& st, const KParams& p, int l
       if (MIS) flags &= ~kFlagNoEmission;  // next_emission = true
       store_common();
       if (!MIS && is_zero(incoming)) return kDestAcc;
-      st.pend[lane]     = pack(eval_scattering(vsdf, outgoing, incoming), sample_scattering_pdf(vsdf, outgoing, incoming));
+      auto phase        = scattering_lobe(vsdf, outgoing, incoming);
+      st.pend[lane]     = pack(phase.bsdfcos, phase.pdf);
       st.ray_o[lane]    = pack(position, bounce);
       st.ray_d[lane]    = pack(incoming, opbounce);
       st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseNextPdf);
@@ -765,12 +765,13 @@ YGL_D int shade_multi(const DScene& scene, const PS& st, const KParams& p, int l
       f3    dl  = sample_lights(scene, position, rl, rel, ruv);
       if (MIS && is_zero(dl)) {
         // `break` out of the sample loop: the indirect update then runs with incoming = 0 (yocto_trace.cpp:857, :892)
-        weight = weight * (eval_bsdfcos(material, normal, outgoing, dl) / sample_bsdfcos_pdf(material, normal, outgoing, dl));
+        weight = weight * lobe_weight(bsdf_lobe(material, normal, outgoing, dl));
         flags |= kFlagNoEmission;
         incoming = dl, have_next = true;
       } else {
-        auto bsdfcos = eval_bsdfcos(material, normal, outgoing, dl);
-        st.aux_o[lane]    = pack(position, MIS ? sample_bsdfcos_pdf(material, normal, outgoing, dl) : 0.0f);
+        auto light_lobe   = bsdf_lobe(material, normal, outgoing, dl);
+        auto bsdfcos      = light_lobe.bsdfcos;
+        st.aux_o[lane]    = pack(position, MIS ? light_lobe.pdf : 0.0f);
         st.aux_dir[lane]  = pack(dl, 0.0f);
         st.aux_bsdf[lane] = pack(bsdfcos, kPhaseDirectPdf);
         store_common();
@@ -797,12 +798,13 @@ YGL_D int shade_multi(const DScene& scene, const PS& st, const KParams& p, int l
       float rnl = rand1f(rng);
       f3    db  = sample_bsdfcos(material, normal, outgoing, rnl, rn);
       if (is_zero(db)) {
-        weight = weight * (eval_bsdfcos(material, normal, outgoing, db) / sample_bsdfcos_pdf(material, normal, outgoing, db));
+        weight = weight * lobe_weight(bsdf_lobe(material, normal, outgoing, db));
         flags |= kFlagNoEmission;
         incoming = db, have_next = true;
       } else {
-        auto bsdfcos = eval_bsdfcos(material, normal, outgoing, db);
-        st.aux_o[lane]    = pack(position, sample_bsdfcos_pdf(material, normal, outgoing, db));
+        auto bsdf_side    = bsdf_lobe(material, normal, outgoing, db);
+        auto bsdfcos      = bsdf_side.bsdfcos;
+        st.aux_o[lane]    = pack(position, bsdf_side.pdf);
         st.aux_dir[lane]  = pack(db, 0.0f);
         st.aux_bsdf[lane] = pack(bsdfcos, kPhaseBsdfPdf);
         store_common();
@@ -842,8 +844,8 @@ YGL_D int shade_multi(const DScene& scene, const PS& st, const KParams& p, int l
         store_common();
         return kDestAcc;
       }
-      st.pend[lane]     = pack(eval_bsdfcos(material, normal, outgoing, incoming),
-              sample_bsdfcos_pdf(material, normal, outgoing, incoming));
+      auto lobe         = bsdf_lobe(material, normal, outgoing, incoming);
+      st.pend[lane]     = pack(lobe.bsdfcos, lobe.pdf);
       st.aux_bsdf[lane] = pack(f3{0, 0, 0}, kPhaseNextPdf);
       dest              = kDestLpdf;
     } else {
@@ -852,8 +854,7 @@ YGL_D int shade_multi(const DScene& scene, const PS& st, const KParams& p, int l
         store_common();
         return kDestAcc;
       }
-      weight = weight * (eval_delta(material, normal, outgoing, incoming) /
-                            sample_delta_pdf(material, normal, outgoing, incoming));
+      weight = weight * lobe_weight(delta_lobe(material, normal, outgoing, incoming));
       if (MIS) flags &= ~kFlagNoEmission;  // next_emission = true
       dest = kDestNone;
     }

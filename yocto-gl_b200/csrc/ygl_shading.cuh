@@ -1,6 +1,16 @@
-// ygl_shading.cuh — Fresnel, GGX microfacet terms, BSDF lobes, transmittance and phase function.
-// Behavioural contract: libs/yocto/yocto_shading.h:303-1111 and the material dispatch of
-// libs/yocto/yocto_trace.cpp:166-335. Operation order follows the reference expressions.
+// ygl_shading.cuh — surface and volume scattering of the path tracer: one FUSED routine per material that returns
+// the cosine-weighted BSDF value AND the sampling pdf of a direction pair together (the integrator always wants both:
+// yocto_trace.cpp:528-529, :700-706, :892), plus the matching direction samplers.
+//
+// Behavioural contract: libs/yocto/yocto_shading.h:303-1111 (Fresnel, GGX distribution / masking, the lobes of the
+// eight material types, transmittance, Henyey-Greenstein phase function) and the dispatch of
+// libs/yocto/yocto_trace.cpp:166-335. Tolerance 0: every returned float equals the reference's bit for bit
+// (tests/test_lobes.py: 3.2 M random and edge-case direction pairs per run against the reference's own dispatchers).
+// That contract fixes the arithmetic of each formula — operand order, where a product is rounded, which branch
+// returns +0 — but not the program around it. What is shared here and computed once per call (the reference
+// evaluates it separately in eval_* and sample_*_pdf): the upward normal, the half vector, the Fresnel terms, the
+// GGX distribution D; `lobe_t` carries value and pdf out together. Identical subexpressions are pure functions of
+// the same inputs, so sharing them cannot change a bit.
 #pragma once
 
 #include "ygl_sampling.cuh"
@@ -20,28 +30,31 @@ struct mpoint {
   float scanisotropy, trdepth;
 };
 
-YGL_HD bool same_hemisphere(const f3& n, const f3& o, const f3& i) {  // shading.h:303
-  return dot(n, o) * dot(n, i) >= 0;
-}
-YGL_HD f3 up_normal_of(const f3& n, const f3& o) { return dot(n, o) <= 0 ? -n : n; }
+// value of bsdf * |cos| and the pdf with which the samplers below produce the incoming direction
+struct lobe_t {
+  f3    bsdfcos;
+  float pdf;
+};
+YGL_HD lobe_t no_lobe() { return {{0, 0, 0}, 0}; }
 
-// fresnel_schlick, shading.h:309-315
-// pow(x, 2.0f) in the reference (yocto_shading.h:907,952): g++ -O2 expands a constant exponent of 2 to
-// x * x, so the reference binary never calls powf there (glibc's powf(x, 2) differs from x * x by one ulp on
-// 0.07 % of inputs). Other exponents (5, 2.4, ...) stay libm calls.
+// pow(x, 2.0f) in the reference (yocto_shading.h:907,952): g++ -O2 expands a constant exponent of 2 to x * x, so the
+// reference binary never calls powf there (glibc's powf(x, 2) differs from x * x by one ulp on 0.07 % of inputs).
 YGL_HD float ysqr(float a) { return a * a; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fresnel (yocto_shading.h:309-376)
+// ---------------------------------------------------------------------------------------------------------------
 YGL_HD f3 fresnel_schlick(const f3& specular, const f3& normal, const f3& outgoing) {
   if (is_zero(specular)) return {0, 0, 0};
   auto cosine = dot(normal, outgoing);
   return specular + (1 - specular) * ypow(yclamp(1 - yabs(cosine), 0.0f, 1.0f), 5.0f);
 }
-// fresnel_dielectric, shading.h:318-338
 YGL_HD float fresnel_dielectric(float eta, const f3& normal, const f3& outgoing) {
   auto cosw  = yabs(dot(normal, outgoing));
   auto sin2  = 1 - cosw * cosw;
   auto eta2  = eta * eta;
   auto cos2t = 1 - sin2 / eta2;
-  if (cos2t < 0) return 1;
+  if (cos2t < 0) return 1;  // total internal reflection
   auto t0 = ysqrt(cos2t);
   auto t1 = eta * t0;
   auto t2 = eta * cosw;
@@ -49,7 +62,6 @@ YGL_HD float fresnel_dielectric(float eta, const f3& normal, const f3& outgoing)
   auto rp = (t0 - t2) / (t0 + t2);
   return (rs * rs + rp * rp) / 2;
 }
-// fresnel_conductor, shading.h:341-366
 YGL_HD f3 fresnel_conductor(const f3& eta, const f3& etak, const f3& normal, const f3& outgoing) {
   auto cosw = dot(normal, outgoing);
   if (cosw <= 0) return {0, 0, 0};
@@ -69,24 +81,27 @@ YGL_HD f3 fresnel_conductor(const f3& eta, const f3& etak, const f3& normal, con
   auto rp       = rs * (t3 - t4) / (t3 + t4);
   return (rp + rs) / 2;
 }
-// eta_to_reflectivity / reflectivity_to_eta, shading.h:369-376
 YGL_HD f3 eta_to_reflectivity(const f3& eta) { return ((eta - 1) * (eta - 1)) / ((eta + 1) * (eta + 1)); }
 YGL_HD f3 reflectivity_to_eta(const f3& reflectivity_) {
   auto reflectivity = vclamp(reflectivity_, 0.0f, 0.99f);
   return (1 + vsqrt(reflectivity)) / (1 - vsqrt(reflectivity));
 }
+// a metal's Fresnel term from its colour (the reflective lobes)
+YGL_HD f3 metal_fresnel(const f3& color, const f3& normal, const f3& direction) {
+  return fresnel_conductor(reflectivity_to_eta(color), {0, 0, 0}, normal, direction);
+}
 
-// microfacet_distribution (GGX branch), shading.h:409-425
-YGL_HD float microfacet_distribution(float roughness, const f3& normal, const f3& halfway) {
+// ---------------------------------------------------------------------------------------------------------------
+// GGX microfacets (the only distribution the lobes use; yocto_shading.h:409-480)
+// ---------------------------------------------------------------------------------------------------------------
+YGL_HD float ggx_distribution(float roughness, const f3& normal, const f3& halfway) {
   auto cosine = dot(normal, halfway);
   if (cosine <= 0) return 0;
   auto roughness2 = roughness * roughness;
   auto cosine2    = cosine * cosine;
-  return roughness2 /
-         (kPi * (cosine2 * roughness2 + 1 - cosine2) * (cosine2 * roughness2 + 1 - cosine2));
+  return roughness2 / (kPi * (cosine2 * roughness2 + 1 - cosine2) * (cosine2 * roughness2 + 1 - cosine2));
 }
-// microfacet_shadowing1 / shadowing (GGX), shading.h:428-456
-YGL_HD float microfacet_shadowing1(float roughness, const f3& normal, const f3& halfway, const f3& direction) {
+YGL_HD float ggx_masking1(float roughness, const f3& normal, const f3& halfway, const f3& direction) {
   auto cosine  = dot(normal, direction);
   auto cosineh = dot(halfway, direction);
   if (cosine * cosineh <= 0) return 0;
@@ -94,306 +109,219 @@ YGL_HD float microfacet_shadowing1(float roughness, const f3& normal, const f3& 
   auto cosine2    = cosine * cosine;
   return 2 * yabs(cosine) / (yabs(cosine) + ysqrt(cosine2 - roughness2 * cosine2 + roughness2));
 }
-YGL_HD float microfacet_shadowing(float roughness, const f3& normal, const f3& halfway, const f3& outgoing,
-    const f3& incoming) {
-  return microfacet_shadowing1(roughness, normal, halfway, outgoing) *
-         microfacet_shadowing1(roughness, normal, halfway, incoming);
+// the terms of one microfacet interaction, shared by the value and the pdf of a lobe
+struct ggx_t {
+  float D;      // distribution of normals at the half vector
+  float G;      // masking-shadowing of the pair
+  float hpdf;   // pdf of sampling that half vector (sample_microfacet_pdf: D * cos, +0 below the horizon)
+};
+YGL_HD ggx_t ggx_terms(float roughness, const f3& normal, const f3& halfway, const f3& outgoing, const f3& incoming) {
+  ggx_t t;
+  t.D = ggx_distribution(roughness, normal, halfway);
+  t.G = ggx_masking1(roughness, normal, halfway, outgoing) * ggx_masking1(roughness, normal, halfway, incoming);
+  auto cosine = dot(normal, halfway);
+  t.hpdf      = cosine < 0 ? 0.0f : t.D * cosine;
+  return t;
 }
-// sample_microfacet(roughness, normal, rn) (GGX), shading.h:459-472
-YGL_HD f3 sample_microfacet(float roughness, const f3& normal, const f2& rn) {
+// a half vector drawn from the GGX distribution around `normal` (sample_microfacet, yocto_shading.h:459-472)
+YGL_HD f3 ggx_sample(float roughness, const f3& normal, const f2& rn) {
   auto phi   = 2 * kPi * rn.x;
   auto theta = yatan(roughness * ysqrt(rn.y / (1 - rn.y)));
   auto local = f3{ycos(phi) * ysin(theta), ysin(phi) * ysin(theta), ycos(theta)};
   return transform_direction(basis_fromz(normal), local);
 }
-// sample_microfacet_pdf, shading.h:475-480
-YGL_HD float sample_microfacet_pdf(float roughness, const f3& normal, const f3& halfway) {
-  auto cosine = dot(normal, halfway);
-  if (cosine < 0) return 0;
-  return microfacet_distribution(roughness, normal, halfway) * cosine;
-}
 
-// ---- matte, shading.h:554-574 ----
-YGL_HD f3 eval_matte(const f3& color, const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return {0, 0, 0};
-  return color / kPi * yabs(dot(n, i));
-}
-YGL_HD f3 sample_matte(const f3& n, const f3& o, const f2& rn) {
-  return sample_hemisphere_cos(up_normal_of(n, o), rn);
-}
-YGL_HD float sample_matte_pdf(const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return 0;
-  return sample_hemisphere_cos_pdf(up_normal_of(n, o), i);
-}
+YGL_HD bool same_side(const f3& n, const f3& o, const f3& i) { return dot(n, o) * dot(n, i) >= 0; }
+YGL_HD f3   facing(const f3& n, const f3& o) { return dot(n, o) <= 0 ? -n : n; }  // the normal on the side of `o`
 
-// ---- glossy, shading.h:577-619 ----
-YGL_HD f3 eval_glossy(const f3& color, float ior, float roughness, const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return {0, 0, 0};
-  auto up      = up_normal_of(n, o);
-  auto F1      = fresnel_dielectric(ior, up, o);
-  auto halfway = normalize(i + o);
-  auto F       = fresnel_dielectric(ior, halfway, i);
-  auto D       = microfacet_distribution(roughness, up, halfway);
-  auto G       = microfacet_shadowing(roughness, up, halfway, o, i);
-  return color * (1 - F1) / kPi * yabs(dot(up, i)) +
-         f3{1, 1, 1} * F * D * G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i));
-}
-YGL_HD f3 sample_glossy(float ior, float roughness, const f3& n, const f3& o, float rnl, const f2& rn) {
-  auto up = up_normal_of(n, o);
-  if (rnl < fresnel_dielectric(ior, up, o)) {
-    auto halfway  = sample_microfacet(roughness, up, rn);
-    auto incoming = reflect(o, halfway);
-    if (!same_hemisphere(up, o, incoming)) return {0, 0, 0};
-    return incoming;
-  } else {
-    return sample_hemisphere_cos(up, rn);
-  }
-}
-YGL_HD float sample_glossy_pdf(float ior, float roughness, const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return 0;
-  auto up      = up_normal_of(n, o);
-  auto halfway = normalize(o + i);
-  auto F       = fresnel_dielectric(ior, up, o);
-  return F * sample_microfacet_pdf(roughness, up, halfway) / (4 * yabs(dot(o, halfway))) +
-         (1 - F) * sample_hemisphere_cos_pdf(up, i);
-}
-
-// ---- reflective (rough), shading.h:622-654 ----
-YGL_HD f3 eval_reflective(const f3& color, float roughness, const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return {0, 0, 0};
-  auto up      = up_normal_of(n, o);
-  auto halfway = normalize(i + o);
-  auto F       = fresnel_conductor(reflectivity_to_eta(color), {0, 0, 0}, halfway, i);
-  auto D       = microfacet_distribution(roughness, up, halfway);
-  auto G       = microfacet_shadowing(roughness, up, halfway, o, i);
-  return F * D * G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i));
-}
-YGL_HD f3 sample_reflective(float roughness, const f3& n, const f3& o, const f2& rn) {
-  auto up       = up_normal_of(n, o);
-  auto halfway  = sample_microfacet(roughness, up, rn);
+// a reflected direction sampled through a GGX half vector; zero when it leaves the hemisphere of `up`
+YGL_HD f3 ggx_reflect(float roughness, const f3& up, const f3& o, const f2& rn) {
+  auto halfway  = ggx_sample(roughness, up, rn);
   auto incoming = reflect(o, halfway);
-  if (!same_hemisphere(up, o, incoming)) return {0, 0, 0};
+  if (!same_side(up, o, incoming)) return {0, 0, 0};
   return incoming;
 }
-YGL_HD float sample_reflective_pdf(float roughness, const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return 0;
-  auto up      = up_normal_of(n, o);
-  auto halfway = normalize(o + i);
-  return sample_microfacet_pdf(roughness, up, halfway) / (4 * yabs(dot(o, halfway)));
-}
-// ---- reflective (delta), shading.h:693-712 ----
-YGL_HD f3 eval_reflective_delta(const f3& color, const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return {0, 0, 0};
-  auto up = up_normal_of(n, o);
-  return fresnel_conductor(reflectivity_to_eta(color), {0, 0, 0}, up, o);
-}
-YGL_HD f3 sample_reflective_delta(const f3& n, const f3& o) { return reflect(o, up_normal_of(n, o)); }
-YGL_HD float sample_reflective_delta_pdf(const f3& n, const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return 0;
-  return 1;
-}
 
-// ---- gltfpbr, shading.h:736-788 ----
-YGL_HD f3 eval_gltfpbr(const f3& color, float ior, float roughness, float metallic, const f3& n, const f3& o,
+// ---------------------------------------------------------------------------------------------------------------
+// rough lobes: value and pdf together
+// ---------------------------------------------------------------------------------------------------------------
+// matte: Lambert (yocto_shading.h:554-574)
+YGL_HD lobe_t matte_lobe(const f3& color, const f3& n, const f3& o, const f3& i) {
+  if (dot(n, i) * dot(n, o) <= 0) return no_lobe();
+  return {color / kPi * yabs(dot(n, i)), sample_hemisphere_cos_pdf(facing(n, o), i)};
+}
+// glossy: dielectric coat over Lambert (yocto_shading.h:577-619)
+YGL_HD lobe_t glossy_lobe(const f3& color, float ior, float roughness, const f3& n, const f3& o, const f3& i) {
+  if (dot(n, i) * dot(n, o) <= 0) return no_lobe();
+  auto up      = facing(n, o);
+  auto F_view  = fresnel_dielectric(ior, up, o);  // also the probability of choosing the coat
+  auto halfway = normalize(i + o);
+  auto F       = fresnel_dielectric(ior, halfway, i);
+  auto ggx     = ggx_terms(roughness, up, halfway, o, i);
+  lobe_t lobe;
+  lobe.bsdfcos = color * (1 - F_view) / kPi * yabs(dot(up, i)) +
+                 f3{1, 1, 1} * F * ggx.D * ggx.G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i));
+  lobe.pdf = F_view * ggx.hpdf / (4 * yabs(dot(o, halfway))) + (1 - F_view) * sample_hemisphere_cos_pdf(up, i);
+  return lobe;
+}
+// reflective: rough metal (yocto_shading.h:622-654)
+YGL_HD lobe_t reflective_lobe(const f3& color, float roughness, const f3& n, const f3& o, const f3& i) {
+  if (dot(n, i) * dot(n, o) <= 0) return no_lobe();
+  auto up      = facing(n, o);
+  auto halfway = normalize(i + o);
+  auto F       = metal_fresnel(color, halfway, i);
+  auto ggx     = ggx_terms(roughness, up, halfway, o, i);
+  return {F * ggx.D * ggx.G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i)), ggx.hpdf / (4 * yabs(dot(o, halfway)))};
+}
+// gltfpbr: metallic-roughness (yocto_shading.h:736-788)
+YGL_HD lobe_t gltfpbr_lobe(const f3& color, float ior, float roughness, float metallic, const f3& n, const f3& o,
     const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return {0, 0, 0};
+  if (dot(n, i) * dot(n, o) <= 0) return no_lobe();
   auto reflectivity = lerp3(eta_to_reflectivity(f3{ior, ior, ior}), color, metallic);
-  auto up           = up_normal_of(n, o);
-  auto F1           = fresnel_schlick(reflectivity, up, o);
+  auto up           = facing(n, o);
+  auto F_view       = fresnel_schlick(reflectivity, up, o);
   auto halfway      = normalize(i + o);
   auto F            = fresnel_schlick(reflectivity, halfway, i);
-  auto D            = microfacet_distribution(roughness, up, halfway);
-  auto G            = microfacet_shadowing(roughness, up, halfway, o, i);
-  return color * (1 - metallic) * (1 - F1) / kPi * yabs(dot(up, i)) +
-         F * D * G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i));
+  auto ggx          = ggx_terms(roughness, up, halfway, o, i);
+  auto pick         = mean3(F_view);  // probability of the specular choice
+  lobe_t lobe;
+  lobe.bsdfcos = color * (1 - metallic) * (1 - F_view) / kPi * yabs(dot(up, i)) +
+                 F * ggx.D * ggx.G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i));
+  lobe.pdf = pick * ggx.hpdf / (4 * yabs(dot(o, halfway))) + (1 - pick) * sample_hemisphere_cos_pdf(up, i);
+  return lobe;
 }
-YGL_HD f3 sample_gltfpbr(const f3& color, float ior, float roughness, float metallic, const f3& n, const f3& o,
-    float rnl, const f2& rn) {
-  auto up           = up_normal_of(n, o);
-  auto reflectivity = lerp3(eta_to_reflectivity(f3{ior, ior, ior}), color, metallic);
-  if (rnl < mean3(fresnel_schlick(reflectivity, up, o))) {
-    auto halfway  = sample_microfacet(roughness, up, rn);
-    auto incoming = reflect(o, halfway);
-    if (!same_hemisphere(up, o, incoming)) return {0, 0, 0};
-    return incoming;
-  } else {
-    return sample_hemisphere_cos(up, rn);
-  }
-}
-YGL_HD float sample_gltfpbr_pdf(const f3& color, float ior, float roughness, float metallic, const f3& n,
-    const f3& o, const f3& i) {
-  if (dot(n, i) * dot(n, o) <= 0) return 0;
-  auto up           = up_normal_of(n, o);
-  auto halfway      = normalize(o + i);
-  auto reflectivity = lerp3(eta_to_reflectivity(f3{ior, ior, ior}), color, metallic);
-  auto F            = mean3(fresnel_schlick(reflectivity, up, o));
-  return F * sample_microfacet_pdf(roughness, up, halfway) / (4 * yabs(dot(o, halfway))) +
-         (1 - F) * sample_hemisphere_cos_pdf(up, i);
-}
-
-// ---- transparent (rough), shading.h:791-849 ----
-YGL_HD f3 eval_transparent(const f3& color, float ior, float roughness, const f3& n, const f3& o, const f3& i) {
-  auto up = up_normal_of(n, o);
+// transparent: thin dielectric sheet, transmission mirrored about the surface (yocto_shading.h:791-849)
+YGL_HD lobe_t transparent_lobe(const f3& color, float ior, float roughness, const f3& n, const f3& o, const f3& i) {
+  auto up = facing(n, o);
   if (dot(n, i) * dot(n, o) >= 0) {
     auto halfway = normalize(i + o);
     auto F       = fresnel_dielectric(ior, halfway, o);
-    auto D       = microfacet_distribution(roughness, up, halfway);
-    auto G       = microfacet_shadowing(roughness, up, halfway, o, i);
-    return f3{1, 1, 1} * F * D * G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i));
-  } else {
-    auto reflected = reflect(-i, up);
-    auto halfway   = normalize(reflected + o);
-    auto F         = fresnel_dielectric(ior, halfway, o);
-    auto D         = microfacet_distribution(roughness, up, halfway);
-    auto G         = microfacet_shadowing(roughness, up, halfway, o, reflected);
-    return color * (1 - F) * D * G / (4 * dot(up, o) * dot(up, reflected)) * (yabs(dot(up, reflected)));
+    auto ggx     = ggx_terms(roughness, up, halfway, o, i);
+    return {f3{1, 1, 1} * F * ggx.D * ggx.G / (4 * dot(up, o) * dot(up, i)) * yabs(dot(up, i)),
+        F * ggx.hpdf / (4 * yabs(dot(o, halfway)))};
   }
+  auto mirrored = reflect(-i, up);  // the transmitted direction folded back to the side of `o`
+  auto halfway  = normalize(mirrored + o);
+  auto F        = fresnel_dielectric(ior, halfway, o);
+  auto ggx      = ggx_terms(roughness, up, halfway, o, mirrored);
+  auto d        = (1 - F) * ggx.hpdf;
+  return {color * (1 - F) * ggx.D * ggx.G / (4 * dot(up, o) * dot(up, mirrored)) * (yabs(dot(up, mirrored))),
+      d / (4 * yabs(dot(o, halfway)))};
 }
-YGL_HD f3 sample_transparent(float ior, float roughness, const f3& n, const f3& o, float rnl, const f2& rn) {
-  auto up      = up_normal_of(n, o);
-  auto halfway = sample_microfacet(roughness, up, rn);
+// refractive (and subsurface): rough dielectric interface (yocto_shading.h:884-957)
+YGL_HD lobe_t refractive_lobe(float ior, float roughness, const f3& n, const f3& o, const f3& i) {
+  auto entering = dot(n, o) >= 0;
+  auto up       = entering ? n : -n;
+  auto rel_ior  = entering ? ior : (1 / ior);
+  if (dot(n, i) * dot(n, o) >= 0) {
+    auto halfway = normalize(i + o);
+    auto F       = fresnel_dielectric(rel_ior, halfway, o);
+    auto ggx     = ggx_terms(roughness, up, halfway, o, i);
+    return {f3{1, 1, 1} * F * ggx.D * ggx.G / yabs(4 * dot(n, o) * dot(n, i)) * yabs(dot(n, i)),
+        F * ggx.hpdf / (4 * yabs(dot(o, halfway)))};
+  }
+  auto halfway = -normalize(rel_ior * i + o) * (entering ? 1.0f : -1.0f);
+  auto F       = fresnel_dielectric(rel_ior, halfway, o);
+  auto ggx     = ggx_terms(roughness, up, halfway, o, i);
+  auto jacobi  = ysqr(rel_ior * dot(halfway, i) + dot(halfway, o));  // change of variables half vector -> direction
+  return {f3{1, 1, 1} * yabs((dot(o, halfway) * dot(i, halfway)) / (dot(o, n) * dot(i, n))) * (1 - F) * ggx.D * ggx.G /
+              jacobi * yabs(dot(n, i)),
+      (1 - F) * ggx.hpdf * yabs(dot(halfway, i)) / jacobi};
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rough lobes: direction samplers (rnl picks the layer, rn the direction)
+// ---------------------------------------------------------------------------------------------------------------
+YGL_HD f3 matte_sample(const f3& n, const f3& o, const f2& rn) { return sample_hemisphere_cos(facing(n, o), rn); }
+YGL_HD f3 glossy_sample(float ior, float roughness, const f3& n, const f3& o, float rnl, const f2& rn) {
+  auto up = facing(n, o);
+  if (rnl < fresnel_dielectric(ior, up, o)) return ggx_reflect(roughness, up, o, rn);
+  return sample_hemisphere_cos(up, rn);
+}
+YGL_HD f3 reflective_sample(float roughness, const f3& n, const f3& o, const f2& rn) {
+  return ggx_reflect(roughness, facing(n, o), o, rn);
+}
+YGL_HD f3 gltfpbr_sample(const f3& color, float ior, float roughness, float metallic, const f3& n, const f3& o, float rnl,
+    const f2& rn) {
+  auto up           = facing(n, o);
+  auto reflectivity = lerp3(eta_to_reflectivity(f3{ior, ior, ior}), color, metallic);
+  if (rnl < mean3(fresnel_schlick(reflectivity, up, o))) return ggx_reflect(roughness, up, o, rn);
+  return sample_hemisphere_cos(up, rn);
+}
+YGL_HD f3 transparent_sample(float ior, float roughness, const f3& n, const f3& o, float rnl, const f2& rn) {
+  auto up        = facing(n, o);
+  auto halfway   = ggx_sample(roughness, up, rn);
+  auto reflected = reflect(o, halfway);
   if (rnl < fresnel_dielectric(ior, halfway, o)) {
-    auto incoming = reflect(o, halfway);
-    if (!same_hemisphere(up, o, incoming)) return {0, 0, 0};
-    return incoming;
-  } else {
-    auto reflected = reflect(o, halfway);
-    auto incoming  = -reflect(reflected, up);
-    if (same_hemisphere(up, o, incoming)) return {0, 0, 0};
-    return incoming;
+    if (!same_side(up, o, reflected)) return {0, 0, 0};
+    return reflected;
   }
+  auto through = -reflect(reflected, up);
+  if (same_side(up, o, through)) return {0, 0, 0};
+  return through;
 }
-YGL_HD float sample_transparent_pdf(float ior, float roughness, const f3& n, const f3& o, const f3& i) {
-  auto up = up_normal_of(n, o);
-  if (dot(n, i) * dot(n, o) >= 0) {
-    auto halfway = normalize(i + o);
-    return fresnel_dielectric(ior, halfway, o) * sample_microfacet_pdf(roughness, up, halfway) /
-           (4 * yabs(dot(o, halfway)));
-  } else {
-    auto reflected = reflect(-i, up);
-    auto halfway   = normalize(reflected + o);
-    auto d = (1 - fresnel_dielectric(ior, halfway, o)) * sample_microfacet_pdf(roughness, up, halfway);
-    return d / (4 * yabs(dot(o, halfway)));
-  }
-}
-// ---- transparent (delta), shading.h:852-881 ----
-YGL_HD f3 eval_transparent_delta(const f3& color, float ior, const f3& n, const f3& o, const f3& i) {
-  auto up = up_normal_of(n, o);
-  if (dot(n, i) * dot(n, o) >= 0) {
-    return f3{1, 1, 1} * fresnel_dielectric(ior, up, o);
-  } else {
-    return color * (1 - fresnel_dielectric(ior, up, o));
-  }
-}
-YGL_HD f3 sample_transparent_delta(float ior, const f3& n, const f3& o, float rnl) {
-  auto up = up_normal_of(n, o);
-  if (rnl < fresnel_dielectric(ior, up, o)) {
-    return reflect(o, up);
-  } else {
-    return -o;
-  }
-}
-YGL_HD float sample_transparent_delta_pdf(float ior, const f3& n, const f3& o, const f3& i) {
-  auto up = up_normal_of(n, o);
-  if (dot(n, i) * dot(n, o) >= 0) {
-    return fresnel_dielectric(ior, up, o);
-  } else {
-    return 1 - fresnel_dielectric(ior, up, o);
-  }
-}
-
-// ---- refractive (rough), shading.h:884-957 ----
-YGL_HD f3 eval_refractive(float ior, float roughness, const f3& n, const f3& o, const f3& i) {
+YGL_HD f3 refractive_sample(float ior, float roughness, const f3& n, const f3& o, float rnl, const f2& rn) {
   auto entering = dot(n, o) >= 0;
   auto up       = entering ? n : -n;
-  auto rel_ior  = entering ? ior : (1 / ior);
-  if (dot(n, i) * dot(n, o) >= 0) {
-    auto halfway = normalize(i + o);
-    auto F       = fresnel_dielectric(rel_ior, halfway, o);
-    auto D       = microfacet_distribution(roughness, up, halfway);
-    auto G       = microfacet_shadowing(roughness, up, halfway, o, i);
-    return f3{1, 1, 1} * F * D * G / yabs(4 * dot(n, o) * dot(n, i)) * yabs(dot(n, i));
-  } else {
-    auto halfway = -normalize(rel_ior * i + o) * (entering ? 1.0f : -1.0f);
-    auto F       = fresnel_dielectric(rel_ior, halfway, o);
-    auto D       = microfacet_distribution(roughness, up, halfway);
-    auto G       = microfacet_shadowing(roughness, up, halfway, o, i);
-    return f3{1, 1, 1} * yabs((dot(o, halfway) * dot(i, halfway)) / (dot(o, n) * dot(i, n))) * (1 - F) * D *
-           G / ysqr(rel_ior * dot(halfway, i) + dot(halfway, o)) * yabs(dot(n, i));
-  }
-}
-YGL_HD f3 sample_refractive(float ior, float roughness, const f3& n, const f3& o, float rnl, const f2& rn) {
-  auto entering = dot(n, o) >= 0;
-  auto up       = entering ? n : -n;
-  auto halfway  = sample_microfacet(roughness, up, rn);
+  auto halfway  = ggx_sample(roughness, up, rn);
   if (rnl < fresnel_dielectric(entering ? ior : (1 / ior), halfway, o)) {
-    auto incoming = reflect(o, halfway);
-    if (!same_hemisphere(up, o, incoming)) return {0, 0, 0};
-    return incoming;
-  } else {
-    auto incoming = refract(o, halfway, entering ? (1 / ior) : ior);
-    if (same_hemisphere(up, o, incoming)) return {0, 0, 0};
-    return incoming;
+    auto reflected = reflect(o, halfway);
+    if (!same_side(up, o, reflected)) return {0, 0, 0};
+    return reflected;
   }
-}
-YGL_HD float sample_refractive_pdf(float ior, float roughness, const f3& n, const f3& o, const f3& i) {
-  auto entering = dot(n, o) >= 0;
-  auto up       = entering ? n : -n;
-  auto rel_ior  = entering ? ior : (1 / ior);
-  if (dot(n, i) * dot(n, o) >= 0) {
-    auto halfway = normalize(i + o);
-    return fresnel_dielectric(rel_ior, halfway, o) * sample_microfacet_pdf(roughness, up, halfway) /
-           (4 * yabs(dot(o, halfway)));
-  } else {
-    auto halfway = -normalize(rel_ior * i + o) * (entering ? 1.0f : -1.0f);
-    return (1 - fresnel_dielectric(rel_ior, halfway, o)) * sample_microfacet_pdf(roughness, up, halfway) *
-           yabs(dot(halfway, i)) / ysqr(rel_ior * dot(halfway, i) + dot(halfway, o));
-  }
-}
-// ---- refractive (delta), shading.h:960-1005; `abs(ior - 1) < 1e-3` compares in double ----
-YGL_HD bool ior_is_one(float ior) { return (double)yabs(ior - 1) < 1e-3; }
-YGL_HD f3 eval_refractive_delta(float ior, const f3& n, const f3& o, const f3& i) {
-  if (ior_is_one(ior)) return dot(n, i) * dot(n, o) <= 0 ? f3{1, 1, 1} : f3{0, 0, 0};
-  auto entering = dot(n, o) >= 0;
-  auto up       = entering ? n : -n;
-  auto rel_ior  = entering ? ior : (1 / ior);
-  if (dot(n, i) * dot(n, o) >= 0) {
-    return f3{1, 1, 1} * fresnel_dielectric(rel_ior, up, o);
-  } else {
-    return f3{1, 1, 1} * (1 / (rel_ior * rel_ior)) * (1 - fresnel_dielectric(rel_ior, up, o));
-  }
-}
-YGL_HD f3 sample_refractive_delta(float ior, const f3& n, const f3& o, float rnl) {
-  if (ior_is_one(ior)) return -o;
-  auto entering = dot(n, o) >= 0;
-  auto up       = entering ? n : -n;
-  auto rel_ior  = entering ? ior : (1 / ior);
-  if (rnl < fresnel_dielectric(rel_ior, up, o)) {
-    return reflect(o, up);
-  } else {
-    return refract(o, up, 1 / rel_ior);
-  }
-}
-YGL_HD float sample_refractive_delta_pdf(float ior, const f3& n, const f3& o, const f3& i) {
-  if (ior_is_one(ior)) return dot(n, i) * dot(n, o) < 0 ? 1.0f : 0.0f;
-  auto entering = dot(n, o) >= 0;
-  auto up       = entering ? n : -n;
-  auto rel_ior  = entering ? ior : (1 / ior);
-  if (dot(n, i) * dot(n, o) >= 0) {
-    return fresnel_dielectric(rel_ior, up, o);
-  } else {
-    return (1 - fresnel_dielectric(rel_ior, up, o));
-  }
-}
-// ---- passthrough, shading.h:1028-1048 ----
-YGL_HD f3 eval_passthrough(const f3& n, const f3& o, const f3& i) {
-  return (dot(n, i) * dot(n, o) >= 0) ? f3{0, 0, 0} : f3{1, 1, 1};
-}
-YGL_HD float sample_passthrough_pdf(const f3& n, const f3& o, const f3& i) {
-  return (dot(n, i) * dot(n, o) >= 0) ? 0.0f : 1.0f;
+  auto refracted = refract(o, halfway, entering ? (1 / ior) : ior);
+  if (same_side(up, o, refracted)) return {0, 0, 0};
+  return refracted;
 }
 
-// ---- volumes, shading.h:1056-1111 ----
+// ---------------------------------------------------------------------------------------------------------------
+// delta lobes (roughness 0): value and discrete probability together, and their samplers
+// (yocto_shading.h:693-712, :852-881, :960-1005, :1028-1048)
+// ---------------------------------------------------------------------------------------------------------------
+YGL_HD lobe_t mirror_lobe(const f3& color, const f3& n, const f3& o, const f3& i) {
+  if (dot(n, i) * dot(n, o) <= 0) return no_lobe();
+  return {metal_fresnel(color, facing(n, o), o), 1};
+}
+YGL_HD lobe_t thin_glass_lobe(const f3& color, float ior, const f3& n, const f3& o, const f3& i) {
+  auto F = fresnel_dielectric(ior, facing(n, o), o);
+  if (dot(n, i) * dot(n, o) >= 0) return {f3{1, 1, 1} * F, F};
+  return {color * (1 - F), 1 - F};
+}
+// `abs(ior - 1) < 1e-3` compares in double in the reference (yocto_shading.h:963)
+YGL_HD bool index_matched(float ior) { return (double)yabs(ior - 1) < 1e-3; }
+YGL_HD lobe_t glass_lobe(float ior, const f3& n, const f3& o, const f3& i) {
+  if (index_matched(ior)) {
+    // the value tests "<= 0", the probability "< 0" (yocto_shading.h:964, :998)
+    return {dot(n, i) * dot(n, o) <= 0 ? f3{1, 1, 1} : f3{0, 0, 0}, dot(n, i) * dot(n, o) < 0 ? 1.0f : 0.0f};
+  }
+  auto entering = dot(n, o) >= 0;
+  auto up       = entering ? n : -n;
+  auto rel_ior  = entering ? ior : (1 / ior);
+  auto F        = fresnel_dielectric(rel_ior, up, o);
+  if (dot(n, i) * dot(n, o) >= 0) return {f3{1, 1, 1} * F, F};
+  return {f3{1, 1, 1} * (1 / (rel_ior * rel_ior)) * (1 - F), (1 - F)};
+}
+YGL_HD lobe_t passthrough_lobe(const f3& n, const f3& o, const f3& i) {
+  if (dot(n, i) * dot(n, o) >= 0) return no_lobe();
+  return {{1, 1, 1}, 1};
+}
+YGL_HD f3 thin_glass_sample(float ior, const f3& n, const f3& o, float rnl) {
+  auto up = facing(n, o);
+  if (rnl < fresnel_dielectric(ior, up, o)) return reflect(o, up);
+  return -o;
+}
+YGL_HD f3 glass_sample(float ior, const f3& n, const f3& o, float rnl) {
+  if (index_matched(ior)) return -o;
+  auto entering = dot(n, o) >= 0;
+  auto up       = entering ? n : -n;
+  auto rel_ior  = entering ? ior : (1 / ior);
+  if (rnl < fresnel_dielectric(rel_ior, up, o)) return reflect(o, up);
+  return refract(o, up, 1 / rel_ior);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// participating media (yocto_shading.h:1056-1111)
+// ---------------------------------------------------------------------------------------------------------------
 YGL_HD f3 eval_transmittance(const f3& density, float distance) { return vexp(-density * distance); }
 YGL_HD float sample_transmittance(const f3& density, float max_distance, float rl, float rd) {
   auto channel  = iclamp((int)(rl * 3), 0, 2);
@@ -402,18 +330,15 @@ YGL_HD float sample_transmittance(const f3& density, float max_distance, float r
   return ymin(distance, max_distance);
 }
 YGL_HD float sample_transmittance_pdf(const f3& density, float distance, float max_distance) {
-  if (distance < max_distance) {
-    return sum3(density * vexp(-density * distance)) / 3;
-  } else {
-    return sum3(vexp(-density * max_distance)) / 3;
-  }
+  if (distance < max_distance) return sum3(density * vexp(-density * distance)) / 3;
+  return sum3(vexp(-density * max_distance)) / 3;
 }
-YGL_HD float eval_phasefunction(float anisotropy, const f3& o, const f3& i) {
+YGL_HD float henyey_greenstein(float anisotropy, const f3& o, const f3& i) {
   auto cosine = -dot(o, i);
   auto denom  = 1 + anisotropy * anisotropy - 2 * anisotropy * cosine;
   return (1 - anisotropy * anisotropy) / (4 * kPi * denom * ysqrt(denom));
 }
-YGL_HD f3 sample_phasefunction(float anisotropy, const f3& o, const f2& rn) {
+YGL_HD f3 henyey_greenstein_sample(float anisotropy, const f3& o, const f2& rn) {
   auto cos_theta = 0.0f;
   if (yabs(anisotropy) < 1e-3f) {
     cos_theta = 1 - 2 * rn.y;
@@ -427,99 +352,85 @@ YGL_HD f3 sample_phasefunction(float anisotropy, const f3& o, const f2& rn) {
   return mat_mul(basis_fromz(-o), local);
 }
 
-// ---- material dispatch, yocto_trace.cpp:166-335 ----
+// ---------------------------------------------------------------------------------------------------------------
+// material dispatch (yocto_trace.cpp:166-335). A material is `delta` when its roughness is zero (or it is a pure
+// volume boundary): rough and delta lobes are disjoint, each returns nothing for the other kind.
+// ---------------------------------------------------------------------------------------------------------------
 YGL_HD bool is_delta(const mpoint& m) {  // yocto_scene.cpp:263-271
   return (m.type == kReflective && m.roughness == 0) || (m.type == kRefractive && m.roughness == 0) ||
          (m.type == kTransparent && m.roughness == 0) || (m.type == kVolumetric);
 }
-YGL_HD f3 eval_emission(const mpoint& m, const f3& n, const f3& o) {
-  return dot(n, o) >= 0 ? m.emission : f3{0, 0, 0};
-}
-YGL_HD_BIG f3 eval_bsdfcos(const mpoint& m, const f3& n, const f3& o, const f3& i) {
-  if (m.roughness == 0) return {0, 0, 0};
+YGL_HD f3 eval_emission(const mpoint& m, const f3& n, const f3& o) { return dot(n, o) >= 0 ? m.emission : f3{0, 0, 0}; }
+
+// eval_bsdfcos + sample_bsdfcos_pdf in one pass
+YGL_HD_BIG lobe_t bsdf_lobe(const mpoint& m, const f3& n, const f3& o, const f3& i) {
+  if (m.roughness == 0) return no_lobe();
   switch (m.type) {
-    case kMatte: return eval_matte(m.color, n, o, i);
-    case kGlossy: return eval_glossy(m.color, m.ior, m.roughness, n, o, i);
-    case kReflective: return eval_reflective(m.color, m.roughness, n, o, i);
-    case kTransparent: return eval_transparent(m.color, m.ior, m.roughness, n, o, i);
+    case kMatte: return matte_lobe(m.color, n, o, i);
+    case kGlossy: return glossy_lobe(m.color, m.ior, m.roughness, n, o, i);
+    case kReflective: return reflective_lobe(m.color, m.roughness, n, o, i);
+    case kTransparent: return transparent_lobe(m.color, m.ior, m.roughness, n, o, i);
     case kRefractive:
-    case kSubsurface: return eval_refractive(m.ior, m.roughness, n, o, i);
-    case kGltfPbr: return eval_gltfpbr(m.color, m.ior, m.roughness, m.metallic, n, o, i);
-    default: return {0, 0, 0};
-  }
-}
-YGL_HD f3 eval_delta(const mpoint& m, const f3& n, const f3& o, const f3& i) {
-  if (m.roughness != 0) return {0, 0, 0};
-  switch (m.type) {
-    case kReflective: return eval_reflective_delta(m.color, n, o, i);
-    case kTransparent: return eval_transparent_delta(m.color, m.ior, n, o, i);
-    case kRefractive: return eval_refractive_delta(m.ior, n, o, i);
-    case kVolumetric: return eval_passthrough(n, o, i);
-    default: return {0, 0, 0};
+    case kSubsurface: return refractive_lobe(m.ior, m.roughness, n, o, i);
+    case kGltfPbr: return gltfpbr_lobe(m.color, m.ior, m.roughness, m.metallic, n, o, i);
+    default: return no_lobe();
   }
 }
 YGL_HD_BIG f3 sample_bsdfcos(const mpoint& m, const f3& n, const f3& o, float rnl, const f2& rn) {
   if (m.roughness == 0) return {0, 0, 0};
   switch (m.type) {
-    case kMatte: return sample_matte(n, o, rn);
-    case kGlossy: return sample_glossy(m.ior, m.roughness, n, o, rnl, rn);
-    case kReflective: return sample_reflective(m.roughness, n, o, rn);
-    case kTransparent: return sample_transparent(m.ior, m.roughness, n, o, rnl, rn);
+    case kMatte: return matte_sample(n, o, rn);
+    case kGlossy: return glossy_sample(m.ior, m.roughness, n, o, rnl, rn);
+    case kReflective: return reflective_sample(m.roughness, n, o, rn);
+    case kTransparent: return transparent_sample(m.ior, m.roughness, n, o, rnl, rn);
     case kRefractive:
-    case kSubsurface: return sample_refractive(m.ior, m.roughness, n, o, rnl, rn);
-    case kGltfPbr: return sample_gltfpbr(m.color, m.ior, m.roughness, m.metallic, n, o, rnl, rn);
+    case kSubsurface: return refractive_sample(m.ior, m.roughness, n, o, rnl, rn);
+    case kGltfPbr: return gltfpbr_sample(m.color, m.ior, m.roughness, m.metallic, n, o, rnl, rn);
     default: return {0, 0, 0};
+  }
+}
+// eval_delta + sample_delta_pdf in one pass
+YGL_HD lobe_t delta_lobe(const mpoint& m, const f3& n, const f3& o, const f3& i) {
+  if (m.roughness != 0) return no_lobe();
+  switch (m.type) {
+    case kReflective: return mirror_lobe(m.color, n, o, i);
+    case kTransparent: return thin_glass_lobe(m.color, m.ior, n, o, i);
+    case kRefractive: return glass_lobe(m.ior, n, o, i);
+    case kVolumetric: return passthrough_lobe(n, o, i);
+    default: return no_lobe();
   }
 }
 YGL_HD f3 sample_delta(const mpoint& m, const f3& n, const f3& o, float rnl) {
   if (m.roughness != 0) return {0, 0, 0};
   switch (m.type) {
-    case kReflective: return sample_reflective_delta(n, o);
-    case kTransparent: return sample_transparent_delta(m.ior, n, o, rnl);
-    case kRefractive: return sample_refractive_delta(m.ior, n, o, rnl);
+    case kReflective: return reflect(o, facing(n, o));
+    case kTransparent: return thin_glass_sample(m.ior, n, o, rnl);
+    case kRefractive: return glass_sample(m.ior, n, o, rnl);
     case kVolumetric: return -o;  // sample_passthrough
     default: return {0, 0, 0};
   }
 }
-YGL_HD_BIG float sample_bsdfcos_pdf(const mpoint& m, const f3& n, const f3& o, const f3& i) {
-  if (m.roughness == 0) return 0;
-  switch (m.type) {
-    case kMatte: return sample_matte_pdf(n, o, i);
-    case kGlossy: return sample_glossy_pdf(m.ior, m.roughness, n, o, i);
-    case kReflective: return sample_reflective_pdf(m.roughness, n, o, i);
-    case kTransparent: return sample_transparent_pdf(m.ior, m.roughness, n, o, i);
-    case kRefractive:
-    case kSubsurface: return sample_refractive_pdf(m.ior, m.roughness, n, o, i);
-    case kGltfPbr: return sample_gltfpbr_pdf(m.color, m.ior, m.roughness, m.metallic, n, o, i);
-    default: return 0;
-  }
-}
-YGL_HD float sample_delta_pdf(const mpoint& m, const f3& n, const f3& o, const f3& i) {
-  if (m.roughness != 0) return 0;
-  switch (m.type) {
-    case kReflective: return sample_reflective_delta_pdf(n, o, i);
-    case kTransparent: return sample_transparent_delta_pdf(m.ior, n, o, i);
-    case kRefractive: return sample_refractive_delta_pdf(m.ior, n, o, i);
-    case kVolumetric: return sample_passthrough_pdf(n, o, i);
-    default: return 0;
-  }
-}
-// volume scattering dispatch, yocto_trace.cpp:316-335 (vsdf = density, scattering, scanisotropy)
+// the reference's one-quantity entry points, for callers that want only one of the two
+YGL_HD f3    eval_bsdfcos(const mpoint& m, const f3& n, const f3& o, const f3& i) { return bsdf_lobe(m, n, o, i).bsdfcos; }
+YGL_HD float sample_bsdfcos_pdf(const mpoint& m, const f3& n, const f3& o, const f3& i) { return bsdf_lobe(m, n, o, i).pdf; }
+YGL_HD f3    eval_delta(const mpoint& m, const f3& n, const f3& o, const f3& i) { return delta_lobe(m, n, o, i).bsdfcos; }
+YGL_HD float sample_delta_pdf(const mpoint& m, const f3& n, const f3& o, const f3& i) { return delta_lobe(m, n, o, i).pdf; }
+
+// volume scattering, yocto_trace.cpp:316-335 (vsdf = density, scattering, scanisotropy)
 struct vsdf_t {
   f3    density, scattering;
   float scanisotropy;
 };
-YGL_HD f3 eval_scattering(const vsdf_t& v, const f3& o, const f3& i) {
-  if (is_zero(v.density)) return {0, 0, 0};
-  return v.scattering * v.density * eval_phasefunction(v.scanisotropy, o, i);
+YGL_HD lobe_t scattering_lobe(const vsdf_t& v, const f3& o, const f3& i) {
+  if (is_zero(v.density)) return no_lobe();
+  auto phase = henyey_greenstein(v.scanisotropy, o, i);
+  return {v.scattering * v.density * phase, phase};
 }
 YGL_HD f3 sample_scattering(const vsdf_t& v, const f3& o, const f2& rn) {
   if (is_zero(v.density)) return {0, 0, 0};
-  return sample_phasefunction(v.scanisotropy, o, rn);
+  return henyey_greenstein_sample(v.scanisotropy, o, rn);
 }
-YGL_HD float sample_scattering_pdf(const vsdf_t& v, const f3& o, const f3& i) {
-  if (is_zero(v.density)) return 0;
-  return eval_phasefunction(v.scanisotropy, o, i);
-}
+YGL_HD f3    eval_scattering(const vsdf_t& v, const f3& o, const f3& i) { return scattering_lobe(v, o, i).bsdfcos; }
+YGL_HD float sample_scattering_pdf(const vsdf_t& v, const f3& o, const f3& i) { return scattering_lobe(v, o, i).pdf; }
 
 }  // namespace ygl
