@@ -908,17 +908,21 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   const int  lane_end      = only_lane >= 0 ? only_lane + 1 : st.num_lanes;
   const int  sample_begin  = only_lane >= 0 ? only_sample : state->samples;
   KParams    kp            = make_kparams(params, sample_begin + nsamples);
-  // The shading kernels can finish a path themselves (accumulate + next camera sample: one launch fewer per
-  // iteration) - measured on B200: 4-6 % faster on small tiles (1/8 of C3, Cornell), 7 % slower on the full 1080p
-  // frame, where the extra divergence in the shading kernels costs more than the launch. Hence: by lane count.
-  const int fuse = tune.fuse >= 0 ? tune.fuse : (st.num_lanes <= 800000 ? 1 : 0);
-  kp.fuse        = fuse;
   // Binned shade queues + one kernel per shading class: the path sampler (trace_path). The other samplers run the
   // unspecialised kernel on one queue.
-  const bool binned     = params.sampler == YGL_SAMPLER_PATH && tune.bin != 0;
+  // Measured on B200 (C3): on the full 1080p frame the binned pipeline renders 16 spp in 179 ms against 193 ms; on a
+  // 1/8 tile (259 K lanes) the extra launches and their tails cost more than the coherence gains (80.9 vs 78.5 ms per
+  // 32 spp). Hence: by lane count unless the option says otherwise.
+  const bool binned     = params.sampler == YGL_SAMPLER_PATH && (tune.bin >= 0 ? tune.bin != 0 : st.num_lanes > 800000);
   const unsigned classes = binned ? ctx->class_mask : 1u;
   DScene     dscene     = ctx->dscene;
   dscene.inst_class     = binned ? ctx->d_inst_class : nullptr;
+  // The shading kernels can finish a path themselves (accumulate + next camera sample: no k_finish launch). Measured on
+  // B200 (C3): with the unspecialised kernel that is 4-6 % faster on small tiles and 7 % slower on the full frame (the
+  // extra divergence costs more than the launch); with per-class kernels it wins on the full frame too (176.6 vs 181.3 ms
+  // per 16 spp).
+  const int fuse = tune.fuse >= 0 ? tune.fuse : (binned || st.num_lanes <= 800000 ? 1 : 0);
+  kp.fuse        = fuse;
 
   // Pipelines: lanes can be split over independent queue sets on separate streams (ramp-up/drain of one
   // overlapping the other). Measured on B200 (C3, 1/8 tile): 2 pipelines were 7 % slower than 1 -> default 1.
@@ -988,10 +992,11 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
     return YGL_OK;
   };
   // A round of check_every iterations is the same launch sequence every time (the queue parity is back where it
-  // started): on small tiles, where an iteration lasts a few hundred microseconds and the gaps between its 7-9
-  // launches are a tenth of that, the round is captured once into a CUDA graph and re-launched as a unit. Not while
-  // timing or counting (those need the individual launches), and pointless on big tiles.
-  const bool use_graph = !timing && !trav && (tune.graph >= 0 ? tune.graph != 0 : st.num_lanes <= 800000);
+  // started), so it can be captured once into a CUDA graph and re-launched as a unit (option "graph"). Not while
+  // timing or counting (those need the individual launches).
+  // Measured on B200 (C3, full frame and 1/8 tile): no difference either way (179.1 vs 179.0 ms, 80.8 vs 81.1 ms) - the
+  // host already enqueues two rounds ahead, so the launches never were the gap. Off unless the option asks for it.
+  const bool use_graph = !timing && !trav && tune.graph > 0;
   (void)extend_grid_threads(ctx->num_sms);  // occupancy query of the extend kernel: done before any capture
   auto destroy_graphs = [&]() {
     for (int j = 0; j < npipes; j++)

@@ -134,10 +134,10 @@ struct Tuning {
   int lone              = -1; // extend tail: vote-free walk of the last <= this many lanes (-1 = by tile size, 0 = never)
   int lone_steps        = 0;  //   ... parked after this many steps (0 = never)
   int fuse              = -1; // shading kernels finish paths themselves (1) or hand them to k_finish (0); -1 = by tile size
-  int bin               = -1; // class-binned shade queues for the path sampler (1/0; -1 = on)
+  int bin               = -1; // class-binned shade queues + per-class kernels for the path sampler (1/0; -1 = by tile size)
   int pipes             = 1;  // independent wavefront pipelines (streams) per state
-  int graph             = -1; // submit iterations as a CUDA graph (1/0; -1 = by tile size)
-  int top_smem          = -1; // extend: stage the instance-level tree in shared memory with a bulk async copy (1/0; -1 = default)
+  int graph             = -1; // submit rounds of iterations as a CUDA graph (1 = on; measured: no gain, so -1 = off)
+  int top_smem          = -1; // extend: stage the instance-level tree in shared memory with a bulk async copy (1 = on; measured slower, so -1 = off)
 };
 
 void launch_begin_iteration(cudaStream_t s, Queues q, int parity);
