@@ -29,7 +29,7 @@ for STEP in "$@"; do
     san)
       timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
     ab2)
-      for CFG in "lib" "lib top_smem=1" "lib graph=1" "lib graph=0" "lib ext_blocks_per_sm=4" "lib ext_blocks_per_sm=5 graph=1" "lib bin=0 graph=1"; do
+      for CFG in "lib" "lib_new" "lib" "lib_new"; do
         set -- $CFG; LIB=$1; shift
         [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
         echo "--- $LIB $*"
@@ -39,6 +39,21 @@ for STEP in "$@"; do
       timeout -s KILL 120 $PERF c1 256 16 2 2>&1 | tail -n 1 | cut -c1-200
       timeout -s KILL 120 $PERF c2 1280 16 2 2>&1 | tail -n 1 | cut -c1-200
       timeout -s KILL 120 $PERF c5 1920 8 2 2>&1 | tail -n 1 | cut -c1-200 ;;
+    scale)   # usage: gpurun --gpus N -- tools/gpu_session.sh TAG scale   (N from nvidia-smi)
+      N=$(nvidia-smi -L | wc -l)
+      for G in 1 2 4 8; do
+        [ $G -le $N ] || continue
+        if [ $G -eq 1 ]; then CMD="python bench.py --no-cpu-baseline"; else CMD="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $((29500 + G)) bench.py --gpus $G"; fi
+        timeout -s KILL 420 $CMD --steps 8 --warmup 3 > gpurun_out/${TAG}_scale_n$G.json 2> gpurun_out/${TAG}_scale_n$G.err; echo "n=$G rc=$?"
+        python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/${TAG}_scale_n$G.json").read().strip().splitlines()[-1])
+    print("  value %.1f e2e %.1f ms/step %.1f frac %.3f share %.2f launches %d" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["kernel_share_of_step"], d["gpu_launches"]))
+except Exception as e:
+    print("  no line:", e)
+PY
+      done ;;
     launches)
       timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
       python tools/ncu_summary.py --launches gpurun_out/${TAG}_launches.csv | head -n 20 ;;

@@ -116,7 +116,8 @@ YGL_D void generate_lane(const DScene& scene, const PS& st, const KParams& p, in
     st.next_ids[lane] = make_int2(-1, -1);
   }
 }
-__global__ void __launch_bounds__(256) k_generate(DScene scene, PathState st, Queues q, KParams p, int parity) {
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
+    const __grid_constant__ Queues q, const __grid_constant__ KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_gen[parity];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -154,11 +155,13 @@ YGL_D void shade_push(const Queues& q, bool pred, int cls, int value) {
 
 template <int TAIL>
 struct ExtendSource {
+  // st and q are REFERENCES to the kernel's __grid_constant__ parameters: a by-value copy put the whole source
+  // (~500 bytes of pointers) into local memory, and every queue or state access in the traversal loop went through it
   const int* __restrict__ queue;
   int        n;
   int*       head;
-  PathState  st;
-  Queues     q;
+  const PathState& st;
+  const Queues&    q;
   int        parity;
   const unsigned char* __restrict__ inst_class;  // shading class per instance, or null: every lane goes to class 0
   int        has_volumes;
@@ -221,7 +224,8 @@ struct ExtendSource {
 #define YGL_EXT_MINBLOCKS 7  // measured on B200 (C3): 4/5/6/7/8 blocks/SM -> 249/249/233/224/227 ms per 32 spp
 #endif
 template <bool COUNT, int TAIL, bool DEEP, bool TOP = false>
-__global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(DScene scene, PathState st, Queues q, int parity,
+__global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
+    const __grid_constant__ Queues q, int parity,
     unsigned long long* trav, int refill_thr, int node_reps, int suspend_below, int lone_below, int lone_steps) {
   Counters*     c = q.counters;
   const int     n = c->n_ext[parity];
@@ -945,7 +949,8 @@ YGL_D void route_shaded(const DScene& scene, const PathState& st, const Queues& 
 
 // The unspecialised shading kernel: every sampler, every kind of lane (queue of class 0).
 template <int SAMPLER>
-__global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shade(DScene scene, PathState st, Queues q, KParams p, int parity) {
+__global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shade(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
+    const __grid_constant__ Queues q, const __grid_constant__ KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_shade[kClsGeneric];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -975,7 +980,8 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_MINBLOCKS) k_shad
 // contains that kind's code only (k_shade<path> carried ~25 K instructions for every lane and ran 8 of 32 lanes per
 // instruction; see DESIGN.md "shading classes").
 template <int CLS, bool FUSE>
-__global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_CLS_MINBLOCKS) k_shade_path(DScene scene, PathState st, Queues q, KParams p, int parity) {
+__global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_CLS_MINBLOCKS) k_shade_path(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
+    const __grid_constant__ Queues q, const __grid_constant__ KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_shade[CLS];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -1050,7 +1056,8 @@ YGL_D void lightpdf_lane(const DScene& scene, const PS& st, const KParams& p, bo
   }
 }
 template <bool FUSE>
-__global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(DScene scene, PathState st, Queues q, KParams p, int parity) {
+__global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
+    const __grid_constant__ Queues q, const __grid_constant__ KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_lpdf;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -1111,7 +1118,8 @@ YGL_D bool accumulate_lane(const DScene& scene, const PS& st, const KParams& p, 
 // Class kClsMiss of the path sampler: every lane of the warp ends its path on the environment, so the kernel
 // accumulates the sample and starts the lane's next camera ray at once, whatever p.fuse says (the code is coherent,
 // and it saves the lane a trip through k_finish).
-__global__ void __launch_bounds__(256, 4) k_shade_miss(DScene scene, PathState st, Queues q, KParams p, int parity) {
+__global__ void __launch_bounds__(256, 4) k_shade_miss(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
+    const __grid_constant__ Queues q, const __grid_constant__ KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_shade[kClsMiss];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -1140,7 +1148,8 @@ __global__ void __launch_bounds__(256, 4) k_shade_miss(DScene scene, PathState s
 
 // The finished paths of an iteration (p.fuse == 0): accumulate, then the lane's next camera sample goes straight into
 // the next extend queue.
-__global__ void __launch_bounds__(256) k_finish(DScene scene, PathState st, Queues q, KParams p, int parity) {
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
+    const __grid_constant__ Queues q, const __grid_constant__ KParams p, int parity) {
   Counters* c   = q.counters;
   const int n   = c->n_acc;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;

@@ -383,18 +383,30 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   // plus a 64K-primitive shape tree).
   __shared__ int s_stack[kSharedStack][THREADS];
   int            l_stack[(DEEP ? 2 * kStackSize + 8 : kShallowStack) - kSharedStack];
+  // The thread's column of the shared stack as a 32-bit shared-space address, computed once: through the generic
+  // `s_stack[sp][tix]` form every push and pop recomputed the shared window base (S2UR CgaCtaId / ULEA / UMOV: 11 % of
+  // the kernel's stall samples in the round-2 profile, profiles/r02_c3_kernels_full.txt).
+  const unsigned s_col = (unsigned)__cvta_generic_to_shared(&s_stack[0][threadIdx.x]);
+  auto           s_put = [&](int entry, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(s_col + (unsigned)entry * (unsigned)(THREADS * sizeof(int))), "r"(v) : "memory");
+  };
+  auto s_get = [&](int entry) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(s_col + (unsigned)entry * (unsigned)(THREADS * sizeof(int))) : "memory");
+    return v;
+  };
   const int      tix  = threadIdx.x;
   int            sp   = 1;
   auto           push = [&](int v) {
-    if (sp < kSharedStack) s_stack[sp][tix] = v;
+    if (sp < kSharedStack) s_put(sp, v);
     else l_stack[sp - kSharedStack] = v;
     sp++;
   };
   auto pop_raw = [&]() {
     --sp;
-    return sp < kSharedStack ? s_stack[sp][tix] : l_stack[sp - kSharedStack];
+    return sp < kSharedStack ? s_get(sp) : l_stack[sp - kSharedStack];
   };
-  s_stack[0][tix] = kMarkDone;  // sentinel: popping an empty stack yields "done"
+  s_put(0, kMarkDone);  // sentinel: popping an empty stack yields "done"
   hit_t res = {-1, -1, {0, 0}, 0, false};
 
   const float tmin = kRayEps;
@@ -519,7 +531,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     sv[5] = __float_as_int(tmax);
     sv[6] = res.instance, sv[7] = res.element, sv[8] = __float_as_int(res.uv.x), sv[9] = __float_as_int(res.uv.y);
     sv[10] = __float_as_int(res.distance), sv[11] = res.hit ? 1 : 0;
-    for (int k = 1; k < sp; k++) sv[12 + k] = k < kSharedStack ? s_stack[k][tix] : l_stack[k - kSharedStack];
+    for (int k = 1; k < sp; k++) sv[12 + k] = k < kSharedStack ? s_get(k) : l_stack[k - kSharedStack];
     src.commit_suspended();
     cur = kMarkDone, sp = 1, have = false;
   };
@@ -554,7 +566,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
           tmax = __int_as_float(sv[5]);
           res  = {sv[6], sv[7], {__int_as_float(sv[8]), __int_as_float(sv[9])}, __int_as_float(sv[10]), sv[11] != 0};
           for (int k = 1; k < sp; k++) {
-            if (k < kSharedStack) s_stack[k][tix] = sv[12 + k];
+            if (k < kSharedStack) s_put(k, sv[12 + k]);
             else l_stack[k - kSharedStack] = sv[12 + k];
           }
           if (pkt >= 0) reload_instance(pkt);
