@@ -268,7 +268,6 @@ def main():
     params.batch = spp_step
 
     ctx = lib.Context(local)
-    ctx.set_mode("wavefront")  # the measured scheduler (the roofline is per k_extend launch); YGL_MODE must not change it
     ds = lib.DeviceScene(ctx, scene)
     W, H = lib.state_size(scene, params)
     rows = lib.tile_rows(H, rank, world)

@@ -10,6 +10,8 @@ for STEP in "$@"; do
   case $STEP in
     tests)
       timeout -s KILL 1500 python -m pytest tests -m gpu -q --maxfail=12 --durations=12 -s > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; grep -a "bvh build\|passed\|failed\|^FAILED\|^ERROR" gpurun_out/${TAG}_tests.log | tail -n 40 | cut -c1-220 ;;
+    tests_new)   # the parity core on a variant build (YGL_B200_LIB is read by the python binding)
+      YGL_B200_LIB=$PWD/yocto-gl_b200/lib_new2/libygl_b200.so timeout -s KILL 900 python -m pytest tests -m gpu -q --maxfail=5 -k "render_matches_oracle or full_size_render or full_state or options or tiles_equal" > gpurun_out/${TAG}_tests_new.log 2>&1; echo "pytest(new) rc=$?"; tail -n 4 gpurun_out/${TAG}_tests_new.log | cut -c1-200 ;;
     tests_fast)
       timeout -s KILL 900 python -m pytest tests -m gpu -q --maxfail=8 -k "not full_size and not libm and not counters" > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/${TAG}_tests.log | cut -c1-220 ;;
     bench)
@@ -29,7 +31,7 @@ for STEP in "$@"; do
     san)
       timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
     ab2)
-      for CFG in "lib" "lib_new" "lib" "lib_new"; do
+      for CFG in "lib" "lib_new" "lib_new2" "lib" "lib_new" "lib_new2"; do
         set -- $CFG; LIB=$1; shift
         [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
         echo "--- $LIB $*"
@@ -41,7 +43,7 @@ for STEP in "$@"; do
       timeout -s KILL 120 $PERF c5 1920 8 2 2>&1 | tail -n 1 | cut -c1-200 ;;
     scale)   # usage: gpurun --gpus N -- tools/gpu_session.sh TAG scale   (N from nvidia-smi)
       N=$(nvidia-smi -L | wc -l)
-      for G in 1 2 4 8; do
+      for G in ${SCALE_N:-1 2 4 8}; do
         [ $G -le $N ] || continue
         if [ $G -eq 1 ]; then CMD="python bench.py --no-cpu-baseline"; else CMD="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $((29500 + G)) bench.py --gpus $G"; fi
         timeout -s KILL 420 $CMD --steps 8 --warmup 3 > gpurun_out/${TAG}_scale_n$G.json 2> gpurun_out/${TAG}_scale_n$G.err; echo "n=$G rc=$?"
@@ -54,6 +56,12 @@ except Exception as e:
     print("  no line:", e)
 PY
       done ;;
+    final)   # the round's measurement set: bench line, other configs, launch list, ncu captures (tools/make_profiles.py)
+      timeout -s KILL 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/${TAG}_bench.json
+      for W in c1 c2 c5; do timeout -s KILL 300 python bench.py --workload $W --no-cpu-baseline > gpurun_out/${TAG}_bench_$W.json 2> gpurun_out/${TAG}_bench_$W.err; echo "bench $W rc=$?"; done
+      timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
+      timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shade|k_lightpdf|k_finish' -s 60 -c 8 -o gpurun_out/${TAG}_kernels $PERF c3 1920 4 0 > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"
+      timeout -s KILL 300 ncu --set full --clock-control none -k regex:'k_extend' -c 1 -o gpurun_out/${TAG}_extend_first $PERF c3 1920 1 0 > gpurun_out/${TAG}_ncu_first.log 2>&1; echo "ncu first rc=$?" ;;
     launches)
       timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
       python tools/ncu_summary.py --launches gpurun_out/${TAG}_launches.csv | head -n 20 ;;

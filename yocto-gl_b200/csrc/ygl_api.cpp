@@ -172,7 +172,7 @@ extern "C" {
 const char* ygl_last_error(void) { return g_error.c_str(); }
 // for the other translation units of the library (ygl_sceneio.cpp)
 void ygl_internal_set_error(const char* message) { g_error = message ? message : ""; }
-const char* ygl_version(void) { return "ygl_b200 0.1 (sm_100a wavefront path tracer)"; }
+const char* ygl_version(void) { return "ygl_b200 0.2 (sm_100a wavefront path tracer; float libm = glibc 2.39 x86-64 FMA builds)"; }
 
 void ygl_trace_params_default(ygl_trace_params* p) {
   *p            = ygl_trace_params{};
@@ -705,13 +705,13 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
     off      = (off + bytes + 255) & ~size_t(255);
     return o;
   };
+  // reference-layout accumulators (downloaded as they are), per-lane scalars, then the path state as interleaved
+  // pairs of 16-byte records (PathStateT): 32 bytes per lane and pair
   size_t o_image = take(lanes * 16), o_albedo = take(lanes * 12), o_normal = take(lanes * 12), o_hits = take(lanes * 4),
-         o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_ro = take(lanes * 16), o_rd = take(lanes * 16),
-         o_rad = take(lanes * 16), o_w = take(lanes * 16), o_huvd = take(lanes * 16), o_hid = take(lanes * 8),
-         o_a0 = take(lanes * 16), o_n0 = take(lanes * 16), o_va = take(lanes * 16), o_vb = take(lanes * 16),
-         o_pend = take(lanes * 16), o_susp = take(lanes * 4), o_ao = take(lanes * 16), o_ad = take(lanes * 16),
-         o_ab = take(lanes * 16), o_au = take(lanes * 16), o_ai = take(lanes * 8), o_nu = take(lanes * 16),
-         o_ni = take(lanes * 8);
+         o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_hid = take(lanes * 8), o_susp = take(lanes * 4),
+         o_ai = take(lanes * 8), o_ni = take(lanes * 8);
+  size_t o_pair[8];
+  for (auto& o : o_pair) o = take(lanes * 32);
   CUDA_TRY(cudaMalloc((void**)&state->mem, off));
   CUDA_TRY(cudaMemset(state->mem, 0, off));
   PathState& st = state->st;
@@ -724,25 +724,23 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
   st.hits     = (int*)(m + o_hits);
   st.rngs     = (ulonglong2*)(m + o_rngs);
   st.sample   = (int*)(m + o_sample);
-  st.ray_o    = (float4*)(m + o_ro);
-  st.ray_d    = (float4*)(m + o_rd);
-  st.radiance = (float4*)(m + o_rad);
-  st.weight   = (float4*)(m + o_w);
-  st.hit_uvd  = (float4*)(m + o_huvd);
   st.hit_ids  = (int2*)(m + o_hid);
-  st.albedo0  = (float4*)(m + o_a0);
-  st.normal0  = (float4*)(m + o_n0);
-  st.vol_a    = (float4*)(m + o_va);
-  st.vol_b    = (float4*)(m + o_vb);
-  st.pend     = (float4*)(m + o_pend);
   st.susp     = (int*)(m + o_susp);
-  st.aux_o    = (float4*)(m + o_ao);
-  st.aux_dir  = (float4*)(m + o_ad);
-  st.aux_bsdf = (float4*)(m + o_ab);
-  st.aux_uvd  = (float4*)(m + o_au);
   st.aux_ids  = (int2*)(m + o_ai);
-  st.next_uvd = (float4*)(m + o_nu);
   st.next_ids = (int2*)(m + o_ni);
+  auto pair = [&](int k, SPair<false>& a, SPair<false>& b) {
+    a = (float4*)(m + o_pair[k]);
+    b = (float4*)(m + o_pair[k]) + 1;
+  };
+  pair(0, st.ray_o, st.ray_d);         // read together by extend, shade, light pdf
+  pair(1, st.radiance, st.weight);     // shade, accumulate
+  pair(2, st.hit_uvd, st.pend);        // shade reads the hit and writes the pending MIS numerator
+  pair(3, st.albedo0, st.normal0);     // bounce-0 guides
+  pair(4, st.vol_a, st.vol_b);         // the volume slot
+  pair(5, st.aux_o, st.aux_dir);       // shadow-ray origin and direction (pathdirect / pathmis)
+  pair(6, st.aux_uvd, st.aux_bsdf);
+  SPair<false> spare;
+  pair(7, st.next_uvd, spare);
   // rng table: seeded sequentially over the FULL image (yocto_trace.cpp:1512-1515), tile slice uploaded
   std::vector<uint64_t> rngs((size_t)w * h * 2);
   state_rngs(*params, w, h, rngs.data());

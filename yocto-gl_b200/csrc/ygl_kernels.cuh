@@ -31,11 +31,13 @@ struct SRef {
   }
 #endif
 };
-template <class T, bool COH>
+// STRIDE (in elements): 2 for the path-state records that are stored as interleaved PAIRS (see PathStateT) so that
+// the two 16-byte halves a stage reads together share one 32-byte DRAM sector.
+template <class T, bool COH, int STRIDE = 1>
 struct SArr {
   T* p;
 #ifdef __CUDACC__
-  __device__ __forceinline__ SRef<T, COH> operator[](long long i) const { return SRef<T, COH>{p + i}; }
+  __device__ __forceinline__ SRef<T, COH> operator[](long long i) const { return SRef<T, COH>{p + i * STRIDE}; }
 #endif
   __host__ __device__ operator T*() const { return p; }
   __host__ __device__ SArr& operator=(T* q) {
@@ -44,9 +46,13 @@ struct SArr {
   }
 };
 
-// Per-lane wavefront state, SoA of 16-byte records so that each stage moves whole 128-bit words.
+// Per-lane wavefront state: 16-byte records, moved as whole 128-bit words. Lanes reach a stage in queue order, i.e.
+// scattered, so every 16-byte access costs a 32-byte DRAM sector; records that a stage touches together are therefore
+// stored as interleaved pairs {a[lane], b[lane]} = one sector (ray_o|ray_d, radiance|weight, hit_uvd|pend, ...).
 // One lane = one pixel of the tile (the only legal parallel axis: each pixel's samples form a
 // sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
+template <bool COH>
+using SPair = SArr<float4, COH, 2>;  // one half of an interleaved pair of float4 records
 template <bool COH>
 struct PathStateT {
   int num_lanes;  // pixels in this tile
@@ -60,25 +66,25 @@ struct PathStateT {
   // ---- per-lane progress ----
   SArr<int, COH> sample;  // index of the sample in flight
   // ---- path in flight ----
-  SArr<float4, COH> ray_o;     // origin.xyz, w: bounce (int bits)
-  SArr<float4, COH> ray_d;     // direction.xyz, w: opbounce (int bits)
-  SArr<float4, COH> radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
-  SArr<float4, COH> weight;    // rgb, w: max_roughness
-  SArr<float4, COH> hit_uvd;   // uv.x uv.y distance hit(int bits)
+  SPair<COH>        ray_o;     // origin.xyz, w: bounce (int bits)
+  SPair<COH>        ray_d;     // direction.xyz, w: opbounce (int bits)
+  SPair<COH>        radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
+  SPair<COH>        weight;    // rgb, w: max_roughness
+  SPair<COH>        hit_uvd;   // uv.x uv.y distance hit(int bits)
   SArr<int2, COH>   hit_ids;   // instance, element
-  SArr<float4, COH> albedo0;   // bounce-0 albedo rgb, w unused
-  SArr<float4, COH> normal0;   // bounce-0 normal (or -camera dir on miss) xyz
-  SArr<float4, COH> vol_a;     // volume slot: density.xyz, scanisotropy
-  SArr<float4, COH> vol_b;     // volume slot: scattering.xyz
-  SArr<float4, COH> pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
+  SPair<COH>        albedo0;   // bounce-0 albedo rgb, w unused
+  SPair<COH>        normal0;   // bounce-0 normal (or -camera dir on miss) xyz
+  SPair<COH>        vol_a;     // volume slot: density.xyz, scanisotropy
+  SPair<COH>        vol_b;     // volume slot: scattering.xyz
+  SPair<COH>        pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
   SArr<int, COH>    susp;      // save slot of the lane's ray while it is parked by k_extend (see Queues::park)
   // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
-  SArr<float4, COH> aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
-  SArr<float4, COH> aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
-  SArr<float4, COH> aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
-  SArr<float4, COH> aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
+  SPair<COH>        aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
+  SPair<COH>        aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
+  SPair<COH>        aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
+  SPair<COH>        aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
   SArr<int2, COH>   aux_ids;   // shadow-ray hit: instance, element
-  SArr<float4, COH> next_uvd;  // pathmis next_intersection (persists across bounces)
+  SPair<COH>        next_uvd;  // pathmis next_intersection (persists across bounces)
   SArr<int2, COH>   next_ids;
 };
 using PathState = PathStateT<false>;  // a kernel boundary separates every writer of lane state from its readers
