@@ -31,7 +31,7 @@ for STEP in "$@"; do
     san)
       timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
     ab2)
-      for CFG in "lib" "lib_new" "lib_new2" "lib" "lib_new" "lib_new2"; do
+      for CFG in "lib" "lib suspend=31 suspend_rounds=48 lone=0" "lib suspend=31 suspend_rounds=96 lone=0" "lib suspend=31 suspend_rounds=160 lone=0" "lib suspend=16 suspend_rounds=64 lone=0" "lib lone=20" "lib bin=1"; do
         set -- $CFG; LIB=$1; shift
         [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
         echo "--- $LIB $*"

@@ -280,6 +280,7 @@ YGL_D f3 sample_lights(const DScene& scene, const f3& position, float rl, float 
 // ---- sample_lights_pdf, yocto_trace.cpp:391-443. WARP-COOPERATIVE (calls trace_ray): the per-light
 // chain of up to 100 instance rays is unrolled into one warp-uniform loop in which every lane that
 // still owes a ray traces its next one; lanes add their terms in the reference's order. ----
+template <bool DEEP>
 YGL_D float sample_lights_pdf(const DScene& scene, bool valid, const f3& position, const f3& direction,
     unsigned& rays) {
   float pdf = 0.0f, lpdf = 0.0f;
@@ -320,7 +321,7 @@ YGL_D float sample_lights_pdf(const DScene& scene, bool valid, const f3& positio
     }
     const bool want = !done;
     if (!__any_sync(kFullWarp, want)) break;
-    hit_t h = trace_ray<false, false>(scene, want, next_position, direction, kRayEps, kFltMax, want ? instance : -1, tc);
+    hit_t h = trace_ray<false, false, DEEP>(scene, want, next_position, direction, kRayEps, kFltMax, want ? instance : -1, tc);
     if (want) {
       rays++;
       bool next_light = !h.hit;
@@ -1008,7 +1009,7 @@ __global__ void __launch_bounds__(YGL_SHADE_THREADS, YGL_SHADE_CLS_MINBLOCKS) k_
 #endif
 // One warp-wide step (WARP-COOPERATIVE: every lane of the warp must call it; `valid` marks lanes that hold a queued
 // lane id). Outputs the lane's destination queue and its extend-queue entry.
-template <class PS>
+template <bool DEEP, class PS>
 YGL_D void lightpdf_lane(const DScene& scene, const PS& st, const KParams& p, bool valid, int lane,
     unsigned& rays, int& dest, int& entry) {
   float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 1, 0);
@@ -1020,7 +1021,7 @@ YGL_D void lightpdf_lane(const DScene& scene, const PS& st, const KParams& p, bo
     const bool direct = phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf;  // pdf of a direct sample at aux_o
     ro = direct ? st.aux_o[lane] : st.ray_o[lane], rd = direct ? st.aux_dir[lane] : st.ray_d[lane];
   }
-  float lpdf = sample_lights_pdf(scene, valid, unpack3(ro), unpack3(rd), rays);
+  float lpdf = sample_lights_pdf<DEEP>(scene, valid, unpack3(ro), unpack3(rd), rays);
   if (valid && (phase == kPhaseDirectPdf || phase == kPhaseBsdfPdf)) {
     // direct lighting: decide whether the shadow ray is needed (yocto_trace.cpp:662-665 / :860-869)
     float4 ab      = st.aux_bsdf[lane];
@@ -1055,7 +1056,7 @@ YGL_D void lightpdf_lane(const DScene& scene, const PS& st, const KParams& p, bo
     entry = lane;
   }
 }
-template <bool FUSE>
+template <bool FUSE, bool DEEP>
 __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
     const __grid_constant__ Queues q, const __grid_constant__ KParams p, int parity) {
   Counters* c   = q.counters;
@@ -1067,7 +1068,7 @@ __global__ void __launch_bounds__(256, YGL_LPDF_MINBLOCKS) k_lightpdf(const __gr
   for (int i0 = tid - wl; i0 < n; i0 += stride) {
     int i    = i0 + wl;
     int lane = i < n ? q.lpdf[i] : 0, dest, entry;
-    lightpdf_lane(scene, st, p, i < n, lane, rays, dest, entry);
+    lightpdf_lane<DEEP>(scene, st, p, i < n, lane, rays, dest, entry);
     if (FUSE) end_of_path(scene, st, p, lane, dest, entry, counts);
     queue_push(q.ext[1 - parity], &c->n_ext[1 - parity], dest == kDestExt, entry);
     if (!FUSE) queue_push(q.acc, &c->n_acc, dest == kDestAcc, lane);
@@ -1330,8 +1331,9 @@ void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Que
   }
 }
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
-  if (p.fuse) k_lightpdf<true><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
-  else k_lightpdf<false><<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
+  auto* kernel = scene.deep_stack ? (p.fuse ? k_lightpdf<true, true> : k_lightpdf<false, true>)
+                                  : (p.fuse ? k_lightpdf<true, false> : k_lightpdf<false, false>);
+  kernel<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }
 void launch_finish(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
   k_finish<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);

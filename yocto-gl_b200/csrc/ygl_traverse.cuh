@@ -17,6 +17,7 @@
 
 namespace ygl {
 
+constexpr int kShallowStack = 72;  // stack capacity of the !DEEP kernel variants (both levels + markers)
 constexpr int kStackSize = 128;  // per level, the reference's own stack size (yocto_bvh.cpp:469); the host build rejects
                                  // deeper trees (the reference's array is unchecked there)
 
@@ -176,10 +177,12 @@ YGL_D ray_setup make_ray(const f3& o, const f3& d) {
 // WARP-COOPERATIVE: all 32 lanes of a warp must call this together (converged); lanes without a
 // ray pass active = false. The votes (__any_sync / __all_sync) are the reconvergence points: sm_100
 // schedules diverged lanes independently and would otherwise never bring them back in step.
-template <bool ANY, bool COUNT>
+// DEEP: stack for trees up to the reference's 128 levels per level of the hierarchy; !DEEP: kShallowStack entries, for
+// scenes whose trees fit (DScene::deep_stack, chosen by the host) - a 1 KB local array per thread otherwise.
+template <bool ANY, bool COUNT, bool DEEP = true>
 YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f3& ray_d, float tmin, float tmax,
     int start_instance, trav_counters& cnt) {
-  int   stack[2 * kStackSize + 8];
+  int   stack[DEEP ? 2 * kStackSize + 8 : kShallowStack];
   int   sp  = 0;
   hit_t res = {-1, -1, {0, 0}, 0, false};
 
@@ -339,7 +342,6 @@ constexpr int kPollMaxInterval = 96;  // ... doubling up to this while it stays 
 constexpr int kStreamThreads   = 128;  // block size of kernels that call trace_stream
 constexpr int kSharedStack     = 28;   // stack entries per lane kept in shared memory by k_extend (14 KB per block)
 constexpr int kSuspendEntries  = kSuspendWords - 12;  // stack entries a parked ray can carry (12 header words)
-constexpr int kShallowStack    = 72;   // stack capacity of the !DEEP instantiation (both levels + markers)
 constexpr int kSuspendMinRounds = 96;  // a warp walks at least this many rounds per launch before suspending: progress guarantee
 constexpr int kSuspendBelow    = 8;    // suspend a drained warp's stragglers once this few lanes are busy (0 = never)
 
