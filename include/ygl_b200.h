@@ -245,6 +245,13 @@ int  ygl_bvh_create_from_host(const ygl_scene_desc* desc, const ygl_bvh_node* to
      const int32_t* top_primitives, int num_top_primitives, const ygl_bvh_node* const* shape_nodes,
      const int* shape_num_nodes, const int32_t* const* shape_primitives, const int* shape_num_primitives,
      ygl_bvh** out);
+/* update_scene_bvh (yocto_bvh.h:94-96, yocto_bvh.cpp:434-451): refit after vertex positions / radii of the listed shapes
+ * or any instance frame changed - same topology, boxes recomputed bottom-up in the reference's merge order, so the
+ * trees equal the reference's refit bit for bit. `desc` is the edited scene (same element counts as at build time).
+ * Like the reference, every instance box is recomputed, whatever updated_instances lists. The device copy is replaced
+ * on the next call that uses the bvh; not to be called while a trace_start batch is running on it. */
+int  ygl_bvh_update(ygl_bvh* bvh, const ygl_scene_desc* desc, const int* updated_instances, int num_updated_instances,
+     const int* updated_shapes, int num_updated_shapes);
 void ygl_bvh_destroy(ygl_bvh* bvh);
 
 /* ---- lights: make_trace_lights (host; CDFs in the reference's summation order) ---- */

@@ -289,6 +289,10 @@ void* ref_bvh_build(void* scene, int highquality) {
   *bvh     = make_scene_bvh(((ref_scene*)scene)->scene, highquality != 0, false);
   return bvh;
 }
+// update_scene_bvh, yocto_bvh.cpp:434: refit `bvh` to the (edited) scene
+void ref_bvh_update(void* bvh, void* scene, const int* shapes, int num_shapes) {
+  update_scene_bvh(*(scene_bvh*)bvh, ((ref_scene*)scene)->scene, {}, vector<int>(shapes, shapes + num_shapes));
+}
 void ref_bvh_destroy(void* bvh) { delete (scene_bvh*)bvh; }
 static const bvh_tree& pick_tree(void* bvh_, int shape) {
   auto bvh = (scene_bvh*)bvh_;

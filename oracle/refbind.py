@@ -36,6 +36,7 @@ class Ref:
         lib.ref_bvh_build.restype = vp
         lib.ref_bvh_build.argtypes = [vp, C.c_int]
         lib.ref_bvh_destroy.argtypes = [vp]
+        lib.ref_bvh_update.argtypes = [vp, vp, vp, C.c_int]
         lib.ref_bvh_tree_size.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.ref_bvh_tree_get.argtypes = [vp, C.c_int, vp, vp]
         lib.ref_intersect_rays.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int]
@@ -124,6 +125,13 @@ class RefScene:
         if highquality not in self._bvh:
             self._bvh[highquality] = self.lib.ref_bvh_build(self.h, int(highquality))
         return self._bvh[highquality]
+
+    def adopt_updated_bvh(self, other, updated_shapes, highquality=False):
+        """update_scene_bvh: take `other`'s trees (a RefScene of the scene before the edit) refitted to this scene."""
+        b = other._bvh.pop(highquality, None) or self.lib.ref_bvh_build(other.h, int(highquality))
+        shapes = np.ascontiguousarray(list(updated_shapes), np.int32)
+        self.lib.ref_bvh_update(b, self.h, shapes.ctypes.data, len(shapes))
+        self._bvh[highquality] = b
 
     def bvh_tree(self, shape, highquality=False):
         b = self.bvh(highquality)

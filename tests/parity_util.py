@@ -79,3 +79,31 @@ def assert_close_to_reference(stats):
     < 0.2 % of pixels differing by more than 1e-4 at these low sample counts."""
     assert stats["rmse_same_paths"] < 1e-5, stats
     assert stats["frac_gt_1e4"] < 2e-3, stats
+
+
+def edited_copy(scene, seed=5):
+    """the same scene after an animation step: every vertex / radius of every other shape moved, every instance frame
+    rotated a little and shifted (topology untouched) - what update_scene_bvh is for"""
+    import copy
+    rng = np.random.default_rng(seed)
+    out = copy.copy(scene)
+    out._keep = None
+    out.shapes = [dict(s) for s in scene.shapes]
+    out.instances = [dict(n) for n in scene.instances]
+    updated = []
+    for si, s in enumerate(out.shapes):
+        if si % 2 == 1 and len(out.shapes) > 1:
+            continue
+        s["positions"] = (s["positions"] * np.float32(1.03) +
+                          rng.uniform(-0.01, 0.01, s["positions"].shape).astype(np.float32))
+        if len(s["radius"]):
+            s["radius"] = s["radius"] * np.float32(1.25)
+        updated.append(si)
+    for n in out.instances:
+        f = np.array(n["frame"], np.float32).reshape(4, 3).copy()
+        a = np.float32(rng.uniform(-0.2, 0.2))
+        rot = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+        f[:3] = f[:3] @ rot
+        f[3] += rng.uniform(-0.05, 0.05, 3).astype(np.float32)
+        n["frame"] = f.reshape(np.shape(n["frame"]))
+    return out, updated

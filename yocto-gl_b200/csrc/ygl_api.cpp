@@ -453,6 +453,26 @@ int ygl_bvh_create_from_host(const ygl_scene_desc* desc, const ygl_bvh_node* top
   *out       = bvh.release();
   return YGL_OK;
 }
+int ygl_bvh_update(ygl_bvh* bvh, const ygl_scene_desc* desc, const int* updated_instances, int num_updated_instances,
+    const int* updated_shapes, int num_updated_shapes) {
+  if (!bvh) return fail(YGL_ERR_INVALID, "null bvh");
+  if (int rc = check_desc(desc)) return rc;
+  if (num_updated_instances < 0 || num_updated_shapes < 0 || (num_updated_shapes > 0 && !updated_shapes))
+    return fail(YGL_ERR_INVALID, "updated id lists missing");
+  (void)updated_instances;  // all instance boxes are refreshed, as in the reference
+  std::string error;
+  if (!update_scene_bvh(*desc, updated_shapes, num_updated_shapes, bvh->host, error)) return fail(YGL_ERR_INVALID, error);
+  // a new epoch drops every cached binding; the device copy is rebuilt on the next use
+  if (bvh->uploaded) {
+    cudaSetDevice(bvh->device);
+    cudaDeviceSynchronize();
+    bvh->arena.release();
+    bvh->arena.host.clear();
+    bvh->uploaded = false;
+  }
+  bvh->epoch = g_epoch++;
+  return YGL_OK;
+}
 static const HostTree* pick_tree(const ygl_bvh* bvh, int shape) {
   if (shape < 0) return &bvh->host.top;
   if (shape >= (int)bvh->host.shapes.size()) return nullptr;

@@ -441,6 +441,53 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
   return true;
 }
 
+// refit_bvh, yocto_bvh.cpp:303-318: boxes again from the leaves up; children always follow their parent in the node
+// array, so one pass from the last node to the root sees every child before its parent
+static void refit_tree(HostTree& tree, const std::vector<box3>& bboxes) {
+  for (int id = (int)tree.nodes.size() - 1; id >= 0; id--) {
+    ygl_bvh_node& node = tree.nodes[id];
+    box3          box;
+    if (node.internal) {
+      for (int k = 0; k < 2; k++) {
+        const ygl_bvh_node& c = tree.nodes[node.start + k];
+        box = merge(box, box3{{c.bbox_min[0], c.bbox_min[1], c.bbox_min[2]}, {c.bbox_max[0], c.bbox_max[1], c.bbox_max[2]}});
+      }
+    } else {
+      for (int k = 0; k < node.num; k++) box = merge(box, bboxes[tree.prims[node.start + k]]);
+    }
+    node.bbox_min[0] = box.min.x, node.bbox_min[1] = box.min.y, node.bbox_min[2] = box.min.z;
+    node.bbox_max[0] = box.max.x, node.bbox_max[1] = box.max.y, node.bbox_max[2] = box.max.z;
+  }
+}
+
+// update_scene_bvh, yocto_bvh.cpp:434-451 (+ update_shape_bvh :398-432): same topology, new boxes. Like the reference,
+// every instance box is recomputed whatever `updated_instances` holds.
+bool update_scene_bvh(const ygl_scene_desc& desc, const int* updated_shapes, int num_updated_shapes, HostBvh& bvh,
+    std::string& error) {
+  if ((int)bvh.shapes.size() != desc.num_shapes) return error = "bvh was built for a scene with another shape count", false;
+  if ((int)bvh.top.prims.size() != desc.num_instances)
+    return error = "bvh was built for a scene with another instance count", false;
+  for (int k = 0; k < num_updated_shapes; k++) {
+    const int si = updated_shapes[k];
+    if (si < 0 || si >= desc.num_shapes) return error = "updated shape id out of range", false;
+    const ygl_shape& s    = desc.shapes[si];
+    const int        kind = shape_bvh_kind(s);
+    std::vector<box3> bboxes;
+    if (!shape_bounds(s, si, kind, bboxes, error)) return false;
+    HostTree& tree = bvh.shapes[si];
+    if (kind != bvh.shape_kind[si] || bboxes.size() != tree.prims.size())
+      return error = "shape " + std::to_string(si) + ": element type or count changed since the build (refit keeps the topology)", false;
+    refit_tree(tree, bboxes);
+    bvh.shape_nodes[si]   = pack_nodes(tree);
+    bvh.shape_packets[si] = pack_leaves(s, kind, tree);
+  }
+  std::vector<box3> ibox;
+  if (!instance_bounds(desc, bvh, ibox, error)) return false;
+  refit_tree(bvh.top, ibox);
+  pack_top(desc, bvh);
+  return true;
+}
+
 // Adopt trees built elsewhere (the reference's make_scene_bvh output): checks + packets only.
 bool adopt_scene_bvh(const ygl_scene_desc& desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
     const int32_t* top_prims, int num_top_prims, const ygl_bvh_node* const* shape_nodes, const int* shape_num_nodes,

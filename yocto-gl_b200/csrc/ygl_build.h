@@ -56,6 +56,9 @@ bool build_tree_device(void* stream, const float* boxes, int n, HostTree& tree, 
 bool adopt_scene_bvh(const ygl_scene_desc& desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
     const int32_t* top_prims, int num_top_prims, const ygl_bvh_node* const* shape_nodes, const int* shape_num_nodes,
     const int32_t* const* shape_prims, const int* shape_num_prims, HostBvh& out, std::string& error);
+// update_scene_bvh, yocto_bvh.cpp:434-451: refit after positions / radii / instance frames moved (topology kept)
+bool update_scene_bvh(const ygl_scene_desc& desc, const int* updated_shapes, int num_updated_shapes, HostBvh& bvh,
+    std::string& error);
 // make_trace_lights, yocto_trace.cpp:1528-1581
 void build_lights(const ygl_scene_desc& desc, std::vector<HostLight>& lights);
 // image size + rng table of make_trace_state, yocto_trace.cpp:1495-1520

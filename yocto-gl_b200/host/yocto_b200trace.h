@@ -8,7 +8,7 @@
 // (tests/test_host_parity.py::test_reference_side_shim_compiles does so in the dev container).
 //
 //   yocto::trace_image(scene, params)            ->  yocto::b200::trace_image(scene, params)
-//   make_trace_bvh / make_trace_lights / make_trace_state / trace_samples / trace_sample / get_image /
+//   make_trace_bvh / update_trace_bvh / make_trace_lights / make_trace_state / trace_samples / trace_sample / get_image /
 //   get_albedo_image / get_normal_image / trace_start / trace_cancel / trace_done / trace_preview likewise.
 //
 // Errors of the C ABI come back as the exceptions the reference uses (yocto_trace.cpp:1437,
@@ -127,6 +127,13 @@ inline std::unique_ptr<b200_bvh> make_trace_bvh(const scene_data& scene, const t
   auto out   = std::make_unique<b200_bvh>();
   check(ygl_bvh_build(&views.desc, params.highqualitybvh ? 1 : 0, &out->handle));
   return out;
+}
+// update_scene_bvh (yocto_bvh.h:88, yocto_bvh.cpp:434): refit to the edited scene, same topology
+inline void update_trace_bvh(b200_bvh& bvh, const scene_data& scene, const std::vector<int>& updated_instances,
+    const std::vector<int>& updated_shapes) {
+  auto views = make_views(scene);
+  check(ygl_bvh_update(bvh.handle, &views.desc, updated_instances.data(), (int)updated_instances.size(),
+      updated_shapes.data(), (int)updated_shapes.size()));
 }
 // make_trace_lights (yocto_trace.cpp:1528)
 inline std::unique_ptr<b200_lights> make_trace_lights(const scene_data& scene, const trace_params&) {

@@ -26,7 +26,7 @@ EXPORTS = [
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
     "ygl_trace_counters", "ygl_context_set_profiling", "ygl_context_set_mode", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
-    "ygl_bvh_build_device", "ygl_scene_load", "ygl_loaded_scene_desc", "ygl_loaded_scene_name", "ygl_loaded_scene_destroy",
+    "ygl_bvh_build_device", "ygl_bvh_update", "ygl_scene_load", "ygl_loaded_scene_desc", "ygl_loaded_scene_name", "ygl_loaded_scene_destroy",
     "ygl_trace_start", "ygl_trace_cancel", "ygl_trace_wait", "ygl_trace_done", "ygl_trace_preview",
     "ygl_context_set_option", "ygl_context_get_option", "ygl_state_reset", "ygl_trace_sample", "ygl_bvh_create_from_host",
 ]
@@ -59,6 +59,7 @@ def load():
     lib.ygl_scene_destroy.argtypes = [vp]
     lib.ygl_bvh_build.argtypes = [P(abi.SceneDesc), i32, P(vp)]
     lib.ygl_bvh_build_device.argtypes = [vp, P(abi.SceneDesc), i32, P(vp)]
+    lib.ygl_bvh_update.argtypes = [vp, P(abi.SceneDesc), vp, i32, vp, i32]
     lib.ygl_bvh_tree_size.argtypes = [vp, i32, P(i32), P(i32)]
     lib.ygl_bvh_tree_get.argtypes = [vp, i32, vp, vp]
     lib.ygl_bvh_destroy.argtypes = [vp]
@@ -166,6 +167,14 @@ class Bvh:
         _check(self.lib.ygl_bvh_create_from_host(C.byref(self.desc), keep[0].ctypes.data, len(keep[0]),
                                                  keep[1].ctypes.data, len(keep[1]), node_ptrs, num_nodes,
                                                  prim_ptrs, num_prims, C.byref(self.h)))
+
+    def update(self, scene, updated_shapes=(), updated_instances=()):
+        """update_scene_bvh: refit to the edited scene (same topology)."""
+        self.desc = scene.desc()
+        shapes = np.ascontiguousarray(list(updated_shapes), np.int32)
+        insts = np.ascontiguousarray(list(updated_instances), np.int32)
+        _check(self.lib.ygl_bvh_update(self.h, C.byref(self.desc), insts.ctypes.data, len(insts),
+                                       shapes.ctypes.data, len(shapes)))
 
     def tree(self, shape):
         nn, npr = C.c_int(), C.c_int()
