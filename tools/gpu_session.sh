@@ -61,7 +61,10 @@ PY
       for W in c1 c2 c5; do timeout -s KILL 300 python bench.py --workload $W --no-cpu-baseline > gpurun_out/${TAG}_bench_$W.json 2> gpurun_out/${TAG}_bench_$W.err; echo "bench $W rc=$?"; done
       timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
       timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shade|k_lightpdf|k_finish' -s 60 -c 8 -o gpurun_out/${TAG}_kernels $PERF c3 1920 4 0 > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"
-      timeout -s KILL 300 ncu --set full --clock-control none -k regex:'k_extend' -c 1 -o gpurun_out/${TAG}_extend_first $PERF c3 1920 1 0 > gpurun_out/${TAG}_ncu_first.log 2>&1; echo "ncu first rc=$?" ;;
+      timeout -s KILL 300 ncu --set full --clock-control none -k regex:'k_extend' -c 1 -o gpurun_out/${TAG}_extend_first $PERF c3 1920 1 0 > gpurun_out/${TAG}_ncu_first.log 2>&1; echo "ncu first rc=$?" 
+      # gpurun brings back at most 64 MiB: compress the captures, and drop the big one rather than lose everything
+      gzip -f gpurun_out/${TAG}_*.ncu-rep; du -sm gpurun_out | cut -f1
+      if [ "$(du -sm gpurun_out | cut -f1)" -gt 58 ]; then rm -f gpurun_out/${TAG}_kernels.ncu-rep.gz; echo "dropped the kernels capture (too large)"; fi ;;
     launches)
       timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
       python tools/ncu_summary.py --launches gpurun_out/${TAG}_launches.csv | head -n 20 ;;

@@ -19,6 +19,9 @@ def run(*cmd):
     return subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT).stdout
 
 
+for gz in (f"{tag}_kernels.ncu-rep.gz", f"{tag}_extend_first.ncu-rep.gz"):
+    if os.path.exists(os.path.join(G, gz)):
+        subprocess.run(["gunzip", "-f", os.path.join(G, gz)], check=True)
 bench = os.path.join(G, f"{tag}_bench.json")
 if os.path.exists(bench):
     line = open(bench).read().strip().splitlines()[-1]
