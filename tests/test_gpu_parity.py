@@ -646,7 +646,7 @@ def test_refitted_bvh(ctx, ref, name):
     rs_new.adopt_updated_bvh(rs_old, updated)
     assert compare_hits(rs_new.intersect(rays), ds2.intersect(rays)) == 0
     assert compare_hits(rs_new.intersect(rays[:20000], find_any=True), ds2.intersect(rays[:20000], find_any=True)) == 0
-    params = abi.trace_params(resolution=96, samples=4, bounces=4)
+    params = abi.trace_params(resolution=96, samples=4, bounces=4, batch=4)
     want = rs_new.trace_image(params)
     st = ds2.make_state(params)
     ds2.trace_samples(st, params)

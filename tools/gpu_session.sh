@@ -11,7 +11,7 @@ for STEP in "$@"; do
     tests)
       timeout -s KILL 1500 python -m pytest tests -m gpu -q --maxfail=12 --durations=12 -s > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; grep -a "bvh build\|passed\|failed\|^FAILED\|^ERROR" gpurun_out/${TAG}_tests.log | tail -n 40 | cut -c1-220 ;;
     tests_new)   # the parity core on a variant build (YGL_B200_LIB is read by the python binding)
-      YGL_B200_LIB=$PWD/yocto-gl_b200/lib_new2/libygl_b200.so timeout -s KILL 900 python -m pytest tests -m gpu -q --maxfail=5 -k "render_matches_oracle or full_size_render or full_state or options or tiles_equal" > gpurun_out/${TAG}_tests_new.log 2>&1; echo "pytest(new) rc=$?"; tail -n 4 gpurun_out/${TAG}_tests_new.log | cut -c1-200 ;;
+      YGL_B200_LIB=$PWD/yocto-gl_b200/${NEWLIB:-lib_new}/libygl_b200.so timeout -s KILL 900 python -m pytest tests -m gpu -q --maxfail=5 -k "${NEWTESTS:-render_matches_oracle or full_size or full_state or options or tiles_equal or counters or deep or intersect}" > gpurun_out/${TAG}_tests_new.log 2>&1; echo "pytest(new) rc=$?"; tail -n 4 gpurun_out/${TAG}_tests_new.log | cut -c1-200 ;;
     tests_fast)
       timeout -s KILL 900 python -m pytest tests -m gpu -q --maxfail=8 -k "not full_size and not libm and not counters" > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/${TAG}_tests.log | cut -c1-220 ;;
     bench)
@@ -31,16 +31,16 @@ for STEP in "$@"; do
     san)
       timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
     ab2)
-      for CFG in "lib" "lib suspend=31 suspend_rounds=48 lone=0" "lib suspend=31 suspend_rounds=96 lone=0" "lib suspend=31 suspend_rounds=160 lone=0" "lib suspend=16 suspend_rounds=64 lone=0" "lib lone=20" "lib bin=1"; do
+      IFS=';' read -ra CFGS <<< "${AB_CFGS:-lib;lib_new}"
+      for CFG in "${CFGS[@]}"; do
         set -- $CFG; LIB=$1; shift
         [ -f yocto-gl_b200/$LIB/libygl_b200.so ] || continue
         echo "--- $LIB $*"
         YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c3 1920 16 2 profile=1 "$@" 2>&1 | tail -n 1 | cut -c1-260
         YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c3 1920 32 2 tile=0,8 profile=1 "$@" 2>&1 | tail -n 1 | cut -c1-260
-      done
-      timeout -s KILL 120 $PERF c1 256 16 2 2>&1 | tail -n 1 | cut -c1-200
-      timeout -s KILL 120 $PERF c2 1280 16 2 2>&1 | tail -n 1 | cut -c1-200
-      timeout -s KILL 120 $PERF c5 1920 8 2 2>&1 | tail -n 1 | cut -c1-200 ;;
+        YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c2 1280 16 2 "$@" 2>&1 | tail -n 1 | cut -c1-200
+        YGL_B200_LIB=$PWD/yocto-gl_b200/$LIB/libygl_b200.so timeout -s KILL 120 $PERF c5 1920 8 2 "$@" 2>&1 | tail -n 1 | cut -c1-200
+      done ;;
     scale)   # usage: gpurun --gpus N -- tools/gpu_session.sh TAG scale   (N from nvidia-smi)
       N=$(nvidia-smi -L | wc -l)
       for G in ${SCALE_N:-1 2 4 8}; do

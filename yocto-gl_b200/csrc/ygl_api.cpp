@@ -165,6 +165,7 @@ struct ygl_state {
 };
 
 static std::atomic<uint64_t> g_epoch{1};
+constexpr int kSharedStackHost  = 28;  // = kSharedStack of ygl_traverse.cuh (the extend kernel's shared-memory stack)
 constexpr int kShallowStackHost = 72;  // = kShallowStack of ygl_traverse.cuh (stack entries of the shallow extend kernel)
 
 extern "C" {
@@ -672,7 +673,9 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
   D.has_volumes      = scene->has_volumes ? 1 : 0;
   int shape_depth = 0;
   for (auto& tree : bvh->host.shapes) shape_depth = std::max(shape_depth, tree.max_stack);
-  D.deep_stack = bvh->host.top.max_stack + shape_depth + 4 > kShallowStackHost ? 1 : 0;
+  // entries a walk can hold: one far sibling per level of both trees + the instance run, the EXIT marker, the sentinel
+  const int stack_need = bvh->host.top.max_stack + shape_depth + 4;
+  D.stack_mode = stack_need > kShallowStackHost ? 2 : stack_need > kSharedStackHost ? 1 : 0;
   ctx->bound_scene = scene, ctx->bound_bvh = bvh, ctx->bound_lights = lights, ctx->bound_epoch = scene->epoch;
   ctx->bound_bvh_epoch = bvh->epoch, ctx->bound_lights_epoch = lights ? lights->epoch : 0;
   return YGL_OK;

@@ -223,7 +223,7 @@ struct ExtendSource {
 #ifndef YGL_EXT_MINBLOCKS
 #define YGL_EXT_MINBLOCKS 7  // measured on B200 (C3): 4/5/6/7/8 blocks/SM -> 249/249/233/224/227 ms per 32 spp
 #endif
-template <bool COUNT, int TAIL, bool DEEP, bool TOP = false>
+template <bool COUNT, int TAIL, int STACK, bool TOP = false>
 __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(const __grid_constant__ DScene scene, const __grid_constant__ PathState st,
     const __grid_constant__ Queues q, int parity,
     unsigned long long* trav, int refill_thr, int node_reps, int suspend_below, int lone_below, int lone_steps) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(const __grid_
   ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, q, parity, scene.inst_class, scene.has_volumes, 0, refill_thr,
       node_reps, suspend_below, lone_below, lone_steps, 0, false};
   trav_counters tc = {};
-  trace_stream<COUNT, kStreamThreads, kSharedStack, DEEP, ExtendSource<TAIL>, TOP>(scene, src, tc);
+  trace_stream<COUNT, kStreamThreads, kSharedStack, STACK, ExtendSource<TAIL>, TOP>(scene, src, tc);
   {
     unsigned v = src.finished;
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFullWarp, v, off);
@@ -1244,7 +1244,7 @@ void launch_generate(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, 
 static int extend_blocks_per_sm() {
   static int per_sm = 0;
   if (!per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_extend<false, 0, false>), 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_extend<false, 0, kStackShallow>), 128, 0);
     if (per_sm < 1) per_sm = 1;
   }
   return per_sm;
@@ -1268,18 +1268,23 @@ void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene
   const int  sb       = tune.suspend >= 0 ? tune.suspend : (big_tile ? kSuspendBelow : 0);
   const int  suspend  = sb > 0 ? (std::min(sb, 31) | std::max(1, tune.suspend_rounds) << 8) : 0;
   const int  lone     = tune.lone >= 0 ? tune.lone : (big_tile ? 0 : 12);
-  // the variant with the full 128-level stack only for scenes whose trees need it (DScene::deep_stack)
-  auto* kernel = scene.deep_stack
-                     ? (lone > 0 ? (trav ? k_extend<true, 1, true> : k_extend<false, 1, true>)
-                                 : (trav ? k_extend<true, 0, true> : k_extend<false, 0, true>))
-                     : (lone > 0 ? (trav ? k_extend<true, 1, false> : k_extend<false, 1, false>)
-                                 : (trav ? k_extend<true, 0, false> : k_extend<false, 0, false>));
+  // the stack variant the bound trees need (DScene::stack_mode): shared memory only, + a small local array, or the
+  // full 128 levels per tree
+  using kernel_t = void (*)(const DScene, const PathState, const Queues, int, unsigned long long*, int, int, int, int, int);
+  static const kernel_t kernels[3][2][2] = {
+      {{k_extend<false, 0, kStackShared>, k_extend<true, 0, kStackShared>},
+          {k_extend<false, 1, kStackShared>, k_extend<true, 1, kStackShared>}},
+      {{k_extend<false, 0, kStackShallow>, k_extend<true, 0, kStackShallow>},
+          {k_extend<false, 1, kStackShallow>, k_extend<true, 1, kStackShallow>}},
+      {{k_extend<false, 0, kStackDeep>, k_extend<true, 0, kStackDeep>},
+          {k_extend<false, 1, kStackDeep>, k_extend<true, 1, kStackDeep>}}};
+  kernel_t kernel = kernels[scene.stack_mode][lone > 0 ? 1 : 0][trav ? 1 : 0];
 #ifndef YGL_PAIR_VISIT
   // A/B (tune.top_smem = 1): the instance-level tree staged in shared memory by a bulk asynchronous copy; only the
   // variant the headline workload runs (timed, parked tail, shallow stack) has this instantiation
   const size_t top_bytes = (size_t)scene.top_num_nodes * 32;
-  if (tune.top_smem > 0 && !trav && lone == 0 && !scene.deep_stack && top_bytes > 0 && top_bytes <= 24 * 1024) {
-    auto* top_kernel = k_extend<false, 0, false, true>;
+  if (tune.top_smem > 0 && !trav && lone == 0 && scene.stack_mode == kStackShared && top_bytes > 0 && top_bytes <= 24 * 1024) {
+    auto* top_kernel = k_extend<false, 0, kStackShared, true>;
     int   top_per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&top_per_sm, top_kernel, 128, top_bytes);
     int top_blocks = num_sms * std::max(1, tune.ext_blocks_per_sm > 0 ? std::min(top_per_sm, tune.ext_blocks_per_sm) : top_per_sm);
@@ -1331,7 +1336,7 @@ void launch_shade(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Que
   }
 }
 void launch_lightpdf(cudaStream_t s, LaunchCfg cfg, DScene scene, PathState st, Queues q, KParams p, int parity) {
-  auto* kernel = scene.deep_stack ? (p.fuse ? k_lightpdf<true, true> : k_lightpdf<false, true>)
+  auto* kernel = scene.stack_mode == kStackDeep ? (p.fuse ? k_lightpdf<true, true> : k_lightpdf<false, true>)
                                   : (p.fuse ? k_lightpdf<true, false> : k_lightpdf<false, false>);
   kernel<<<cfg.blocks, cfg.threads, 0, s>>>(scene, st, q, p, parity);
 }

@@ -125,7 +125,7 @@ struct DScene {
   int           num_lights;
   // shading class of a hit on instance i = 1 + material type (ygl_kernels.cuh); null = shade queues are not binned
   const unsigned char* inst_class;
-  int                  deep_stack;   // the trees need more traversal stack than the shallow kernel variant carries
+  int                  stack_mode;   // traversal stack the trees need: kStackShared / kStackShallow / kStackDeep (ygl_traverse.cuh)
   int                  has_volumes;  // some material can start a participating medium (refractive / subsurface / volumetric)
 };
 

@@ -178,7 +178,7 @@ YGL_D ray_setup make_ray(const f3& o, const f3& d) {
 // ray pass active = false. The votes (__any_sync / __all_sync) are the reconvergence points: sm_100
 // schedules diverged lanes independently and would otherwise never bring them back in step.
 // DEEP: stack for trees up to the reference's 128 levels per level of the hierarchy; !DEEP: kShallowStack entries, for
-// scenes whose trees fit (DScene::deep_stack, chosen by the host) - a 1 KB local array per thread otherwise.
+// scenes whose trees fit (DScene::stack_mode, chosen by the host) - a 1 KB local array per thread otherwise.
 template <bool ANY, bool COUNT, bool DEEP = true>
 YGL_D hit_t trace_ray(const DScene& scene, bool active, const f3& ray_o, const f3& ray_d, float tmin, float tmax,
     int start_instance, trav_counters& cnt) {
@@ -340,19 +340,22 @@ constexpr int kRefillThreshold = 8;  // refill once this many lanes are idle
 constexpr int kPollInterval    = 6;  // scheduling rounds between two polls of an empty ring queue ...
 constexpr int kPollMaxInterval = 96;  // ... doubling up to this while it stays empty
 constexpr int kStreamThreads   = 128;  // block size of kernels that call trace_stream
+constexpr int kStackShared = 0, kStackShallow = 1, kStackDeep = 2;  // trace_stream<STACK>
 constexpr int kSharedStack     = 28;   // stack entries per lane kept in shared memory by k_extend (14 KB per block)
 constexpr int kSuspendEntries  = kSuspendWords - 12;  // stack entries a parked ray can carry (12 header words)
 constexpr int kSuspendMinRounds = 96;  // a warp walks at least this many rounds per launch before suspending: progress guarantee
 constexpr int kSuspendBelow    = 8;    // suspend a drained warp's stragglers once this few lanes are busy (0 = never)
 
-// DEEP: stack capacity for trees up to the reference's 128 levels per level of the hierarchy (a 1 KB local array per
-// thread: its mere presence in the frame costs the kernel ~8 % through L1 pressure); !DEEP: kShallowStack entries,
-// chosen by the host when the bound scene's trees fit (DScene::deep_stack).
+// STACK: kStackDeep = capacity for trees up to the reference's 128 levels per level of the hierarchy (a 1 KB local array
+// per thread: its mere presence in the frame costs the kernel ~8 % through L1 pressure); kStackShallow = kShallowStack
+// entries, the ones beyond the shared part in a small local array; kStackShared = the shared part only (SHARED entries,
+// no local array, no bounds branches on push / pop). The host picks by the depth of the bound trees (DScene::stack_need).
 // TOP: the instance-level tree is staged once per block into (dynamic) shared memory with one bulk asynchronous copy
 // (cp.async.bulk + mbarrier, the TMA engine's 1-D path) and its nodes are then read with LDS instead of through L1.
 // BASELINE.json's north_star names this staging; measured on B200 it is an A/B, not the default.
-template <bool COUNT, int THREADS, int SHARED, bool DEEP, class Source, bool TOP = false>
+template <bool COUNT, int THREADS, int SHARED, int STACK, class Source, bool TOP = false>
 YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
+  constexpr bool kSpill = STACK != kStackShared;  // entries beyond the shared part exist (a per-thread local array)
   constexpr int kSharedStack = SHARED;
   extern __shared__ __align__(16) float4 s_top[];  // TOP only: top_num_nodes x 2 float4 (dynamic shared memory)
   if (TOP) {
@@ -384,7 +387,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   // deeper entries spill to a per-thread local array (rare: kSharedStack covers a 1000-instance tree
   // plus a 64K-primitive shape tree).
   __shared__ int s_stack[kSharedStack][THREADS];
-  int            l_stack[(DEEP ? 2 * kStackSize + 8 : kShallowStack) - kSharedStack];
+  int            l_stack[kSpill ? (STACK == kStackDeep ? 2 * kStackSize + 8 : kShallowStack) - kSharedStack : 1];
   // The thread's column of the shared stack as a 32-bit shared-space address, computed once: through the generic
   // `s_stack[sp][tix]` form every push and pop recomputed the shared window base (S2UR CgaCtaId / ULEA / UMOV: 11 % of
   // the kernel's stall samples in the round-2 profile, profiles/r02_c3_kernels_full.txt).
@@ -400,14 +403,11 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   const int      tix  = threadIdx.x;
   int            sp   = 1;
   auto           push = [&](int v) {
-    if (sp < kSharedStack) s_put(sp, v);
+    if (!kSpill || sp < kSharedStack) s_put(sp, v);
     else l_stack[sp - kSharedStack] = v;
     sp++;
   };
-  auto pop_raw = [&]() {
-    --sp;
-    return sp < kSharedStack ? s_get(sp) : l_stack[sp - kSharedStack];
-  };
+  auto peek = [&]() { return !kSpill || sp <= kSharedStack ? s_get(sp - 1) : l_stack[sp - 1 - kSharedStack]; };
   s_put(0, kMarkDone);  // sentinel: popping an empty stack yields "done"
   hit_t res = {-1, -1, {0, 0}, 0, false};
 
@@ -457,22 +457,33 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     bottom       = true;
     cur_packet   = first;
   };
-  auto advance = [&]() {
-    int v = pop_raw();
-    if (v == kMarkExit) {  // leaving an instance: back to the world-space ray; never two EXITs in a row
-      ray        = world;
-      nodes      = scene.top_nodes;
-      bottom     = false;
-      cur_packet = -1;
-      v          = pop_raw();
-    }
-    if (v == kMarkDone) sp = 1;
+  // The top entry comes off the stack; the sentinel at entry 0 stays (an empty stack keeps yielding "done"). An EXIT
+  // marker is handed back as it is: the lane leaves its instance at the start of its next node round (leave_instance).
+  auto pop = [&]() {
+    const int v = peek();
+    sp -= v == kMarkDone ? 0 : 1;
     return v;
+  };
+  // leaving an instance: back to the world-space ray. Only what the instance-level walk reads is restored (its slabs
+  // need origin, 1/direction and the signs; the direction itself is set again by the next `enter`).
+  auto leave_instance = [&]() {
+    ray.o = world.o, ray.dinv = world.dinv, ray.sgn = world.sgn, ray.exact = world.exact;
+    nodes      = scene.top_nodes;
+    bottom     = false;
+    cur_packet = -1;
   };
 
   int cur = kMarkDone, leaf_next = 0, leaf_end = 0, rounds = 0, poll_wait = 0, poll_gap = kPollInterval;
-  // one node visit of the lane's walk (cur >= 0)
+  // one node visit of the lane's walk (cur >= 0, or the EXIT marker: leave the instance, then visit what follows).
+  // After the slab test the three outcomes (inner node hit: stack the far child, walk into the near one; leaf hit: hand
+  // the leaf to the primitive / instance path; miss or empty leaf: pop) are folded into selects around one speculative
+  // read of the stack top, so the lanes of a warp stay together whatever each of them found.
   auto visit_node = [&]() {
+    if (cur == kMarkExit) {  // never two EXITs in a row
+      leave_instance();
+      cur = pop();
+    }
+    if (cur < 0) return;
     float4 n0, n1;
     if (TOP && !bottom) n0 = s_top[2 * cur], n1 = s_top[2 * cur + 1];
     else n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
@@ -480,25 +491,22 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       if (bottom) cnt.bot_nodes++;
       else cnt.top_nodes++;
     }
-    bool inside = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
-                            : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
-    const int word = __float_as_int(n1.w);
-    if (!inside) {
-      cur = advance();
-    } else if (word_internal(word)) {
-      const int start = word_first_child(word);
-      int       neg   = (ray.sgn >> word_axis(word)) & 1;
-      push(start + 1 - neg);
-      cur = start + neg;
-    } else if (bottom) {
-      leaf_next = word_first_prim(word);
-      leaf_end  = leaf_next + word_num(word);
-      cur       = leaf_next < leaf_end ? kMarkLeaf : advance();
-    } else {
-      // leaf of the instance tree (<= 4 instances, visited in order): one ENTER entry for the run
-      const int num = word_num(word);
-      cur           = num > 0 ? ~(word_first_prim(word) | ((num - 1) << 28)) : advance();
-    }
+    const int  top_entry = peek();
+    const bool inside    = ray.exact ? slab_test_exact(ray.o, ray.dinv, tmin, tmax, n0, n1)
+                                     : slab_test_fast(ray.o, ray.dinv, tmin, tmax, n0, n1);
+    const int  word  = __float_as_int(n1.w);
+    const bool inner = inside && word_internal(word);
+    const int  num   = inside ? word_num(word) : 0;  // (read as a leaf word; unused for inner nodes)
+    const int  first = word_first_prim(word);
+    const int  start = word_first_child(word);
+    const int  neg   = (ray.sgn >> word_axis(word)) & 1;
+    if (inner) push(start + 1 - neg);
+    const bool leaf = !inner && num > 0;
+    if (leaf && bottom) leaf_next = first, leaf_end = first + num;
+    // leaf of the instance tree (<= 4 instances, visited in order): one ENTER entry for the run
+    const int leaf_cur = bottom ? kMarkLeaf : ~(first | (int)((unsigned)(num - 1) << 28));
+    if (!inner && !leaf) sp -= top_entry == kMarkDone ? 0 : 1;
+    cur = inner ? start + neg : leaf ? leaf_cur : top_entry;
   };
   // one primitive of the current leaf
   auto test_prim = [&](int idx) {
@@ -538,7 +546,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     cur = kMarkDone, sp = 1, have = false;
   };
   while (true) {
-    const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0);
+    const unsigned want_node  = __ballot_sync(kFullWarp, cur >= 0 || cur == kMarkExit);
     const unsigned want_prim  = __ballot_sync(kFullWarp, cur == kMarkLeaf);
     const unsigned want_enter = __ballot_sync(kFullWarp, cur < 0 && cur > kMarkLeaf);
     const unsigned busy       = want_node | want_prim | want_enter;
@@ -607,11 +615,11 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
           suspend_lane();
           break;
         }
-        if (cur >= 0) {
+        if (cur >= 0 || cur == kMarkExit) {
           visit_node();
         } else if (cur == kMarkLeaf) {
           while (leaf_next < leaf_end) test_prim(leaf_next++);
-          cur = advance();
+          cur = pop();
         } else {
           cur = enter(cur);
         }
@@ -624,7 +632,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
       // several node visits per scheduling round: cuts the vote overhead on the most frequent path
 #pragma unroll 1
       for (int rep = 0; rep < src.node_reps; rep++)
-        if (cur >= 0) visit_node();
+        if (cur >= 0 || cur == kMarkExit) visit_node();
     } else if (n_prim >= n_enter) {
       // all primitives of the lane's leaf (<= 4, bvh_max_prims) in one go, warp-uniform trip count
       const bool in_leaf = cur == kMarkLeaf;
@@ -633,7 +641,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
         if (!__any_sync(kFullWarp, test)) break;
         if (test) test_prim(leaf_next++);
       }
-      if (in_leaf) cur = advance();
+      if (in_leaf) cur = pop();
     } else {
       if (cur < 0 && cur > kMarkLeaf) cur = enter(cur);
     }
