@@ -68,6 +68,9 @@ PY
     launches)
       timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
       python tools/ncu_summary.py --launches gpurun_out/${TAG}_launches.csv | head -n 20 ;;
+    ncu_ext)   # two mid-frame launches of the extend kernel only, with source correlation
+      timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:'k_extend' -s 3 -c 2 -o gpurun_out/${TAG}_extend $PERF c3 1920 2 0 > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"
+      gzip -f gpurun_out/${TAG}_extend.ncu-rep ;;
     ncu)
       timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:'k_extend|k_shade|k_lightpdf|k_finish' -s 40 -c 8 -o gpurun_out/${TAG}_kernels $PERF c3 1920 2 0 > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"; tail -n 2 gpurun_out/${TAG}_ncu.log | cut -c1-200 ;;
   esac

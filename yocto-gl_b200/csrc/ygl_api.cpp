@@ -1286,6 +1286,7 @@ struct OptionRef {
 };
 const OptionRef kOptions[] = {
     {"ext_blocks_per_sm", &Tuning::ext_blocks_per_sm}, {"refill", &Tuning::refill}, {"node_reps", &Tuning::node_reps},
+    {"prim_weight", &Tuning::prim_weight}, {"enter_weight", &Tuning::enter_weight},
     {"suspend", &Tuning::suspend}, {"suspend_rounds", &Tuning::suspend_rounds}, {"lone", &Tuning::lone},
     {"lone_steps", &Tuning::lone_steps}, {"fuse", &Tuning::fuse}, {"bin", &Tuning::bin}, {"pipes", &Tuning::pipes},
     {"graph", &Tuning::graph}, {"top_smem", &Tuning::top_smem},

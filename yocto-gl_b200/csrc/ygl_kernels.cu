@@ -167,6 +167,7 @@ struct ExtendSource {
   int        has_volumes;
   int        lane;
   int        refill_thr, node_reps, suspend_below, lone_below, lone_steps;  // tuning knobs (see launch_extend)
+  int        prim_weight, enter_weight;                                     //   (path vote weights, in eighths)
   unsigned   finished;                              // rays completed by this thread (scene_rays counter)
   bool       shadow;                                // current ray is a shadow ray (pathdirect / pathmis)
   // Queue entries: lane id; bit 31 set = the ray was suspended by the previous launch (resume it).
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(128, YGL_EXT_MINBLOCKS) k_extend(const __grid_
   Counters*     c = q.counters;
   const int     n = c->n_ext[parity];
   ExtendSource<TAIL> src{q.ext[parity], n, &c->ext_head, st, q, parity, scene.inst_class, scene.has_volumes, 0, refill_thr,
-      node_reps, suspend_below, lone_below, lone_steps, 0, false};
+      node_reps & 0xff, suspend_below, lone_below, lone_steps, (node_reps >> 8) & 0xff, (node_reps >> 16) & 0xff, 0, false};
   trav_counters tc = {};
   trace_stream<COUNT, kStreamThreads, kSharedStack, STACK, ExtendSource<TAIL>, TOP>(scene, src, tc);
   {
@@ -1268,6 +1269,9 @@ void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene
   const int  sb       = tune.suspend >= 0 ? tune.suspend : (big_tile ? kSuspendBelow : 0);
   const int  suspend  = sb > 0 ? (std::min(sb, 31) | std::max(1, tune.suspend_rounds) << 8) : 0;
   const int  lone     = tune.lone >= 0 ? tune.lone : (big_tile ? 0 : 12);
+  // node visits per round and the two vote weights travel in one kernel argument
+  const int reps_and_weights = (std::max(1, tune.node_reps) & 0xff) | (std::min(255, std::max(1, tune.prim_weight)) << 8) |
+                               (std::min(255, std::max(1, tune.enter_weight)) << 16);
   // the stack variant the bound trees need (DScene::stack_mode): shared memory only, + a small local array, or the
   // full 128 levels per tree
   using kernel_t = void (*)(const DScene, const PathState, const Queues, int, unsigned long long*, int, int, int, int, int);
@@ -1289,12 +1293,12 @@ void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&top_per_sm, top_kernel, 128, top_bytes);
     int top_blocks = num_sms * std::max(1, tune.ext_blocks_per_sm > 0 ? std::min(top_per_sm, tune.ext_blocks_per_sm) : top_per_sm);
     top_blocks     = std::max(1, std::min(top_blocks, needed));
-    top_kernel<<<top_blocks, 128, top_bytes, s>>>(scene, st, q, parity, trav, tune.refill, tune.node_reps, suspend, lone,
+    top_kernel<<<top_blocks, 128, top_bytes, s>>>(scene, st, q, parity, trav, tune.refill, reps_and_weights, suspend, lone,
         tune.lone_steps);
     return;
   }
 #endif
-  kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, tune.refill, tune.node_reps, suspend, lone, tune.lone_steps);
+  kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, tune.refill, reps_and_weights, suspend, lone, tune.lone_steps);
 }
 
 template <int CLS>

@@ -135,6 +135,8 @@ struct Tuning {
   int ext_blocks_per_sm = 0;  // extend grid: blocks per SM (0 = the occupancy maximum)
   int refill            = 8;  // extend: idle lanes of a warp that trigger a refill
   int node_reps         = 3;  // extend: node visits per scheduling round
+  int prim_weight       = 12;  // extend: weight (in eighths) of the lanes waiting for primitive tests in the path vote
+  int enter_weight      = 12; //   ... and of the lanes waiting to enter an instance (8 = plain majority; measured on B200: 12 / 12 wins 2 %)
   int suspend           = -1; // extend tail: park a drained warp's stragglers once <= this many lanes are busy (-1 = by tile size, 0 = never)
   int suspend_rounds    = 96; //   ... after at least this many rounds
   int lone              = -1; // extend tail: vote-free walk of the last <= this many lanes (-1 = by tile size, 0 = never)

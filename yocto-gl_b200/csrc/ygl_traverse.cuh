@@ -387,6 +387,9 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
   // deeper entries spill to a per-thread local array (rare: kSharedStack covers a 1000-instance tree
   // plus a 64K-primitive shape tree).
   __shared__ int s_stack[kSharedStack][THREADS];
+#ifdef YGL_COOP_PRIMS
+  __shared__ unsigned char s_tasks[THREADS / 32][128];  // per warp: (owner lane | primitive of its leaf << 5) per numbered test
+#endif
   int            l_stack[kSpill ? (STACK == kStackDeep ? 2 * kStackSize + 8 : kShallowStack) - kSharedStack : 1];
   // The thread's column of the shared stack as a 32-bit shared-space address, computed once: through the generic
   // `s_stack[sp][tix]` form every push and pop recomputed the shared window base (S2UR CgaCtaId / ULEA / UMOV: 11 % of
@@ -508,28 +511,28 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     if (!inner && !leaf) sp -= top_entry == kMarkDone ? 0 : 1;
     cur = inner ? start + neg : leaf ? leaf_cur : top_entry;
   };
+  // one primitive test: element `idx` of a shape of type `kd` whose leaf packets start at `pk`, against the ray (o, d)
+  // with the range [tmin, tmx]
+  auto test_element = [&](const f3& o, const f3& d, float tmx, const float4* pk, int kd, int idx, f2& puv, float& pd) {
+    if (kd == kElemTriangles) {
+      float4 a = __ldg(pk + 3 * idx), b = __ldg(pk + 3 * idx + 1), c = __ldg(pk + 3 * idx + 2);
+      return hit_triangle(o, d, tmin, tmx, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
+    } else if (kd == kElemQuads) {
+      float4 a = __ldg(pk + 4 * idx), b = __ldg(pk + 4 * idx + 1), c = __ldg(pk + 4 * idx + 2), e = __ldg(pk + 4 * idx + 3);
+      return hit_quad(o, d, tmin, tmx, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z}, f3{e.x, e.y, e.z}, puv, pd);
+    } else if (kd == kElemLines) {
+      float4 a = __ldg(pk + 2 * idx), b = __ldg(pk + 2 * idx + 1);
+      return hit_line(o, d, tmin, tmx, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
+    }
+    float4 a = __ldg(pk + idx);
+    return hit_point(o, d, tmin, tmx, f3{a.x, a.y, a.z}, a.w, puv, pd);
+  };
   // one primitive of the current leaf
   auto test_prim = [&](int idx) {
     if (COUNT) cnt.prims_by_kind[kind]++;
     f2    puv = {0, 0};
     float pd  = 0;
-    bool  h;
-    if (kind == kElemTriangles) {
-      float4 a = __ldg(packets + 3 * idx), b = __ldg(packets + 3 * idx + 1), c = __ldg(packets + 3 * idx + 2);
-      h = hit_triangle(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y}, f3{b.z, b.w, c.x}, puv, pd);
-    } else if (kind == kElemQuads) {
-      float4 a = __ldg(packets + 4 * idx), b = __ldg(packets + 4 * idx + 1), c = __ldg(packets + 4 * idx + 2),
-             e = __ldg(packets + 4 * idx + 3);
-      h = hit_quad(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, f3{c.x, c.y, c.z},
-          f3{e.x, e.y, e.z}, puv, pd);
-    } else if (kind == kElemLines) {
-      float4 a = __ldg(packets + 2 * idx), b = __ldg(packets + 2 * idx + 1);
-      h = hit_line(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, f3{b.x, b.y, b.z}, a.w, b.w, puv, pd);
-    } else {
-      float4 a = __ldg(packets + idx);
-      h = hit_point(ray.o, ray.d, tmin, tmax, f3{a.x, a.y, a.z}, a.w, puv, pd);
-    }
-    if (h) {
+    if (test_element(ray.o, ray.d, tmax, packets, kind, idx, puv, pd)) {
       res  = {cur_instance, __ldg(prims + idx), puv, pd, true};
       tmax = pd;
     }
@@ -628,12 +631,73 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
     }
     const int n_node = __popc(want_node), n_prim = __popc(want_prim), n_enter = __popc(want_enter);
 
-    if (n_node >= n_prim && n_node >= n_enter) {
+    // the path most lanes wait for runs; prim_weight / enter_weight (eighths) can tilt the vote towards the two
+    // minority paths, whose lanes would otherwise sit out until they outnumber the node walkers
+    const int v_node = 8 * n_node, v_prim = src.prim_weight * n_prim, v_enter = src.enter_weight * n_enter;
+    if (v_node >= v_prim && v_node >= v_enter) {
       // several node visits per scheduling round: cuts the vote overhead on the most frequent path
 #pragma unroll 1
       for (int rep = 0; rep < src.node_reps; rep++)
         if (cur >= 0 || cur == kMarkExit) visit_node();
-    } else if (n_prim >= n_enter) {
+#ifdef YGL_COOP_PRIMS
+    } else if (v_prim >= v_enter) {
+      // ---- primitive tests, spread over the whole warp: the leaves of the waiting lanes hold 1-4 primitives each; all
+      // of them are numbered (owner lanes in lane order, a leaf's primitives in leaf order) and lane w tests number w,
+      // w + 32, ... on behalf of its owner, whose ray it fetches with shuffles. Owners then take their results in leaf
+      // order: a primitive counts if the test passed with the range the owner had when the round began AND its distance
+      // is not beyond the owner's current tmax - the same decisions as testing one after the other (a hit only ever
+      // shrinks tmax; should tmax become NaN, the rest of that leaf is tested one by one). ----
+      const int      wl      = tix & 31;
+      const bool     in_leaf = cur == kMarkLeaf;
+      const int      mine    = in_leaf ? leaf_end - leaf_next : 0;
+      const unsigned lt      = (1u << wl) - 1u;
+      const unsigned b0 = __ballot_sync(kFullWarp, mine & 1), b1 = __ballot_sync(kFullWarp, mine & 2),
+                     b2 = __ballot_sync(kFullWarp, mine & 4);
+      const int my_first = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+      const int total    = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+      unsigned char* tasks = s_tasks[tix >> 5];
+      for (int k = 0; k < 4; k++)
+        if (k < mine) tasks[my_first + k] = (unsigned char)(wl | k << 5);
+      __syncwarp();
+      if (COUNT && in_leaf) cnt.prims_by_kind[kind] += mine;
+      int                      taken = -1, redo_from = 4;
+      const unsigned long long pk64  = (unsigned long long)packets;
+      for (int base = 0; base < total; base += 32) {
+        const int  t    = base + wl;
+        const bool work = t < total;
+        const int  task = tasks[work ? t : 0];
+        const int  from = task & 31, k = task >> 5;
+        const f3   o    = {__shfl_sync(kFullWarp, ray.o.x, from), __shfl_sync(kFullWarp, ray.o.y, from), __shfl_sync(kFullWarp, ray.o.z, from)};
+        const f3   d    = {__shfl_sync(kFullWarp, ray.d.x, from), __shfl_sync(kFullWarp, ray.d.y, from), __shfl_sync(kFullWarp, ray.d.z, from)};
+        const float tmx = __shfl_sync(kFullWarp, tmax, from);
+        const int   idx = __shfl_sync(kFullWarp, leaf_next, from) + k;
+        const int   kd  = __shfl_sync(kFullWarp, kind, from);
+        const float4* pk = (const float4*)(((unsigned long long)__shfl_sync(kFullWarp, (unsigned)(pk64 >> 32), from) << 32) |
+                                           __shfl_sync(kFullWarp, (unsigned)pk64, from));
+        f2    puv = {0, 0};
+        float pd  = 0;
+        const bool     h    = work && test_element(o, d, tmx, pk, kd, idx, puv, pd);
+        const unsigned hits = __ballot_sync(kFullWarp, h);
+        for (int k2 = 0; k2 < 4; k2++) {
+          const int   tt = my_first + k2, lane_of = tt & 31;
+          const float ru = __shfl_sync(kFullWarp, puv.x, lane_of), rv = __shfl_sync(kFullWarp, puv.y, lane_of),
+                      rt = __shfl_sync(kFullWarp, pd, lane_of);
+          if (k2 < mine && k2 < redo_from && tt >= base && tt < base + 32 && (hits >> lane_of & 1) && !(rt > tmax)) {
+            res.instance = cur_instance, res.uv = {ru, rv}, res.distance = rt, res.hit = true;
+            tmax  = rt;
+            taken = k2;
+            if (rt != rt) redo_from = k2 + 1;
+          }
+        }
+      }
+      if (in_leaf) {
+        if (taken >= 0) res.element = __ldg(prims + leaf_next + taken);
+        for (int k = redo_from; k < mine; k++) test_prim(leaf_next + k);  // (tmax is NaN: practically never)
+        leaf_next = leaf_end;
+        cur       = pop();
+      }
+#else
+    } else if (v_prim >= v_enter) {
       // all primitives of the lane's leaf (<= 4, bvh_max_prims) in one go, warp-uniform trip count
       const bool in_leaf = cur == kMarkLeaf;
       for (int k = 0; k < 4; k++) {
@@ -642,6 +706,7 @@ YGL_D void trace_stream(const DScene& scene, Source& src, trav_counters& cnt) {
         if (test) test_prim(leaf_next++);
       }
       if (in_leaf) cur = pop();
+#endif
     } else {
       if (cur < 0 && cur > kMarkLeaf) cur = enter(cur);
     }
