@@ -68,6 +68,11 @@ PY
     launches)
       timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_ncu.log 2>&1; echo "launches rc=$?"
       python tools/ncu_summary.py --launches gpurun_out/${TAG}_launches.csv | head -n 20 ;;
+    sweep)   # SWEEP="c3 1920 32 2 tile=0,8 profile=1 refill=4;..." : one gpu_perf.py line per entry
+      IFS=';' read -ra RUNS <<< "$SWEEP"
+      for RUN in "${RUNS[@]}"; do
+        timeout -s KILL 150 $PERF $RUN 2>&1 | tail -n 1 | cut -c1-250
+      done ;;
     ncu_ext)   # two mid-frame launches of the extend kernel only, with source correlation
       timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:'k_extend' -s 3 -c 2 -o gpurun_out/${TAG}_extend $PERF c3 1920 2 0 > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"
       gzip -f gpurun_out/${TAG}_extend.ncu-rep ;;
