@@ -729,12 +729,11 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
     return o;
   };
   // reference-layout accumulators (downloaded as they are), per-lane scalars, then the path state as interleaved
-  // pairs of 16-byte records (PathStateT): 32 bytes per lane and pair
+  // groups of 16-byte records (PathStateT)
   size_t o_image = take(lanes * 16), o_albedo = take(lanes * 12), o_normal = take(lanes * 12), o_hits = take(lanes * 4),
          o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_hid = take(lanes * 8), o_susp = take(lanes * 4),
          o_ai = take(lanes * 8), o_ni = take(lanes * 8);
-  size_t o_pair[8];
-  for (auto& o : o_pair) o = take(lanes * 32);
+  size_t o_groups = take(lanes * 16 * 16);  // 16 float4 records per lane, interleaved in groups (see below)
   CUDA_TRY(cudaMalloc((void**)&state->mem, off));
   CUDA_TRY(cudaMemset(state->mem, 0, off));
   PathState& st = state->st;
@@ -751,19 +750,16 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
   st.susp     = (int*)(m + o_susp);
   st.aux_ids  = (int2*)(m + o_ai);
   st.next_ids = (int2*)(m + o_ni);
-  auto pair = [&](int k, SPair<false>& a, SPair<false>& b) {
-    a = (float4*)(m + o_pair[k]);
-    b = (float4*)(m + o_pair[k]) + 1;
-  };
-  pair(0, st.ray_o, st.ray_d);         // read together by extend, shade, light pdf
-  pair(1, st.radiance, st.weight);     // shade, accumulate
-  pair(2, st.hit_uvd, st.pend);        // shade reads the hit and writes the pending MIS numerator
-  pair(3, st.albedo0, st.normal0);     // bounce-0 guides
-  pair(4, st.vol_a, st.vol_b);         // the volume slot
-  pair(5, st.aux_o, st.aux_dir);       // shadow-ray origin and direction (pathdirect / pathmis)
-  pair(6, st.aux_uvd, st.aux_bsdf);
   SPair<false> spare;
-  pair(7, st.next_uvd, spare);
+  SPair<false>* members[16] = {&st.ray_o, &st.ray_d,  // read together by extend, shade, light pdf
+      &st.radiance, &st.weight,                          // shade, accumulate
+      &st.hit_uvd, &st.pend,                             // shade reads the hit and writes the pending MIS numerator
+      &st.albedo0, &st.normal0,                          // bounce-0 guides
+      &st.vol_a, &st.vol_b,                              // the volume slot
+      &st.aux_o, &st.aux_dir,                            // shadow-ray origin and direction (pathdirect / pathmis)
+      &st.aux_uvd, &st.aux_bsdf, &st.next_uvd, &spare};
+  constexpr int kGroup = YGL_STATE_GROUP;  // consecutive members share one 16 * kGroup byte record per lane
+  for (int k = 0; k < 16; k++) *members[k] = (float4*)(m + o_groups + (size_t)(k / kGroup) * lanes * 16 * kGroup) + k % kGroup;
   // rng table: seeded sequentially over the FULL image (yocto_trace.cpp:1512-1515), tile slice uploaded
   std::vector<uint64_t> rngs((size_t)w * h * 2);
   state_rngs(*params, w, h, rngs.data());

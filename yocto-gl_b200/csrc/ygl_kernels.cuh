@@ -51,8 +51,11 @@ struct SArr {
 // stored as interleaved pairs {a[lane], b[lane]} = one sector (ray_o|ray_d, radiance|weight, hit_uvd|pend, ...).
 // One lane = one pixel of the tile (the only legal parallel axis: each pixel's samples form a
 // sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
+#ifndef YGL_STATE_GROUP
+#define YGL_STATE_GROUP 2  // float4 records interleaved per lane: 2 = pairs (one 32-byte sector), 4 = quads (64 bytes)
+#endif
 template <bool COH>
-using SPair = SArr<float4, COH, 2>;  // one half of an interleaved pair of float4 records
+using SPair = SArr<float4, COH, YGL_STATE_GROUP>;  // one member of an interleaved group of float4 records
 template <bool COH>
 struct PathStateT {
   int num_lanes;  // pixels in this tile
