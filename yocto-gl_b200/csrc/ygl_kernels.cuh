@@ -48,11 +48,13 @@ struct SArr {
 
 // Per-lane wavefront state: 16-byte records, moved as whole 128-bit words. Lanes reach a stage in queue order, i.e.
 // scattered, so every 16-byte access costs a 32-byte DRAM sector; records that a stage touches together are therefore
-// stored as interleaved pairs {a[lane], b[lane]} = one sector (ray_o|ray_d, radiance|weight, hit_uvd|pend, ...).
+// stored interleaved, YGL_STATE_GROUP of them per lane: neighbours share a 32-byte sector (ray_o|ray_d, radiance|weight,
+// hit_uvd|misc, ...) and the hot eight share one 128-byte line.
 // One lane = one pixel of the tile (the only legal parallel axis: each pixel's samples form a
 // sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
 #ifndef YGL_STATE_GROUP
-#define YGL_STATE_GROUP 2  // float4 records interleaved per lane: 2 = pairs (one 32-byte sector), 4 = quads (64 bytes)
+#define YGL_STATE_GROUP 8  // float4 records interleaved per lane. Measured on B200 (C3 frame): pairs -4 % against separate arrays,
+                           // quads another -2.8 %, eight (one 128-byte line per lane) another -1.1 %
 #endif
 template <bool COH>
 using SPair = SArr<float4, COH, YGL_STATE_GROUP>;  // one member of an interleaved group of float4 records
@@ -67,20 +69,20 @@ struct PathStateT {
   SArr<int, COH>        hits;
   SArr<ulonglong2, COH> rngs;  // rng_state {state, inc}
   // ---- per-lane progress ----
-  SArr<int, COH> sample;  // index of the sample in flight
+  SArr<int, COH, 4 * YGL_STATE_GROUP> sample;  // index of the sample in flight (third word of the lane's `misc` record)
   // ---- path in flight ----
   SPair<COH>        ray_o;     // origin.xyz, w: bounce (int bits)
   SPair<COH>        ray_d;     // direction.xyz, w: opbounce (int bits)
   SPair<COH>        radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
   SPair<COH>        weight;    // rgb, w: max_roughness
   SPair<COH>        hit_uvd;   // uv.x uv.y distance hit(int bits)
-  SArr<int2, COH>   hit_ids;   // instance, element
+  SArr<int2, COH, 2 * YGL_STATE_GROUP> hit_ids;  // instance, element (first half of the lane's `misc` record, next to hit_uvd)
   SPair<COH>        albedo0;   // bounce-0 albedo rgb, w unused
   SPair<COH>        normal0;   // bounce-0 normal (or -camera dir on miss) xyz
   SPair<COH>        vol_a;     // volume slot: density.xyz, scanisotropy
   SPair<COH>        vol_b;     // volume slot: scattering.xyz
   SPair<COH>        pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
-  SArr<int, COH>    susp;      // save slot of the lane's ray while it is parked by k_extend (see Queues::park)
+  SArr<int, COH, 4 * YGL_STATE_GROUP> susp;  // save slot of the lane's ray while it is parked by k_extend (fourth word of `misc`)
   // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
   SPair<COH>        aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
   SPair<COH>        aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
