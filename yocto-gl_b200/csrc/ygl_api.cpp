@@ -731,7 +731,7 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
   // reference-layout accumulators (downloaded as they are), per-lane scalars, then the path state as interleaved
   // groups of 16-byte records (PathStateT)
   size_t o_image = take(lanes * 16), o_albedo = take(lanes * 12), o_normal = take(lanes * 12), o_hits = take(lanes * 4),
-         o_rngs = take(lanes * 16),
+         o_rngs = take(lanes * 16), o_sample = take(lanes * 4), o_hid = take(lanes * 8), o_susp = take(lanes * 4),
          o_ai = take(lanes * 8), o_ni = take(lanes * 8);
   size_t o_groups = take(lanes * 16 * 16);  // 16 float4 records per lane, interleaved in groups (see below)
   CUDA_TRY(cudaMalloc((void**)&state->mem, off));
@@ -745,21 +745,21 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
   st.normal   = (float*)(m + o_normal);
   st.hits     = (int*)(m + o_hits);
   st.rngs     = (ulonglong2*)(m + o_rngs);
+  st.sample   = (int*)(m + o_sample);
+  st.hit_ids  = (int2*)(m + o_hid);
+  st.susp     = (int*)(m + o_susp);
   st.aux_ids  = (int2*)(m + o_ai);
   st.next_ids = (int2*)(m + o_ni);
-  SPair<false> misc;  // {hit instance, hit element, sample index, park slot}: hit_ids / sample / susp point into it
+  SPair<false> spare;
   SPair<false>* members[16] = {&st.ray_o, &st.ray_d,  // read together by extend, shade, light pdf
       &st.radiance, &st.weight,                          // shade, accumulate
-      &st.hit_uvd, &misc,                                // written together when extend commits a ray, read by shade
-      &st.pend, &st.normal0,                             // pending MIS numerator; bounce-0 normal
-      &st.albedo0, &st.vol_a, &st.vol_b,                 // bounce-0 albedo, the volume slot
+      &st.hit_uvd, &st.pend,                             // shade reads the hit and writes the pending MIS numerator
+      &st.albedo0, &st.normal0,                          // bounce-0 guides
+      &st.vol_a, &st.vol_b,                              // the volume slot
       &st.aux_o, &st.aux_dir,                            // shadow-ray origin and direction (pathdirect / pathmis)
-      &st.aux_uvd, &st.aux_bsdf, &st.next_uvd};
+      &st.aux_uvd, &st.aux_bsdf, &st.next_uvd, &spare};
   constexpr int kGroup = YGL_STATE_GROUP;  // consecutive members share one 16 * kGroup byte record per lane
   for (int k = 0; k < 16; k++) *members[k] = (float4*)(m + o_groups + (size_t)(k / kGroup) * lanes * 16 * kGroup) + k % kGroup;
-  st.hit_ids = (int2*)(float4*)misc;
-  st.sample  = (int*)(float4*)misc + 2;
-  st.susp    = (int*)(float4*)misc + 3;
   // rng table: seeded sequentially over the FULL image (yocto_trace.cpp:1512-1515), tile slice uploaded
   std::vector<uint64_t> rngs((size_t)w * h * 2);
   state_rngs(*params, w, h, rngs.data());

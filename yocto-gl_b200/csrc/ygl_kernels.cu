@@ -199,7 +199,8 @@ struct ExtendSource {
     int cls = kClsGeneric;
     if (flag) {
       (shadow ? st.aux_uvd : st.hit_uvd)[lane] = make_float4(h.uv.x, h.uv.y, h.distance, __int_as_float(h.hit ? 1 : 0));
-      (shadow ? st.aux_ids : st.hit_ids)[lane] = make_int2(h.instance, h.element);
+      if (shadow) st.aux_ids[lane] = make_int2(h.instance, h.element);  // (the two arrays differ in stride: no ?: between them)
+      else st.hit_ids[lane] = make_int2(h.instance, h.element);
       finished++;
       if (inst_class) {
         cls = h.hit ? (int)__ldg(inst_class + h.instance) : kClsMiss;

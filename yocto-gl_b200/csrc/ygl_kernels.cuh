@@ -31,13 +31,26 @@ struct SRef {
   }
 #endif
 };
-// STRIDE (in elements): 2 for the path-state records that are stored as interleaved PAIRS (see PathStateT) so that
-// the two 16-byte halves a stage reads together share one 32-byte DRAM sector.
+// STRIDE (in elements): > 1 for the path-state records that are stored interleaved per lane (see PathStateT).
+// Strided arrays do NOT decay to their pointer: two arrays of different stride in a ?: would both decay and then be
+// indexed as contiguous (that happened once). Contiguous ones (the specialisation below) do: memcpy, memset.
 template <class T, bool COH, int STRIDE = 1>
 struct SArr {
   T* p;
 #ifdef __CUDACC__
   __device__ __forceinline__ SRef<T, COH> operator[](long long i) const { return SRef<T, COH>{p + i * STRIDE}; }
+#endif
+  __host__ __device__ explicit operator T*() const { return p; }
+  __host__ __device__ SArr& operator=(T* q) {
+    p = q;
+    return *this;
+  }
+};
+template <class T, bool COH>
+struct SArr<T, COH, 1> {
+  T* p;
+#ifdef __CUDACC__
+  __device__ __forceinline__ SRef<T, COH> operator[](long long i) const { return SRef<T, COH>{p + i}; }
 #endif
   __host__ __device__ operator T*() const { return p; }
   __host__ __device__ SArr& operator=(T* q) {
@@ -49,7 +62,8 @@ struct SArr {
 // Per-lane wavefront state: 16-byte records, moved as whole 128-bit words. Lanes reach a stage in queue order, i.e.
 // scattered, so every 16-byte access costs a 32-byte DRAM sector; records that a stage touches together are therefore
 // stored interleaved, YGL_STATE_GROUP of them per lane: neighbours share a 32-byte sector (ray_o|ray_d, radiance|weight,
-// hit_uvd|misc, ...) and the hot eight share one 128-byte line.
+// hit_uvd|pend, ...) and the hot eight share one 128-byte line. (Packing hit_ids / sample / susp into a ninth record
+// next to hit_uvd was measured too: +3.8 % on the C3 frame, dropped.)
 // One lane = one pixel of the tile (the only legal parallel axis: each pixel's samples form a
 // sequential chain through its rng stream and running mean, yocto_trace.cpp:1461-1492).
 #ifndef YGL_STATE_GROUP
@@ -69,20 +83,20 @@ struct PathStateT {
   SArr<int, COH>        hits;
   SArr<ulonglong2, COH> rngs;  // rng_state {state, inc}
   // ---- per-lane progress ----
-  SArr<int, COH, 4 * YGL_STATE_GROUP> sample;  // index of the sample in flight (third word of the lane's `misc` record)
+  SArr<int, COH> sample;  // index of the sample in flight
   // ---- path in flight ----
   SPair<COH>        ray_o;     // origin.xyz, w: bounce (int bits)
   SPair<COH>        ray_d;     // direction.xyz, w: opbounce (int bits)
   SPair<COH>        radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
   SPair<COH>        weight;    // rgb, w: max_roughness
   SPair<COH>        hit_uvd;   // uv.x uv.y distance hit(int bits)
-  SArr<int2, COH, 2 * YGL_STATE_GROUP> hit_ids;  // instance, element (first half of the lane's `misc` record, next to hit_uvd)
+  SArr<int2, COH>   hit_ids;   // instance, element
   SPair<COH>        albedo0;   // bounce-0 albedo rgb, w unused
   SPair<COH>        normal0;   // bounce-0 normal (or -camera dir on miss) xyz
   SPair<COH>        vol_a;     // volume slot: density.xyz, scanisotropy
   SPair<COH>        vol_b;     // volume slot: scattering.xyz
   SPair<COH>        pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
-  SArr<int, COH, 4 * YGL_STATE_GROUP> susp;  // save slot of the lane's ray while it is parked by k_extend (fourth word of `misc`)
+  SArr<int, COH>    susp;      // save slot of the lane's ray while it is parked by k_extend (see Queues::park)
   // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
   SPair<COH>        aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
   SPair<COH>        aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
