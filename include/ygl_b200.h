@@ -358,6 +358,16 @@ int ygl_intersect_rays(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* 
 int ygl_intersect_rays_device(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh,
     const void* d_rays, int64_t n, int instance, int find_any, void* d_out, void* d_counters);
 
+/* ---- post-process: tonemap_image (yocto_image.h:242-245, yocto_image.cpp:911-922; tonemap yocto_color.h:356-366) ----
+ * HDR -> LDR of `num_pixels` vec4f pixels: rgb *= exp2(exposure) if exposure != 0, the ACES fit if filmic, the sRGB
+ * curve if srgb, alpha copied; results are bit-identical to the reference's (its float libm is restated on the device).
+ * `ldr` (vec4f per pixel) and / or `ldr_bytes` (vec4b per pixel = float_to_byte of it) are written; either may be null. */
+int ygl_tonemap_image(ygl_context* ctx, const float* hdr, int64_t num_pixels, float exposure, int filmic, int srgb,
+    float* ldr, uint8_t* ldr_bytes);
+/* The same on the image a state holds on its device (the tile's pixels, row-major): what an interactive viewer shows
+ * after every batch (apps/ytrace.cpp:219-226) without downloading the float image first. */
+int ygl_state_tonemap(ygl_state* state, float exposure, int filmic, int srgb, float* ldr, uint8_t* ldr_bytes);
+
 /* Test hook: the device-side libm (glibc's float routines restated for the GPU) applied to host arrays.
  * fn: 0 sin, 1 cos, 2 exp, 3 log, 4 atan, 5 acos, 6 atan2(x[i], y[i]), 7 pow(x[i], y[i]), 8 sqrt, 9 fmod. */
 int ygl_debug_libm(ygl_context* ctx, int fn, const float* x, const float* y, int64_t n, float* out);

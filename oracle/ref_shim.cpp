@@ -16,6 +16,7 @@
 #include <yocto/yocto_scene.h>
 #include <yocto/yocto_sceneio.h>
 #include <yocto/yocto_shape.h>
+#include <yocto/yocto_image.h>
 #include <yocto/yocto_trace.h>
 
 #include <chrono>
@@ -389,6 +390,17 @@ double ref_trace_image(void* scene_, const ygl_trace_params* params_, int sample
   if (hits) memcpy(hits, state.hits.data(), n * sizeof(int));
   if (rngs) memcpy(rngs, state.rngs.data(), n * sizeof(rng_state));
   return elapsed;
+}
+
+// tonemap_image, yocto_image.cpp:911-922 (both outputs)
+void ref_tonemap_image(const float* hdr, int64_t n, float exposure, int filmic, int srgb, float* ldr, uint8_t* ldr_bytes) {
+  auto in = vector<vec4f>((const vec4f*)hdr, (const vec4f*)hdr + n);
+  auto f  = vector<vec4f>(n);
+  auto b  = vector<vec4b>(n);
+  tonemap_image(f, in, exposure, filmic != 0, srgb != 0);
+  tonemap_image(b, in, exposure, filmic != 0, srgb != 0);
+  if (ldr) memcpy(ldr, f.data(), n * sizeof(vec4f));
+  if (ldr_bytes) memcpy(ldr_bytes, b.data(), n * sizeof(vec4b));
 }
 
 int ref_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }

@@ -37,6 +37,7 @@ class Ref:
         lib.ref_bvh_build.argtypes = [vp, C.c_int]
         lib.ref_bvh_destroy.argtypes = [vp]
         lib.ref_bvh_update.argtypes = [vp, vp, vp, C.c_int]
+        lib.ref_tonemap_image.argtypes = [vp, C.c_int64, C.c_float, C.c_int, C.c_int, vp, vp]
         lib.ref_bvh_tree_size.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.ref_bvh_tree_get.argtypes = [vp, C.c_int, vp, vp]
         lib.ref_intersect_rays.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int]
@@ -97,6 +98,14 @@ class Ref:
         sc = abi.Scene.from_desc(d)
         self.lib.ref_scene_destroy(h)
         return sc
+
+    def tonemap_image(self, hdr, exposure=0.0, filmic=False, srgb=True):
+        """tonemap_image (yocto_image.cpp:911-922): (vec4f image, vec4b image)"""
+        hdr = np.ascontiguousarray(hdr, np.float32)
+        ldr, ldr_b = np.zeros_like(hdr), np.zeros(hdr.shape, np.uint8)
+        self.lib.ref_tonemap_image(hdr.ctypes.data, hdr.size // 4, exposure, int(filmic), int(srgb), ldr.ctypes.data,
+                                   ldr_b.ctypes.data)
+        return ldr, ldr_b
 
     def rng_floats(self, seed, seq, n):
         out = np.zeros(n, np.float32)

@@ -651,3 +651,35 @@ def test_refitted_bvh(ctx, ref, name):
     st = ds2.make_state(params)
     ds2.trace_samples(st, params)
     assert st.download()["image"].tobytes() == want["image"].tobytes()
+
+
+def test_tonemap_matches_reference(ctx, ref):
+    """ygl_tonemap_image / ygl_state_tonemap against tonemap_image (yocto_image.cpp:911-922): vec4f and vec4b outputs bit
+    for bit, on a rendered frame and on a sweep that covers the sRGB knee, denormals, huge values, negatives, inf, NaN."""
+    rng = np.random.default_rng(11)
+    special = np.array([0.0, -0.0, 1e-45, 1e-8, 0.0031307, 0.0031308, 0.0031309, 0.18, 0.5, 1.0, 1.0000001, 3.9, 255.0 / 256,
+                        1e4, 3e38, np.inf, -1e-3, -2.5, -np.inf, np.nan], np.float32)
+    sweep = np.concatenate([special, np.exp(rng.uniform(-30, 12, 60000)).astype(np.float32),
+                            rng.uniform(0, 1.2, 60000).astype(np.float32)])
+    sweep = np.resize(sweep, (len(sweep) // 4 + 1) * 4).reshape(-1, 4)
+    scene = get_scene("features")
+    params = abi.trace_params(resolution=96, samples=4, bounces=4, batch=4)
+    ds = lib.DeviceScene(ctx, scene)
+    st = ds.make_state(params)
+    ds.trace_samples(st, params)
+    frame = st.download()["image"]
+    for exposure in (0.0, 1.5, -2.25):
+        for filmic in (False, True):
+            for srgb in (False, True):
+                for hdr in (sweep, frame):
+                    want_f, want_b = ref.tonemap_image(hdr, exposure, filmic, srgb)
+                    got_f, got_b = ctx.tonemap_image(hdr, exposure, filmic, srgb)
+                    key = (exposure, filmic, srgb, hdr.shape)
+                    assert got_b.tobytes() == want_b.tobytes(), key
+                    ok = (got_f.view(np.uint32) == want_f.view(np.uint32)) | (np.isnan(got_f) & np.isnan(want_f))
+                    assert ok.all(), (key, hdr.reshape(-1)[~ok.reshape(-1)][:8])
+                want_f, want_b = ref.tonemap_image(frame, exposure, filmic, srgb)
+                got_f, got_b = st.tonemap(exposure, filmic, srgb)
+                assert got_f.tobytes() == want_f.tobytes() and got_b.tobytes() == want_b.tobytes(), (exposure, filmic, srgb)
+    with pytest.raises(lib.YglError):
+        lib._check(ctx.lib.ygl_tonemap_image(ctx.h, None, 4, 0.0, 0, 1, None, None))

@@ -1230,6 +1230,41 @@ __global__ void k_debug_libm(int fn, const float* __restrict__ x, const float* _
     out[i] = r;
   }
 }
+// ---- tonemap_image, yocto_image.cpp:911-922 (tonemap: yocto_color.h:356-366; tonemap_filmic :287-296; rgb_to_srgb
+// :239-242; float_to_byte :218-222). exp2(exposure) is evaluated once, on the host, by the same libm the reference
+// calls; the per-pixel arithmetic (ACES fit, one powf per channel) runs here, bit for bit. ----
+YGL_D float tonemap_channel(float v, float scale, bool scaled, bool filmic, bool srgb) {
+  if (scaled) v = v * scale;
+  if (filmic) {
+    float h = v * 0.6f;
+    float l = (h * h * 2.51f + h * 0.03f) / (h * h * 2.43f + h * 0.59f + 0.14f);
+    v       = (0.0f > l) ? 0.0f : l;  // max({0,0,0}, ldr): yocto's max keeps a NaN
+  }
+  if (srgb) v = (v <= 0.0031308f) ? 12.92f * v : (1 + 0.055f) * ypow(v, 1 / 2.4f) - 0.055f;
+  return v;
+}
+// int(a * 256) as the reference's x86-64 build computes it (cvttss2si: NaN and out-of-range give INT_MIN), then clamp
+YGL_D unsigned char tonemap_byte(float a) {
+  float v = a * 256;
+  int   i = (v >= -2147483648.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000;
+  return (unsigned char)(i < 0 ? 0 : i > 255 ? 255 : i);
+}
+__global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ hdr, long long n, float scale, int scaled, int filmic,
+    int srgb, float4* __restrict__ ldr, uchar4* __restrict__ ldr_bytes) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = hdr[i];
+    float4 o = make_float4(tonemap_channel(p.x, scale, scaled, filmic, srgb), tonemap_channel(p.y, scale, scaled, filmic, srgb),
+        tonemap_channel(p.z, scale, scaled, filmic, srgb), p.w);
+    if (ldr) ldr[i] = o;
+    if (ldr_bytes) ldr_bytes[i] = make_uchar4(tonemap_byte(o.x), tonemap_byte(o.y), tonemap_byte(o.z), tonemap_byte(o.w));
+  }
+}
+void launch_tonemap(cudaStream_t s, int num_sms, const float4* hdr, long long n, float scale, bool scaled, bool filmic, bool srgb,
+    float4* ldr, uchar4* ldr_bytes) {
+  if (n <= 0) return;
+  const long long blocks = std::min<long long>((n + 255) / 256, (long long)num_sms * 8);
+  k_tonemap<<<(unsigned)blocks, 256, 0, s>>>(hdr, n, scale, scaled ? 1 : 0, filmic ? 1 : 0, srgb ? 1 : 0, ldr, ldr_bytes);
+}
 void launch_debug_libm(cudaStream_t s, int fn, const float* x, const float* y, long long n, float* out) {
   k_debug_libm<<<1184, 256, 0, s>>>(fn, x, y, n, out);
 }

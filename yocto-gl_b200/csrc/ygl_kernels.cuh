@@ -188,5 +188,8 @@ void launch_intersect_rays(cudaStream_t s, LaunchCfg cfg, DScene scene, const fl
     int find_any, void* out, unsigned long long* counters);
 
 void launch_debug_libm(cudaStream_t s, int fn, const float* x, const float* y, long long n, float* out);
+// tonemap_image (yocto_image.cpp:911-922): scale = exp2(exposure) from the host; ldr and / or ldr_bytes may be null
+void launch_tonemap(cudaStream_t s, int num_sms, const float4* hdr, long long n, float scale, bool scaled, bool filmic, bool srgb,
+    float4* ldr, uchar4* ldr_bytes);
 
 }  // namespace ygl

@@ -128,6 +128,25 @@ inline std::unique_ptr<b200_bvh> make_trace_bvh(const scene_data& scene, const t
   check(ygl_bvh_build(&views.desc, params.highqualitybvh ? 1 : 0, &out->handle));
   return out;
 }
+// tonemap_image (yocto_image.h:242-245): HDR -> LDR on the device, bit-identical to the CPU version
+inline void tonemap_image(b200_context& ctx, std::vector<vec4f>& ldr, const std::vector<vec4f>& hdr, float exposure,
+    bool filmic = false, bool srgb = true) {
+  ldr.resize(hdr.size());
+  check(ygl_tonemap_image(ctx.handle, (const float*)hdr.data(), (int64_t)hdr.size(), exposure, filmic ? 1 : 0, srgb ? 1 : 0,
+      (float*)ldr.data(), nullptr));
+}
+inline void tonemap_image(b200_context& ctx, std::vector<vec4b>& ldr, const std::vector<vec4f>& hdr, float exposure,
+    bool filmic = false, bool srgb = true) {
+  ldr.resize(hdr.size());
+  check(ygl_tonemap_image(ctx.handle, (const float*)hdr.data(), (int64_t)hdr.size(), exposure, filmic ? 1 : 0, srgb ? 1 : 0,
+      nullptr, (uint8_t*)ldr.data()));
+}
+// ... and of the image a state holds, without downloading the floats first (the interactive loop, apps/ytrace.cpp:219-226)
+inline void tonemap_image(std::vector<vec4b>& ldr, const b200_state& state, float exposure, bool filmic = false,
+    bool srgb = true) {
+  ldr.resize((size_t)state.width * state.height);
+  check(ygl_state_tonemap(state.handle, exposure, filmic ? 1 : 0, srgb ? 1 : 0, nullptr, (uint8_t*)ldr.data()));
+}
 // update_scene_bvh (yocto_bvh.h:88, yocto_bvh.cpp:434): refit to the edited scene, same topology
 inline void update_trace_bvh(b200_bvh& bvh, const scene_data& scene, const std::vector<int>& updated_instances,
     const std::vector<int>& updated_shapes) {

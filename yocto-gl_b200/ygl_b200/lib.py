@@ -26,7 +26,7 @@ EXPORTS = [
     "ygl_state_destroy", "ygl_make_state_rngs", "ygl_trace_samples", "ygl_trace_image",
     "ygl_trace_counters", "ygl_context_set_profiling", "ygl_context_set_mode", "ygl_trace_timings", "ygl_intersect_rays", "ygl_intersect_rays_device", "ygl_debug_libm", "ygl_comm_id_size",
     "ygl_comm_create_id", "ygl_comm_init", "ygl_tile_rows", "ygl_gather_image", "ygl_comm_destroy",
-    "ygl_bvh_build_device", "ygl_bvh_update", "ygl_scene_load", "ygl_loaded_scene_desc", "ygl_loaded_scene_name", "ygl_loaded_scene_destroy",
+    "ygl_bvh_build_device", "ygl_bvh_update", "ygl_tonemap_image", "ygl_state_tonemap", "ygl_scene_load", "ygl_loaded_scene_desc", "ygl_loaded_scene_name", "ygl_loaded_scene_destroy",
     "ygl_trace_start", "ygl_trace_cancel", "ygl_trace_wait", "ygl_trace_done", "ygl_trace_preview",
     "ygl_context_set_option", "ygl_context_get_option", "ygl_state_reset", "ygl_trace_sample", "ygl_bvh_create_from_host",
 ]
@@ -59,6 +59,8 @@ def load():
     lib.ygl_scene_destroy.argtypes = [vp]
     lib.ygl_bvh_build.argtypes = [P(abi.SceneDesc), i32, P(vp)]
     lib.ygl_bvh_build_device.argtypes = [vp, P(abi.SceneDesc), i32, P(vp)]
+    lib.ygl_tonemap_image.argtypes = [vp, vp, C.c_int64, C.c_float, i32, i32, vp, vp]
+    lib.ygl_state_tonemap.argtypes = [vp, C.c_float, i32, i32, vp, vp]
     lib.ygl_bvh_update.argtypes = [vp, P(abi.SceneDesc), vp, i32, vp, i32]
     lib.ygl_bvh_tree_size.argtypes = [vp, i32, P(i32), P(i32)]
     lib.ygl_bvh_tree_get.argtypes = [vp, i32, vp, vp]
@@ -245,6 +247,15 @@ class Context:
         self.h = C.c_void_p()
         _check(self.lib.ygl_context_create(device, C.byref(self.h)))
 
+    def tonemap_image(self, hdr, exposure=0.0, filmic=False, srgb=True):
+        """tonemap_image (yocto_image.h:242-245) of host pixels (..., 4) float32: (vec4f image, vec4b image)."""
+        hdr = np.ascontiguousarray(hdr, np.float32)
+        assert hdr.shape[-1] == 4
+        ldr, ldr_b = np.zeros_like(hdr), np.zeros(hdr.shape, np.uint8)
+        _check(self.lib.ygl_tonemap_image(self.h, _p(hdr), hdr.size // 4, exposure, int(filmic), int(srgb), _p(ldr),
+                                          _p(ldr_b)))
+        return ldr, ldr_b
+
     def synchronize(self):
         _check(self.lib.ygl_context_synchronize(self.h))
 
@@ -415,6 +426,13 @@ class State:
         _check(self.lib.ygl_state_download(self.h, _p(image), _p(albedo), _p(normal), _p(hits),
                                            _p(rngs)))
         return dict(image=image, albedo=albedo, normal=normal, hits=hits, rngs=rngs)
+
+    def tonemap(self, exposure=0.0, filmic=False, srgb=True):
+        """tonemap_image of the state's device image: (vec4f image, vec4b image)."""
+        ldr = np.zeros((self.num_rows, self.width, 4), np.float32)
+        ldr_b = np.zeros((self.num_rows, self.width, 4), np.uint8)
+        _check(self.lib.ygl_state_tonemap(self.h, exposure, int(filmic), int(srgb), _p(ldr), _p(ldr_b)))
+        return ldr, ldr_b
 
     def reset(self, params):
         """reset_cutrace_state-style: zero accumulators, samples = 0, rng streams re-seeded from params.seed."""
