@@ -217,8 +217,9 @@ void ygl_scene_destroy(ygl_scene* scene);
  * shapes and PNG / Radiance-HDR textures, read into flat host arrays. The returned object owns the arrays its
  * ygl_scene_desc views; hand that desc to ygl_scene_create / ygl_bvh_build / ygl_lights_create / ygl_state_create.
  * Defaults, lookat frames, texcoord flip, polygon fans, missing camera and missing radius follow the reference
- * (yocto_sceneio.cpp:3618-3860, :1008-1035, :1796-1837, :2119-2148). OBJ / glTF / pbrt / EXR inputs and subdivs are
- * refused with an error. ---- */
+ * (yocto_sceneio.cpp:3618-3860, :1008-1035, :1796-1837, :2119-2148). Subdivs (.obj control meshes) are loaded and
+ * tesselated right away (tesselate_subdivs, yocto_scene.cpp:739-813: what every reference app does after load_scene).
+ * OBJ / glTF / pbrt shapes and EXR / JPG textures are refused with an error. ---- */
 typedef struct ygl_loaded_scene ygl_loaded_scene;
 int  ygl_scene_load(const char* filename, ygl_loaded_scene** out);
 const ygl_scene_desc* ygl_loaded_scene_desc(const ygl_loaded_scene* scene);

@@ -20,12 +20,16 @@ def pool(kind, name):
 
 
 def scene_file(name, tmpdir):
-    """Path of <tmpdir>/<name>/<name>.json with shapes/ and textures/ symlinked to the shared pool."""
+    """Path of <tmpdir>/<name>/<name>.json with every shape / texture uri symlinked to its pooled file."""
+    import json
     d = os.path.join(str(tmpdir), name)
-    os.makedirs(d, exist_ok=True)
     dst = os.path.join(d, name + ".json")
     if not os.path.exists(dst):
+        os.makedirs(d, exist_ok=True)
         os.symlink(os.path.join(DATA, "scenes", name + ".json"), dst)
-        for kind in ("shapes", "textures"):
-            os.symlink(os.path.join(DATA, "pool", kind), os.path.join(d, kind))
+        files = json.load(open(os.path.join(DATA, "scenes", name + ".files")))
+        for uri, pooled in files.items():
+            kind = uri.split("/")[0]
+            os.makedirs(os.path.join(d, kind), exist_ok=True)
+            os.symlink(os.path.join(DATA, "pool", kind, pooled), os.path.join(d, uri))
     return dst

@@ -358,7 +358,7 @@ import scene_data  # noqa: E402
 @pytest.mark.skipif(not scene_data.available(), reason="oracle/_ref/data not present")
 @pytest.mark.parametrize("name", [n for n in scene_data.names() if n != "cornellbox"] or ["none"])
 def test_reference_scene_files_render_bit_exact(ctx, ref, name, tmp_path):
-    """tests/_version43/{features1, materials1-4, shapes4}: loaded with ygl_scene_load (JSON + PLY + PNG/HDR), rendered
+    """The reference's own test scenes (tests/_version43, incl. the two with subdivs): loaded with ygl_scene_load, rendered
     on the GPU, compared bit for bit with the reference rendering the scene IT loaded from the same file — every
     camera of the file for one of them, the default camera for the rest."""
     path = scene_data.scene_file(name, tmp_path)

@@ -8,7 +8,8 @@
 //   load_texture        libs/yocto/yocto_sceneio.cpp:1796-1837   .hdr -> float rgba (stb's RGBE rule), .png -> byte rgba
 //   add_missing_camera / add_missing_radius          yocto_sceneio.cpp:2119-2148
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
-// Not built: OBJ/glTF/pbrt/EXR inputs, subdivs (tesselate_subdivs, yocto_scene.cpp:739-813): such scenes are refused.
+// Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
+// Not built: OBJ / glTF / pbrt shapes and EXR / JPG textures: such scenes are refused.
 #include <zlib.h>
 
 #include <algorithm>
@@ -21,6 +22,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -742,6 +744,444 @@ bool parallel_load(size_t n, std::string& error, const std::function<bool(size_t
   return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// subdivs: load_subdiv (.obj, yocto_sceneio.cpp:1188-1232, :2915-2926; load_obj yocto_modelio.cpp:1393-1492) and
+// tesselate_subdiv (yocto_scene.cpp:739-805) with subdivide_catmullclark / subdivide_quads (yocto_shape.cpp:2779-3064),
+// quads_normals (:1495-1511), split_facevarying (:2567-2618) and the host-side eval_texture (yocto_scene.cpp:111-160).
+// ---------------------------------------------------------------------------------------------------------------
+struct v2 {
+  float x, y;
+};
+v2 operator+(const v2& a, const v2& b) { return {a.x + b.x, a.y + b.y}; }
+v2 operator-(const v2& a, const v2& b) { return {a.x - b.x, a.y - b.y}; }
+v2 operator*(const v2& a, float b) { return {a.x * b, a.y * b}; }
+v2 operator/(const v2& a, float b) { return {a.x / b, a.y / b}; }
+struct i2 {
+  int  x, y;
+  bool operator==(const i2& o) const { return x == o.x && y == o.y; }
+};
+struct i3 {
+  int  x, y, z;
+  bool operator==(const i3& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct i4 {
+  int x, y, z, w;
+};
+// std::hash<vec2i> / <vec3i> of yocto_shape.h:376-395: with the same hash, the same insertion sequence and the same
+// standard library the maps below iterate in the reference's order (get_boundary walks the edge map)
+struct i2_hash {
+  size_t operator()(const i2& v) const {
+    const std::hash<int> hasher;
+    size_t               h = 0;
+    h ^= hasher(v.x) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    h ^= hasher(v.y) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+struct i3_hash {
+  size_t operator()(const i3& v) const {
+    const std::hash<int> hasher;
+    size_t               h = 0;
+    h ^= hasher(v.x) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    h ^= hasher(v.y) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    h ^= hasher(v.z) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+struct EdgeData {
+  int index, nfaces;
+};
+using EdgeMap = std::unordered_map<i2, EdgeData, i2_hash>;
+void insert_edge(EdgeMap& emap, const i2& edge) {
+  auto es = edge.x < edge.y ? edge : i2{edge.y, edge.x};
+  auto it = emap.find(es);
+  if (it == emap.end()) emap.insert(it, {es, EdgeData{(int)emap.size(), 1}});
+  else it->second.nfaces += 1;
+}
+EdgeMap make_edge_map(const std::vector<i4>& quads) {
+  EdgeMap emap;
+  for (auto& q : quads) {
+    insert_edge(emap, {q.x, q.y});
+    insert_edge(emap, {q.y, q.z});
+    if (q.z != q.w) insert_edge(emap, {q.z, q.w});
+    insert_edge(emap, {q.w, q.x});
+  }
+  return emap;
+}
+int edge_index(const EdgeMap& emap, const i2& edge) {
+  auto es = edge.x < edge.y ? edge : i2{edge.y, edge.x};
+  auto it = emap.find(es);
+  return it == emap.end() ? -1 : it->second.index;
+}
+// the split shared by subdivide_quads and subdivide_catmullclark: vertices, then edge midpoints, then face centres
+template <class T>
+void split_quads(const std::vector<i4>& quads, const std::vector<T>& vertices, const EdgeMap& emap, std::vector<i4>& tquads,
+    std::vector<T>& tvertices) {
+  std::vector<i2> edges(emap.size());
+  for (auto& [edge, data] : emap) edges[data.index] = edge;
+  tvertices.clear();
+  tvertices.reserve(vertices.size() + edges.size() + quads.size());
+  for (auto& vertex : vertices) tvertices.push_back(vertex);
+  for (auto& edge : edges) tvertices.push_back((vertices[edge.x] + vertices[edge.y]) / 2);
+  for (auto& quad : quads) {
+    if (quad.z != quad.w) tvertices.push_back((vertices[quad.x] + vertices[quad.y] + vertices[quad.z] + vertices[quad.w]) / 4);
+    else tvertices.push_back((vertices[quad.x] + vertices[quad.y] + vertices[quad.z]) / 3);
+  }
+  const int nverts = (int)vertices.size(), nedges = (int)edges.size();
+  auto edge_vertex = [&](int a, int b) { return nverts + edge_index(emap, {a, b}); };
+  tquads.clear();
+  tquads.reserve(quads.size() * 4);
+  for (size_t quad_id = 0; quad_id < quads.size(); quad_id++) {
+    const i4& quad   = quads[quad_id];
+    const int centre = nverts + nedges + (int)quad_id;
+    if (quad.z != quad.w) {
+      tquads.push_back({quad.x, edge_vertex(quad.x, quad.y), centre, edge_vertex(quad.w, quad.x)});
+      tquads.push_back({quad.y, edge_vertex(quad.y, quad.z), centre, edge_vertex(quad.x, quad.y)});
+      tquads.push_back({quad.z, edge_vertex(quad.z, quad.w), centre, edge_vertex(quad.y, quad.z)});
+      tquads.push_back({quad.w, edge_vertex(quad.w, quad.x), centre, edge_vertex(quad.z, quad.w)});
+    } else {
+      tquads.push_back({quad.x, edge_vertex(quad.x, quad.y), centre, edge_vertex(quad.z, quad.x)});
+      tquads.push_back({quad.y, edge_vertex(quad.y, quad.z), centre, edge_vertex(quad.x, quad.y)});
+      tquads.push_back({quad.z, edge_vertex(quad.z, quad.x), centre, edge_vertex(quad.y, quad.z)});
+    }
+  }
+}
+template <class T>
+void subdivide_quads(std::vector<i4>& quads, std::vector<T>& vertices) {
+  if (quads.empty() || vertices.empty()) return;
+  auto            emap = make_edge_map(quads);
+  std::vector<i4> tquads;
+  std::vector<T>  tvertices;
+  split_quads(quads, vertices, emap, tquads, tvertices);
+  quads.swap(tquads), vertices.swap(tvertices);
+}
+template <class T>
+void subdivide_catmullclark(std::vector<i4>& quads, std::vector<T>& vertices, bool lock_boundary) {
+  if (quads.empty() || vertices.empty()) return;
+  auto            emap = make_edge_map(quads);
+  std::vector<i2> boundary;
+  for (auto& [edge, data] : emap)
+    if (data.nfaces < 2) boundary.push_back(edge);
+  std::vector<i4> tquads;
+  std::vector<T>  tvertices;
+  split_quads(quads, vertices, emap, tquads, tvertices);
+  const int       nverts = (int)vertices.size();
+  std::vector<i2> tboundary;
+  tboundary.reserve(boundary.size() * 2);
+  for (auto& edge : boundary) {
+    const int mid = nverts + edge_index(emap, edge);
+    tboundary.push_back({edge.x, mid});
+    tboundary.push_back({mid, edge.y});
+  }
+  // creases
+  // (locked boundary: its vertices are crease vertices; free boundary: its edges are crease edges)
+  std::vector<int> tcrease_verts;
+  if (lock_boundary)
+    for (auto& b : tboundary) tcrease_verts.push_back(b.x), tcrease_verts.push_back(b.y);
+  const std::vector<i2>  no_edges;
+  const std::vector<i2>& tcrease_edges = lock_boundary ? no_edges : tboundary;
+  // valence
+  std::vector<int> tvert_val(tvertices.size(), 2);
+  for (auto& edge : tboundary) tvert_val[edge.x] = tvert_val[edge.y] = lock_boundary ? 0 : 1;
+  // averaging pass
+  std::vector<T>   avert(tvertices.size(), T{});
+  std::vector<int> acount(tvertices.size(), 0);
+  for (auto point : tcrease_verts) {
+    if (tvert_val[point] != 0) continue;
+    avert[point] = avert[point] + tvertices[point];
+    acount[point] += 1;
+  }
+  for (auto& edge : tcrease_edges) {
+    auto centroid = (tvertices[edge.x] + tvertices[edge.y]) / 2;
+    for (int vid : {edge.x, edge.y}) {
+      if (tvert_val[vid] != 1) continue;
+      avert[vid] = avert[vid] + centroid;
+      acount[vid] += 1;
+    }
+  }
+  for (auto& quad : tquads) {
+    auto centroid = (tvertices[quad.x] + tvertices[quad.y] + tvertices[quad.z] + tvertices[quad.w]) / 4;
+    for (int vid : {quad.x, quad.y, quad.z, quad.w}) {
+      if (tvert_val[vid] != 2) continue;
+      avert[vid] = avert[vid] + centroid;
+      acount[vid] += 1;
+    }
+  }
+  for (size_t i = 0; i < tvertices.size(); i++) avert[i] = avert[i] / (float)acount[i];
+  // correction pass: p = p + (avg_p - p) * (4 / avg_count)
+  for (size_t i = 0; i < tvertices.size(); i++) {
+    if (tvert_val[i] != 2) continue;
+    avert[i] = tvertices[i] + (avert[i] - tvertices[i]) * (4 / (float)acount[i]);
+  }
+  quads.swap(tquads), vertices.swap(avert);
+}
+// quads_normals, yocto_shape.cpp:1495-1511 (quad_normal / quad_area, yocto_geometry.h:516-532)
+std::vector<v3> quads_normals(const std::vector<i4>& quads, const std::vector<v3>& positions) {
+  std::vector<v3> normals(positions.size(), v3{0, 0, 0});
+  auto triangle_normal = [](const v3& p0, const v3& p1, const v3& p2) { return normalize(cross(p1 - p0, p2 - p0)); };
+  auto triangle_area   = [](const v3& p0, const v3& p1, const v3& p2) { return length(cross(p1 - p0, p2 - p0)) / 2; };
+  for (auto& q : quads) {
+    const v3 &p0 = positions[q.x], &p1 = positions[q.y], &p2 = positions[q.z], &p3 = positions[q.w];
+    auto normal = normalize(triangle_normal(p0, p1, p3) + triangle_normal(p2, p3, p1));
+    auto area   = triangle_area(p0, p1, p3) + triangle_area(p2, p3, p1);
+    normals[q.x] = normals[q.x] + normal * area;
+    normals[q.y] = normals[q.y] + normal * area;
+    normals[q.z] = normals[q.z] + normal * area;
+    if (q.z != q.w) normals[q.w] = normals[q.w] + normal * area;
+  }
+  for (auto& normal : normals) normal = normalize(normal);
+  return normals;
+}
+// mean(eval_texture(texture, uv, false)), yocto_scene.cpp:111-163 + yocto_math.h:1521-1522, on the host
+float texture_mean(const HostTexture& tex, const v2& uv) {
+  if (tex.width == 0 || tex.height == 0) return 0;
+  auto fmin = [](float a, float b) { return (a < b) ? a : b; };
+  auto fmax = [](float a, float b) { return (a > b) ? a : b; };
+  auto imin = [](int a, int b) { return (a < b) ? a : b; };
+  auto imax = [](int a, int b) { return (a > b) ? a : b; };
+  const int w = tex.width, h = tex.height;
+  float     s = 0.0f, t = 0.0f;
+  if (tex.clamp) {
+    s = fmin(fmax(uv.x, 0.0f), 1.0f) * w;
+    t = fmin(fmax(uv.y, 0.0f), 1.0f) * h;
+  } else {
+    s = std::fmod(uv.x, 1.0f) * w;
+    if (s < 0) s += w;
+    t = std::fmod(uv.y, 1.0f) * h;
+    if (t < 0) t += h;
+  }
+  const int   i = imin(imax((int)s, 0), w - 1), j = imin(imax((int)t, 0), h - 1);
+  const int   ii = (i + 1) % w, jj = (j + 1) % h;
+  const float u = s - i, v = t - j;
+  struct c4 {
+    float x, y, z, w;
+  };
+  auto lookup = [&](int i, int j) {
+    const size_t k = ((size_t)j * w + i) * 4;
+    if (!tex.pixelsf.empty()) return c4{tex.pixelsf[k], tex.pixelsf[k + 1], tex.pixelsf[k + 2], tex.pixelsf[k + 3]};
+    return c4{tex.pixelsb[k] / 255.0f, tex.pixelsb[k + 1] / 255.0f, tex.pixelsb[k + 2] / 255.0f, tex.pixelsb[k + 3] / 255.0f};
+  };
+  auto scale = [](const c4& a, float b) { return c4{a.x * b, a.y * b, a.z * b, a.w * b}; };
+  auto add   = [](const c4& a, const c4& b) { return c4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; };
+  c4 color;
+  if (tex.nearest) {
+    color = lookup(i, j);
+  } else {
+    color = add(add(add(scale(scale(lookup(i, j), 1 - u), 1 - v), scale(scale(lookup(i, jj), 1 - u), v)),
+                    scale(scale(lookup(ii, j), u), 1 - v)),
+        scale(scale(lookup(ii, jj), u), v));
+  }
+  return (color.x + color.y + color.z + color.w) / 4;
+}
+
+struct HostSubdiv {
+  std::vector<i4> quadspos, quadsnorm, quadstexcoord;
+  std::vector<v3> positions, normals;
+  std::vector<v2> texcoords;
+  int   subdivisions = 0, catmullclark = 1, smooth = 1;
+  float displacement     = 0;
+  int   displacement_tex = -1, shape = -1;
+};
+// load_subdiv for .obj: the single-shape face-varying load_obj + get_positions / get_normals / get_texcoords(flip) /
+// get_fvquads (yocto_modelio.cpp:1393-1458, :1857-1912)
+bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& error) {
+  const auto ext = path_extension(filename);
+  if (ext != ".obj" && ext != ".OBJ") return error = "unsupported format " + filename + " (subdivs are read from .obj)", false;
+  std::vector<uint8_t> data;
+  if (!read_file(filename, data, error)) return false;
+  auto parse_error = [&]() { return error = "cannot parse " + filename, false; };
+  data.push_back(0);
+  struct Vertex {
+    int position = 0, texcoord = 0, normal = 0;
+  };
+  std::vector<Vertex> vertices;
+  std::vector<int>    face_sizes;
+  const char*         p   = (const char*)data.data();
+  const char* const   end = p + data.size() - 1;
+  auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; };
+  while (p < end) {
+    const char* eol = (const char*)memchr(p, '\n', end - p);
+    if (!eol) eol = end;
+    std::string line(p, eol);
+    p = eol < end ? eol + 1 : end;
+    if (auto hash = line.find('#'); hash != std::string::npos) line.resize(hash);
+    const char* s = line.c_str();
+    auto skip  = [&]() { while (*s && is_space(*s)) s++; };
+    auto token = [&]() {
+      skip();
+      const char* b = s;
+      while (*s && !is_space(*s)) s++;
+      return std::string(b, s);
+    };
+    auto number = [&](float& v) {
+      skip();
+      char* e = nullptr;
+      v       = strtof(s, &e);
+      if (e == s) return false;
+      s = e;
+      return true;
+    };
+    auto integer = [&](int& v) {  // std::from_chars: no leading '+', no whitespace
+      char* e = nullptr;
+      if (*s == '+') return false;
+      long r = strtol(s, &e, 10);
+      if (e == s) return false;
+      v = (int)r, s = e;
+      return true;
+    };
+    skip();
+    if (!*s) continue;
+    const std::string cmd = token();
+    if (cmd == "v") {
+      v3 v;
+      if (!number(v.x) || !number(v.y) || !number(v.z)) return parse_error();
+      subdiv.positions.push_back(v);
+    } else if (cmd == "vn") {
+      v3 v;
+      if (!number(v.x) || !number(v.y) || !number(v.z)) return parse_error();
+      subdiv.normals.push_back(v);
+    } else if (cmd == "vt") {
+      v2 v;
+      if (!number(v.x) || !number(v.y)) return parse_error();
+      subdiv.texcoords.push_back(v);
+    } else if (cmd == "f" || cmd == "l" || cmd == "p") {
+      int size = 0;
+      skip();
+      while (*s) {
+        Vertex vert;
+        skip();
+        if (!integer(vert.position)) return parse_error();
+        if (*s == '/') {
+          s++;
+          if (*s == '/') {
+            s++;
+            if (!integer(vert.normal)) return parse_error();
+          } else {
+            if (!integer(vert.texcoord)) return parse_error();
+            if (*s == '/') {
+              s++;
+              if (!integer(vert.normal)) return parse_error();
+            }
+          }
+        }
+        if (vert.position == 0) break;
+        if (vert.position < 0) vert.position = (int)subdiv.positions.size() + vert.position + 1;
+        if (vert.texcoord < 0) vert.texcoord = (int)subdiv.texcoords.size() + vert.texcoord + 1;
+        if (vert.normal < 0) vert.normal = (int)subdiv.normals.size() + vert.normal + 1;
+        if (cmd == "f") vertices.push_back(vert), size++;
+        skip();
+      }
+      if (cmd == "f") face_sizes.push_back(size);
+    }
+  }
+  for (auto& t : subdiv.texcoords) t.y = 1 - t.y;  // get_texcoords(obj, texcoords, flipv = true)
+  // get_fvquads: quads stay quads, other faces become fans of degenerate quads; a channel exists if the FIRST vertex of
+  // the shape has it
+  const bool has_pos = !vertices.empty() && vertices[0].position != 0, has_norm = !vertices.empty() && vertices[0].normal != 0,
+             has_tex = !vertices.empty() && vertices[0].texcoord != 0;
+  size_t cur = 0;
+  for (int size : face_sizes) {
+    auto emit = [&](int a, int b, int c, int d) {
+      const Vertex &va = vertices[cur + a], &vb = vertices[cur + b], &vc = vertices[cur + c], &vd = vertices[cur + d];
+      if (has_pos) subdiv.quadspos.push_back({va.position - 1, vb.position - 1, vc.position - 1, vd.position - 1});
+      if (has_norm) subdiv.quadsnorm.push_back({va.normal - 1, vb.normal - 1, vc.normal - 1, vd.normal - 1});
+      if (has_tex) subdiv.quadstexcoord.push_back({va.texcoord - 1, vb.texcoord - 1, vc.texcoord - 1, vd.texcoord - 1});
+    };
+    if (size == 4) emit(0, 1, 2, 3);
+    else
+      for (int c = 2; c < size; c++) emit(0, c - 1, c, c);
+    cur += size;
+  }
+  if (subdiv.quadspos.empty()) return error = "empty shape " + filename, false;
+  return true;
+}
+
+// tesselate_subdiv, yocto_scene.cpp:739-805: the subdivided, displaced, split surface replaces the shape
+bool tesselate_subdiv(HostShape& shape, HostSubdiv subdiv, const std::vector<HostTexture>& textures, std::string& error) {
+  if (subdiv.subdivisions > 0) {
+    for (int k = 0; k < subdiv.subdivisions; k++) {
+      if (subdiv.catmullclark) {
+        subdivide_catmullclark(subdiv.quadstexcoord, subdiv.texcoords, true);
+        subdivide_catmullclark(subdiv.quadsnorm, subdiv.normals, true);
+        subdivide_catmullclark(subdiv.quadspos, subdiv.positions, false);
+      } else {
+        subdivide_quads(subdiv.quadstexcoord, subdiv.texcoords);
+        subdivide_quads(subdiv.quadsnorm, subdiv.normals);
+        subdivide_quads(subdiv.quadspos, subdiv.positions);
+      }
+    }
+    if (subdiv.smooth) {
+      subdiv.normals   = quads_normals(subdiv.quadspos, subdiv.positions);
+      subdiv.quadsnorm = subdiv.quadspos;
+    } else {
+      subdiv.normals.clear(), subdiv.quadsnorm.clear();
+    }
+  }
+  if (subdiv.displacement != 0 && subdiv.displacement_tex != -1) {
+    if (subdiv.texcoords.empty()) return error = "missing texture coordinates", false;
+    if (subdiv.displacement_tex < 0 || subdiv.displacement_tex >= (int)textures.size())
+      return error = "displacement texture id out of range", false;
+    const HostTexture& tex = textures[subdiv.displacement_tex];
+    std::vector<float> offset(subdiv.positions.size(), 0);
+    std::vector<int>   count(subdiv.positions.size(), 0);
+    for (size_t fid = 0; fid < subdiv.quadspos.size(); fid++) {
+      const int qpos[4] = {subdiv.quadspos[fid].x, subdiv.quadspos[fid].y, subdiv.quadspos[fid].z, subdiv.quadspos[fid].w};
+      const int qtxt[4] = {subdiv.quadstexcoord[fid].x, subdiv.quadstexcoord[fid].y, subdiv.quadstexcoord[fid].z,
+          subdiv.quadstexcoord[fid].w};
+      for (int i = 0; i < 4; i++) {
+        float disp = texture_mean(tex, subdiv.texcoords[qtxt[i]]);
+        if (!tex.pixelsb.empty()) disp -= 0.5f;
+        offset[qpos[i]] += subdiv.displacement * disp;
+        count[qpos[i]] += 1;
+      }
+    }
+    auto normals = quads_normals(subdiv.quadspos, subdiv.positions);
+    for (size_t vid = 0; vid < subdiv.positions.size(); vid++)
+      subdiv.positions[vid] = subdiv.positions[vid] + normals[vid] * offset[vid] / (float)count[vid];
+    if (subdiv.smooth || !subdiv.normals.empty()) {
+      subdiv.quadsnorm = subdiv.quadspos;
+      subdiv.normals   = quads_normals(subdiv.quadspos, subdiv.positions);
+    }
+  }
+  // split_facevarying, yocto_shape.cpp:2567-2618: one vertex per distinct (position, normal, texcoord) triple, in order
+  // of first use
+  shape = HostShape{};
+  std::unordered_map<i3, int, i3_hash> vert_map;
+  std::vector<i3>                      verts;
+  shape.quads.resize(subdiv.quadspos.size() * 4);
+  for (size_t fid = 0; fid < subdiv.quadspos.size(); fid++) {
+    const int qp[4] = {subdiv.quadspos[fid].x, subdiv.quadspos[fid].y, subdiv.quadspos[fid].z, subdiv.quadspos[fid].w};
+    for (int c = 0; c < 4; c++) {
+      const int n = subdiv.quadsnorm.empty() ? -1 : (&subdiv.quadsnorm[fid].x)[c];
+      const int t = subdiv.quadstexcoord.empty() ? -1 : (&subdiv.quadstexcoord[fid].x)[c];
+      const i3  v = {qp[c], n, t};
+      auto      it = vert_map.find(v);
+      if (it == vert_map.end()) {
+        const int index = (int)vert_map.size();
+        vert_map.insert(it, {v, index});
+        verts.push_back(v);
+        shape.quads[fid * 4 + c] = index;
+      } else {
+        shape.quads[fid * 4 + c] = it->second;
+      }
+    }
+  }
+  if (!subdiv.positions.empty()) {
+    shape.positions.resize(verts.size() * 3);
+    for (size_t k = 0; k < verts.size(); k++) memcpy(&shape.positions[k * 3], &subdiv.positions[verts[k].x], 12);
+  }
+  if (!subdiv.normals.empty()) {
+    shape.normals.resize(verts.size() * 3);
+    for (size_t k = 0; k < verts.size(); k++) memcpy(&shape.normals[k * 3], &subdiv.normals[verts[k].y], 12);
+  }
+  if (!subdiv.texcoords.empty()) {
+    shape.texcoords.resize(verts.size() * 2);
+    for (size_t k = 0; k < verts.size(); k++) memcpy(&shape.texcoords[k * 2], &subdiv.texcoords[verts[k].z], 8);
+  }
+  return true;
+}
+
 }  // namespace
 
 struct ygl_loaded_scene {
@@ -862,9 +1302,23 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
       shape_files.push_back(uri);
     }
   }
-  if (auto group = json.find("subdivs"); group && !group->array.empty()) {
-    error = "cannot load " + filename + ": subdivs (tesselate_subdivs) are not supported";
-    return false;
+  std::vector<HostSubdiv>  subdivs;
+  std::vector<std::string> subdiv_files;
+  if (auto group = json.find("subdivs")) {
+    for (auto& e : group->array) {
+      HostSubdiv  subdiv;
+      std::string name, uri;
+      rd.get(e, "name", name);
+      rd.get(e, "uri", uri);
+      rd.get(e, "shape", subdiv.shape);
+      rd.get(e, "subdivisions", subdiv.subdivisions);
+      rd.get_bool(e, "catmullclark", subdiv.catmullclark);
+      rd.get_bool(e, "smooth", subdiv.smooth);
+      rd.get(e, "displacement", subdiv.displacement);
+      rd.get(e, "displacement_tex", subdiv.displacement_tex);
+      subdivs.push_back(subdiv);
+      subdiv_files.push_back(uri);
+    }
   }
   if (auto group = json.find("instances")) {
     for (auto& e : group->array) {
@@ -912,6 +1366,9 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
   auto dependent_error = [&]() { return error = "cannot load " + filename + " since " + error, false; };
   if (!parallel_load(shape_files.size(), error,
           [&](size_t i, std::string& err) { return load_shape(path_join(dirname, shape_files[i]), scene.shape_data[i], err); }))
+    return dependent_error();
+  if (!parallel_load(subdiv_files.size(), error,
+          [&](size_t i, std::string& err) { return load_subdiv(path_join(dirname, subdiv_files[i]), subdivs[i], err); }))
     return dependent_error();
   if (!parallel_load(texture_files.size(), error, [&](size_t i, std::string& err) {
         return load_texture(path_join(dirname, texture_files[i]), scene.texture_data[i], err);
@@ -963,6 +1420,12 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
     if (shape.points.empty() && shape.lines.empty()) continue;
     if (!shape.radius.empty()) continue;
     shape.radius.assign(shape.positions.size() / 3, 0.001f);
+  }
+  // tesselate_subdivs (yocto_scene.cpp:807-812): what every reference app does right after load_scene
+  for (auto& subdiv : subdivs) {
+    if (subdiv.shape < 0 || subdiv.shape >= (int)scene.shape_data.size())
+      return error = "cannot load " + filename + ": subdiv shape id out of range", false;
+    if (!tesselate_subdiv(scene.shape_data[subdiv.shape], subdiv, scene.texture_data, error)) return dependent_error();
   }
   return true;
 }
