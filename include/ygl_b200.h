@@ -342,7 +342,7 @@ enum { YGL_MODE_WAVEFRONT = 0, YGL_MODE_PERSISTENT = 1 };
 int ygl_context_set_mode(ygl_context* ctx, int mode);
 /* Scheduling knobs of a context, by name (the library reads no environment variables). None can change a result
  * bit. Names: "ext_blocks_per_sm", "refill", "node_reps", "prim_weight", "enter_weight", "suspend", "suspend_rounds", "lone", "lone_steps", "fuse",
- * "bin", "pipes", "graph", "top_smem" (struct Tuning in ygl_kernels.cuh documents each). -1 restores the automatic choice where one exists. */
+ * "bin", "pipes", "graph", "top_smem", "carveout" (struct Tuning in ygl_kernels.cuh documents each). -1 restores the automatic choice where one exists. */
 int ygl_context_set_option(ygl_context* ctx, const char* name, double value);
 int ygl_context_get_option(ygl_context* ctx, const char* name, double* value);
 /* Timings of the last ygl_trace_samples / ygl_trace_image with time_kernels on:

@@ -1286,7 +1286,7 @@ const OptionRef kOptions[] = {
     {"prim_weight", &Tuning::prim_weight}, {"enter_weight", &Tuning::enter_weight},
     {"suspend", &Tuning::suspend}, {"suspend_rounds", &Tuning::suspend_rounds}, {"lone", &Tuning::lone},
     {"lone_steps", &Tuning::lone_steps}, {"fuse", &Tuning::fuse}, {"bin", &Tuning::bin}, {"pipes", &Tuning::pipes},
-    {"graph", &Tuning::graph}, {"top_smem", &Tuning::top_smem},
+    {"graph", &Tuning::graph}, {"top_smem", &Tuning::top_smem}, {"carveout", &Tuning::carveout},
 };
 }  // namespace
 int ygl_context_set_option(ygl_context* ctx, const char* name, double value) {

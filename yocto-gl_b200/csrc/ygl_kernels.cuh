@@ -164,6 +164,7 @@ struct Tuning {
   int bin               = -1; // class-binned shade queues + per-class kernels for the path sampler (1/0; -1 = by tile size)
   int pipes             = 1;  // independent wavefront pipelines (streams) per state
   int graph             = -1; // submit rounds of iterations as a CUDA graph (1 = on; measured: no gain, so -1 = off)
+  int carveout          = -1; // extend: preferred shared-memory carve-out in percent (-1 = leave the driver's choice)
   int top_smem          = -1; // extend: stage the instance-level tree in shared memory with a bulk async copy (1 = on; measured slower, so -1 = off)
 };
 
