@@ -751,8 +751,8 @@ static int state_create_sized(ygl_context* ctx, int w, int h, const ygl_trace_pa
   st.susp     = (int*)(m + o_susp);
   st.aux_ids  = (int2*)(m + o_ai);
   st.next_ids = (int2*)(m + o_ni);
-  SPair<false> spare;
-  SPair<false>* members[16] = {&st.ray_o, &st.ray_d,  // read together by extend, shade, light pdf
+  SRec<false> spare;
+  SRec<false>* members[16] = {&st.ray_o, &st.ray_d,  // read together by extend, shade, light pdf
       &st.radiance, &st.weight,                          // shade, accumulate
       &st.hit_uvd, &st.pend,                             // shade reads the hit and writes the pending MIS numerator
       &st.albedo0, &st.normal0,                          // bounce-0 guides

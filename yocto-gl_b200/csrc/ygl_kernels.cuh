@@ -1,4 +1,4 @@
-// ygl_kernels.cuh — launch-side declarations shared by ygl_kernels.cu (device) and ygl_host.cpp.
+// ygl_kernels.cuh — launch-side declarations shared by ygl_kernels.cu (device) and ygl_api.cpp (host).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -71,7 +71,7 @@ struct SArr<T, COH, 1> {
                            // quads another -2.8 %, eight (one 128-byte line per lane) another -1.1 %
 #endif
 template <bool COH>
-using SPair = SArr<float4, COH, YGL_STATE_GROUP>;  // one member of an interleaved group of float4 records
+using SRec = SArr<float4, COH, YGL_STATE_GROUP>;  // one member of an interleaved group of float4 records
 template <bool COH>
 struct PathStateT {
   int num_lanes;  // pixels in this tile
@@ -85,25 +85,25 @@ struct PathStateT {
   // ---- per-lane progress ----
   SArr<int, COH> sample;  // index of the sample in flight
   // ---- path in flight ----
-  SPair<COH>        ray_o;     // origin.xyz, w: bounce (int bits)
-  SPair<COH>        ray_d;     // direction.xyz, w: opbounce (int bits)
-  SPair<COH>        radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
-  SPair<COH>        weight;    // rgb, w: max_roughness
-  SPair<COH>        hit_uvd;   // uv.x uv.y distance hit(int bits)
+  SRec<COH>        ray_o;     // origin.xyz, w: bounce (int bits)
+  SRec<COH>        ray_d;     // direction.xyz, w: opbounce (int bits)
+  SRec<COH>        radiance;  // rgb, w: flags (int bits): 1 hit, 2 in-volume slot occupied
+  SRec<COH>        weight;    // rgb, w: max_roughness
+  SRec<COH>        hit_uvd;   // uv.x uv.y distance hit(int bits)
   SArr<int2, COH>   hit_ids;   // instance, element
-  SPair<COH>        albedo0;   // bounce-0 albedo rgb, w unused
-  SPair<COH>        normal0;   // bounce-0 normal (or -camera dir on miss) xyz
-  SPair<COH>        vol_a;     // volume slot: density.xyz, scanisotropy
-  SPair<COH>        vol_b;     // volume slot: scattering.xyz
-  SPair<COH>        pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
+  SRec<COH>        albedo0;   // bounce-0 albedo rgb, w unused
+  SRec<COH>        normal0;   // bounce-0 normal (or -camera dir on miss) xyz
+  SRec<COH>        vol_a;     // volume slot: density.xyz, scanisotropy
+  SRec<COH>        vol_b;     // volume slot: scattering.xyz
+  SRec<COH>        pend;      // pending MIS numerator: bsdfcos.rgb, w: bsdf/phase pdf
   SArr<int, COH>    susp;      // save slot of the lane's ray while it is parked by k_extend (see Queues::park)
   // ---- pathdirect / pathmis only: the extra shadow-ray stage of a bounce ----
-  SPair<COH>        aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
-  SPair<COH>        aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
-  SPair<COH>        aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
-  SPair<COH>        aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
+  SRec<COH>        aux_o;     // shading position (shadow-ray origin), w: bsdf pdf of the pending direct sample
+  SRec<COH>        aux_dir;   // direct-sample direction, w: light pdf (pathdirect) / mis weight (pathmis)
+  SRec<COH>        aux_bsdf;  // bsdfcos of the direct sample, w: phase (int bits)
+  SRec<COH>        aux_uvd;   // shadow-ray hit: uv.x uv.y distance hit
   SArr<int2, COH>   aux_ids;   // shadow-ray hit: instance, element
-  SPair<COH>        next_uvd;  // pathmis next_intersection (persists across bounces)
+  SRec<COH>        next_uvd;  // pathmis next_intersection (persists across bounces)
   SArr<int2, COH>   next_ids;
 };
 using PathState = PathStateT<false>;  // a kernel boundary separates every writer of lane state from its readers
