@@ -928,10 +928,11 @@ static int run_wavefront(ygl_context* ctx, ygl_state* state, const ygl_trace_par
   KParams    kp            = make_kparams(params, sample_begin + nsamples);
   // Binned shade queues + one kernel per shading class: the path sampler (trace_path). The other samplers run the
   // unspecialised kernel on one queue.
-  // Measured on B200 (C3): on the full 1080p frame the binned pipeline renders 16 spp in 179 ms against 193 ms; on a
-  // 1/8 tile (259 K lanes) the extra launches and their tails cost more than the coherence gains (80.9 vs 78.5 ms per
-  // 32 spp). Hence: by lane count unless the option says otherwise.
-  const bool binned     = params.sampler == YGL_SAMPLER_PATH && (tune.bin >= 0 ? tune.bin != 0 : st.num_lanes > 800000);
+  // Measured on B200 (C3, per 32 spp, final state layout): full 1080p frame binned 142 ms per 16 spp against 160; half
+  // frame (1.04 M lanes) 159.7 against 184.4 ms; quarter (518 K lanes) 100.4 against 108.0; on a 1/8 tile (259 K lanes)
+  // the extra launches and their tails cost what the coherence gains (70.3 vs 70.0). Hence: by lane count unless the
+  // option says otherwise.
+  const bool binned     = params.sampler == YGL_SAMPLER_PATH && (tune.bin >= 0 ? tune.bin != 0 : st.num_lanes > 400000);
   const unsigned classes = binned ? ctx->class_mask : 1u;
   DScene     dscene     = ctx->dscene;
   dscene.inst_class     = binned ? ctx->d_inst_class : nullptr;
