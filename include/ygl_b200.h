@@ -219,7 +219,8 @@ void ygl_scene_destroy(ygl_scene* scene);
  * Defaults, lookat frames, texcoord flip, polygon fans, missing camera and missing radius follow the reference
  * (yocto_sceneio.cpp:3618-3860, :1008-1035, :1796-1837, :2119-2148). Subdivs (.obj control meshes) are loaded and
  * tesselated right away (tesselate_subdivs, yocto_scene.cpp:739-813: what every reference app does after load_scene).
- * OBJ / glTF / pbrt shapes and EXR / JPG textures are refused with an error. ---- */
+ * Shapes may also be .obj files (load_shape's de-duplicated, non-face-varying reading). glTF / pbrt / stl shapes and
+ * EXR / JPG textures are refused with an error. ---- */
 typedef struct ygl_loaded_scene ygl_loaded_scene;
 int  ygl_scene_load(const char* filename, ygl_loaded_scene** out);
 const ygl_scene_desc* ygl_loaded_scene_desc(const ygl_loaded_scene* scene);

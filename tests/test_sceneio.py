@@ -100,3 +100,49 @@ def test_ascii_and_big_endian_ply_and_lookat(ref, tmp_path):
     (d / "mini2.json").write_text(json.dumps(scene))
     os.symlink(d / "shapes", tmp_path / "shapes2")
     assert_scenes_identical(lib.load_scene(d / "mini2.json"), ref.load_scene(d / "mini2.json"))
+
+
+OBJ_MIXED = """# quads and a pentagon, shared and split vertices, negative indices, a polyline and points
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0.25
+v 0.5 1.5 0.125
+v 2 0 -1
+vn 0 0 1
+vn 0 0.6 0.8
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0.25 0.75
+f 1/1/1 2/2/1 3/3/1 4/4/2
+f 4/4/2 3/3/1 5/1/2
+f -6/1/1 -5/2/1 -1/2/2 3/3/1 5/4/2
+l 1 2 6
+p 6 1
+"""
+OBJ_TRIS = """v -1 0 0.5
+v 1 0 0.5
+v 0 1.0e0 0.5
+v 0 -1 .5
+vt 0.1 0.9
+f 1 2 3
+f 1//1 4//1 2//1
+vn 0 0 1
+f 2/1 3/1 1/1
+"""
+
+
+@pytest.mark.parametrize("name, text", [("mixed", OBJ_MIXED), ("tris", OBJ_TRIS)])
+def test_obj_shapes_match_reference_loader(ref, tmp_path, name, text):
+    """.obj shapes (load_shape, yocto_sceneio.cpp:1036-1051): vertex de-duplication in order of first use, quads as soon
+    as one face has four corners, fans, the cursor rule of get_lines / get_points, texcoord flip."""
+    os.makedirs(tmp_path / "shapes")
+    (tmp_path / "shapes" / "a.obj").write_text(text)
+    path = tmp_path / "scene.json"
+    path.write_text(json.dumps({"asset": {"version": "4.2"}, "shapes": [{"name": "a", "uri": "shapes/a.obj"}],
+                                "materials": [{"name": "m", "color": [0.5, 0.5, 0.5]}],
+                                "instances": [{"name": "i", "shape": 0, "material": 0}]}))
+    ours, theirs = lib.load_scene(str(path)), ref.load_scene(str(path))
+    assert_scenes_identical(ours, theirs)
+    assert len(ours.shapes[0]["positions"]) > 0

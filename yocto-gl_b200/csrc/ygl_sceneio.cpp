@@ -9,7 +9,7 @@
 //   add_missing_camera / add_missing_radius          yocto_sceneio.cpp:2119-2148
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
 // Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
-// Not built: OBJ / glTF / pbrt shapes and EXR / JPG textures: such scenes are refused.
+// Shapes: .ply and .obj. Not built: glTF / pbrt / stl shapes, EXR / JPG textures: such scenes are refused.
 #include <zlib.h>
 
 #include <algorithm>
@@ -446,8 +446,11 @@ void ply_vertex_values(const std::vector<PlyElement>& ply, const char* const (&n
     for (size_t i = 0; i < n && i < props[k]->values.size(); i++) out[i * N + k] = (float)props[k]->values[i];
 }
 // load_shape for .ply, yocto_sceneio.cpp:1018-1035 (flip_texcoord = true as load_json_scene passes)
+bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& error);  // .obj, further down
 bool load_shape(const std::string& filename, HostShape& shape, std::string& error) {
-  if (path_extension(filename) != ".ply") return error = "unsupported format " + filename, false;
+  const auto ext = path_extension(filename);
+  if (ext == ".obj" || ext == ".OBJ") return load_obj_shape(filename, shape, error);
+  if (ext != ".ply") return error = "unsupported format " + filename, false;
   std::vector<PlyElement> ply;
   if (!load_ply(filename, ply, error)) return false;
   ply_vertex_values(ply, {"x", "y", "z"}, shape.positions);
@@ -983,22 +986,36 @@ struct HostSubdiv {
   float displacement     = 0;
   int   displacement_tex = -1, shape = -1;
 };
-// load_subdiv for .obj: the single-shape face-varying load_obj + get_positions / get_normals / get_texcoords(flip) /
-// get_fvquads (yocto_modelio.cpp:1393-1458, :1857-1912)
-bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& error) {
-  const auto ext = path_extension(filename);
-  if (ext != ".obj" && ext != ".OBJ") return error = "unsupported format " + filename + " (subdivs are read from .obj)", false;
+// The single-shape load_obj of yocto_modelio.cpp:1393-1458 up to (not including) its vertex conversion: raw v / vn / vt
+// arrays, the vertices of every f / l / p element with 1-based (already resolved) indices, element sizes and types.
+struct ObjVertex {
+  int  position = 0, texcoord = 0, normal = 0;
+  bool operator==(const ObjVertex& o) const { return position == o.position && texcoord == o.texcoord && normal == o.normal; }
+};
+struct ObjVertexHash {  // std::hash<obj_vertex>, yocto_modelio.h:399-408
+  size_t operator()(const ObjVertex& v) const {
+    const std::hash<int> hasher;
+    size_t               h = 0;
+    h ^= hasher(v.position) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    h ^= hasher(v.normal) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    h ^= hasher(v.texcoord) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+struct ObjData {
+  std::vector<v3>        positions, normals;
+  std::vector<v2>        texcoords;
+  std::vector<ObjVertex> vertices;
+  std::vector<int>       sizes;  // per element
+  std::vector<char>      types;  // per element: 'f', 'l' or 'p'
+};
+bool read_obj(const std::string& filename, ObjData& obj, std::string& error) {
   std::vector<uint8_t> data;
   if (!read_file(filename, data, error)) return false;
   auto parse_error = [&]() { return error = "cannot parse " + filename, false; };
   data.push_back(0);
-  struct Vertex {
-    int position = 0, texcoord = 0, normal = 0;
-  };
-  std::vector<Vertex> vertices;
-  std::vector<int>    face_sizes;
-  const char*         p   = (const char*)data.data();
-  const char* const   end = p + data.size() - 1;
+  const char*       p   = (const char*)data.data();
+  const char* const end = p + data.size() - 1;
   auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; };
   while (p < end) {
     const char* eol = (const char*)memchr(p, '\n', end - p);
@@ -1022,7 +1039,8 @@ bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& e
       s = e;
       return true;
     };
-    auto integer = [&](int& v) {  // std::from_chars: no leading '+', no whitespace
+    auto integer = [&](int& v) {  // std::from_chars: no leading '+'
+      skip();
       char* e = nullptr;
       if (*s == '+') return false;
       long r = strtol(s, &e, 10);
@@ -1036,21 +1054,20 @@ bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& e
     if (cmd == "v") {
       v3 v;
       if (!number(v.x) || !number(v.y) || !number(v.z)) return parse_error();
-      subdiv.positions.push_back(v);
+      obj.positions.push_back(v);
     } else if (cmd == "vn") {
       v3 v;
       if (!number(v.x) || !number(v.y) || !number(v.z)) return parse_error();
-      subdiv.normals.push_back(v);
+      obj.normals.push_back(v);
     } else if (cmd == "vt") {
       v2 v;
       if (!number(v.x) || !number(v.y)) return parse_error();
-      subdiv.texcoords.push_back(v);
+      obj.texcoords.push_back(v);
     } else if (cmd == "f" || cmd == "l" || cmd == "p") {
       int size = 0;
       skip();
       while (*s) {
-        Vertex vert;
-        skip();
+        ObjVertex vert;
         if (!integer(vert.position)) return parse_error();
         if (*s == '/') {
           s++;
@@ -1066,24 +1083,40 @@ bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& e
           }
         }
         if (vert.position == 0) break;
-        if (vert.position < 0) vert.position = (int)subdiv.positions.size() + vert.position + 1;
-        if (vert.texcoord < 0) vert.texcoord = (int)subdiv.texcoords.size() + vert.texcoord + 1;
-        if (vert.normal < 0) vert.normal = (int)subdiv.normals.size() + vert.normal + 1;
-        if (cmd == "f") vertices.push_back(vert), size++;
+        if (vert.position < 0) vert.position = (int)obj.positions.size() + vert.position + 1;
+        if (vert.texcoord < 0) vert.texcoord = (int)obj.texcoords.size() + vert.texcoord + 1;
+        if (vert.normal < 0) vert.normal = (int)obj.normals.size() + vert.normal + 1;
+        obj.vertices.push_back(vert);
+        size++;
         skip();
       }
-      if (cmd == "f") face_sizes.push_back(size);
+      obj.sizes.push_back(size);
+      obj.types.push_back(cmd[0]);
     }
   }
+  return true;
+}
+
+// load_subdiv for .obj: load_obj(face_varying = true) + get_positions / get_normals / get_texcoords(flip) / get_fvquads
+// (yocto_sceneio.cpp:1209-1221, yocto_modelio.cpp:1857-1912)
+bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& error) {
+  const auto ext = path_extension(filename);
+  if (ext != ".obj" && ext != ".OBJ") return error = "unsupported format " + filename + " (subdivs are read from .obj)", false;
+  ObjData obj;
+  if (!read_obj(filename, obj, error)) return false;
+  subdiv.positions = obj.positions, subdiv.normals = obj.normals, subdiv.texcoords = obj.texcoords;
   for (auto& t : subdiv.texcoords) t.y = 1 - t.y;  // get_texcoords(obj, texcoords, flipv = true)
   // get_fvquads: quads stay quads, other faces become fans of degenerate quads; a channel exists if the FIRST vertex of
-  // the shape has it
-  const bool has_pos = !vertices.empty() && vertices[0].position != 0, has_norm = !vertices.empty() && vertices[0].normal != 0,
-             has_tex = !vertices.empty() && vertices[0].texcoord != 0;
+  // the shape has it. (Like the reference, non-face elements do not advance the vertex cursor.)
+  const auto& vertices = obj.vertices;
+  const bool  has_pos = !vertices.empty() && vertices[0].position != 0, has_norm = !vertices.empty() && vertices[0].normal != 0,
+              has_tex = !vertices.empty() && vertices[0].texcoord != 0;
   size_t cur = 0;
-  for (int size : face_sizes) {
+  for (size_t e = 0; e < obj.sizes.size(); e++) {
+    if (obj.types[e] != 'f') continue;
+    const int size = obj.sizes[e];
     auto emit = [&](int a, int b, int c, int d) {
-      const Vertex &va = vertices[cur + a], &vb = vertices[cur + b], &vc = vertices[cur + c], &vd = vertices[cur + d];
+      const ObjVertex &va = vertices[cur + a], &vb = vertices[cur + b], &vc = vertices[cur + c], &vd = vertices[cur + d];
       if (has_pos) subdiv.quadspos.push_back({va.position - 1, vb.position - 1, vc.position - 1, vd.position - 1});
       if (has_norm) subdiv.quadsnorm.push_back({va.normal - 1, vb.normal - 1, vc.normal - 1, vd.normal - 1});
       if (has_tex) subdiv.quadstexcoord.push_back({va.texcoord - 1, vb.texcoord - 1, vc.texcoord - 1, vd.texcoord - 1});
@@ -1094,6 +1127,72 @@ bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& e
     cur += size;
   }
   if (subdiv.quadspos.empty()) return error = "empty shape " + filename, false;
+  return true;
+}
+
+// load_shape for .obj (yocto_sceneio.cpp:1036-1051): load_obj(face_varying = false) - one vertex per distinct
+// (position, texcoord, normal) triple in order of first use (yocto_modelio.cpp:1460-1489) - then get_faces / get_lines /
+// get_points (:1771-1856), including their cursor rule: an element of another type does not advance the vertex cursor.
+bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& error) {
+  ObjData obj;
+  if (!read_obj(filename, obj, error)) return false;
+  std::unordered_map<ObjVertex, ObjVertex, ObjVertexHash> vertex_map;
+  for (auto& vertex : obj.vertices) {
+    auto it = vertex_map.find(vertex);
+    if (it == vertex_map.end()) {
+      ObjVertex  fresh = vertex;
+      const int  index = (int)vertex_map.size();
+      if (vertex.position > 0) {
+        const v3& p = obj.positions[vertex.position - 1];
+        shape.positions.insert(shape.positions.end(), {p.x, p.y, p.z});
+        fresh.position = index + 1;
+      }
+      if (vertex.normal > 0) {
+        const v3& n = obj.normals[vertex.normal - 1];
+        shape.normals.insert(shape.normals.end(), {n.x, n.y, n.z});
+        fresh.normal = index + 1;
+      }
+      if (vertex.texcoord > 0) {
+        const v2& t = obj.texcoords[vertex.texcoord - 1];
+        shape.texcoords.insert(shape.texcoords.end(), {t.x, 1 - t.y});  // get_texcoords(obj, texcoords, flipv = true)
+        fresh.texcoord = index + 1;
+      }
+      vertex_map[vertex] = fresh;
+      vertex             = fresh;
+    } else {
+      vertex = it->second;
+    }
+  }
+  bool has_quads = false;
+  for (size_t e = 0; e < obj.sizes.size(); e++) has_quads |= obj.types[e] == 'f' && obj.sizes[e] == 4;
+  auto pos = [&](size_t i) { return obj.vertices[i].position - 1; };
+  size_t cur = 0;
+  for (size_t e = 0; e < obj.sizes.size(); e++) {  // get_faces
+    if (obj.types[e] != 'f') continue;
+    const int size = obj.sizes[e];
+    if (has_quads) {
+      if (size == 4) shape.quads.insert(shape.quads.end(), {pos(cur), pos(cur + 1), pos(cur + 2), pos(cur + 3)});
+      else
+        for (int c = 2; c < size; c++) shape.quads.insert(shape.quads.end(), {pos(cur), pos(cur + c - 1), pos(cur + c), pos(cur + c)});
+    } else {
+      for (int c = 2; c < size; c++) shape.triangles.insert(shape.triangles.end(), {pos(cur), pos(cur + c - 1), pos(cur + c)});
+    }
+    cur += size;
+  }
+  cur = 0;
+  for (size_t e = 0; e < obj.sizes.size(); e++) {  // get_lines
+    if (obj.types[e] != 'l') continue;
+    for (int c = 1; c < obj.sizes[e]; c++) shape.lines.insert(shape.lines.end(), {pos(cur + c - 1), pos(cur + c)});
+    cur += obj.sizes[e];
+  }
+  cur = 0;
+  for (size_t e = 0; e < obj.sizes.size(); e++) {  // get_points (every point of an element is its first vertex, as there)
+    if (obj.types[e] != 'p') continue;
+    for (int c = 0; c < obj.sizes[e]; c++) shape.points.push_back(pos(cur));
+    cur += obj.sizes[e];
+  }
+  if (shape.points.empty() && shape.lines.empty() && shape.triangles.empty() && shape.quads.empty())
+    return error = "empty shape " + filename, false;
   return true;
 }
 
