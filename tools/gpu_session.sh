@@ -28,8 +28,9 @@ for STEP in "$@"; do
       timeout -s KILL 120 $PERF c1 256 16 2 2>&1 | tail -n 1 | cut -c1-200
       timeout -s KILL 120 $PERF c2 1280 16 2 2>&1 | tail -n 1 | cut -c1-200
       timeout -s KILL 120 $PERF c5 1920 8 2 2>&1 | tail -n 1 | cut -c1-200 ;;
-    san)
-      timeout -s KILL 400 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "persistent_mode and 2" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     Host Frame\|^=========         in \|^$" gpurun_out/${TAG}_san.log | head -n 40 | cut -c1-240 ;;
+    san)     # memcheck over the three stack variants of the extend kernel and the shading kernels, small sizes
+      timeout -s KILL 500 compute-sanitizer --tool memcheck --print-limit 3 python -m pytest tests/test_gpu_parity.py -q -x -k "${SANTESTS:-(render_matches_oracle and (cornell or instanced4 or hair)) or deep_tree or refitted_bvh and instanced4}" > gpurun_out/${TAG}_san.log 2>&1; echo "sanitizer rc=$?"; grep -a "ERROR SUMMARY\|passed\|failed" gpurun_out/${TAG}_san.log | tail -n 4
+      timeout -s KILL 300 compute-sanitizer --tool memcheck --print-limit 3 $PERF c3 256 2 0 > gpurun_out/${TAG}_san_c3.log 2>&1; echo "sanitizer c3 rc=$?"; grep -a "ERROR SUMMARY\|Msamples" gpurun_out/${TAG}_san_c3.log | tail -n 3 | cut -c1-200 ;;
     ab2)
       IFS=';' read -ra CFGS <<< "${AB_CFGS:-lib;lib_new}"
       for CFG in "${CFGS[@]}"; do
