@@ -1406,22 +1406,24 @@ int ygl_intersect_rays(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* 
 // Test hook: evaluates the device libm function `fn` (0 sin, 1 cos, 2 exp, 3 log, 4 atan, 5 acos,
 // 6 atan2(x,y) with x as first argument, 7 pow(x,y), 8 sqrt, 9 fmod(x,y)) on host arrays.
 // tonemap_image (yocto_image.h:242-245, yocto_image.cpp:911-922)
+struct DeviceBuffer {  // cudaMalloc'd scratch that is freed on every path out of a function
+  void* p = nullptr;
+  ~DeviceBuffer() {
+    if (p) cudaFree(p);
+  }
+};
 static int tonemap_on_device(ygl_context* ctx, const float4* d_hdr, int64_t n, float exposure, int filmic, int srgb,
     float* ldr, uint8_t* ldr_bytes) {
-  float4* d_ldr   = nullptr;
-  uchar4* d_bytes = nullptr;
-  if (ldr) CUDA_TRY(cudaMalloc((void**)&d_ldr, n * 16));
-  if (ldr_bytes) CUDA_TRY(cudaMalloc((void**)&d_bytes, n * 4));
+  DeviceBuffer d_ldr, d_bytes;
+  if (ldr) CUDA_TRY(cudaMalloc(&d_ldr.p, n * 16));
+  if (ldr_bytes) CUDA_TRY(cudaMalloc(&d_bytes.p, n * 4));
   // `if (exposure != 0) rgb *= exp2(exposure)`: one libm call per image, made where the reference makes it
   const bool  scaled = exposure != 0;
   const float scale  = scaled ? std::exp2(exposure) : 1.0f;
-  launch_tonemap(ctx->stream, ctx->num_sms, d_hdr, n, scale, scaled, filmic != 0, srgb != 0, d_ldr, d_bytes);
-  if (ldr) cudaMemcpyAsync(ldr, d_ldr, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
-  if (ldr_bytes) cudaMemcpyAsync(ldr_bytes, d_bytes, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  if (d_ldr) cudaFree(d_ldr);
-  if (d_bytes) cudaFree(d_bytes);
-  if (e != cudaSuccess) return fail(YGL_ERR_CUDA, cudaGetErrorString(e));
+  launch_tonemap(ctx->stream, ctx->num_sms, d_hdr, n, scale, scaled, filmic != 0, srgb != 0, (float4*)d_ldr.p, (uchar4*)d_bytes.p);
+  if (ldr) CUDA_TRY(cudaMemcpyAsync(ldr, d_ldr.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ldr_bytes) CUDA_TRY(cudaMemcpyAsync(ldr_bytes, d_bytes.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return YGL_OK;
 }
 int ygl_tonemap_image(ygl_context* ctx, const float* hdr, int64_t num_pixels, float exposure, int filmic, int srgb, float* ldr,
@@ -1430,12 +1432,10 @@ int ygl_tonemap_image(ygl_context* ctx, const float* hdr, int64_t num_pixels, fl
   if (!ldr && !ldr_bytes) return fail(YGL_ERR_INVALID, "no output buffer");
   if (num_pixels == 0) return YGL_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
-  float4* d_hdr = nullptr;
-  CUDA_TRY(cudaMalloc((void**)&d_hdr, num_pixels * 16));
-  cudaMemcpyAsync(d_hdr, hdr, num_pixels * 16, cudaMemcpyHostToDevice, ctx->stream);
-  int rc = tonemap_on_device(ctx, d_hdr, num_pixels, exposure, filmic, srgb, ldr, ldr_bytes);
-  cudaFree(d_hdr);
-  return rc;
+  DeviceBuffer d_hdr;
+  CUDA_TRY(cudaMalloc(&d_hdr.p, num_pixels * 16));
+  CUDA_TRY(cudaMemcpyAsync(d_hdr.p, hdr, num_pixels * 16, cudaMemcpyHostToDevice, ctx->stream));
+  return tonemap_on_device(ctx, (const float4*)d_hdr.p, num_pixels, exposure, filmic, srgb, ldr, ldr_bytes);
 }
 int ygl_state_tonemap(ygl_state* state, float exposure, int filmic, int srgb, float* ldr, uint8_t* ldr_bytes) {
   if (!state) return fail(YGL_ERR_INVALID, "null state");

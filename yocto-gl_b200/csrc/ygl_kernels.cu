@@ -1334,15 +1334,9 @@ void launch_extend(cudaStream_t s, int num_sms, const Tuning& tune, DScene scene
     return;
   }
 #endif
-  if (tune.carveout >= 0) {
-    // how the SM's 256 KB split between L1 and shared memory is a per-kernel preference; set once per value
-    static int applied[3][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};
-    int& have = applied[scene.stack_mode][lone > 0 ? 1 : 0][trav ? 1 : 0];
-    if (have != tune.carveout) {
-      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, tune.carveout));
-      have = tune.carveout;
-    }
-  }
+  // how the SM's 256 KB split between L1 and shared memory is a per-kernel, per-device preference
+  if (tune.carveout >= 0)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, tune.carveout));
   kernel<<<blocks, 128, 0, s>>>(scene, st, q, parity, trav, tune.refill, reps_and_weights, suspend, lone, tune.lone_steps);
 }
 
