@@ -15,14 +15,19 @@ import sys
 
 SCENES = ["features1", "materials1", "materials2", "materials3", "materials4", "materials5", "shapes1", "shapes4", "cornellbox",
           "arealights1", "environments1", "environments2", "furnace1", "furnace2", "instances1", "features2", "shapes2"]
+# the same scenes in the older scene format 4.0 (objects keyed by name, files found by name): stored as v40_<name>
+SCENES_V40 = ["arealights1", "cornellbox", "environments1", "environments2", "features1", "features2", "furnace1", "instances1",
+              "materials1", "materials2", "materials3", "materials4", "materials5", "shapes1", "shapes2", "shapes3"]
 EXTRA_SHAPES = ["bunny.ply", "hairball1.ply", "sphere.ply", "floor.ply", "arealight1.ply", "arealight2.ply"]
 EXTRA_TEXTURES = ["sky.hdr", "floor.png"]
 
 
 def main(ref, out):
     tests = os.path.join(ref, "tests")
+    out40 = out.rstrip("/") + "_v40"    # format-4.0 scenes: host-only loader tests, listed in .gpurunignore (76 MB)
     for sub in ("pool/shapes", "pool/textures", "pool/subdivs", "scenes"):
         os.makedirs(os.path.join(out, sub), exist_ok=True)
+    os.makedirs(os.path.join(out40, "scenes"), exist_ok=True)
 
     def copy(src, dst):
         if not os.path.exists(dst) or os.path.getsize(dst) != os.path.getsize(src):
@@ -36,14 +41,14 @@ def main(ref, out):
             copy(src, os.path.join(out, "pool", kind, f))
             by_hash[(kind, hashlib.sha1(open(src, "rb").read()).hexdigest())] = f
 
-    def pooled(src, kind):
+    def pooled(src, kind, root=None):
         """scene files go into the pool under a content hash (several scenes ship different files of one name)"""
         data = open(src, "rb").read()
         digest = hashlib.sha1(data).hexdigest()
-        if (kind, digest) in by_hash:
+        if (kind, digest) in by_hash and root is None:
             return by_hash[(kind, digest)]
         name = digest[:12] + "_" + os.path.basename(src)
-        dst = os.path.join(out, "pool", kind, name)
+        dst = os.path.join(root or out, "pool", kind, name)
         if not os.path.exists(dst):
             open(dst, "wb").write(data)
         return name
@@ -60,8 +65,32 @@ def main(ref, out):
                 assert uri.startswith(group + "/"), uri
                 files[uri] = pooled(os.path.join(src_dir, uri), group)
         json.dump(files, open(os.path.join(out, "scenes", name + ".files"), "w"), indent=0)
-    total = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(out) for f in fs)
-    print(f"copy_test_data: {total / 1e6:.1f} MB under {out}")
+    for name in SCENES_V40:
+        src_dir = os.path.join(tests, "_version40", name)
+        src = os.path.join(src_dir, name + ".json")
+        scene = json.load(open(src))
+        copy(src, os.path.join(out40, "scenes", name + ".json"))
+        mentioned = set()
+
+        def walk(x):
+            if isinstance(x, dict):
+                for v in x.values():
+                    walk(v)
+            elif isinstance(x, str):
+                mentioned.add(x)
+        walk(scene)
+        mentioned |= set(scene.get("subdivs", {}))          # a subdiv's file is named after its key
+        files = {}
+        for group in ("shapes", "textures", "subdivs", "instances"):
+            os.makedirs(os.path.join(out40, "pool", group), exist_ok=True)
+            d = os.path.join(src_dir, group)
+            for f in sorted(os.listdir(d)) if os.path.isdir(d) else []:
+                if os.path.splitext(f)[0] in mentioned and not f.endswith(".py"):
+                    files[group + "/" + f] = pooled(os.path.join(d, f), group, out40)
+        json.dump(files, open(os.path.join(out40, "scenes", name + ".files"), "w"), indent=0)
+    for root in (out, out40):
+        total = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(root) for f in fs)
+        print(f"copy_test_data: {total / 1e6:.1f} MB under {root}")
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@ import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DATA = os.path.join(ROOT, "oracle", "_ref", "data")
+DATA_V40 = DATA + "_v40"   # the same scenes in scene format 4.0: host-only loader tests, does not travel to the GPU box
 
 
 def available():
@@ -19,17 +20,23 @@ def pool(kind, name):
     return os.path.join(DATA, "pool", kind, name)
 
 
-def scene_file(name, tmpdir):
+def names_v40():
+    d = os.path.join(DATA_V40, "scenes")
+    return sorted(f[:-5] for f in os.listdir(d) if f.endswith(".json")) if os.path.isdir(d) else []
+
+
+def scene_file(name, tmpdir, data=None):
     """Path of <tmpdir>/<name>/<name>.json with every shape / texture uri symlinked to its pooled file."""
     import json
+    data = data or DATA
     d = os.path.join(str(tmpdir), name)
     dst = os.path.join(d, name + ".json")
     if not os.path.exists(dst):
         os.makedirs(d, exist_ok=True)
-        os.symlink(os.path.join(DATA, "scenes", name + ".json"), dst)
-        files = json.load(open(os.path.join(DATA, "scenes", name + ".files")))
+        os.symlink(os.path.join(data, "scenes", name + ".json"), dst)
+        files = json.load(open(os.path.join(data, "scenes", name + ".files")))
         for uri, pooled in files.items():
             kind = uri.split("/")[0]
             os.makedirs(os.path.join(d, kind), exist_ok=True)
-            os.symlink(os.path.join(DATA, "pool", kind, pooled), os.path.join(d, uri))
+            os.symlink(os.path.join(data, "pool", kind, pooled), os.path.join(d, uri))
     return dst

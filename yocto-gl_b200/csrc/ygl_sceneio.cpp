@@ -183,15 +183,18 @@ struct JParser {
 // get_opt of the reference: a present key of the wrong type is a parse error, a missing key keeps the default
 struct JReader {
   bool ok = true;
+  // (nlohmann converts a JSON boolean to any arithmetic type but double / int64: `"lens": true` reads as 1)
   void get(const JValue& e, const char* key, float& value) {
     if (auto v = e.find(key)) {
-      if (v->type != JValue::Number) ok = false;
+      if (v->type == JValue::Bool) value = v->boolean ? 1.0f : 0.0f;
+      else if (v->type != JValue::Number) ok = false;
       else value = (float)v->number;
     }
   }
   void get(const JValue& e, const char* key, int& value) {
     if (auto v = e.find(key)) {
-      if (v->type != JValue::Number) ok = false;
+      if (v->type == JValue::Bool) value = v->boolean ? 1 : 0;
+      else if (v->type != JValue::Number) ok = false;
       else value = (int)v->number;
     }
   }
@@ -209,10 +212,12 @@ struct JReader {
   }
   void get_floats(const JValue& e, const char* key, float* value, size_t n) {
     if (auto v = e.find(key)) {
-      if (v->type != JValue::Array || v->array.size() != n) return void(ok = false);
+      // std::array from_json reads j.at(i) for i < n: a longer array passes, a shorter one throws
+      if (v->type != JValue::Array || v->array.size() < n) return void(ok = false);
       for (size_t i = 0; i < n; i++) {
-        if (v->array[i].type != JValue::Number) return void(ok = false);
-        value[i] = (float)v->array[i].number;
+        if (v->array[i].type == JValue::Bool) value[i] = v->array[i].boolean ? 1.0f : 0.0f;
+        else if (v->array[i].type != JValue::Number) return void(ok = false);
+        else value[i] = (float)v->array[i].number;
       }
     }
   }
@@ -1299,6 +1304,27 @@ struct ygl_loaded_scene {
 
 namespace {
 
+// what a scene file names next to its own arrays: files to read, subdivs to tesselate, and (format 4.0 only) the
+// instance lists that expand one JSON object into many instances
+struct SceneParts {
+  std::vector<std::string>     shape_files, texture_files, subdiv_files;  // relative to the scene's directory
+  std::vector<HostSubdiv>      subdivs;
+  std::vector<std::string>     instance_files;                           // 4.0: instances/<name>.ply
+  std::unordered_map<int, int> instance_ply;                              // 4.0: instance id -> instance_files index
+};
+
+float* frame_of(ygl_frame3f& f) { return (float*)&f; }
+static_assert(sizeof(ygl_frame3f) == 48, "frame layout");
+
+bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, SceneParts& parts, JReader& rd);
+bool parse_json_scene_v40(const JValue& json, const std::string& dirname, ygl_loaded_scene& scene, SceneParts& parts, JReader& rd);
+bool load_scene_parts(const std::string& filename, ygl_loaded_scene& scene, SceneParts& parts, std::string& error);
+void add_missing_camera(ygl_loaded_scene& scene);
+void add_missing_radius(ygl_loaded_scene& scene);
+
+// load_json_scene, yocto_sceneio.cpp:3618-3631: a file without asset.version is format 4.0 (:3025-3372), "4.1" goes to a
+// loader that ends in `return false` whatever it read (:3614) - the reference cannot load such files and neither do we -,
+// everything else must say 4.2 or 5.0
 bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::string& error) {
   std::vector<uint8_t> text;
   if (!read_file(filename, text, error)) return false;
@@ -1306,23 +1332,32 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
   JValue  json;
   JParser parser{(const char*)text.data(), (const char*)text.data() + text.size() - 1};
   auto    parse_error = [&]() { return error = "cannot parse " + filename, false; };
-  if (!parser.parse(json) || json.type != JValue::Object) return parse_error();
+  if (!parser.parse(json)) return parse_error();
   parser.skip();
   if (parser.p != parser.end) return parse_error();
 
-  JReader rd;
-  std::string version;
-  if (auto asset = json.find("asset")) {
-    rd.get(*asset, "copyright", scene.copyright);
+  JReader      rd;
+  SceneParts   parts;
+  const JValue* asset       = json.find("asset");
+  const JValue* version_key = asset ? asset->find("version") : nullptr;
+  if (asset) rd.get(*asset, "copyright", scene.copyright);
+  if (!version_key) {
+    if (json.type != JValue::Object) return parse_error();
+    if (!parse_json_scene_v40(json, path_dirname(filename), scene, parts, rd) || !rd.ok) return parse_error();
+  } else {
+    if (version_key->type == JValue::String && version_key->string == "4.1")
+      return error = "cannot load " + filename + ": the reference's loader for scene format 4.1 always fails", false;
+    std::string version;
     rd.get(*asset, "version", version);
+    if (!rd.ok || (version != "4.2" && version != "5.0")) return parse_error();
+    if (!parse_json_scene_v42(json, scene, parts, rd) || !rd.ok) return parse_error();
   }
-  if (version != "4.2" && version != "5.0") {
-    error = "cannot parse " + filename + ": only scene format 4.2 / 5.0 is supported (found '" + version + "')";
-    return false;
-  }
-  std::vector<std::string> shape_files, texture_files;
-  auto frame_of = [](ygl_frame3f& f) { return (float*)&f; };
-  static_assert(sizeof(ygl_frame3f) == 48, "frame layout");
+  return load_scene_parts(filename, scene, parts, error);
+}
+
+bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, SceneParts& parts, JReader& rd) {
+  auto& shape_files = parts.shape_files;
+  auto& texture_files = parts.texture_files;
   if (auto group = json.find("cameras")) {
     for (auto& e : group->array) {
       ygl_camera camera = {};
@@ -1370,10 +1405,8 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
       m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
       std::string name, type;
       rd.get(e, "name", name);
-      if (e.find("type")) {
-        rd.get(e, "type", type);
-        m.type = material_type_from_name(type);
-      }
+      if (auto t = e.find("type"))  // the enum conversion never throws: anything but a known label is the first entry
+        m.type = t->type == JValue::String ? material_type_from_name(t->string) : 0;
       rd.get_floats(e, "emission", m.emission, 3);
       rd.get_floats(e, "color", m.color, 3);
       rd.get(e, "metallic", m.metallic);
@@ -1401,8 +1434,8 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
       shape_files.push_back(uri);
     }
   }
-  std::vector<HostSubdiv>  subdivs;
-  std::vector<std::string> subdiv_files;
+  auto& subdivs      = parts.subdivs;
+  auto& subdiv_files = parts.subdiv_files;
   if (auto group = json.find("subdivs")) {
     for (auto& e : group->array) {
       HostSubdiv  subdiv;
@@ -1457,11 +1490,211 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
       scene.names[5].push_back(name);
     }
   }
-  if (!rd.ok) return parse_error();
+  return rd.ok;
+}
 
-  // resources, in parallel like the reference
+// Scene format 4.0 (load_json_scene_version40, yocto_sceneio.cpp:3025-3372): every group is an object keyed by element
+// name, read in the fixed order cameras, environments, materials, instances, objects, subdivs; shapes and textures have
+// no entries of their own - an instance / material / environment / subdiv names them and the first mention creates
+// them; material labels are the older set (metallic, volume); `lookat` never flips x and z; files are found by trying
+// extensions under shapes/ textures/ subdivs/ instances/.
+bool path_exists(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (f) fclose(f);
+  return f != nullptr;
+}
+bool parse_json_scene_v40(const JValue& json, const std::string& dirname, ygl_loaded_scene& scene, SceneParts& parts, JReader& rd) {
+  if (auto asset = json.find("asset"); asset && asset->type != JValue::Object) return false;
+  // nlohmann's items(): object members in file order, array elements under their index, nothing for null
+  using Item = std::pair<std::string, const JValue*>;
+  auto items = [&](const char* name) {
+    std::vector<Item> out;
+    auto group = json.find(name);
+    if (!group || group->type == JValue::Null) return out;
+    if (group->type == JValue::Object) {
+      for (auto& kv : group->object) out.push_back({kv.first, &kv.second});
+    } else if (group->type == JValue::Array) {
+      for (size_t i = 0; i < group->array.size(); i++) out.push_back({std::to_string(i), &group->array[i]});
+    } else {
+      rd.ok = false;
+    }
+    for (auto& item : out)
+      if (item.second->type != JValue::Object) rd.ok = false;  // json.value(key, default) throws on anything else
+    if (!rd.ok) out.clear();
+    return out;
+  };
+  // a reference by name; an empty or missing name keeps the default (-1)
+  std::vector<std::string>             shape_names, texture_names, subdiv_names;
+  std::unordered_map<std::string, int> shape_map, texture_map, material_map, instance_map;
+  auto named = [&](const JValue& e, const char* key, std::string& name) {
+    name.clear();
+    rd.get(e, key, name);
+    return rd.ok && !name.empty();
+  };
+  auto get_created = [&](const JValue& e, const char* key, int& value, std::unordered_map<std::string, int>& map,
+                         std::vector<std::string>& names) {
+    std::string name;
+    if (!named(e, key, name)) return;
+    auto it = map.find(name);
+    if (it == map.end()) {
+      names.push_back(name);
+      it = map.insert({name, (int)names.size() - 1}).first;
+    }
+    value = it->second;
+  };
+  auto lookat = [&](const JValue& e, ygl_frame3f& frame, float* focus) {
+    if (!e.find("lookat")) return;
+    float m[9];
+    memcpy(m, &frame, sizeof(m));  // the default of the read is what the frame holds
+    rd.get_floats(e, "lookat", m, 9);
+    v3 eye = {m[0], m[1], m[2]}, center = {m[3], m[4], m[5]}, up = {m[6], m[7], m[8]};
+    if (focus) *focus = length(eye - center);
+    lookat_frame(frame_of(frame), eye, center, up, false);
+  };
+  for (auto& [key, e] : items("cameras")) {
+    ygl_camera camera = {};
+    memcpy(&camera.frame, kIdentityFrame, 48);
+    camera.orthographic = 0, camera.lens = 0.050f, camera.film = 0.036f, camera.aspect = 1.500f, camera.focus = 10000,
+    camera.aperture = 0;
+    rd.get_floats(*e, "frame", frame_of(camera.frame), 12);
+    rd.get_bool(*e, "orthographic", camera.orthographic);
+    rd.get_bool(*e, "ortho", camera.orthographic);
+    rd.get(*e, "lens", camera.lens);
+    rd.get(*e, "aspect", camera.aspect);
+    rd.get(*e, "film", camera.film);
+    rd.get(*e, "focus", camera.focus);
+    rd.get(*e, "aperture", camera.aperture);
+    lookat(*e, camera.frame, &camera.focus);
+    scene.cameras.push_back(camera);
+    scene.names[0].push_back(key);
+  }
+  for (auto& [key, e] : items("environments")) {
+    ygl_environment env = {};
+    memcpy(&env.frame, kIdentityFrame, 48);
+    env.emission_tex = -1;
+    rd.get_floats(*e, "frame", frame_of(env.frame), 12);
+    rd.get_floats(*e, "emission", env.emission, 3);
+    get_created(*e, "emission_tex", env.emission_tex, texture_map, texture_names);
+    lookat(*e, env.frame, nullptr);
+    scene.environments.push_back(env);
+    scene.names[5].push_back(key);
+  }
+  for (auto& [key, e] : items("materials")) {
+    ygl_material m = {};
+    m.type = 0, m.roughness = 0, m.metallic = 0, m.ior = 1.5f, m.scanisotropy = 0, m.trdepth = 0.01f, m.opacity = 1;
+    m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
+    material_map[key] = (int)scene.materials.size();
+    if (auto t = e->find("type"); t && t->type == JValue::String) {
+      static const char* labels[] = {"matte", "glossy", "metallic", "transparent", "refractive", "subsurface", "volume", "gltfpbr"};
+      for (int i = 0; i < 8; i++)
+        if (t->string == labels[i]) m.type = i;  // same ordinals as today's reflective / volumetric
+    }
+    rd.get_floats(*e, "emission", m.emission, 3);
+    rd.get_floats(*e, "color", m.color, 3);
+    rd.get(*e, "metallic", m.metallic);
+    rd.get(*e, "roughness", m.roughness);
+    rd.get(*e, "ior", m.ior);
+    rd.get(*e, "trdepth", m.trdepth);
+    rd.get_floats(*e, "scattering", m.scattering, 3);
+    rd.get(*e, "scanisotropy", m.scanisotropy);
+    rd.get(*e, "opacity", m.opacity);
+    get_created(*e, "emission_tex", m.emission_tex, texture_map, texture_names);
+    get_created(*e, "color_tex", m.color_tex, texture_map, texture_names);
+    get_created(*e, "roughness_tex", m.roughness_tex, texture_map, texture_names);
+    get_created(*e, "scattering_tex", m.scattering_tex, texture_map, texture_names);
+    get_created(*e, "normal_tex", m.normal_tex, texture_map, texture_names);
+    scene.materials.push_back(m);
+    scene.names[2].push_back(key);
+  }
+  for (const char* group : {"instances", "objects"}) {
+    for (auto& [key, e] : items(group)) {
+      ygl_instance inst = {};
+      memcpy(&inst.frame, kIdentityFrame, 48);
+      inst.shape = inst.material = -1;
+      rd.get_floats(*e, "frame", frame_of(inst.frame), 12);
+      get_created(*e, "shape", inst.shape, shape_map, shape_names);
+      std::string material;
+      if (named(*e, "material", material)) {  // materials are not created on mention: an unknown name is an error
+        auto it = material_map.find(material);
+        if (it == material_map.end()) rd.ok = false;
+        else inst.material = it->second;
+      }
+      lookat(*e, inst.frame, nullptr);
+      if (group[0] == 'o' && e->find("instance")) {  // only "objects" read the instance list
+        int list = -1;
+        get_created(*e, "instance", list, instance_map, parts.instance_files);
+        if (list >= 0) parts.instance_ply[(int)scene.instances.size()] = list;
+      }
+      scene.instances.push_back(inst);
+      scene.names[4].push_back(key);
+    }
+  }
+  for (auto& [key, e] : items("subdivs")) {
+    HostSubdiv subdiv;
+    get_created(*e, "shape", subdiv.shape, shape_map, shape_names);
+    rd.get(*e, "subdivisions", subdiv.subdivisions);
+    rd.get_bool(*e, "catmullclark", subdiv.catmullclark);
+    rd.get_bool(*e, "smooth", subdiv.smooth);
+    rd.get(*e, "displacement", subdiv.displacement);
+    get_created(*e, "displacement_tex", subdiv.displacement_tex, texture_map, texture_names);
+    parts.subdivs.push_back(subdiv);
+    subdiv_names.push_back(key);
+  }
+  if (!rd.ok) return false;
+  // find_path, yocto_sceneio.cpp:3250-3258: the first extension whose file exists, else the first extension
+  auto find_path = [&](const std::string& name, const char* group, std::initializer_list<const char*> extensions) {
+    for (auto ext : extensions)
+      if (path_exists(path_join(dirname, path_join(group, name + ext)))) return path_join(group, name + ext);
+    return path_join(group, name + *extensions.begin());
+  };
+  for (auto& name : shape_names) parts.shape_files.push_back(find_path(name, "shapes", {".ply", ".obj"}));
+  for (auto& name : subdiv_names) parts.subdiv_files.push_back(find_path(name, "subdivs", {".ply", ".obj"}));
+  for (auto& name : texture_names) parts.texture_files.push_back(find_path(name, "textures", {".hdr", ".exr", ".png", ".jpg"}));
+  for (auto& name : parts.instance_files) name = find_path(name, "instances", {".ply"});
+  scene.names[1] = texture_names;
+  scene.names[3] = shape_names;
+  return true;
+}
+
+// frame3f * frame3f, yocto_math.h:2108-2110 with mat3f * vec3f = a.x * b.x + a.y * b.y + a.z * b.z (:1942-1944)
+void frame_multiply(float* out, const float* a, const float* b) {
+  auto rot = [&](const float* v, float* r) {
+    for (int k = 0; k < 3; k++) r[k] = (a[0 + k] * v[0] + a[3 + k] * v[1]) + a[6 + k] * v[2];
+  };
+  float r[12];
+  rot(b + 0, r + 0), rot(b + 3, r + 3), rot(b + 6, r + 6), rot(b + 9, r + 9);
+  for (int k = 0; k < 3; k++) r[9 + k] = r[9 + k] + a[9 + k];
+  memcpy(out, r, sizeof(r));
+}
+
+// load_instance, yocto_sceneio.cpp:2873-2892: element "instance" with twelve scalar properties
+bool load_instance_frames(const std::string& filename, std::vector<float>& frames, std::string& error) {
+  if (path_extension(filename) != ".ply") return error = "unsupported format " + filename, false;
+  std::vector<PlyElement> ply;
+  if (!load_ply(filename, ply, error)) return false;
+  static const char* names[12] = {"xx", "xy", "xz", "yx", "yy", "yz", "zx", "zy", "zz", "ox", "oy", "oz"};
+  const PlyProperty* props[12];
+  for (int k = 0; k < 12; k++) {
+    props[k] = ply_find(ply, "instance", names[k]);
+    if (!props[k] || props[k]->is_list) return error = "cannot parse " + filename, false;
+  }
+  const size_t n = props[0]->values.size();
+  frames.assign(n * 12, 0.0f);
+  for (int k = 0; k < 12; k++)
+    for (size_t i = 0; i < n && i < props[k]->values.size(); i++) frames[i * 12 + k] = (float)props[k]->values[i];
+  return true;
+}
+
+// the part every JSON format shares: read the files the scene names (in parallel like the reference), expand 4.0's
+// instance lists, apply the fix-ups, tesselate
+bool load_scene_parts(const std::string& filename, ygl_loaded_scene& scene, SceneParts& parts, std::string& error) {
+  auto& shape_files = parts.shape_files;
+  auto& texture_files = parts.texture_files;
+  auto& subdiv_files = parts.subdiv_files;
+  auto& subdivs = parts.subdivs;
   const auto dirname = path_dirname(filename);
   scene.shape_data.resize(shape_files.size());
+  scene.texture_data.resize(texture_files.size());
   auto dependent_error = [&]() { return error = "cannot load " + filename + " since " + error, false; };
   if (!parallel_load(shape_files.size(), error,
           [&](size_t i, std::string& err) { return load_shape(path_join(dirname, shape_files[i]), scene.shape_data[i], err); }))
@@ -1473,8 +1706,46 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
         return load_texture(path_join(dirname, texture_files[i]), scene.texture_data[i], err);
       }))
     return dependent_error();
+  std::vector<std::vector<float>> instance_frames(parts.instance_files.size());
+  if (!parallel_load(parts.instance_files.size(), error, [&](size_t i, std::string& err) {
+        return load_instance_frames(path_join(dirname, parts.instance_files[i]), instance_frames[i], err);
+      }))
+    return dependent_error();
+  // "apply instances", yocto_sceneio.cpp:3335-3363: an object with an instance list becomes one instance per listed
+  // frame (list frame * object frame), named <object>_<k>
+  if (!parts.instance_files.empty()) {
+    auto instances = std::move(scene.instances);
+    auto names     = std::move(scene.names[4]);
+    scene.instances.clear(), scene.names[4].clear();
+    for (size_t i = 0; i < instances.size(); i++) {
+      auto it = parts.instance_ply.find((int)i);
+      if (it == parts.instance_ply.end()) {
+        scene.instances.push_back(instances[i]);
+        scene.names[4].push_back(names[i]);
+        continue;
+      }
+      const auto& frames = instance_frames[it->second];
+      for (size_t k = 0; k < frames.size() / 12; k++) {
+        ygl_instance inst = instances[i];
+        frame_multiply(frame_of(inst.frame), &frames[k * 12], frame_of(instances[i].frame));
+        scene.instances.push_back(inst);
+        scene.names[4].push_back(names[i] + "_" + std::to_string(k));
+      }
+    }
+  }
+  add_missing_camera(scene);
+  add_missing_radius(scene);
+  // tesselate_subdivs (yocto_scene.cpp:807-812): what every reference app does right after load_scene
+  for (auto& subdiv : subdivs) {
+    if (subdiv.shape < 0 || subdiv.shape >= (int)scene.shape_data.size())
+      return error = "cannot load " + filename + ": subdiv shape id out of range", false;
+    if (!tesselate_subdiv(scene.shape_data[subdiv.shape], subdiv, scene.texture_data, error)) return dependent_error();
+  }
+  return true;
+}
 
-  // fix-ups: add_missing_camera (yocto_sceneio.cpp:2119-2139), add_missing_radius (:2142-2148)
+// fix-ups: add_missing_camera (yocto_sceneio.cpp:2119-2139), add_missing_radius (:2142-2148)
+void add_missing_camera(ygl_loaded_scene& scene) {
   if (scene.cameras.empty()) {
     struct box {
       v3 min = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, max = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
@@ -1515,18 +1786,13 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
     scene.cameras.push_back(camera);
     scene.names[0].push_back("camera");
   }
+}
+void add_missing_radius(ygl_loaded_scene& scene) {
   for (auto& shape : scene.shape_data) {
     if (shape.points.empty() && shape.lines.empty()) continue;
     if (!shape.radius.empty()) continue;
     shape.radius.assign(shape.positions.size() / 3, 0.001f);
   }
-  // tesselate_subdivs (yocto_scene.cpp:807-812): what every reference app does right after load_scene
-  for (auto& subdiv : subdivs) {
-    if (subdiv.shape < 0 || subdiv.shape >= (int)scene.shape_data.size())
-      return error = "cannot load " + filename + ": subdiv shape id out of range", false;
-    if (!tesselate_subdiv(scene.shape_data[subdiv.shape], subdiv, scene.texture_data, error)) return dependent_error();
-  }
-  return true;
 }
 
 void make_desc(ygl_loaded_scene& scene) {
