@@ -215,3 +215,21 @@ def test_format40_objects_and_instance_lists(ref, tmp_path):
         lib.load_scene(bad)
     with pytest.raises(RuntimeError):
         ref.load_scene(bad)
+
+
+def test_ply_file_as_scene_with_procedural_sky(ref, tmp_path):
+    """`load_scene("x.ply")` (load_ply_scene, yocto_sceneio.cpp:4364): the shape, the default matte material, the framing
+    camera and add_sky's 1024 x 512 Preetham sky (make_sunsky) as environment - every texel bit-identical."""
+    src = scene_data.pool("shapes", "bunny.ply")
+    path = tmp_path / "bunny.ply"
+    os.symlink(src, path)
+    ours, theirs = lib.load_scene(path), ref.load_scene(path)
+    assert_scenes_identical(ours, theirs)
+    sky = ours.textures[0]
+    assert sky["pixels"].shape == (512, 1024, 4) and sky["pixels"].dtype == np.float32 and sky["linear"]
+    assert float(sky["pixels"][:256, :, :3].max()) > 0.05 and np.ptp(sky["pixels"][256:, :, :3], axis=(0, 1)).max() == 0
+    tri = tmp_path / "tri.ply"
+    _write_tri_ply(tri)
+    assert_scenes_identical(lib.load_scene(tri), ref.load_scene(tri))
+    with pytest.raises(lib.YglError):
+        lib.load_scene(tmp_path / "scene.gltf")

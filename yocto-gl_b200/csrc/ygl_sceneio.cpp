@@ -1795,6 +1795,122 @@ void add_missing_radius(ygl_loaded_scene& scene) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// A single .ply file as a scene (load_ply_scene, yocto_sceneio.cpp:4364-4381): the shape under an identity frame, the
+// default matte material (add_missing_material, :2151-2163), the framing camera, and - since such a scene never has a
+// light - the procedural sky of add_sky (yocto_scene.cpp:645-653): make_sunsky(1024, 512, pi / 4) as a linear
+// environment texture with emission 1.
+// make_sunsky (yocto_image.cpp:1245-1373) is the Preetham / Perez daylight model in xyY, evaluated for the upper half of
+// a lat-long image, with the lower half filled by the light the ground reflects. Float arithmetic in the reference's
+// order through this host's libm (the same one the reference calls); the sun disk is off in add_sky's call.
+// ---------------------------------------------------------------------------------------------------------------
+struct SkyModel {
+  float zenith[3];       // xyY at the zenith
+  float perez[5][3];     // A..E per xyY channel
+};
+// cubic in the sun angle with the reference's association: ((k3 t^3 + k2 t^2) + k1 t) + k0
+float sun_cubic(const float (&k)[4], float t) { return k[0] * std::pow(t, 3.f) + k[1] * std::pow(t, 2.f) + k[2] * t + k[3]; }
+SkyModel make_sky_model(float theta_sun, float turbidity) {
+  static const float chroma[2][3][4] = {
+      {{+0.00165f, -0.00374f, +0.00208f, +0.00000f}, {-0.02902f, +0.06377f, -0.03202f, +0.00394f}, {+0.11693f, -0.21196f, +0.06052f, +0.25885f}},
+      {{+0.00275f, -0.00610f, +0.00316f, +0.00000f}, {-0.04214f, +0.08970f, -0.04153f, +0.00515f}, {+0.15346f, -0.26756f, +0.06669f, +0.26688f}}};
+  static const float perez_slope[5][3]  = {{-0.01925f, -0.01669f, +0.17872f}, {-0.06651f, -0.09495f, -0.35540f},
+       {-0.00041f, -0.00792f, -0.02266f}, {-0.06409f, -0.04405f, +0.12064f}, {-0.00325f, -0.01092f, -0.06696f}};
+  static const float perez_offset[5][3] = {{-0.25922f, -0.26078f, -1.46303f}, {+0.00081f, +0.00921f, +0.42749f},
+      {+0.21247f, +0.21023f, +5.32505f}, {-0.89887f, -1.65369f, -2.57705f}, {+0.04517f, +0.05291f, +0.37027f}};
+  const float pif = 3.14159265358979323846f;
+  SkyModel sky;
+  for (int c = 0; c < 2; c++)
+    sky.zenith[c] = sun_cubic(chroma[c][0], theta_sun) * std::pow(turbidity, 2.f) + sun_cubic(chroma[c][1], theta_sun) * turbidity +
+                    sun_cubic(chroma[c][2], theta_sun);
+  sky.zenith[2] = 1000 * (4.0453f * turbidity - 4.9710f) * std::tan((4.0f / 9.0f - turbidity / 120.0f) * (pif - 2 * theta_sun)) -
+                  .2155f * turbidity + 2.4192f;
+  for (int k = 0; k < 5; k++)
+    for (int c = 0; c < 3; c++) sky.perez[k][c] = perez_slope[k][c] * turbidity + perez_offset[k][c];
+  return sky;
+}
+// one sky colour: Perez' F(theta, gamma) / F(0, theta_sun) per xyY channel, then xyY -> XYZ -> linear sRGB, / 10000
+void sky_radiance(const SkyModel& sky, float theta, float gamma, float theta_sun, float rgb[3]) {
+  float xyY[3];
+  for (int c = 0; c < 3; c++) {
+    const float A = sky.perez[0][c], B = sky.perez[1][c], C = sky.perez[2][c], D = sky.perez[3][c], E = sky.perez[4][c];
+    const float num = (1 + A * std::exp(B / std::cos(theta))) * (1 + C * std::exp(D * gamma) + E * std::cos(gamma) * std::cos(gamma));
+    const float den = (1 + A * std::exp(B)) * (1 + C * std::exp(D * theta_sun) + E * std::cos(theta_sun) * std::cos(theta_sun));
+    xyY[c]          = sky.zenith[c] * num / den;
+  }
+  float xyz[3] = {0, 0, 0};  // xyY_to_xyz, yocto_color.h:402-405
+  if (xyY[1] != 0) xyz[0] = xyY[0] * xyY[2] / xyY[1], xyz[1] = xyY[2], xyz[2] = (1 - xyY[0] - xyY[1]) * xyY[2] / xyY[1];
+  static const float to_rgb[3][3] = {{+3.2406f, -0.9689f, +0.0557f}, {-1.5372f, +1.8758f, -0.2040f}, {-0.4986f, +0.0415f, +1.0570f}};
+  for (int c = 0; c < 3; c++) rgb[c] = (to_rgb[0][c] * xyz[0] + to_rgb[1][c] * xyz[1] + to_rgb[2][c] * xyz[2]) / 10000;
+}
+void make_sky_texture(HostTexture& tex, int width, int height, float theta_sun, float turbidity, const float (&ground_albedo)[3]) {
+  const float pif = 3.14159265358979323846f, eps = 1.1920928955078125e-07f;
+  auto fmin = [](float a, float b) { return (a < b) ? a : b; };
+  auto fmax = [](float a, float b) { return (a > b) ? a : b; };
+  const SkyModel sky          = make_sky_model(theta_sun, turbidity);
+  const float    sun_dir[3]   = {0, std::cos(theta_sun), std::sin(theta_sun)};
+  tex.width = width, tex.height = height, tex.linear = 1;
+  tex.pixelsf.assign((size_t)width * height * 4, 0.0f);
+  for (int j = 0; j < height / 2; j++) {
+    float theta = pif * ((j + 0.5f) / height);
+    theta       = fmin(fmax(theta, 0.0f), pif / 2 - eps);
+    for (int i = 0; i < width; i++) {
+      const float phi   = 2 * pif * (float(i + 0.5f) / width);
+      const float w[3]  = {std::cos(phi) * std::sin(theta), std::cos(theta), std::sin(phi) * std::sin(theta)};
+      const float gamma = std::acos(fmin(fmax(w[0] * sun_dir[0] + w[1] * sun_dir[1] + w[2] * sun_dir[2], -1.0f), 1.0f));
+      float rgb[3];
+      sky_radiance(sky, theta, gamma, theta_sun, rgb);
+      float* px = &tex.pixelsf[((size_t)j * width + i) * 4];
+      px[0] = rgb[0] + 0.0f, px[1] = rgb[1] + 0.0f, px[2] = rgb[2] + 0.0f, px[3] = 1;  // "+ sun colour", which is zero here
+    }
+  }
+  float ground[3] = {0, 0, 0};
+  if (ground_albedo[0] != 0 || ground_albedo[1] != 0 || ground_albedo[2] != 0) {
+    for (int j = 0; j < height / 2; j++) {
+      const float theta = pif * ((j + 0.5f) / height);
+      for (int i = 0; i < width; i++) {
+        const float* le    = &tex.pixelsf[((size_t)j * width + i) * 4];
+        const float  angle = std::sin(theta) * 4 * pif / (width * height);
+        for (int c = 0; c < 3; c++) ground[c] += le[c] * (ground_albedo[c] / pif) * std::cos(theta) * angle;
+      }
+    }
+  }
+  for (int j = height / 2; j < height; j++)
+    for (int i = 0; i < width; i++) {
+      float* px = &tex.pixelsf[((size_t)j * width + i) * 4];
+      px[0] = ground[0], px[1] = ground[1], px[2] = ground[2], px[3] = 1;
+    }
+}
+
+bool load_ply_scene(const std::string& filename, ygl_loaded_scene& scene, std::string& error) {
+  scene.shape_data.resize(1);
+  if (!load_shape(filename, scene.shape_data[0], error)) return false;
+  ygl_instance inst = {};
+  memcpy(&inst.frame, kIdentityFrame, 48);
+  inst.shape = 0, inst.material = 0;
+  scene.instances.push_back(inst);
+  ygl_material m = {};
+  m.type = 0, m.roughness = 0, m.metallic = 0, m.ior = 1.5f, m.scanisotropy = 0, m.trdepth = 0.01f, m.opacity = 1;
+  m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
+  m.color[0] = m.color[1] = m.color[2] = 0.8f;
+  scene.materials.push_back(m);
+  add_missing_camera(scene);
+  add_missing_radius(scene);
+  // the model's parameters reach it through memory the compiler cannot see through, as they reach the reference's
+  // make_sunsky from another translation unit: libm is called at run time, nothing is folded at build time
+  volatile float sun_angle = 3.14159265358979323846f / 4, turbidity = 3;
+  scene.texture_data.emplace_back();
+  make_sky_texture(scene.texture_data.back(), 1024, 512, sun_angle, turbidity, {0.2f, 0.2f, 0.2f});
+  scene.names[1].push_back("sky");
+  ygl_environment env = {};
+  memcpy(&env.frame, kIdentityFrame, 48);
+  env.emission[0] = env.emission[1] = env.emission[2] = 1;
+  env.emission_tex = 0;
+  scene.environments.push_back(env);
+  scene.names[5].push_back("sky");
+  return true;
+}
+
 void make_desc(ygl_loaded_scene& scene) {
   scene.shapes.clear(), scene.textures.clear();
   for (auto& s : scene.shape_data) {
@@ -1840,7 +1956,13 @@ int ygl_scene_load(const char* filename, ygl_loaded_scene** out) {
   if (!filename || !out) return ygl_internal_set_error("null argument"), YGL_ERR_INVALID;
   auto        scene = std::make_unique<ygl_loaded_scene>();
   std::string error;
-  if (!load_json_scene(filename, *scene, error)) return ygl_internal_set_error(error.c_str()), YGL_ERR_RUNTIME;
+  // load_scene, yocto_sceneio.cpp:2761-2782: the extension picks the format
+  const auto ext = path_extension(filename);
+  bool       ok  = false;
+  if (ext == ".json") ok = load_json_scene(filename, *scene, error);
+  else if (ext == ".ply") ok = load_ply_scene(filename, *scene, error);
+  else error = "unsupported format " + std::string(filename), ok = false;
+  if (!ok) return ygl_internal_set_error(error.c_str()), YGL_ERR_RUNTIME;
   make_desc(*scene);
   *out = scene.release();
   return YGL_OK;
