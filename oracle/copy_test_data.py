@@ -88,6 +88,11 @@ def main(ref, out):
                 if os.path.splitext(f)[0] in mentioned and not f.endswith(".py"):
                     files[group + "/" + f] = pooled(os.path.join(d, f), group, out40)
         json.dump(files, open(os.path.join(out40, "scenes", name + ".files"), "w"), indent=0)
+    # the reference's own renderings of six of these scenes (tests/_renderings, Radiance RGBE): coarse radiometric check
+    os.makedirs(os.path.join(out40, "renderings"), exist_ok=True)
+    for f in sorted(os.listdir(os.path.join(tests, "_renderings"))):
+        if f.endswith("-mst.hdr"):
+            copy(os.path.join(tests, "_renderings", f), os.path.join(out40, "renderings", f))
     for root in (out, out40):
         total = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(root) for f in fs)
         print(f"copy_test_data: {total / 1e6:.1f} MB under {root}")

@@ -233,3 +233,26 @@ def test_ply_file_as_scene_with_procedural_sky(ref, tmp_path):
     assert_scenes_identical(lib.load_scene(tri), ref.load_scene(tri))
     with pytest.raises(lib.YglError):
         lib.load_scene(tmp_path / "scene.gltf")
+
+
+@pytest.mark.parametrize("name", ["features1", "features2", "materials1", "materials2", "materials3"])
+def test_oracle_agrees_with_the_references_published_renderings(ref, name, tmp_path):
+    """The only image-level fixtures the reference ships for this path: tests/_renderings/<scene>-mst.hdr,
+    1280 x 533 RGBE of an unknown sample count, made with a slightly different camera than the scene files hold today
+    (the objects are a few percent larger), so pixels cannot be compared. What can: the mean radiance of the frame, which
+    pins light intensities, the environment and the exposure of the whole pipeline. The oracle (the reference's code,
+    compiled here) renders the scene file our loader read, 4 spp, and must land within 4 % of the published frame.
+    (materials4-mst.hdr is left out: it shows two emissive volumes that today's materials4.json no longer contains.)"""
+    from ygl_b200 import abi
+    golden = os.path.join(scene_data.DATA_V40, "renderings", name + "-mst.hdr")
+    if not os.path.exists(golden):
+        pytest.skip("oracle/_ref/data_v40/renderings not present (run `make -C oracle data`)")
+    os.makedirs(tmp_path / "g" / "textures")
+    os.symlink(golden, tmp_path / "g" / "textures" / "g.hdr")
+    (tmp_path / "g" / "g.json").write_text(json.dumps({"asset": {"version": "4.2"}, "textures": [{"name": "g", "uri": "textures/g.hdr"}]}))
+    published = lib.load_scene(tmp_path / "g" / "g.json").textures[0]["pixels"][..., :3]     # our own RGBE reader
+    scene = lib.load_scene(scene_data.scene_file(name, tmp_path))                                # our own scene reader
+    image = ref.scene(scene).trace_image(abi.trace_params(resolution=1280, samples=4, bounces=8))["image"][..., :3]
+    assert image.shape == published.shape == (533, 1280, 3)
+    ours, theirs = float(np.minimum(image, 10).mean()), float(np.minimum(published, 10).mean())
+    assert abs(ours - theirs) / theirs < 0.04, (ours, theirs)
