@@ -256,3 +256,20 @@ def test_oracle_agrees_with_the_references_published_renderings(ref, name, tmp_p
     assert image.shape == published.shape == (533, 1280, 3)
     ours, theirs = float(np.minimum(image, 10).mean()), float(np.minimum(published, 10).mean())
     assert abs(ours - theirs) / theirs < 0.04, (ours, theirs)
+
+
+def test_reference_side_load_scene_shim(tmp_path):
+    """The C++ drop-in for `yocto::load_scene` (yocto::b200::load_scene, yocto-gl_b200/host/yocto_b200trace.h) in a
+    reference-side program (oracle/shim_load_demo.cpp) next to the reference's own loader + tesselate_subdivs: the two
+    scene_data objects - every array, every name - must be identical. Format 4.2 with subdivs, format 4.0, a .ply scene."""
+    import subprocess
+    exe = os.path.join(scene_data.ROOT, "oracle", "_ref", "shim_load_demo")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shim_load_demo not built (needs the reference headers)")
+    files = [scene_data.scene_file(name, tmp_path) for name in ("features2", "materials3", "shapes1")]
+    if scene_data.names_v40():
+        files += [scene_data.scene_file(name, tmp_path / "v40", scene_data.DATA_V40) for name in ("shapes2", "instances1")]
+    files.append(scene_data.pool("shapes", "bunny.ply"))
+    res = subprocess.run([exe] + [str(f) for f in files], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert res.stdout.count("identical") == len(files), res.stdout[-2000:]

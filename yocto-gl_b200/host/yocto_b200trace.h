@@ -9,7 +9,8 @@
 //
 //   yocto::trace_image(scene, params)            ->  yocto::b200::trace_image(scene, params)
 //   make_trace_bvh / update_trace_bvh / make_trace_lights / make_trace_state / trace_samples / trace_sample / get_image /
-//   get_albedo_image / get_normal_image / trace_start / trace_cancel / trace_done / trace_preview likewise.
+//   get_albedo_image / get_normal_image / trace_start / trace_cancel / trace_done / trace_preview likewise;
+//   yocto::load_scene(filename)                  ->  yocto::b200::load_scene(filename)  (+ tesselate_subdivs)
 //
 // Errors of the C ABI come back as the exceptions the reference uses (yocto_trace.cpp:1437,
 // :1679-1691): YGL_ERR_INVALID -> std::invalid_argument, everything else -> std::runtime_error.
@@ -22,6 +23,7 @@
 
 #include <memory>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "../../include/ygl_b200.h"
@@ -268,6 +270,77 @@ inline image_data trace_image(const scene_data& scene, const trace_params& param
   auto image = make_image(w, h, true);
   check(ygl_trace_image(ctx.handle, &views.desc, &abi, &w, &h, (float*)image.pixels.data()));
   return image;
+}
+
+// load_scene (yocto_sceneio.h:93-96): the library's own reader (JSON 4.0 / 4.2 / 5.0, .ply scenes, PLY / OBJ shapes,
+// PNG / HDR textures) filling the reference's scene_data. Subdivs arrive tesselated (scene.subdivs stays empty), which is
+// the state every reference app reaches with tesselate_subdivs right after load_scene (apps/ytrace.cpp:110-113).
+inline bool load_scene(const std::string& filename, scene_data& scene, std::string& error) {
+  ygl_loaded_scene* loaded = nullptr;
+  if (ygl_scene_load(filename.c_str(), &loaded) != YGL_OK) {
+    error = ygl_last_error();
+    return false;
+  }
+  auto guard = std::unique_ptr<ygl_loaded_scene, void (*)(ygl_loaded_scene*)>{loaded, ygl_loaded_scene_destroy};
+  auto desc  = ygl_loaded_scene_desc(loaded);
+  auto frame = [](const ygl_frame3f& f) { return *(const frame3f*)&f; };
+  static_assert(sizeof(ygl_frame3f) == sizeof(frame3f), "frame layout");
+  scene = scene_data{};
+  for (auto k = 0; k < desc->num_cameras; k++) {
+    auto& c = desc->cameras[k];
+    auto& camera = scene.cameras.emplace_back();
+    camera.frame = frame(c.frame), camera.orthographic = c.orthographic != 0, camera.lens = c.lens, camera.film = c.film;
+    camera.aspect = c.aspect, camera.focus = c.focus, camera.aperture = c.aperture;
+  }
+  for (auto k = 0; k < desc->num_instances; k++)
+    scene.instances.push_back({frame(desc->instances[k].frame), desc->instances[k].shape, desc->instances[k].material});
+  for (auto k = 0; k < desc->num_environments; k++) {
+    auto& e = desc->environments[k];
+    scene.environments.push_back({frame(e.frame), {e.emission[0], e.emission[1], e.emission[2]}, e.emission_tex});
+  }
+  for (auto k = 0; k < desc->num_materials; k++) {
+    auto& m        = desc->materials[k];
+    auto& material = scene.materials.emplace_back();
+    material.type = (material_type)m.type, material.emission = {m.emission[0], m.emission[1], m.emission[2]};
+    material.color = {m.color[0], m.color[1], m.color[2]}, material.roughness = m.roughness, material.metallic = m.metallic;
+    material.ior = m.ior, material.scattering = {m.scattering[0], m.scattering[1], m.scattering[2]};
+    material.scanisotropy = m.scanisotropy, material.trdepth = m.trdepth, material.opacity = m.opacity;
+    material.emission_tex = m.emission_tex, material.color_tex = m.color_tex, material.roughness_tex = m.roughness_tex;
+    material.scattering_tex = m.scattering_tex, material.normal_tex = m.normal_tex;
+  }
+  for (auto k = 0; k < desc->num_textures; k++) {
+    auto& t       = desc->textures[k];
+    auto& texture = scene.textures.emplace_back();
+    texture.width = t.width, texture.height = t.height, texture.linear = t.linear != 0, texture.nearest = t.nearest != 0;
+    texture.clamp = t.clamp != 0;
+    auto count    = (size_t)t.width * (size_t)t.height;
+    if (t.pixelsf) texture.pixelsf.assign((const vec4f*)t.pixelsf, (const vec4f*)t.pixelsf + count);
+    if (t.pixelsb) texture.pixelsb.assign((const vec4b*)t.pixelsb, (const vec4b*)t.pixelsb + count);
+  }
+  for (auto k = 0; k < desc->num_shapes; k++) {
+    auto& s     = desc->shapes[k];
+    auto& shape = scene.shapes.emplace_back();
+    shape.points.assign(s.points, s.points + s.num_points);
+    shape.lines.assign((const vec2i*)s.lines, (const vec2i*)s.lines + s.num_lines);
+    shape.triangles.assign((const vec3i*)s.triangles, (const vec3i*)s.triangles + s.num_triangles);
+    shape.quads.assign((const vec4i*)s.quads, (const vec4i*)s.quads + s.num_quads);
+    shape.positions.assign((const vec3f*)s.positions, (const vec3f*)s.positions + s.num_positions);
+    shape.normals.assign((const vec3f*)s.normals, (const vec3f*)s.normals + s.num_normals);
+    shape.texcoords.assign((const vec2f*)s.texcoords, (const vec2f*)s.texcoords + s.num_texcoords);
+    shape.colors.assign((const vec4f*)s.colors, (const vec4f*)s.colors + s.num_colors);
+    shape.radius.assign(s.radius, s.radius + s.num_radius);
+  }
+  std::vector<std::string>* names[6] = {&scene.camera_names, &scene.texture_names, &scene.material_names, &scene.shape_names,
+      &scene.instance_names, &scene.environment_names};
+  for (auto kind = 0; kind < 6; kind++)
+    for (auto k = 0; auto name = ygl_loaded_scene_name(loaded, kind, k); k++) names[kind]->push_back(name);
+  return true;
+}
+inline scene_data load_scene(const std::string& filename) {
+  auto scene = scene_data{};
+  auto error = std::string{};
+  if (!b200::load_scene(filename, scene, error)) throw std::runtime_error{error};
+  return scene;
 }
 
 }  // namespace yocto::b200
