@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -61,12 +62,20 @@ std::string path_extension(const std::string& path) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// JSON: a small document model (objects keep insertion order; numbers are doubles, like nlohmann's number_float_t)
+// JSON: a small document model with the acceptance rules and number model of nlohmann::ordered_json, the reference's
+// parser: objects keep insertion order and a repeated key overwrites the first one's value in place; a number without
+// fraction or exponent is an integer (int64 if negative, uint64 otherwise - so "-0" is +0 - and a double only when it
+// fits neither), everything else a double that must be finite; strict number grammar (no "+1", ".5", "1.", "01", "inf");
+// strings must be well-formed UTF-8 without raw control characters, \u escapes pair up surrogates; one optional BOM.
 // ---------------------------------------------------------------------------------------------------------------
 struct JValue {
   enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+  enum NumberKind : uint8_t { Float, Signed, Unsigned };
   bool                                           boolean = false;
-  double                                         number  = 0;
+  NumberKind                                     kind    = Float;
+  double                                         number  = 0;  // Float
+  int64_t                                        inumber = 0;  // Signed
+  uint64_t                                       unumber = 0;  // Unsigned
   std::string                                    string;
   std::vector<JValue>                            array;
   std::vector<std::pair<std::string, JValue>>    object;
@@ -76,6 +85,9 @@ struct JValue {
       if (kv.first == key) return &kv.second;
     return nullptr;
   }
+  // static_cast<T>(stored value), what nlohmann's get<T>() does for a number
+  float as_float() const { return kind == Float ? (float)number : kind == Signed ? (float)inumber : (float)unumber; }
+  int   as_int() const { return kind == Float ? (int)number : kind == Signed ? (int)inumber : (int)unumber; }
 };
 
 struct JParser {
@@ -86,11 +98,34 @@ struct JParser {
     while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) p++;
   }
   bool fail() { return ok = false; }
+  static void append_utf8(std::string& out, unsigned cp) {
+    if (cp < 0x80) out += (char)cp;
+    else if (cp < 0x800) out += (char)(0xC0 | (cp >> 6)), out += (char)(0x80 | (cp & 0x3F));
+    else if (cp < 0x10000) out += (char)(0xE0 | (cp >> 12)), out += (char)(0x80 | ((cp >> 6) & 0x3F)), out += (char)(0x80 | (cp & 0x3F));
+    else
+      out += (char)(0xF0 | (cp >> 18)), out += (char)(0x80 | ((cp >> 12) & 0x3F)), out += (char)(0x80 | ((cp >> 6) & 0x3F)),
+          out += (char)(0x80 | (cp & 0x3F));
+  }
+  bool hex4(unsigned& cp) {  // p at the 'u'
+    if (end - p < 5) return false;
+    cp = 0;
+    for (int k = 1; k <= 4; k++) {
+      const char c = p[k];
+      cp <<= 4;
+      if (c >= '0' && c <= '9') cp |= (unsigned)(c - '0');
+      else if (c >= 'a' && c <= 'f') cp |= (unsigned)(c - 'a' + 10);
+      else if (c >= 'A' && c <= 'F') cp |= (unsigned)(c - 'A' + 10);
+      else return false;
+    }
+    p += 4;
+    return true;
+  }
   bool parse_string(std::string& out) {
     if (p >= end || *p != '"') return fail();
     p++;
     while (p < end && *p != '"') {
-      if (*p == '\\') {
+      const unsigned char c = (unsigned char)*p;
+      if (c == '\\') {
         if (++p >= end) return fail();
         switch (*p) {
           case '"': out += '"'; break;
@@ -102,26 +137,99 @@ struct JParser {
           case 'r': out += '\r'; break;
           case 't': out += '\t'; break;
           case 'u': {
-            if (end - p < 5) return fail();
-            unsigned cp = (unsigned)strtoul(std::string(p + 1, p + 5).c_str(), nullptr, 16);
-            p += 4;
-            if (cp < 0x80) out += (char)cp;
-            else if (cp < 0x800) out += (char)(0xC0 | (cp >> 6)), out += (char)(0x80 | (cp & 0x3F));
-            else out += (char)(0xE0 | (cp >> 12)), out += (char)(0x80 | ((cp >> 6) & 0x3F)), out += (char)(0x80 | (cp & 0x3F));
+            unsigned cp = 0;
+            if (!hex4(cp)) return fail();
+            if (cp >= 0xD800 && cp <= 0xDBFF) {  // a high surrogate needs its low half right behind
+              unsigned low = 0;
+              if (end - p < 3 || p[1] != '\\' || p[2] != 'u') return fail();
+              p += 2;
+              if (!hex4(low) || low < 0xDC00 || low > 0xDFFF) return fail();
+              cp = 0x10000 + ((cp - 0xD800) << 10) + (low - 0xDC00);
+            } else if (cp >= 0xDC00 && cp <= 0xDFFF) {
+              return fail();
+            }
+            append_utf8(out, cp);
           } break;
           default: return fail();
         }
         p++;
-      } else {
+      } else if (c < 0x20) {
+        return fail();
+      } else if (c < 0x80) {
         out += *p++;
+      } else {  // one well-formed UTF-8 sequence (Unicode table 3-7)
+        int      more = 0;
+        unsigned lo = 0x80, hi = 0xBF;
+        if (c >= 0xC2 && c <= 0xDF) more = 1;
+        else if (c == 0xE0) more = 2, lo = 0xA0;
+        else if ((c >= 0xE1 && c <= 0xEC) || c == 0xEE || c == 0xEF) more = 2;
+        else if (c == 0xED) more = 2, hi = 0x9F;
+        else if (c == 0xF0) more = 3, lo = 0x90;
+        else if (c >= 0xF1 && c <= 0xF3) more = 3;
+        else if (c == 0xF4) more = 3, hi = 0x8F;
+        else return fail();
+        if (end - p <= more) return fail();
+        for (int k = 1; k <= more; k++) {
+          const unsigned char t = (unsigned char)p[k];
+          if (t < lo || t > hi) return fail();
+          lo = 0x80, hi = 0xBF;
+        }
+        out.append(p, (size_t)more + 1);
+        p += more + 1;
       }
     }
     if (p >= end) return fail();
     p++;
     return true;
   }
+  bool parse_number(JValue& v) {
+    const char* start = p;
+    const char* q     = p;
+    auto digit = [&](const char* c) { return c < end && *c >= '0' && *c <= '9'; };
+    if (q < end && *q == '-') q++;
+    if (!digit(q)) return fail();
+    if (*q == '0') q++;
+    else
+      while (digit(q)) q++;
+    bool integer = true;
+    if (q < end && *q == '.') {
+      integer = false;
+      if (!digit(++q)) return fail();
+      while (digit(q)) q++;
+    }
+    if (q < end && (*q == 'e' || *q == 'E')) {
+      integer = false;
+      q++;
+      if (q < end && (*q == '+' || *q == '-')) q++;
+      if (!digit(q)) return fail();
+      while (digit(q)) q++;
+    }
+    const std::string token(start, q);
+    v.type = JValue::Number, v.kind = JValue::Float;
+    p      = q;
+    if (integer) {
+      errno = 0;
+      char* stop = nullptr;
+      if (token[0] == '-') {
+        const long long x = strtoll(token.c_str(), &stop, 10);
+        if (errno == 0) return v.kind = JValue::Signed, v.inumber = x, true;
+      } else {
+        const unsigned long long x = strtoull(token.c_str(), &stop, 10);
+        if (errno == 0) return v.kind = JValue::Unsigned, v.unumber = x, true;
+      }
+    }
+    v.number = strtod(token.c_str(), nullptr);
+    if (!std::isfinite(v.number)) return fail();  // "number overflow parsing"
+    return true;
+  }
+  bool parse_document(JValue& v) {
+    if (end - p >= 3 && (unsigned char)p[0] == 0xEF && (unsigned char)p[1] == 0xBB && (unsigned char)p[2] == 0xBF) p += 3;
+    if (!parse(v)) return false;
+    skip();
+    return p == end ? true : fail();
+  }
   bool parse(JValue& v, int depth = 0) {
-    if (depth > 64) return fail();
+    if (depth > 256) return fail();
     skip();
     if (p >= end) return fail();
     if (*p == '{') {
@@ -129,6 +237,7 @@ struct JParser {
       p++;
       skip();
       if (p < end && *p == '}') return p++, true;
+      std::unordered_map<std::string, size_t> index;  // only kept up once the object is large
       while (true) {
         skip();
         std::string key;
@@ -136,8 +245,24 @@ struct JParser {
         skip();
         if (p >= end || *p != ':') return fail();
         p++;
-        v.object.emplace_back(std::move(key), JValue{});
-        if (!parse(v.object.back().second, depth + 1)) return false;
+        size_t slot = v.object.size();
+        if (v.object.size() < 32) {
+          for (size_t k = 0; k < v.object.size(); k++)
+            if (v.object[k].first == key) slot = k;
+        } else {
+          if (index.empty())
+            for (size_t k = 0; k < v.object.size(); k++) index.emplace(v.object[k].first, k);
+          auto it = index.find(key);
+          if (it != index.end()) slot = it->second;
+          else index.emplace(key, slot);
+        }
+        if (slot == v.object.size()) v.object.emplace_back(std::move(key), JValue{});
+        else v.object[slot].second = JValue{};
+        {
+          JValue value;  // parsed aside: the vector may not grow under a reference into it
+          if (!parse(value, depth + 1)) return false;
+          v.object[slot].second = std::move(value);
+        }
         skip();
         if (p < end && *p == ',') {
           p++;
@@ -171,12 +296,7 @@ struct JParser {
     if (end - p >= 4 && !strncmp(p, "true", 4)) return v.type = JValue::Bool, v.boolean = true, p += 4, true;
     if (end - p >= 5 && !strncmp(p, "false", 5)) return v.type = JValue::Bool, v.boolean = false, p += 5, true;
     if (end - p >= 4 && !strncmp(p, "null", 4)) return v.type = JValue::Null, p += 4, true;
-    char* stop = nullptr;
-    v.number   = strtod(p, &stop);  // the buffer is NUL-terminated by the caller
-    if (stop == p) return fail();
-    v.type = JValue::Number;
-    p      = stop;
-    return true;
+    return parse_number(v);
   }
 };
 
@@ -188,14 +308,14 @@ struct JReader {
     if (auto v = e.find(key)) {
       if (v->type == JValue::Bool) value = v->boolean ? 1.0f : 0.0f;
       else if (v->type != JValue::Number) ok = false;
-      else value = (float)v->number;
+      else value = v->as_float();
     }
   }
   void get(const JValue& e, const char* key, int& value) {
     if (auto v = e.find(key)) {
       if (v->type == JValue::Bool) value = v->boolean ? 1 : 0;
       else if (v->type != JValue::Number) ok = false;
-      else value = (int)v->number;
+      else value = v->as_int();
     }
   }
   void get_bool(const JValue& e, const char* key, int& value) {
@@ -217,7 +337,7 @@ struct JReader {
       for (size_t i = 0; i < n; i++) {
         if (v->array[i].type == JValue::Bool) value[i] = v->array[i].boolean ? 1.0f : 0.0f;
         else if (v->array[i].type != JValue::Number) return void(ok = false);
-        else value[i] = (float)v->array[i].number;
+        else value[i] = v->array[i].as_float();
       }
     }
   }
@@ -1332,9 +1452,7 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
   JValue  json;
   JParser parser{(const char*)text.data(), (const char*)text.data() + text.size() - 1};
   auto    parse_error = [&]() { return error = "cannot parse " + filename, false; };
-  if (!parser.parse(json)) return parse_error();
-  parser.skip();
-  if (parser.p != parser.end) return parse_error();
+  if (!parser.parse_document(json)) return parse_error();
 
   JReader      rd;
   SceneParts   parts;
@@ -1356,10 +1474,27 @@ bool load_json_scene(const std::string& filename, ygl_loaded_scene& scene, std::
 }
 
 bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, SceneParts& parts, JReader& rd) {
+  // `for (auto& element : group)` of nlohmann: the elements of an array, the values of an object, nothing for null, the
+  // value itself otherwise; get_opt on anything but an object throws - a parse error
+  auto elements = [&](const char* name) {
+    std::vector<const JValue*> out;
+    auto group = json.find(name);
+    if (!group || group->type == JValue::Null) return out;
+    if (group->type == JValue::Array)
+      for (auto& e : group->array) out.push_back(&e);
+    else if (group->type == JValue::Object)
+      for (auto& kv : group->object) out.push_back(&kv.second);
+    else rd.ok = false;
+    for (auto e : out)
+      if (e->type != JValue::Object) rd.ok = false;
+    if (!rd.ok) out.clear();
+    return out;
+  };
   auto& shape_files = parts.shape_files;
   auto& texture_files = parts.texture_files;
-  if (auto group = json.find("cameras")) {
-    for (auto& e : group->array) {
+  {
+    for (auto ep : elements("cameras")) {
+      auto& e = *ep;
       ygl_camera camera = {};
       memcpy(&camera.frame, kIdentityFrame, 48);
       camera.orthographic = 0, camera.lens = 0.050f, camera.film = 0.036f, camera.aspect = 1.500f, camera.focus = 10000,
@@ -1384,8 +1519,9 @@ bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, ScenePart
       scene.names[0].push_back(name);
     }
   }
-  if (auto group = json.find("textures")) {
-    for (auto& e : group->array) {
+  {
+    for (auto ep : elements("textures")) {
+      auto& e = *ep;
       HostTexture tex;
       std::string name, uri;
       rd.get(e, "name", name);
@@ -1398,8 +1534,9 @@ bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, ScenePart
       texture_files.push_back(uri);
     }
   }
-  if (auto group = json.find("materials")) {
-    for (auto& e : group->array) {
+  {
+    for (auto ep : elements("materials")) {
+      auto& e = *ep;
       ygl_material m = {};
       m.type = 0, m.roughness = 0, m.metallic = 0, m.ior = 1.5f, m.scanisotropy = 0, m.trdepth = 0.01f, m.opacity = 1;
       m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
@@ -1425,8 +1562,9 @@ bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, ScenePart
       scene.names[2].push_back(name);
     }
   }
-  if (auto group = json.find("shapes")) {
-    for (auto& e : group->array) {
+  {
+    for (auto ep : elements("shapes")) {
+      auto& e = *ep;
       std::string name, uri;
       rd.get(e, "name", name);
       rd.get(e, "uri", uri);
@@ -1436,8 +1574,9 @@ bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, ScenePart
   }
   auto& subdivs      = parts.subdivs;
   auto& subdiv_files = parts.subdiv_files;
-  if (auto group = json.find("subdivs")) {
-    for (auto& e : group->array) {
+  {
+    for (auto ep : elements("subdivs")) {
+      auto& e = *ep;
       HostSubdiv  subdiv;
       std::string name, uri;
       rd.get(e, "name", name);
@@ -1452,8 +1591,9 @@ bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, ScenePart
       subdiv_files.push_back(uri);
     }
   }
-  if (auto group = json.find("instances")) {
-    for (auto& e : group->array) {
+  {
+    for (auto ep : elements("instances")) {
+      auto& e = *ep;
       ygl_instance inst = {};
       memcpy(&inst.frame, kIdentityFrame, 48);
       inst.shape = inst.material = -1;
@@ -1471,8 +1611,9 @@ bool parse_json_scene_v42(const JValue& json, ygl_loaded_scene& scene, ScenePart
       scene.names[4].push_back(name);
     }
   }
-  if (auto group = json.find("environments")) {
-    for (auto& e : group->array) {
+  {
+    for (auto ep : elements("environments")) {
+      auto& e = *ep;
       ygl_environment env = {};
       memcpy(&env.frame, kIdentityFrame, 48);
       env.emission_tex = -1;
