@@ -733,54 +733,30 @@ bool load_hdr(const std::vector<uint8_t>& data, HostTexture& tex) {
   return true;
 }
 
-// PNG -> byte rgba as stbi_load(..., 4) returns it: 8- or 16-bit samples (16 -> high byte), grey / grey+alpha /
-// rgb / rgba / palette, tRNS transparency, non-interlaced.
-bool load_png(const std::vector<uint8_t>& data, HostTexture& tex) {
-  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-  if (data.size() < 8 || memcmp(data.data(), sig, 8)) return false;
-  auto   be32 = [&](size_t o) { return (uint32_t)data[o] << 24 | (uint32_t)data[o + 1] << 16 | (uint32_t)data[o + 2] << 8 | data[o + 3]; };
-  size_t pos = 8;
-  int    w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
-  std::vector<uint8_t> idat, palette, trns;
-  while (pos + 12 <= data.size()) {
-    const uint32_t len = be32(pos);
-    const char*    id  = (const char*)&data[pos + 4];
-    if (pos + 12 + (size_t)len > data.size()) return false;
-    const uint8_t* body = &data[pos + 8];
-    if (!memcmp(id, "IHDR", 4)) {
-      if (len < 13) return false;
-      w = (int)be32(pos + 8), h = (int)be32(pos + 12);
-      depth = body[8], ctype = body[9], interlace = body[12];
-    } else if (!memcmp(id, "PLTE", 4)) {
-      palette.assign(body, body + len);
-    } else if (!memcmp(id, "tRNS", 4)) {
-      trns.assign(body, body + len);
-    } else if (!memcmp(id, "IDAT", 4)) {
-      idat.insert(idat.end(), body, body + len);
-    } else if (!memcmp(id, "IEND", 4)) {
-      break;
-    }
-    pos += 12 + (size_t)len;
-  }
-  if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16)) return false;
-  const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-  if (!channels || (ctype == 3 && depth != 8)) return false;
-  const size_t bpp = (size_t)channels * depth / 8, stride = bpp * w;
-  std::vector<uint8_t> raw((stride + 1) * h);
-  uLongf rawlen = (uLongf)raw.size();
-  if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) return false;
-  // undo the scanline filters (PNG spec section 9)
+// PNG -> byte rgba as stbi_load(..., 4) returns it (stb_image.h, stbi__parse_png_file / stbi__create_png_image): 1 / 2 /
+// 4 / 8 / 16-bit samples (sub-byte grey scaled to 0..255, 16 -> high byte), grey / grey+alpha / rgb / rgba / palette,
+// tRNS transparency (a colour key, or per-entry alpha of a palette whose missing entries read as transparent black),
+// Adam7 interlacing, and stb's acceptance rules for chunk sizes.
+struct PngLayout {
+  int w = 0, h = 0, depth = 0, ctype = 0, channels = 0;
+};
+// one (sub)image: `raw` holds h filtered scanlines of w pixels; the result has one byte per sample for depths <= 8
+// (sub-byte samples unpacked, not yet scaled) and two for depth 16
+bool png_unfilter(const uint8_t* raw, size_t raw_size, int w, int h, const PngLayout& png, std::vector<uint8_t>& out) {
+  const size_t bpp    = std::max<size_t>(1, (size_t)png.channels * png.depth / 8);  // filter distance in bytes
+  const size_t stride = ((size_t)png.channels * w * png.depth + 7) / 8;
+  if (raw_size < (stride + 1) * h) return false;
   std::vector<uint8_t> img(stride * h);
   for (int j = 0; j < h; j++) {
     const uint8_t  filter = raw[(stride + 1) * j];
     const uint8_t* src    = &raw[(stride + 1) * j + 1];
     uint8_t*       dst    = &img[stride * j];
     const uint8_t* up     = j ? dst - stride : nullptr;
-    for (size_t i = 0; i < stride; i++) {
+    if (filter > 4) return false;
+    for (size_t i = 0; i < stride; i++) {  // PNG specification, section 9
       const int a = i >= bpp ? dst[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
       int       v = src[i];
       switch (filter) {
-        case 0: break;
         case 1: v += a; break;
         case 2: v += b; break;
         case 3: v += (a + b) >> 1; break;
@@ -788,37 +764,145 @@ bool load_png(const std::vector<uint8_t>& data, HostTexture& tex) {
           const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
           v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
         } break;
-        default: return false;
+        default: break;
       }
       dst[i] = (uint8_t)v;
     }
   }
+  if (png.depth >= 8) return out = std::move(img), true;
+  out.resize((size_t)w * h);  // one channel: unpack the most significant bits first
+  const int mask = (1 << png.depth) - 1;
+  for (int j = 0; j < h; j++)
+    for (int i = 0; i < w; i++) {
+      const size_t bit = (size_t)i * png.depth;
+      out[(size_t)j * w + i] = (uint8_t)((img[stride * j + bit / 8] >> (8 - png.depth - bit % 8)) & mask);
+    }
+  return true;
+}
+bool load_png(const std::vector<uint8_t>& data, HostTexture& tex) {
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  if (data.size() < 8 || memcmp(data.data(), sig, 8)) return false;
+  auto   be32 = [&](size_t o) { return (uint32_t)data[o] << 24 | (uint32_t)data[o + 1] << 16 | (uint32_t)data[o + 2] << 8 | data[o + 3]; };
+  size_t pos = 8;
+  PngLayout png;
+  int       interlace = 0;
+  bool      first = true, have_trns = false, ended = false;
+  uint8_t   palette[256][4] = {};  // entries a PLTE chunk does not fill read as 0, 0, 0, 0 (stb: uninitialised memory)
+  int       palette_len = 0;
+  uint8_t   key8[3]  = {};         // colour key of an 8-bit image (already scaled like the samples)
+  uint16_t  key16[3] = {};
+  std::vector<uint8_t> idat;
+  while (!ended) {
+    if (pos + 8 > data.size()) return false;
+    const uint32_t len = be32(pos);
+    const char*    id  = (const char*)&data[pos + 4];
+    if (pos + 12 + (size_t)len > data.size()) {
+      if (memcmp(id, "IEND", 4) || pos + 8 + (size_t)len > data.size()) return false;  // stb never reads IEND's checksum
+    }
+    const uint8_t* body = &data[pos + 8];
+    if (first && memcmp(id, "IHDR", 4)) return false;
+    if (!memcmp(id, "IHDR", 4)) {
+      if (!first || len != 13) return false;
+      png.w = (int)be32(pos + 8), png.h = (int)be32(pos + 12);
+      png.depth = body[8], png.ctype = body[9], interlace = body[12];
+      if (be32(pos + 8) > (1u << 24) || be32(pos + 12) > (1u << 24) || png.w == 0 || png.h == 0) return false;
+      if (png.depth != 1 && png.depth != 2 && png.depth != 4 && png.depth != 8 && png.depth != 16) return false;
+      if (png.ctype > 6 || (png.ctype == 3 && png.depth == 16) || (png.ctype != 3 && (png.ctype & 1))) return false;
+      if (body[10] != 0 || body[11] != 0 || interlace > 1) return false;
+      png.channels = png.ctype == 3 ? 1 : ((png.ctype & 2) ? 3 : 1) + ((png.ctype & 4) ? 1 : 0);
+    } else if (!memcmp(id, "PLTE", 4)) {
+      if (len > 256 * 3 || len % 3 != 0) return false;
+      palette_len = (int)len / 3;
+      for (int k = 0; k < palette_len; k++)
+        palette[k][0] = body[3 * k], palette[k][1] = body[3 * k + 1], palette[k][2] = body[3 * k + 2], palette[k][3] = 255;
+    } else if (!memcmp(id, "tRNS", 4)) {
+      if (!idat.empty()) return false;
+      if (png.ctype == 3) {
+        if (palette_len == 0 || (int)len > palette_len) return false;
+        for (uint32_t k = 0; k < len; k++) palette[k][3] = body[k];
+      } else {
+        if (!(png.channels & 1) || len != (uint32_t)png.channels * 2) return false;
+        static const uint8_t scale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+        for (int k = 0; k < png.channels; k++) {
+          key16[k] = (uint16_t)(body[2 * k] << 8 | body[2 * k + 1]);
+          if (png.depth < 16) key8[k] = (uint8_t)((key16[k] & 255) * scale[png.depth]);
+        }
+        have_trns = true;
+      }
+    } else if (!memcmp(id, "IDAT", 4)) {
+      if (png.ctype == 3 && palette_len == 0) return false;
+      idat.insert(idat.end(), body, body + len);
+    } else if (!memcmp(id, "IEND", 4)) {
+      ended = true;
+    } else if (!(id[0] & 32)) {
+      return false;  // an unknown critical chunk
+    }
+    first = false;
+    pos += 12 + (size_t)len;
+  }
+  if (idat.empty()) return false;
+  const int w = png.w, h = png.h;
+  // inflate everything; interlaced images are seven sub-images one after the other
+  const size_t bytes_per_sample = png.depth == 16 ? 2 : 1;
+  const size_t bpp_out          = (size_t)png.channels * bytes_per_sample;
+  size_t       expected         = 0;
+  static const int xorig[7] = {0, 4, 0, 2, 0, 1, 0}, yorig[7] = {0, 0, 4, 0, 2, 0, 1};
+  static const int xspc[7] = {8, 8, 4, 4, 2, 2, 1}, yspc[7] = {8, 8, 8, 4, 4, 2, 2};
+  auto raw_size = [&](int pw, int ph) { return (((size_t)png.channels * pw * png.depth + 7) / 8 + 1) * ph; };
+  if (!interlace) {
+    expected = raw_size(w, h);
+  } else {
+    for (int p = 0; p < 7; p++) {
+      const int pw = (w - xorig[p] + xspc[p] - 1) / xspc[p], ph = (h - yorig[p] + yspc[p] - 1) / yspc[p];
+      if (pw > 0 && ph > 0) expected += raw_size(pw, ph);
+    }
+  }
+  std::vector<uint8_t> raw(expected);
+  uLongf rawlen = (uLongf)raw.size();
+  if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) return false;
+  std::vector<uint8_t> img((size_t)w * h * bpp_out);
+  if (!interlace) {
+    if (!png_unfilter(raw.data(), raw.size(), w, h, png, img)) return false;
+  } else {
+    size_t offset = 0;
+    for (int p = 0; p < 7; p++) {
+      const int pw = (w - xorig[p] + xspc[p] - 1) / xspc[p], ph = (h - yorig[p] + yspc[p] - 1) / yspc[p];
+      if (pw <= 0 || ph <= 0) continue;
+      std::vector<uint8_t> part;
+      if (!png_unfilter(raw.data() + offset, raw.size() - offset, pw, ph, png, part)) return false;
+      for (int j = 0; j < ph; j++)
+        for (int i = 0; i < pw; i++)
+          memcpy(&img[((size_t)(j * yspc[p] + yorig[p]) * w + (size_t)i * xspc[p] + xorig[p]) * bpp_out],
+              &part[((size_t)j * pw + i) * bpp_out], bpp_out);
+      offset += raw_size(pw, ph);
+    }
+  }
+  if (png.depth < 8 && png.ctype == 0) {  // sub-byte grey spreads over 0..255
+    static const uint8_t scale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+    for (auto& v : img) v = (uint8_t)(v * scale[png.depth]);
+  }
   tex.width = w, tex.height = h;
   tex.pixelsb.resize((size_t)w * h * 4);
-  const size_t step = depth / 8;  // 16-bit samples are big-endian: the first byte is the high byte stb keeps
+  const bool   wide = png.depth == 16;
+  const size_t step = bytes_per_sample;  // 16-bit samples are big-endian: the first byte is the high byte stb keeps
   for (size_t i = 0; i < (size_t)w * h; i++) {
-    const uint8_t* s = &img[i * bpp];
+    const uint8_t* s = &img[i * bpp_out];
     uint8_t*       d = &tex.pixelsb[4 * i];
-    switch (ctype) {
+    auto sample16 = [&](int k) { return (uint16_t)(s[2 * k] << 8 | s[2 * k + 1]); };
+    switch (png.ctype) {
       case 0: {
         d[0] = d[1] = d[2] = s[0], d[3] = 255;
-        if (trns.size() >= 2 && ((depth == 16) ? (s[0] == trns[0] && s[1] == trns[1]) : s[0] == trns[1])) d[3] = 0;
+        if (have_trns && (wide ? sample16(0) == key16[0] : s[0] == key8[0])) d[3] = 0;
       } break;
       case 2: {
         d[0] = s[0], d[1] = s[step], d[2] = s[2 * step], d[3] = 255;
-        if (trns.size() >= 6) {
+        if (have_trns) {
           bool key = true;
-          for (int k = 0; k < 3; k++)
-            key = key && (depth == 16 ? (s[2 * k] == trns[2 * k] && s[2 * k + 1] == trns[2 * k + 1]) : s[k] == trns[2 * k + 1]);
+          for (int k = 0; k < 3; k++) key = key && (wide ? sample16(k) == key16[k] : s[k] == key8[k]);
           if (key) d[3] = 0;
         }
       } break;
-      case 3: {
-        const size_t k = s[0];
-        if (3 * k + 2 >= palette.size()) return false;
-        d[0] = palette[3 * k], d[1] = palette[3 * k + 1], d[2] = palette[3 * k + 2];
-        d[3] = k < trns.size() ? trns[k] : 255;
-      } break;
+      case 3: memcpy(d, palette[s[0]], 4); break;
       case 4: d[0] = d[1] = d[2] = s[0], d[3] = s[step]; break;
       case 6: d[0] = s[0], d[1] = s[step], d[2] = s[2 * step], d[3] = s[3 * step]; break;
     }
