@@ -1,0 +1,211 @@
+"""Differential tests of the shape readers (PLY and OBJ in ygl_sceneio.cpp) against the reference's load_shape
+(yocto_sceneio.cpp:1008-1051 over yocto_modelio's load_ply / load_obj): seeded random files - PLY in ascii and both binary
+byte orders, properties of every scalar type in any order, list properties with any count / index type, extra elements and
+properties, polygons of 0..7 corners, polylines, points, radius / colour / texcoord variants; OBJ with shared and split
+vertices, negative indices, missing components, polygons, lines and points, comments - must load to bit-identical arrays
+(or be refused by both). Host-only; every file is read in a forked child so that a crash of the reference is survived."""
+import json
+import os
+import random
+import struct
+
+import pytest
+
+from ygl_b200 import lib
+from test_sceneio import assert_scenes_identical
+
+SCALARS = {"char": "b", "uchar": "B", "short": "h", "ushort": "H", "int": "i", "uint": "I", "float": "f", "double": "d",
+           "int8": "b", "uint8": "B", "int16": "h", "uint16": "H", "int32": "i", "uint32": "I", "float32": "f", "float64": "d"}
+
+
+def make_ply(rng):
+    fmt = rng.choice(["ascii", "binary_little_endian", "binary_big_endian"])
+    nverts = rng.randint(3, 12)
+    groups = [["x", "y", "z"]]
+    for extra in (["nx", "ny", "nz"], rng.choice([["u", "v"], ["s", "t"]]), rng.choice([["red", "green", "blue"], ["red", "green", "blue", "alpha"]]),
+                  ["radius"], ["quality"]):
+        if rng.random() < 0.5:
+            groups.append(extra)
+    if rng.random() < 0.15:
+        groups[0] = ["x", "y"]                    # an incomplete triple: the reference then reads no positions at all
+    props = [p for g in groups for p in g]
+    if rng.random() < 0.5:
+        rng.shuffle(props)
+    elements = []   # (name, count, [(prop name, type or (count type, item type), values per row)])
+
+    def scalar_type(name):
+        if name in ("red", "green", "blue", "alpha"):
+            return rng.choice(["uchar", "uint8", "float", "ushort"])
+        return rng.choice(["float", "float32", "double", "float64"] if rng.random() < 0.9 else ["int", "short"])
+    vertex = []
+    for p in props:
+        t = scalar_type(p)
+        code = SCALARS[t]
+        if code in "fd":
+            vals = [rng.choice([0.0, 1.0, -1.0, 0.5]) if rng.random() < 0.2 else round(rng.uniform(-2, 2), rng.randint(1, 7)) for _ in range(nverts)]
+        else:
+            hi = {"b": 127, "B": 255, "h": 32767, "H": 65535, "i": 100000, "I": 100000}[code]
+            vals = [rng.randint(0 if code.isupper() else -hi, hi) for _ in range(nverts)]
+        vertex.append((p, t, vals))
+    elements.append(("vertex", nverts, vertex))
+
+    def index_list(name, sizes_choices, count):
+        ctype = rng.choice(["uchar", "uint8"]) if rng.random() < 0.97 else rng.choice(["int", "ushort"])   # only bytes are accepted
+        itype = rng.choice(["int", "uint", "int32", "ushort", "uchar", "short"])
+        rows = [[rng.randrange(nverts) for _ in range(rng.choice(sizes_choices))] for _ in range(count)]
+        return (name, (ctype, itype), rows)
+    kinds = rng.sample(["face", "line", "point"], rng.randint(1, 3))
+    if rng.random() < 0.3:
+        elements.append(("material", 2, [("ambient", "float", [0.5, 0.25])]))       # an element nobody reads
+    for kind in kinds:
+        n = rng.randint(1, 6)
+        if kind == "face":
+            shapes = rng.choice([[3], [4], [3, 4], [3, 4, 5, 6, 7], [0, 1, 2, 3], [3, 3, 3, 4]])
+            cols = [index_list(rng.choice(["vertex_indices", "vertex_indices", "vertex_index"]), shapes, n)]
+            if rng.random() < 0.3:
+                cols.append(("flags", "uchar", [rng.randrange(4) for _ in range(n)]))
+                rng.shuffle(cols)
+        elif kind == "line":
+            cols = [index_list("vertex_indices", [2, 2, 3, 5, 1, 0], n)]
+        else:
+            cols = [index_list("vertex_indices", [1, 1, 2, 0], n)]
+        elements.append((kind, n, cols))
+    if rng.random() < 0.3:
+        rng.shuffle(elements)
+    nl = b"\n"
+    head = [b"ply", b"format " + fmt.encode() + b" 1.0"]
+    if rng.random() < 0.5:
+        head.append(b"comment made by a test")
+    if rng.random() < 0.2:
+        head.append(b"obj_info whatever 1 2 3")
+    for name, count, cols in elements:
+        head.append(b"element %s %d" % (name.encode(), count))
+        for pname, ptype, _ in cols:
+            if isinstance(ptype, tuple):
+                head.append(b"property list %s %s %s" % (ptype[0].encode(), ptype[1].encode(), pname.encode()))
+            else:
+                head.append(b"property %s %s" % (ptype.encode(), pname.encode()))
+        if rng.random() < 0.1:
+            head.append(b"comment in between")
+    head.append(b"end_header")
+    out = nl.join(head) + nl
+    order = {"ascii": None, "binary_little_endian": "<", "binary_big_endian": ">"}[fmt]
+    for name, count, cols in elements:
+        for r in range(count):
+            if order is None:
+                words = []
+                for pname, ptype, vals in cols:
+                    if isinstance(ptype, tuple):
+                        words += [str(len(vals[r]))] + [str(v) for v in vals[r]]
+                    else:
+                        words.append(repr(vals[r]) if isinstance(vals[r], float) else str(vals[r]))
+                out += (" " * rng.randint(0, 1) + (" " * rng.randint(1, 2)).join(words)).encode() + nl
+            else:
+                for pname, ptype, vals in cols:
+                    if isinstance(ptype, tuple):
+                        out += struct.pack(order + SCALARS[ptype[0]], len(vals[r]))
+                        out += b"".join(struct.pack(order + SCALARS[ptype[1]], v) for v in vals[r])
+                    else:
+                        out += struct.pack(order + SCALARS[ptype], vals[r])
+    return out
+
+
+def make_obj(rng):
+    nv, nn, nt = rng.randint(3, 9), rng.choice([0, 0, 2, 4]), rng.choice([0, 0, 3, 5])
+    lines = ["# a test file"] if rng.random() < 0.5 else []
+    number = lambda: rng.choice(["0", "1", "-1", "0.5", "1e-3", "-2.5E1", ".25", "3."]) if rng.random() < 0.3 else repr(round(rng.uniform(-3, 3), rng.randint(0, 6)))
+    body = [f"v {number()} {number()} {number()}" for _ in range(nv)]
+    body += [f"vn {number()} {number()} {number()}" for _ in range(nn)]
+    body += [f"vt {number()} {number()}" for _ in range(nt)]
+
+    def vert():
+        i = rng.randrange(nv)
+        v = str(i + 1) if rng.random() < 0.8 else str(i - nv)
+        t = (str(rng.randrange(nt) + 1) if rng.random() < 0.8 else str(-1 - rng.randrange(nt))) if nt and rng.random() < 0.8 else ""
+        n = (str(rng.randrange(nn) + 1) if rng.random() < 0.8 else str(-1 - rng.randrange(nn))) if nn and rng.random() < 0.8 else ""
+        return v + ("/" + t + ("/" + n if n else "") if t or n else "")
+    elems = []
+    kinds = rng.choice([["f"], ["f"], ["f", "l"], ["l"], ["p"], ["f", "l", "p"], ["l", "p"]])
+    for _ in range(rng.randint(1, 7)):
+        kind = rng.choice(kinds)
+        n = {"f": rng.choice([3, 3, 4, 4, 5, 6]), "l": rng.choice([2, 3, 4]), "p": rng.choice([1, 1, 2])}[kind]
+        elems.append(kind + " " + " ".join(vert() for _ in range(n)))
+    if rng.random() < 0.3:
+        elems.insert(rng.randrange(len(elems) + 1), "g part" if rng.random() < 0.5 else "s 1")
+    if rng.random() < 0.3:
+        elems.insert(rng.randrange(len(elems) + 1), "usemtl stuff")
+    if rng.random() < 0.3:      # vertices declared after their use by negative index resolve differently: keep order, but interleave some
+        rng.shuffle(body)
+    text = "\n".join(lines + body + elems) + ("\n" if rng.random() < 0.9 else "")
+    if rng.random() < 0.2:
+        text = text.replace("\n", "\r\n")
+    return text.encode()
+
+
+def _verdict(ref, scene):
+    try:
+        ours, ours_error = lib.load_scene(scene), None
+    except lib.YglError as e:
+        ours, ours_error = None, str(e)
+    try:
+        theirs, theirs_error = ref.load_scene(scene), None
+    except RuntimeError as e:
+        theirs, theirs_error = None, str(e)
+    if (ours is None) != (theirs is None):
+        return f"accepted by one loader only (ours: {ours_error!r}, reference: {theirs_error!r})"
+    if ours is None:
+        return "refused"
+    try:
+        assert_scenes_identical(ours, theirs)
+    except AssertionError as e:
+        return f"scenes differ at {e}"
+    return "same"
+
+
+def _run(ref, tmp_path, name, data):
+    os.makedirs(tmp_path / "shapes", exist_ok=True)
+    (tmp_path / "shapes" / name).write_bytes(data)
+    scene = tmp_path / (name + ".json")
+    scene.write_text(json.dumps({"asset": {"version": "4.2"}, "cameras": [{"name": "c"}], "shapes": [{"name": "s", "uri": "shapes/" + name}]}))
+    r, w = os.pipe()
+    pid = os.fork()
+    if pid == 0:
+        verdict = "child failed"
+        try:
+            os.close(r)
+            os.write(w, b"started;")
+            verdict = _verdict(ref, scene)
+        finally:
+            os.write(w, verdict.encode())
+            os._exit(0)
+    os.close(w)
+    out = b""
+    while chunk := os.read(r, 4096):
+        out += chunk
+    os.close(r)
+    os.waitpid(pid, 0)
+    return out.decode().partition(";")[2] or "reference crashed"
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_ply_files_load_like_the_reference(ref, seed, tmp_path):
+    rng = random.Random(seed)
+    counts = {"same": 0, "refused": 0, "reference crashed": 0}
+    for k in range(150):
+        data = make_ply(rng)
+        verdict = _run(ref, tmp_path, f"s{k}.ply", data)
+        assert verdict in counts, f"file {k} (seed {seed}): {verdict}\n{data[:1200]!r}"
+        counts[verdict] += 1
+    assert counts["same"] >= 100, counts
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_obj_files_load_like_the_reference(ref, seed, tmp_path):
+    rng = random.Random(seed)
+    counts = {"same": 0, "refused": 0, "reference crashed": 0}
+    for k in range(150):
+        data = make_obj(rng)
+        verdict = _run(ref, tmp_path, f"s{k}.obj", data)
+        assert verdict in counts, f"file {k} (seed {seed}): {verdict}\n{data.decode()}"
+        counts[verdict] += 1
+    assert counts["same"] >= 100, counts

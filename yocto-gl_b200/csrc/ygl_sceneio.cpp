@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -454,29 +455,35 @@ bool load_ply(const std::string& filename, std::vector<PlyElement>& elements, st
     return tokens;
   };
   std::string line;
-  if (!next_line(line) || line != "ply") return parse_error();
   int  format = -1;  // 0 ascii, 1 little endian, 2 big endian
-  bool header_done = false;
+  bool header_done = false, first_line = true;
   while (next_line(line)) {
+    if (auto hash = line.find('#'); hash != std::string::npos) line.resize(hash);  // remove_comment, yocto_modelio.cpp:336
     auto tok = split(line);
     if (tok.empty()) continue;
-    if (tok[0] == "format") {
+    if (first_line) {
+      if (tok[0] != "ply") return parse_error();
+      first_line = false;
+    } else if (tok[0] == "ply") {
+    } else if (tok[0] == "format") {
       if (tok.size() < 2) return parse_error();
       format = tok[1] == "ascii" ? 0 : tok[1] == "binary_little_endian" ? 1 : tok[1] == "binary_big_endian" ? 2 : -1;
       if (format < 0) return parse_error();
     } else if (tok[0] == "comment" || tok[0] == "obj_info") {
     } else if (tok[0] == "element") {
-      if (tok.size() != 3) return parse_error();
+      if (tok.size() < 3) return parse_error();
+      size_t count = 0;
+      if (std::from_chars(tok[2].data(), tok[2].data() + tok[2].size(), count).ptr == tok[2].data()) return parse_error();
       elements.emplace_back();
       elements.back().name  = tok[1];
-      elements.back().count = (size_t)strtoull(tok[2].c_str(), nullptr, 10);
+      elements.back().count = count;
     } else if (tok[0] == "property") {
       if (elements.empty() || tok.size() < 3) return parse_error();
       PlyProperty prop;
       if (tok[1] == "list") {
-        if (tok.size() != 5) return parse_error();
+        if (tok.size() < 5) return parse_error();
         prop.is_list = true, prop.count_type = ply_type(tok[2]), prop.type = ply_type(tok[3]), prop.name = tok[4];
-        if (prop.count_type == PlyBad) return parse_error();
+        if (prop.count_type != U8) return parse_error();  // the reference keeps list sizes in bytes and refuses the rest (:570)
       } else {
         prop.type = ply_type(tok[1]), prop.name = tok[2];
       }
@@ -496,32 +503,70 @@ bool load_ply(const std::string& filename, std::vector<PlyElement>& elements, st
       else prop.values.reserve(elem.count);
     }
   if (format == 0) {
-    auto next_number = [&](double& v) {
-      while (p < end && isspace((unsigned char)*p)) p++;
+    // one line per element row, every value read with the parser of its declared type (parse_value, yocto_modelio.cpp:
+    // 405-418): from_chars - integers stop at the first character that is not a digit, a value that does not fit leaves
+    // the zero it started from, floats are rounded once to their own width
+    const char* line_end = p;
+    auto read_row = [&]() {
       if (p >= end) return false;
-      char* stop = nullptr;
-      v          = strtod(p, &stop);
+      const char* e = (const char*)memchr(p, '\n', end - p);
+      line_end      = e ? e + 1 : end;
+      return true;
+    };
+    auto skip_space = [&]() {
+      while (p < line_end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) p++;
+    };
+    auto parse_as = [&](PlyType t, double& v) {
+      skip_space();
+      const char* stop = p;
+      auto integer = [&](auto x) {
+        stop = std::from_chars(p, line_end, x).ptr;
+        v    = (double)x;
+      };
+      switch (t) {
+        case I8: integer((int8_t)0); break;
+        case I16: integer((int16_t)0); break;
+        case I32: integer((int32_t)0); break;
+        case I64: integer((int64_t)0); break;
+        case U8: integer((uint8_t)0); break;
+        case U16: integer((uint16_t)0); break;
+        case U32: integer((uint32_t)0); break;
+        case U64: integer((uint64_t)0); break;
+        case F32: {
+          float x = 0;
+          stop    = std::from_chars(p, line_end, x).ptr;
+          v       = x;
+        } break;
+        default: {
+          double x = 0;
+          stop     = std::from_chars(p, line_end, x).ptr;
+          v        = x;
+        } break;
+      }
       if (stop == p) return false;
       p = stop;
       return true;
     };
     for (auto& elem : elements)
-      for (size_t row = 0; row < elem.count; row++)
+      for (size_t row = 0; row < elem.count; row++) {
+        if (!read_row()) return error = "cannot read " + filename, false;
         for (auto& prop : elem.properties) {
           double v;
           if (!prop.is_list) {
-            if (!next_number(v)) return parse_error();
-            prop.values.push_back(prop.type == F32 ? (double)(float)v : v);
+            if (!parse_as(prop.type, v)) return parse_error();
+            prop.values.push_back(v);
           } else {
-            if (!next_number(v)) return parse_error();
-            const uint8_t n = (uint8_t)(long long)v;
+            if (!parse_as(U8, v)) return parse_error();
+            const uint8_t n = (uint8_t)v;
             prop.sizes.push_back(n);
             for (int k = 0; k < n; k++) {
-              if (!next_number(v)) return parse_error();
+              if (!parse_as(prop.type, v)) return parse_error();
               prop.values.push_back(v);
             }
           }
         }
+        p = line_end;
+      }
   } else {
     const uint8_t* q    = (const uint8_t*)p;
     const uint8_t* qend = (const uint8_t*)end;
