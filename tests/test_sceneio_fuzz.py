@@ -3,9 +3,9 @@
 with a few mutated values per document (wrong types, short and long arrays, booleans as numbers, the numbers nlohmann
 reads as integers or rejects: "-0", 2^64, 1e400; groups given as the other container kind; repeated keys; \\u escapes,
 raw UTF-8, ill-formed UTF-8, a BOM; truncated text) - must be refused by both loaders or give bit-identical scenes.
-Every document is loaded in a forked child: the reference reads out of bounds on some inputs it accepts (an instance
-without a valid shape in a scene it has to frame), which the generator avoids, and a crash of the reference must not
-take the test down. Host-only."""
+Every document is loaded in a worker process (tests/loader_worker.py): the reference reads out of bounds on some inputs it
+accepts (an instance without a valid shape in a scene it has to frame), which the generator avoids, and a crash of the
+reference must not take the test down. Host-only."""
 import json
 import os
 import random
@@ -13,7 +13,8 @@ import random
 import pytest
 
 from ygl_b200 import lib
-from test_sceneio import _write_tri_ply, assert_scenes_identical
+from loader_worker import LoaderPair
+from test_sceneio import _write_tri_ply
 
 RAW_NUMBERS = ["1e400", "-1e400", "1E5", "-0", "-0.0", "0.1e-46", "123456789012345678901234567890", "9007199254740993",
                "18446744073709551615", "18446744073709551616", "-9223372036854775808", "-9223372036854775809", "1.0e+2", "0e0",
@@ -144,55 +145,18 @@ def make_document(rng):
     return data
 
 
-def load_both(ref, path):
-    """'same' / 'refused' / a description of the difference; run in a forked child, the verdict comes back by pipe"""
-    try:
-        ours, our_error = lib.load_scene(path), None
-    except lib.YglError as e:
-        ours, our_error = None, str(e)
-    try:
-        theirs, their_error = ref.load_scene(path), None
-    except RuntimeError as e:
-        theirs, their_error = None, str(e)
-    if (ours is None) != (theirs is None):
-        return f"accepted by one loader only (ours: {our_error!r}, reference: {their_error!r})"
-    if ours is None:
-        return "refused"
-    try:
-        assert_scenes_identical(ours, theirs)
-    except AssertionError as e:
-        return f"scenes differ at {e}"
-    return "same"
-
-
 @pytest.mark.parametrize("seed", [101, 202, 303])
 def test_random_scene_documents_load_like_the_reference(ref, seed, tmp_path):
     rng = random.Random(seed)
     os.makedirs(tmp_path / "shapes")
     _write_tri_ply(tmp_path / "shapes" / "tri.ply")
     verdicts = {"same": 0, "refused": 0, "reference crashed": 0}
+    loaders = LoaderPair()
     for k in range(150):
         path = tmp_path / f"doc{k}.json"
         data = make_document(rng)
         path.write_bytes(data)
-        r, w = os.pipe()
-        pid = os.fork()
-        if pid == 0:
-            verdict = "child failed"
-            try:
-                os.close(r)
-                os.write(w, b"started;")
-                verdict = load_both(ref, path)
-            finally:
-                os.write(w, verdict.encode())
-                os._exit(0)
-        os.close(w)
-        out = b""
-        while chunk := os.read(r, 4096):
-            out += chunk
-        os.close(r)
-        os.waitpid(pid, 0)
-        verdict = out.decode().partition(";")[2] or "reference crashed"   # our loader never crashes: see below
+        verdict = loaders.verdict(path)
         assert verdict in verdicts, f"document {k} (seed {seed}): {verdict}\n{data[:1500]!r}"
         verdicts[verdict] += 1
         if verdict == "reference crashed":       # then ours alone must still come back
@@ -200,4 +164,5 @@ def test_random_scene_documents_load_like_the_reference(ref, seed, tmp_path):
                 lib.load_scene(path)
             except lib.YglError:
                 pass
+    loaders.close()
     assert verdicts["same"] >= 30 and verdicts["refused"] >= 30, verdicts

@@ -3,7 +3,8 @@
 byte orders, properties of every scalar type in any order, list properties with any count / index type, extra elements and
 properties, polygons of 0..7 corners, polylines, points, radius / colour / texcoord variants; OBJ with shared and split
 vertices, negative indices, missing components, polygons, lines and points, comments - must load to bit-identical arrays
-(or be refused by both). Host-only; every file is read in a forked child so that a crash of the reference is survived."""
+(or be refused by both). Host-only; the files are read in a worker process (tests/loader_worker.py) so that a crash of
+the reference is survived."""
 import json
 import os
 import random
@@ -11,8 +12,7 @@ import struct
 
 import pytest
 
-from ygl_b200 import lib
-from test_sceneio import assert_scenes_identical
+from loader_worker import LoaderPair
 
 SCALARS = {"char": "b", "uchar": "B", "short": "h", "ushort": "H", "int": "i", "uint": "I", "float": "f", "double": "d",
            "int8": "b", "uint8": "B", "int16": "h", "uint16": "H", "int32": "i", "uint32": "I", "float32": "f", "float64": "d"}
@@ -142,60 +142,25 @@ def make_obj(rng):
     return text.encode()
 
 
-def _verdict(ref, scene):
-    try:
-        ours, ours_error = lib.load_scene(scene), None
-    except lib.YglError as e:
-        ours, ours_error = None, str(e)
-    try:
-        theirs, theirs_error = ref.load_scene(scene), None
-    except RuntimeError as e:
-        theirs, theirs_error = None, str(e)
-    if (ours is None) != (theirs is None):
-        return f"accepted by one loader only (ours: {ours_error!r}, reference: {theirs_error!r})"
-    if ours is None:
-        return "refused"
-    try:
-        assert_scenes_identical(ours, theirs)
-    except AssertionError as e:
-        return f"scenes differ at {e}"
-    return "same"
-
-
-def _run(ref, tmp_path, name, data):
+def _run(loaders, tmp_path, name, data):
     os.makedirs(tmp_path / "shapes", exist_ok=True)
     (tmp_path / "shapes" / name).write_bytes(data)
     scene = tmp_path / (name + ".json")
     scene.write_text(json.dumps({"asset": {"version": "4.2"}, "cameras": [{"name": "c"}], "shapes": [{"name": "s", "uri": "shapes/" + name}]}))
-    r, w = os.pipe()
-    pid = os.fork()
-    if pid == 0:
-        verdict = "child failed"
-        try:
-            os.close(r)
-            os.write(w, b"started;")
-            verdict = _verdict(ref, scene)
-        finally:
-            os.write(w, verdict.encode())
-            os._exit(0)
-    os.close(w)
-    out = b""
-    while chunk := os.read(r, 4096):
-        out += chunk
-    os.close(r)
-    os.waitpid(pid, 0)
-    return out.decode().partition(";")[2] or "reference crashed"
+    return loaders.verdict(scene)
 
 
 @pytest.mark.parametrize("seed", [1, 2])
 def test_random_ply_files_load_like_the_reference(ref, seed, tmp_path):
     rng = random.Random(seed)
     counts = {"same": 0, "refused": 0, "reference crashed": 0}
+    loaders = LoaderPair()
     for k in range(150):
         data = make_ply(rng)
-        verdict = _run(ref, tmp_path, f"s{k}.ply", data)
+        verdict = _run(loaders, tmp_path, f"s{k}.ply", data)
         assert verdict in counts, f"file {k} (seed {seed}): {verdict}\n{data[:1200]!r}"
         counts[verdict] += 1
+    loaders.close()
     assert counts["same"] >= 100, counts
 
 
@@ -203,9 +168,11 @@ def test_random_ply_files_load_like_the_reference(ref, seed, tmp_path):
 def test_random_obj_files_load_like_the_reference(ref, seed, tmp_path):
     rng = random.Random(seed)
     counts = {"same": 0, "refused": 0, "reference crashed": 0}
+    loaders = LoaderPair()
     for k in range(150):
         data = make_obj(rng)
-        verdict = _run(ref, tmp_path, f"s{k}.obj", data)
+        verdict = _run(loaders, tmp_path, f"s{k}.obj", data)
         assert verdict in counts, f"file {k} (seed {seed}): {verdict}\n{data.decode()}"
         counts[verdict] += 1
+    loaders.close()
     assert counts["same"] >= 100, counts
