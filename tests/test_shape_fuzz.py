@@ -202,10 +202,18 @@ def make_subdiv_scene(rng, d):
     lines += [f"vt {rng.random():.4f} {rng.random():.4f}" for _ in range(ntex)]
     lines += ["vn 0 0 1", "vn 0 1 0", "vn 1 0 0"] if has_n else []
     for f in faces:
+        # the three topologies must agree on which faces are triangles (last two corners equal): what the reference does
+        # otherwise is undefined (it reads past the shorter per-face array) and we refuse such a mesh
+        tex = [v + 1 if rng.random() < 0.8 else rng.randint(1, ntex) for v in f] if has_t else []
+        nrm = [rng.randint(1, 3) for _ in f] if has_n else []
+        if len(f) == 4:
+            if has_t and tex[2] == tex[3]:
+                tex[2], tex[3] = f[2] + 1, f[3] + 1
+            if has_n and nrm[2] == nrm[3]:
+                nrm[3] = nrm[2] % 3 + 1
         corners = []
-        for v in f:
-            t = str(v + 1 if rng.random() < 0.8 else rng.randint(1, ntex)) if has_t else ""
-            n = str(rng.randint(1, 3)) if has_n else ""
+        for c, v in enumerate(f):
+            t, n = (str(tex[c]) if has_t else ""), (str(nrm[c]) if has_n else "")
             corners.append(str(v + 1) + ("/" + t + ("/" + n if n else "") if t or n else ""))
         lines.append("f " + " ".join(corners))
     (d / "subdivs" / "s.obj").write_text("\n".join(lines) + "\n")

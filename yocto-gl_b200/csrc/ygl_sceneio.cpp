@@ -1452,6 +1452,26 @@ bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& 
 
 // tesselate_subdiv, yocto_scene.cpp:739-805: the subdivided, displaced, split surface replaces the shape
 bool tesselate_subdiv(HostShape& shape, HostSubdiv subdiv, const std::vector<HostTexture>& textures, std::string& error) {
+  // What the reference leaves undefined is refused here: an index outside its array, and - when the mesh is subdivided -
+  // position / normal / texcoord topologies that disagree on which faces are triangles (q.z == q.w): those split into
+  // three and four faces and the per-face arrays stop lining up (the reference then reads past their ends)
+  auto in_range = [](const std::vector<i4>& quads, size_t n) {
+    for (auto& q : quads)
+      for (int c : {q.x, q.y, q.z, q.w})
+        if (c < 0 || (size_t)c >= n) return false;
+    return true;
+  };
+  if (!in_range(subdiv.quadspos, subdiv.positions.size()) || !in_range(subdiv.quadsnorm, subdiv.normals.size()) ||
+      !in_range(subdiv.quadstexcoord, subdiv.texcoords.size()))
+    return error = "subdiv index out of range", false;
+  for (auto* other : {&subdiv.quadsnorm, &subdiv.quadstexcoord}) {
+    if (other->empty()) continue;
+    if (other->size() != subdiv.quadspos.size()) return error = "subdiv topologies differ in size", false;
+    if (subdiv.subdivisions > 0)
+      for (size_t f = 0; f < other->size(); f++)
+        if (((*other)[f].z == (*other)[f].w) != (subdiv.quadspos[f].z == subdiv.quadspos[f].w))
+          return error = "subdiv topologies disagree on a triangle", false;
+  }
   if (subdiv.subdivisions > 0) {
     for (int k = 0; k < subdiv.subdivisions; k++) {
       if (subdiv.catmullclark) {
