@@ -1452,10 +1452,16 @@ bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& 
 
 // tesselate_subdiv, yocto_scene.cpp:739-805: the subdivided, displaced, split surface replaces the shape
 bool tesselate_subdiv(HostShape& shape, HostSubdiv subdiv, const std::vector<HostTexture>& textures, std::string& error) {
-  // What the reference leaves undefined is refused here: an index outside its array, and - when the mesh is subdivided -
-  // position / normal / texcoord topologies that disagree on which faces are triangles (q.z == q.w): those split into
-  // three and four faces and the per-face arrays stop lining up (the reference then reads past their ends)
+  // What the reference leaves undefined is refused here: an index outside its array, per-face arrays of different
+  // lengths, and - when the mesh is subdivided - position and texcoord topologies that disagree on which faces are
+  // triangles (q.z == q.w): those split into three and four faces and stop lining up (the reference then reads past the
+  // shorter array). The normals of the file are dead as soon as the mesh is subdivided (recomputed if smooth, dropped if
+  // not, :752-767), so they are neither checked nor subdivided then: the reference's own cube-subdiv.obj names normals
+  // 9..24 of 8, which it reads out of bounds and then throws away.
+  const bool normals_live = subdiv.subdivisions <= 0;
+  if (!normals_live) subdiv.quadsnorm.clear(), subdiv.normals.clear();
   auto in_range = [](const std::vector<i4>& quads, size_t n) {
+    if (n == 0) return true;  // no data: the topology is carried along but never dereferenced
     for (auto& q : quads)
       for (int c : {q.x, q.y, q.z, q.w})
         if (c < 0 || (size_t)c >= n) return false;
