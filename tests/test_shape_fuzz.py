@@ -249,3 +249,32 @@ def test_random_subdivs_tesselate_like_the_reference(ref, tmp_path):
         counts[verdict] += 1
     loaders.close()
     assert counts["same"] >= 80, counts     # (the reference itself crashes on a few of the meshes with stray indices)
+
+
+def test_stl_shapes_load_like_the_reference(ref, tmp_path):
+    """Binary .stl shapes (load_stl, yocto_modelio.cpp:2164): vertices merged by float equality in order of first use
+    (-0 joins +0, a NaN joins nothing), a header that says "solid" but whose length fits the binary layout, two solids in
+    one file (refused), a truncated file (refused), ascii text (refused: the reference's ascii branch cannot pass an
+    "outer loop" line)."""
+    rng = random.Random(9)
+    nan = struct.unpack("<f", b"\x00\x00\xc0\x7f")[0]
+
+    def solid(ntri, pool):
+        out = struct.pack("<I", ntri)
+        for _ in range(ntri):
+            out += struct.pack("<3f", 0, 0, 1) + b"".join(struct.pack("<3f", *rng.choice(pool)) for _ in range(3)) + struct.pack("<H", rng.randrange(4))
+        return out
+    pool = [(rng.choice([0.0, -0.0, 1.0, 0.5, -2.25, nan]), rng.uniform(-1, 1) if rng.random() < 0.5 else 0.0, rng.choice([0.0, -0.0, 3.0])) for _ in range(12)]
+    files = {
+        "plain.stl": (b"made by a test".ljust(80, b"\0") + solid(40, pool), "same"),
+        "solid_header.stl": (b"solid but binary".ljust(80, b" ") + solid(7, pool), "same"),
+        "empty_solid.stl": (b"x".ljust(80, b"\0") + solid(0, pool), "same"),
+        "two_solids.stl": (b"x".ljust(80, b"\0") + solid(3, pool) + solid(2, pool), "refused"),
+        "truncated.stl": ((b"x".ljust(80, b"\0") + solid(5, pool))[:-20], "refused"),
+        "no_solid.stl": (b"x".ljust(80, b"\0"), "refused"),
+        "ascii.stl": (b"solid s\nfacet normal 0 0 1\nouter loop\nvertex 0 0 0\nvertex 1 0 0\nvertex 0 1 0\nendloop\nendfacet\nendsolid s\n".ljust(120, b"\n"), "refused"),
+    }
+    loaders = LoaderPair()
+    for name, (data, expected) in files.items():
+        assert _run(loaders, tmp_path, name, data) == expected, name
+    loaders.close()

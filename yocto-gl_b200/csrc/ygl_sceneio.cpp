@@ -1,4 +1,4 @@
-// ygl_sceneio.cpp — scene ingestion: Yocto/GL JSON scene files (asset version 4.2 / 5.0) with
+// ygl_sceneio.cpp — scene ingestion: Yocto/GL JSON scene files (formats 4.0 and 4.2 / 5.0) with
 // PLY shapes and PNG / Radiance-HDR textures, read straight into the flat host arrays a ygl_scene_desc views, ready
 // for ygl_scene_create / ygl_bvh_build / ygl_lights_create. Host C++ only.
 //
@@ -9,10 +9,11 @@
 //   add_missing_camera / add_missing_radius          yocto_sceneio.cpp:2119-2148
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
 // Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
-// Shapes: .ply and .obj. Not built: glTF / pbrt / stl shapes, EXR / JPG textures: such scenes are refused.
+// Shapes: .ply, .obj, binary .stl. Not built: glTF / pbrt / mitsuba / obj scenes, EXR / JPG textures: refused.
 #include <zlib.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cerrno>
 #include <charconv>
@@ -617,9 +618,67 @@ void ply_vertex_values(const std::vector<PlyElement>& ply, const char* const (&n
 }
 // load_shape for .ply, yocto_sceneio.cpp:1018-1035 (flip_texcoord = true as load_json_scene passes)
 bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& error);  // .obj, further down
+// load_shape for .stl (yocto_sceneio.cpp:1053-1062 over load_stl, yocto_modelio.cpp:2164-2331): the binary format only
+// - 80 bytes of header, then per solid a count and 50 bytes per triangle; the file is binary unless it starts with
+// "solid" and its length disagrees with its first count; exactly one solid. (The reference's ascii branch fails on
+// every "outer loop" line, :2303, so ascii files are refused there as here.) Vertices are merged when their three
+// floats compare equal (-0 == +0, a NaN equals nothing), numbered in order of first use.
+struct StlVertexHash {
+  size_t operator()(const std::array<float, 3>& v) const {
+    size_t h = 0;
+    for (float x : v) {
+      uint32_t bits = 0;
+      if (x != 0) memcpy(&bits, &x, 4);  // both zeros hash alike
+      h ^= std::hash<uint32_t>()(bits) + 0x9e3779b9 + (h << 6) + (h >> 2);
+    }
+    return h;
+  }
+};
+bool load_stl_shape(const std::string& filename, HostShape& shape, std::string& error) {
+  std::vector<uint8_t> data;
+  if (!read_file(filename, data, error)) return false;
+  auto read_error = [&]() { return error = "cannot read " + filename, false; };
+  if (data.size() < 80) return read_error();
+  bool binary = memcmp(data.data(), "solid", 5) != 0;
+  if (!binary) {
+    if (data.size() < 84) return read_error();
+    uint32_t count;
+    memcpy(&count, &data[80], 4);
+    binary = data.size() == 80 + 4 + (size_t)50 * count;
+  }
+  if (!binary) return error = "cannot parse " + filename, false;
+  size_t pos = 80, solids = 0;
+  std::vector<std::array<float, 3>> corners;
+  while (pos < data.size()) {
+    if (data.size() - pos < 4) return read_error();
+    uint32_t count;
+    memcpy(&count, &data[pos], 4);
+    pos += 4;
+    if ((data.size() - pos) / 50 < count) return read_error();
+    if (solids++ == 0) {
+      corners.resize((size_t)count * 3);
+      for (size_t t = 0; t < count; t++) memcpy(corners[3 * t].data(), &data[pos + 50 * t + 12], 36);
+    }
+    pos += (size_t)50 * count;
+  }
+  if (solids == 0) return read_error();
+  if (solids != 1) return error = "empty shape " + filename, false;  // "shape_error": one solid per file
+  std::unordered_map<std::array<float, 3>, int, StlVertexHash> index;
+  shape.triangles.reserve(corners.size());
+  for (auto& corner : corners) {
+    auto it = index.find(corner);
+    if (it == index.end()) {
+      it = index.insert({corner, (int)(shape.positions.size() / 3)}).first;
+      shape.positions.insert(shape.positions.end(), corner.begin(), corner.end());
+    }
+    shape.triangles.push_back(it->second);
+  }
+  return true;
+}
 bool load_shape(const std::string& filename, HostShape& shape, std::string& error) {
   const auto ext = path_extension(filename);
   if (ext == ".obj" || ext == ".OBJ") return load_obj_shape(filename, shape, error);
+  if (ext == ".stl") return load_stl_shape(filename, shape, error);
   if (ext != ".ply") return error = "unsupported format " + filename, false;
   std::vector<PlyElement> ply;
   if (!load_ply(filename, ply, error)) return false;
