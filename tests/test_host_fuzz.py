@@ -118,3 +118,40 @@ def test_lights_match_reference_on_random_scenes(ref, seed):
         assert len(l_ref) == len(l_my), (seed, it)
         for a, b in zip(l_ref, l_my):
             assert a[0] == b[0] and a[1] == b[1] and a[2].tobytes() == b[2].tobytes(), (seed, it)
+
+
+def test_bvh_refit_matches_reference_on_random_degenerate_scenes(ref):
+    """ygl_bvh_update against update_scene_bvh (yocto_bvh.cpp:303-318, 398-451): the trees of a random scene refitted to
+    an edited copy (some shapes get new vertices of a new distribution - possibly NaN -, every frame moves) must equal
+    the reference's refit of its own trees, node for node."""
+    import copy
+    for it in range(60):
+        rng = np.random.default_rng(7000 + it)
+        sc = abi.Scene()
+        sc.add_camera()
+        material = sc.add_material(color=(0.5, 0.5, 0.5))
+        nshapes = int(rng.integers(1, 4))
+        for _ in range(nshapes):
+            _add_shape(rng, sc, [0.0, 0.001, 0.1, 1.0])
+        for _ in range(int(rng.integers(1, 40))):
+            sc.add_instance(int(rng.integers(0, nshapes)), material, frame=_frame(rng))
+        moved = copy.copy(sc)
+        moved._keep = None
+        moved.shapes = [dict(s) for s in sc.shapes]
+        moved.instances = [dict(n) for n in sc.instances]
+        updated = [k for k in range(nshapes) if rng.random() < 0.6]
+        for k in updated:
+            moved.shapes[k]["positions"] = _positions(rng, len(moved.shapes[k]["positions"]))
+            if len(moved.shapes[k]["radius"]):
+                moved.shapes[k]["radius"] = rng.choice([0.0, 0.02, 0.5], len(moved.shapes[k]["radius"])).astype(np.float32)
+        for n in moved.instances:
+            n["frame"] = _frame(rng)
+        for highquality in (False, True):
+            mine = lib.Bvh(sc, highquality)
+            mine.update(moved, updated)
+            rs_old, rs_new = ref.scene(sc), ref.scene(moved)
+            rs_new.adopt_updated_bvh(rs_old, updated, highquality)
+            for shape in [-1] + list(range(nshapes)):
+                n_ref, p_ref = rs_new.bvh_tree(shape, highquality)
+                n_my, p_my = mine.tree(shape)
+                assert n_ref.tobytes() == n_my.tobytes() and p_ref.tobytes() == p_my.tobytes(), (it, highquality, shape)
