@@ -10,6 +10,7 @@
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
 // Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
 // Shapes: .ply, .obj, binary .stl. Not built: glTF / pbrt / mitsuba / obj scenes, EXR / JPG textures: refused.
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -572,20 +573,68 @@ bool load_ply(const std::string& filename, std::vector<PlyElement>& elements, st
     const uint8_t* q    = (const uint8_t*)p;
     const uint8_t* qend = (const uint8_t*)end;
     const bool     be   = format == 2;
-    for (auto& elem : elements)
+    // a column of `count` values of one type, `stride` bytes apart, converted with the type decided outside the loop
+    auto read_column = [&](const uint8_t* src, size_t stride, size_t count, PlyType t, double* dst) {
+      auto run = [&](auto sample) {
+        using T = decltype(sample);
+        for (size_t i = 0; i < count; i++, src += stride) {
+          T v;
+          if (be && sizeof(T) > 1) {
+            uint8_t b[sizeof(T)];
+            for (size_t k = 0; k < sizeof(T); k++) b[k] = src[sizeof(T) - 1 - k];
+            memcpy(&v, b, sizeof(T));
+          } else {
+            memcpy(&v, src, sizeof(T));
+          }
+          dst[i] = (double)v;
+        }
+      };
+      switch (t) {
+        case I8: run(int8_t{}); break;
+        case U8: run(uint8_t{}); break;
+        case I16: run(int16_t{}); break;
+        case U16: run(uint16_t{}); break;
+        case I32: run(int32_t{}); break;
+        case U32: run(uint32_t{}); break;
+        case I64: run(int64_t{}); break;
+        case U64: run(uint64_t{}); break;
+        case F32: run(float{}); break;
+        default: run(double{}); break;
+      }
+    };
+    for (auto& elem : elements) {
+      bool has_list = false;
+      size_t row_bytes = 0;
+      for (auto& prop : elem.properties) has_list |= prop.is_list, row_bytes += ply_size(prop.type);
+      if (!has_list) {  // fixed-size rows: one strided pass per property
+        if (row_bytes && (size_t)(qend - q) / row_bytes < elem.count) return parse_error();
+        size_t offset = 0;
+        for (auto& prop : elem.properties) {
+          prop.values.resize(elem.count);
+          read_column(q + offset, row_bytes, elem.count, prop.type, prop.values.data());
+          offset += ply_size(prop.type);
+        }
+        q += row_bytes * elem.count;
+        continue;
+      }
       for (size_t row = 0; row < elem.count; row++)
         for (auto& prop : elem.properties) {
           if (!prop.is_list) {
             if (qend - q < ply_size(prop.type)) return parse_error();
             prop.values.push_back(ply_read_binary(q, prop.type, be));
           } else {
-            if (qend - q < ply_size(prop.count_type)) return parse_error();
-            const uint8_t n = (uint8_t)(long long)ply_read_binary(q, prop.count_type, be);
+            if (qend - q < 1) return parse_error();
+            const uint8_t n = *q++;  // list sizes are bytes (checked in the header)
             prop.sizes.push_back(n);
-            if (qend - q < (ptrdiff_t)n * ply_size(prop.type)) return parse_error();
-            for (int k = 0; k < n; k++) prop.values.push_back(ply_read_binary(q, prop.type, be));
+            const size_t item = ply_size(prop.type);
+            if ((size_t)(qend - q) < n * item) return parse_error();
+            const size_t at = prop.values.size();
+            prop.values.resize(at + n);
+            read_column(q, item, n, prop.type, prop.values.data() + at);
+            q += n * item;
           }
         }
+    }
   }
   return true;
 }
@@ -788,9 +837,15 @@ bool load_hdr(const std::vector<uint8_t>& data, HostTexture& tex) {
   if (sscanf(line.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) return false;
   tex.width = w, tex.height = h;
   tex.pixelsf.assign((size_t)w * h * 4, 0.0f);
+  static const struct Scales {  // 2^(e - 136) for every exponent byte: what ldexp returns, computed once
+    float of[256];
+    Scales() {
+      for (int e = 0; e < 256; e++) of[e] = (float)ldexp(1.0f, e - (int)(128 + 8));
+    }
+  } scales;
   auto convert = [](float* out, const uint8_t* rgbe) {
     if (rgbe[3] != 0) {
-      float f1 = (float)ldexp(1.0f, rgbe[3] - (int)(128 + 8));
+      float f1 = scales.of[rgbe[3]];
       out[0] = rgbe[0] * f1, out[1] = rgbe[1] * f1, out[2] = rgbe[2] * f1;
     } else {
       out[0] = out[1] = out[2] = 0;
@@ -857,20 +912,27 @@ bool png_unfilter(const uint8_t* raw, size_t raw_size, int w, int h, const PngLa
     uint8_t*       dst    = &img[stride * j];
     const uint8_t* up     = j ? dst - stride : nullptr;
     if (filter > 4) return false;
-    for (size_t i = 0; i < stride; i++) {  // PNG specification, section 9
-      const int a = i >= bpp ? dst[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
-      int       v = src[i];
-      switch (filter) {
-        case 1: v += a; break;
-        case 2: v += b; break;
-        case 3: v += (a + b) >> 1; break;
-        case 4: {
+    // PNG specification, section 9 (a: left, b: above, c: above left; bytes before the row or the image read as 0)
+    switch (filter) {
+      case 0: memcpy(dst, src, stride); break;
+      case 1:
+        for (size_t i = 0; i < stride; i++) dst[i] = (uint8_t)(src[i] + (i >= bpp ? dst[i - bpp] : 0));
+        break;
+      case 2:
+        if (!up) memcpy(dst, src, stride);
+        else
+          for (size_t i = 0; i < stride; i++) dst[i] = (uint8_t)(src[i] + up[i]);
+        break;
+      case 3:
+        for (size_t i = 0; i < stride; i++) dst[i] = (uint8_t)(src[i] + (((i >= bpp ? dst[i - bpp] : 0) + (up ? up[i] : 0)) >> 1));
+        break;
+      default:
+        for (size_t i = 0; i < stride; i++) {
+          const int a = i >= bpp ? dst[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
           const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
-          v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-        } break;
-        default: break;
-      }
-      dst[i] = (uint8_t)v;
+          dst[i] = (uint8_t)(src[i] + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)));
+        }
+        break;
     }
   }
   if (png.depth >= 8) return out = std::move(img), true;
@@ -1043,7 +1105,9 @@ int material_type_from_name(const std::string& name) {
 const float kIdentityFrame[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
 
 // load resources on the host cores; the first error (lowest index) wins, like the reference's parallel_for
-bool parallel_load(size_t n, std::string& error, const std::function<bool(size_t, std::string&)>& fn) {
+// (`order`, if given, is the sequence in which items are handed out - largest first keeps the cores even)
+bool parallel_load(size_t n, std::string& error, const std::function<bool(size_t, std::string&)>& fn,
+    const std::vector<size_t>* order = nullptr) {
   std::vector<std::string> errors(n);
   std::vector<char>        failed(n, 0);
   std::atomic<size_t>      next{0};
@@ -1051,8 +1115,10 @@ bool parallel_load(size_t n, std::string& error, const std::function<bool(size_t
   std::vector<std::thread> pool;
   for (unsigned t = 0; t < nthreads; t++)
     pool.emplace_back([&]() {
-      for (size_t i = next++; i < n; i = next++)
+      for (size_t k = next++; k < n; k = next++) {
+        const size_t i = order ? (*order)[k] : k;
         if (!fn(i, errors[i])) failed[i] = 1;
+      }
     });
   for (auto& t : pool) t.join();
   for (size_t i = 0; i < n; i++)
@@ -1326,70 +1392,65 @@ bool read_obj(const std::string& filename, ObjData& obj, std::string& error) {
   std::vector<uint8_t> data;
   if (!read_file(filename, data, error)) return false;
   auto parse_error = [&]() { return error = "cannot parse " + filename, false; };
-  data.push_back(0);
   const char*       p   = (const char*)data.data();
-  const char* const end = p + data.size() - 1;
+  const char* const end = p + data.size();
   auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; };
+  // lines are parsed in place; numbers with from_chars like the reference's parse_value (yocto_modelio.cpp:405-418):
+  // no leading '+', an integer that does not fit leaves the 0 it started from
   while (p < end) {
     const char* eol = (const char*)memchr(p, '\n', end - p);
     if (!eol) eol = end;
-    std::string line(p, eol);
+    const char* s    = p;
+    const char* stop = (const char*)memchr(p, '#', eol - p);  // remove_comment
+    if (!stop) stop = eol;
     p = eol < end ? eol + 1 : end;
-    if (auto hash = line.find('#'); hash != std::string::npos) line.resize(hash);
-    const char* s = line.c_str();
-    auto skip  = [&]() { while (*s && is_space(*s)) s++; };
-    auto token = [&]() {
-      skip();
-      const char* b = s;
-      while (*s && !is_space(*s)) s++;
-      return std::string(b, s);
-    };
+    auto skip = [&]() { while (s < stop && is_space(*s)) s++; };
     auto number = [&](float& v) {
       skip();
-      char* e = nullptr;
-      v       = strtof(s, &e);
-      if (e == s) return false;
-      s = e;
+      auto r = std::from_chars(s, stop, v);
+      if (r.ptr == s) return false;
+      s = r.ptr;
       return true;
     };
-    auto integer = [&](int& v) {  // std::from_chars: no leading '+'
+    auto integer = [&](int& v) {
       skip();
-      char* e = nullptr;
-      if (*s == '+') return false;
-      long r = strtol(s, &e, 10);
-      if (e == s) return false;
-      v = (int)r, s = e;
+      auto r = std::from_chars(s, stop, v);
+      if (r.ptr == s) return false;
+      s = r.ptr;
       return true;
     };
     skip();
-    if (!*s) continue;
-    const std::string cmd = token();
-    if (cmd == "v") {
-      v3 v;
+    if (s >= stop) continue;
+    const char* cmd = s;
+    while (s < stop && !is_space(*s)) s++;
+    const size_t cmd_len = (size_t)(s - cmd);
+    auto is_cmd = [&](const char* name) { return strlen(name) == cmd_len && !memcmp(cmd, name, cmd_len); };
+    if (is_cmd("v")) {
+      v3 v = {0, 0, 0};
       if (!number(v.x) || !number(v.y) || !number(v.z)) return parse_error();
       obj.positions.push_back(v);
-    } else if (cmd == "vn") {
-      v3 v;
+    } else if (is_cmd("vn")) {
+      v3 v = {0, 0, 0};
       if (!number(v.x) || !number(v.y) || !number(v.z)) return parse_error();
       obj.normals.push_back(v);
-    } else if (cmd == "vt") {
-      v2 v;
+    } else if (is_cmd("vt")) {
+      v2 v = {0, 0};
       if (!number(v.x) || !number(v.y)) return parse_error();
       obj.texcoords.push_back(v);
-    } else if (cmd == "f" || cmd == "l" || cmd == "p") {
+    } else if (is_cmd("f") || is_cmd("l") || is_cmd("p")) {
       int size = 0;
       skip();
-      while (*s) {
+      while (s < stop) {
         ObjVertex vert;
         if (!integer(vert.position)) return parse_error();
-        if (*s == '/') {
+        if (s < stop && *s == '/') {
           s++;
-          if (*s == '/') {
+          if (s < stop && *s == '/') {
             s++;
             if (!integer(vert.normal)) return parse_error();
           } else {
             if (!integer(vert.texcoord)) return parse_error();
-            if (*s == '/') {
+            if (s < stop && *s == '/') {
               s++;
               if (!integer(vert.normal)) return parse_error();
             }
@@ -2051,20 +2112,32 @@ bool load_scene_parts(const std::string& filename, ygl_loaded_scene& scene, Scen
   scene.shape_data.resize(shape_files.size());
   scene.texture_data.resize(texture_files.size());
   auto dependent_error = [&]() { return error = "cannot load " + filename + " since " + error, false; };
-  if (!parallel_load(shape_files.size(), error,
-          [&](size_t i, std::string& err) { return load_shape(path_join(dirname, shape_files[i]), scene.shape_data[i], err); }))
-    return dependent_error();
-  if (!parallel_load(subdiv_files.size(), error,
-          [&](size_t i, std::string& err) { return load_subdiv(path_join(dirname, subdiv_files[i]), subdivs[i], err); }))
-    return dependent_error();
-  if (!parallel_load(texture_files.size(), error, [&](size_t i, std::string& err) {
-        return load_texture(path_join(dirname, texture_files[i]), scene.texture_data[i], err);
-      }))
-    return dependent_error();
+  // One work list for every file the scene names - shapes, subdiv control meshes, textures, instance lists - instead of
+  // the reference's four passes: the largest file of each kind no longer waits for the other kinds. Errors keep the
+  // reference's precedence (the first failing shape, else the first failing subdiv, ...): the list is in that order and
+  // the lowest failing index wins.
   std::vector<std::vector<float>> instance_frames(parts.instance_files.size());
-  if (!parallel_load(parts.instance_files.size(), error, [&](size_t i, std::string& err) {
+  const size_t n_shapes = shape_files.size(), n_subdivs = subdiv_files.size(), n_textures = texture_files.size();
+  const size_t n_files = n_shapes + n_subdivs + n_textures + parts.instance_files.size();
+  std::vector<size_t> order(n_files), bytes(n_files, 0);
+  for (size_t i = 0; i < n_files; i++) {
+    const auto& name = i < n_shapes ? shape_files[i] : i < n_shapes + n_subdivs ? subdiv_files[i - n_shapes]
+                       : i < n_shapes + n_subdivs + n_textures ? texture_files[i - n_shapes - n_subdivs]
+                                                               : parts.instance_files[i - n_shapes - n_subdivs - n_textures];
+    struct stat st;
+    if (stat(path_join(dirname, name).c_str(), &st) == 0) bytes[i] = (size_t)st.st_size;
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return bytes[a] > bytes[b]; });
+  if (!parallel_load(n_files, error, [&](size_t i, std::string& err) {
+        if (i < n_shapes) return load_shape(path_join(dirname, shape_files[i]), scene.shape_data[i], err);
+        i -= n_shapes;
+        if (i < n_subdivs) return load_subdiv(path_join(dirname, subdiv_files[i]), subdivs[i], err);
+        i -= n_subdivs;
+        if (i < n_textures) return load_texture(path_join(dirname, texture_files[i]), scene.texture_data[i], err);
+        i -= n_textures;
         return load_instance_frames(path_join(dirname, parts.instance_files[i]), instance_frames[i], err);
-      }))
+      }, &order))
     return dependent_error();
   // "apply instances", yocto_sceneio.cpp:3335-3363: an object with an instance list becomes one instance per listed
   // frame (list frame * object frame), named <object>_<k>
@@ -2091,10 +2164,22 @@ bool load_scene_parts(const std::string& filename, ygl_loaded_scene& scene, Scen
   add_missing_camera(scene);
   add_missing_radius(scene);
   // tesselate_subdivs (yocto_scene.cpp:807-812): what every reference app does right after load_scene
+  std::vector<char> targeted(scene.shape_data.size(), 0);
+  bool              distinct = true;
   for (auto& subdiv : subdivs) {
     if (subdiv.shape < 0 || subdiv.shape >= (int)scene.shape_data.size())
       return error = "cannot load " + filename + ": subdiv shape id out of range", false;
-    if (!tesselate_subdiv(scene.shape_data[subdiv.shape], subdiv, scene.texture_data, error)) return dependent_error();
+    distinct = distinct && !targeted[subdiv.shape];
+    targeted[subdiv.shape] = 1;
+  }
+  if (distinct) {  // every subdiv writes its own shape: one core each (the reference walks them one after the other)
+    if (!parallel_load(subdivs.size(), error, [&](size_t i, std::string& err) {
+          return tesselate_subdiv(scene.shape_data[subdivs[i].shape], subdivs[i], scene.texture_data, err);
+        }))
+      return dependent_error();
+  } else {
+    for (auto& subdiv : subdivs)
+      if (!tesselate_subdiv(scene.shape_data[subdiv.shape], subdiv, scene.texture_data, error)) return dependent_error();
   }
   return true;
 }
