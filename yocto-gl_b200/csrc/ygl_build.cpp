@@ -9,7 +9,9 @@
 #include <atomic>
 #include <cmath>
 #include <functional>
+#include <condition_variable>
 #include <limits>
+#include <mutex>
 #include <thread>
 
 #include "ygl_sampling.cuh"
@@ -62,8 +64,11 @@ std::pair<int, int> split_middle(std::vector<int>& prims, const std::vector<f3>&
 }
 
 // split_sah, yocto_bvh.cpp:108-164 (16 bins per axis; cost normalised by the centroid box area)
+// (`spread`, if given, runs the 45 independent (axis, bin) evaluations of a large node on several cores; each
+// evaluation still folds its boxes over the primitives in order, and the minimum is taken in the reference's order)
+using Spread = std::function<void(int, const std::function<void(int)>&)>;
 std::pair<int, int> split_sah(std::vector<int>& prims, const std::vector<box3>& bboxes, const std::vector<f3>& centers,
-    int start, int end) {
+    int start, int end, const Spread* spread = nullptr) {
   box3 cb;
   for (int i = start; i < end; i++) cb = merge(cb, centers[prims[i]]);
   f3 csize = cb.max - cb.min;
@@ -76,21 +81,32 @@ std::pair<int, int> split_sah(std::vector<int>& prims, const std::vector<box3>& 
     f3 size = b.max - b.min;
     return 1e-12f + 2 * size.x * size.y + 2 * size.x * size.z + 2 * size.y * size.z;
   };
+  auto evaluate = [&](int saxis, int b, float& bsplit) {
+    bsplit = comp(cb.min, saxis) + b * comp(csize, saxis) / nbins;
+    box3 lbox, rbox;
+    int  ln = 0, rn = 0;
+    for (int i = start; i < end; i++) {
+      if (comp(centers[prims[i]], saxis) < bsplit) {
+        lbox = merge(lbox, bboxes[prims[i]]);
+        ln += 1;
+      } else {
+        rbox = merge(rbox, bboxes[prims[i]]);
+        rn += 1;
+      }
+    }
+    return 1 + ln * area(lbox) / area(cb) + rn * area(rbox) / area(cb);
+  };
+  float costs[3][nbins], splits[3][nbins];
+  if (spread) {
+    (*spread)(3 * (nbins - 1), [&](int k) {
+      const int saxis = k / (nbins - 1), b = 1 + k % (nbins - 1);
+      costs[saxis][b] = evaluate(saxis, b, splits[saxis][b]);
+    });
+  }
   for (int saxis = 0; saxis < 3; saxis++) {
     for (int b = 1; b < nbins; b++) {
-      float bsplit = comp(cb.min, saxis) + b * comp(csize, saxis) / nbins;
-      box3  lbox, rbox;
-      int   ln = 0, rn = 0;
-      for (int i = start; i < end; i++) {
-        if (comp(centers[prims[i]], saxis) < bsplit) {
-          lbox = merge(lbox, bboxes[prims[i]]);
-          ln += 1;
-        } else {
-          rbox = merge(rbox, bboxes[prims[i]]);
-          rn += 1;
-        }
-      }
-      float cost = 1 + ln * area(lbox) / area(cb) + rn * area(rbox) / area(cb);
+      float bsplit = 0;
+      float cost   = spread ? (bsplit = splits[saxis][b], costs[saxis][b]) : evaluate(saxis, b, bsplit);
       if (cost < min_cost) {
         min_cost = cost;
         split    = bsplit;
@@ -107,35 +123,31 @@ std::pair<int, int> split_sah(std::vector<int>& prims, const std::vector<box3>& 
 
 // make_bvh, yocto_bvh.cpp:238-302: explicit LIFO of {node, start, end}; children allocated
 // adjacently when the parent is visited; leaves hold <= 4 primitives.
-HostTree make_tree(const std::vector<box3>& bboxes, bool highquality) {
-  const int kMaxPrims = 4;
-  HostTree  tree;
-  tree.prims.resize(bboxes.size());
-  for (size_t i = 0; i < bboxes.size(); i++) tree.prims[i] = (int)i;
-  std::vector<f3> centers(bboxes.size());
-  for (size_t i = 0; i < bboxes.size(); i++) centers[i] = center(bboxes[i]);
-
+constexpr int kMaxPrims = 4;
+// the reference's loop over the primitives prims[first, last): `nodes` receives the subtree with its root at index 0
+void build_range(std::vector<int>& prims, const std::vector<box3>& bboxes, const std::vector<f3>& centers, int first, int last,
+    bool highquality, std::vector<ygl_bvh_node>& nodes) {
   struct item {
     int node, start, end;
   };
-  std::vector<item> stack = {{0, 0, (int)bboxes.size()}};
-  tree.nodes.reserve(bboxes.size() * 2 + 1);
-  tree.nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
+  std::vector<item> stack = {{0, first, last}};
+  nodes.reserve((size_t)(last - first) * 2 + 1);
+  nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
   while (!stack.empty()) {
     item it = stack.back();
     stack.pop_back();
     box3 bb;
-    for (int i = it.start; i < it.end; i++) bb = merge(bb, bboxes[tree.prims[i]]);
+    for (int i = it.start; i < it.end; i++) bb = merge(bb, bboxes[prims[i]]);
     ygl_bvh_node node = {{bb.min.x, bb.min.y, bb.min.z}, {bb.max.x, bb.max.y, bb.max.z}, 0, 0, 0, 0};
     if (it.end - it.start > kMaxPrims) {
-      auto [mid, axis] = highquality ? split_sah(tree.prims, bboxes, centers, it.start, it.end)
-                                     : split_middle(tree.prims, centers, it.start, it.end);
+      auto [mid, axis] = highquality ? split_sah(prims, bboxes, centers, it.start, it.end)
+                                     : split_middle(prims, centers, it.start, it.end);
       node.internal = 1;
       node.axis     = (int8_t)axis;
       node.num      = 2;
-      node.start    = (int)tree.nodes.size();
-      tree.nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
-      tree.nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
+      node.start    = (int)nodes.size();
+      nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
+      nodes.push_back(ygl_bvh_node{{kFltMax, kFltMax, kFltMax}, {kLowest, kLowest, kLowest}, 0, 0, 0, 0});
       stack.push_back({node.start + 0, it.start, mid});
       stack.push_back({node.start + 1, mid, it.end});
     } else {
@@ -143,7 +155,167 @@ HostTree make_tree(const std::vector<box3>& bboxes, bool highquality) {
       node.num      = (int16_t)(it.end - it.start);
       node.start    = it.start;
     }
-    tree.nodes[it.node] = node;
+    nodes[it.node] = node;
+  }
+}
+
+// A few threads that stay up for the length of one large build: run(count, fn) hands fn(0..count-1) out to them and
+// to the caller and returns when all are done.
+class WorkCrew {
+ public:
+  explicit WorkCrew(int threads) {
+    for (int t = 1; t < threads; t++) crew_.emplace_back([this]() { serve(); });
+  }
+  ~WorkCrew() {
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      quit_ = true;
+    }
+    wake_.notify_all();
+    for (auto& t : crew_) t.join();
+  }
+  void run(int count, const std::function<void(int)>& fn) {
+    if (count <= 0) return;
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      fn_ = &fn, count_ = count, next_ = 0, pending_ = count, round_++;
+    }
+    wake_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lock(mutex_);
+    done_.wait(lock, [&]() { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work() {
+    while (true) {
+      const std::function<void(int)>* fn = nullptr;
+      int                             k  = 0;
+      {
+        std::lock_guard<std::mutex> lock(mutex_);
+        if (!fn_ || next_ >= count_) return;
+        fn = fn_, k = next_++;
+      }
+      (*fn)(k);
+      std::lock_guard<std::mutex> lock(mutex_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void serve() {
+    uint64_t seen = 0;
+    while (true) {
+      {
+        std::unique_lock<std::mutex> lock(mutex_);
+        wake_.wait(lock, [&]() { return quit_ || round_ != seen; });
+        if (quit_) return;
+        seen = round_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread>        crew_;
+  std::mutex                      mutex_;
+  std::condition_variable         wake_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int                             count_ = 0, next_ = 0, pending_ = 0;
+  uint64_t                        round_ = 0;
+  bool                            quit_  = false;
+};
+
+constexpr int kParallelBuildMin = 32768;  // primitives from which one tree is built on several cores
+
+// The same tree on several cores. The reference's loop is a pre-order walk that visits a node's right child first and
+// gives a node's two children the next two free slots when it visits the node. Two consequences make the result
+// reproducible out of order: (1) what a node does depends only on the primitives in its own range, which only its
+// ancestors have permuted - disjoint subtrees can be built at the same time; (2) everything below a node is visited, and
+// therefore numbered, in one uninterrupted stretch - a subtree built on its own has its descendants in one block, in the
+// order the full walk would give them. So: split the nodes near the root one after the other (for SAH with the 45
+// candidate evaluations of a node spread over the cores), build the subtrees below a size limit independently with the
+// serial loop, then replay the walk over the few top nodes to hand out slots and copy each subtree's block behind it.
+HostTree make_tree_parallel(const std::vector<box3>& bboxes, bool highquality, int threads) {
+  HostTree  tree;
+  const int n = (int)bboxes.size();
+  tree.prims.resize(n);
+  for (int i = 0; i < n; i++) tree.prims[i] = i;
+  std::vector<f3> centers(n);
+  for (int i = 0; i < n; i++) centers[i] = center(bboxes[i]);
+  WorkCrew     crew(threads);
+  const Spread spread = [&](int count, const std::function<void(int)>& fn) { crew.run(count, fn); };
+  struct Top {
+    int          start, end, left = -1, right = -1, subtree = -1;
+    ygl_bvh_node node;
+  };
+  std::vector<Top> top = {{0, n}};
+  const int        limit = std::max(4096, n / (threads * 8));
+  std::vector<int> roots;  // top entries that are built as independent subtrees
+  for (size_t t = 0; t < top.size(); t++) {
+    const int first = top[t].start, last = top[t].end;
+    if (last - first <= limit) {
+      top[t].subtree = (int)roots.size();
+      roots.push_back((int)t);
+      continue;
+    }
+    box3 bb;
+    for (int i = first; i < last; i++) bb = merge(bb, bboxes[tree.prims[i]]);
+    auto [mid, axis] = highquality ? split_sah(tree.prims, bboxes, centers, first, last, &spread)
+                                   : split_middle(tree.prims, centers, first, last);
+    top[t].node      = {{bb.min.x, bb.min.y, bb.min.z}, {bb.max.x, bb.max.y, bb.max.z}, 0, 2, (int8_t)axis, 1};
+    const int left = (int)top.size();
+    top.push_back({first, mid});
+    top.push_back({mid, last});
+    top[t].left = left, top[t].right = left + 1;
+  }
+  std::vector<std::vector<ygl_bvh_node>> subtrees(roots.size());
+  // largest first: the ranges differ in size
+  std::vector<int> order(roots.size());
+  for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+  std::stable_sort(order.begin(), order.end(),
+      [&](int a, int b) { return top[roots[a]].end - top[roots[a]].start > top[roots[b]].end - top[roots[b]].start; });
+  crew.run((int)roots.size(), [&](int k) {
+    const Top& root = top[roots[order[k]]];
+    build_range(tree.prims, bboxes, centers, root.start, root.end, highquality, subtrees[order[k]]);
+  });
+  // replay the walk over the top nodes
+  size_t total = top.size() - roots.size();
+  for (auto& nodes : subtrees) total += nodes.size();
+  tree.nodes.resize(total);
+  std::vector<std::pair<int, int>> stack = {{0, 0}};  // (top entry, slot)
+  int                              cursor = 1;
+  while (!stack.empty()) {
+    auto [t, slot] = stack.back();
+    stack.pop_back();
+    if (top[t].subtree < 0) {
+      ygl_bvh_node node = top[t].node;
+      node.start        = cursor;
+      cursor += 2;
+      tree.nodes[slot] = node;
+      stack.push_back({top[t].left, node.start});
+      stack.push_back({top[t].right, node.start + 1});
+      continue;
+    }
+    const auto& nodes = subtrees[top[t].subtree];
+    const int   base  = cursor - 1;  // local index k >= 1 lands at base + k
+    for (size_t k = 0; k < nodes.size(); k++) {
+      ygl_bvh_node node = nodes[k];
+      if (node.internal) node.start += base;
+      tree.nodes[k == 0 ? slot : base + (int)k] = node;
+    }
+    cursor += (int)nodes.size() - 1;
+  }
+  return tree;
+}
+
+HostTree make_tree(const std::vector<box3>& bboxes, bool highquality, int threads = 1) {
+  HostTree tree;
+  if (threads > 1 && (int)bboxes.size() >= kParallelBuildMin) {
+    tree = make_tree_parallel(bboxes, highquality, threads);
+  } else {
+    tree.prims.resize(bboxes.size());
+    for (size_t i = 0; i < bboxes.size(); i++) tree.prims[i] = (int)i;
+    std::vector<f3> centers(bboxes.size());
+    for (size_t i = 0; i < bboxes.size(); i++) centers[i] = center(bboxes[i]);
+    build_range(tree.prims, bboxes, centers, 0, (int)bboxes.size(), highquality, tree.nodes);
   }
   // stack need of a traversal = deepest level + 1
   if (!tree.nodes.empty()) {
@@ -405,16 +577,17 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
       done[si]              = 1;
     }
   }
-  // one tree per shape: independent, built on all host cores (the reference does the same, yocto_bvh.cpp:376-378)
-  parallel_shapes(nshapes, [&](int si) {
-    if (done[si]) return;
+  // one tree per shape: independent, built on all host cores (the reference does the same, yocto_bvh.cpp:376-378);
+  // the large ones first, one after the other, each on all cores (make_tree_parallel), then the small ones side by side
+  const int host_threads = std::max(1, (int)std::thread::hardware_concurrency());
+  auto build_shape = [&](int si, int threads) {
     const ygl_shape&  s    = desc.shapes[si];
     const int         kind = shape_bvh_kind(s);
     std::vector<box3> bboxes;
     if (!shape_bounds(s, si, kind, bboxes, errors[si])) return;
     out.shape_kind[si] = kind;
     HostTree& tree     = out.shapes[si];
-    tree               = make_tree(bboxes, highquality);
+    tree               = make_tree(bboxes, highquality, threads);
     // (an empty shape still gets a single empty root leaf, exactly like the reference's make_bvh)
     if (tree.max_stack > kMaxTreeDepth) {
       errors[si] = "shape " + std::to_string(si) + ": BVH depth " + std::to_string(tree.max_stack) +
@@ -424,6 +597,12 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
     if (!tree_fits_node_words(tree, errors[si])) return;
     out.shape_nodes[si]   = pack_nodes(tree);
     out.shape_packets[si] = pack_leaves(s, kind, tree);
+  };
+  if (host_threads > 1)
+    for (int si = 0; si < nshapes; si++)
+      if (!done[si] && element_count(desc.shapes[si]) >= kParallelBuildMin) build_shape(si, host_threads), done[si] = 1;
+  parallel_shapes(nshapes, [&](int si) {
+    if (!done[si]) build_shape(si, 1);
   });
   for (auto& e : errors)
     if (!e.empty()) return error = e, false;
@@ -433,7 +612,7 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
   if (use_device && (int)ibox.size() >= kDeviceBuildMin) {
     if (!build_tree_device(device_stream, (const float*)ibox.data(), (int)ibox.size(), out.top, error)) return false;
   } else {
-    out.top = make_tree(ibox, highquality);
+    out.top = make_tree(ibox, highquality, host_threads);
   }
   if (out.top.max_stack > kMaxTreeDepth) return error = "instance BVH too deep for the traversal stack (128 entries)", false;
   if (!tree_fits_node_words(out.top, error)) return false;

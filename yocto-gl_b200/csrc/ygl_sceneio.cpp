@@ -2283,6 +2283,16 @@ void sky_radiance(const SkyModel& sky, float theta, float gamma, float theta_sun
   static const float to_rgb[3][3] = {{+3.2406f, -0.9689f, +0.0557f}, {-1.5372f, +1.8758f, -0.2040f}, {-0.4986f, +0.0415f, +1.0570f}};
   for (int c = 0; c < 3; c++) rgb[c] = (to_rgb[0][c] * xyz[0] + to_rgb[1][c] * xyz[1] + to_rgb[2][c] * xyz[2]) / 10000;
 }
+void parallel_rows(int rows, const std::function<void(int)>& fn) {
+  const unsigned nthreads = std::max(1u, std::min((unsigned)rows, std::thread::hardware_concurrency()));
+  std::atomic<int>         next{0};
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nthreads; t++)
+    pool.emplace_back([&]() {
+      for (int j = next++; j < rows; j = next++) fn(j);
+    });
+  for (auto& t : pool) t.join();
+}
 void make_sky_texture(HostTexture& tex, int width, int height, float theta_sun, float turbidity, const float (&ground_albedo)[3]) {
   const float pif = 3.14159265358979323846f, eps = 1.1920928955078125e-07f;
   auto fmin = [](float a, float b) { return (a < b) ? a : b; };
@@ -2291,7 +2301,8 @@ void make_sky_texture(HostTexture& tex, int width, int height, float theta_sun, 
   const float    sun_dir[3]   = {0, std::cos(theta_sun), std::sin(theta_sun)};
   tex.width = width, tex.height = height, tex.linear = 1;
   tex.pixelsf.assign((size_t)width * height * 4, 0.0f);
-  for (int j = 0; j < height / 2; j++) {
+  // rows are independent: one strip per core (the ground term below is a running sum and stays in pixel order)
+  parallel_rows(height / 2, [&](int j) {
     float theta = pif * ((j + 0.5f) / height);
     theta       = fmin(fmax(theta, 0.0f), pif / 2 - eps);
     for (int i = 0; i < width; i++) {
@@ -2303,7 +2314,7 @@ void make_sky_texture(HostTexture& tex, int width, int height, float theta_sun, 
       float* px = &tex.pixelsf[((size_t)j * width + i) * 4];
       px[0] = rgb[0] + 0.0f, px[1] = rgb[1] + 0.0f, px[2] = rgb[2] + 0.0f, px[3] = 1;  // "+ sun colour", which is zero here
     }
-  }
+  });
   float ground[3] = {0, 0, 0};
   if (ground_albedo[0] != 0 || ground_albedo[1] != 0 || ground_albedo[2] != 0) {
     for (int j = 0; j < height / 2; j++) {
@@ -2324,7 +2335,15 @@ void make_sky_texture(HostTexture& tex, int width, int height, float theta_sun, 
 
 bool load_ply_scene(const std::string& filename, ygl_loaded_scene& scene, std::string& error) {
   scene.shape_data.resize(1);
-  if (!load_shape(filename, scene.shape_data[0], error)) return false;
+  // the sky does not depend on the shape: it is made while the file is read. The model's parameters reach it through
+  // memory the compiler cannot see through, as they reach the reference's make_sunsky from another translation unit:
+  // libm is called at run time, nothing is folded at build time
+  volatile float sun_angle = 3.14159265358979323846f / 4, turbidity = 3;
+  HostTexture    sky;
+  std::thread    sky_maker([&]() { make_sky_texture(sky, 1024, 512, sun_angle, turbidity, {0.2f, 0.2f, 0.2f}); });
+  const bool     loaded = load_shape(filename, scene.shape_data[0], error);
+  sky_maker.join();
+  if (!loaded) return false;
   ygl_instance inst = {};
   memcpy(&inst.frame, kIdentityFrame, 48);
   inst.shape = 0, inst.material = 0;
@@ -2336,11 +2355,7 @@ bool load_ply_scene(const std::string& filename, ygl_loaded_scene& scene, std::s
   scene.materials.push_back(m);
   add_missing_camera(scene);
   add_missing_radius(scene);
-  // the model's parameters reach it through memory the compiler cannot see through, as they reach the reference's
-  // make_sunsky from another translation unit: libm is called at run time, nothing is folded at build time
-  volatile float sun_angle = 3.14159265358979323846f / 4, turbidity = 3;
-  scene.texture_data.emplace_back();
-  make_sky_texture(scene.texture_data.back(), 1024, 512, sun_angle, turbidity, {0.2f, 0.2f, 0.2f});
+  scene.texture_data.push_back(std::move(sky));
   scene.names[1].push_back("sky");
   ygl_environment env = {};
   memcpy(&env.frame, kIdentityFrame, 48);
