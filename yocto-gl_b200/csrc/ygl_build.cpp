@@ -9,7 +9,10 @@
 #include <atomic>
 #include <cmath>
 #include <functional>
+#include <sched.h>
+
 #include <condition_variable>
+#include <cstdio>
 #include <limits>
 #include <mutex>
 #include <thread>
@@ -19,6 +22,24 @@
 namespace ygl {
 
 namespace {
+
+// Cores this process may really use: the smaller of the affinity mask and the cgroup CPU quota (a container lease of
+// 16 CPUs on a 128-thread host reports 128 from hardware_concurrency; starting 128 threads there only adds switching)
+inline int host_parallelism() {
+  static const int cores = []() {
+    int n = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = std::min(n > 0 ? n : CPU_COUNT(&set), CPU_COUNT(&set));
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      long long quota = 0, period = 0;
+      if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
+        n = std::min<long long>(n > 0 ? n : 1, (quota + period - 1) / period);
+      fclose(f);
+    }
+    return std::max(1, n);
+  }();
+  return cores;
+}
 
 constexpr float kLowest = -kFltMax;  // flt_min = numeric_limits<float>::lowest(), yocto_math.h:78
 
@@ -335,7 +356,7 @@ HostTree make_tree(const std::vector<box3>& bboxes, bool highquality, int thread
 
 // run fn(0..n-1) on the host cores (dynamic: shapes differ wildly in size)
 void parallel_shapes(int n, const std::function<void(int)>& fn) {
-  const int nthreads = std::max(1, std::min<int>(n, (int)std::thread::hardware_concurrency()));
+  const int nthreads = std::max(1, std::min<int>(n, host_parallelism()));
   if (nthreads <= 1) {
     for (int i = 0; i < n; i++) fn(i);
     return;
@@ -579,7 +600,7 @@ bool build_scene_bvh(const ygl_scene_desc& desc, bool highquality, HostBvh& out,
   }
   // one tree per shape: independent, built on all host cores (the reference does the same, yocto_bvh.cpp:376-378);
   // the large ones first, one after the other, each on all cores (make_tree_parallel), then the small ones side by side
-  const int host_threads = std::max(1, (int)std::thread::hardware_concurrency());
+  const int host_threads = host_parallelism();
   auto build_shape = [&](int si, int threads) {
     const ygl_shape&  s    = desc.shapes[si];
     const int         kind = shape_bvh_kind(s);

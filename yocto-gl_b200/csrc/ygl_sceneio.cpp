@@ -10,6 +10,7 @@
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
 // Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
 // Shapes: .ply, .obj, binary .stl. Not built: glTF / pbrt / mitsuba / obj scenes, EXR / JPG textures: refused.
+#include <sched.h>
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -33,6 +34,24 @@
 #include "../../include/ygl_b200.h"
 
 namespace {
+
+// Cores this process may really use: the smaller of the affinity mask and the cgroup CPU quota (a container lease of
+// 16 CPUs on a 128-thread host reports 128 from hardware_concurrency; starting 128 threads there only adds switching)
+inline int host_parallelism() {
+  static const int cores = []() {
+    int n = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = std::min(n > 0 ? n : CPU_COUNT(&set), CPU_COUNT(&set));
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      long long quota = 0, period = 0;
+      if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
+        n = std::min<long long>(n > 0 ? n : 1, (quota + period - 1) / period);
+      fclose(f);
+    }
+    return std::max(1, n);
+  }();
+  return cores;
+}
 
 // the library's per-thread error string lives in ygl_api.cpp
 
@@ -1111,7 +1130,7 @@ bool parallel_load(size_t n, std::string& error, const std::function<bool(size_t
   std::vector<std::string> errors(n);
   std::vector<char>        failed(n, 0);
   std::atomic<size_t>      next{0};
-  const unsigned           nthreads = std::max(1u, std::min((unsigned)n, std::thread::hardware_concurrency()));
+  const unsigned           nthreads = std::max(1u, std::min((unsigned)n, (unsigned)host_parallelism()));
   std::vector<std::thread> pool;
   for (unsigned t = 0; t < nthreads; t++)
     pool.emplace_back([&]() {
@@ -2284,7 +2303,7 @@ void sky_radiance(const SkyModel& sky, float theta, float gamma, float theta_sun
   for (int c = 0; c < 3; c++) rgb[c] = (to_rgb[0][c] * xyz[0] + to_rgb[1][c] * xyz[1] + to_rgb[2][c] * xyz[2]) / 10000;
 }
 void parallel_rows(int rows, const std::function<void(int)>& fn) {
-  const unsigned nthreads = std::max(1u, std::min((unsigned)rows, std::thread::hardware_concurrency()));
+  const unsigned nthreads = std::max(1u, std::min((unsigned)rows, (unsigned)host_parallelism()));
   std::atomic<int>         next{0};
   std::vector<std::thread> pool;
   for (unsigned t = 0; t < nthreads; t++)
