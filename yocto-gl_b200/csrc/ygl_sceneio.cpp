@@ -2385,6 +2385,487 @@ bool load_ply_scene(const std::string& filename, ygl_loaded_scene& scene, std::s
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// glTF 2.0 (.gltf with external or base64 buffers, .glb): load_gltf_scene, yocto_sceneio.cpp:4430-4767, which reads
+// the file with cgltf (exts/cgltf) and converts: one shape per mesh primitive (POSITION / NORMAL / TEXCOORD_0 /
+// COLOR_0 / RADIUS through cgltf_accessor_read_float: component types, normalisation, strides; indices or implied
+// indices for triangles, strips, fans, lines, loops, line strips), one instance per primitive of every node with a
+// mesh under the node's world transform (cgltf_node_transform_world: TRS or matrix, multiplied up the parent chain in
+// cgltf's float association), one camera per node with a camera, gltfpbr materials (base colour / alpha, metallic,
+// roughness, emission x KHR_materials_emissive_strength, KHR_materials_transmission -> transparent), one texture per
+// image (uri, "%20" -> space), then add_missing_material / camera / radius and - a glTF file has no environment - the
+// procedural sky. Numbers are read as cgltf reads them (atof, narrowed to float). Where cgltf reads unchecked
+// (accessors past their buffers, indices past their arrays) the file is refused here.
+// ---------------------------------------------------------------------------------------------------------------
+struct GltfAccessor {
+  int    view = -1, component = 0, components = 0;
+  size_t offset = 0, count = 0, stride = 0;
+  bool   normalized = false, sparse = false, matrix = false;
+};
+struct GltfView {
+  int    buffer = -1;
+  size_t offset = 0, size = 0, stride = 0;
+};
+float gltf_float(const JValue& v) { return (float)(v.kind == JValue::Float ? v.number : v.kind == JValue::Signed ? (double)v.inumber : (double)v.unumber); }
+long long gltf_int(const JValue& v) { return v.kind == JValue::Float ? (long long)v.number : v.kind == JValue::Signed ? (long long)v.inumber : (long long)v.unumber; }
+bool base64_decode(const char* text, size_t size, std::vector<uint8_t>& out) {  // cgltf_load_buffer_base64: `size` bytes
+  out.resize(size);
+  unsigned buffer = 0, bits = 0;
+  for (size_t i = 0; i < size; i++) {
+    while (bits < 8) {
+      const char ch = *text++;
+      const int  index = (unsigned)(ch - 'A') < 26 ? ch - 'A' : (unsigned)(ch - 'a') < 26 ? ch - 'a' + 26 : (unsigned)(ch - '0') < 10 ? ch - '0' + 52
+                         : ch == '+' ? 62 : ch == '/' ? 63 : -1;
+      if (index < 0) return false;
+      buffer = (buffer << 6) | (unsigned)index;
+      bits += 6;
+    }
+    out[i] = (uint8_t)(buffer >> (bits - 8));
+    bits -= 8;
+  }
+  return true;
+}
+std::string uri_decode(const std::string& uri) {  // cgltf_decode_uri: %XX
+  std::string out;
+  auto hex = [](char c) { return (unsigned)(c - '0') < 10 ? c - '0' : (unsigned)(c - 'a') < 6 ? c - 'a' + 10 : (unsigned)(c - 'A') < 6 ? c - 'A' + 10 : -1; };
+  for (size_t i = 0; i < uri.size(); i++) {
+    if (uri[i] == '%' && i + 2 < uri.size() + 0 && hex(uri[i + 1]) >= 0 && hex(uri[i + 2]) >= 0) {
+      out += (char)(hex(uri[i + 1]) * 16 + hex(uri[i + 2]));
+      i += 2;
+    } else {
+      out += uri[i];
+    }
+  }
+  return out;
+}
+
+bool load_gltf_scene(const std::string& filename, ygl_loaded_scene& scene, std::string& error) {
+  std::vector<uint8_t> file;
+  if (!read_file(filename, file, error)) return false;
+  auto parse_error = [&]() { return error = "cannot parse " + filename, false; };
+  auto unsupported = [&](const char* what) { return error = "cannot load " + filename + " for sunsupported " + what, false; };
+  auto buffers_error = [&]() { return error = "cannot load " + filename + " since cannot load buffers", false; };
+  // container: a .glb wraps the JSON and one binary chunk
+  const uint8_t* json_begin = file.data();
+  size_t         json_size  = file.size();
+  const uint8_t* bin        = nullptr;
+  size_t         bin_size   = 0;
+  auto u32 = [&](size_t at) { uint32_t v; memcpy(&v, &file[at], 4); return v; };
+  if (file.size() >= 4 && u32(0) == 0x46546C67u) {
+    if (file.size() < 20 || u32(4) != 2 || u32(8) > file.size()) return parse_error();
+    const size_t total = u32(8), json_len = u32(12);
+    if (u32(16) != 0x4E4F534Au || 20 + json_len > total) return parse_error();
+    json_begin = &file[20], json_size = json_len;
+    const size_t next = 20 + json_len;
+    if (next + 8 <= total) {
+      const size_t len = u32(next);
+      if (u32(next + 4) != 0x004E4942u || next + 8 + len > total) return parse_error();
+      bin = &file[next + 8], bin_size = len;
+    }
+  }
+  JValue  json;
+  JParser parser{(const char*)json_begin, (const char*)json_begin + json_size};
+  if (!parser.parse_document(json) || json.type != JValue::Object) return parse_error();
+  auto array_of = [&](const JValue& parent, const char* key) -> const std::vector<JValue>& {
+    static const std::vector<JValue> none;
+    auto v = parent.find(key);
+    return v && v->type == JValue::Array ? v->array : none;
+  };
+  auto number_at = [&](const JValue& e, const char* key, double fallback) {
+    auto v = e.find(key);
+    return v && v->type == JValue::Number ? (double)gltf_int(*v) : fallback;
+  };
+  auto float_at = [&](const JValue& e, const char* key, float fallback) {
+    auto v = e.find(key);
+    return v && v->type == JValue::Number ? gltf_float(*v) : fallback;
+  };
+  auto floats_at = [&](const JValue& e, const char* key, float* out, size_t n) {
+    auto v = e.find(key);
+    if (!v || v->type != JValue::Array) return false;
+    for (size_t k = 0; k < n && k < v->array.size(); k++)
+      if (v->array[k].type == JValue::Number) out[k] = gltf_float(v->array[k]);
+    return true;
+  };
+  auto string_at = [&](const JValue& e, const char* key) -> const std::string* {
+    auto v = e.find(key);
+    return v && v->type == JValue::String ? &v->string : nullptr;
+  };
+  const auto dirname = path_dirname(filename);
+
+  // buffers
+  const auto& jbuffers = array_of(json, "buffers");
+  std::vector<std::vector<uint8_t>> buffers(jbuffers.size());
+  std::vector<const uint8_t*>       buffer_data(jbuffers.size(), nullptr);
+  std::vector<size_t>               buffer_size(jbuffers.size(), 0);
+  for (size_t i = 0; i < jbuffers.size(); i++) {
+    const size_t size = (size_t)number_at(jbuffers[i], "byteLength", 0);
+    auto         uri  = string_at(jbuffers[i], "uri");
+    if (i == 0 && !uri && bin) {
+      if (bin_size < size) return buffers_error();
+      buffer_data[i] = bin, buffer_size[i] = bin_size;
+      continue;
+    }
+    if (!uri) continue;
+    if (uri->compare(0, 5, "data:") == 0) {
+      const auto comma = uri->find(',');
+      if (comma == std::string::npos || comma < 7 || uri->compare(comma - 7, 7, ";base64") != 0) return buffers_error();
+      if ((uri->size() - comma - 1) * 6 / 8 < size || !base64_decode(uri->c_str() + comma + 1, size, buffers[i])) return buffers_error();
+    } else if (uri->find("://") == std::string::npos) {
+      std::string ignored;
+      if (!read_file(path_join(dirname, uri_decode(*uri)), buffers[i], ignored) || buffers[i].size() < size) return buffers_error();
+    } else {
+      return buffers_error();
+    }
+    buffer_data[i] = buffers[i].data(), buffer_size[i] = buffers[i].size();
+  }
+  std::vector<GltfView> views;
+  for (auto& jv : array_of(json, "bufferViews")) {
+    GltfView view;
+    view.buffer = (int)number_at(jv, "buffer", -1);
+    view.offset = (size_t)number_at(jv, "byteOffset", 0), view.size = (size_t)number_at(jv, "byteLength", 0);
+    view.stride = (size_t)number_at(jv, "byteStride", 0);
+    views.push_back(view);
+  }
+  std::vector<GltfAccessor> accessors;
+  for (auto& ja : array_of(json, "accessors")) {
+    GltfAccessor a;
+    a.view   = (int)number_at(ja, "bufferView", -1);
+    a.offset = (size_t)number_at(ja, "byteOffset", 0), a.count = (size_t)number_at(ja, "count", 0);
+    const int ctype = (int)number_at(ja, "componentType", 0);
+    a.component     = ctype;  // 5120 i8, 5121 u8, 5122 i16, 5123 u16, 5125 u32, 5126 f32
+    if (auto n = ja.find("normalized")) a.normalized = n->type == JValue::Bool && n->boolean;
+    a.sparse = ja.find("sparse") != nullptr;
+    if (auto t = string_at(ja, "type")) {
+      a.components = *t == "SCALAR" ? 1 : *t == "VEC2" ? 2 : *t == "VEC3" ? 3 : *t == "VEC4" ? 4 : *t == "MAT2" ? 4 : *t == "MAT3" ? 9 : *t == "MAT4" ? 16 : 0;
+      a.matrix     = (*t)[0] == 'M';
+    }
+    const size_t csize = ctype == 5120 || ctype == 5121 ? 1 : ctype == 5122 || ctype == 5123 ? 2 : ctype == 5125 || ctype == 5126 ? 4 : 0;
+    a.stride           = a.view >= 0 && a.view < (int)views.size() ? views[a.view].stride : 0;
+    if (a.stride == 0) a.stride = csize * a.components;  // (matrix alignment rules only matter for matrices, refused below)
+    accessors.push_back(a);
+  }
+  // one element of an accessor, bounds-checked; nullptr = the accessor has no data (reads as zeros, like cgltf)
+  auto component_size = [](int ctype) { return ctype == 5120 || ctype == 5121 ? 1 : ctype == 5122 || ctype == 5123 ? 2 : ctype == 5125 || ctype == 5126 ? 4 : 0; };
+  auto element_at = [&](const GltfAccessor& a, size_t index, const uint8_t*& ptr) {
+    ptr = nullptr;
+    if (a.view < 0) return true;
+    if (a.view >= (int)views.size()) return false;
+    const GltfView& view = views[a.view];
+    if (view.buffer < 0 || view.buffer >= (int)buffer_data.size() || !buffer_data[view.buffer]) return false;
+    const size_t at = view.offset + a.offset + a.stride * index, need = (size_t)component_size(a.component) * a.components;
+    if (at + need > buffer_size[view.buffer]) return false;
+    ptr = buffer_data[view.buffer] + at;
+    return true;
+  };
+  auto read_float = [](const uint8_t* in, int ctype, bool normalized) -> float {  // cgltf_component_read_float
+    if (ctype == 5126) { float v; memcpy(&v, in, 4); return v; }
+    int16_t  s16; uint16_t u16; uint32_t u32v;
+    switch (ctype) {
+      case 5122: memcpy(&s16, in, 2); return normalized ? s16 / (float)32767 : (float)(size_t)s16;
+      case 5123: memcpy(&u16, in, 2); return normalized ? u16 / (float)65535 : (float)(size_t)u16;
+      case 5120: return normalized ? (int8_t)in[0] / (float)127 : (float)(size_t)(int8_t)in[0];
+      case 5121: return normalized ? in[0] / (float)255 : (float)(size_t)in[0];
+      case 5125: memcpy(&u32v, in, 4); return normalized ? 0.0f : (float)(size_t)u32v;
+      default: return 0;
+    }
+  };
+  auto read_uint = [](const uint8_t* in, int ctype) -> uint32_t {  // cgltf_component_read_uint
+    int16_t s16; uint16_t u16; uint32_t u32v;
+    switch (ctype) {
+      case 5120: return (uint32_t)(int8_t)in[0];
+      case 5121: return in[0];
+      case 5122: memcpy(&s16, in, 2); return (uint32_t)s16;
+      case 5123: memcpy(&u16, in, 2); return u16;
+      case 5125: memcpy(&u32v, in, 4); return u32v;
+      default: return 0;
+    }
+  };
+
+  // cameras (attached to nodes below)
+  std::vector<ygl_camera> cameras;
+  for (auto& jc : array_of(json, "cameras")) {
+    ygl_camera camera = {};
+    memcpy(&camera.frame, kIdentityFrame, 48);
+    camera.orthographic = 0, camera.lens = 0.050f, camera.film = 0.036f, camera.aspect = 1.500f, camera.focus = 10000, camera.aperture = 0;
+    auto type = string_at(jc, "type");
+    if (type && *type == "orthographic") {
+      float xmag = 0, ymag = 0;
+      if (auto o = jc.find("orthographic")) xmag = float_at(*o, "xmag", 0), ymag = float_at(*o, "ymag", 0);
+      camera.aspect = xmag / ymag, camera.lens = ymag, camera.film = 0.036f;
+    } else if (type && *type == "perspective") {
+      float aspect = 0, yfov = 0;
+      if (auto o = jc.find("perspective")) aspect = float_at(*o, "aspectRatio", 0.0f), yfov = float_at(*o, "yfov", 0);
+      camera.aspect = aspect;
+      if (camera.aspect == 0) camera.aspect = 16.0f / 9.0f;
+      camera.film = 0.036f;
+      if (camera.aspect >= 1) camera.lens = (camera.film / camera.aspect) / (2 * std::tan(yfov / 2));
+      else camera.lens = camera.film / (2 * std::tan(yfov / 2));
+      camera.focus = 1;
+    } else {
+      return unsupported("camera type");
+    }
+    cameras.push_back(camera);
+  }
+  // images -> textures
+  const auto& jimages   = array_of(json, "images");
+  const auto& jtextures = array_of(json, "textures");
+  std::vector<std::string> texture_files;
+  for (auto& ji : jimages) {
+    auto uri = string_at(ji, "uri");
+    if (!uri) return unsupported("image without uri");  // (the reference dereferences a null uri here)
+    std::string path = *uri;
+    for (size_t at = 0; (at = path.find("%20", at)) != std::string::npos; at += 1) path.replace(at, 3, " ");
+    texture_files.push_back(path);
+  }
+  auto texture_of = [&](const JValue& owner, const char* key) {  // texture view -> image index
+    auto view = owner.find(key);
+    if (!view || view->type != JValue::Object) return -1;
+    const int t = (int)number_at(*view, "index", -1);
+    if (t < 0 || t >= (int)jtextures.size()) return -1;
+    const int image = (int)number_at(jtextures[t], "source", -1);
+    return image >= 0 && image < (int)jimages.size() ? image : -1;
+  };
+  // materials
+  const auto& jmaterials = array_of(json, "materials");
+  for (auto& jm : jmaterials) {
+    ygl_material m = {};
+    m.type = 7 /* gltfpbr */, m.roughness = 0, m.metallic = 0, m.ior = 1.5f, m.scanisotropy = 0, m.trdepth = 0.01f, m.opacity = 1;
+    m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
+    floats_at(jm, "emissiveFactor", m.emission, 3);
+    const JValue* extensions = jm.find("extensions");
+    if (extensions) {
+      if (auto strength = extensions->find("KHR_materials_emissive_strength")) {
+        const float k = float_at(*strength, "emissiveStrength", 1.0f);
+        for (float& e : m.emission) e *= k;
+      }
+    }
+    m.emission_tex = texture_of(jm, "emissiveTexture");
+    m.normal_tex   = texture_of(jm, "normalTexture");
+    if (auto pbr = jm.find("pbrMetallicRoughness"); pbr && pbr->type == JValue::Object) {
+      float base[4] = {1, 1, 1, 1};
+      floats_at(*pbr, "baseColorFactor", base, 4);
+      m.color[0] = base[0], m.color[1] = base[1], m.color[2] = base[2], m.opacity = base[3];
+      m.metallic      = float_at(*pbr, "metallicFactor", 1.0f);
+      m.roughness     = float_at(*pbr, "roughnessFactor", 1.0f);
+      m.color_tex     = texture_of(*pbr, "baseColorTexture");
+      m.roughness_tex = texture_of(*pbr, "metallicRoughnessTexture");
+    }
+    if (extensions) {
+      if (auto transmission = extensions->find("KHR_materials_transmission"); transmission && transmission->type == JValue::Object) {
+        const float t = float_at(*transmission, "transmissionFactor", 0.0f);
+        if (t > 0) {
+          m.type = 3 /* transparent */, m.color[0] = m.color[1] = m.color[2] = t;
+          m.color_tex = texture_of(*transmission, "transmissionTexture");
+        }
+      }
+    }
+    scene.materials.push_back(m);
+  }
+  // meshes -> shapes, and per mesh the (shape, material) pairs its nodes instantiate
+  std::vector<std::vector<std::pair<int, int>>> mesh_primitives;
+  for (auto& jmesh : array_of(json, "meshes")) {
+    mesh_primitives.emplace_back();
+    for (auto& jp : array_of(jmesh, "primitives")) {
+      auto attributes = jp.find("attributes");
+      if (!attributes || attributes->type != JValue::Object || attributes->object.empty()) continue;
+      scene.shape_data.emplace_back();
+      HostShape& shape    = scene.shape_data.back();
+      const int  material = (int)number_at(jp, "material", -1);
+      mesh_primitives.back().push_back({(int)scene.shape_data.size() - 1, material >= 0 && material < (int)jmaterials.size() ? material : -1});
+      for (auto& [name, jacc] : attributes->object) {
+        const int id = jacc.type == JValue::Number ? (int)gltf_int(jacc) : -1;
+        if (id < 0 || id >= (int)accessors.size()) return parse_error();
+        const GltfAccessor& a = accessors[id];
+        if (a.sparse) return unsupported("sparse accessor");
+        std::vector<float>* target = nullptr;
+        size_t              width  = (size_t)a.components;
+        if (name == "POSITION") {
+          if (a.components != 3) return unsupported("position components");
+          target = &shape.positions;
+        } else if (name == "NORMAL") {
+          if (a.components != 3) return unsupported("normal components");
+          target = &shape.normals;
+        } else if (name == "TEXCOORD" || name == "TEXCOORD_0") {
+          if (a.components != 2) return unsupported("texcoord components");
+          target = &shape.texcoords;
+        } else if (name == "COLOR" || name == "COLOR_0") {
+          if (a.components != 3 && a.components != 4) return unsupported("color components");
+          target = &shape.colors, width = 4;
+        } else if (name == "TANGENT") {
+          if (a.components != 4) return unsupported("tangent components");
+          continue;  // tangents are not read on the path (ygl_shape has none)
+        } else if (name == "RADIUS") {
+          if (a.components != 1) return unsupported("radius components");
+          target = &shape.radius;
+        } else {
+          continue;
+        }
+        if (a.matrix) return unsupported("accessor float conversion");
+        target->assign(a.count * width, 0.0f);
+        if (width != (size_t)a.components)
+          for (size_t i = 0; i < a.count; i++) (*target)[i * 4 + 3] = 1;
+        const size_t csize = (size_t)component_size(a.component);
+        for (size_t i = 0; i < a.count; i++) {
+          const uint8_t* element = nullptr;
+          if (!element_at(a, i, element)) return unsupported("accessor float conversion");
+          for (int c = 0; c < a.components; c++)
+            (*target)[i * width + c] = element ? read_float(element + csize * c, a.component, a.normalized) : 0.0f;
+        }
+      }
+      const int    mode      = (int)number_at(jp, "mode", 4);
+      const int    nverts    = (int)(shape.positions.size() / 3);
+      std::vector<int> indices;
+      const bool   indexed = jp.find("indices") != nullptr;
+      if (indexed) {
+        const int id = (int)number_at(jp, "indices", -1);
+        if (id < 0 || id >= (int)accessors.size()) return parse_error();
+        const GltfAccessor& a = accessors[id];
+        if (a.components != 1 || a.matrix) return unsupported("non-scalar indices");
+        if (a.sparse) return unsupported("accessor uint conversion");
+        indices.resize(a.count);
+        for (size_t i = 0; i < a.count; i++) {
+          const uint8_t* element = nullptr;
+          if (!element_at(a, i, element)) return unsupported("accessor uint conversion");
+          indices[i] = element ? (int)read_uint(element, a.component) : 0;
+        }
+      } else {
+        indices.resize(nverts);
+        for (int i = 0; i < nverts; i++) indices[i] = i;
+      }
+      const int n = (int)indices.size();
+      auto&     t = shape.triangles;
+      auto&     l = shape.lines;
+      switch (mode) {
+        case 4:
+          for (int i = 0; i < n / 3; i++) t.insert(t.end(), {indices[i * 3], indices[i * 3 + 1], indices[i * 3 + 2]});
+          break;
+        case 6:
+          if (n < 2) return unsupported("primitive type");  // (the reference resizes to a negative count)
+          for (int i = 2; i < n; i++) t.insert(t.end(), {indices[0], indices[i - 1], indices[i]});
+          break;
+        case 5:
+          if (n < 2) return unsupported("primitive type");
+          for (int i = 2; i < n; i++) t.insert(t.end(), {indices[i - 2], indices[i - 1], indices[i]});
+          break;
+        case 1:
+          for (int i = 0; i < n / 2; i++) l.insert(l.end(), {indices[i * 2], indices[i * 2 + 1]});
+          break;
+        case 2:
+          if (n < 1) return unsupported("primitive type");
+          if (indexed) {  // {indices[i], indices[i + 1] % n}: the reference reads one index past the end for the last
+            return unsupported("indexed line loop");  // segment and reduces the VALUE, not the position; undefined there
+          }
+          for (int i = 1; i < n; i++) l.insert(l.end(), {i - 1, i});
+          l.insert(l.end(), {n - 1, 0});
+          break;
+        case 3:
+          if (n < 1) return unsupported("primitive type");
+          for (int i = 1; i < n; i++) l.insert(l.end(), {indices[i - 1], indices[i]});
+          break;
+        case 0: return unsupported(indexed ? "points primitive" : "point primitive");
+        default: return unsupported("primitive type");
+      }
+    }
+  }
+  // nodes: parents from the children lists, then cameras and instances in node order
+  const auto& jnodes = array_of(json, "nodes");
+  std::vector<int> parent(jnodes.size(), -1);
+  for (size_t i = 0; i < jnodes.size(); i++)
+    for (auto& child : array_of(jnodes[i], "children")) {
+      const long long c = child.type == JValue::Number ? gltf_int(child) : -1;
+      if (c < 0 || c >= (long long)jnodes.size()) return parse_error();
+      parent[c] = (int)i;
+    }
+  auto local_matrix = [&](const JValue& node, float* lm) {  // cgltf_node_transform_local
+    float matrix[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (floats_at(node, "matrix", matrix, 16)) {
+      memcpy(lm, matrix, sizeof(matrix));
+      return;
+    }
+    float t[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, sc[3] = {1, 1, 1};
+    floats_at(node, "translation", t, 3), floats_at(node, "rotation", q, 4), floats_at(node, "scale", sc, 3);
+    const float qx = q[0], qy = q[1], qz = q[2], qw = q[3], sx = sc[0], sy = sc[1], sz = sc[2];
+    lm[0] = (1 - 2 * qy * qy - 2 * qz * qz) * sx, lm[1] = (2 * qx * qy + 2 * qz * qw) * sx, lm[2] = (2 * qx * qz - 2 * qy * qw) * sx, lm[3] = 0.f;
+    lm[4] = (2 * qx * qy - 2 * qz * qw) * sy, lm[5] = (1 - 2 * qx * qx - 2 * qz * qz) * sy, lm[6] = (2 * qy * qz + 2 * qx * qw) * sy, lm[7] = 0.f;
+    lm[8] = (2 * qx * qz + 2 * qy * qw) * sz, lm[9] = (2 * qy * qz - 2 * qx * qw) * sz, lm[10] = (1 - 2 * qx * qx - 2 * qy * qy) * sz, lm[11] = 0.f;
+    lm[12] = t[0], lm[13] = t[1], lm[14] = t[2], lm[15] = 1.f;
+  };
+  auto world_frame = [&](size_t node, ygl_frame3f& frame) {  // cgltf_node_transform_world, then mat_to_frame
+    float lm[16];
+    local_matrix(jnodes[node], lm);
+    int hops = 0;
+    for (int p = parent[node]; p >= 0; p = parent[p]) {
+      if (++hops > (int)jnodes.size()) return false;  // a cycle
+      float pm[16];
+      local_matrix(jnodes[p], pm);
+      for (int i = 0; i < 4; ++i) {
+        const float l0 = lm[i * 4 + 0], l1 = lm[i * 4 + 1], l2 = lm[i * 4 + 2];
+        const float r0 = l0 * pm[0] + l1 * pm[4] + l2 * pm[8], r1 = l0 * pm[1] + l1 * pm[5] + l2 * pm[9], r2 = l0 * pm[2] + l1 * pm[6] + l2 * pm[10];
+        lm[i * 4 + 0] = r0, lm[i * 4 + 1] = r1, lm[i * 4 + 2] = r2;
+      }
+      lm[12] += pm[12], lm[13] += pm[13], lm[14] += pm[14];
+    }
+    const float f[12] = {lm[0], lm[1], lm[2], lm[4], lm[5], lm[6], lm[8], lm[9], lm[10], lm[12], lm[13], lm[14]};
+    memcpy(&frame, f, sizeof(f));
+    return true;
+  };
+  for (size_t i = 0; i < jnodes.size(); i++) {
+    if (jnodes[i].find("camera")) {
+      const int c = (int)number_at(jnodes[i], "camera", -1);
+      if (c < 0 || c >= (int)cameras.size()) return parse_error();
+      ygl_camera camera = cameras[c];
+      if (!world_frame(i, camera.frame)) return parse_error();
+      scene.cameras.push_back(camera);
+    }
+    if (jnodes[i].find("mesh")) {
+      const int mesh = (int)number_at(jnodes[i], "mesh", -1);
+      if (mesh < 0 || mesh >= (int)mesh_primitives.size()) return parse_error();
+      for (auto& [shape, material] : mesh_primitives[mesh]) {
+        ygl_instance inst = {};
+        inst.shape = shape, inst.material = material;
+        if (!world_frame(i, inst.frame)) return parse_error();
+        scene.instances.push_back(inst);
+      }
+    }
+  }
+  // textures, fix-ups, sky
+  volatile float sun_angle = 3.14159265358979323846f / 4, turbidity = 3;
+  HostTexture    sky;
+  std::thread    sky_maker([&]() { make_sky_texture(sky, 1024, 512, sun_angle, turbidity, {0.2f, 0.2f, 0.2f}); });
+  scene.texture_data.resize(texture_files.size());
+  const bool loaded = parallel_load(texture_files.size(), error, [&](size_t i, std::string& err) {
+    return load_texture(path_join(dirname, texture_files[i]), scene.texture_data[i], err);
+  });
+  sky_maker.join();
+  if (!loaded) return error = "cannot save " + filename + " since " + error, false;  // (the reference's own wording)
+  int default_material = -1;  // add_missing_material, yocto_sceneio.cpp:2151-2163
+  for (auto& inst : scene.instances) {
+    if (inst.material >= 0) continue;
+    if (default_material < 0) {
+      ygl_material m = {};
+      m.type = 0, m.roughness = 0, m.metallic = 0, m.ior = 1.5f, m.scanisotropy = 0, m.trdepth = 0.01f, m.opacity = 1;
+      m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
+      m.color[0] = m.color[1] = m.color[2] = 0.8f;
+      scene.materials.push_back(m);
+      default_material = (int)scene.materials.size() - 1;
+    }
+    inst.material = default_material;
+  }
+  add_missing_camera(scene);
+  add_missing_radius(scene);
+  // add_missing_lights: has_lights (yocto_scene.cpp:678-689) only counts emissive instances whose shape has triangles AND
+  // quads, which no glTF shape has, and a glTF file has no environment: the sky is always added
+  scene.texture_data.push_back(std::move(sky));
+  scene.names[1].push_back("sky");  // (the only name the reference's scene carries: glTF images stay nameless)
+  ygl_environment env = {};
+  memcpy(&env.frame, kIdentityFrame, 48);
+  env.emission[0] = env.emission[1] = env.emission[2] = 1;
+  env.emission_tex = (int)scene.texture_data.size() - 1;
+  scene.environments.push_back(env);
+  scene.names[5].push_back("sky");
+  return true;
+}
+
 void make_desc(ygl_loaded_scene& scene) {
   scene.shapes.clear(), scene.textures.clear();
   for (auto& s : scene.shape_data) {
@@ -2435,6 +2916,7 @@ int ygl_scene_load(const char* filename, ygl_loaded_scene** out) {
   bool       ok  = false;
   if (ext == ".json") ok = load_json_scene(filename, *scene, error);
   else if (ext == ".ply") ok = load_ply_scene(filename, *scene, error);
+  else if (ext == ".gltf" || ext == ".glb") ok = load_gltf_scene(filename, *scene, error);
   else error = "unsupported format " + std::string(filename), ok = false;
   if (!ok) return ygl_internal_set_error(error.c_str()), YGL_ERR_RUNTIME;
   make_desc(*scene);
