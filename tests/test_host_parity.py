@@ -51,8 +51,6 @@ def test_pcg_known_answers(ref):
 @pytest.mark.parametrize("name", list(SCENES))
 @pytest.mark.parametrize("highquality", [False, True])
 def test_bvh_matches_reference_bitwise(ref, name, highquality):
-    if highquality and name in ("hair", "bunny4"):
-        pytest.skip("SAH on the large cases is covered by the smaller scenes")
     scene = SCENES[name]()
     rs, mine = ref.scene(scene), lib.Bvh(scene, highquality)
     for shape in [-1] + list(range(len(scene.shapes))):
@@ -66,8 +64,6 @@ def test_bvh_matches_reference_bitwise(ref, name, highquality):
 @pytest.mark.parametrize("highquality", [False, True])
 def test_bvh_refit_matches_reference_bitwise(ref, name, highquality):
     """ygl_bvh_update against update_scene_bvh (yocto_bvh.cpp:434-451) on the reference's own trees"""
-    if highquality and name == "hair":
-        pytest.skip("SAH on the large case is covered by the smaller scenes")
     scene = SCENES[name]()
     moved, updated = edited_copy(scene)
     mine = lib.Bvh(scene, highquality)
