@@ -59,7 +59,20 @@ def make_gltf(rng, d, stem):
         doc["images"], doc["textures"] = [], []
         for k in range(nimages):
             name = f"{stem} img{k}.png" if rng.random() < 0.3 else f"{stem}_img{k}.png"
-            (d / "tex" / name).write_bytes(make_png(rng, rng.randint(1, 6), rng.randint(1, 5), rng.choice([2, 6]), 8, 0))
+            data = make_png(rng, rng.randint(1, 6), rng.randint(1, 5), rng.choice([2, 6]), 8, 0)
+            if rng.random() < 0.5:      # glTF assets mostly carry JPEG textures
+                try:
+                    import io
+                    from PIL import Image
+                    out = io.BytesIO()
+                    jw, jh = rng.randint(1, 20), rng.randint(1, 20)
+                    pixels = np.array([[[rng.randrange(256) for _ in range(3)] for _ in range(jw)] for _ in range(jh)], np.uint8)
+                    Image.fromarray(pixels, "RGB").save(out, "JPEG", quality=rng.choice([30, 80, 95]), progressive=rng.random() < 0.3,
+                                                        subsampling=rng.choice([0, 1, 2]))
+                    name, data = name[:-4] + ".jpg", out.getvalue()
+                except ImportError:
+                    pass
+            (d / "tex" / name).write_bytes(data)
             doc["images"].append({"uri": "tex/" + name.replace(" ", "%20")})
             doc["textures"].append({"source": k})
     view = lambda: {"index": rng.randrange(nimages)} if nimages and rng.random() < 0.5 else None

@@ -207,3 +207,57 @@ def test_random_radiance_files_decode_like_stb_image(ref, tmp_path):
                        "orientation": b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n+Y 1 +X 1\n\0\0\0\0"}.items():
         ours, theirs = _both(ref, tmp_path, "bad.hdr", data)
         assert ours is None and theirs is None, (what, ours is None, theirs is None)
+
+
+def _jpeg_cases(rng, count):
+    """(bytes, description) of JPEG files written by Pillow and OpenCV: grey / RGB / CMYK, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 /
+    4:1:1 chroma layouts, baseline and progressive, default and optimised Huffman tables, restart intervals, sizes that
+    are not multiples of the MCU"""
+    import io
+    PIL = pytest.importorskip("PIL.Image")
+    cv2 = pytest.importorskip("cv2")
+    for k in range(count):
+        w, h = rng.choice([1, 2, 7, 8, 9, 15, 16, 17, 31, 33, 64, 70]), rng.choice([1, 3, 8, 9, 16, 17, 25, 40])
+        kind = rng.random()
+        smooth = np.add.outer(np.linspace(0, 255, h), np.linspace(0, 120, w))[..., None] % 256
+        noise = np.array([[[rng.randrange(256) for _ in range(4)] for _ in range(w)] for _ in range(h)], np.float64)
+        pixels = (smooth * 0.6 + noise * rng.choice([0.05, 0.4, 1.0])).clip(0, 255).astype(np.uint8)
+        quality = rng.choice([5, 30, 60, 75, 90, 100])
+        if kind < 0.6:
+            mode = rng.choice(["L", "RGB", "RGB", "RGB", "CMYK"])
+            channels = {"L": 1, "RGB": 3, "CMYK": 4}[mode]
+            image = PIL.fromarray(pixels[..., 0] if channels == 1 else pixels[..., :channels], mode)
+            options = dict(quality=quality, progressive=rng.random() < 0.4, optimize=rng.random() < 0.4)
+            if mode == "RGB":
+                options["subsampling"] = rng.choice([0, 1, 2])
+            if rng.random() < 0.3:
+                options["restart_marker_blocks"] = rng.choice([1, 2, 5])
+            out = io.BytesIO()
+            try:
+                image.save(out, "JPEG", **options)
+            except TypeError:
+                options.pop("restart_marker_blocks", None)
+                image.save(out, "JPEG", **options)
+            yield out.getvalue(), f"pillow {mode} {w}x{h} {options}"
+        else:
+            params = [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_PROGRESSIVE, int(rng.random() < 0.4),
+                      cv2.IMWRITE_JPEG_OPTIMIZE, int(rng.random() < 0.4), cv2.IMWRITE_JPEG_RST_INTERVAL, rng.choice([0, 0, 1, 3, 7])]
+            if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+                params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, rng.choice([0x411111, 0x221111, 0x211111, 0x121111, 0x111111])]
+            ok, data = cv2.imencode(".jpg", pixels[..., 0] if rng.random() < 0.2 else pixels[..., :3], params)
+            assert ok
+            yield data.tobytes(), f"opencv {w}x{h} {params}"
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_jpeg_files_decode_like_stb_image(ref, seed, tmp_path):
+    """Every texel of 120 JPEG files per seed against stb_image: its integer IDCT, its triangle-filter chroma upsampling
+    and its fixed-point YCbCr conversion are what 'the same image' means for this format."""
+    rng = random.Random(seed)
+    for k, (data, what) in enumerate(_jpeg_cases(rng, 120)):
+        ours, theirs = _both(ref, tmp_path, f"j{k}.jpg", data)
+        assert ours is not None and theirs is not None, (k, what, ours is None, theirs is None)
+        assert _same(ours, theirs), (k, what)
+    for what, data in {"no SOI": b"\xff\xd9", "truncated": data[:len(data) // 3], "text": b"not a jpeg at all"}.items():
+        ours, theirs = _both(ref, tmp_path, "bad.jpg", data)
+        assert ours is None and theirs is None, (what, ours is None, theirs is None)

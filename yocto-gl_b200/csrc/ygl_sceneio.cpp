@@ -9,7 +9,8 @@
 //   add_missing_camera / add_missing_radius          yocto_sceneio.cpp:2119-2148
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
 // Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
-// Shapes: .ply, .obj, binary .stl. Not built: glTF / pbrt / mitsuba / obj scenes, EXR / JPG textures: refused.
+// Shapes: .ply, .obj, binary .stl; textures .png, .jpg, .hdr; scenes .json, .ply, .gltf / .glb. Not built: pbrt / mitsuba /
+// obj scenes, EXR textures: refused.
 #include <sched.h>
 #include <sys/stat.h>
 #include <zlib.h>
@@ -1095,13 +1096,603 @@ bool load_png(const std::vector<uint8_t>& data, HostTexture& tex) {
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// JPEG -> byte rgba as stbi_load(..., 4) returns it. The format leaves the inverse DCT, the chroma upsampling and the
+// colour conversion to the decoder, so "the same bytes as the reference" means stb_image's choices (stb_image.h,
+// stbi__idct_block / stbi__resample_row_* / stbi__YCbCr_to_RGB_row; its SSE2 variants are written to match them
+// exactly): the 12-bit fixed-point "islow" IDCT with two extra bits between the passes, triangle-filter upsampling for
+// 2x factors (3:1 weights, rounded) and replication for the others, and the reduced-precision YCbCr -> RGB.
+// Baseline and progressive Huffman streams, 8-bit, 1 / 3 / 4 components, restart intervals, JFIF / Adobe markers.
+// ---------------------------------------------------------------------------------------------------------------
+class JpegDecoder {
+ public:
+  bool decode(const std::vector<uint8_t>& file, HostTexture& tex) {
+    at_ = file.data(), end_ = file.data() + file.size();
+    if (next_marker() != 0xD8) return false;  // SOI
+    int m = next_marker();
+    while (m != 0xC0 && m != 0xC1 && m != 0xC2) {  // tables and application segments up to the frame header
+      if (!segment(m)) return false;
+      m = next_marker();
+      while (m == kNoMarker) {
+        if (at_ >= end_) return false;
+        m = next_marker();
+      }
+    }
+    progressive_ = m == 0xC2;
+    if (!frame_header()) return false;
+    m = next_marker();
+    while (m != 0xD9) {  // until EOI
+      if (m == 0xDA) {
+        if (!scan_header() || !scan()) return false;
+        if (pending_ == kNoMarker) {  // zero padding after the entropy-coded data
+          while (at_ < end_) {
+            if (byte() == 255) {
+              pending_ = byte();
+              break;
+            }
+          }
+        }
+      } else if (m == 0xDC) {  // DNL
+        const int len = u16(), lines = u16();
+        if (len != 4 || lines != height_) return false;
+      } else if (!segment(m)) {
+        return false;
+      }
+      m = next_marker();
+    }
+    if (progressive_) finish_progressive();
+    return assemble(tex);
+  }
+
+ private:
+  static constexpr int kNoMarker = 0xff;
+  struct Huffman {
+    uint8_t  size[257], values[256];
+    uint16_t code[256];
+    unsigned maxcode[18];
+    int      delta[17];
+    bool build(const int* count) {  // canonical codes in symbol order
+      int k = 0;
+      for (int i = 0; i < 16; i++)
+        for (int j = 0; j < count[i]; j++) {
+          if (k >= 256) return false;
+          size[k++] = (uint8_t)(i + 1);
+        }
+      size[k] = 0;
+      unsigned next = 0;
+      k = 0;
+      for (int len = 1; len <= 16; len++) {
+        delta[len] = k - (int)next;
+        if (size[k] == len) {
+          while (size[k] == len) code[k++] = (uint16_t)(next++);
+          if (next - 1 >= (1u << len)) return false;
+        }
+        maxcode[len] = next << (16 - len);
+        next <<= 1;
+      }
+      maxcode[17] = 0xffffffff;
+      return true;
+    }
+  };
+  struct Component {
+    int id = 0, h = 0, v = 0, tq = 0, hd = 0, ha = 0, dc_pred = 0;
+    int x = 0, y = 0, w2 = 0, h2 = 0, coeff_w = 0;
+    std::vector<uint8_t> data;    // w2 x h2 samples
+    std::vector<int16_t> coeff;   // progressive: 64 per block
+  };
+
+  const uint8_t *at_ = nullptr, *end_ = nullptr;
+  int  pending_ = kNoMarker;  // a marker met inside entropy-coded data
+  bool progressive_ = false, jfif_ = false, no_more_ = false;
+  int  adobe_transform_ = -1, rgb_ids_ = 0;
+  int  width_ = 0, height_ = 0, ncomp_ = 0, h_max_ = 1, v_max_ = 1, mcu_x_ = 0, mcu_y_ = 0;
+  int  restart_interval_ = 0, todo_ = 0, eob_run_ = 0;
+  int  scan_n_ = 0, order_[4] = {}, spec_start_ = 0, spec_end_ = 0, succ_high_ = 0, succ_low_ = 0;
+  uint32_t  bits_ = 0;
+  int       nbits_ = 0;
+  uint16_t  dequant_[4][64] = {};
+  Huffman   dc_[4], ac_[4];
+  Component comp_[4];
+
+  int byte() { return at_ < end_ ? *at_++ : 0; }
+  int u16() {
+    const int hi = byte();
+    return hi << 8 | byte();
+  }
+  void skip(int n) { at_ = n < 0 || end_ - at_ < n ? end_ : at_ + n; }
+  int  next_marker() {
+    if (pending_ != kNoMarker) {
+      const int m = pending_;
+      pending_    = kNoMarker;
+      return m;
+    }
+    int x = byte();
+    if (x != 0xff) return kNoMarker;
+    while (x == 0xff) x = byte();
+    return x;
+  }
+  static int zigzag(int k) {
+    static const uint8_t order[64 + 15] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20,
+        13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60,
+        61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+    return order[k];
+  }
+
+  bool segment(int m) {
+    switch (m) {
+      case kNoMarker: return false;
+      case 0xDD:
+        if (u16() != 4) return false;
+        restart_interval_ = u16();
+        return true;
+      case 0xDB: {
+        int len = u16() - 2;
+        while (len > 0) {
+          const int q = byte(), wide = q >> 4, t = q & 15;
+          if ((wide != 0 && wide != 1) || t > 3) return false;
+          for (int i = 0; i < 64; i++) dequant_[t][zigzag(i)] = (uint16_t)(wide ? u16() : byte());
+          len -= wide ? 129 : 65;
+        }
+        return len == 0;
+      }
+      case 0xC4: {
+        int len = u16() - 2;
+        while (len > 0) {
+          const int q = byte(), cls = q >> 4, slot = q & 15;
+          if (cls > 1 || slot > 3) return false;
+          int sizes[16], n = 0;
+          for (int& sz : sizes) n += sz = byte();
+          len -= 17;
+          Huffman& table = cls == 0 ? dc_[slot] : ac_[slot];
+          if (!table.build(sizes)) return false;
+          for (int i = 0; i < n; i++) table.values[i] = (uint8_t)byte();
+          len -= n;
+        }
+        return len == 0;
+      }
+      default: break;
+    }
+    if ((m >= 0xE0 && m <= 0xEF) || m == 0xFE) {
+      int len = u16();
+      if (len < 2) return false;
+      len -= 2;
+      if (m == 0xE0 && len >= 5) {
+        bool ok = true;
+        for (char c : {'J', 'F', 'I', 'F', '\0'}) ok &= byte() == c;
+        len -= 5;
+        if (ok) jfif_ = true;
+      } else if (m == 0xEE && len >= 12) {
+        bool ok = true;
+        for (char c : {'A', 'd', 'o', 'b', 'e', '\0'}) ok &= byte() == c;
+        len -= 6;
+        if (ok) {
+          byte(), u16(), u16();
+          adobe_transform_ = byte();
+          len -= 6;
+        }
+      }
+      skip(len);
+      return true;
+    }
+    return false;
+  }
+
+  bool frame_header() {
+    const int len = u16();
+    if (len < 11 || byte() != 8) return false;
+    height_ = u16(), width_ = u16();
+    if (height_ == 0 || width_ == 0 || height_ > (1 << 24) || width_ > (1 << 24)) return false;
+    ncomp_ = byte();
+    if (ncomp_ != 1 && ncomp_ != 3 && ncomp_ != 4) return false;
+    if (len != 8 + 3 * ncomp_) return false;
+    for (int i = 0; i < ncomp_; i++) {
+      Component& c = comp_[i];
+      c.id         = byte();
+      if (ncomp_ == 3 && c.id == "RGB"[i]) rgb_ids_++;
+      const int q = byte();
+      c.h = q >> 4, c.v = q & 15, c.tq = byte();
+      if (!c.h || c.h > 4 || !c.v || c.v > 4 || c.tq > 3) return false;
+    }
+    if ((uint64_t)width_ * height_ * ncomp_ > (1u << 30)) return false;
+    for (int i = 0; i < ncomp_; i++) h_max_ = std::max(h_max_, comp_[i].h), v_max_ = std::max(v_max_, comp_[i].v);
+    for (int i = 0; i < ncomp_; i++)
+      if (h_max_ % comp_[i].h != 0 || v_max_ % comp_[i].v != 0) return false;
+    mcu_x_ = (width_ + h_max_ * 8 - 1) / (h_max_ * 8), mcu_y_ = (height_ + v_max_ * 8 - 1) / (v_max_ * 8);
+    for (int i = 0; i < ncomp_; i++) {
+      Component& c = comp_[i];
+      c.x = (width_ * c.h + h_max_ - 1) / h_max_, c.y = (height_ * c.v + v_max_ - 1) / v_max_;
+      c.w2 = mcu_x_ * c.h * 8, c.h2 = mcu_y_ * c.v * 8;  // whole MCUs: the surplus is cut at assembly
+      c.data.assign((size_t)c.w2 * c.h2, 0);
+      if (progressive_) c.coeff_w = c.w2 / 8, c.coeff.assign((size_t)c.w2 * c.h2, 0);
+    }
+    return true;
+  }
+
+  bool scan_header() {
+    const int len = u16();
+    scan_n_       = byte();
+    if (scan_n_ < 1 || scan_n_ > 4 || scan_n_ > ncomp_ || len != 6 + 2 * scan_n_) return false;
+    for (int i = 0; i < scan_n_; i++) {
+      const int id = byte(), q = byte();
+      int       which = 0;
+      while (which < ncomp_ && comp_[which].id != id) which++;
+      if (which == ncomp_) return false;
+      comp_[which].hd = q >> 4, comp_[which].ha = q & 15;
+      if (comp_[which].hd > 3 || comp_[which].ha > 3) return false;
+      order_[i] = which;
+    }
+    spec_start_ = byte(), spec_end_ = byte();
+    const int approx = byte();
+    succ_high_ = approx >> 4, succ_low_ = approx & 15;
+    if (progressive_) {
+      if (spec_start_ > 63 || spec_end_ > 63 || spec_start_ > spec_end_ || succ_high_ > 13 || succ_low_ > 13) return false;
+    } else {
+      if (spec_start_ != 0 || succ_high_ != 0 || succ_low_ != 0) return false;
+      spec_end_ = 63;
+    }
+    return true;
+  }
+
+  // ---- entropy-coded bits ----
+  void fill() {
+    do {
+      const unsigned b = no_more_ ? 0 : (unsigned)byte();
+      if (b == 0xff) {
+        int c = byte();
+        while (c == 0xff) c = byte();
+        if (c != 0) {
+          pending_ = c, no_more_ = true;
+          return;
+        }
+      }
+      bits_ |= b << (24 - nbits_);
+      nbits_ += 8;
+    } while (nbits_ <= 24);
+  }
+  int symbol(const Huffman& h) {
+    if (nbits_ < 16) fill();
+    const unsigned top = bits_ >> 16;
+    int            len = 1;
+    while (top >= h.maxcode[len]) len++;
+    if (len == 17) {
+      nbits_ -= 16;
+      return -1;
+    }
+    if (len > nbits_) return -1;
+    const int index = (int)((bits_ >> (32 - len)) & ((1u << len) - 1)) + h.delta[len];
+    if (index < 0 || index > 255) return -1;
+    nbits_ -= len, bits_ <<= len;
+    return h.values[index];
+  }
+  int take(int n) {  // n unsigned bits
+    if (n == 0) return 0;
+    if (nbits_ < n) fill();
+    const unsigned k = bits_ >> (32 - n);
+    bits_ <<= n, nbits_ -= n;
+    return (int)k;
+  }
+  int take_signed(int n) {  // "receive and extend"
+    if (n == 0) return 0;
+    if (nbits_ < n) fill();
+    const bool     positive = bits_ >> 31;
+    const unsigned k        = bits_ >> (32 - n);
+    bits_ <<= n, nbits_ -= n;
+    return (int)k + (positive ? 0 : (int)((~0u << n) + 1));
+  }
+  void reset() {
+    nbits_ = 0, bits_ = 0, no_more_ = false, pending_ = kNoMarker, eob_run_ = 0;
+    for (auto& c : comp_) c.dc_pred = 0;
+    todo_ = restart_interval_ ? restart_interval_ : 0x7fffffff;
+  }
+  bool restart_due() {  // after an MCU: true = the scan ends here (no restart marker where one is due)
+    if (--todo_ > 0) return false;
+    if (nbits_ < 24) fill();
+    if (!(pending_ >= 0xd0 && pending_ <= 0xd7)) return true;
+    reset();
+    return false;
+  }
+
+  bool block_baseline(int16_t* data, Component& c) {
+    const int t = symbol(dc_[c.hd]);
+    if (t < 0 || t > 15) return false;
+    memset(data, 0, 64 * sizeof(int16_t));
+    const uint16_t* dq = dequant_[c.tq];
+    c.dc_pred += take_signed(t);
+    data[0] = (int16_t)(c.dc_pred * dq[0]);
+    for (int k = 1; k < 64;) {
+      const int rs = symbol(ac_[c.ha]);
+      if (rs < 0) return false;
+      const int s = rs & 15, r = rs >> 4;
+      if (s == 0) {
+        if (rs != 0xf0) break;
+        k += 16;
+      } else {
+        k += r;
+        const int z = zigzag(k++);
+        data[z]     = (int16_t)(take_signed(s) * dq[z]);
+      }
+    }
+    return true;
+  }
+  bool block_dc_progressive(int16_t* data, Component& c) {
+    if (spec_end_ != 0) return false;
+    if (succ_high_ == 0) {
+      memset(data, 0, 64 * sizeof(int16_t));
+      const int t = symbol(dc_[c.hd]);
+      if (t < 0 || t > 15) return false;
+      c.dc_pred += take_signed(t);
+      data[0] = (int16_t)(c.dc_pred * (1 << succ_low_));
+    } else if (take(1)) {
+      data[0] += (int16_t)(1 << succ_low_);
+    }
+    return true;
+  }
+  void refine(int16_t& v, int16_t bit) {
+    if (take(1) && (v & bit) == 0) v = (int16_t)(v > 0 ? v + bit : v - bit);
+  }
+  bool block_ac_progressive(int16_t* data, Component& c) {
+    if (spec_start_ == 0) return false;
+    const Huffman& table = ac_[c.ha];
+    if (succ_high_ == 0) {
+      if (eob_run_) return --eob_run_, true;
+      int k = spec_start_;
+      do {
+        const int rs = symbol(table);
+        if (rs < 0) return false;
+        const int s = rs & 15, r = rs >> 4;
+        if (s == 0) {
+          if (r < 15) {
+            eob_run_ = (1 << r) + take(r) - 1;
+            break;
+          }
+          k += 16;
+        } else {
+          k += r;
+          data[zigzag(k++)] = (int16_t)(take_signed(s) * (1 << succ_low_));
+        }
+      } while (k <= spec_end_);
+      return true;
+    }
+    const int16_t bit = (int16_t)(1 << succ_low_);
+    if (eob_run_) {
+      --eob_run_;
+      for (int k = spec_start_; k <= spec_end_; k++)
+        if (int16_t& v = data[zigzag(k)]; v != 0) refine(v, bit);
+      return true;
+    }
+    int k = spec_start_;
+    do {
+      const int rs = symbol(table);
+      if (rs < 0) return false;
+      int s = rs & 15, r = rs >> 4;
+      if (s == 0) {
+        if (r < 15) {
+          eob_run_ = (1 << r) - 1 + take(r);
+          r        = 64;  // to the end of the band
+        }
+      } else {
+        if (s != 1) return false;
+        s = take(1) ? bit : -bit;
+      }
+      while (k <= spec_end_) {
+        int16_t& v = data[zigzag(k++)];
+        if (v != 0) {
+          refine(v, bit);
+        } else {
+          if (r == 0) {
+            v = (int16_t)s;
+            break;
+          }
+          --r;
+        }
+      }
+    } while (k <= spec_end_);
+    return true;
+  }
+
+  // 8x8 inverse DCT on dequantised coefficients, writing clamped samples
+  static void idct_1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7, int (&x)[4], int (&t)[4]) {
+    auto f = [](double v) { return (int)(v * 4096 + 0.5); };
+    int p2 = s2, p3 = s6;
+    int p1 = (p2 + p3) * f(0.5411961f);
+    int t2 = p1 + p3 * f(-1.847759065f), t3 = p1 + p2 * f(0.765366865f);
+    p2 = s0, p3 = s4;
+    int t0 = (p2 + p3) * 4096, t1 = (p2 - p3) * 4096;
+    x[0] = t0 + t3, x[3] = t0 - t3, x[1] = t1 + t2, x[2] = t1 - t2;
+    t0 = s7, t1 = s5, t2 = s3, t3 = s1;
+    p3 = t0 + t2;
+    int p4 = t1 + t3;
+    p1 = t0 + t3, p2 = t1 + t2;
+    const int p5 = (p3 + p4) * f(1.175875602f);
+    t0 = t0 * f(0.298631336f), t1 = t1 * f(2.053119869f), t2 = t2 * f(3.072711026f), t3 = t3 * f(1.501321110f);
+    p1 = p5 + p1 * f(-0.899976223f), p2 = p5 + p2 * f(-2.562915447f);
+    p3 = p3 * f(-1.961570560f), p4 = p4 * f(-0.390180644f);
+    t[3] = t3 + p1 + p4, t[2] = t2 + p2 + p3, t[1] = t1 + p2 + p4, t[0] = t0 + p1 + p3;
+  }
+  static uint8_t clamp8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
+  static void    idct(uint8_t* out, int stride, const int16_t* d) {
+    int val[64];
+    for (int i = 0; i < 8; i++) {  // columns, keeping two extra bits
+      const int16_t* c = d + i;
+      int*           v = val + i;
+      if (c[8] == 0 && c[16] == 0 && c[24] == 0 && c[32] == 0 && c[40] == 0 && c[48] == 0 && c[56] == 0) {
+        const int dc = c[0] * 4;
+        for (int r = 0; r < 8; r++) v[r * 8] = dc;
+        continue;
+      }
+      int x[4], t[4];
+      idct_1d(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56], x, t);
+      for (int& e : x) e += 512;
+      v[0] = (x[0] + t[3]) >> 10, v[56] = (x[0] - t[3]) >> 10, v[8] = (x[1] + t[2]) >> 10, v[48] = (x[1] - t[2]) >> 10;
+      v[16] = (x[2] + t[1]) >> 10, v[40] = (x[2] - t[1]) >> 10, v[24] = (x[3] + t[0]) >> 10, v[32] = (x[3] - t[0]) >> 10;
+    }
+    for (int i = 0; i < 8; i++, out += stride) {  // rows: remove 2^17, centre on 128
+      const int* v = val + i * 8;
+      int        x[4], t[4];
+      idct_1d(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], x, t);
+      for (int& e : x) e += 65536 + (128 << 17);
+      out[0] = clamp8((x[0] + t[3]) >> 17), out[7] = clamp8((x[0] - t[3]) >> 17), out[1] = clamp8((x[1] + t[2]) >> 17);
+      out[6] = clamp8((x[1] - t[2]) >> 17), out[2] = clamp8((x[2] + t[1]) >> 17), out[5] = clamp8((x[2] - t[1]) >> 17);
+      out[3] = clamp8((x[3] + t[0]) >> 17), out[4] = clamp8((x[3] - t[0]) >> 17);
+    }
+  }
+
+  bool scan() {
+    reset();
+    int16_t block[64];
+    auto    one = [&](Component& c, int bx, int by) {  // the block at (bx, by) of component c
+      if (!progressive_) {
+        if (!block_baseline(block, c)) return false;
+        idct(&c.data[(size_t)c.w2 * by * 8 + bx * 8], c.w2, block);
+        return true;
+      }
+      int16_t* data = &c.coeff[64 * ((size_t)bx + (size_t)by * c.coeff_w)];
+      return spec_start_ == 0 ? block_dc_progressive(data, c) : block_ac_progressive(data, c);
+    };
+    if (scan_n_ == 1) {  // one component: its own blocks in raster order
+      Component& c = comp_[order_[0]];
+      const int  w = (c.x + 7) >> 3, h = (c.y + 7) >> 3;
+      for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+          if (!one(c, i, j)) return false;
+          if (restart_due()) return true;
+        }
+      return true;
+    }
+    for (int j = 0; j < mcu_y_; j++)  // interleaved MCUs
+      for (int i = 0; i < mcu_x_; i++) {
+        for (int k = 0; k < scan_n_; k++) {
+          Component& c = comp_[order_[k]];
+          for (int y = 0; y < c.v; y++)
+            for (int x = 0; x < c.h; x++) {
+              if (progressive_ && spec_start_ != 0) return false;  // AC scans carry one component
+              if (!one(c, i * c.h + x, j * c.v + y)) return false;
+            }
+        }
+        if (restart_due()) return true;
+      }
+    return true;
+  }
+  void finish_progressive() {
+    for (int n = 0; n < ncomp_; n++) {
+      Component& c = comp_[n];
+      const int  w = (c.x + 7) >> 3, h = (c.y + 7) >> 3;
+      for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+          int16_t* data = &c.coeff[64 * ((size_t)i + (size_t)j * c.coeff_w)];
+          for (int k = 0; k < 64; k++) data[k] = (int16_t)(data[k] * dequant_[c.tq][k]);
+          idct(&c.data[(size_t)c.w2 * j * 8 + i * 8], c.w2, data);
+        }
+    }
+  }
+
+  // ---- full-resolution rows: 2x factors by the 3:1 triangle filter, others by replication ----
+  static const uint8_t* upsample(uint8_t* out, const uint8_t* near, const uint8_t* far, int w, int hs, int vs) {
+    if (hs == 1 && vs == 1) return near;
+    if (hs == 1 && vs == 2) {
+      for (int i = 0; i < w; i++) out[i] = (uint8_t)((3 * near[i] + far[i] + 2) >> 2);
+    } else if (hs == 2 && vs == 1) {
+      if (w == 1) return out[0] = out[1] = near[0], out;
+      out[0] = near[0], out[1] = (uint8_t)((near[0] * 3 + near[1] + 2) >> 2);
+      for (int i = 1; i < w - 1; i++) {
+        const int n    = 3 * near[i] + 2;
+        out[i * 2]     = (uint8_t)((n + near[i - 1]) >> 2);
+        out[i * 2 + 1] = (uint8_t)((n + near[i + 1]) >> 2);
+      }
+      out[(w - 1) * 2] = (uint8_t)((near[w - 2] * 3 + near[w - 1] + 2) >> 2), out[(w - 1) * 2 + 1] = near[w - 1];
+    } else if (hs == 2 && vs == 2) {
+      if (w == 1) return out[0] = out[1] = (uint8_t)((3 * near[0] + far[0] + 2) >> 2), out;
+      int t1 = 3 * near[0] + far[0];
+      out[0] = (uint8_t)((t1 + 2) >> 2);
+      for (int i = 1; i < w; i++) {
+        const int t0   = t1;
+        t1             = 3 * near[i] + far[i];
+        out[i * 2 - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
+        out[i * 2]     = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+      }
+      out[w * 2 - 1] = (uint8_t)((t1 + 2) >> 2);
+    } else {
+      for (int i = 0; i < w; i++)
+        for (int j = 0; j < hs; j++) out[i * hs + j] = near[i];
+    }
+    return out;
+  }
+  static void ycc_to_rgb(uint8_t* out, const uint8_t* y, const uint8_t* pcb, const uint8_t* pcr, int count) {
+    auto fixed = [](float v) { return ((int)(v * 4096.0f + 0.5f)) << 8; };
+    for (int i = 0; i < count; i++, out += 4) {
+      const int luma = (y[i] << 20) + (1 << 19), cr = pcr[i] - 128, cb = pcb[i] - 128;
+      int       r    = luma + cr * fixed(1.40200f);
+      int       g    = luma + (cr * -fixed(0.71414f)) + (int)((unsigned)(cb * -fixed(0.34414f)) & 0xffff0000u);
+      int       b    = luma + cb * fixed(1.77200f);
+      out[0] = clamp8(r >> 20), out[1] = clamp8(g >> 20), out[2] = clamp8(b >> 20), out[3] = 255;
+    }
+  }
+  static uint8_t scale8(uint8_t x, uint8_t y) {  // x * y / 255, rounded
+    const unsigned t = x * y + 128;
+    return (uint8_t)((t + (t >> 8)) >> 8);
+  }
+  bool assemble(HostTexture& tex) {
+    const bool is_rgb = ncomp_ == 3 && (rgb_ids_ == 3 || (adobe_transform_ == 0 && !jfif_));
+    struct Plane {
+      int                  hs, vs, ystep, w_lores, ypos;
+      const uint8_t *      line0, *line1;
+      std::vector<uint8_t> row;
+    } plane[4];
+    for (int k = 0; k < ncomp_; k++) {
+      Plane& p  = plane[k];
+      p.hs = h_max_ / comp_[k].h, p.vs = v_max_ / comp_[k].v, p.ystep = p.vs >> 1;
+      p.w_lores = (width_ + p.hs - 1) / p.hs, p.ypos = 0;
+      p.line0 = p.line1 = comp_[k].data.data();
+      p.row.resize((size_t)width_ + 3 + 8);
+    }
+    tex.width = width_, tex.height = height_;
+    tex.pixelsb.resize((size_t)width_ * height_ * 4);
+    for (int j = 0; j < height_; j++) {
+      uint8_t*       out = &tex.pixelsb[(size_t)j * width_ * 4];
+      const uint8_t* rows[4] = {};
+      for (int k = 0; k < ncomp_; k++) {
+        Plane&     p      = plane[k];
+        const bool bottom = p.ystep >= (p.vs >> 1);
+        rows[k]           = upsample(p.row.data(), bottom ? p.line1 : p.line0, bottom ? p.line0 : p.line1, p.w_lores, p.hs, p.vs);
+        if (++p.ystep >= p.vs) {
+          p.ystep = 0, p.line0 = p.line1;
+          if (++p.ypos < comp_[k].y) p.line1 += comp_[k].w2;
+        }
+      }
+      if (ncomp_ == 3 && is_rgb) {
+        for (int i = 0; i < width_; i++) out[4 * i] = rows[0][i], out[4 * i + 1] = rows[1][i], out[4 * i + 2] = rows[2][i], out[4 * i + 3] = 255;
+      } else if (ncomp_ == 3) {
+        ycc_to_rgb(out, rows[0], rows[1], rows[2], width_);
+      } else if (ncomp_ == 4 && adobe_transform_ == 0) {  // CMYK
+        for (int i = 0; i < width_; i++) {
+          const uint8_t m = rows[3][i];
+          out[4 * i] = scale8(rows[0][i], m), out[4 * i + 1] = scale8(rows[1][i], m), out[4 * i + 2] = scale8(rows[2][i], m), out[4 * i + 3] = 255;
+        }
+      } else if (ncomp_ == 4) {
+        ycc_to_rgb(out, rows[0], rows[1], rows[2], width_);
+        if (adobe_transform_ == 2)  // YCCK
+          for (int i = 0; i < width_; i++) {
+            const uint8_t m = rows[3][i];
+            for (int c = 0; c < 3; c++) out[4 * i + c] = scale8((uint8_t)(255 - out[4 * i + c]), m);
+          }
+      } else {
+        for (int i = 0; i < width_; i++) out[4 * i] = out[4 * i + 1] = out[4 * i + 2] = rows[0][i], out[4 * i + 3] = 255;
+      }
+    }
+    return true;
+  }
+};
+
 // load_texture, yocto_sceneio.cpp:1796-1837: the file type decides `linear`; nearest / clamp come from the JSON
 bool load_texture(const std::string& filename, HostTexture& tex, std::string& error) {
   const auto ext = path_extension(filename);
-  if (ext != ".hdr" && ext != ".png") return error = "unsupported format " + filename, false;
+  if (ext != ".hdr" && ext != ".png" && ext != ".jpg" && ext != ".jpeg") return error = "unsupported format " + filename, false;
   std::vector<uint8_t> data;
   if (!read_file(filename, data, error)) return false;
-  if (ext == ".hdr") {
+  if (ext == ".jpg" || ext == ".jpeg") {
+    if (!JpegDecoder().decode(data, tex)) return error = "cannot raed " + filename, false;
+    tex.linear = 0;
+  } else if (ext == ".hdr") {
     if (!load_hdr(data, tex)) return error = "cannot raed " + filename, false;  // (the reference's own spelling)
     tex.linear = 1;
   } else {
