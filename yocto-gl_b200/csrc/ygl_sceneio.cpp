@@ -1683,15 +1683,212 @@ class JpegDecoder {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// OpenEXR -> float rgba as tinyexr's LoadEXR returns it (exts/tinyexr/tinyexr.h:11607-11860, what load_texture calls
+// for .exr): single-part scanline files, channels of type half (widened exactly), float, or uint (whose bits are then
+// read as a float, like there), compression none / RLE / ZIPS / ZIP (zlib or run lengths, then the byte predictor and
+// the two-halves interleave; a block whose stored size equals its raw size is taken as raw). R, G, B (+ A, else 1) are
+// picked by name among the first four channels; a single channel fills all four components. Lines of a
+// decreasing-Y file land mirrored, as in tinyexr. Tiled, multi-part, deep and PIZ / PXR24 / B44 / DWA files are refused.
+// ---------------------------------------------------------------------------------------------------------------
+float half_bits_to_float(uint16_t h) {
+  uint32_t sign = (uint32_t)(h & 0x8000) << 16, exponent = (h >> 10) & 31, mantissa = h & 0x3ff, bits;
+  if (exponent == 31) {
+    bits = sign | 0x7f800000u | (mantissa << 13);  // infinity, or a NaN that keeps its payload
+  } else if (exponent != 0) {
+    bits = sign | ((exponent + 112) << 23) | (mantissa << 13);
+  } else if (mantissa == 0) {
+    bits = sign;
+  } else {  // a subnormal half is a normal float
+    int shift = 0;
+    while (!(mantissa & 0x400)) mantissa <<= 1, shift++;
+    bits = sign | ((uint32_t)(113 - shift) << 23) | ((mantissa & 0x3ff) << 13);
+  }
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+bool load_exr(const std::vector<uint8_t>& file, HostTexture& tex) {
+  const uint8_t *p = file.data(), *end = p + file.size();
+  auto i32 = [&](const uint8_t* at) { int32_t v; memcpy(&v, at, 4); return v; };
+  if (file.size() < 8 || i32(p) != 20000630 || p[4] != 2) return false;
+  const uint32_t flags = (uint32_t)i32(p + 4) >> 8;  // 0x2 tiled, 0x4 long names, 0x8 deep, 0x10 multi-part
+  if (flags & (0x2 | 0x8 | 0x10)) return false;
+  p += 8;
+  struct Channel {
+    std::string name;
+    int         type = 0, bytes = 0;
+    size_t      offset = 0;
+  };
+  std::vector<Channel> channels;
+  int  compression = -1, line_order = 0, window[4] = {0, 0, -1, -1};
+  bool have_window = false;
+  while (true) {  // attributes: name\0 type\0 size data
+    if (p >= end) return false;
+    if (*p == 0) {
+      p++;
+      break;
+    }
+    const uint8_t* z = (const uint8_t*)memchr(p, 0, end - p);
+    if (!z) return false;
+    const std::string name((const char*)p, (const char*)z);
+    p = z + 1;
+    z = (const uint8_t*)memchr(p, 0, end - p);
+    if (!z) return false;
+    const std::string type((const char*)p, (const char*)z);
+    p = z + 1;
+    if (end - p < 4) return false;
+    const int64_t size = i32(p);
+    p += 4;
+    if (size < 0 || end - p < size) return false;
+    if (name == "channels") {
+      const uint8_t *c = p, *cend = p + size;
+      while (c < cend && *c) {
+        const uint8_t* cz = (const uint8_t*)memchr(c, 0, cend - c);
+        if (!cz || cend - cz < 17) return false;
+        Channel ch;
+        ch.name = std::string((const char*)c, (const char*)cz);
+        ch.type = i32(cz + 1);
+        if (ch.type < 0 || ch.type > 2) return false;
+        if (i32(cz + 9) != 1 || i32(cz + 13) != 1) return false;  // subsampled channels
+        ch.bytes = ch.type == 1 ? 2 : 4;
+        channels.push_back(ch);
+        c = cz + 17;
+      }
+    } else if (name == "compression") {
+      if (size < 1) return false;
+      compression = p[0];
+    } else if (name == "dataWindow") {
+      if (size < 16) return false;
+      for (int k = 0; k < 4; k++) window[k] = i32(p + 4 * k);
+      have_window = true;
+    } else if (name == "lineOrder") {
+      if (size < 1) return false;
+      line_order = p[0];
+    }
+    p += size;
+  }
+  if (channels.empty() || !have_window || compression < 0 || compression > 3) return false;
+  if (window[2] < window[0] || window[3] < window[1]) return false;
+  const int64_t width = (int64_t)window[2] - window[0] + 1, height = (int64_t)window[3] - window[1] + 1;
+  if (width > (1 << 23) || height > (1 << 23) || width * height > (int64_t(1) << 28)) return false;
+  size_t pixel_bytes = 0;
+  for (auto& ch : channels) ch.offset = pixel_bytes, pixel_bytes += ch.bytes;
+  const int    block_lines = compression == 3 ? 16 : 1;
+  const size_t num_blocks  = (size_t)((height + block_lines - 1) / block_lines);
+  if ((size_t)(end - p) < num_blocks * 8) return false;
+  // every channel as 32-bit words (floats, or the uint's bits)
+  std::vector<std::vector<uint32_t>> planes(channels.size(), std::vector<uint32_t>((size_t)(width * height), 0));
+  std::vector<uint8_t> raw, scratch;
+  for (size_t b = 0; b < num_blocks; b++) {
+    uint64_t offset;
+    memcpy(&offset, p + 8 * b, 8);
+    if (offset >= file.size() || file.size() - offset < 8) return false;
+    const uint8_t* chunk = file.data() + offset;
+    int64_t        line  = i32(chunk);
+    const int64_t  stored = i32(chunk + 4);
+    if (stored <= 0 || (uint64_t)stored > file.size() - offset - 8) return false;
+    if (line > (2 << 20) || line < -(2 << 20)) return false;
+    const int64_t last = std::min<int64_t>(line + block_lines, (int64_t)window[3] + 1);
+    const int64_t lines = last - line;
+    line -= window[1];
+    if (lines <= 0 || line < 0 || line + lines > height) return false;
+    const size_t size = (size_t)(width * lines) * pixel_bytes;
+    raw.resize(size);
+    const uint8_t* src = chunk + 8;
+    if (compression == 0 || (size_t)stored == size) {
+      if ((size_t)stored < size) return false;
+      memcpy(raw.data(), src, size);
+    } else {
+      scratch.resize(size);
+      if (compression == 1) {  // run lengths
+        if (stored <= 2) return false;
+        size_t  out = 0;
+        int64_t in  = 0;
+        while (in < stored) {
+          const int8_t code = (int8_t)src[in++];
+          if (code < 0) {
+            const size_t count = (size_t)(-(int)code);
+            if (out + count > size || in + (int64_t)count > stored) return false;
+            memcpy(&scratch[out], src + in, count);
+            out += count, in += (int64_t)count;
+          } else {
+            const size_t count = (size_t)code + 1;
+            if (out + count > size || in >= stored) return false;
+            memset(&scratch[out], src[in++], count);
+            out += count;
+          }
+        }
+        if (out != size) return false;
+      } else {
+        uLongf got = (uLongf)size;
+        if (uncompress(scratch.data(), &got, src, (uLong)stored) != Z_OK) return false;
+        // (a shorter result leaves the tail as it is: zeros)
+        if (got < size) memset(&scratch[got], 0, size - got);
+      }
+      for (size_t i = 1; i < size; i++) scratch[i] = (uint8_t)(scratch[i - 1] + scratch[i] - 128);  // predictor
+      const size_t half = (size + 1) / 2;                                                            // interleave
+      for (size_t i = 0; i < size; i++) raw[i] = scratch[(i & 1) ? half + i / 2 : i / 2];
+    }
+    for (size_t c = 0; c < channels.size(); c++)
+      for (int64_t v = 0; v < lines; v++) {
+        const uint8_t* row = &raw[(size_t)v * pixel_bytes * (size_t)width + channels[c].offset * (size_t)width];
+        const int64_t  y   = line_order == 0 ? line + v : height - 1 - (line + v);
+        uint32_t*      dst = &planes[c][(size_t)(y * width)];
+        if (channels[c].type == 1) {
+          for (int64_t u = 0; u < width; u++) {
+            uint16_t h;
+            memcpy(&h, row + 2 * u, 2);
+            const float f = half_bits_to_float(h);
+            memcpy(&dst[u], &f, 4);
+          }
+        } else {
+          memcpy(dst, row, (size_t)width * 4);
+        }
+      }
+  }
+  // LoadEXR's channel choice: names among the first four channels of the default layer (names without a '.')
+  std::vector<size_t> layer;
+  for (size_t c = 0; c < channels.size(); c++)
+    if (channels[c].name.find('.') == std::string::npos) layer.push_back(c);
+  if (layer.empty()) return false;
+  int r = -1, g = -1, b = -1, a = -1;
+  for (size_t k = 0; k < layer.size() && k < 4; k++) {
+    const auto& name = channels[layer[k]].name;
+    if (name == "R") r = (int)layer[k];
+    else if (name == "G") g = (int)layer[k];
+    else if (name == "B") b = (int)layer[k];
+    else if (name == "A") a = (int)layer[k];
+  }
+  tex.width = (int)width, tex.height = (int)height;
+  tex.pixelsf.resize((size_t)(width * height) * 4);
+  const float one = 1.0f;
+  uint32_t    one_bits;
+  memcpy(&one_bits, &one, 4);
+  uint32_t* out = (uint32_t*)tex.pixelsf.data();
+  if (layer.size() == 1) {
+    const auto& plane = planes[layer[0]];
+    for (size_t i = 0; i < plane.size(); i++) out[4 * i] = out[4 * i + 1] = out[4 * i + 2] = out[4 * i + 3] = plane[i];
+    return true;
+  }
+  if (r < 0 || g < 0 || b < 0) return false;
+  for (size_t i = 0; i < (size_t)(width * height); i++)
+    out[4 * i] = planes[r][i], out[4 * i + 1] = planes[g][i], out[4 * i + 2] = planes[b][i], out[4 * i + 3] = a >= 0 ? planes[a][i] : one_bits;
+  return true;
+}
+
 // load_texture, yocto_sceneio.cpp:1796-1837: the file type decides `linear`; nearest / clamp come from the JSON
 bool load_texture(const std::string& filename, HostTexture& tex, std::string& error) {
   const auto ext = path_extension(filename);
-  if (ext != ".hdr" && ext != ".png" && ext != ".jpg" && ext != ".jpeg") return error = "unsupported format " + filename, false;
+  if (ext != ".hdr" && ext != ".png" && ext != ".jpg" && ext != ".jpeg" && ext != ".exr") return error = "unsupported format " + filename, false;
   std::vector<uint8_t> data;
   if (!read_file(filename, data, error)) return false;
   if (ext == ".jpg" || ext == ".jpeg") {
     if (!JpegDecoder().decode(data, tex)) return error = "cannot raed " + filename, false;
     tex.linear = 0;
+  } else if (ext == ".exr") {
+    if (!load_exr(data, tex)) return error = "cannot raed " + filename, false;
+    tex.linear = 1;
   } else if (ext == ".hdr") {
     if (!load_hdr(data, tex)) return error = "cannot raed " + filename, false;  // (the reference's own spelling)
     tex.linear = 1;
