@@ -265,15 +265,16 @@ def test_jpeg_files_decode_like_stb_image(ref, seed, tmp_path):
 
 def test_exr_files_decode_like_tinyexr(ref, tmp_path):
     """OpenEXR scanline files written by OpenCV - half and float channels, 1 / 3 / 4 channels, compression none / RLE / ZIPS
-    / ZIP, sizes around the 16-line ZIP blocks - against tinyexr's LoadEXR: every float bit-identical (half -> float is
+    / ZIP / PIZ, sizes around the 16-line ZIP and 32-line PIZ blocks, values that exercise both PIZ lifting steps - against
+    tinyexr's LoadEXR: every float bit-identical (half -> float is
     exact, including subnormals, infinities and NaN payloads). And the reference's own sky1.exr (2048 x 1024, ZIP, half)."""
     os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
     cv2 = pytest.importorskip("cv2")
     import scene_data
     rng = random.Random(31)
     done = 0
-    for k in range(60):
-        w, h = rng.choice([1, 2, 5, 16, 17, 40]), rng.choice([1, 3, 15, 16, 17, 33, 50])
+    for k in range(90):
+        w, h = rng.choice([1, 2, 5, 16, 17, 40, 130]), rng.choice([1, 3, 15, 16, 17, 33, 50, 70])
         channels = rng.choice([1, 3, 4])
         pixels = np.array([[[rng.choice([0.0, 1.0, -2.5, 6.1e-5, 1e-7, 65504.0, 1e6, float("inf"), rng.uniform(-10, 10), rng.random()])
                              for _ in range(channels)] for _ in range(w)] for _ in range(h)], np.float32)
@@ -281,7 +282,8 @@ def test_exr_files_decode_like_tinyexr(ref, tmp_path):
             pixels = pixels[..., 0]
         params = [cv2.IMWRITE_EXR_TYPE, rng.choice([cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_TYPE_FLOAT]),
                   cv2.IMWRITE_EXR_COMPRESSION, rng.choice([cv2.IMWRITE_EXR_COMPRESSION_NO, cv2.IMWRITE_EXR_COMPRESSION_RLE,
-                                                           cv2.IMWRITE_EXR_COMPRESSION_ZIPS, cv2.IMWRITE_EXR_COMPRESSION_ZIP])]
+                                                           cv2.IMWRITE_EXR_COMPRESSION_ZIPS, cv2.IMWRITE_EXR_COMPRESSION_ZIP,
+                                                           cv2.IMWRITE_EXR_COMPRESSION_PIZ, cv2.IMWRITE_EXR_COMPRESSION_PIZ])]
         with np.errstate(over="ignore"):
             ok, data = cv2.imencode(".exr", pixels, params)
         if not ok:
@@ -290,11 +292,12 @@ def test_exr_files_decode_like_tinyexr(ref, tmp_path):
         assert ours is not None and theirs is not None, (k, w, h, channels, params, ours is None, theirs is None)
         assert _same(ours, theirs), (k, w, h, channels, params)
         done += 1
-    assert done == 60
-    for what, params in {"piz": [cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ]}.items():
+    assert done == 90
+    for what, params in {"pxr24": [cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PXR24],
+                         "b44": [cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_B44]}.items():
         ok, data = cv2.imencode(".exr", np.ones((20, 20, 3), np.float32), params)
-        ours, _ = _both(ref, tmp_path, "piz.exr", data.tobytes())
-        assert ours is None        # (tinyexr reads PIZ; this reader refuses it and says so)
+        ours, theirs = _both(ref, tmp_path, what + ".exr", data.tobytes())
+        assert ours is None and theirs is None, what       # codecs tinyexr does not carry either
     sky = os.path.join("/root/reference/tests/_data/textures/sky1.exr")
     if os.path.exists(sky):
         ours, theirs = _both(ref, tmp_path, "sky1.exr", open(sky, "rb").read())

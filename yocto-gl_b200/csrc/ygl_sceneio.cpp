@@ -9,8 +9,8 @@
 //   add_missing_camera / add_missing_radius          yocto_sceneio.cpp:2119-2148
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
 // Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
-// Shapes: .ply, .obj, binary .stl; textures .png, .jpg, .hdr; scenes .json, .ply, .gltf / .glb. Not built: pbrt / mitsuba /
-// obj scenes, EXR textures: refused.
+// Shapes: .ply, .obj, binary .stl; textures .png, .jpg, .hdr, .exr; scenes .json, .ply, .gltf / .glb. Not built: pbrt /
+// mitsuba / obj scenes, tiled EXR: refused.
 #include <sched.h>
 #include <sys/stat.h>
 #include <zlib.h>
@@ -1687,9 +1687,10 @@ class JpegDecoder {
 // OpenEXR -> float rgba as tinyexr's LoadEXR returns it (exts/tinyexr/tinyexr.h:11607-11860, what load_texture calls
 // for .exr): single-part scanline files, channels of type half (widened exactly), float, or uint (whose bits are then
 // read as a float, like there), compression none / RLE / ZIPS / ZIP (zlib or run lengths, then the byte predictor and
-// the two-halves interleave; a block whose stored size equals its raw size is taken as raw). R, G, B (+ A, else 1) are
+// the two-halves interleave) / PIZ (below); a block whose stored size equals its raw size is taken as raw. R, G, B (+ A, else 1) are
 // picked by name among the first four channels; a single channel fills all four components. Lines of a
-// decreasing-Y file land mirrored, as in tinyexr. Tiled, multi-part, deep and PIZ / PXR24 / B44 / DWA files are refused.
+// decreasing-Y file land mirrored, as in tinyexr. Tiled, multi-part, deep and PXR24 / B44 / DWA files are refused (the
+// last three by tinyexr too).
 // ---------------------------------------------------------------------------------------------------------------
 float half_bits_to_float(uint16_t h) {
   uint32_t sign = (uint32_t)(h & 0x8000) << 16, exponent = (h >> 10) & 31, mantissa = h & 0x3ff, bits;
@@ -1708,6 +1709,224 @@ float half_bits_to_float(uint16_t h) {
   memcpy(&f, &bits, 4);
   return f;
 }
+// PIZ blocks (OpenEXR's lossless wavelet codec, 32 lines per block): [min, max of the 16-bit values in use][that slice
+// of the 65536-bit "value in use" bitmap][length][Huffman data]. The 16-bit words of the block - every channel as a plane,
+// a float as two interleaved words - are Huffman coded (canonical codes of up to 58 bits whose lengths arrive as a
+// run-length packed 6-bit table; the last symbol in use means "repeat the previous word n times"), Haar-wavelet
+// transformed level by level with the 14-bit (or, above 2^14 values in use, the 16-bit modulo) lifting step, and mapped
+// through the bitmap's ranking. The codec is lossless: any correct decoder returns tinyexr's bytes.
+struct PizHuffman {
+  static constexpr int kSymbols = 65537, kFastBits = 14;
+  std::vector<uint8_t>  length;                // per symbol
+  std::vector<uint32_t> fast;                  // kFastBits-bit prefix -> symbol << 6 | length, 0 = longer code
+  uint64_t              first[60] = {};        // lowest code of each length
+  uint32_t              count[60] = {}, base[60] = {};
+  std::vector<uint32_t> by_length;             // symbols ordered by (length, symbol)
+  bool unpack(const uint8_t*& p, const uint8_t* end, int lo, int hi) {
+    length.assign(kSymbols, 0);
+    uint64_t acc = 0;
+    int      have = 0;
+    auto bits = [&](int n, int& v) {
+      while (have < n) {
+        if (p >= end) return false;
+        acc = (acc << 8) | *p++, have += 8;
+      }
+      have -= n;
+      v = (int)((acc >> have) & ((1u << n) - 1));
+      return true;
+    };
+    for (int s = lo; s <= hi; s++) {
+      int l;
+      if (!bits(6, l)) return false;
+      if (l == 63) {  // a long run of unused symbols
+        int run;
+        if (!bits(8, run)) return false;
+        run += 6;
+        if (s + run > hi + 1) return false;
+        s += run - 1;
+      } else if (l >= 59) {  // a short run
+        const int run = l - 59 + 2;
+        if (s + run > hi + 1) return false;
+        s += run - 1;
+      } else {
+        length[s] = (uint8_t)l;
+      }
+    }
+    // canonical codes: shorter codes are numerically higher, equal lengths ascend with the symbol
+    uint64_t n[60] = {};
+    for (int s = 0; s < kSymbols; s++) n[length[s]]++;
+    uint64_t c = 0;
+    for (int l = 58; l > 0; l--) {
+      const uint64_t next = (c + n[l]) >> 1;
+      count[l] = (uint32_t)n[l], first[l] = c;
+      c = next;
+    }
+    uint32_t at = 0;
+    for (int l = 1; l <= 58; l++) base[l] = at, at += count[l];
+    by_length.assign(at, 0);
+    uint32_t fill[60] = {};
+    fast.assign((size_t)1 << kFastBits, 0);
+    for (int s = 0; s < kSymbols; s++) {
+      const int l = length[s];
+      if (!l) continue;
+      const uint32_t rank = fill[l]++;
+      by_length[base[l] + rank] = (uint32_t)s;
+      if (l <= kFastBits) {
+        const uint64_t code = first[l] + rank;
+        const size_t   from = (size_t)(code << (kFastBits - l)), span = (size_t)1 << (kFastBits - l);
+        if (from + span > fast.size()) return false;
+        for (size_t k = 0; k < span; k++) fast[from + k] = ((uint32_t)s << 6) | (uint32_t)l;
+      }
+    }
+    return true;
+  }
+};
+bool piz_huffman_decode(const uint8_t* data, size_t size, std::vector<uint16_t>& out) {
+  if (size < 20) return false;
+  auto u32 = [&](size_t at) { uint32_t v; memcpy(&v, data + at, 4); return v; };
+  const uint32_t lo = u32(0), hi = u32(4), nbits = u32(12);
+  if (lo >= 65537 || hi >= 65537) return false;
+  const uint8_t *p = data + 20, *end = data + size;
+  PizHuffman     table;
+  if (!table.unpack(p, end, (int)lo, (int)hi)) return false;
+  if ((uint64_t)nbits > (uint64_t)(end - p) * 8) return false;
+  // MSB-first bit reader over exactly nbits bits
+  uint64_t acc = 0, used = 0;
+  int      have = 0;
+  auto refill = [&]() {
+    while (have <= 56 && p < end) acc |= (uint64_t)*p++ << (56 - have), have += 8;
+  };
+  size_t written = 0;
+  while (used < nbits) {
+    refill();
+    uint32_t symbol;
+    int      l;
+    const uint32_t quick = table.fast[acc >> (64 - PizHuffman::kFastBits)];
+    if (quick) {
+      symbol = quick >> 6, l = (int)(quick & 63);
+    } else {
+      l = PizHuffman::kFastBits + 1;
+      for (;; l++) {
+        if (l > 58) return false;
+        const uint64_t code = acc >> (64 - l);
+        if (table.count[l] && code >= table.first[l] && code - table.first[l] < table.count[l]) {
+          symbol = table.by_length[table.base[l] + (uint32_t)(code - table.first[l])];
+          break;
+        }
+      }
+    }
+    if (used + (uint64_t)l > nbits) return false;
+    acc <<= l, have -= l, used += (uint64_t)l;
+    if (symbol == hi) {  // the run-length symbol: eight more bits give the count
+      refill();
+      if (used + 8 > nbits) return false;
+      const unsigned run = (unsigned)(acc >> 56);
+      acc <<= 8, have -= 8, used += 8;
+      if (written == 0 || written + run > out.size()) return false;
+      for (unsigned k = 0; k < run; k++) out[written + k] = out[written - 1];
+      written += run;
+    } else {
+      if (written >= out.size()) return false;
+      out[written++] = (uint16_t)symbol;
+    }
+  }
+  return true;  // (tinyexr does not insist on the word count either)
+}
+// one inverse lifting step: (low, high) -> the two samples
+inline void piz_unlift(bool narrow, uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+  if (narrow) {
+    const int hi = (int16_t)h, ai = (int16_t)l + (hi & 1) + (hi >> 1);
+    a = (uint16_t)(int16_t)ai, b = (uint16_t)(int16_t)(ai - hi);
+  } else {
+    const int bb = ((int)l - ((int)h >> 1)) & 0xffff;
+    a = (uint16_t)(((int)h + bb - 0x8000) & 0xffff), b = (uint16_t)bb;
+  }
+}
+void piz_wavelet_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t max_value) {
+  const bool narrow = max_value < (1 << 14);
+  const int  n      = nx > ny ? ny : nx;
+  int        p      = 1;
+  while (p <= n) p <<= 1;
+  p >>= 1;
+  int p2 = p;
+  p >>= 1;
+  for (; p >= 1; p2 = p, p >>= 1) {  // from the coarsest level down
+    uint16_t*       py  = in;
+    uint16_t* const ey  = in + (ptrdiff_t)oy * (ny - p2);
+    const ptrdiff_t oy1 = (ptrdiff_t)oy * p, oy2 = (ptrdiff_t)oy * p2, ox1 = (ptrdiff_t)ox * p, ox2 = (ptrdiff_t)ox * p2;
+    uint16_t        i00, i01, i10, i11;
+    for (; py <= ey; py += oy2) {
+      uint16_t*       px = py;
+      uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
+      for (; px <= ex; px += ox2) {  // a 2 x 2 cell
+        uint16_t *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
+        piz_unlift(narrow, *px, *p10, i00, i10);
+        piz_unlift(narrow, *p01, *p11, i01, i11);
+        piz_unlift(narrow, i00, i01, *px, *p01);
+        piz_unlift(narrow, i10, i11, *p10, *p11);
+      }
+      if (nx & p) {  // an odd column
+        uint16_t* p10 = px + oy1;
+        piz_unlift(narrow, *px, *p10, i00, *p10);
+        *px = i00;
+      }
+    }
+    if (ny & p) {  // an odd line
+      uint16_t*       px = py;
+      uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
+      for (; px <= ex; px += ox2) {
+        uint16_t* p01 = px + ox1;
+        piz_unlift(narrow, *px, *p01, i00, *p01);
+        *px = i00;
+      }
+    }
+  }
+}
+bool piz_decode(const uint8_t* src, size_t stored, const std::vector<int>& channel_bytes, int width, int lines, uint8_t* out, size_t size) {
+  if (stored == size) return memcpy(out, src, size), true;
+  if (stored < 4) return false;
+  uint16_t min_used, max_used;
+  memcpy(&min_used, src, 2), memcpy(&max_used, src + 2, 2);
+  std::vector<uint8_t> bitmap(8192, 0);
+  size_t at = 4;
+  if (max_used >= 8192) return false;
+  if (min_used <= max_used) {
+    const size_t n = (size_t)max_used - min_used + 1;
+    if (stored < at + n) return false;
+    memcpy(&bitmap[min_used], src + at, n);
+    at += n;
+  }
+  std::vector<uint16_t> ranked(65536, 0);  // rank among the values in use -> value
+  size_t                in_use = 0;
+  for (int v = 0; v < 65536; v++)
+    if (v == 0 || (bitmap[v >> 3] & (1 << (v & 7)))) ranked[in_use++] = (uint16_t)v;
+  const uint16_t max_value = (uint16_t)(in_use - 1);
+  if (stored < at + 4) return false;
+  int32_t length;
+  memcpy(&length, src + at, 4);
+  at += 4;
+  if (length < 0 || at + (size_t)length > stored) return false;
+  std::vector<uint16_t> words(size / 2, 0);
+  if (length > 0) piz_huffman_decode(src + at, (size_t)length, words);  // (a failed block decodes to what it got, like there)
+  size_t start = 0;
+  for (int bytes : channel_bytes) {
+    const int per = bytes / 2;
+    for (int j = 0; j < per; j++) piz_wavelet_decode(&words[start + j], width, per, lines, width * per, max_value);
+    start += (size_t)width * lines * per;
+  }
+  for (auto& w : words) w = ranked[w];
+  std::vector<size_t> cursor(channel_bytes.size());
+  start = 0;
+  for (size_t c = 0; c < channel_bytes.size(); c++) cursor[c] = start, start += (size_t)width * lines * (channel_bytes[c] / 2);
+  for (int y = 0; y < lines; y++)
+    for (size_t c = 0; c < channel_bytes.size(); c++) {
+      const size_t n = (size_t)width * (channel_bytes[c] / 2);
+      memcpy(out, &words[cursor[c]], n * 2);
+      out += n * 2, cursor[c] += n;
+    }
+  return true;
+}
+
 bool load_exr(const std::vector<uint8_t>& file, HostTexture& tex) {
   const uint8_t *p = file.data(), *end = p + file.size();
   auto i32 = [&](const uint8_t* at) { int32_t v; memcpy(&v, at, 4); return v; };
@@ -1768,13 +1987,13 @@ bool load_exr(const std::vector<uint8_t>& file, HostTexture& tex) {
     }
     p += size;
   }
-  if (channels.empty() || !have_window || compression < 0 || compression > 3) return false;
+  if (channels.empty() || !have_window || compression < 0 || compression > 4) return false;
   if (window[2] < window[0] || window[3] < window[1]) return false;
   const int64_t width = (int64_t)window[2] - window[0] + 1, height = (int64_t)window[3] - window[1] + 1;
   if (width > (1 << 23) || height > (1 << 23) || width * height > (int64_t(1) << 28)) return false;
   size_t pixel_bytes = 0;
   for (auto& ch : channels) ch.offset = pixel_bytes, pixel_bytes += ch.bytes;
-  const int    block_lines = compression == 3 ? 16 : 1;
+  const int    block_lines = compression == 3 ? 16 : compression == 4 ? 32 : 1;
   const size_t num_blocks  = (size_t)((height + block_lines - 1) / block_lines);
   if ((size_t)(end - p) < num_blocks * 8) return false;
   // every channel as 32-bit words (floats, or the uint's bits)
@@ -1799,6 +2018,10 @@ bool load_exr(const std::vector<uint8_t>& file, HostTexture& tex) {
     if (compression == 0 || (size_t)stored == size) {
       if ((size_t)stored < size) return false;
       memcpy(raw.data(), src, size);
+    } else if (compression == 4) {
+      std::vector<int> channel_bytes;
+      for (auto& ch : channels) channel_bytes.push_back(ch.bytes);
+      if (!piz_decode(src, (size_t)stored, channel_bytes, (int)width, (int)lines, raw.data(), size)) return false;
     } else {
       scratch.resize(size);
       if (compression == 1) {  // run lengths
