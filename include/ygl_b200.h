@@ -219,13 +219,14 @@ void ygl_scene_destroy(ygl_scene* scene);
  * shapes / textures created by mention and found by trying extensions, "objects" with instance lists); ".ply" = one
  * shape as a scene with the default material, a framing camera and add_sky's procedural sky (load_ply_scene,
  * :4364-4381); ".gltf" / ".glb" = glTF 2.0 (load_gltf_scene, :4430-4767 over cgltf: meshes, node transforms, cameras,
- * pbr / transmission materials, external, base64 and GLB buffers; the sky is added as for .ply). Shapes are .ply, .obj (load_shape's de-duplicated reading) or binary .stl, textures .png, .jpg (baseline
+ * pbr / transmission materials, external, base64 and GLB buffers; the sky is added as for .ply); ".obj" = Wavefront OBJ
+ * with its .mtl libraries and the reference's .obx side file (load_obj_scene, :4111-4243). Shapes are .ply, .obj (load_shape's de-duplicated reading) or binary .stl, textures .png, .jpg (baseline
  * and progressive, decoded exactly as stb_image does), Radiance .hdr or OpenEXR (scanline; none / RLE / ZIPS / ZIP / PIZ).
  * The returned object owns the arrays its ygl_scene_desc views; hand that desc to ygl_scene_create / ygl_bvh_build /
  * ygl_lights_create / ygl_state_create. Defaults, lookat frames, texcoord flip, polygon fans, missing camera and
  * missing radius follow the reference (:1008-1035, :1796-1837, :2119-2148). Subdivs (.obj control meshes) are loaded
  * and tesselated right away (tesselate_subdivs, yocto_scene.cpp:739-813: what every reference app does after
- * load_scene). Format 4.1 (the reference's loader for it always fails, :3614), pbrt / mitsuba / obj / stl
+ * load_scene). Format 4.1 (the reference's loader for it always fails, :3614), pbrt / mitsuba / stl
  * scenes, ascii stl (the reference cannot read it either) and tiled / multi-part EXR textures are refused with an error. ---- */
 typedef struct ygl_loaded_scene ygl_loaded_scene;
 int  ygl_scene_load(const char* filename, ygl_loaded_scene** out);

@@ -278,3 +278,99 @@ def test_stl_shapes_load_like_the_reference(ref, tmp_path):
     for name, (data, expected) in files.items():
         assert _run(loaders, tmp_path, name, data) == expected, name
     loaders.close()
+
+
+def make_obj_scene(rng, d, stem):
+    """an .obj with objects / groups, several materials from one or two .mtl files (all the colour, exponent, opacity and
+    texture statements), elements before the first usemtl, repeated usemtl, and sometimes the .obx side file with cameras
+    and environments"""
+    import struct
+    import zlib
+    nmat = rng.randint(0, 4)
+    names = [f"mat{k}" for k in range(nmat)]
+    number = lambda: repr(round(rng.uniform(0, 1), rng.randint(1, 4)))
+    triple = lambda: " ".join(number() for _ in range(3))
+    chunk = lambda tag, body: struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xffffffff)
+    texture_names = []
+    for k in range(rng.randint(0, 2)):
+        name = f"{stem}_t{k}.png"
+        rows = b"".join(b"\0" + bytes(rng.randrange(256) for _ in range(3 * 3)) for _ in range(2))
+        (d / name).write_bytes(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 3, 2, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(rows)) + chunk(b"IEND", b""))
+        texture_names.append(name)
+    libs = [names[:len(names) // 2 + 1], names[len(names) // 2 + 1:]] if nmat > 2 and rng.random() < 0.4 else [names]
+    for k, lib in enumerate(libs):
+        lines = ["# materials"]
+        if rng.random() < 0.2:
+            lines.append("Kd 0.1 0.2 0.3")           # before the first newmtl: goes to the placeholder
+        for name in lib:
+            lines.append(f"newmtl {name}")
+            for key in ("Ke", "Ka", "Kd", "Ks", "Kt", "Tf"):
+                if rng.random() < 0.45:
+                    lines.append(f"{key} " + (triple() if rng.random() < 0.8 else "0 0 0"))
+            for key in ("Ns", "d", "Tr", "illum"):
+                if rng.random() < 0.4:
+                    lines.append(f"{key} " + (str(rng.choice([0, 1, 2, 10, 200, 1500])) if key in ("Ns", "illum") else number()))
+            for key in ("map_Kd", "map_Ks", "map_Ke", "map_Tr", "map_d", "map_bump", "norm", "map_Ka"):
+                if texture_names and rng.random() < 0.25:
+                    option = "-bm 0.5 " if key == "map_bump" and rng.random() < 0.5 else ""
+                    lines.append(f"{key} {option}{rng.choice(texture_names)}")
+            if rng.random() < 0.2:
+                lines.append("Ni 1.33")              # not read by the reference
+        (d / f"{stem}_{k}.mtl").write_text("\n".join(lines) + "\n")
+    nv = rng.randint(4, 12)
+    out = [f"v {number()} {number()} {number()}" for _ in range(nv)]
+    nn, nt = rng.choice([0, 3]), rng.choice([0, 4])
+    out += [f"vn {number()} {number()} {number()}" for _ in range(nn)] + [f"vt {number()} {number()}" for _ in range(nt)]
+
+    def vert():
+        v = rng.randint(1, nv) if rng.random() < 0.85 else -rng.randint(1, nv)
+        t = str(rng.randint(1, nt)) if nt and rng.random() < 0.7 else ""
+        n = str(rng.randint(1, nn)) if nn and rng.random() < 0.7 else ""
+        return str(v) + ("/" + t + ("/" + n if n else "") if t or n else "")
+    body = []
+    if rng.random() < 0.4:
+        body.append("f " + " ".join(vert() for _ in range(3)))         # before any mtllib / usemtl: the grey default
+    for k in range(len(libs)):
+        body.append(f"mtllib {stem}_{k}.mtl")
+    if rng.random() < 0.2 and libs:
+        body.append(f"mtllib {stem}_0.mtl")                             # a repeated library is read once
+    for _ in range(rng.randint(1, 10)):
+        r = rng.random()
+        if r < 0.2:
+            body.append(rng.choice(["o", "g"]) + (" part%d" % rng.randint(0, 3) if rng.random() < 0.8 else ""))
+        elif r < 0.45 and names:
+            body.append("usemtl " + rng.choice(names))
+        else:
+            kind = rng.choice(["f", "f", "f", "l", "p"])
+            n = {"f": rng.choice([3, 4, 5]), "l": rng.choice([2, 3]), "p": 1}[kind]
+            body.append(kind + " " + " ".join(vert() for _ in range(n)))
+    if not any(line[0] in "flp" for line in body):
+        body.append("f 1 2 3")
+    (d / f"{stem}.obj").write_text("\n".join(out + body) + "\n")
+    if rng.random() < 0.4:
+        side = []
+        for k in range(rng.randint(0, 2)):
+            side += [f"newCam cam{k}", f"Ca {rng.choice([1.0, 1.5, 2.4])}", f"Cl {number()}"]
+            side += ["Ct 1 2 3 0 0.5 0 0 1 0"] if rng.random() < 0.6 else ["Cx 1 0 0 0 1 0 0 0 1 0.5 1 4", "Cf 2.5", "Co 1"]
+        for k in range(rng.randint(0, 2)):
+            side += [f"newEnv env{k}", f"Ee {triple()}"] + ([f"map_Ee {rng.choice(texture_names)}"] if texture_names and rng.random() < 0.5 else [])
+            side += ["Et 0 0 0 0 0 -1 0 1 0"] if rng.random() < 0.5 else []
+        (d / f"{stem}.obx").write_text("\n".join(side) + "\n")
+    return d / f"{stem}.obj"
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_obj_scenes_load_like_the_reference(ref, seed, tmp_path):
+    """`load_scene("x.obj")` (load_obj_scene, yocto_sceneio.cpp:4111): shapes split by object / group and material,
+    .mtl materials classified and converted, textures in order of first mention, .obx cameras and environments."""
+    rng = random.Random(seed)
+    counts = {"same": 0, "refused": 0, "reference crashed": 0}
+    loaders = LoaderPair()
+    for k in range(120):
+        path = make_obj_scene(rng, tmp_path, f"s{k}")
+        verdict = loaders.verdict(path)
+        assert verdict in counts, f"scene {k} (seed {seed}): {verdict}\n{path.read_text()}\n" + "\n".join(
+            p.read_text() for p in sorted(tmp_path.glob(f"s{k}_*.mtl")))
+        counts[verdict] += 1
+    loaders.close()
+    assert counts["same"] >= 80, counts

@@ -9,8 +9,8 @@
 //   add_missing_camera / add_missing_radius          yocto_sceneio.cpp:2119-2148
 // Numbers in JSON are read as doubles and narrowed to float, as nlohmann::json does for the reference.
 // Subdivs (.obj control meshes) are read and tesselated at load (tesselate_subdivs, yocto_scene.cpp:739-813).
-// Shapes: .ply, .obj, binary .stl; textures .png, .jpg, .hdr, .exr; scenes .json, .ply, .gltf / .glb. Not built: pbrt /
-// mitsuba / obj scenes, tiled EXR: refused.
+// Shapes: .ply, .obj, binary .stl; textures .png, .jpg, .hdr, .exr; scenes .json, .ply, .gltf / .glb, .obj. Not built: pbrt /
+// mitsuba scenes, tiled EXR: refused.
 #include <sched.h>
 #include <sys/stat.h>
 #include <zlib.h>
@@ -2537,27 +2537,30 @@ bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& e
 // load_shape for .obj (yocto_sceneio.cpp:1036-1051): load_obj(face_varying = false) - one vertex per distinct
 // (position, texcoord, normal) triple in order of first use (yocto_modelio.cpp:1460-1489) - then get_faces / get_lines /
 // get_points (:1771-1856), including their cursor rule: an element of another type does not advance the vertex cursor.
-bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& error) {
-  ObjData obj;
-  if (!read_obj(filename, obj, error)) return false;
+// The vertices of one OBJ shape -> de-duplicated vertex arrays and element arrays (load_obj's non-face-varying
+// conversion, yocto_modelio.cpp:1330-1360, and the getters :1850-2010). `material` < 0 takes every element; otherwise only
+// the elements of that material count - and, as there, only those advance the vertex cursor.
+void convert_obj_shape(const std::vector<v3>& positions, const std::vector<v3>& normals, const std::vector<v2>& texcoords,
+    std::vector<ObjVertex>& vertices, const std::vector<int>& sizes, const std::vector<char>& types, const std::vector<int>* materials,
+    int material, HostShape& shape) {
   std::unordered_map<ObjVertex, ObjVertex, ObjVertexHash> vertex_map;
-  for (auto& vertex : obj.vertices) {
+  for (auto& vertex : vertices) {
     auto it = vertex_map.find(vertex);
     if (it == vertex_map.end()) {
       ObjVertex  fresh = vertex;
       const int  index = (int)vertex_map.size();
       if (vertex.position > 0) {
-        const v3& p = obj.positions[vertex.position - 1];
+        const v3& p = positions[vertex.position - 1];
         shape.positions.insert(shape.positions.end(), {p.x, p.y, p.z});
         fresh.position = index + 1;
       }
       if (vertex.normal > 0) {
-        const v3& n = obj.normals[vertex.normal - 1];
+        const v3& n = normals[vertex.normal - 1];
         shape.normals.insert(shape.normals.end(), {n.x, n.y, n.z});
         fresh.normal = index + 1;
       }
       if (vertex.texcoord > 0) {
-        const v2& t = obj.texcoords[vertex.texcoord - 1];
+        const v2& t = texcoords[vertex.texcoord - 1];
         shape.texcoords.insert(shape.texcoords.end(), {t.x, 1 - t.y});  // get_texcoords(obj, texcoords, flipv = true)
         fresh.texcoord = index + 1;
       }
@@ -2567,13 +2570,14 @@ bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& 
       vertex = it->second;
     }
   }
+  auto counts = [&](size_t e, char type) { return types[e] == type && (material < 0 || !materials || (*materials)[e] == material); };
   bool has_quads = false;
-  for (size_t e = 0; e < obj.sizes.size(); e++) has_quads |= obj.types[e] == 'f' && obj.sizes[e] == 4;
-  auto pos = [&](size_t i) { return obj.vertices[i].position - 1; };
+  for (size_t e = 0; e < sizes.size(); e++) has_quads |= types[e] == 'f' && sizes[e] == 4;
+  auto pos = [&](size_t i) { return vertices[i].position - 1; };
   size_t cur = 0;
-  for (size_t e = 0; e < obj.sizes.size(); e++) {  // get_faces
-    if (obj.types[e] != 'f') continue;
-    const int size = obj.sizes[e];
+  for (size_t e = 0; e < sizes.size(); e++) {  // get_faces
+    if (!counts(e, 'f')) continue;
+    const int size = sizes[e];
     if (has_quads) {
       if (size == 4) shape.quads.insert(shape.quads.end(), {pos(cur), pos(cur + 1), pos(cur + 2), pos(cur + 3)});
       else
@@ -2584,17 +2588,22 @@ bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& 
     cur += size;
   }
   cur = 0;
-  for (size_t e = 0; e < obj.sizes.size(); e++) {  // get_lines
-    if (obj.types[e] != 'l') continue;
-    for (int c = 1; c < obj.sizes[e]; c++) shape.lines.insert(shape.lines.end(), {pos(cur + c - 1), pos(cur + c)});
-    cur += obj.sizes[e];
+  for (size_t e = 0; e < sizes.size(); e++) {  // get_lines
+    if (!counts(e, 'l')) continue;
+    for (int c = 1; c < sizes[e]; c++) shape.lines.insert(shape.lines.end(), {pos(cur + c - 1), pos(cur + c)});
+    cur += sizes[e];
   }
   cur = 0;
-  for (size_t e = 0; e < obj.sizes.size(); e++) {  // get_points (every point of an element is its first vertex, as there)
-    if (obj.types[e] != 'p') continue;
-    for (int c = 0; c < obj.sizes[e]; c++) shape.points.push_back(pos(cur));
-    cur += obj.sizes[e];
+  for (size_t e = 0; e < sizes.size(); e++) {  // get_points (every point of an element is its first vertex, as there)
+    if (!counts(e, 'p')) continue;
+    for (int c = 0; c < sizes[e]; c++) shape.points.push_back(pos(cur));
+    cur += sizes[e];
   }
+}
+bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& error) {
+  ObjData obj;
+  if (!read_obj(filename, obj, error)) return false;
+  convert_obj_shape(obj.positions, obj.normals, obj.texcoords, obj.vertices, obj.sizes, obj.types, nullptr, -1, shape);
   if (shape.points.empty() && shape.lines.empty() && shape.triangles.empty() && shape.quads.empty())
     return error = "empty shape " + filename, false;
   return true;
@@ -3877,6 +3886,363 @@ bool load_gltf_scene(const std::string& filename, ygl_loaded_scene& scene, std::
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wavefront OBJ as a scene (load_obj_scene, yocto_sceneio.cpp:4111-4243, over load_obj / load_mtl / load_obx of
+// yocto_modelio.cpp:949-1376): one shape + instance per (object / group, material) with vertices de-duplicated per
+// shape; materials of the .mtl files classified as transparent / reflective / glossy / matte from Kt, Ks, Kd with the
+// roughness taken from the Phong exponent; textures by first mention; cameras and environments from the reference's own
+// ".obx" side file; a framing camera if there is none. No light is added: such a scene renders with what it emits.
+// ---------------------------------------------------------------------------------------------------------------
+struct ObjLine {  // one line, comment removed, read token by token like parse_value (yocto_modelio.cpp:376-430)
+  const char *s, *stop;
+  void skip() { while (s < stop && (*s == ' ' || *s == '\t' || *s == '\r' || *s == '\n')) s++; }
+  bool empty() { return skip(), s >= stop; }
+  bool word(std::string& out) {
+    skip();
+    if (s >= stop) return false;
+    if (*s != '"') {
+      const char* b = s;
+      while (s < stop && !(*s == ' ' || *s == '\t' || *s == '\r' || *s == '\n')) s++;
+      out.assign(b, s);
+      return true;
+    }
+    const char* b = ++s;
+    while (s < stop && *s != '"') s++;
+    if (s >= stop) return false;
+    out.assign(b, s++);
+    return true;
+  }
+  template <typename T>
+  bool number(T& v) {
+    skip();
+    auto r = std::from_chars(s, stop, v);
+    if (r.ptr == s) return false;
+    s = r.ptr;
+    return true;
+  }
+  bool numbers(float* v, int n) {
+    for (int k = 0; k < n; k++)
+      if (!number(v[k])) return false;
+    return true;
+  }
+  bool vertex(ObjVertex& v) {
+    v = ObjVertex{};
+    if (!number(v.position)) return false;
+    if (s < stop && *s == '/') {  // (blanks are skipped before an index, never before a slash)
+      s++;
+      if (s < stop && *s == '/') {
+        s++;
+        if (!number(v.normal)) return false;
+      } else {
+        if (!number(v.texcoord)) return false;
+        if (s < stop && *s == '/') {
+          s++;
+          if (!number(v.normal)) return false;
+        }
+      }
+    }
+    return true;
+  }
+};
+template <typename F>
+bool for_each_obj_line(const std::vector<uint8_t>& data, F&& fn) {
+  const char *p = (const char*)data.data(), *end = p + data.size();
+  while (p < end) {
+    const char* eol = (const char*)memchr(p, '\n', end - p);
+    if (!eol) eol = end;
+    const char* stop = (const char*)memchr(p, '#', eol - p);
+    ObjLine     line{p, stop ? stop : eol};
+    p = eol < end ? eol + 1 : end;
+    if (line.empty()) continue;
+    std::string cmd;
+    if (!line.word(cmd)) return false;
+    if (cmd.empty()) continue;
+    if (!fn(cmd, line)) return false;
+  }
+  return true;
+}
+struct ObjMaterial {
+  std::string name;
+  float emission[3] = {0, 0, 0}, diffuse[3] = {0, 0, 0}, specular[3] = {0, 0, 0}, transmission[3] = {0, 0, 0};
+  float exponent = 10, ior = 1.5f, opacity = 1;
+  int   emission_tex = -1, diffuse_tex = -1, specular_tex = -1, transmission_tex = -1, normal_tex = -1;
+};
+struct ObjShapeData {
+  std::vector<ObjVertex> vertices;
+  std::vector<int>       sizes, materials;
+  std::vector<char>      types;
+};
+struct ObjModel {
+  std::vector<v3>              positions, normals;
+  std::vector<v2>              texcoords;
+  std::vector<ObjShapeData>    shapes;
+  std::vector<ObjMaterial>     materials;
+  std::vector<std::string>     textures;
+  std::vector<ygl_camera>      cameras;
+  std::vector<ygl_environment> environments;
+  std::unordered_map<std::string, int> texture_ids;
+  bool texture(ObjLine& line, int& id) {  // the last token of the line is the path; -bm / -clamp options are not used here
+    std::string token, path;
+    while (!line.empty()) {
+      if (!line.word(token)) return false;
+      path = token;
+    }
+    if (path.empty() && token.empty()) return false;
+    for (auto& c : path)
+      if (c == '\\') c = '/';
+    auto it = texture_ids.find(path);
+    if (it == texture_ids.end()) {
+      textures.push_back(path);
+      it = texture_ids.insert({path, (int)textures.size() - 1}).first;
+    }
+    id = it->second;
+    return true;
+  }
+};
+bool load_mtl(const std::string& filename, ObjModel& obj, std::string& error) {
+  std::vector<uint8_t> data;
+  if (!read_file(filename, data, error)) return false;
+  const size_t first = obj.materials.size();
+  obj.materials.emplace_back();  // a placeholder that swallows what comes before the first newmtl
+  int  unused_tex = -1;
+  float unused[3];
+  const bool ok = for_each_obj_line(data, [&](const std::string& cmd, ObjLine& line) {
+    ObjMaterial& m = obj.materials.back();
+    if (cmd == "newmtl") {
+      obj.materials.emplace_back();
+      return line.word(obj.materials.back().name);
+    }
+    if (cmd == "illum") { int illum; return line.number(illum); }
+    if (cmd == "Ke") return line.numbers(m.emission, 3);
+    if (cmd == "Ka") return line.numbers(unused, 3);
+    if (cmd == "Kd") return line.numbers(m.diffuse, 3);
+    if (cmd == "Ks") return line.numbers(m.specular, 3);
+    if (cmd == "Kt") return line.numbers(m.transmission, 3);
+    if (cmd == "Tf") {
+      if (!line.numbers(m.transmission, 3)) return false;
+      for (float& t : m.transmission) t = std::max(1 - t, 0.0f);
+      if (std::max(m.transmission[0], std::max(m.transmission[1], m.transmission[2])) < 0.001f) m.transmission[0] = m.transmission[1] = m.transmission[2] = 0;
+      return true;
+    }
+    if (cmd == "Tr") {
+      if (!line.number(m.opacity)) return false;
+      m.opacity = 1 - m.opacity;
+      return true;
+    }
+    if (cmd == "Ns") return line.number(m.exponent);
+    if (cmd == "d") return line.number(m.opacity);
+    if (cmd == "map_Ke") return obj.texture(line, m.emission_tex);
+    if (cmd == "map_Kd") return obj.texture(line, m.diffuse_tex);
+    if (cmd == "map_Ks") return obj.texture(line, m.specular_tex);
+    if (cmd == "map_Tr") return obj.texture(line, m.transmission_tex);
+    if (cmd == "map_norm" || cmd == "norm") return obj.texture(line, m.normal_tex);
+    if (cmd == "map_Ka" || cmd == "map_d" || cmd == "map_bump" || cmd == "bump" || cmd == "map_disp" || cmd == "disp")
+      return obj.texture(line, unused_tex);  // registered in the texture list like there, not used by the conversion
+    return true;
+  });
+  if (!ok) return error = "cannot parse " + filename, false;
+  // "remove placeholder material": the reference erases the FIRST material of the model, which is the placeholder only
+  // when nothing was there before - after elements without usemtl (the grey default) or a second mtllib it drops that
+  // earlier material and the empty placeholder stays. Kept, so that material indices come out the same.
+  (void)first;
+  obj.materials.erase(obj.materials.begin());
+  return true;
+}
+bool load_obx(const std::string& filename, ObjModel& obj, std::string& error) {
+  std::vector<uint8_t> data;
+  if (!read_file(filename, data, error)) return false;
+  auto fresh_camera = []() {
+    ygl_camera c = {};
+    memcpy(&c.frame, kIdentityFrame, 48);
+    c.orthographic = 0, c.aspect = 16.0f / 9.0f, c.lens = 0.50f, c.film = 0.036f, c.focus = 0, c.aperture = 0;
+    return c;
+  };
+  auto fresh_environment = []() {
+    ygl_environment e = {};
+    memcpy(&e.frame, kIdentityFrame, 48);
+    e.emission_tex = -1;
+    return e;
+  };
+  obj.cameras.push_back(fresh_camera()), obj.environments.push_back(fresh_environment());  // placeholders
+  const bool ok = for_each_obj_line(data, [&](const std::string& cmd, ObjLine& line) {
+    ygl_camera&      camera = obj.cameras.back();
+    ygl_environment& env    = obj.environments.back();
+    std::string      name;
+    float            l[9];
+    if (cmd == "newCam") return obj.cameras.push_back(fresh_camera()), line.word(name);
+    if (cmd == "Co") { int v; if (!line.number(v)) return false; camera.orthographic = v != 0; return true; }
+    if (cmd == "Ca") return line.number(camera.aspect);
+    if (cmd == "Cl") return line.number(camera.lens);
+    if (cmd == "Cs") return line.number(camera.film);
+    if (cmd == "Cf") return line.number(camera.focus);
+    if (cmd == "Cp") return line.number(camera.aperture);
+    if (cmd == "Cx") return line.numbers(frame_of(camera.frame), 12);
+    if (cmd == "Ct") {
+      if (!line.numbers(l, 9)) return false;
+      lookat_frame(frame_of(camera.frame), {l[0], l[1], l[2]}, {l[3], l[4], l[5]}, {l[6], l[7], l[8]}, false);
+      if (camera.focus == 0) camera.focus = length(v3{l[3] - l[0], l[4] - l[1], l[5] - l[2]});
+      return true;
+    }
+    if (cmd == "newEnv") return obj.environments.push_back(fresh_environment()), line.word(name);
+    if (cmd == "Ee") return line.numbers(env.emission, 3);
+    if (cmd == "map_Ee") return obj.texture(line, env.emission_tex);
+    if (cmd == "Ex") return line.numbers(frame_of(env.frame), 12);
+    if (cmd == "Et") {
+      if (!line.numbers(l, 9)) return false;
+      lookat_frame(frame_of(env.frame), {l[0], l[1], l[2]}, {l[3], l[4], l[5]}, {l[6], l[7], l[8]}, true);
+      return true;
+    }
+    return true;
+  });
+  if (!ok) return error = "cannot parse " + filename, false;
+  obj.cameras.erase(obj.cameras.begin()), obj.environments.erase(obj.environments.begin());
+  return true;
+}
+bool load_obj_model(const std::string& filename, ObjModel& obj, std::string& error) {
+  std::vector<uint8_t> data;
+  if (!read_file(filename, data, error)) return false;
+  std::string oname, gname;
+  std::vector<std::string>             mtllibs;
+  std::unordered_map<std::string, int> material_ids;
+  int  cur_material = -1;
+  std::unordered_map<int, int> cur_shapes = {{-1, 0}};  // material -> shape, within the current object / group
+  obj.shapes.emplace_back();
+  int         cur_shape = 0;
+  std::string failure;
+  const bool  ok = for_each_obj_line(data, [&](const std::string& cmd, ObjLine& line) {
+    if (cmd == "v" || cmd == "vn") {
+      v3 v = {0, 0, 0};
+      (cmd == "v" ? obj.positions : obj.normals).push_back(v);  // (the slot exists even if the line then fails)
+      return line.numbers(&(cmd == "v" ? obj.positions : obj.normals).back().x, 3);
+    }
+    if (cmd == "vt") {
+      obj.texcoords.push_back({0, 0});
+      return line.numbers(&obj.texcoords.back().x, 2);
+    }
+    if (cmd == "f" || cmd == "l" || cmd == "p") {
+      if (cur_material < 0) {  // elements before any usemtl get a grey default material
+        ObjMaterial m;
+        m.name = "__default__", m.diffuse[0] = m.diffuse[1] = m.diffuse[2] = 0.8f;
+        obj.materials.push_back(m);
+        cur_material = 0, material_ids[m.name] = 0;
+      }
+      ObjShapeData& shape = obj.shapes[cur_shape];
+      shape.sizes.push_back(0), shape.types.push_back(cmd[0]), shape.materials.push_back(cur_material);
+      while (!line.empty()) {
+        ObjVertex v;
+        if (!line.vertex(v)) return false;
+        if (v.position == 0) break;
+        if (v.position < 0) v.position = (int)obj.positions.size() + v.position + 1;
+        if (v.texcoord < 0) v.texcoord = (int)obj.texcoords.size() + v.texcoord + 1;
+        if (v.normal < 0) v.normal = (int)obj.normals.size() + v.normal + 1;
+        shape.vertices.push_back(v);
+        shape.sizes.back()++;
+      }
+      return true;
+    }
+    if (cmd == "o" || cmd == "g") {
+      std::string& name = cmd == "o" ? oname : gname;
+      name.clear();
+      if (!line.empty() && !line.word(name)) return false;
+      obj.shapes.emplace_back();
+      cur_shape  = (int)obj.shapes.size() - 1;
+      cur_shapes = {{cur_material, cur_shape}};
+      return true;
+    }
+    if (cmd == "usemtl") {
+      std::string name;
+      if (!line.word(name)) return false;
+      auto it = material_ids.find(name);
+      if (it == material_ids.end()) return false;
+      if (cur_material != it->second) {
+        cur_material = it->second;
+        auto shape   = cur_shapes.find(cur_material);
+        if (shape == cur_shapes.end()) {
+          obj.shapes.emplace_back();
+          cur_shape = (int)obj.shapes.size() - 1, cur_shapes[cur_material] = cur_shape;
+        } else {
+          cur_shape = shape->second;
+        }
+      }
+      return true;
+    }
+    if (cmd == "mtllib") {
+      std::string name;
+      if (!line.word(name)) return false;
+      if (std::find(mtllibs.begin(), mtllibs.end(), name) != mtllibs.end()) return true;
+      mtllibs.push_back(name);
+      if (!load_mtl(path_join(path_dirname(filename), name), obj, failure)) return false;
+      for (size_t k = 0; k < obj.materials.size(); k++) material_ids[obj.materials[k].name] = (int)k;
+      return true;
+    }
+    return true;
+  });
+  if (!ok) return error = failure.empty() ? "cannot parse " + filename : "cannot load " + filename + " since " + failure, false;
+  obj.shapes.erase(std::remove_if(obj.shapes.begin(), obj.shapes.end(), [](const ObjShapeData& shape) { return shape.sizes.empty(); }),
+      obj.shapes.end());
+  auto dot = filename.find_last_of('.');
+  const std::string side = filename.substr(0, dot) + ".obx";
+  if (path_exists(side) && !load_obx(side, obj, failure)) return error = "cannot load " + filename + " since " + failure, false;
+  return true;
+}
+bool load_obj_scene(const std::string& filename, ygl_loaded_scene& scene, std::string& error) {
+  ObjModel obj;
+  if (!load_obj_model(filename, obj, error)) return false;
+  scene.cameras = obj.cameras;
+  auto exponent_to_roughness = [](float exponent) {
+    if (exponent >= 1000) return 0.0f;
+    float roughness = exponent;
+    roughness       = std::pow(2 / (roughness + 2), 1 / 4.0f);
+    if (roughness < 0.01f) roughness = 0;
+    if (roughness > 0.99f) roughness = 1;
+    return roughness;
+  };
+  auto largest = [](const float* v) { return (double)std::max(v[0], std::max(v[1], v[2])); };
+  for (auto& om : obj.materials) {
+    ygl_material m = {};
+    m.type = 7, m.roughness = 0, m.metallic = 0, m.ior = 1.5f, m.scanisotropy = 0, m.trdepth = 0.01f, m.opacity = 1;
+    m.emission_tex = m.color_tex = m.roughness_tex = m.scattering_tex = m.normal_tex = -1;
+    memcpy(m.emission, om.emission, 12);
+    m.emission_tex = om.emission_tex;
+    if (largest(om.transmission) > 0.1) m.type = 3, memcpy(m.color, om.transmission, 12), m.color_tex = om.transmission_tex;
+    else if (largest(om.specular) > 0.2) m.type = 2, memcpy(m.color, om.specular, 12), m.color_tex = om.specular_tex;
+    else if (largest(om.specular) > 0) m.type = 1, memcpy(m.color, om.diffuse, 12), m.color_tex = om.diffuse_tex;
+    else m.type = 0, memcpy(m.color, om.diffuse, 12), m.color_tex = om.diffuse_tex;
+    m.roughness = exponent_to_roughness(om.exponent), m.ior = om.ior, m.metallic = 0, m.opacity = om.opacity, m.normal_tex = om.normal_tex;
+    scene.materials.push_back(m);
+  }
+  for (auto& shape : obj.shapes) {
+    scene.shape_data.emplace_back();
+    ygl_instance inst = {};
+    memcpy(&inst.frame, kIdentityFrame, 48);
+    inst.shape = (int)scene.shape_data.size() - 1, inst.material = shape.materials.front();
+    convert_obj_shape(obj.positions, obj.normals, obj.texcoords, shape.vertices, shape.sizes, shape.types, &shape.materials, inst.material,
+        scene.shape_data.back());
+    scene.instances.push_back(inst);
+  }
+  scene.environments = obj.environments;
+  auto numbered = [](size_t count, const char* prefix, std::vector<std::string>& names) {  // make_names, :2104-2116
+    const std::string width = std::to_string(count);
+    for (size_t k = 0; k < count; k++) {
+      std::string number = std::to_string(k + 1);
+      while (number.size() < width.size()) number = "0" + number;
+      names.push_back(prefix + number);
+    }
+  };
+  numbered(scene.cameras.size(), "camera", scene.names[0]), numbered(obj.textures.size(), "texture", scene.names[1]);
+  numbered(scene.materials.size(), "material", scene.names[2]), numbered(scene.shape_data.size(), "shape", scene.names[3]);
+  numbered(scene.instances.size(), "instance", scene.names[4]);
+  scene.texture_data.resize(obj.textures.size());
+  const auto dirname = path_dirname(filename);
+  if (!parallel_load(obj.textures.size(), error, [&](size_t i, std::string& err) {
+        return load_texture(path_join(dirname, obj.textures[i]), scene.texture_data[i], err);
+      }))
+    return error = "cannot load " + filename + " since " + error, false;
+  add_missing_camera(scene);
+  add_missing_radius(scene);
+  return true;
+}
+
 void make_desc(ygl_loaded_scene& scene) {
   scene.shapes.clear(), scene.textures.clear();
   for (auto& s : scene.shape_data) {
@@ -3928,6 +4294,7 @@ int ygl_scene_load(const char* filename, ygl_loaded_scene** out) {
   if (ext == ".json") ok = load_json_scene(filename, *scene, error);
   else if (ext == ".ply") ok = load_ply_scene(filename, *scene, error);
   else if (ext == ".gltf" || ext == ".glb") ok = load_gltf_scene(filename, *scene, error);
+  else if (ext == ".obj") ok = load_obj_scene(filename, *scene, error);
   else error = "unsupported format " + std::string(filename), ok = false;
   if (!ok) return ygl_internal_set_error(error.c_str()), YGL_ERR_RUNTIME;
   make_desc(*scene);
