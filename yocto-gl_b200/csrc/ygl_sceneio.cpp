@@ -1248,9 +1248,13 @@ bool load_subdiv(const std::string& filename, HostSubdiv& subdiv, std::string& e
 // The vertices of one OBJ shape -> de-duplicated vertex arrays and element arrays (load_obj's non-face-varying
 // conversion, yocto_modelio.cpp:1330-1360, and the getters :1850-2010). `material` < 0 takes every element; otherwise only
 // the elements of that material count - and, as there, only those advance the vertex cursor.
-void convert_obj_shape(const std::vector<v3>& positions, const std::vector<v3>& normals, const std::vector<v2>& texcoords,
+bool convert_obj_shape(const std::vector<v3>& positions, const std::vector<v3>& normals, const std::vector<v2>& texcoords,
     std::vector<ObjVertex>& vertices, const std::vector<int>& sizes, const std::vector<char>& types, const std::vector<int>* materials,
     int material, HostShape& shape) {
+  for (auto& vertex : vertices)  // an index past its array is read unchecked by the reference: refused here
+    if (vertex.position > (int)positions.size() || vertex.normal > (int)normals.size() || vertex.texcoord > (int)texcoords.size() ||
+        vertex.position < 0 || vertex.normal < 0 || vertex.texcoord < 0)
+      return false;
   std::unordered_map<ObjVertex, ObjVertex, ObjVertexHash> vertex_map;
   for (auto& vertex : vertices) {
     auto it = vertex_map.find(vertex);
@@ -1307,11 +1311,13 @@ void convert_obj_shape(const std::vector<v3>& positions, const std::vector<v3>& 
     for (int c = 0; c < sizes[e]; c++) shape.points.push_back(pos(cur));
     cur += sizes[e];
   }
+  return true;
 }
 bool load_obj_shape(const std::string& filename, HostShape& shape, std::string& error) {
   ObjData obj;
   if (!read_obj(filename, obj, error)) return false;
-  convert_obj_shape(obj.positions, obj.normals, obj.texcoords, obj.vertices, obj.sizes, obj.types, nullptr, -1, shape);
+  if (!convert_obj_shape(obj.positions, obj.normals, obj.texcoords, obj.vertices, obj.sizes, obj.types, nullptr, -1, shape))
+    return error = "cannot parse " + filename + ": vertex index out of range", false;
   if (shape.points.empty() && shape.lines.empty() && shape.triangles.empty() && shape.quads.empty())
     return error = "empty shape " + filename, false;
   return true;
@@ -2924,8 +2930,9 @@ bool load_obj_scene(const std::string& filename, ygl_loaded_scene& scene, std::s
     ygl_instance inst = {};
     memcpy(&inst.frame, kIdentityFrame, 48);
     inst.shape = (int)scene.shape_data.size() - 1, inst.material = shape.materials.front();
-    convert_obj_shape(obj.positions, obj.normals, obj.texcoords, shape.vertices, shape.sizes, shape.types, &shape.materials, inst.material,
-        scene.shape_data.back());
+    if (!convert_obj_shape(obj.positions, obj.normals, obj.texcoords, shape.vertices, shape.sizes, shape.types, &shape.materials,
+            inst.material, scene.shape_data.back()))
+      return error = "cannot parse " + filename + ": vertex index out of range", false;
     scene.instances.push_back(inst);
   }
   scene.environments = obj.environments;
