@@ -43,6 +43,7 @@ bool load_hdr(const std::vector<uint8_t>& data, HostTexture& tex) {
   token(line);
   int w = 0, h = 0;
   if (sscanf(line.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) return false;
+  if (w > (1 << 24) || h > (1 << 24) || (uint64_t)w * h > (1u << 27)) return false;  // (stb: "too large")
   tex.width = w, tex.height = h;
   tex.pixelsf.assign((size_t)w * h * 4, 0.0f);
   static const struct Scales {  // 2^(e - 136) for every exponent byte: what ldexp returns, computed once
@@ -180,6 +181,7 @@ bool load_png(const std::vector<uint8_t>& data, HostTexture& tex) {
       png.w = (int)be32(pos + 8), png.h = (int)be32(pos + 12);
       png.depth = body[8], png.ctype = body[9], interlace = body[12];
       if (be32(pos + 8) > (1u << 24) || be32(pos + 12) > (1u << 24) || png.w == 0 || png.h == 0) return false;
+      if ((uint64_t)png.w * png.h > (1u << 28)) return false;  // (stb refuses what does not fit 2^30 bytes)
       if (png.depth != 1 && png.depth != 2 && png.depth != 4 && png.depth != 8 && png.depth != 16) return false;
       if (png.ctype > 6 || (png.ctype == 3 && png.depth == 16) || (png.ctype != 3 && (png.ctype & 1))) return false;
       if (body[10] != 0 || body[11] != 0 || interlace > 1) return false;

@@ -855,7 +855,11 @@ bool parallel_load(size_t n, std::string& error, const std::function<bool(size_t
     pool.emplace_back([&]() {
       for (size_t k = next++; k < n; k = next++) {
         const size_t i = order ? (*order)[k] : k;
-        if (!fn(i, errors[i])) failed[i] = 1;
+        try {  // nothing may leave a worker thread (or, further up, the C ABI) as an exception
+          if (!fn(i, errors[i])) failed[i] = 1;
+        } catch (const std::exception& e) {
+          errors[i] = std::string("out of memory or internal error (") + e.what() + ")", failed[i] = 1;
+        }
       }
     });
   for (auto& t : pool) t.join();
@@ -3001,20 +3005,24 @@ extern "C" {
 
 int ygl_scene_load(const char* filename, ygl_loaded_scene** out) {
   if (!filename || !out) return ygl_internal_set_error("null argument"), YGL_ERR_INVALID;
-  auto        scene = std::make_unique<ygl_loaded_scene>();
-  std::string error;
-  // load_scene, yocto_sceneio.cpp:2761-2782: the extension picks the format
-  const auto ext = path_extension(filename);
-  bool       ok  = false;
-  if (ext == ".json") ok = load_json_scene(filename, *scene, error);
-  else if (ext == ".ply") ok = load_ply_scene(filename, *scene, error);
-  else if (ext == ".gltf" || ext == ".glb") ok = load_gltf_scene(filename, *scene, error);
-  else if (ext == ".obj") ok = load_obj_scene(filename, *scene, error);
-  else error = "unsupported format " + std::string(filename), ok = false;
-  if (!ok) return ygl_internal_set_error(error.c_str()), YGL_ERR_RUNTIME;
-  make_desc(*scene);
-  *out = scene.release();
-  return YGL_OK;
+  try {
+    auto        scene = std::make_unique<ygl_loaded_scene>();
+    std::string error;
+    // load_scene, yocto_sceneio.cpp:2761-2782: the extension picks the format
+    const auto ext = path_extension(filename);
+    bool       ok  = false;
+    if (ext == ".json") ok = load_json_scene(filename, *scene, error);
+    else if (ext == ".ply") ok = load_ply_scene(filename, *scene, error);
+    else if (ext == ".gltf" || ext == ".glb") ok = load_gltf_scene(filename, *scene, error);
+    else if (ext == ".obj") ok = load_obj_scene(filename, *scene, error);
+    else error = "unsupported format " + std::string(filename), ok = false;
+    if (!ok) return ygl_internal_set_error(error.c_str()), YGL_ERR_RUNTIME;
+    make_desc(*scene);
+    *out = scene.release();
+    return YGL_OK;
+  } catch (const std::exception& e) {  // a file that asks for more memory than there is, ...
+    return ygl_internal_set_error((std::string("cannot load ") + filename + ": " + e.what()).c_str()), YGL_ERR_RUNTIME;
+  }
 }
 const ygl_scene_desc* ygl_loaded_scene_desc(const ygl_loaded_scene* scene) { return scene ? &scene->desc : nullptr; }
 const char* ygl_loaded_scene_name(const ygl_loaded_scene* scene, int kind, int index) {
