@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <exception>
 #include <string>
 #include <chrono>
 #include <thread>
@@ -191,7 +192,7 @@ void ygl_trace_params_default(ygl_trace_params* p) {
 }
 
 // ------------------------------------------------------------------------------------------
-int ygl_context_create(int device, ygl_context** out) {
+int ygl_context_create(int device, ygl_context** out) try {
   if (!out) return fail(YGL_ERR_INVALID, "null output");
   int count = 0;
   CUDA_TRY(cudaGetDeviceCount(&count));
@@ -219,6 +220,8 @@ int ygl_context_create(int device, ygl_context** out) {
   CUDA_TRY(cudaMalloc((void**)&ctx->d_trav, 8 * sizeof(unsigned long long)));
   *out = ctx.release();
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_context_create: ") + e.what());
 }
 
 void ygl_comm_destroy(ygl_context* ctx);
@@ -289,7 +292,7 @@ static DCamera to_dcamera(const ygl_camera& c) {
   return d;
 }
 
-int ygl_scene_create(ygl_context* ctx, const ygl_scene_desc* desc, ygl_scene** out) {
+int ygl_scene_create(ygl_context* ctx, const ygl_scene_desc* desc, ygl_scene** out) try {
   if (!ctx || !out) return fail(YGL_ERR_INVALID, "null argument");
   if (int rc = check_desc(desc)) return rc;
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -389,6 +392,8 @@ int ygl_scene_create(ygl_context* ctx, const ygl_scene_desc* desc, ygl_scene** o
   A.host.shrink_to_fit();
   *out = scene.release();
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_scene_create: ") + e.what());
 }
 
 int ygl_scene_update_cameras(ygl_scene* scene, const ygl_camera* cameras, int num_cameras) {
@@ -411,7 +416,7 @@ void ygl_scene_destroy(ygl_scene* scene) {
 }
 
 // ------------------------------------------------------------------------------------------
-int ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
+int ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out) try {
   if (!out) return fail(YGL_ERR_INVALID, "null output");
   if (int rc = check_desc(desc)) return rc;
   auto        bvh = std::make_unique<ygl_bvh>();
@@ -420,8 +425,10 @@ int ygl_bvh_build(const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
   bvh->epoch = g_epoch++;
   *out       = bvh.release();
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_bvh_build: ") + e.what());
 }
-int ygl_bvh_build_device(ygl_context* ctx, const ygl_scene_desc* desc, int highquality, ygl_bvh** out) {
+int ygl_bvh_build_device(ygl_context* ctx, const ygl_scene_desc* desc, int highquality, ygl_bvh** out) try {
   if (!ctx || !out) return fail(YGL_ERR_INVALID, "null argument");
   if (int rc = check_desc(desc)) return rc;
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -432,10 +439,12 @@ int ygl_bvh_build_device(ygl_context* ctx, const ygl_scene_desc* desc, int highq
   bvh->epoch = g_epoch++;
   *out       = bvh.release();
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_bvh_build_device: ") + e.what());
 }
 int ygl_bvh_create_from_host(const ygl_scene_desc* desc, const ygl_bvh_node* top_nodes, int num_top_nodes,
     const int32_t* top_primitives, int num_top_primitives, const ygl_bvh_node* const* shape_nodes,
-    const int* shape_num_nodes, const int32_t* const* shape_primitives, const int* shape_num_primitives, ygl_bvh** out) {
+    const int* shape_num_nodes, const int32_t* const* shape_primitives, const int* shape_num_primitives, ygl_bvh** out) try {
   if (!out) return fail(YGL_ERR_INVALID, "null output");
   if (int rc = check_desc(desc)) return rc;
   if (!top_nodes || num_top_nodes < 1 || (num_top_primitives > 0 && !top_primitives))
@@ -454,9 +463,11 @@ int ygl_bvh_create_from_host(const ygl_scene_desc* desc, const ygl_bvh_node* top
   bvh->epoch = g_epoch++;
   *out       = bvh.release();
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_bvh_create_from_host: ") + e.what());
 }
 int ygl_bvh_update(ygl_bvh* bvh, const ygl_scene_desc* desc, const int* updated_instances, int num_updated_instances,
-    const int* updated_shapes, int num_updated_shapes) {
+    const int* updated_shapes, int num_updated_shapes) try {
   if (!bvh) return fail(YGL_ERR_INVALID, "null bvh");
   if (int rc = check_desc(desc)) return rc;
   if (num_updated_instances < 0 || num_updated_shapes < 0 || (num_updated_shapes > 0 && !updated_shapes))
@@ -474,6 +485,8 @@ int ygl_bvh_update(ygl_bvh* bvh, const ygl_scene_desc* desc, const int* updated_
   }
   bvh->epoch = g_epoch++;
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_bvh_update: ") + e.what());
 }
 static const HostTree* pick_tree(const ygl_bvh* bvh, int shape) {
   if (shape < 0) return &bvh->host.top;
@@ -547,7 +560,7 @@ static int bvh_upload(const ygl_bvh* bvh, int device) {
 }
 
 // ------------------------------------------------------------------------------------------
-int ygl_lights_create(const ygl_scene_desc* desc, ygl_lights** out) {
+int ygl_lights_create(const ygl_scene_desc* desc, ygl_lights** out) try {
   if (!out) return fail(YGL_ERR_INVALID, "null output");
   if (int rc = check_desc(desc)) return rc;
   auto lights = std::make_unique<ygl_lights>();
@@ -555,6 +568,8 @@ int ygl_lights_create(const ygl_scene_desc* desc, ygl_lights** out) {
   lights->epoch = g_epoch++;
   *out          = lights.release();
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_lights_create: ") + e.what());
 }
 int ygl_lights_count(const ygl_lights* lights) { return lights ? (int)lights->host.size() : 0; }
 int ygl_lights_get(const ygl_lights* lights, int i, int* instance, int* environment, int* cdf_size, float* cdf) {
@@ -684,7 +699,7 @@ static int bind_scene(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
 
 // ------------------------------------------------------------------------------------------
 int ygl_make_state_rngs(const ygl_scene_desc* desc, const ygl_trace_params* params, int* width, int* height,
-    uint64_t* rngs) {
+    uint64_t* rngs) try {
   if (!desc || !params) return fail(YGL_ERR_INVALID, "null argument");
   int         w, h;
   std::string error;
@@ -693,6 +708,8 @@ int ygl_make_state_rngs(const ygl_scene_desc* desc, const ygl_trace_params* para
   if (height) *height = h;
   if (rngs) state_rngs(*params, w, h, rngs);
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_make_state_rngs: ") + e.what());
 }
 
 // Rows row_begin, row_begin + row_step, ... below row_end of the full image.
@@ -810,7 +827,7 @@ int ygl_state_layout(const ygl_state* state, int* row_first, int* row_step, int*
   return YGL_OK;
 }
 
-int ygl_state_download(ygl_state* state, float* image, float* albedo, float* normal, int32_t* hits, uint64_t* rngs) {
+int ygl_state_download(ygl_state* state, float* image, float* albedo, float* normal, int32_t* hits, uint64_t* rngs) try {
   if (!state) return fail(YGL_ERR_INVALID, "null state");
   CUDA_TRY(cudaSetDevice(state->ctx->device));
   cudaStream_t s = state->ctx->stream;
@@ -822,10 +839,12 @@ int ygl_state_download(ygl_state* state, float* image, float* albedo, float* nor
   if (rngs) CUDA_TRY(cudaMemcpyAsync(rngs, state->st.rngs, n * 16, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_state_download: ") + e.what());
 }
 
 int ygl_state_upload(ygl_state* state, int samples, const float* image, const float* albedo, const float* normal,
-    const int32_t* hits, const uint64_t* rngs) {
+    const int32_t* hits, const uint64_t* rngs) try {
   if (!state) return fail(YGL_ERR_INVALID, "null state");
   CUDA_TRY(cudaSetDevice(state->ctx->device));
   cudaStream_t s = state->ctx->stream;
@@ -838,6 +857,8 @@ int ygl_state_upload(ygl_state* state, int samples, const float* image, const fl
   CUDA_TRY(cudaStreamSynchronize(s));
   state->samples = samples;
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_state_upload: ") + e.what());
 }
 
 int ygl_state_reset(ygl_state* state, const ygl_trace_params* params) {
@@ -1149,7 +1170,7 @@ static int check_sampler(const ygl_trace_params& p) {
 }
 
 int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
-    const ygl_lights* lights, const ygl_trace_params* params) {
+    const ygl_lights* lights, const ygl_trace_params* params) try {
   if (!ctx || !state || !params) return fail(YGL_ERR_INVALID, "null argument");
   if (state->ctx != ctx) return fail(YGL_ERR_INVALID, "state belongs to another context");
   if (int rc = check_sampler(*params)) return rc;
@@ -1161,10 +1182,12 @@ int ygl_trace_samples(ygl_context* ctx, ygl_state* state, const ygl_scene* scene
   memset(ctx->stats, 0, sizeof(ctx->stats));
   memset(ctx->timings, 0, sizeof(ctx->timings));
   return run_render(ctx, state, *params, params->batch);
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_trace_samples: ") + e.what());
 }
 
 int ygl_trace_sample(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
-    const ygl_lights* lights, int i, int j, int sample, const ygl_trace_params* params) {
+    const ygl_lights* lights, int i, int j, int sample, const ygl_trace_params* params) try {
   if (!ctx || !state || !params) return fail(YGL_ERR_INVALID, "null argument");
   if (state->ctx != ctx) return fail(YGL_ERR_INVALID, "state belongs to another context");
   if (int rc = check_sampler(*params)) return rc;
@@ -1180,11 +1203,13 @@ int ygl_trace_sample(ygl_context* ctx, ygl_state* state, const ygl_scene* scene,
   memset(ctx->stats, 0, sizeof(ctx->stats));
   memset(ctx->timings, 0, sizeof(ctx->timings));
   return run_wavefront(ctx, state, *params, 1, lane, sample);
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_trace_sample: ") + e.what());
 }
 
 // ---- progressive rendering: trace_start / trace_cancel / trace_done / trace_preview (yocto_trace.cpp:1627-1676) ----
 int ygl_trace_start(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, const ygl_bvh* bvh,
-    const ygl_lights* lights, const ygl_trace_params* params) {
+    const ygl_lights* lights, const ygl_trace_params* params) try {
   if (!ctx || !state || !params) return fail(YGL_ERR_INVALID, "null argument");
   if (state->ctx != ctx) return fail(YGL_ERR_INVALID, "state belongs to another context");
   if (ctx->worker.joinable()) {
@@ -1205,12 +1230,19 @@ int ygl_trace_start(ygl_context* ctx, ygl_state* state, const ygl_scene* scene, 
   const ygl_trace_params p = *params;
   ctx->worker = std::thread([ctx, state, p]() {
     // like the reference's worker (yocto_trace.cpp:1633-1648): one batch, abandoned early when stop is raised
-    int rc = cudaSetDevice(ctx->device) == cudaSuccess ? run_render(ctx, state, p, p.batch) : fail(YGL_ERR_CUDA, "cudaSetDevice");
+    int rc;
+    try {
+      rc = cudaSetDevice(ctx->device) == cudaSuccess ? run_render(ctx, state, p, p.batch) : fail(YGL_ERR_CUDA, "cudaSetDevice");
+    } catch (const std::exception& e) {
+      rc = fail(YGL_ERR_RUNTIME, std::string("ygl_trace_start: ") + e.what());
+    }
     ctx->worker_rc = rc;
     if (rc) ctx->worker_error = g_error;  // g_error is per thread: hand the message to the caller's thread
     if (!ctx->stop.load() && rc == YGL_OK) ctx->done = 1;
   });
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_trace_start: ") + e.what());
 }
 static int worker_join(ygl_context* ctx) {
   if (ctx->worker.joinable()) ctx->worker.join();
@@ -1231,7 +1263,7 @@ int ygl_trace_wait(ygl_context* ctx) {
 int ygl_trace_done(ygl_context* ctx) { return ctx && ctx->done.load() ? 1 : 0; }
 
 int ygl_trace_preview(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_lights* lights,
-    const ygl_trace_params* params, int width, int height, float* image) {
+    const ygl_trace_params* params, int width, int height, float* image) try {
   if (!ctx || !scene || !params || !image) return fail(YGL_ERR_INVALID, "null argument");
   if (ctx->worker.joinable() && !ctx->done.load()) return fail(YGL_ERR_INVALID, "a batch is running: cancel or wait first");
   if (params->camera < 0 || params->camera >= scene->num_cameras) return fail(YGL_ERR_INVALID, "camera id out of range");
@@ -1261,6 +1293,8 @@ int ygl_trace_preview(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* b
       memcpy(image + ((size_t)j * width + i) * 4, preview.data() + ((size_t)pj * pw + pi) * 4, 16);
     }
   return YGL_OK;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_trace_preview: ") + e.what());
 }
 
 int ygl_trace_counters(ygl_context* ctx, uint64_t counters[16]) {
@@ -1316,7 +1350,7 @@ int ygl_trace_timings(ygl_context* ctx, double ms[4]) {
 }
 
 int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trace_params* params, int* width,
-    int* height, float* image) {
+    int* height, float* image) try {
   if (!ctx || !desc || !params) return fail(YGL_ERR_INVALID, "null argument");
   int         w, h;
   std::string error;
@@ -1354,6 +1388,8 @@ int ygl_trace_image(ygl_context* ctx, const ygl_scene_desc* desc, const ygl_trac
   ygl_bvh_destroy(bvh);
   g_error = keep;
   return rc;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_trace_image: ") + e.what());
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1373,7 +1409,7 @@ int ygl_intersect_rays_device(ygl_context* ctx, const ygl_scene* scene, const yg
 }
 
 int ygl_intersect_rays(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* bvh, const ygl_ray* rays, int64_t n,
-    int instance, int find_any, ygl_intersection* out) {
+    int instance, int find_any, ygl_intersection* out) try {
   if (!ctx || !rays || !out) return fail(YGL_ERR_INVALID, "null argument");
   if (n <= 0) return YGL_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1401,6 +1437,8 @@ int ygl_intersect_rays(ygl_context* ctx, const ygl_scene* scene, const ygl_bvh* 
   cudaFree(d_rays);
   cudaFree(d_out);
   return rc;
+} catch (const std::exception& e) {
+  return fail(YGL_ERR_RUNTIME, std::string("ygl_intersect_rays: ") + e.what());
 }
 
 // Test hook: evaluates the device libm function `fn` (0 sin, 1 cos, 2 exp, 3 log, 4 atan, 5 acos,
