@@ -1032,42 +1032,38 @@ inline void piz_unlift(bool narrow, uint16_t l, uint16_t h, uint16_t& a, uint16_
     a = (uint16_t)(((int)h + bb - 0x8000) & 0xffff), b = (uint16_t)bb;
   }
 }
-void piz_wavelet_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t max_value) {
+// Inverse 2-D Haar transform of an nx x ny grid of words (`sx`, `sy`: distance between neighbours in x and in y), in
+// place, from the coarsest level down. At the level with step `half`, the word at a grid point (x, y) with x, y
+// multiples of 2 * half is an average and its neighbours at +half are differences: first the two vertical pairs of a
+// 2 x 2 cell are undone, then the two horizontal ones; a last odd column or row has only its one pair.
+void piz_wavelet_decode(uint16_t* words, int nx, int sx, int ny, int sy, uint16_t max_value) {
   const bool narrow = max_value < (1 << 14);
-  const int  n      = nx > ny ? ny : nx;
-  int        p      = 1;
-  while (p <= n) p <<= 1;
-  p >>= 1;
-  int p2 = p;
-  p >>= 1;
-  for (; p >= 1; p2 = p, p >>= 1) {  // from the coarsest level down
-    uint16_t*       py  = in;
-    uint16_t* const ey  = in + (ptrdiff_t)oy * (ny - p2);
-    const ptrdiff_t oy1 = (ptrdiff_t)oy * p, oy2 = (ptrdiff_t)oy * p2, ox1 = (ptrdiff_t)ox * p, ox2 = (ptrdiff_t)ox * p2;
-    uint16_t        i00, i01, i10, i11;
-    for (; py <= ey; py += oy2) {
-      uint16_t*       px = py;
-      uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
-      for (; px <= ex; px += ox2) {  // a 2 x 2 cell
-        uint16_t *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
-        piz_unlift(narrow, *px, *p10, i00, i10);
-        piz_unlift(narrow, *p01, *p11, i01, i11);
-        piz_unlift(narrow, i00, i01, *px, *p01);
-        piz_unlift(narrow, i10, i11, *p10, *p11);
+  auto at = [&](int x, int y) -> uint16_t& { return words[(ptrdiff_t)x * sx + (ptrdiff_t)y * sy]; };
+  int  step = 1;
+  while (step <= std::min(nx, ny)) step <<= 1;
+  step >>= 1;  // the largest power of two that still fits the smaller side: cell size of the coarsest level
+  for (int half = step >> 1; half >= 1; step = half, half >>= 1) {
+    int y = 0;
+    for (; y + step <= ny; y += step) {
+      int x = 0;
+      for (; x + step <= nx; x += step) {
+        uint16_t top_left, bottom_left, top_right, bottom_right;
+        piz_unlift(narrow, at(x, y), at(x, y + half), top_left, bottom_left);
+        piz_unlift(narrow, at(x + half, y), at(x + half, y + half), top_right, bottom_right);
+        piz_unlift(narrow, top_left, top_right, at(x, y), at(x + half, y));
+        piz_unlift(narrow, bottom_left, bottom_right, at(x, y + half), at(x + half, y + half));
       }
-      if (nx & p) {  // an odd column
-        uint16_t* p10 = px + oy1;
-        piz_unlift(narrow, *px, *p10, i00, *p10);
-        *px = i00;
+      if (nx & half) {  // a column without a right-hand partner
+        uint16_t top, bottom;
+        piz_unlift(narrow, at(x, y), at(x, y + half), top, bottom);
+        at(x, y) = top, at(x, y + half) = bottom;
       }
     }
-    if (ny & p) {  // an odd line
-      uint16_t*       px = py;
-      uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
-      for (; px <= ex; px += ox2) {
-        uint16_t* p01 = px + ox1;
-        piz_unlift(narrow, *px, *p01, i00, *p01);
-        *px = i00;
+    if (ny & half) {  // a row without a partner below
+      for (int x = 0; x + step <= nx; x += step) {
+        uint16_t left, right;
+        piz_unlift(narrow, at(x, y), at(x + half, y), left, right);
+        at(x, y) = left, at(x + half, y) = right;
       }
     }
   }
