@@ -336,11 +336,11 @@ class JpegDecoder {
 
  private:
   static constexpr int kNoMarker = 0xff;
-  struct Huffman {
-    uint8_t  size[257], values[256];
-    uint16_t code[256];
-    unsigned maxcode[18];
-    int      delta[17];
+  struct Huffman {  // a table no DHT segment has filled decodes nothing: every lookup runs off its end
+    uint8_t  size[257] = {}, values[256] = {};
+    uint16_t code[256] = {};
+    unsigned maxcode[18] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0xffffffffu};
+    int      delta[17] = {};
     bool build(const int* count) {  // canonical codes in symbol order
       int k = 0;
       for (int i = 0; i < 16; i++)

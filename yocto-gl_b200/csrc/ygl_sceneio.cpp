@@ -2209,9 +2209,13 @@ bool load_gltf_scene(const std::string& filename, ygl_loaded_scene& scene, std::
     auto v = parent.find(key);
     return v && v->type == JValue::Array ? v->array : none;
   };
+  bool sizes_ok = true;  // an offset / length / count / index that is negative or absurd makes the file invalid
   auto number_at = [&](const JValue& e, const char* key, double fallback) {
     auto v = e.find(key);
-    return v && v->type == JValue::Number ? (double)gltf_int(*v) : fallback;
+    if (!v || v->type != JValue::Number) return fallback;
+    const double value = (double)gltf_int(*v);
+    if (!(value >= -1 && value < 1e12)) sizes_ok = false;
+    return value < 0 ? -1.0 : value;
   };
   auto float_at = [&](const JValue& e, const char* key, float fallback) {
     auto v = e.find(key);
@@ -2236,7 +2240,9 @@ bool load_gltf_scene(const std::string& filename, ygl_loaded_scene& scene, std::
   std::vector<const uint8_t*>       buffer_data(jbuffers.size(), nullptr);
   std::vector<size_t>               buffer_size(jbuffers.size(), 0);
   for (size_t i = 0; i < jbuffers.size(); i++) {
-    const size_t size = (size_t)number_at(jbuffers[i], "byteLength", 0);
+    const double declared = number_at(jbuffers[i], "byteLength", 0);
+    if (declared < 0) return buffers_error();
+    const size_t size = (size_t)declared;
     auto         uri  = string_at(jbuffers[i], "uri");
     if (i == 0 && !uri && bin) {
       if (bin_size < size) return buffers_error();
@@ -2260,15 +2266,24 @@ bool load_gltf_scene(const std::string& filename, ygl_loaded_scene& scene, std::
   for (auto& jv : array_of(json, "bufferViews")) {
     GltfView view;
     view.buffer = (int)number_at(jv, "buffer", -1);
-    view.offset = (size_t)number_at(jv, "byteOffset", 0), view.size = (size_t)number_at(jv, "byteLength", 0);
-    view.stride = (size_t)number_at(jv, "byteStride", 0);
+    auto size_of = [&](const char* key) {
+      const double v = number_at(jv, key, 0);
+      if (v < 0) sizes_ok = false;
+      return v < 0 ? (size_t)0 : (size_t)v;
+    };
+    view.offset = size_of("byteOffset"), view.size = size_of("byteLength"), view.stride = size_of("byteStride");
     views.push_back(view);
   }
   std::vector<GltfAccessor> accessors;
   for (auto& ja : array_of(json, "accessors")) {
     GltfAccessor a;
     a.view   = (int)number_at(ja, "bufferView", -1);
-    a.offset = (size_t)number_at(ja, "byteOffset", 0), a.count = (size_t)number_at(ja, "count", 0);
+    auto size_of = [&](const char* key) {
+      const double v = number_at(ja, key, 0);
+      if (v < 0) sizes_ok = false;
+      return v < 0 ? (size_t)0 : (size_t)v;
+    };
+    a.offset = size_of("byteOffset"), a.count = size_of("count");
     const int ctype = (int)number_at(ja, "componentType", 0);
     a.component     = ctype;  // 5120 i8, 5121 u8, 5122 i16, 5123 u16, 5125 u32, 5126 f32
     if (auto n = ja.find("normalized")) a.normalized = n->type == JValue::Bool && n->boolean;
@@ -2282,6 +2297,7 @@ bool load_gltf_scene(const std::string& filename, ygl_loaded_scene& scene, std::
     if (a.stride == 0) a.stride = csize * a.components;  // (matrix alignment rules only matter for matrices, refused below)
     accessors.push_back(a);
   }
+  if (!sizes_ok) return parse_error();
   // one element of an accessor, bounds-checked; nullptr = the accessor has no data (reads as zeros, like cgltf)
   auto component_size = [](int ctype) { return ctype == 5120 || ctype == 5121 ? 1 : ctype == 5122 || ctype == 5123 ? 2 : ctype == 5125 || ctype == 5126 ? 4 : 0; };
   auto element_at = [&](const GltfAccessor& a, size_t index, const uint8_t*& ptr) {
