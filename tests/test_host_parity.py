@@ -176,3 +176,25 @@ def test_reference_side_shim_compiles(tmp_path):
     obj = tmp_path / "use_shim.o"
     subprocess.run(["g++", "-std=c++17", "-include", "cstdint", "-I", ref_root, "-I", ROOT, "-c", str(src), "-o",
                     str(obj)], check=True)
+
+
+def test_c_example_compiles_as_c99_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/ygl_b200.h is a C header: yocto-gl_b200/host/example_render.c (scene file -> render -> tonemap -> PPM through
+    the C ABI) must compile as C99 and link against the library. Without a CUDA device it has to stop at
+    ygl_context_create with the library's error - there is no CPU path to fall back to."""
+    import subprocess
+    import scene_data
+    exe = tmp_path / "example_render"
+    lib_dir = os.path.join(ROOT, "yocto-gl_b200", "lib")
+    build = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "yocto-gl_b200", "host", "example_render.c"), "-o", str(exe), "-L", lib_dir,
+                            "-l:libygl_b200.so", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    if not scene_data.available():
+        pytest.skip("oracle/_ref/data not present")
+    run = subprocess.run([str(exe), scene_data.pool("shapes", "bunny.ply"), str(tmp_path / "out.ppm"), "32", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert "1 shapes, 1 instances" in run.stdout
+    if run.returncode != 0:     # no GPU here
+        assert run.returncode == 2 and "ygl_context_create" in run.stderr and "CUDA" in run.stderr, run.stderr
+        assert not (tmp_path / "out.ppm").exists()
